@@ -1,0 +1,414 @@
+"""ORACLE — test infrastructure only (never imported by the product path).
+
+CPU restatement (torch-CPU used purely as a math library, fp64 by default) of the
+training / inference hot path of vliu15/3d-brain-tumor-segmentation.  Every function
+cites the reference file:line it follows (paths relative to /root/reference).
+
+Parity status: the reference's real runtime (tensorflow==2.0.0-alpha0, requirements.txt:2)
+cannot be installed here, and the reference ships no tests or golden vectors.  The
+restatement is therefore pinned in two ways instead:
+  1. `oracle/run_reference.py` executes the reference's OWN python files (model.py,
+     layers/*.py, util.py) on top of `oracle/tf_shim` (a tiny torch-backed stand-in for
+     the handful of TF/Keras symbols they use) and `tests/test_oracle_vs_reference.py`
+     checks this file against it -> first-party math (GroupNormalization.call, block /
+     encoder / decoder / VAE wiring, losses) is pinned on the reference's own code;
+  2. third-party TF op semantics (SAME padding, Conv3DTranspose, Adam) are restated
+     from their published definitions => "parity unpinned" for those.
+
+All tensors are channels_last  [B, D, H, W, C];  weights are in Keras layouts:
+  Conv3D kernel (kd,kh,kw,Cin,Cout); Conv3DTranspose kernel (kd,kh,kw,Cout,Cin);
+  Dense kernel (in,out).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Params = Dict[str, torch.Tensor]
+
+
+# ----------------------------------------------------------------------------------
+# TF/Keras built-in semantics (third-party; restated from SURVEY.md App. B)
+# ----------------------------------------------------------------------------------
+def _same_pads(n: int, k: int, s: int) -> Tuple[int, int]:
+    """TF 'SAME' padding rule: out=ceil(n/s); total=max((out-1)*s+k-n,0); before=total//2."""
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    before = total // 2
+    return before, total - before
+
+
+def conv3d_same(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1) -> torch.Tensor:
+    """tf.keras.layers.Conv3D(padding='same') on NDHWC input (call sites resnet.py:80-87,
+    downsample.py:28-35, decoder.py:55-63, vae.py:92-99).  Cross-correlation, no flip."""
+    k = w.shape[0]
+    xc = x.permute(0, 4, 1, 2, 3)
+    pads = []
+    for n in reversed(xc.shape[2:]):  # F.pad wants last dim first
+        pb, pa = _same_pads(n, k, stride)
+        pads += [pb, pa]
+    xc = F.pad(xc, pads)
+    wc = w.permute(4, 3, 0, 1, 2)
+    y = F.conv3d(xc, wc, b, stride=stride)
+    return y.permute(0, 2, 3, 4, 1)
+
+
+def conv3d_transpose_same(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    """tf.keras.layers.Conv3DTranspose(kernel 3, strides 2, padding 'same') (upsample.py:28-33):
+    the exact adjoint (conv3d_backprop_input) of the SAME/stride-2 conv with filter
+    (kd,kh,kw,Cout,Cin); output spatial = 2*in."""
+    xc = x.permute(0, 4, 1, 2, 3)
+    wc = w.permute(4, 3, 0, 1, 2)  # (Cin, Cout, kd,kh,kw) as conv_transpose3d expects
+    y = F.conv_transpose3d(xc, wc, None, stride=2, padding=0)
+    d, h, ww = x.shape[1:4]
+    y = y[:, :, : 2 * d, : 2 * h, : 2 * ww]
+    if b is not None:
+        y = y + b.view(1, -1, 1, 1, 1)
+    return y.permute(0, 2, 3, 4, 1)
+
+
+def dense(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    y = x @ w
+    return y if b is None else y + b
+
+
+# ----------------------------------------------------------------------------------
+# layers/group_norm.py:83-124
+# ----------------------------------------------------------------------------------
+def group_norm(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
+               groups: int = 8, eps: float = 1e-5, axis: int = -1) -> torch.Tensor:
+    """Literal restatement of GroupNormalization.call: raw reshape of [B,...,C] to
+    [B,G,...,C/G] (no transpose, group_norm.py:84-100), moments over axes 2.. (:105),
+    division by sqrt(var+eps) (:107), gamma/beta reshaped to broadcast_shape (:114-122)."""
+    shape = list(x.shape)
+    nd = len(shape)
+    ax = axis % nd
+    broadcast_shape = [1] * nd
+    broadcast_shape[ax] = shape[ax] // groups
+    broadcast_shape.insert(1, groups)
+    group_axes = list(shape)
+    group_axes[ax] = shape[ax] // groups
+    group_axes.insert(1, groups)
+    g = x.reshape([group_axes[0], groups] + group_axes[2:])
+    red = tuple(range(2, len(group_axes)))
+    mean = g.mean(dim=red, keepdim=True)
+    var = ((g - mean) ** 2).mean(dim=red, keepdim=True)
+    g = (g - mean) / torch.sqrt(var + eps)
+    if gamma is not None:
+        g = g * gamma.reshape(broadcast_shape)
+    if beta is not None:
+        g = g + beta.reshape(broadcast_shape)
+    return g.reshape(shape)
+
+
+def group_norm_chunk(x, gamma, beta, groups=8, eps=1e-5):
+    """Independent second derivation of the channels_last behaviour: group g is the
+    g-th contiguous 1/G chunk of each sample's flat buffer; affine index j = g*(C/G) + c % (C/G).
+    Used only to cross-check group_norm() above."""
+    B = x.shape[0]
+    C = x.shape[-1]
+    cg = C // groups
+    flat = x.reshape(B, groups, -1)
+    mean = flat.mean(dim=2, keepdim=True)
+    var = ((flat - mean) ** 2).mean(dim=2, keepdim=True)
+    xh = ((flat - mean) / torch.sqrt(var + eps))
+    n = flat.shape[2]
+    c = torch.arange(n) % C  # chunk length is a multiple of C/G but maybe not of C
+    # element e of chunk g sits at flat offset g*n+e -> channel (g*n+e) % C
+    offs = (torch.arange(groups).view(-1, 1) * n + torch.arange(n).view(1, -1)) % C
+    j = torch.arange(groups).view(-1, 1) * cg + offs % cg
+    out = xh * gamma[j].unsqueeze(0) + beta[j].unsqueeze(0)
+    return out.reshape(x.shape)
+
+
+# ----------------------------------------------------------------------------------
+# layers/resnet.py:116-138
+# ----------------------------------------------------------------------------------
+def resnet_block(p: Params, pre: str, x: torch.Tensor, groups: int = 8) -> torch.Tensor:
+    res = conv3d_same(x, p[pre + "ptwise.kernel"], p[pre + "ptwise.bias"])            # :118
+    chse = res.mean(dim=(1, 2, 3))                                                     # :121
+    chse = torch.relu(dense(chse, p[pre + "dense_relu.kernel"], None))                 # :122
+    chse = torch.sigmoid(dense(chse, p[pre + "dense_sigmoid.kernel"], None))           # :123
+    chse = chse.reshape(chse.shape[0], 1, 1, 1, -1)                                    # :124
+    spse = torch.sigmoid(conv3d_same(res, p[pre + "spatial.kernel"], None))            # :127
+    res = res * (spse + chse)                                                          # :130
+    h = x
+    for i in (1, 2):                                                                   # :133-136
+        h = conv3d_same(h, p[pre + f"conv{i}.kernel"], p[pre + f"conv{i}.bias"])
+        h = group_norm(h, p[pre + f"gn{i}.gamma"], p[pre + f"gn{i}.beta"], groups)
+        h = torch.relu(h)
+    return res + h                                                                     # :137
+
+
+def conv_downsample(p: Params, pre: str, x, groups=8):
+    """layers/downsample.py:41-45"""
+    x = conv3d_same(x, p[pre + "conv.kernel"], p[pre + "conv.bias"], stride=2)
+    x = group_norm(x, p[pre + "norm.gamma"], p[pre + "norm.beta"], groups)
+    return torch.relu(x)
+
+
+def conv_upsample(p: Params, pre: str, x, groups=8):
+    """layers/upsample.py:39-43"""
+    x = conv3d_transpose_same(x, p[pre + "conv.kernel"], p[pre + "conv.bias"])
+    x = group_norm(x, p[pre + "norm.gamma"], p[pre + "norm.beta"], groups)
+    return torch.relu(x)
+
+
+# ----------------------------------------------------------------------------------
+# layers/encoder.py:69-101, layers/decoder.py:65-83, layers/vae.py:114-143, model.py:58-71
+# ----------------------------------------------------------------------------------
+def encoder(p: Params, x, depth=4, groups=8, dropout_mask=None, dropout=0.2):
+    if dropout_mask is not None:                       # encoder.py:71 (training only)
+        x = x * dropout_mask / (1.0 - dropout)
+    residuals = []
+    for i in range(depth):
+        cache: List[torch.Tensor] = []
+        for j in range(i + 1):
+            if j > 0:
+                x = torch.cat([x] + cache, dim=-1)     # :85  (x is cache[-1]: duplicated, F3)
+            x = resnet_block(p, f"enc.L{i}.B{j}.", x, groups)
+            cache.append(x)
+        if i > 0:
+            x = torch.cat(cache, dim=-1)               # :91
+        residuals.append(x)
+        if i < depth - 1:
+            x = conv_downsample(p, f"enc.L{i}.down.", x, groups)   # :98
+    return residuals
+
+
+def decoder(p: Params, x, residuals, depth=4, groups=8):
+    for i, residual in zip(range(depth - 2, -1, -1), residuals[::-1]):
+        x = conv_upsample(p, f"dec.L{i}.up.", x, groups)           # :72
+        x = torch.cat([residual, x], dim=-1)                       # :75
+        x = resnet_block(p, f"dec.L{i}.block.", x, groups)         # :78
+    x = conv3d_same(x, p["dec.out.kernel"], p["dec.out.bias"])     # :81
+    return torch.sigmoid(x)
+
+
+def vae(p: Params, x, eps, depth=4, groups=8):
+    """eps ~ N(0,1) of shape [B, latent] is injected (vae.py:9-13 draws it internally)."""
+    x = conv_downsample(p, "vae.down.", x, groups)                 # :116
+    B = x.shape[0]
+    x = x.reshape(B, -1)                                           # :119 Flatten (channels_last)
+    x = dense(x, p["vae.proj.kernel"], p["vae.proj.bias"])         # :120
+    latent = x.shape[1] // 2
+    z_mean, z_logvar = x[:, :latent], x[:, latent:]                # :123-124
+    z = z_mean + torch.exp(0.5 * z_logvar) * eps                   # :13
+    x = torch.relu(dense(z, p["vae.unproj.kernel"], p["vae.unproj.bias"]))   # :128
+    return x, z_mean, z_logvar
+
+
+def vae_full(p: Params, bott, eps, depth=4, groups=8):
+    d, h, w = bott.shape[1:4]
+    x, z_mean, z_logvar = vae(p, bott, eps, depth, groups)
+    x = x.reshape(x.shape[0], d // 2, h // 2, w // 2, 1)           # :129, :109-111
+    x = conv_upsample(p, "vae.up.", x, groups)                     # :132
+    for i in range(depth - 2, -1, -1):                             # :135-138
+        x = conv_upsample(p, f"vae.L{i}.up.", x, groups)
+        x = resnet_block(p, f"vae.L{i}.block.", x, groups)
+    x = conv3d_same(x, p["vae.out.kernel"], p["vae.out.bias"])     # :141
+    return x, z_mean, z_logvar
+
+
+def model_forward(p: Params, x, eps=None, depth=4, groups=8, inference=False,
+                  dropout_mask=None, dropout=0.2):
+    """model.py:58-71"""
+    res = encoder(p, x, depth, groups, dropout_mask, dropout)
+    y_pred = decoder(p, res[-1], res[:-1], depth, groups)
+    if inference:
+        return y_pred, None, None, None
+    y_vae, z_mean, z_logvar = vae_full(p, res[-1], eps, depth, groups)
+    return y_pred, y_vae, z_mean, z_logvar
+
+
+# ----------------------------------------------------------------------------------
+# util.py:5-57, train.py:145-146
+# ----------------------------------------------------------------------------------
+def dice_vae_loss(x, y, y_pred, y_vae, z_mean, z_logvar):
+    """util.py:13-24 (channels_last: dice axes (0,1,2,3))."""
+    l2 = ((x - y_vae) ** 2).mean()
+    kld = (z_mean ** 2 + torch.exp(z_logvar) - z_logvar - 1.0).mean()
+    ax = (0, 1, 2, 3)
+    inter = (y_pred * y).sum(dim=ax)
+    pred = (y_pred ** 2).sum(dim=ax)
+    true = (y ** 2).sum(dim=ax)
+    dice = (1.0 - (2.0 * inter + 1.0) / (pred + true + 1.0)).mean()
+    return dice + 0.1 * l2 + 0.1 * kld
+
+
+def dice_coefficient(y_true, y_pred):
+    """util.py:35-57 (channels_last).  NB the macro average reduces axes (0,1,2) only, so the
+    ratio is [W, C]-shaped before the mean — kept, it is the reference's number."""
+    mask = (y_pred.max(dim=-1, keepdim=True).values > 0.5).to(y_pred.dtype)
+    C = y_pred.shape[-1]
+    hard = F.one_hot(y_pred.argmax(dim=-1), C).to(y_pred.dtype) * mask
+    inter = (hard * y_true).sum(dim=(0, 1, 2))
+    pred = hard.sum(dim=(0, 1, 2))
+    true = y_true.sum(dim=(0, 1, 2))
+    macro = ((2.0 * inter + 1.0) / (pred + true + 1.0)).mean()
+    micro = (hard * y_true).sum() / (hard.sum() + y_true.sum())
+    return macro, micro
+
+
+def l2_regularized_names(p: Params) -> List[str]:
+    """Names of tensors carrying an L2 regulariser in the reference:
+    all Conv3D/Dense kernels except ConvUpsample's Conv3DTranspose (upsample.py:28-33 has none);
+    GN gamma/beta only inside ResnetBlocks (resnet.py:93-94,109-110); no biases."""
+    names = []
+    for k in p:
+        if k.endswith(".kernel") or k in ("dec.out.kernel", "vae.out.kernel"):
+            if ".up.conv." in k:
+                continue
+            names.append(k)
+        elif (".gn1." in k or ".gn2." in k):
+            names.append(k)
+    return names
+
+
+def l2_reg(p: Params, l2_scale=1e-5):
+    """train.py:146: tf.reduce_sum(model.losses) with tf.keras.regularizers.l2(l) = l*sum(w^2)."""
+    tot = 0.0
+    for k in l2_regularized_names(p):
+        tot = tot + l2_scale * (p[k] ** 2).sum()
+    return tot
+
+
+def adam_step_tf(theta, m, v, g, t: int, lr: float, b1=0.9, b2=0.999, eps=1e-7):
+    """tf.keras.optimizers.Adam dense update (util.py:60-78), t = iterations+1."""
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    alpha = lr * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+    theta.sub_(alpha * m / (torch.sqrt(v) + eps))
+
+
+def poly_lr(epoch: int, init_lr=1e-4, n_epochs=300.0):
+    """util.py:82-84"""
+    return init_lr * ((1.0 - epoch / n_epochs) ** 0.9)
+
+
+def pad_to_spatial_res(res: int, x):
+    """test.py:164-178 — trailing zero pad; adds a full `res` when already aligned (App. C)."""
+    shape = x.shape[:-1]
+    pad = [res - (s % res) for s in shape]
+    out = torch.zeros([s + q for s, q in zip(shape, pad)] + [x.shape[-1]], dtype=x.dtype)
+    out[: shape[0], : shape[1], : shape[2]] = x
+    return out, list(shape)
+
+
+# ----------------------------------------------------------------------------------
+# Deterministic synthetic weights / inputs
+# ----------------------------------------------------------------------------------
+def param_shapes(in_ch=2, out_ch=3, base_filters=16, depth=4, reduction=2, crop=(128, 128, 128),
+                 with_vae=True) -> Dict[str, Tuple[int, ...]]:
+    """Shapes of all trainable tensors in Keras layouts, keyed by this repo's names."""
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def block(pre, cin, f):
+        s[pre + "ptwise.kernel"] = (1, 1, 1, cin, f)
+        s[pre + "ptwise.bias"] = (f,)
+        s[pre + "dense_relu.kernel"] = (f, f // reduction)
+        s[pre + "dense_sigmoid.kernel"] = (f // reduction, f)
+        s[pre + "spatial.kernel"] = (1, 1, 1, f, 1)
+        s[pre + "conv1.kernel"] = (3, 3, 3, cin, f)
+        s[pre + "conv1.bias"] = (f,)
+        s[pre + "gn1.gamma"] = (f,)
+        s[pre + "gn1.beta"] = (f,)
+        s[pre + "conv2.kernel"] = (3, 3, 3, f, f)
+        s[pre + "conv2.bias"] = (f,)
+        s[pre + "gn2.gamma"] = (f,)
+        s[pre + "gn2.beta"] = (f,)
+
+    def down(pre, cin, f):
+        s[pre + "conv.kernel"] = (3, 3, 3, cin, f)
+        s[pre + "conv.bias"] = (f,)
+        s[pre + "norm.gamma"] = (f,)
+        s[pre + "norm.beta"] = (f,)
+
+    def up(pre, cin, f):
+        s[pre + "conv.kernel"] = (3, 3, 3, f, cin)
+        s[pre + "conv.bias"] = (f,)
+        s[pre + "norm.gamma"] = (f,)
+        s[pre + "norm.beta"] = (f,)
+
+    cin = in_ch
+    for i in range(depth):
+        f = base_filters * 2 ** i
+        for j in range(i + 1):
+            block(f"enc.L{i}.B{j}.", cin if j == 0 else (j + 1) * f, f)
+        cin = f if i == 0 else (i + 1) * f
+        if i < depth - 1:
+            down(f"enc.L{i}.down.", cin, f)
+            cin = f
+    bott = cin
+    res_ch = [base_filters if i == 0 else (i + 1) * base_filters * 2 ** i for i in range(depth)]
+    c = bott
+    for i in range(depth - 2, -1, -1):
+        f = base_filters * 2 ** i
+        up(f"dec.L{i}.up.", c, f)
+        block(f"dec.L{i}.block.", res_ch[i] + f, f)
+        c = f
+    s["dec.out.kernel"] = (1, 1, 1, c, out_ch)
+    s["dec.out.bias"] = (out_ch,)
+    if with_vae:
+        d, h, w = [n // 2 ** (depth - 1) for n in crop]
+        f = base_filters // 2
+        down("vae.down.", bott, f)
+        flat = (d // 2) * (h // 2) * (w // 2) * f
+        s["vae.proj.kernel"] = (flat, base_filters * 2 ** (depth - 1))
+        s["vae.proj.bias"] = (base_filters * 2 ** (depth - 1),)
+        latent = base_filters * 2 ** (depth - 2)
+        s["vae.unproj.kernel"] = (latent, d * h * w // 8)
+        s["vae.unproj.bias"] = (d * h * w // 8,)
+        up("vae.up.", 1, base_filters * 2 ** (depth - 1))
+        c = base_filters * 2 ** (depth - 1)
+        for i in range(depth - 2, -1, -1):
+            f = base_filters * 2 ** i
+            up(f"vae.L{i}.up.", c, f)
+            block(f"vae.L{i}.block.", f, f)
+            c = f
+        s["vae.out.kernel"] = (3, 3, 3, c, in_ch)
+        s["vae.out.bias"] = (in_ch,)
+    return s
+
+
+def init_params(shapes: Dict[str, Tuple[int, ...]], seed=2, dtype=torch.float64) -> Params:
+    """Synthetic weights of the reference's scale: kernels ~ N(0, 2/fan_in)
+    (he-like), GN gamma 1+0.1N (incl. gn2, whose reference init 0 would kill the conv branch, F4),
+    beta 0.1N, biases 0.01N."""
+    rng = np.random.default_rng(seed)
+    p: Params = {}
+    for k, shp in shapes.items():
+        if k.endswith("kernel"):
+            if len(shp) == 5:
+                fan_in = shp[0] * shp[1] * shp[2] * shp[3]
+                if ".up.conv." in k:  # transpose conv: (k,k,k,Cout,Cin)
+                    fan_in = shp[0] * shp[1] * shp[2] * shp[4] / 8.0  # ~27/8 taps hit per output
+            else:
+                fan_in = shp[0]
+            a = rng.standard_normal(shp) * math.sqrt(2.0 / fan_in)
+        elif k.endswith("gamma"):
+            a = 1.0 + 0.1 * rng.standard_normal(shp)
+        elif k.endswith("beta"):
+            a = 0.1 * rng.standard_normal(shp)
+        else:
+            a = 0.01 * rng.standard_normal(shp)
+        p[k] = torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+    return p
+
+
+def synth_batch(shape=(1, 128, 128, 128), in_ch=2, out_ch=3, latent=64, seed=0, dtype=torch.float64):
+    """x ~ N(0,1) seed; y: iid labels p=(0.85,0.05,..) one-hot minus background; eps ~ N(0,1);
+    dropout mask Bernoulli(0.8)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(shape + (in_ch,))
+    pr = [0.85] + [0.15 / out_ch] * out_ch
+    lab = np.random.default_rng(seed + 1).choice(out_ch + 1, size=shape, p=pr)
+    y = np.stack([(lab == c + 1) for c in range(out_ch)], axis=-1).astype(np.float64)
+    eps = np.random.default_rng(seed + 3).standard_normal((shape[0], latent))
+    mask = (np.random.default_rng(seed + 4).random(shape + (in_ch,)) < 0.8).astype(np.float64)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+    return t(x), t(y), t(eps), t(mask)
