@@ -1,0 +1,592 @@
+// b3d — ResnetBlock epilogue (reference layers/resnet.py:121-137), fused:
+//   chse = sigmoid(relu(mean_vox(res) W1) W2)                         (tiny 1-CTA kernel)
+//   out  = res * (sigmoid(res . w_sp) + chse) + relu(GN2(h2))         (one pass: 2 reads + 1 write)
+// and its backward as two passes (reductions, then elementwise), SURVEY App. D.
+// HBM-bound; T = F/4 lanes cooperate on one voxel (128-bit loads, shuffle reduce of the
+// per-voxel channel dot).  GN2 follows the contiguous-chunk semantics of norm.cu and requires
+// voxel-aligned chunks (D*H*W % groups == 0); otherwise callers use HAS_GN=0 + the norm.cu kernels.
+#include "common.cuh"
+
+namespace b3d {
+
+constexpr int kBT = 256;
+constexpr int kMaxNPL = 4;
+
+struct BlockGeom {
+  long long S;        // voxels per sample
+  long long vpc;      // voxels per chunk (S / G)
+  int F, T, npl;      // channels, lanes per voxel, float4 per lane
+  int G, cg;
+  int vox_per_cta;    // voxels handled by one CTA
+};
+
+__device__ __forceinline__ float group_sum(float v, int T) {
+  for (int o = T >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void moments(const double* __restrict__ stats, int chunk, double inv_L, float eps,
+                                        float& mean, float& rstd) {
+  const double s0 = stats[2 * chunk], s1 = stats[2 * chunk + 1];
+  const double m = s0 * inv_L;
+  double var = s1 * inv_L - m * m;
+  var = var < 0.0 ? 0.0 : var;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// grid: (segments per chunk, B*G).  Each CTA walks vox_per_cta voxels of one chunk.
+template <bool HAS_GN>
+__global__ void __launch_bounds__(kBT)
+    block_epilogue_fwd_kernel(const float* __restrict__ res, const float* __restrict__ h2,
+                              const double* __restrict__ stats, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, const float* __restrict__ wsp,
+                              const float* __restrict__ chse, float* __restrict__ out, BlockGeom gm, float eps) {
+  const int chunk = blockIdx.y, b = chunk / gm.G, g = chunk % gm.G;
+  const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
+  float mean = 0.f, rstd = 1.f;
+  if (HAS_GN) moments(stats, chunk, 1.0 / ((double)gm.vpc * gm.F), eps, mean, rstd);
+  float4 w4[kMaxNPL], c4[kMaxNPL], ga4[kMaxNPL], be4[kMaxNPL];
+#pragma unroll
+  for (int q = 0; q < kMaxNPL; ++q)
+    if (q < gm.npl) {
+      const int c = (q * T + lane) * 4;
+      w4[q] = *reinterpret_cast<const float4*>(wsp + c);
+      c4[q] = *reinterpret_cast<const float4*>(chse + (long long)b * gm.F + c);
+      if (HAS_GN) {
+        float ga[4], be[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = g * gm.cg + (c + i) % gm.cg;
+          ga[i] = gamma[j];
+          be[i] = beta[j];
+        }
+        ga4[q] = make_float4(ga[0], ga[1], ga[2], ga[3]);
+        be4[q] = make_float4(be[0], be[1], be[2], be[3]);
+      }
+    }
+  const long long v0 = (long long)blockIdx.x * gm.vox_per_cta;
+  const long long vend = min(v0 + gm.vox_per_cta, gm.vpc);
+  const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
+  const int iters = (int)((vend - v0 + vstep - 1) / vstep);   // CTA-uniform: whole warps stay in the shuffles
+  for (int it = 0; it < iters; ++it) {
+    const long long v = v0 + (long long)it * vstep + vl;
+    const bool act = v < vend;
+    const long long eo = (vbase + (act ? v : v0)) * gm.F;
+    float4 r[kMaxNPL], h[kMaxNPL];
+    float dot = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxNPL; ++q)
+      if (q < gm.npl) {
+        const int c = (q * T + lane) * 4;
+        r[q] = ld_stream(reinterpret_cast<const float4*>(res + eo + c));
+        h[q] = ld_stream(reinterpret_cast<const float4*>(h2 + eo + c));
+        dot += r[q].x * w4[q].x + r[q].y * w4[q].y + r[q].z * w4[q].z + r[q].w * w4[q].w;
+      }
+    dot = group_sum(dot, T);
+    const float s = sigmoidf_(dot);
+    if (act) {
+#pragma unroll
+      for (int q = 0; q < kMaxNPL; ++q)
+        if (q < gm.npl) {
+          const int c = (q * T + lane) * 4;
+          float4 a = h[q];
+          if (HAS_GN) {
+            a.x = fmaxf((a.x - mean) * rstd * ga4[q].x + be4[q].x, 0.f);
+            a.y = fmaxf((a.y - mean) * rstd * ga4[q].y + be4[q].y, 0.f);
+            a.z = fmaxf((a.z - mean) * rstd * ga4[q].z + be4[q].z, 0.f);
+            a.w = fmaxf((a.w - mean) * rstd * ga4[q].w + be4[q].w, 0.f);
+          }
+          float4 o;
+          o.x = r[q].x * (s + c4[q].x) + a.x;
+          o.y = r[q].y * (s + c4[q].y) + a.y;
+          o.z = r[q].z * (s + c4[q].z) + a.z;
+          o.w = r[q].w * (s + c4[q].w) + a.w;
+          st_stream(reinterpret_cast<float4*>(out + eo + c), o);
+        }
+    }
+  }
+}
+
+// Backward pass A — reductions.  Accumulates (atomics; outputs pre-zeroed by the host wrapper):
+//   dchse[b][c] += sum_v do*res ; dwsp[c] += sum_v dlogit*res ; dgamma_j, dbeta_j ; csum[chunk] = (S1,S2)
+template <bool HAS_GN>
+__global__ void __launch_bounds__(kBT)
+    block_epilogue_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ res,
+                                     const float* __restrict__ h2, const double* __restrict__ stats,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ wsp, float* __restrict__ dchse,
+                                     float* __restrict__ dwsp, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, double* __restrict__ csum, BlockGeom gm, float eps) {
+  extern __shared__ float sm[];  // [4][F]: dchse, dwsp, dgam(c), dbet(c)
+  for (int i = threadIdx.x; i < 4 * gm.F; i += kBT) sm[i] = 0.f;
+  __syncthreads();
+  const int chunk = blockIdx.y, b = chunk / gm.G, g = chunk % gm.G;
+  const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
+  float mean = 0.f, rstd = 1.f;
+  if (HAS_GN) moments(stats, chunk, 1.0 / ((double)gm.vpc * gm.F), eps, mean, rstd);
+  float4 w4[kMaxNPL], ga4[kMaxNPL], be4[kMaxNPL];
+  float acc_c[kMaxNPL][4], acc_w[kMaxNPL][4], acc_g[kMaxNPL][4], acc_b[kMaxNPL][4];
+#pragma unroll
+  for (int q = 0; q < kMaxNPL; ++q) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc_c[q][i] = acc_w[q][i] = acc_g[q][i] = acc_b[q][i] = 0.f;
+    if (q < gm.npl) {
+      const int c = (q * T + lane) * 4;
+      w4[q] = *reinterpret_cast<const float4*>(wsp + c);
+      if (HAS_GN) {
+        float ga[4], be[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = g * gm.cg + (c + i) % gm.cg;
+          ga[i] = gamma[j];
+          be[i] = beta[j];
+        }
+        ga4[q] = make_float4(ga[0], ga[1], ga[2], ga[3]);
+        be4[q] = make_float4(be[0], be[1], be[2], be[3]);
+      }
+    }
+  }
+  float s1 = 0.f, s2 = 0.f;
+  const long long v0 = (long long)blockIdx.x * gm.vox_per_cta;
+  const long long vend = min(v0 + gm.vox_per_cta, gm.vpc);
+  const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
+  const int iters = (int)((vend - v0 + vstep - 1) / vstep);   // CTA-uniform: whole warps stay in the shuffles
+  for (int it = 0; it < iters; ++it) {
+    const long long v = v0 + (long long)it * vstep + vl;
+    const bool act = v < vend;
+    const long long eo = (vbase + (act ? v : v0)) * gm.F;
+    float4 r[kMaxNPL], d[kMaxNPL];
+    float dot = 0.f, ds = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxNPL; ++q)
+      if (q < gm.npl) {
+        const int c = (q * T + lane) * 4;
+        r[q] = ld_stream(reinterpret_cast<const float4*>(res + eo + c));
+        d[q] = ld_stream(reinterpret_cast<const float4*>(dout + eo + c));
+        if (!act) d[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dot += r[q].x * w4[q].x + r[q].y * w4[q].y + r[q].z * w4[q].z + r[q].w * w4[q].w;
+        ds += r[q].x * d[q].x + r[q].y * d[q].y + r[q].z * d[q].z + r[q].w * d[q].w;
+      }
+    dot = group_sum(dot, T);
+    ds = group_sum(ds, T);
+    const float s = sigmoidf_(dot);
+    const float dl = ds * s * (1.f - s);
+#pragma unroll
+    for (int q = 0; q < kMaxNPL; ++q)
+      if (q < gm.npl) {
+        const float rr[4] = {r[q].x, r[q].y, r[q].z, r[q].w};
+        const float dd[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc_c[q][i] += dd[i] * rr[i];
+          acc_w[q][i] += dl * rr[i];
+        }
+        if (HAS_GN) {
+          const int c = (q * T + lane) * 4;
+          const float4 hv = ld_stream(reinterpret_cast<const float4*>(h2 + eo + c));
+          const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+          const float ga[4] = {ga4[q].x, ga4[q].y, ga4[q].z, ga4[q].w};
+          const float be[4] = {be4[q].x, be4[q].y, be4[q].z, be4[q].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float xh = (hh[i] - mean) * rstd;
+            const float gq = (xh * ga[i] + be[i]) > 0.f ? dd[i] : 0.f;
+            acc_g[q][i] += gq * xh;
+            acc_b[q][i] += gq;
+            const float hq = gq * ga[i];
+            s1 += hq;
+            s2 += hq * xh;
+          }
+        }
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < kMaxNPL; ++q)
+    if (q < gm.npl) {
+      const int c = (q * T + lane) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        atomicAdd(&sm[0 * gm.F + c + i], acc_c[q][i]);
+        atomicAdd(&sm[1 * gm.F + c + i], acc_w[q][i]);
+        if (HAS_GN) {
+          atomicAdd(&sm[2 * gm.F + c + i], acc_g[q][i]);
+          atomicAdd(&sm[3 * gm.F + c + i], acc_b[q][i]);
+        }
+      }
+    }
+  __shared__ double red[64];
+  double dd2[2] = {(double)s1, (double)s2};
+  block_sum<2, double>(dd2, red);
+  if (HAS_GN && threadIdx.x == 0) {
+    atomicAdd(&csum[2 * chunk], dd2[0]);
+    atomicAdd(&csum[2 * chunk + 1], dd2[1]);
+  }
+  for (int c = threadIdx.x; c < gm.F; c += kBT) {
+    atomicAdd(&dchse[(long long)b * gm.F + c], sm[c]);
+    atomicAdd(&dwsp[c], sm[gm.F + c]);
+    if (HAS_GN) {
+      const int j = g * gm.cg + c % gm.cg;
+      atomicAdd(&dgamma[j], sm[2 * gm.F + c]);
+      atomicAdd(&dbeta[j], sm[3 * gm.F + c]);
+    }
+  }
+}
+
+// Backward pass B — elementwise:  dres, dh2
+template <bool HAS_GN>
+__global__ void __launch_bounds__(kBT)
+    block_epilogue_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ res,
+                                    const float* __restrict__ h2, const double* __restrict__ stats,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ wsp, const float* __restrict__ chse,
+                                    const float* __restrict__ dgap, const double* __restrict__ csum,
+                                    float* __restrict__ dres, float* __restrict__ dh2, BlockGeom gm, float eps) {
+  const int chunk = blockIdx.y, b = chunk / gm.G, g = chunk % gm.G;
+  const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
+  float mean = 0.f, rstd = 1.f, m1 = 0.f, m2 = 0.f;
+  if (HAS_GN) {
+    const double L = (double)gm.vpc * gm.F;
+    moments(stats, chunk, 1.0 / L, eps, mean, rstd);
+    m1 = (float)(csum[2 * chunk] / L);
+    m2 = (float)(csum[2 * chunk + 1] / L);
+  }
+  float4 w4[kMaxNPL], c4[kMaxNPL], g4[kMaxNPL], ga4[kMaxNPL], be4[kMaxNPL];
+#pragma unroll
+  for (int q = 0; q < kMaxNPL; ++q)
+    if (q < gm.npl) {
+      const int c = (q * T + lane) * 4;
+      w4[q] = *reinterpret_cast<const float4*>(wsp + c);
+      c4[q] = *reinterpret_cast<const float4*>(chse + (long long)b * gm.F + c);
+      g4[q] = *reinterpret_cast<const float4*>(dgap + (long long)b * gm.F + c);
+      if (HAS_GN) {
+        float ga[4], be[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = g * gm.cg + (c + i) % gm.cg;
+          ga[i] = gamma[j];
+          be[i] = beta[j];
+        }
+        ga4[q] = make_float4(ga[0], ga[1], ga[2], ga[3]);
+        be4[q] = make_float4(be[0], be[1], be[2], be[3]);
+      }
+    }
+  const long long v0 = (long long)blockIdx.x * gm.vox_per_cta;
+  const long long vend = min(v0 + gm.vox_per_cta, gm.vpc);
+  const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
+  const int iters = (int)((vend - v0 + vstep - 1) / vstep);   // CTA-uniform: whole warps stay in the shuffles
+  for (int it = 0; it < iters; ++it) {
+    const long long v = v0 + (long long)it * vstep + vl;
+    const bool act = v < vend;
+    const long long eo = (vbase + (act ? v : v0)) * gm.F;
+    float4 r[kMaxNPL], d[kMaxNPL];
+    float dot = 0.f, ds = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxNPL; ++q)
+      if (q < gm.npl) {
+        const int c = (q * T + lane) * 4;
+        r[q] = ld_stream(reinterpret_cast<const float4*>(res + eo + c));
+        d[q] = ld_stream(reinterpret_cast<const float4*>(dout + eo + c));
+        dot += r[q].x * w4[q].x + r[q].y * w4[q].y + r[q].z * w4[q].z + r[q].w * w4[q].w;
+        ds += r[q].x * d[q].x + r[q].y * d[q].y + r[q].z * d[q].z + r[q].w * d[q].w;
+      }
+    dot = group_sum(dot, T);
+    ds = group_sum(ds, T);
+    const float s = sigmoidf_(dot);
+    const float dl = ds * s * (1.f - s);
+    if (act) {
+#pragma unroll
+      for (int q = 0; q < kMaxNPL; ++q)
+        if (q < gm.npl) {
+          const int c = (q * T + lane) * 4;
+          float4 o;
+          o.x = d[q].x * (s + c4[q].x) + dl * w4[q].x + g4[q].x;
+          o.y = d[q].y * (s + c4[q].y) + dl * w4[q].y + g4[q].y;
+          o.z = d[q].z * (s + c4[q].z) + dl * w4[q].z + g4[q].z;
+          o.w = d[q].w * (s + c4[q].w) + dl * w4[q].w + g4[q].w;
+          st_stream(reinterpret_cast<float4*>(dres + eo + c), o);
+          if (HAS_GN) {
+            const float4 hv = ld_stream(reinterpret_cast<const float4*>(h2 + eo + c));
+            const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+            const float dd[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
+            const float ga[4] = {ga4[q].x, ga4[q].y, ga4[q].z, ga4[q].w};
+            const float be[4] = {be4[q].x, be4[q].y, be4[q].z, be4[q].w};
+            float oo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float xh = (hh[i] - mean) * rstd;
+              const float gq = (xh * ga[i] + be[i]) > 0.f ? dd[i] : 0.f;
+              oo[i] = rstd * (gq * ga[i] - m1 - xh * m2);
+            }
+            st_stream(reinterpret_cast<float4*>(dh2 + eo + c), make_float4(oo[0], oo[1], oo[2], oo[3]));
+          }
+        }
+    }
+  }
+}
+
+// ---- channel squeeze-excitation FCs (resnet.py:121-124); one CTA, loops over the batch ----------
+__global__ void __launch_bounds__(256)
+    se_fc_fwd_kernel(const float* __restrict__ gap_sum, const float* __restrict__ w1, const float* __restrict__ w2,
+                     float* __restrict__ hidden, float* __restrict__ chse, int B, int F, int R, float inv_vox) {
+  extern __shared__ float sm[];  // mean[F], hid[R]
+  float* mean = sm;
+  float* hid = sm + F;
+  for (int b = 0; b < B; ++b) {
+    for (int c = threadIdx.x; c < F; c += blockDim.x) mean[c] = gap_sum[b * F + c] * inv_vox;
+    __syncthreads();
+    for (int k = threadIdx.x; k < R; k += blockDim.x) {
+      float a = 0.f;
+      for (int c = 0; c < F; ++c) a += mean[c] * w1[c * R + k];
+      a = fmaxf(a, 0.f);
+      hid[k] = a;
+      hidden[b * R + k] = a;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < F; c += blockDim.x) {
+      float a = 0.f;
+      for (int k = 0; k < R; ++k) a += hid[k] * w2[k * F + c];
+      chse[b * F + c] = 1.f / (1.f + expf(-a));
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    se_fc_bwd_kernel(const float* __restrict__ gap_sum, const float* __restrict__ w1, const float* __restrict__ w2,
+                     const float* __restrict__ hidden, const float* __restrict__ chse,
+                     const float* __restrict__ dchse, float* __restrict__ dw1, float* __restrict__ dw2,
+                     float* __restrict__ dgap, int B, int F, int R, float inv_vox) {
+  extern __shared__ float sm[];  // dz2[F], dz1[R]
+  float* dz2 = sm;
+  float* dz1 = sm + F;
+  for (int i = threadIdx.x; i < F * R; i += blockDim.x) dw1[i] = 0.f, dw2[i] = 0.f;
+  __syncthreads();
+  for (int b = 0; b < B; ++b) {
+    for (int c = threadIdx.x; c < F; c += blockDim.x) {
+      const float y = chse[b * F + c];
+      dz2[c] = dchse[b * F + c] * y * (1.f - y);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < R; k += blockDim.x) {
+      float a = 0.f;
+      for (int c = 0; c < F; ++c) a += w2[k * F + c] * dz2[c];
+      dz1[k] = hidden[b * R + k] > 0.f ? a : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < F * R; i += blockDim.x) {
+      const int k2 = i / F, c2 = i % F;              // dw2[k][c]
+      dw2[i] += hidden[b * R + k2] * dz2[c2];
+      const int c1 = i / R, k1 = i % R;              // dw1[c][k]
+      dw1[i] += gap_sum[b * F + c1] * inv_vox * dz1[k1];
+    }
+    for (int c = threadIdx.x; c < F; c += blockDim.x) {
+      float a = 0.f;
+      for (int k = 0; k < R; ++k) a += w1[c * R + k] * dz1[k];
+      dgap[b * F + c] = a * inv_vox;
+    }
+    __syncthreads();
+  }
+}
+
+static int block_geom(const TView& res, int groups, bool has_gn, BlockGeom* gm, int* nchunks) {
+  const int F = (int)res.shape[res.ndim - 1];
+  const long long B = res.shape[0];
+  const long long S = res.numel / B / F;
+  B3D_REQUIRE(F % 4 == 0, B3D_ERR_UNSUPPORTED, "block epilogue: filters (%d) must be a multiple of 4", F);
+  int G = has_gn ? groups : 1;
+  if (has_gn) {
+    B3D_REQUIRE(F >= groups && F % groups == 0, B3D_ERR_SHAPE,
+                "Number of groups (%d) must be a multiple of the number of channels (%d).", groups, F);
+    B3D_REQUIRE(S % groups == 0, B3D_ERR_UNSUPPORTED,
+                "fused GN epilogue needs D*H*W (%lld) divisible by groups (%d)", (long long)S, groups);
+  } else {
+    // no chunk structure needed: split every sample into up to 8 pseudo-chunks for grid parallelism
+    G = 1;
+  }
+  int q = F / 4, T = 1;
+  while (T < 32 && q % (T * 2) == 0) T *= 2;
+  B3D_REQUIRE(q / T <= kMaxNPL, B3D_ERR_UNSUPPORTED, "block epilogue: unsupported filter count %d", F);
+  gm->S = S;
+  gm->vpc = S / G;
+  gm->F = F;
+  gm->T = T;
+  gm->npl = q / T;
+  gm->G = G;
+  gm->cg = has_gn ? F / groups : F;
+  const int vstep = kBT / T;
+  // ~8 voxel-iterations per thread-group, but enough CTAs to fill the machine
+  long long vp = (long long)vstep * 16;
+  gm->vox_per_cta = (int)vp;
+  *nchunks = (int)(B * G);
+  B3D_REQUIRE(*nchunks <= 65535, B3D_ERR_SHAPE, "batch*groups too large");
+  return B3D_OK;
+}
+
+static inline dim3 block_grid(const BlockGeom& gm, int nchunks) {
+  return dim3((unsigned)((gm.vpc + gm.vox_per_cta - 1) / gm.vox_per_cta), (unsigned)nchunks, 1);
+}
+
+static int vecF(const DLTensor* t, long long n, const char* name, TView* v) {
+  B3D_TRY(view(t, DT_F32, -1, false, name, v));
+  B3D_REQUIRE(v->numel == n, B3D_ERR_SHAPE, "%s: expected %lld values, got %lld", name, n, (long long)v->numel);
+  return B3D_OK;
+}
+
+}  // namespace b3d
+
+using namespace b3d;
+
+extern "C" int b3d_se_fc_fwd(const DLTensor* gap_sum_, const DLTensor* w1_, const DLTensor* w2_,
+                             DLTensor* hidden_, DLTensor* chse_, float inv_vox, void* stream) {
+  TView gs, w1, w2, hid, ch;
+  B3D_TRY(view(gap_sum_, DT_F32, 2, false, "gap_sum", &gs));
+  B3D_TRY(view(w1_, DT_F32, 2, false, "w1", &w1));
+  B3D_TRY(view(w2_, DT_F32, 2, false, "w2", &w2));
+  const int B = (int)gs.shape[0], F = (int)gs.shape[1], R = (int)w1.shape[1];
+  B3D_REQUIRE(w1.shape[0] == F && w2.shape[0] == R && w2.shape[1] == F, B3D_ERR_SHAPE, "se_fc: weight shapes");
+  B3D_TRY(vecF(hidden_, (long long)B * R, "hidden", &hid));
+  B3D_TRY(vecF(chse_, (long long)B * F, "chse", &ch));
+  se_fc_fwd_kernel<<<1, 256, sizeof(float) * (F + R), (cudaStream_t)stream>>>(
+      (const float*)gs.p, (const float*)w1.p, (const float*)w2.p, (float*)hid.p, (float*)ch.p, B, F, R, inv_vox);
+  B3D_LAUNCH_CHECK("se_fc_fwd");
+  return B3D_OK;
+}
+
+extern "C" int b3d_se_fc_bwd(const DLTensor* gap_sum_, const DLTensor* w1_, const DLTensor* w2_,
+                             const DLTensor* hidden_, const DLTensor* chse_, const DLTensor* dchse_,
+                             DLTensor* dw1_, DLTensor* dw2_, DLTensor* dgap_, float inv_vox, void* stream) {
+  TView gs, w1, w2, hid, ch, dch, dw1, dw2, dg;
+  B3D_TRY(view(gap_sum_, DT_F32, 2, false, "gap_sum", &gs));
+  B3D_TRY(view(w1_, DT_F32, 2, false, "w1", &w1));
+  B3D_TRY(view(w2_, DT_F32, 2, false, "w2", &w2));
+  const int B = (int)gs.shape[0], F = (int)gs.shape[1], R = (int)w1.shape[1];
+  B3D_REQUIRE(w1.shape[0] == F && w2.shape[0] == R && w2.shape[1] == F, B3D_ERR_SHAPE, "se_fc: weight shapes");
+  B3D_TRY(vecF(hidden_, (long long)B * R, "hidden", &hid));
+  B3D_TRY(vecF(chse_, (long long)B * F, "chse", &ch));
+  B3D_TRY(vecF(dchse_, (long long)B * F, "dchse", &dch));
+  B3D_TRY(vecF(dw1_, (long long)F * R, "dw1", &dw1));
+  B3D_TRY(vecF(dw2_, (long long)F * R, "dw2", &dw2));
+  B3D_TRY(vecF(dgap_, (long long)B * F, "dgap", &dg));
+  se_fc_bwd_kernel<<<1, 256, sizeof(float) * (F + R), (cudaStream_t)stream>>>(
+      (const float*)gs.p, (const float*)w1.p, (const float*)w2.p, (const float*)hid.p, (const float*)ch.p,
+      (const float*)dch.p, (float*)dw1.p, (float*)dw2.p, (float*)dg.p, B, F, R, inv_vox);
+  B3D_LAUNCH_CHECK("se_fc_bwd");
+  return B3D_OK;
+}
+
+extern "C" int b3d_block_epilogue_fwd(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
+                                      const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
+                                      const DLTensor* chse_, DLTensor* out_, int groups, float eps, int has_gn,
+                                      void* stream) {
+  TView res, h2, out, st, ga, be, wsp, ch;
+  BlockGeom gm;
+  int nchunks;
+  B3D_TRY(view(res_, DT_F32, -1, false, "res", &res));
+  B3D_TRY(view(h2_, DT_F32, -1, false, "h2", &h2));
+  B3D_TRY(view(out_, DT_F32, -1, false, "out", &out));
+  B3D_REQUIRE(res.numel == h2.numel && res.numel == out.numel, B3D_ERR_SHAPE, "block epilogue: size mismatch");
+  B3D_TRY(block_geom(res, groups, has_gn != 0, &gm, &nchunks));
+  B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
+  B3D_TRY(vecF(chse_, res.shape[0] * gm.F, "chse", &ch));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (has_gn) {
+    B3D_TRY(view(stats_, DT_F64, -1, false, "stats", &st));
+    B3D_REQUIRE(st.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats: wrong size");
+    B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
+    B3D_TRY(vecF(beta_, gm.F, "beta", &be));
+    block_epilogue_fwd_kernel<true><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+        (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+        (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps);
+  } else {
+    block_epilogue_fwd_kernel<false><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+        (const float*)res.p, (const float*)h2.p, nullptr, nullptr, nullptr, (const float*)wsp.p,
+        (const float*)ch.p, (float*)out.p, gm, eps);
+  }
+  B3D_LAUNCH_CHECK("block_epilogue_fwd");
+  return B3D_OK;
+}
+
+extern "C" int b3d_block_epilogue_bwd_reduce(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,
+                                             const DLTensor* stats_, const DLTensor* gamma_,
+                                             const DLTensor* beta_, const DLTensor* wsp_, DLTensor* dchse_,
+                                             DLTensor* dwsp_, DLTensor* dgamma_, DLTensor* dbeta_,
+                                             DLTensor* csum_, int groups, float eps, int has_gn, void* stream) {
+  TView dout, res, h2, st, ga, be, wsp, dch, dws, dga, dbe, cs;
+  BlockGeom gm;
+  int nchunks;
+  B3D_TRY(view(dout_, DT_F32, -1, false, "dout", &dout));
+  B3D_TRY(view(res_, DT_F32, -1, false, "res", &res));
+  B3D_REQUIRE(res.numel == dout.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+  B3D_TRY(block_geom(res, groups, has_gn != 0, &gm, &nchunks));
+  B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
+  B3D_TRY(vecF(dchse_, res.shape[0] * gm.F, "dchse", &dch));
+  B3D_TRY(vecF(dwsp_, gm.F, "dwsp", &dws));
+  cudaStream_t s = (cudaStream_t)stream;
+  B3D_TRY(cuda_ok(cudaMemsetAsync(dch.p, 0, sizeof(float) * dch.numel, s), "memset"));
+  B3D_TRY(cuda_ok(cudaMemsetAsync(dws.p, 0, sizeof(float) * gm.F, s), "memset"));
+  const size_t smem = sizeof(float) * 4 * gm.F;
+  if (has_gn) {
+    B3D_TRY(view(h2_, DT_F32, -1, false, "h2", &h2));
+    B3D_REQUIRE(res.numel == h2.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+    B3D_TRY(view(stats_, DT_F64, -1, false, "stats", &st));
+    B3D_TRY(view(csum_, DT_F64, -1, false, "csum", &cs));
+    B3D_REQUIRE(st.numel == 2LL * nchunks && cs.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats/csum: wrong size");
+    B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
+    B3D_TRY(vecF(beta_, gm.F, "beta", &be));
+    B3D_TRY(vecF(dgamma_, gm.F, "dgamma", &dga));
+    B3D_TRY(vecF(dbeta_, gm.F, "dbeta", &dbe));
+    B3D_TRY(cuda_ok(cudaMemsetAsync(cs.p, 0, sizeof(double) * 2 * nchunks, s), "memset"));
+    B3D_TRY(cuda_ok(cudaMemsetAsync(dga.p, 0, sizeof(float) * gm.F, s), "memset"));
+    B3D_TRY(cuda_ok(cudaMemsetAsync(dbe.p, 0, sizeof(float) * gm.F, s), "memset"));
+    block_epilogue_bwd_reduce_kernel<true><<<block_grid(gm, nchunks), kBT, smem, s>>>(
+        (const float*)dout.p, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p,
+        (const float*)be.p, (const float*)wsp.p, (float*)dch.p, (float*)dws.p, (float*)dga.p, (float*)dbe.p,
+        (double*)cs.p, gm, eps);
+  } else {
+    block_epilogue_bwd_reduce_kernel<false><<<block_grid(gm, nchunks), kBT, smem, s>>>(
+        (const float*)dout.p, (const float*)res.p, nullptr, nullptr, nullptr, nullptr, (const float*)wsp.p,
+        (float*)dch.p, (float*)dws.p, nullptr, nullptr, nullptr, gm, eps);
+  }
+  B3D_LAUNCH_CHECK("block_epilogue_bwd_reduce");
+  return B3D_OK;
+}
+
+extern "C" int b3d_block_epilogue_bwd_apply(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,
+                                            const DLTensor* stats_, const DLTensor* gamma_,
+                                            const DLTensor* beta_, const DLTensor* wsp_, const DLTensor* chse_,
+                                            const DLTensor* dgap_, const DLTensor* csum_, DLTensor* dres_,
+                                            DLTensor* dh2_, int groups, float eps, int has_gn, void* stream) {
+  TView dout, res, h2, st, ga, be, wsp, ch, dg, cs, dres, dh2;
+  BlockGeom gm;
+  int nchunks;
+  B3D_TRY(view(dout_, DT_F32, -1, false, "dout", &dout));
+  B3D_TRY(view(res_, DT_F32, -1, false, "res", &res));
+  B3D_TRY(view(dres_, DT_F32, -1, false, "dres", &dres));
+  B3D_REQUIRE(res.numel == dout.numel && res.numel == dres.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+  B3D_TRY(block_geom(res, groups, has_gn != 0, &gm, &nchunks));
+  B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
+  B3D_TRY(vecF(chse_, res.shape[0] * gm.F, "chse", &ch));
+  B3D_TRY(vecF(dgap_, res.shape[0] * gm.F, "dgap", &dg));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (has_gn) {
+    B3D_TRY(view(h2_, DT_F32, -1, false, "h2", &h2));
+    B3D_TRY(view(dh2_, DT_F32, -1, false, "dh2", &dh2));
+    B3D_REQUIRE(res.numel == h2.numel && res.numel == dh2.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+    B3D_TRY(view(stats_, DT_F64, -1, false, "stats", &st));
+    B3D_TRY(view(csum_, DT_F64, -1, false, "csum", &cs));
+    B3D_REQUIRE(st.numel == 2LL * nchunks && cs.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats/csum: wrong size");
+    B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
+    B3D_TRY(vecF(beta_, gm.F, "beta", &be));
+    block_epilogue_bwd_apply_kernel<true><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+        (const float*)dout.p, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p,
+        (const float*)be.p, (const float*)wsp.p, (const float*)ch.p, (const float*)dg.p, (const double*)cs.p,
+        (float*)dres.p, (float*)dh2.p, gm, eps);
+  } else {
+    block_epilogue_bwd_apply_kernel<false><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+        (const float*)dout.p, (const float*)res.p, nullptr, nullptr, nullptr, nullptr, (const float*)wsp.p,
+        (const float*)ch.p, (const float*)dg.p, nullptr, (float*)dres.p, nullptr, gm, eps);
+  }
+  B3D_LAUNCH_CHECK("block_epilogue_bwd_apply");
+  return B3D_OK;
+}

@@ -1,0 +1,115 @@
+// b3d — shared helpers for the sm_100a kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b3d_dlpack.h"
+
+#define B3D_OK 0
+#define B3D_ERR_ARG (-1)
+#define B3D_ERR_DEVICE (-2)
+#define B3D_ERR_DTYPE (-3)
+#define B3D_ERR_LAYOUT (-4)
+#define B3D_ERR_SHAPE (-5)
+#define B3D_ERR_CUDA (-6)
+#define B3D_ERR_UNSUPPORTED (-7)
+
+namespace b3d {
+
+void set_error(const char* fmt, ...);
+
+// ---- DLPack validation ---------------------------------------------------------------------
+struct TView {
+  void* p = nullptr;
+  int ndim = 0;
+  int64_t shape[6] = {0, 0, 0, 0, 0, 0};
+  int64_t pitch = 0;  // elements between consecutive "rows" of the last dim (== shape[last] if compact)
+  int64_t numel = 0;
+  int device = 0;
+};
+
+// dtype codes
+enum { DT_F32 = 0, DT_F64 = 1, DT_I64 = 2, DT_BF16 = 3 };
+
+// Validates: CUDA device, dtype, ndim, and compact row-major strides; if allow_pitch, the last
+// dim may be a channel slice of a wider NDHWC buffer (stride[last]==1, outer strides compact
+// w.r.t. a pitch >= shape[last]).
+int view(const DLTensor* t, int dtype, int ndim, bool allow_pitch, const char* name, TView* out);
+
+inline int cuda_ok(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return B3D_ERR_CUDA;
+  }
+  return B3D_OK;
+}
+
+#define B3D_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != B3D_OK) return _rc; \
+  } while (0)
+
+#define B3D_LAUNCH_CHECK(name) B3D_TRY(b3d::cuda_ok(cudaGetLastError(), name))
+
+#define B3D_REQUIRE(cond, code, ...) \
+  do {                               \
+    if (!(cond)) {                   \
+      b3d::set_error(__VA_ARGS__);   \
+      return code;                   \
+    }                                \
+  } while (0)
+
+int sm_count();
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in thread 0.  smem: NV*32 floats.
+template <int NV, typename T>
+__device__ __forceinline__ void block_sum(T (&v)[NV], T* smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem[i * 32 + wid] = v[i];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      T t = lane < nw ? smem[i * 32 + lane] : T(0);
+      v[i] = warp_sum(t);
+    }
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// streaming 128-bit accesses (read-once / write-once tensors)
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w));
+}
+
+}  // namespace b3d

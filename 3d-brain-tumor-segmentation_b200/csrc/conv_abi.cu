@@ -1,0 +1,228 @@
+// b3d — C-ABI entry points for the convolution family (see include/b3d.h for the contract).
+#include "common.cuh"
+#include "conv_common.cuh"
+
+using namespace b3d;
+
+namespace {
+
+struct ConvArgs {
+  TView x, w, y;
+  int k;
+};
+
+int spatial_ok(const TView& big, const TView& small, int stride, const char* what) {
+  for (int i = 1; i <= 3; ++i) {
+    if (stride == 1) {
+      B3D_REQUIRE(big.shape[i] == small.shape[i], B3D_ERR_SHAPE, "%s: spatial dims differ (dim %d: %lld vs %lld)",
+                  what, i, (long long)big.shape[i], (long long)small.shape[i]);
+    } else {
+      B3D_REQUIRE(big.shape[i] % 2 == 0 && big.shape[i] == 2 * small.shape[i], B3D_ERR_SHAPE,
+                  "%s: stride-2 needs even sizes with big == 2*small (dim %d: %lld vs %lld)", what, i,
+                  (long long)big.shape[i], (long long)small.shape[i]);
+    }
+  }
+  B3D_REQUIRE(big.shape[0] == small.shape[0], B3D_ERR_SHAPE, "%s: batch differs", what);
+  return B3D_OK;
+}
+
+int weight_view(const DLTensor* w_, TView* w, int* k) {
+  B3D_TRY(view(w_, DT_F32, 5, false, "w", w));
+  *k = (int)w->shape[0];
+  B3D_REQUIRE((*k == 1 || *k == 3) && w->shape[1] == *k && w->shape[2] == *k, B3D_ERR_UNSUPPORTED,
+              "conv: kernel must be 1x1x1 or 3x3x3 (got %lldx%lldx%lld)", (long long)w->shape[0],
+              (long long)w->shape[1], (long long)w->shape[2]);
+  return B3D_OK;
+}
+
+void fill_in(ConvGeom& g, const TView& x) {
+  g.B = (int)x.shape[0]; g.Di = (int)x.shape[1]; g.Hi = (int)x.shape[2]; g.Wi = (int)x.shape[3];
+  g.Cin = (int)x.shape[4]; g.xp = x.pitch;
+}
+void fill_out(ConvGeom& g, const TView& y) {
+  g.Do = (int)y.shape[1]; g.Ho = (int)y.shape[2]; g.Wo = (int)y.shape[3];
+  g.Cout = (int)y.shape[4]; g.yp = y.pitch;
+}
+
+int run(const ConvGeom& g, const TView& x, const TView& w, const float* bias, const TView& y,
+        const DLTensor* stats_, int groups, const DLTensor* gap_, const DLTensor* wpacked_, cudaStream_t s) {
+  double* stats = nullptr;
+  float* gap = nullptr;
+  if (stats_ != nullptr) {
+    TView st;
+    B3D_TRY(view(stats_, DT_F64, -1, false, "gn_stats", &st));
+    const long long S = (long long)g.Do * g.Ho * g.Wo;
+    B3D_REQUIRE(groups >= 1 && g.Cout % groups == 0 && S % groups == 0, B3D_ERR_UNSUPPORTED,
+                "conv: fused GN stats need Cout %% groups == 0 and D*H*W %% groups == 0");
+    B3D_REQUIRE(st.numel == 2LL * g.B * groups, B3D_ERR_SHAPE, "gn_stats: expected %d fp64 values", 2 * g.B * groups);
+    B3D_REQUIRE(y.pitch == g.Cout, B3D_ERR_LAYOUT, "conv: fused GN stats need a contiguous output");
+    stats = (double*)st.p;
+    B3D_TRY(cuda_ok(cudaMemsetAsync(stats, 0, sizeof(double) * st.numel, s), "memset stats"));
+  }
+  if (gap_ != nullptr) {
+    TView gp;
+    B3D_TRY(view(gap_, DT_F32, 2, false, "gap", &gp));
+    B3D_REQUIRE(gp.shape[0] == g.B && gp.shape[1] == g.Cout, B3D_ERR_SHAPE, "gap: expected [B, Cout]");
+    gap = (float*)gp.p;
+    B3D_TRY(cuda_ok(cudaMemsetAsync(gap, 0, sizeof(float) * gp.numel, s), "memset gap"));
+  }
+  if (wpacked_ != nullptr) {
+    TView wp;
+    B3D_TRY(view(wpacked_, DT_F32, 1, false, "wpacked", &wp));
+    B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "conv: shape not supported by the tcgen05 path");
+    B3D_REQUIRE((size_t)wp.numel == tc_packed_weight_elems(g.k, g.Cin, g.Cout), B3D_ERR_SHAPE,
+                "wpacked: wrong size");
+    return launch_conv_tc(g, (const float*)x.p, (const float*)wp.p, bias, (float*)y.p, stats, gap, s);
+  }
+  return launch_conv_gather(g, (const float*)x.p, (const float*)w.p, bias, (float*)y.p, stats, gap, s);
+}
+
+int bias_ptr(const DLTensor* bias_, int C, const float** out) {
+  *out = nullptr;
+  if (bias_ == nullptr) return B3D_OK;
+  TView b;
+  B3D_TRY(view(bias_, DT_F32, 1, false, "bias", &b));
+  B3D_REQUIRE(b.numel == C, B3D_ERR_SHAPE, "bias: expected %d values", C);
+  *out = (const float*)b.p;
+  return B3D_OK;
+}
+
+// geometry of forward / dgrad for the four (stride, transposed) variants
+int geom_fwd(ConvGeom& g, const TView& x, const TView& w, const TView& y, int k, int stride, int transposed) {
+  memset(&g, 0, sizeof(g));
+  fill_in(g, x);
+  fill_out(g, y);
+  g.k = k; g.pad = k / 2;
+  if (!transposed) {
+    B3D_REQUIRE(w.shape[3] == g.Cin && w.shape[4] == g.Cout, B3D_ERR_SHAPE,
+                "conv fwd: kernel (..,%lld,%lld) does not match Cin=%d Cout=%d", (long long)w.shape[3],
+                (long long)w.shape[4], g.Cin, g.Cout);
+    B3D_TRY(spatial_ok(x, y, stride, "conv fwd"));
+    g.mode = stride == 1 ? CONV_S1 : CONV_DOWN;
+    g.wtap = (long long)g.Cin * g.Cout; g.sw_in = g.Cout; g.sw_out = 1;
+  } else {
+    B3D_REQUIRE(w.shape[3] == g.Cout && w.shape[4] == g.Cin, B3D_ERR_SHAPE,
+                "conv-transpose fwd: kernel must be (3,3,3,Cout,Cin)");
+    B3D_TRY(spatial_ok(y, x, 2, "conv-transpose fwd"));
+    g.mode = CONV_UP;
+    g.wtap = (long long)g.Cin * g.Cout; g.sw_in = 1; g.sw_out = g.Cin;
+  }
+  return B3D_OK;
+}
+
+int geom_dgrad(ConvGeom& g, const TView& dy, const TView& w, const TView& dx, int k, int stride, int transposed) {
+  memset(&g, 0, sizeof(g));
+  fill_in(g, dy);   // gathered tensor is dy: "Cin" of the gather = Cout of the layer
+  fill_out(g, dx);
+  g.k = k; g.pad = k / 2;
+  if (!transposed) {
+    B3D_REQUIRE(w.shape[3] == g.Cout && w.shape[4] == g.Cin, B3D_ERR_SHAPE, "conv dgrad: kernel/channels mismatch");
+    B3D_TRY(spatial_ok(dx, dy, stride, "conv dgrad"));
+    g.mode = stride == 1 ? CONV_S1 : CONV_UP;
+    g.flip = stride == 1 ? 1 : 0;
+    g.wtap = (long long)g.Cin * g.Cout; g.sw_in = 1; g.sw_out = g.Cin;  // w[t][ci_layer][co_layer]
+  } else {
+    B3D_REQUIRE(w.shape[3] == g.Cin && w.shape[4] == g.Cout, B3D_ERR_SHAPE, "conv-transpose dgrad: kernel mismatch");
+    B3D_TRY(spatial_ok(dy, dx, 2, "conv-transpose dgrad"));
+    g.mode = CONV_DOWN;
+    g.wtap = (long long)g.Cin * g.Cout; g.sw_in = g.Cout; g.sw_out = 1;  // w[t][co_layer][ci_layer]
+  }
+  return B3D_OK;
+}
+
+}  // namespace
+
+extern "C" int b3d_conv3d_fwd(const DLTensor* x_, const DLTensor* w_, const DLTensor* bias_, DLTensor* y_,
+                              int stride, int transposed, int act, DLTensor* gn_stats_, int groups,
+                              DLTensor* gap_, int accumulate, const DLTensor* wpacked_, void* stream) {
+  TView x, w, y;
+  int k;
+  B3D_TRY(view(x_, DT_F32, 5, true, "x", &x));
+  B3D_TRY(view(y_, DT_F32, 5, true, "y", &y));
+  B3D_TRY(weight_view(w_, &w, &k));
+  B3D_REQUIRE(stride == 1 || (stride == 2 && k == 3), B3D_ERR_UNSUPPORTED, "conv: stride must be 1, or 2 with k=3");
+  B3D_REQUIRE(!transposed || stride == 2, B3D_ERR_UNSUPPORTED, "conv-transpose: only k=3 stride=2");
+  ConvGeom g;
+  B3D_TRY(geom_fwd(g, x, w, y, k, stride, transposed));
+  g.act = act; g.accumulate = accumulate; g.groups = groups;
+  const float* bias;
+  B3D_TRY(bias_ptr(bias_, g.Cout, &bias));
+  return run(g, x, w, bias, y, gn_stats_, groups, gap_, wpacked_, (cudaStream_t)stream);
+}
+
+extern "C" int b3d_conv3d_dgrad(const DLTensor* dy_, const DLTensor* w_, DLTensor* dx_, int stride,
+                                int transposed, int accumulate, const DLTensor* wpacked_, void* stream) {
+  TView dy, w, dx;
+  int k;
+  B3D_TRY(view(dy_, DT_F32, 5, true, "dy", &dy));
+  B3D_TRY(view(dx_, DT_F32, 5, true, "dx", &dx));
+  B3D_TRY(weight_view(w_, &w, &k));
+  B3D_REQUIRE(stride == 1 || (stride == 2 && k == 3), B3D_ERR_UNSUPPORTED, "conv: stride must be 1, or 2 with k=3");
+  ConvGeom g;
+  B3D_TRY(geom_dgrad(g, dy, w, dx, k, stride, transposed));
+  g.accumulate = accumulate;
+  return run(g, dy, w, nullptr, dx, nullptr, 1, nullptr, wpacked_, (cudaStream_t)stream);
+}
+
+extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTensor* dw_, DLTensor* dbias_,
+                                int stride, int transposed, void* stream) {
+  TView x, dy, dw;
+  int k;
+  B3D_TRY(view(x_, DT_F32, 5, true, "x", &x));
+  B3D_TRY(view(dy_, DT_F32, 5, true, "dy", &dy));
+  B3D_TRY(weight_view(dw_, &dw, &k));
+  cudaStream_t s = (cudaStream_t)stream;
+  WgradGeom wg;
+  memset(&wg, 0, sizeof(wg));
+  const TView& big = transposed ? dy : x;
+  const TView& sml = transposed ? x : dy;
+  B3D_TRY(spatial_ok(big, sml, stride, "conv wgrad"));
+  B3D_REQUIRE(dw.shape[3] == big.shape[4] && dw.shape[4] == sml.shape[4], B3D_ERR_SHAPE,
+              "conv wgrad: dw channel dims do not match the activations");
+  wg.B = (int)big.shape[0];
+  wg.Db = (int)big.shape[1]; wg.Hb = (int)big.shape[2]; wg.Wb = (int)big.shape[3]; wg.nA = (int)big.shape[4];
+  wg.Ds = (int)sml.shape[1]; wg.Hs = (int)sml.shape[2]; wg.Ws = (int)sml.shape[3]; wg.nB = (int)sml.shape[4];
+  wg.k = k; wg.s = stride; wg.pad = stride == 1 ? k / 2 : 0;
+  wg.bigp = big.pitch; wg.smallp = sml.pitch;
+  B3D_TRY(launch_conv_wgrad(wg, (const float*)big.p, (const float*)sml.p, (float*)dw.p, s));
+  if (dbias_ != nullptr) {
+    TView db;
+    B3D_TRY(view(dbias_, DT_F32, 1, false, "dbias", &db));
+    B3D_REQUIRE(db.numel == dy.shape[4], B3D_ERR_SHAPE, "dbias: expected %lld values", (long long)dy.shape[4]);
+    B3D_TRY(launch_colsum((const float*)dy.p, (float*)db.p, dy.numel / dy.shape[4], (int)dy.shape[4], dy.pitch,
+                          true, s));
+  }
+  return B3D_OK;
+}
+
+// 1 when the tcgen05 implicit-GEMM kernel handles a (gather-form) conv of these channel counts
+extern "C" int b3d_conv3d_tc_supported(int k, int stride, int transposed, int c_gathered, int c_produced) {
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.k = k; g.mode = (stride == 1 && !transposed) ? CONV_S1 : CONV_DOWN;
+  g.Cin = c_gathered; g.Cout = c_produced;
+  g.Wo = 8; g.Ho = 16; g.Do = 1; g.B = 1;
+  return tc_conv_supported(g) ? 1 : 0;
+}
+
+extern "C" long long b3d_conv3d_packed_elems(int k, int c_gathered, int c_produced) {
+  return (long long)tc_packed_weight_elems(k, c_gathered, c_produced);
+}
+
+// Re-lays a Keras conv kernel out for the tcgen05 kernel.  dgrad=0: forward operand of Conv3D;
+// dgrad=1: data-gradient operand (taps flipped, channel roles swapped).
+extern "C" int b3d_conv3d_pack_weights(const DLTensor* w_, DLTensor* packed_, int dgrad, void* stream) {
+  TView w, p;
+  int k;
+  B3D_TRY(weight_view(w_, &w, &k));
+  B3D_TRY(view(packed_, DT_F32, 1, false, "packed", &p));
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.k = k; g.mode = CONV_S1;
+  const int A = (int)w.shape[3], Bc = (int)w.shape[4];
+  g.wtap = (long long)A * Bc;
+  if (!dgrad) { g.Cin = A; g.Cout = Bc; g.sw_in = Bc; g.sw_out = 1; g.flip = 0; }
+  else        { g.Cin = Bc; g.Cout = A; g.sw_in = 1; g.sw_out = Bc; g.flip = 1; }
+  B3D_REQUIRE((size_t)p.numel == tc_packed_weight_elems(k, g.Cin, g.Cout), B3D_ERR_SHAPE, "packed: wrong size");
+  return launch_tc_pack_weights(g, (const float*)w.p, (float*)p.p, (cudaStream_t)stream);
+}

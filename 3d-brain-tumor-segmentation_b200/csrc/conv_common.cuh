@@ -1,0 +1,41 @@
+// b3d — geometry descriptors shared by the generic and tcgen05 convolution paths.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b3d {
+
+enum { CONV_S1 = 0, CONV_DOWN = 1, CONV_UP = 2 };
+
+// gather form:  y[b,o,co] = act( sum_{t,ci} x[b,pos(o,t),ci] * w[tw(t)*wtap + ci*sw_in + co*sw_out] + bias[co] )
+struct ConvGeom {
+  int B, Di, Hi, Wi, Cin;   // input  (gathered) tensor
+  int Do, Ho, Wo, Cout;     // output tensor
+  int k, pad, mode, flip;   // kernel size (1|3), S1 padding, CONV_*, reverse taps
+  long long xp, yp;         // channel pitch of x / y (elements per voxel row)
+  long long wtap;           // elements between taps in w (= A*B)
+  int sw_in, sw_out;        // strides of the contracted / produced channel in w
+  int act, accumulate;      // 1 = sigmoid; y += result
+  int groups;               // GN groups when stats are requested
+};
+
+// outer-product form:  dw[t][a][b] = sum_{n,o} big[n, s*o+t-pad, a] * small[n, o, b]
+struct WgradGeom {
+  int B, Db, Hb, Wb, nA;    // "big" tensor (the one indexed with the tap offset)
+  int Ds, Hs, Ws, nB;       // "small" tensor
+  int k, s, pad;
+  long long bigp, smallp;   // channel pitches
+};
+
+int launch_conv_gather(const ConvGeom& cg, const float* x, const float* w, const float* bias, float* y,
+                       double* stats, float* gap, cudaStream_t s);
+int launch_conv_wgrad(const WgradGeom& wg, const float* big, const float* small, float* dw, cudaStream_t s);
+int launch_colsum(const float* x, float* out, long long N, int C, long long pitch, bool zero, cudaStream_t s);
+
+// tcgen05 path (conv_tc.cu).  Returns true when the shape is handled there.
+bool tc_conv_supported(const ConvGeom& cg);
+int launch_conv_tc(const ConvGeom& cg, const float* x, const float* wpacked, const float* bias, float* y,
+                   double* stats, float* gap, cudaStream_t s);
+size_t tc_packed_weight_elems(int k, int Cin, int Cout);
+int launch_tc_pack_weights(const ConvGeom& cg, const float* w, float* wpacked, cudaStream_t s);
+
+}  // namespace b3d

@@ -1,0 +1,289 @@
+// b3d — shape-generic CUDA-core convolution kernels (fp32 FMA).
+//
+// These cover every Conv3D / Conv3DTranspose variant of the reference (k in {1,3}, stride in {1,2},
+// SAME padding as TF defines it — SURVEY F2) for ANY channel count, and are the path used for the
+// layers that are not tensor-core work: Cin=2 first conv, Cout<=3 output convs, 1x1x1 convs
+// (HBM-bound) and the strided / transposed resampling convs.  The 3x3x3 stride-1 convs with
+// Cin%8==0, Cout%16==0 — 92 % of the FLOPs — run on the tcgen05 kernel in conv_tc.cu instead.
+//
+// One "gather form" covers forward and data-gradient of all variants:
+//     y[b, o, co] = sum_{t, ci} x[b, pos(o, t), ci] * W[tw(t)][ci][co]
+//   S1  : pos = o + t - pad                (conv s1 fwd; with FLIP also its dgrad)
+//   DOWN: pos = 2*o + t                    (conv s2 fwd;  dgrad of Conv3DTranspose)
+//   UP  : pos = (o - t)/2 if even          (Conv3DTranspose fwd; dgrad of conv s2)
+// and one "outer-product form" covers all weight gradients:
+//     dW[t][a][b] = sum_{n, o} BIG[n, s*o + t - pad, a] * SMALL[n, o, b]
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace b3d {
+
+constexpr int kGT = 128;    // threads (= output voxels) per CTA in the gather kernel
+constexpr int kCiT = 16;    // input channels staged per weight chunk
+
+template <int CO_T>
+__global__ void __launch_bounds__(kGT)
+    conv_gather_kernel(ConvGeom cg, const float* __restrict__ x, const float* __restrict__ w,
+                       const float* __restrict__ bias, float* __restrict__ y, double* __restrict__ stats,
+                       float* __restrict__ gap) {
+  extern __shared__ float ws[];  // [taps][kCiT][CO_T]
+  const int taps = cg.k * cg.k * cg.k;
+  const long long nvox = (long long)cg.B * cg.Do * cg.Ho * cg.Wo;
+  const long long v = (long long)blockIdx.x * kGT + threadIdx.x;
+  const bool act = v < nvox;
+  const int co0 = blockIdx.y * CO_T;
+  int ow = 0, oh = 0, od = 0, b = 0;
+  if (act) {
+    long long t = v;
+    ow = (int)(t % cg.Wo); t /= cg.Wo;
+    oh = (int)(t % cg.Ho); t /= cg.Ho;
+    od = (int)(t % cg.Do); t /= cg.Do;
+    b = (int)t;
+  }
+  float acc[CO_T];
+#pragma unroll
+  for (int i = 0; i < CO_T; ++i) acc[i] = 0.f;
+
+  const bool vec4 = (cg.Cin % 4 == 0) && (cg.xp % 4 == 0) && (((uintptr_t)x & 15) == 0);
+  const long long xb = (long long)b * cg.Di * cg.Hi * cg.Wi;
+
+  for (int ci0 = 0; ci0 < cg.Cin; ci0 += kCiT) {
+    const int nci = min(kCiT, cg.Cin - ci0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < taps * kCiT * CO_T; i += kGT) {
+      const int co = i % CO_T, ci = (i / CO_T) % kCiT, t = i / (CO_T * kCiT);
+      float val = 0.f;
+      if (ci < nci && co0 + co < cg.Cout) {
+        int tw = t;
+        if (cg.flip) tw = taps - 1 - t;
+        val = w[(long long)tw * cg.wtap + (long long)(ci0 + ci) * cg.sw_in + (long long)(co0 + co) * cg.sw_out];
+      }
+      ws[i] = val;
+    }
+    __syncthreads();
+    if (!act) continue;
+    for (int t = 0; t < taps; ++t) {
+      const int tk = t % cg.k, th = (t / cg.k) % cg.k, td = t / (cg.k * cg.k);
+      int id, ih, iw;
+      if (cg.mode == CONV_S1) {
+        id = od + td - cg.pad; ih = oh + th - cg.pad; iw = ow + tk - cg.pad;
+      } else if (cg.mode == CONV_DOWN) {
+        id = 2 * od + td; ih = 2 * oh + th; iw = 2 * ow + tk;
+      } else {
+        id = od - td; ih = oh - th; iw = ow - tk;
+        if ((id | ih | iw) < 0 || ((id | ih | iw) & 1)) continue;
+        id >>= 1; ih >>= 1; iw >>= 1;
+      }
+      if (id < 0 || id >= cg.Di || ih < 0 || ih >= cg.Hi || iw < 0 || iw >= cg.Wi) continue;
+      const float* xp = x + ((xb + ((long long)id * cg.Hi + ih) * cg.Wi + iw) * cg.xp + ci0);
+      const float* wt = ws + t * kCiT * CO_T;
+      if (vec4) {
+        for (int ci = 0; ci < nci; ci += 4) {
+          const float4 xv = *reinterpret_cast<const float4*>(xp + ci);
+          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(xs[u], wt[(ci + u) * CO_T + co], acc[co]);
+          }
+        }
+      } else {
+        for (int ci = 0; ci < nci; ++ci) {
+          const float xv = xp[ci];
+#pragma unroll
+          for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(xv, wt[ci * CO_T + co], acc[co]);
+        }
+      }
+    }
+  }
+
+  // epilogue: bias, activation, accumulate, store, optional GN chunk stats and GAP sums
+  float s0 = 0.f, s1 = 0.f;
+  if (act) {
+    float* yp = y + v * cg.yp + co0;
+#pragma unroll
+    for (int co = 0; co < CO_T; ++co) {
+      if (co0 + co < cg.Cout) {
+        float r = acc[co] + (bias ? bias[co0 + co] : 0.f);
+        if (cg.act == 1) r = 1.f / (1.f + expf(-r));
+        if (cg.accumulate) r += yp[co];
+        yp[co] = r;
+        acc[co] = r;
+        s0 += r;
+        s1 += r * r;
+      } else {
+        acc[co] = 0.f;
+      }
+    }
+  }
+  if (stats != nullptr) {
+    // chunk of a voxel (voxel-aligned chunks guaranteed by the host wrapper)
+    const long long S = (long long)cg.Do * cg.Ho * cg.Wo;
+    const int chunk = act ? (int)(b * cg.groups + ((v - (long long)b * S) / (S / cg.groups))) : -1;
+    const int c0 = __shfl_sync(0xffffffffu, chunk, 0);
+    const bool uni = __all_sync(0xffffffffu, chunk == c0 || chunk < 0);
+    if (uni) {
+      const float a0 = warp_sum(s0), a1 = warp_sum(s1);
+      const int cc = __reduce_max_sync(0xffffffffu, chunk);
+      if ((threadIdx.x & 31) == 0 && cc >= 0) {
+        atomicAdd(&stats[2 * cc], (double)a0);
+        atomicAdd(&stats[2 * cc + 1], (double)a1);
+      }
+    } else if (act) {
+      atomicAdd(&stats[2 * chunk], (double)s0);
+      atomicAdd(&stats[2 * chunk + 1], (double)s1);
+    }
+  }
+  if (gap != nullptr) {
+    // per-(b, co) sums over voxels: warp reduce when the warp sits in one sample
+    const int b0 = __shfl_sync(0xffffffffu, b, 0);
+    const bool uni = __all_sync(0xffffffffu, b == b0 || !act);
+#pragma unroll
+    for (int co = 0; co < CO_T; ++co) {
+      if (co0 + co < cg.Cout) {
+        if (uni) {
+          const float a = warp_sum(act ? acc[co] : 0.f);
+          if ((threadIdx.x & 31) == 0) atomicAdd(&gap[(long long)b0 * cg.Cout + co0 + co], a);
+        } else if (act) {
+          atomicAdd(&gap[(long long)b * cg.Cout + co0 + co], acc[co]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient, outer-product form.  CTA tile 32(a) x 32(b); K = voxels, staged 32 at a time.
+constexpr int kWT = 32, kWK = 32;
+
+__global__ void __launch_bounds__(256)
+    conv_wgrad_kernel(WgradGeom wg, const float* __restrict__ big, const float* __restrict__ small,
+                      float* __restrict__ dw) {
+  __shared__ float As[kWK][kWT + 1];
+  __shared__ float Bs[kWK][kWT + 1];
+  const int nbt = (wg.nB + kWT - 1) / kWT;
+  const int a0 = (blockIdx.x / nbt) * kWT, b0 = (blockIdx.x % nbt) * kWT;
+  const int t = blockIdx.y;
+  const int tk = t % wg.k, th = (t / wg.k) % wg.k, td = t / (wg.k * wg.k);
+  const long long nvox = (long long)wg.B * wg.Ds * wg.Hs * wg.Ws;
+  const long long per = (nvox + gridDim.z - 1) / gridDim.z;
+  const long long vbeg = (long long)blockIdx.z * per, vend = min(nvox, vbeg + per);
+  const int ta = threadIdx.x / 16, tb = threadIdx.x % 16;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (long long v0 = vbeg; v0 < vend; v0 += kWK) {
+    __syncthreads();
+    // stage: 32 voxels x 32 channels for each operand; thread -> (voxel = tid/8, 4 channels = (tid%8)*4)
+    {
+      const int vl = threadIdx.x / 8, c4 = (threadIdx.x % 8) * 4;
+      const long long v = v0 + vl;
+      float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (v < vend) {
+        long long q = v;
+        const int ow = (int)(q % wg.Ws); q /= wg.Ws;
+        const int oh = (int)(q % wg.Hs); q /= wg.Hs;
+        const int od = (int)(q % wg.Ds); q /= wg.Ds;
+        const int n = (int)q;
+        const int id = wg.s * od + td - wg.pad, ih = wg.s * oh + th - wg.pad, iw = wg.s * ow + tk - wg.pad;
+        if (id >= 0 && id < wg.Db && ih >= 0 && ih < wg.Hb && iw >= 0 && iw < wg.Wb) {
+          const float* bp = big + ((((long long)n * wg.Db + id) * wg.Hb + ih) * wg.Wb + iw) * wg.bigp;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (a0 + c4 + u < wg.nA) av[u] = bp[a0 + c4 + u];
+          const float* sp = small + v * wg.smallp;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (b0 + c4 + u < wg.nB) bv[u] = sp[b0 + c4 + u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        As[vl][c4 + u] = av[u];
+        Bs[vl][c4 + u] = bv[u];
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < kWK; ++kk) {
+      const float a_0 = As[kk][ta], a_1 = As[kk][ta + 16];
+      const float b_0 = Bs[kk][tb], b_1 = Bs[kk][tb + 16];
+      acc[0][0] = fmaf(a_0, b_0, acc[0][0]);
+      acc[0][1] = fmaf(a_0, b_1, acc[0][1]);
+      acc[1][0] = fmaf(a_1, b_0, acc[1][0]);
+      acc[1][1] = fmaf(a_1, b_1, acc[1][1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int a = a0 + ta + 16 * i, b = b0 + tb + 16 * j;
+      if (a < wg.nA && b < wg.nB) atomicAdd(&dw[(long long)t * wg.nA * wg.nB + (long long)a * wg.nB + b], acc[i][j]);
+    }
+}
+
+// per-channel column sums:  out[c] (+)= sum_n x[n][c]      (bias gradients, GAP)
+__global__ void __launch_bounds__(256)
+    colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long N, int C, long long pitch,
+                  long long rows_per_cta) {
+  extern __shared__ float sm[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+  // thread -> fixed channel when C | 256, else strided elements
+  const long long e0 = r0 * C, e1 = r1 * C;
+  if (256 % C == 0 && pitch == C) {
+    float a = 0.f;
+    for (long long e = e0 + threadIdx.x; e < e1; e += 256) a += x[e];
+    atomicAdd(&sm[threadIdx.x % C], a);
+  } else {
+    for (long long r = r0; r < r1; ++r)
+      for (int c = threadIdx.x; c < C; c += 256) sm[c] += x[r * pitch + c];  // thread-private columns
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[i], sm[i]);
+}
+
+int launch_conv_gather(const ConvGeom& cg, const float* x, const float* w, const float* bias, float* y,
+                       double* stats, float* gap, cudaStream_t s) {
+  const long long nvox = (long long)cg.B * cg.Do * cg.Ho * cg.Wo;
+  const int taps = cg.k * cg.k * cg.k;
+  const unsigned gx = (unsigned)((nvox + kGT - 1) / kGT);
+#define LAUNCH(CO)                                                                                         \
+  do {                                                                                                     \
+    const size_t smem = sizeof(float) * taps * kCiT * CO;                                                  \
+    dim3 grid(gx, (cg.Cout + CO - 1) / CO, 1);                                                             \
+    conv_gather_kernel<CO><<<grid, kGT, smem, s>>>(cg, x, w, bias, y, stats, gap);                         \
+  } while (0)
+  if (cg.Cout >= 16) LAUNCH(16);
+  else if (cg.Cout > 4) LAUNCH(8);
+  else LAUNCH(4);
+#undef LAUNCH
+  B3D_LAUNCH_CHECK("conv_gather");
+  return B3D_OK;
+}
+
+int launch_conv_wgrad(const WgradGeom& wg, const float* big, const float* small, float* dw, cudaStream_t s) {
+  const int taps = wg.k * wg.k * wg.k;
+  const int tiles = ((wg.nA + kWT - 1) / kWT) * ((wg.nB + kWT - 1) / kWT);
+  const long long nvox = (long long)wg.B * wg.Ds * wg.Hs * wg.Ws;
+  int split = (8 * sm_count() + tiles * taps - 1) / (tiles * taps);
+  const long long maxsplit = (nvox + 255) / 256;
+  if (split > maxsplit) split = (int)maxsplit;
+  if (split < 1) split = 1;
+  B3D_TRY(cuda_ok(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)taps * wg.nA * wg.nB, s), "memset dw"));
+  conv_wgrad_kernel<<<dim3(tiles, taps, split), 256, 0, s>>>(wg, big, small, dw);
+  B3D_LAUNCH_CHECK("conv_wgrad");
+  return B3D_OK;
+}
+
+int launch_colsum(const float* x, float* out, long long N, int C, long long pitch, bool zero, cudaStream_t s) {
+  if (zero) B3D_TRY(cuda_ok(cudaMemsetAsync(out, 0, sizeof(float) * C, s), "memset colsum"));
+  long long rows_per = (N + 4LL * sm_count() - 1) / (4LL * sm_count());
+  if (rows_per < 64) rows_per = 64;
+  const unsigned grid = (unsigned)((N + rows_per - 1) / rows_per);
+  colsum_kernel<<<grid, 256, sizeof(float) * C, s>>>(x, out, N, C, pitch, rows_per);
+  B3D_LAUNCH_CHECK("colsum");
+  return B3D_OK;
+}
+
+}  // namespace b3d

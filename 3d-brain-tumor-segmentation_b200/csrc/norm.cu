@@ -1,0 +1,389 @@
+// b3d — GroupNormalization (reference layers/group_norm.py:83-124) in its channels_last form:
+// "group" g of sample b is the g-th contiguous 1/G chunk of the sample's flat NDHWC buffer
+// (SURVEY F1); the affine index of flat element e is  j = g*(C/G) + (e mod C) mod (C/G).
+// HBM-bound: every kernel streams whole chunks with 128-bit accesses; reductions are
+// per-thread fp32 -> warp shuffle -> block -> one fp64 atomic per CTA.
+//
+//   stats[b][g] = (sum x, sum x^2)  fp64   (also produced by the conv epilogues)
+//   algorithmic bytes/elem: stats 4, apply 8, bwd_reduce 8, bwd_apply 12.
+#include "common.cuh"
+
+namespace b3d {
+
+constexpr int kThreads = 256;
+constexpr int kIter = 8;  // float4 per thread per CTA
+
+struct ChunkGeom {
+  long long L;     // elements per chunk
+  int C, cg, G;    // channels, channels per group, groups
+  float inv_L;
+};
+
+__device__ __forceinline__ void chunk_moments(const double* __restrict__ stats, int chunk, double inv_L,
+                                              float eps, float& mean, float& rstd) {
+  const double s0 = stats[2 * chunk], s1 = stats[2 * chunk + 1];
+  const double m = s0 * inv_L;
+  double var = s1 * inv_L - m * m;
+  var = var < 0.0 ? 0.0 : var;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats,
+                                                           long long L) {
+  const int chunk = blockIdx.y;
+  const float* xc = x + (long long)chunk * L;
+  const long long base = (long long)blockIdx.x * (kThreads * kIter * VEC);
+  float s[2] = {0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < kIter; ++k) {
+    const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
+    if (e < L) {
+      if (VEC == 4) {
+        const float4 v = ld_stream(reinterpret_cast<const float4*>(xc + e));
+        s[0] += (v.x + v.y) + (v.z + v.w);
+        s[1] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      } else {
+        const float v = xc[e];
+        s[0] += v;
+        s[1] += v * v;
+      }
+    }
+  }
+  __shared__ double red[64];
+  double d[2] = {(double)s[0], (double)s[1]};
+  block_sum<2, double>(d, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&stats[2 * chunk], d[0]);
+    atomicAdd(&stats[2 * chunk + 1], d[1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int VEC, bool RELU>
+__global__ void __launch_bounds__(kThreads)
+    gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* __restrict__ y, ChunkGeom gm, float eps) {
+  const int chunk = blockIdx.y;
+  const int g = chunk % gm.G;
+  float mean, rstd;
+  chunk_moments(stats, chunk, 1.0 / (double)gm.L, eps, mean, rstd);
+  const long long off = (long long)chunk * gm.L;
+  const long long base = (long long)blockIdx.x * (kThreads * kIter * VEC);
+  const int jbase = g * gm.cg;
+  const long long goff = (long long)g * gm.L;
+#pragma unroll
+  for (int k = 0; k < kIter; ++k) {
+    const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
+    if (e < gm.L) {
+      const int c0 = (int)((goff + e) % gm.cg);
+      if (VEC == 4) {
+        const float4 v = ld_stream(reinterpret_cast<const float4*>(x + off + e));
+        float in[4] = {v.x, v.y, v.z, v.w}, o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int j = c0 + i;
+          j = j >= gm.cg ? j % gm.cg : j;
+          float t = (in[i] - mean) * rstd * __ldg(gamma + jbase + j) + __ldg(beta + jbase + j);
+          o[i] = RELU ? fmaxf(t, 0.f) : t;
+        }
+        st_stream(reinterpret_cast<float4*>(y + off + e), make_float4(o[0], o[1], o[2], o[3]));
+      } else {
+        float t = (x[off + e] - mean) * rstd * __ldg(gamma + jbase + c0) + __ldg(beta + jbase + c0);
+        y[off + e] = RELU ? fmaxf(t, 0.f) : t;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward pass 1: per chunk  S1 = sum h, S2 = sum h*xhat  (h = dy*[y>0]*gamma_j) -> csum fp64;
+//                  per affine index  dgamma_j += sum dy*[y>0]*xhat,  dbeta_j += sum dy*[y>0].
+// Fast path needs cg | (kThreads*VEC) so that a thread's affine indices are loop-invariant.
+template <int VEC, bool RELU>
+__global__ void __launch_bounds__(kThreads)
+    gn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, const double* __restrict__ stats,
+                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ csum,
+                         ChunkGeom gm, float eps) {
+  extern __shared__ float sm[];  // [2*cg] + reduction scratch
+  float* sg = sm;
+  float* sb = sm + gm.cg;
+  for (int i = threadIdx.x; i < 2 * gm.cg; i += kThreads) sm[i] = 0.f;
+  __syncthreads();
+  const int chunk = blockIdx.y;
+  const int g = chunk % gm.G;
+  float mean, rstd;
+  chunk_moments(stats, chunk, 1.0 / (double)gm.L, eps, mean, rstd);
+  const long long off = (long long)chunk * gm.L;
+  const long long base = (long long)blockIdx.x * (kThreads * kIter * VEC);
+  const int jbase = g * gm.cg;
+  const long long goff = (long long)g * gm.L;
+  const bool invariant = ((kThreads * VEC) % gm.cg) == 0;
+  float s1 = 0.f, s2 = 0.f;
+  float ag[VEC], ab[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) ag[i] = ab[i] = 0.f;
+  int c_first = -1;
+#pragma unroll
+  for (int k = 0; k < kIter; ++k) {
+    const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
+    if (e < gm.L) {
+      const int c0 = (int)((goff + e) % gm.cg);
+      if (c_first < 0) c_first = c0;
+      float dv[4], xv[4];
+      if (VEC == 4) {
+        const float4 a = ld_stream(reinterpret_cast<const float4*>(dy + off + e));
+        const float4 b = ld_stream(reinterpret_cast<const float4*>(x + off + e));
+        dv[0] = a.x, dv[1] = a.y, dv[2] = a.z, dv[3] = a.w;
+        xv[0] = b.x, xv[1] = b.y, xv[2] = b.z, xv[3] = b.w;
+      } else {
+        dv[0] = dy[off + e];
+        xv[0] = x[off + e];
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        int j = c0 + i;
+        j = j >= gm.cg ? j % gm.cg : j;
+        const float ga = __ldg(gamma + jbase + j);
+        const float xh = (xv[i] - mean) * rstd;
+        float gq = dv[i];
+        if (RELU) gq = (xh * ga + __ldg(beta + jbase + j)) > 0.f ? gq : 0.f;
+        const float h = gq * ga;
+        s1 += h;
+        s2 += h * xh;
+        if (invariant) {
+          ag[i] += gq * xh;
+          ab[i] += gq;
+        } else {
+          atomicAdd(&sg[j], gq * xh);
+          atomicAdd(&sb[j], gq);
+        }
+      }
+    }
+  }
+  if (invariant && c_first >= 0) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int j = (c_first + i) % gm.cg;
+      atomicAdd(&sg[j], ag[i]);
+      atomicAdd(&sb[j], ab[i]);
+    }
+  }
+  __shared__ double red[64];
+  double d[2] = {(double)s1, (double)s2};
+  block_sum<2, double>(d, red);  // contains __syncthreads -> smem atomics above are complete
+  if (threadIdx.x == 0) {
+    atomicAdd(&csum[2 * chunk], d[0]);
+    atomicAdd(&csum[2 * chunk + 1], d[1]);
+  }
+  for (int j = threadIdx.x; j < gm.cg; j += kThreads) {
+    atomicAdd(&dgamma[jbase + j], sg[j]);
+    atomicAdd(&dbeta[jbase + j], sb[j]);
+  }
+}
+
+// backward pass 2: dx = rstd * (h - S1/L - xhat * S2/L)
+template <int VEC, bool RELU>
+__global__ void __launch_bounds__(kThreads)
+    gn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const double* __restrict__ stats,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        const double* __restrict__ csum, float* __restrict__ dx, ChunkGeom gm, float eps) {
+  const int chunk = blockIdx.y;
+  const int g = chunk % gm.G;
+  float mean, rstd;
+  chunk_moments(stats, chunk, 1.0 / (double)gm.L, eps, mean, rstd);
+  const float m1 = (float)(csum[2 * chunk] / (double)gm.L);
+  const float m2 = (float)(csum[2 * chunk + 1] / (double)gm.L);
+  const long long off = (long long)chunk * gm.L;
+  const long long base = (long long)blockIdx.x * (kThreads * kIter * VEC);
+  const int jbase = g * gm.cg;
+  const long long goff = (long long)g * gm.L;
+#pragma unroll
+  for (int k = 0; k < kIter; ++k) {
+    const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
+    if (e < gm.L) {
+      const int c0 = (int)((goff + e) % gm.cg);
+      float dv[4], xv[4], o[4];
+      if (VEC == 4) {
+        const float4 a = ld_stream(reinterpret_cast<const float4*>(dy + off + e));
+        const float4 b = ld_stream(reinterpret_cast<const float4*>(x + off + e));
+        dv[0] = a.x, dv[1] = a.y, dv[2] = a.z, dv[3] = a.w;
+        xv[0] = b.x, xv[1] = b.y, xv[2] = b.z, xv[3] = b.w;
+      } else {
+        dv[0] = dy[off + e];
+        xv[0] = x[off + e];
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        int j = c0 + i;
+        j = j >= gm.cg ? j % gm.cg : j;
+        const float ga = __ldg(gamma + jbase + j);
+        const float xh = (xv[i] - mean) * rstd;
+        float gq = dv[i];
+        if (RELU) gq = (xh * ga + __ldg(beta + jbase + j)) > 0.f ? gq : 0.f;
+        o[i] = rstd * (gq * ga - m1 - xh * m2);
+      }
+      if (VEC == 4)
+        st_stream(reinterpret_cast<float4*>(dx + off + e), make_float4(o[0], o[1], o[2], o[3]));
+      else
+        dx[off + e] = o[0];
+    }
+  }
+}
+
+static int gn_geom(const TView& x, int groups, ChunkGeom* gm, int* nchunks) {
+  const int C = (int)x.shape[x.ndim - 1];
+  // reference group_norm.py:51-59
+  B3D_REQUIRE(groups >= 1 && C >= groups, B3D_ERR_SHAPE,
+              "Number of groups (%d) cannot be more than the number of channels (%d).", groups, C);
+  B3D_REQUIRE(C % groups == 0, B3D_ERR_SHAPE,
+              "Number of groups (%d) must be a multiple of the number of channels (%d).", groups, C);
+  const long long B = x.shape[0];
+  const long long ns = x.numel / B;
+  gm->L = ns / groups;
+  gm->C = C;
+  gm->cg = C / groups;
+  gm->G = groups;
+  gm->inv_L = 1.0f / (float)gm->L;
+  *nchunks = (int)(B * groups);
+  B3D_REQUIRE(*nchunks <= 65535, B3D_ERR_SHAPE, "batch*groups too large");
+  return B3D_OK;
+}
+
+static inline dim3 gn_grid(const ChunkGeom& gm, int nchunks, int vec) {
+  const long long per = (long long)kThreads * kIter * vec;
+  return dim3((unsigned)((gm.L + per - 1) / per), (unsigned)nchunks, 1);
+}
+
+static int check_stats(const DLTensor* t, int nchunks, const char* name, TView* v) {
+  B3D_TRY(view(t, DT_F64, -1, false, name, v));
+  B3D_REQUIRE(v->numel == 2LL * nchunks, B3D_ERR_SHAPE, "%s: expected %d fp64 values, got %lld", name,
+              2 * nchunks, (long long)v->numel);
+  return B3D_OK;
+}
+
+static int check_affine(const DLTensor* t, int C, const char* name, TView* v) {
+  B3D_TRY(view(t, DT_F32, 1, false, name, v));
+  B3D_REQUIRE(v->numel == C, B3D_ERR_SHAPE, "%s: expected %d values, got %lld", name, C, (long long)v->numel);
+  return B3D_OK;
+}
+
+}  // namespace b3d
+
+using namespace b3d;
+
+extern "C" int b3d_gn_stats(const DLTensor* x_, DLTensor* stats_, int groups, void* stream) {
+  TView x, st;
+  ChunkGeom gm;
+  int nchunks;
+  B3D_TRY(view(x_, DT_F32, -1, false, "x", &x));
+  B3D_TRY(gn_geom(x, groups, &gm, &nchunks));
+  B3D_TRY(check_stats(stats_, nchunks, "stats", &st));
+  cudaStream_t s = (cudaStream_t)stream;
+  B3D_TRY(cuda_ok(cudaMemsetAsync(st.p, 0, sizeof(double) * 2 * nchunks, s), "memset stats"));
+  const bool v4 = (gm.L % 4 == 0) && (((uintptr_t)x.p & 15) == 0);
+  if (v4)
+    gn_stats_kernel<4><<<gn_grid(gm, nchunks, 4), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L);
+  else
+    gn_stats_kernel<1><<<gn_grid(gm, nchunks, 1), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L);
+  B3D_LAUNCH_CHECK("gn_stats");
+  return B3D_OK;
+}
+
+extern "C" int b3d_gn_apply(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
+                            const DLTensor* beta_, DLTensor* y_, int groups, float eps, int relu, void* stream) {
+  TView x, y, st, ga, be;
+  ChunkGeom gm;
+  int nchunks;
+  B3D_TRY(view(x_, DT_F32, -1, false, "x", &x));
+  B3D_TRY(view(y_, DT_F32, -1, false, "y", &y));
+  B3D_REQUIRE(x.numel == y.numel, B3D_ERR_SHAPE, "gn_apply: x/y size mismatch");
+  B3D_TRY(gn_geom(x, groups, &gm, &nchunks));
+  B3D_TRY(check_stats(stats_, nchunks, "stats", &st));
+  B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
+  B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool v4 = (gm.L % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)y.p) & 15) == 0);
+#define LAUNCH(V, R)                                                                                     \
+  gn_apply_kernel<V, R><<<gn_grid(gm, nchunks, V), kThreads, 0, s>>>(                                    \
+      (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps)
+  if (v4) {
+    if (relu) LAUNCH(4, true); else LAUNCH(4, false);
+  } else {
+    if (relu) LAUNCH(1, true); else LAUNCH(1, false);
+  }
+#undef LAUNCH
+  B3D_LAUNCH_CHECK("gn_apply");
+  return B3D_OK;
+}
+
+extern "C" int b3d_gn_bwd_reduce(const DLTensor* dy_, const DLTensor* x_, const DLTensor* stats_,
+                                 const DLTensor* gamma_, const DLTensor* beta_, DLTensor* dgamma_,
+                                 DLTensor* dbeta_, DLTensor* csum_, int groups, float eps, int relu, void* stream) {
+  TView x, dy, st, ga, be, dga, dbe, cs;
+  ChunkGeom gm;
+  int nchunks;
+  B3D_TRY(view(x_, DT_F32, -1, false, "x", &x));
+  B3D_TRY(view(dy_, DT_F32, -1, false, "dy", &dy));
+  B3D_REQUIRE(x.numel == dy.numel, B3D_ERR_SHAPE, "gn_bwd_reduce: x/dy size mismatch");
+  B3D_TRY(gn_geom(x, groups, &gm, &nchunks));
+  B3D_TRY(check_stats(stats_, nchunks, "stats", &st));
+  B3D_TRY(check_stats(csum_, nchunks, "csum", &cs));
+  B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
+  B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
+  B3D_TRY(check_affine(dgamma_, gm.C, "dgamma", &dga));
+  B3D_TRY(check_affine(dbeta_, gm.C, "dbeta", &dbe));
+  cudaStream_t s = (cudaStream_t)stream;
+  B3D_TRY(cuda_ok(cudaMemsetAsync(cs.p, 0, sizeof(double) * 2 * nchunks, s), "memset csum"));
+  B3D_TRY(cuda_ok(cudaMemsetAsync(dga.p, 0, sizeof(float) * gm.C, s), "memset dgamma"));
+  B3D_TRY(cuda_ok(cudaMemsetAsync(dbe.p, 0, sizeof(float) * gm.C, s), "memset dbeta"));
+  const bool v4 = (gm.L % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)dy.p) & 15) == 0);
+  const size_t smem = sizeof(float) * 2 * gm.cg;
+#define LAUNCH(V, R)                                                                                       \
+  gn_bwd_reduce_kernel<V, R><<<gn_grid(gm, nchunks, V), kThreads, smem, s>>>(                              \
+      (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, \
+      (float*)dga.p, (float*)dbe.p, (double*)cs.p, gm, eps)
+  if (v4) {
+    if (relu) LAUNCH(4, true); else LAUNCH(4, false);
+  } else {
+    if (relu) LAUNCH(1, true); else LAUNCH(1, false);
+  }
+#undef LAUNCH
+  B3D_LAUNCH_CHECK("gn_bwd_reduce");
+  return B3D_OK;
+}
+
+extern "C" int b3d_gn_bwd_apply(const DLTensor* dy_, const DLTensor* x_, const DLTensor* stats_,
+                                const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* csum_,
+                                DLTensor* dx_, int groups, float eps, int relu, void* stream) {
+  TView x, dy, dx, st, ga, be, cs;
+  ChunkGeom gm;
+  int nchunks;
+  B3D_TRY(view(x_, DT_F32, -1, false, "x", &x));
+  B3D_TRY(view(dy_, DT_F32, -1, false, "dy", &dy));
+  B3D_TRY(view(dx_, DT_F32, -1, false, "dx", &dx));
+  B3D_REQUIRE(x.numel == dy.numel && x.numel == dx.numel, B3D_ERR_SHAPE, "gn_bwd_apply: size mismatch");
+  B3D_TRY(gn_geom(x, groups, &gm, &nchunks));
+  B3D_TRY(check_stats(stats_, nchunks, "stats", &st));
+  B3D_TRY(check_stats(csum_, nchunks, "csum", &cs));
+  B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
+  B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool v4 =
+      (gm.L % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)dy.p | (uintptr_t)dx.p) & 15) == 0);
+#define LAUNCH(V, R)                                                                                       \
+  gn_bwd_apply_kernel<V, R><<<gn_grid(gm, nchunks, V), kThreads, 0, s>>>(                                  \
+      (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, \
+      (const double*)cs.p, (float*)dx.p, gm, eps)
+  if (v4) {
+    if (relu) LAUNCH(4, true); else LAUNCH(4, false);
+  } else {
+    if (relu) LAUNCH(1, true); else LAUNCH(1, false);
+  }
+#undef LAUNCH
+  B3D_LAUNCH_CHECK("gn_bwd_apply");
+  return B3D_OK;
+}

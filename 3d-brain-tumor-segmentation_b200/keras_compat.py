@@ -1,0 +1,230 @@
+"""Host-side stand-in for the small part of the Keras `Layer` protocol the reference's hot path relies on:
+lazy `build` on first call, `trainable_variables` / `losses` collected in attribute order,
+`get_config()`, Keras initialisers and `l2` regularisers.
+Weights are torch CUDA tensors in Keras layouts; nothing here does arithmetic on the hot path.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+
+_GEN = torch.Generator().manual_seed(20260117)
+
+
+def set_seed(seed: int):
+    _GEN.manual_seed(seed)
+
+
+def _trunc_normal(shape, std):
+    # Keras he_normal / glorot_normal: truncated normal (|z| <= 2), stddev / 0.87962566 (App. B)
+    t = torch.empty(shape, dtype=torch.float32)
+    torch.nn.init.trunc_normal_(t, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=_GEN)
+    return t * (std / 0.87962566103423978)
+
+
+def _fans(shape):
+    if len(shape) == 2:
+        return shape[0], shape[1]
+    rf = 1
+    for s in shape[:-2]:
+        rf *= s
+    return shape[-2] * rf, shape[-1] * rf
+
+
+def make_initial_value(shape, initializer):
+    shape = tuple(int(s) for s in shape)
+    if initializer in (None, "zeros"):
+        return torch.zeros(shape)
+    if initializer == "ones":
+        return torch.ones(shape)
+    fan_in, fan_out = _fans(shape)
+    if initializer == "he_normal":
+        return _trunc_normal(shape, math.sqrt(2.0 / fan_in))
+    if initializer == "glorot_normal":
+        return _trunc_normal(shape, math.sqrt(2.0 / (fan_in + fan_out)))
+    if initializer == "glorot_uniform":
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        return (torch.rand(shape, generator=_GEN) * 2 - 1) * lim
+    raise ValueError(f"unknown initializer {initializer!r}")
+
+
+class L2:
+    """tf.keras.regularizers.l2(l): l * sum(w^2)."""
+
+    def __init__(self, l=0.01):
+        self.l = float(l)
+
+
+class Variable:
+    """A named trainable tensor + its regulariser (what Keras' add_weight returns)."""
+    __slots__ = ("name", "tensor", "regularizer")
+
+    def __init__(self, name, tensor, regularizer):
+        self.name, self.tensor, self.regularizer = name, tensor, regularizer
+
+
+class Layer:
+    def __init__(self, name: Optional[str] = None, **kwargs):
+        self.name = name or type(self).__name__.lower()
+        self.built = False
+        self._vars: List[Variable] = []
+
+    # ---- Keras protocol
+    def __call__(self, inputs, *args, **kwargs):
+        if not self.built:
+            self.build(_shape_of(inputs), _device_of(inputs))
+            self.built = True
+        return self.call(inputs, *args, **kwargs)
+
+    def build(self, input_shape, device):
+        pass
+
+    def call(self, inputs, training=None):
+        raise NotImplementedError
+
+    def add_weight(self, name, shape, initializer, device, regularizer: Optional[L2] = None):
+        t = make_initial_value(shape, initializer).to(device).requires_grad_(True)
+        self._vars.append(Variable(name, t, regularizer))
+        return t
+
+    def get_config(self):
+        return {"name": self.name, "trainable": True, "dtype": "float32"}
+
+    # ---- tracking (attribute order; recurses into nested lists like Keras' ListWrapper)
+    def _sublayers(self) -> List["Layer"]:
+        out: List[Layer] = []
+
+        def walk(v):
+            if isinstance(v, Layer):
+                out.append(v)
+            elif isinstance(v, (list, tuple)):
+                for u in v:
+                    walk(u)
+
+        for k, v in self.__dict__.items():
+            if not k.startswith("_"):
+                walk(v)
+        return out
+
+    def _all_layers(self) -> List["Layer"]:
+        res = [self]
+        for l in self._sublayers():
+            res += l._all_layers()
+        return res
+
+    def variables(self) -> List[Variable]:
+        return [v for l in self._all_layers() for v in l._vars]
+
+    @property
+    def trainable_variables(self) -> List[torch.Tensor]:
+        return [v.tensor for v in self.variables()]
+
+
+def _shape_of(x):
+    if isinstance(x, torch.Tensor):
+        return list(x.shape)
+    if isinstance(x, (list, tuple)):
+        return [_shape_of(v) for v in x]
+    return None
+
+
+def _device_of(x):
+    if isinstance(x, torch.Tensor):
+        return x.device
+    if isinstance(x, (list, tuple)):
+        for v in x:
+            d = _device_of(v)
+            if d is not None:
+                return d
+    return None
+
+
+# ----------------------------------------------------------------------------------------------
+# The Keras built-ins the reference composes, as thin weight holders over b3d kernels.
+# ----------------------------------------------------------------------------------------------
+from . import ops  # noqa: E402
+
+
+def _require_channels_last(data_format):
+    if data_format != "channels_last":
+        raise NotImplementedError(
+            "b3d: only data_format='channels_last' (the reference's CPU/oracle layout) is built so far; "
+            "channels_first is listed under SURVEY §8(f).")
+
+
+class Conv3D(Layer):
+    """tf.keras.layers.Conv3D(padding='same'); kernel (k,k,k,Cin,Cout)."""
+
+    def __init__(self, filters, kernel_size, strides=1, padding="same", data_format="channels_last",
+                 activation=None, use_bias=True, kernel_initializer="glorot_uniform", kernel_regularizer=None,
+                 **kw):
+        super().__init__(**kw)
+        _require_channels_last(data_format)
+        if padding != "same":
+            raise NotImplementedError("b3d Conv3D: only padding='same'")
+        if activation not in (None, "sigmoid"):
+            raise NotImplementedError("b3d Conv3D: activation must be None or 'sigmoid'")
+        self.filters, self.kernel_size, self.strides = filters, kernel_size, strides
+        self.activation, self.use_bias = activation, use_bias
+        self.kernel_initializer, self.kernel_regularizer = kernel_initializer, kernel_regularizer
+        self.kernel = self.bias = None
+
+    def build(self, input_shape, device):
+        k = self.kernel_size
+        self.kernel = self.add_weight("kernel", (k, k, k, input_shape[-1], self.filters), self.kernel_initializer,
+                                      device, self.kernel_regularizer)
+        if self.use_bias:
+            self.bias = self.add_weight("bias", (self.filters,), "zeros", device)
+        self.built = True
+
+    def call(self, x, training=None, gn_groups=0, want_gap=False, aux=False):
+        y, stats, gap = ops.conv3d(x, self.kernel, self.bias, self.strides, False,
+                                   1 if self.activation == "sigmoid" else 0, gn_groups, want_gap)
+        return (y, stats, gap) if aux else y
+
+
+class Conv3DTranspose(Layer):
+    """tf.keras.layers.Conv3DTranspose(kernel 3, strides 2, padding 'same'); kernel (3,3,3,Cout,Cin)."""
+
+    def __init__(self, filters, kernel_size=3, strides=2, padding="same", data_format="channels_last",
+                 kernel_initializer="glorot_uniform", **kw):
+        super().__init__(**kw)
+        _require_channels_last(data_format)
+        if (kernel_size, strides, padding) != (3, 2, "same"):
+            raise NotImplementedError("b3d Conv3DTranspose: only kernel_size=3, strides=2, padding='same'")
+        self.filters, self.kernel_initializer = filters, kernel_initializer
+        self.kernel = self.bias = None
+
+    def build(self, input_shape, device):
+        self.kernel = self.add_weight("kernel", (3, 3, 3, self.filters, input_shape[-1]), self.kernel_initializer,
+                                      device)
+        self.bias = self.add_weight("bias", (self.filters,), "zeros", device)
+        self.built = True
+
+    def call(self, x, training=None, gn_groups=0, aux=False):
+        y, stats, _ = ops.conv3d(x, self.kernel, self.bias, 2, True, 0, gn_groups, False)
+        return (y, stats) if aux else y
+
+
+class Dense(Layer):
+    def __init__(self, units, activation=None, use_bias=True, kernel_initializer="glorot_uniform",
+                 kernel_regularizer=None, **kw):
+        super().__init__(**kw)
+        if activation not in (None, "relu"):
+            raise NotImplementedError("b3d Dense.call: activation must be None or 'relu' "
+                                      "(the SE denses are fused into the ResnetBlock epilogue)")
+        self.units, self.activation, self.use_bias = units, activation, use_bias
+        self.kernel_initializer, self.kernel_regularizer = kernel_initializer, kernel_regularizer
+        self.kernel = self.bias = None
+
+    def build(self, input_shape, device):
+        self.kernel = self.add_weight("kernel", (input_shape[-1], self.units), self.kernel_initializer, device,
+                                      self.kernel_regularizer)
+        if self.use_bias:
+            self.bias = self.add_weight("bias", (self.units,), "zeros", device)
+        self.built = True
+
+    def call(self, x, training=None):
+        return ops.dense(x, self.kernel, self.bias, 1 if self.activation == "relu" else 0)

@@ -1,0 +1,228 @@
+"""Model — surface of /root/reference/model.py (:9-56 ctor, :58-71 call).
+
+    Encoder -> Decoder(last, rest) -> optional VAE(last);  returns (y_pred, y_vae, z_mean, z_logvar),
+    with Nones after y_pred when `inference=True`.
+
+B200-side additions (not in the reference): all trainable tensors live in ONE flat fp32 buffer
+(regularised tensors first) with a matching flat gradient buffer, so that the L2 penalties
+(train.py:146), the TF-form Adam update (util.py:60-84) and the data-parallel gradient all-reduce
+are each a single pass over HBM / a single collective.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from .keras_compat import Layer
+from . import ops
+from .layers.encoder import Encoder
+from .layers.decoder import Decoder
+from .layers.vae import VariationalAutoencoder
+
+
+class _EpochVariable:
+    """tf.Variable(0, name='epoch', trainable=False) (model.py:29)."""
+
+    def __init__(self, v=0):
+        self._v = int(v)
+        self.name = 'epoch'
+        self.trainable = False
+
+    def value(self):
+        return self
+
+    def numpy(self):
+        return self._v
+
+    def assign(self, v):
+        self._v = int(v)
+
+    def __int__(self):
+        return self._v
+
+
+class FlatParams:
+    """All trainable tensors of a model as views of one buffer; `grad` is the matching flat gradient."""
+
+    def __init__(self, variables, device):
+        reg = [v for v in variables if v.regularizer is not None]
+        unreg = [v for v in variables if v.regularizer is None]
+        self.order = reg + unreg
+        pad = lambda n: (n + 3) // 4 * 4          # keep every tensor 16-byte aligned
+        sizes = [pad(v.tensor.numel()) for v in self.order]
+        total = sum(sizes)
+        self.theta = torch.zeros(total, device=device, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=device, dtype=torch.float32)
+        self.spans = {}
+        off = 0
+        seg = [0]
+        for v, sz in zip(self.order, sizes):
+            n = v.tensor.numel()
+            view = self.theta[off:off + n].view(v.tensor.shape)
+            view.copy_(v.tensor.detach())
+            v.tensor.data = view                      # same leaf object, storage now inside the flat buffer
+            v.tensor.grad = self.grad[off:off + n].view(v.tensor.shape)
+            self.spans[id(v.tensor)] = (off, n)
+            v.tensor._b3d_flat = self
+            off += sz
+            if v.regularizer is not None:
+                seg.append(off)
+        self.n_reg = len(reg)
+        self.reg_end = seg[-1]
+        self.reg_tensors = [v.tensor for v in reg]
+        ls = {v.regularizer.l for v in reg}
+        if len(ls) > 1:
+            raise NotImplementedError("b3d: per-tensor L2 scales must all be equal")
+        self.l2 = ls.pop() if ls else 0.0
+        # segment table of the regularised tensors (padding belongs to the preceding tensor; it stays 0)
+        self.offsets = torch.tensor(seg, dtype=torch.int64, device=device)
+        self.total = total
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def attach_grads(self):
+        for v in self.order:
+            off, n = self.spans[id(v.tensor)]
+            v.tensor.grad = self.grad[off:off + n].view(v.tensor.shape)
+
+
+class _L2LossesFn(torch.autograd.Function):
+    """model.losses: one l*sum(w^2) per regularised tensor, computed by ONE kernel over the flat buffer.
+    Backward accumulates 2*l*w*gout straight into the flat gradient buffer (the tensors' .grad views)."""
+
+    @staticmethod
+    def forward(ctx, flat: FlatParams, *params):
+        out = torch.empty(flat.n_reg, device=flat.theta.device, dtype=torch.float32)
+        ops._call("b3d_l2_losses", flat.theta, flat.offsets, out, float(flat.l2))
+        ctx.flat = flat
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        flat = ctx.flat
+        ops._call("b3d_l2_grad", flat.theta, flat.grad, flat.offsets, gout.contiguous(), 2.0 * float(flat.l2))
+        return (None,) * (1 + flat.n_reg)
+
+
+class Model(Layer):
+    def __init__(self,
+                 data_format='channels_last',
+                 groups=8,
+                 reduction=2,
+                 l2_scale=1e-5,
+                 dropout=0.2,
+                 downsampling='conv',
+                 upsampling='conv',
+                 base_filters=16,
+                 depth=4,
+                 in_ch=2,
+                 out_ch=3):
+        super().__init__()
+        self.epoch = _EpochVariable(0)
+        self.encoder = Encoder(data_format=data_format, groups=groups, reduction=reduction, l2_scale=l2_scale,
+                               dropout=dropout, downsampling=downsampling, base_filters=base_filters, depth=depth)
+        self.decoder = Decoder(data_format=data_format, groups=groups, reduction=reduction, l2_scale=l2_scale,
+                               upsampling=upsampling, base_filters=base_filters, depth=depth, out_ch=out_ch)
+        self.vae = VariationalAutoencoder(data_format=data_format, groups=groups, reduction=reduction,
+                                          l2_scale=l2_scale, upsampling=upsampling, base_filters=base_filters,
+                                          depth=depth, out_ch=in_ch)
+        self._flat: Optional[FlatParams] = None
+
+    # ---- Keras protocol
+    def __call__(self, inputs, training=None, inference=None, **kw):
+        if not self.built:
+            # the reference builds all weights with a first call on zeros (train.py:96); here the first
+            # call does a weight-creating dry run, then re-homes every tensor into the flat buffer
+            with torch.no_grad():
+                self.call(inputs, training=False, inference=False)
+            self.built = True
+            self.flatten_parameters()
+        return self.call(inputs, training=training, inference=inference, **kw)
+
+    def call(self, inputs, training=None, inference=None, dropout_mask=None, eps=None):
+        # Inference mode does not evaluate the VAE branch (model.py:60)
+        assert (not inference or not training), \
+            'Cannot run training and inference modes simultaneously.'
+        residuals = self.encoder(inputs, training=training, dropout_mask=dropout_mask)
+        y_pred = self.decoder((residuals[-1], residuals[:-1]), training=training)
+        if inference:
+            return (y_pred, None, None, None)
+        y_vae, z_mean, z_logvar = self.vae(residuals[-1], training=training, eps=eps)
+        return (y_pred, y_vae, z_mean, z_logvar)
+
+    # ---- flat parameter storage
+    def flatten_parameters(self) -> FlatParams:
+        if self._flat is None:
+            vs = self.variables()
+            self._flat = FlatParams(vs, vs[0].tensor.device)
+        return self._flat
+
+    @property
+    def flat(self) -> Optional[FlatParams]:
+        return self._flat
+
+    @property
+    def losses(self) -> List[torch.Tensor]:
+        """L2 penalties of all regularised tensors (168 for the default model; train.py:146 sums them)."""
+        flat = self.flatten_parameters()
+        out = _L2LossesFn.apply(flat, *flat.reg_tensors)
+        return list(out.unbind(0))
+
+    # ---- weight exchange by this repo's structural names (oracle.ref_model.param_shapes)
+    def named_variables(self):
+        out = {}
+
+        def blk(b, pre):
+            out[pre + "ptwise.kernel"] = b.conv3d_ptwise.kernel
+            out[pre + "ptwise.bias"] = b.conv3d_ptwise.bias
+            out[pre + "dense_relu.kernel"] = b.dense_relu.kernel
+            out[pre + "dense_sigmoid.kernel"] = b.dense_sigmoid.kernel
+            out[pre + "spatial.kernel"] = b.spatial.kernel
+            for i in (0, 1):
+                conv, norm, _ = b.convs[i]
+                out[pre + f"conv{i+1}.kernel"] = conv.kernel
+                out[pre + f"conv{i+1}.bias"] = conv.bias
+                out[pre + f"gn{i+1}.gamma"] = norm.gamma
+                out[pre + f"gn{i+1}.beta"] = norm.beta
+
+        def rs(l, pre):
+            out[pre + "conv.kernel"] = l.conv.kernel
+            out[pre + "conv.bias"] = l.conv.bias
+            out[pre + "norm.gamma"] = l.norm.gamma
+            out[pre + "norm.beta"] = l.norm.beta
+
+        depth = len(self.encoder.levels)
+        for i, (convs, _, down) in enumerate(self.encoder.levels):
+            for j, (b, _) in enumerate(convs):
+                blk(b, f"enc.L{i}.B{j}.")
+            if down is not None:
+                rs(down, f"enc.L{i}.down.")
+        for i, (up, _, b) in zip(range(depth - 2, -1, -1), self.decoder.levels):
+            rs(up, f"dec.L{i}.up.")
+            blk(b, f"dec.L{i}.block.")
+        out["dec.out.kernel"], out["dec.out.bias"] = self.decoder.out.kernel, self.decoder.out.bias
+        v = self.vae
+        if v.built:
+            rs(v.downsample, "vae.down.")
+            out["vae.proj.kernel"], out["vae.proj.bias"] = v.proj.kernel, v.proj.bias
+            out["vae.unproj.kernel"], out["vae.unproj.bias"] = v.unproj.kernel, v.unproj.bias
+            rs(v.upsample, "vae.up.")
+            for i, (up, b) in zip(range(depth - 2, -1, -1), v.levels):
+                rs(up, f"vae.L{i}.up.")
+                blk(b, f"vae.L{i}.block.")
+            out["vae.out.kernel"], out["vae.out.bias"] = v.out.kernel, v.out.bias
+        return out
+
+    def load_named_weights(self, params):
+        nv = self.named_variables()
+        missing = set(nv) - set(params)
+        if missing:
+            raise KeyError(f"missing weights: {sorted(missing)[:5]} ...")
+        with torch.no_grad():
+            for k, t in nv.items():
+                src = params[k]
+                if tuple(src.shape) != tuple(t.shape):
+                    raise ValueError(f"{k}: shape {tuple(src.shape)} != {tuple(t.shape)}")
+                t.copy_(src.to(device=t.device, dtype=t.dtype))

@@ -1,0 +1,353 @@
+"""torch.autograd glue around the b3d C-ABI (include/b3d.h).  torch is only the tensor container and
+the tape; every arithmetic op below is a hand-written sm_100a kernel reached through ctypes.
+
+All activations are channels_last [B, D, H, W, C] fp32 CUDA tensors; weights are in Keras layouts.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from ._lib import call, lib
+
+_f32 = torch.float32
+
+# kernel-launch accounting for bench.py ("gpu_launches"): incremented per C-ABI call that launches
+LAUNCHES = {"n": 0}
+
+
+def _call(name, *a):
+    LAUNCHES["n"] += 1
+    return call(name, *a)
+
+
+def _new(shape, like, dtype=_f32):
+    return torch.empty(shape, device=like.device, dtype=dtype)
+
+
+def _check(x: torch.Tensor, name="input"):
+    if not x.is_cuda:
+        raise RuntimeError(f"b3d: {name} must be a CUDA tensor — there is no CPU path")
+    if x.dtype != _f32:
+        raise TypeError(f"b3d: {name} must be float32, got {x.dtype}")
+
+
+def tc_supported(k, stride, transposed, c_gathered, c_produced) -> bool:
+    return bool(lib.b3d_conv3d_tc_supported(k, stride, int(transposed), c_gathered, c_produced))
+
+
+def pack_weights(w: torch.Tensor, dgrad: bool) -> torch.Tensor:
+    k = w.shape[0]
+    cg, cp = (w.shape[4], w.shape[3]) if dgrad else (w.shape[3], w.shape[4])
+    n = lib.b3d_conv3d_packed_elems(k, cg, cp)
+    out = _new((n,), w)
+    _call("b3d_conv3d_pack_weights", w, out, int(dgrad))
+    return out
+
+
+# set False to force the CUDA-core kernels everywhere (used by tests to cross-check the tcgen05 path)
+USE_TC = {"on": True}
+
+
+class Conv3dFn(Function):
+    """Conv3D / Conv3DTranspose with TF 'SAME' padding (+bias, optional sigmoid), optionally emitting
+    GroupNorm chunk statistics and global-average-pool sums of its output from the epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, transposed, act, gn_groups, want_gap):
+        _check(x)
+        x = x.contiguous()
+        B, D, H, W_, Cin = x.shape
+        k = w.shape[0]
+        if transposed:
+            Cout, od = w.shape[3], (2 * D, 2 * H, 2 * W_)
+        else:
+            Cout = w.shape[4]
+            od = (D, H, W_) if stride == 1 else (D // 2, H // 2, W_ // 2)
+        y = _new((B,) + od + (Cout,), x)
+        S = od[0] * od[1] * od[2]
+        stats = gap = None
+        if gn_groups and Cout % gn_groups == 0 and S % gn_groups == 0:
+            stats = _new((B, gn_groups, 2), x, torch.float64)
+        if want_gap:
+            gap = _new((B, Cout), x)
+        wp = None
+        if USE_TC["on"] and tc_supported(k, stride, transposed, Cin, Cout):
+            wp = pack_weights(w, False)
+        _call("b3d_conv3d_fwd", x, w, bias, y, stride, int(transposed), int(act), stats, gn_groups or 1, gap, 0, wp)
+        ctx.save_for_backward(x, w, y if act else None)
+        ctx.cfg = (stride, transposed, act, bias is not None)
+        outs = (y, stats, gap)
+        ctx.mark_non_differentiable(*[t for t in (stats, gap) if t is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, dy, _ds, _dg):
+        x, w, y = ctx.saved_tensors
+        stride, transposed, act, has_bias = ctx.cfg
+        dy = dy.contiguous()
+        if act:
+            t = torch.empty_like(dy)
+            _call("b3d_sigmoid_bwd", dy, y, t)
+            dy = t
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            k = w.shape[0]
+            cg = w.shape[3] if transposed else w.shape[4]
+            cp = w.shape[4] if transposed else w.shape[3]
+            wp = None
+            if USE_TC["on"] and not transposed and tc_supported(k, stride, False, cg, cp):
+                wp = pack_weights(w, True)
+            _call("b3d_conv3d_dgrad", dy, w, dx, stride, int(transposed), 0, wp)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            db = _new((dy.shape[-1],), dy) if has_bias else None
+            _call("b3d_conv3d_wgrad", x, dy, dw, db, stride, int(transposed))
+        return dx, dw, db, None, None, None, None, None
+
+
+def conv3d(x, w, bias=None, stride=1, transposed=False, act=0, gn_groups=0, want_gap=False):
+    return Conv3dFn.apply(x, w, bias, stride, transposed, act, gn_groups, want_gap)
+
+
+class GroupNormFn(Function):
+    """GroupNormalization.call (+ optional fused ReLU) with the reference's channels_last semantics
+    (layers/group_norm.py:83-124).  `stats` may come from the producing conv's epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, stats, groups, eps, relu):
+        _check(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        # reference group_norm.py:51-59
+        if C < groups:
+            raise ValueError(f"Number of groups ({groups}) cannot be more than the number of channels ({C}).")
+        if C % groups != 0:
+            raise ValueError(f"Number of groups ({groups}) must be a multiple of the number of channels ({C}).")
+        if stats is None:
+            stats = _new((x.shape[0], groups, 2), x, torch.float64)
+            _call("b3d_gn_stats", x, stats, groups)
+        y = torch.empty_like(x)
+        _call("b3d_gn_apply", x, stats, gamma, beta, y, groups, float(eps), int(relu))
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.cfg = (groups, float(eps), int(relu))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, stats = ctx.saved_tensors
+        groups, eps, relu = ctx.cfg
+        dy = dy.contiguous()
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+        csum = torch.empty_like(stats)
+        _call("b3d_gn_bwd_reduce", dy, x, stats, gamma, beta, dgamma, dbeta, csum, groups, eps, relu)
+        dx = torch.empty_like(x)
+        _call("b3d_gn_bwd_apply", dy, x, stats, gamma, beta, csum, dx, groups, eps, relu)
+        return dx, dgamma, dbeta, None, None, None, None
+
+
+def group_norm(x, gamma, beta, stats=None, groups=8, eps=1e-5, relu=False):
+    return GroupNormFn.apply(x, gamma, beta, stats, groups, eps, relu)
+
+
+class BlockEpilogueFn(Function):
+    """out = res*(sigmoid(res.w_sp) + chse) + relu(GN2(h2)),  chse = sigmoid(relu(mean(res) W1) W2)
+    (layers/resnet.py:121-137).  With stats2=None, `h2` is taken as already normalised+activated."""
+
+    @staticmethod
+    def forward(ctx, res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps):
+        _check(res)
+        res, h2 = res.contiguous(), h2.contiguous()
+        B, F = res.shape[0], res.shape[-1]
+        S = res.numel() // (B * F)
+        R = w1.shape[1]
+        hidden, chse = _new((B, R), res), _new((B, F), res)
+        inv = 1.0 / S
+        _call("b3d_se_fc_fwd", gap_sum, w1, w2, hidden, chse, inv)
+        out = torch.empty_like(res)
+        has_gn = stats2 is not None
+        wsp_v = wsp.reshape(F)
+        _call("b3d_block_epilogue_fwd", res, h2, stats2, gamma2 if has_gn else None, beta2 if has_gn else None,
+              wsp_v, chse, out, groups, float(eps), int(has_gn))
+        ctx.save_for_backward(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, hidden, chse)
+        ctx.cfg = (groups, float(eps), has_gn, inv)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, hidden, chse = ctx.saved_tensors
+        groups, eps, has_gn, inv = ctx.cfg
+        dout = dout.contiguous()
+        B, F = res.shape[0], res.shape[-1]
+        wsp_v = wsp.reshape(F)
+        dchse, dwsp = _new((B, F), res), _new((F,), res)
+        dgamma = torch.empty_like(gamma2) if has_gn else None
+        dbeta = torch.empty_like(beta2) if has_gn else None
+        csum = torch.empty_like(stats2) if has_gn else None
+        _call("b3d_block_epilogue_bwd_reduce", dout, res, h2 if has_gn else None, stats2,
+              gamma2 if has_gn else None, beta2 if has_gn else None, wsp_v, dchse, dwsp, dgamma, dbeta, csum,
+              groups, eps, int(has_gn))
+        dw1, dw2, dgap = torch.empty_like(w1), torch.empty_like(w2), _new((B, F), res)
+        _call("b3d_se_fc_bwd", gap_sum, w1, w2, hidden, chse, dchse, dw1, dw2, dgap, inv)
+        dres = torch.empty_like(res)
+        dh2 = torch.empty_like(h2) if has_gn else None
+        _call("b3d_block_epilogue_bwd_apply", dout, res, h2 if has_gn else None, stats2,
+              gamma2 if has_gn else None, beta2 if has_gn else None, wsp_v, chse, dgap, csum, dres, dh2,
+              groups, eps, int(has_gn))
+        if not has_gn:
+            dh2 = dout
+        return dres, dh2, None, dgamma, dbeta, dwsp.reshape(wsp.shape), None, dw1, dw2, None, None
+
+
+def block_epilogue(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups=8, eps=1e-5):
+    return BlockEpilogueFn.apply(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps)
+
+
+class DenseFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        _check(x)
+        x = x.contiguous()
+        y = _new((x.shape[0], w.shape[1]), x)
+        _call("b3d_dense_fwd", x, w, b, y, int(act))
+        ctx.save_for_backward(x, w, y)
+        ctx.cfg = (int(act), b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        act, has_b = ctx.cfg
+        dy = dy.contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = _new((w.shape[1],), w) if has_b else None
+        _call("b3d_dense_bwd", x, w, y, dy, dx, dw, db, act)
+        return dx, dw, db, None
+
+
+def dense(x, w, b=None, act=0):
+    return DenseFn.apply(x, w, b, act)
+
+
+class VaeSampleFn(Function):
+    """proj = [z_mean | z_logvar] -> (z, z_mean, z_logvar),  z = z_mean + exp(0.5 z_logvar) * eps
+    (layers/vae.py:9-13, 123-125)."""
+
+    @staticmethod
+    def forward(ctx, proj, eps):
+        _check(proj)
+        proj, eps = proj.contiguous(), eps.contiguous()
+        B, L = proj.shape[0], proj.shape[1] // 2
+        z = _new((B, L), proj)
+        _call("b3d_vae_sample_fwd", proj, eps, z)
+        ctx.save_for_backward(proj, eps)
+        return z, proj[:, :L].contiguous(), proj[:, L:].contiguous()
+
+    @staticmethod
+    def backward(ctx, dz, dmu, dlv):
+        proj, eps = ctx.saved_tensors
+        dproj = torch.empty_like(proj)
+        c = lambda t: None if t is None else t.contiguous()
+        _call("b3d_vae_sample_bwd", proj, eps, c(dz), c(dmu), c(dlv), dproj)
+        return dproj, None
+
+
+def vae_sample(proj, eps):
+    return VaeSampleFn.apply(proj, eps)
+
+
+class DiceVAELossFn(Function):
+    """util.py:13-24 as one reduction pass + a scalar finalize; backward is one elementwise pass."""
+
+    @staticmethod
+    def forward(ctx, x, y, y_pred, y_vae, z_mean, z_logvar):
+        _check(y_pred, "y_pred")
+        C = y_pred.shape[-1]
+        vae = y_vae is not None
+        c = lambda t: None if t is None else t.contiguous()
+        x, y, y_pred, y_vae, z_mean, z_logvar = map(c, (x, y, y_pred, y_vae, z_mean, z_logvar))
+        sums = _new((3 * C + 2,), y_pred, torch.float64)
+        out = _new((4,), y_pred)
+        _call("b3d_loss_fwd", x if vae else None, y, y_pred, y_vae, z_mean if vae else None,
+              z_logvar if vae else None, sums, out)
+        ctx.save_for_backward(x if vae else None, y, y_pred, y_vae, z_mean if vae else None,
+                              z_logvar if vae else None, sums)
+        ctx.parts = out
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, y_pred, y_vae, z_mean, z_logvar, sums = ctx.saved_tensors
+        vae = y_vae is not None
+        g = g.reshape(1).contiguous().to(_f32)
+        dyp = torch.empty_like(y_pred)
+        dyv = torch.empty_like(y_vae) if vae else None
+        dmu = torch.empty_like(z_mean) if vae else None
+        dlv = torch.empty_like(z_logvar) if vae else None
+        _call("b3d_loss_bwd", x, y, y_pred, y_vae, z_mean, z_logvar, sums, g, dyp, dyv, dmu, dlv)
+        return None, None, dyp, dyv, dmu, dlv
+
+
+def dice_vae_loss(x, y, y_pred, y_vae=None, z_mean=None, z_logvar=None):
+    return DiceVAELossFn.apply(x, y, y_pred, y_vae, z_mean, z_logvar)
+
+
+def dice_coefficient(y_true, y_pred):
+    """util.py:35-57 -> (macro, micro) as 0-d tensors (no gradient)."""
+    _check(y_pred, "y_pred")
+    y_true, y_pred = y_true.contiguous(), y_pred.detach().contiguous()
+    W, C = y_pred.shape[3], y_pred.shape[4]
+    acc = _new((W * C * 3,), y_pred)
+    out = _new((2,), y_pred)
+    _call("b3d_dice_coeff", y_true, y_pred, acc, out)
+    return out[0], out[1]
+
+
+class ConcatFn(Function):
+    """Channel concat (encoder.py:85,91; decoder.py:75) materialised by strided copies."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        C = [t.shape[-1] for t in xs]
+        out = _new(tuple(xs[0].shape[:-1]) + (sum(C),), xs[0])
+        o = 0
+        for t, c in zip(xs, C):
+            _call("b3d_copy_channels", t.contiguous(), out[..., o:o + c], 0)
+            o += c
+        ctx.C = C
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = d.contiguous()
+        outs, o = [], 0
+        for i, c in enumerate(ctx.C):
+            if ctx.needs_input_grad[i]:
+                g = _new(tuple(d.shape[:-1]) + (c,), d)
+                _call("b3d_copy_channels", d[..., o:o + c], g, 0)
+                outs.append(g)
+            else:
+                outs.append(None)
+            o += c
+        return tuple(outs)
+
+
+def concat(xs):
+    return ConcatFn.apply(*xs)
+
+
+def dropout(x, rate, training, mask=None, seed=0, counter=None):
+    """tf.keras.layers.Dropout on the (non-differentiable) input volume (encoder.py:39,71).
+    `mask` injects a keep-mask for deterministic parity runs."""
+    if not training or rate == 0.0:
+        return x
+    _check(x)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    if mask is not None:
+        _call("b3d_mul_scale", x, mask.contiguous(), y, 1.0 / (1.0 - rate))
+    else:
+        _call("b3d_dropout", x, y, None, float(rate), int(seed), counter)
+    return y

@@ -1,0 +1,113 @@
+"""Loss, metric and optimiser with the reference's names and call signatures
+(/root/reference/util.py:5-24 DiceVAELoss, :27-57 DiceCoefficient, :60-84 ScheduledOptim)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class DiceVAELoss(object):
+    """soft-Dice (summed over batch and space, squared denominators, +1 smoothing) + 0.1*MSE(x, y_vae)
+    + 0.1*mean(mu^2 + exp(logvar) - logvar - 1)  — one reduction pass (csrc/misc.cu)."""
+
+    def __init__(self, name='custom_loss', data_format='channels_last', **kwargs):
+        if data_format != 'channels_last':
+            raise NotImplementedError("b3d: channels_first is listed under SURVEY §8(f)")
+        self.axis = (0, 1, 2, 3)
+
+    def __call__(self, x, y, y_pred, y_vae, z_mean, z_logvar, sample_weight=None):
+        return ops.dice_vae_loss(x, y, y_pred, y_vae, z_mean, z_logvar)
+
+
+class DiceCoefficient(object):
+    """Hard dice of one_hot(argmax)*[max>0.5]: (macro, micro); macro keeps the reference's
+    un-reduced W axis (util.py:36,50-54)."""
+
+    def __init__(self, name='dice_coefficient', data_format='channels_last'):
+        if data_format != 'channels_last':
+            raise NotImplementedError("b3d: channels_first is listed under SURVEY §8(f)")
+        self.name = name
+        self.data_format = data_format
+
+    def __call__(self, y_true, y_pred):
+        return ops.dice_coefficient(y_true, y_pred)
+
+
+class ScheduledOptim(object):
+    """tf.keras.optimizers.Adam semantics:
+        alpha_t = lr*sqrt(1-b2^t)/(1-b1^t);  theta -= alpha_t * m / (sqrt(v) + eps),  eps = 1e-7,
+    with the per-epoch polynomial schedule of util.py:82-84.  When the variables are a model's flat
+    parameter buffer the whole update is ONE kernel over (theta, m, v, g)."""
+
+    def __init__(self, learning_rate=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-7, amsgrad=False,
+                 name='Adam', n_epochs=300, **kwargs):
+        if amsgrad:
+            raise NotImplementedError("amsgrad")
+        self.init_lr = float(learning_rate)
+        self.beta_1, self.beta_2, self.epsilon = float(beta_1), float(beta_2), float(epsilon)
+        self.n_epochs = float(n_epochs)
+        self._lr = float(learning_rate)
+        self._state = None        # device fp64 [2] = (iterations, lr)
+        self._slots = {}          # id(tensor-or-flat) -> (m, v)
+        self.grad_scale = 1.0     # data-parallel averaging factor folded into the update
+
+    def __call__(self, epoch):
+        new_lr = self.init_lr * ((1.0 - epoch / self.n_epochs) ** 0.9)
+        self._set_hyper('learning_rate', new_lr)
+
+    def _set_hyper(self, name, value):
+        assert name == 'learning_rate'
+        self._lr = float(value)
+        if self._state is not None:
+            self._state[1] = self._lr
+
+    @property
+    def learning_rate(self):
+        return torch.tensor(self._lr, dtype=torch.float64)
+
+    @property
+    def iterations(self):
+        return 0 if self._state is None else int(self._state[0].item())
+
+    def _ensure_state(self, device):
+        if self._state is None:
+            self._state = torch.tensor([0.0, self._lr], dtype=torch.float64, device=device)
+
+    def _mv(self, key, like):
+        if key not in self._slots:
+            self._slots[key] = (torch.zeros_like(like), torch.zeros_like(like))
+        return self._slots[key]
+
+    def apply_flat(self, flat):
+        """Fused update of a model's flat parameter buffer from its flat gradient buffer."""
+        self._ensure_state(flat.theta.device)
+        m, v = self._mv(id(flat), flat.theta)
+        ops._call("b3d_adam_step", flat.theta, m, v, flat.grad, self._state, self.beta_1, self.beta_2,
+                  self.epsilon, float(self.grad_scale), 1)
+
+    def apply_gradients(self, grads_and_vars, flat=None):
+        gv = list(grads_and_vars)
+        if flat is not None or _is_flat_group(gv):
+            flat = flat or gv[0][1]._b3d_flat
+            return self.apply_flat(flat)
+        self._ensure_state(gv[0][1].device)
+        for i, (g, var) in enumerate(gv):
+            m, v = self._mv(id(var), var)
+            th = var.detach().view(-1)
+            ops._call("b3d_adam_step", th, m.view(-1), v.view(-1), g.contiguous().view(-1), self._state,
+                      self.beta_1, self.beta_2, self.epsilon, float(self.grad_scale), int(i == len(gv) - 1))
+
+
+def _is_flat_group(gv):
+    """True when (grads, vars) are exactly a model's flat parameter group with its own .grad views."""
+    flat = getattr(gv[0][1], "_b3d_flat", None)
+    if flat is None or len(gv) != len(flat.order):
+        return False
+    for g, v in gv:
+        if getattr(v, "_b3d_flat", None) is not flat or g is None:
+            return False
+        off, n = flat.spans[id(v)]
+        if g.data_ptr() != flat.grad.data_ptr() + 4 * off:
+            return False
+    return True

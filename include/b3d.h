@@ -1,0 +1,141 @@
+/* b3d — C-ABI of the B200-native hot path of vliu15/3d-brain-tumor-segmentation.
+ *
+ * The reference has no FFI of its own: its "operator API" is the Keras layer surface
+ * (layers/*.py, model.py, util.py).  Each entry point below is the arithmetic behind one of
+ * those call sites (cited as reference file:line) and is what the Python layer classes in
+ * `3d-brain-tumor-segmentation_b200/` bind through ctypes (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *  - every tensor argument is a BORROWED `const DLTensor*` (include/b3d_dlpack.h); a
+ *    `DLManagedTensor*` from `to_dlpack` may be passed as-is.  The callee never frees, never
+ *    retains past return (+ stream order), and never allocates device memory: outputs and
+ *    workspaces are caller-allocated.  NULL is allowed only where marked "nullable".
+ *  - tensors must live on a CUDA device (kDLCUDA) — there is NO CPU path — and be fp32 unless
+ *    stated otherwise; activations are channels_last [B, D, H, W, C], compact row-major
+ *    (conv inputs/outputs may be channel slices of a wider NDHWC buffer); weights use the Keras
+ *    layouts: Conv3D (kd,kh,kw,Cin,Cout), Conv3DTranspose (kd,kh,kw,Cout,Cin), Dense (in,out).
+ *  - `void* stream` is a cudaStream_t; all work is enqueued on it, nothing synchronises, so
+ *    every call is CUDA-graph capturable.
+ *  - return 0 on success, a negative B3D_ERR_* code otherwise; `b3d_last_error()` returns the
+ *    thread-local message.  No exceptions cross the ABI; no global mutable state.
+ */
+#ifndef B3D_H_
+#define B3D_H_
+#include "b3d_dlpack.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B3D_ERR_ARG (-1)
+#define B3D_ERR_DEVICE (-2)
+#define B3D_ERR_DTYPE (-3)
+#define B3D_ERR_LAYOUT (-4)
+#define B3D_ERR_SHAPE (-5)
+#define B3D_ERR_CUDA (-6)
+#define B3D_ERR_UNSUPPORTED (-7)
+
+const char* b3d_last_error(void);
+int b3d_abi_version(void);
+
+/* ---- Conv3D / Conv3DTranspose, TF 'same' padding ------------------------------------------
+ * replaces tf.keras.layers.Conv3D at resnet.py:30-37 (1x1x1), :64-73, :80-87, :96-103 (3x3x3),
+ * downsample.py:28-35 (k3 s2: pad_before 0 / pad_after 1), decoder.py:55-63 (1x1x1 + sigmoid),
+ * vae.py:92-99, and tf.keras.layers.Conv3DTranspose at upsample.py:28-33 (k3 s2 = adjoint of the
+ * strided SAME conv; output = 2x input).
+ *   stride: 1, or 2 (k=3 only; even sizes).  transposed: 1 => Conv3DTranspose (stride must be 2).
+ *   act: 0 none, 1 sigmoid.  accumulate: y += result.
+ *   gn_stats (nullable): fp64 [B, groups, 2], receives (sum, sum of squares) of y per GroupNorm
+ *     chunk straight from the conv epilogue.  gap (nullable): fp32 [B, Cout] = sum over voxels of y.
+ *   wpacked (nullable): weights re-laid-out by b3d_conv3d_pack_weights => run the tcgen05
+ *     implicit-GEMM kernel (requires b3d_conv3d_tc_supported); NULL => CUDA-core kernel. */
+int b3d_conv3d_fwd(const DLTensor* x, const DLTensor* w, const DLTensor* bias /*nullable*/, DLTensor* y,
+                   int stride, int transposed, int act, DLTensor* gn_stats, int groups, DLTensor* gap,
+                   int accumulate, const DLTensor* wpacked, void* stream);
+/* data gradient (what tape.gradient computes for the layer input, train.py:151) */
+int b3d_conv3d_dgrad(const DLTensor* dy, const DLTensor* w, DLTensor* dx, int stride, int transposed,
+                     int accumulate, const DLTensor* wpacked, void* stream);
+/* weight (+ bias, nullable) gradient */
+int b3d_conv3d_wgrad(const DLTensor* x, const DLTensor* dy, DLTensor* dw, DLTensor* dbias, int stride,
+                     int transposed, void* stream);
+int b3d_conv3d_tc_supported(int k, int stride, int transposed, int c_gathered, int c_produced);
+long long b3d_conv3d_packed_elems(int k, int c_gathered, int c_produced);
+int b3d_conv3d_pack_weights(const DLTensor* w, DLTensor* packed, int dgrad, void* stream);
+
+/* ---- GroupNormalization.call, channels_last semantics (group_norm.py:83-124) -----
+ * "group" g = g-th contiguous 1/G chunk of each sample's flat buffer; eps inside sqrt; population
+ * variance.  stats: fp64 [B, G, 2] = (sum x, sum x^2).  relu=1 fuses the following Activation('relu')
+ * (resnet.py:95,111; downsample.py:39; upsample.py:37).  Errors (B3D_ERR_SHAPE, reference
+ * ValueError text) when C < groups or C % groups != 0 (group_norm.py:51-59). */
+int b3d_gn_stats(const DLTensor* x, DLTensor* stats, int groups, void* stream);
+int b3d_gn_apply(const DLTensor* x, const DLTensor* stats, const DLTensor* gamma, const DLTensor* beta,
+                 DLTensor* y, int groups, float eps, int relu, void* stream);
+int b3d_gn_bwd_reduce(const DLTensor* dy, const DLTensor* x, const DLTensor* stats, const DLTensor* gamma,
+                      const DLTensor* beta, DLTensor* dgamma, DLTensor* dbeta, DLTensor* csum /*fp64 [B,G,2]*/,
+                      int groups, float eps, int relu, void* stream);
+int b3d_gn_bwd_apply(const DLTensor* dy, const DLTensor* x, const DLTensor* stats, const DLTensor* gamma,
+                     const DLTensor* beta, const DLTensor* csum, DLTensor* dx, int groups, float eps, int relu,
+                     void* stream);
+
+/* ---- ResnetBlock epilogue (resnet.py:121-137) --------------------------------------------------
+ * chse = sigmoid(relu(gap_sum*inv_vox . W1) . W2);  out = res*(sigmoid(res.w_sp)+chse) + relu(GN2(h2)).
+ * has_gn=0: h2 is already normalised+activated (stats/gamma/beta NULL). */
+int b3d_se_fc_fwd(const DLTensor* gap_sum, const DLTensor* w1, const DLTensor* w2, DLTensor* hidden,
+                  DLTensor* chse, float inv_vox, void* stream);
+int b3d_se_fc_bwd(const DLTensor* gap_sum, const DLTensor* w1, const DLTensor* w2, const DLTensor* hidden,
+                  const DLTensor* chse, const DLTensor* dchse, DLTensor* dw1, DLTensor* dw2, DLTensor* dgap,
+                  float inv_vox, void* stream);
+int b3d_block_epilogue_fwd(const DLTensor* res, const DLTensor* h2, const DLTensor* stats, const DLTensor* gamma,
+                           const DLTensor* beta, const DLTensor* wsp, const DLTensor* chse, DLTensor* out,
+                           int groups, float eps, int has_gn, void* stream);
+int b3d_block_epilogue_bwd_reduce(const DLTensor* dout, const DLTensor* res, const DLTensor* h2,
+                                  const DLTensor* stats, const DLTensor* gamma, const DLTensor* beta,
+                                  const DLTensor* wsp, DLTensor* dchse, DLTensor* dwsp, DLTensor* dgamma,
+                                  DLTensor* dbeta, DLTensor* csum, int groups, float eps, int has_gn,
+                                  void* stream);
+int b3d_block_epilogue_bwd_apply(const DLTensor* dout, const DLTensor* res, const DLTensor* h2,
+                                 const DLTensor* stats, const DLTensor* gamma, const DLTensor* beta,
+                                 const DLTensor* wsp, const DLTensor* chse, const DLTensor* dgap,
+                                 const DLTensor* csum, DLTensor* dres, DLTensor* dh2, int groups, float eps,
+                                 int has_gn, void* stream);
+
+/* ---- VAE bottleneck (vae.py:9-13, :119-129): Dense, reparameterisation -------------------------*/
+int b3d_dense_fwd(const DLTensor* x, const DLTensor* w, const DLTensor* bias, DLTensor* y, int act /*1 relu*/,
+                  void* stream);
+int b3d_dense_bwd(const DLTensor* x, const DLTensor* w, const DLTensor* y, const DLTensor* dy,
+                  DLTensor* dx /*nullable*/, DLTensor* dw, DLTensor* db /*nullable*/, int act, void* stream);
+int b3d_vae_sample_fwd(const DLTensor* proj /*[B,2L]=mean|logvar*/, const DLTensor* eps, DLTensor* z, void* stream);
+int b3d_vae_sample_bwd(const DLTensor* proj, const DLTensor* eps, const DLTensor* dz, const DLTensor* dmean,
+                       const DLTensor* dlogvar, DLTensor* dproj, void* stream);
+
+/* ---- DiceVAELoss / DiceCoefficient (util.py:13-24, :35-57) --------------------------------------
+ * sums: fp64 [3*C+2] workspace; out: fp32 [4] = total, dice, l2, kld.  y_vae NULL => dice only. */
+int b3d_loss_fwd(const DLTensor* x, const DLTensor* y, const DLTensor* y_pred, const DLTensor* y_vae,
+                 const DLTensor* z_mean, const DLTensor* z_logvar, DLTensor* sums, DLTensor* out, void* stream);
+int b3d_loss_bwd(const DLTensor* x, const DLTensor* y, const DLTensor* y_pred, const DLTensor* y_vae,
+                 const DLTensor* z_mean, const DLTensor* z_logvar, const DLTensor* sums, const DLTensor* gout,
+                 DLTensor* dy_pred, DLTensor* dy_vae, DLTensor* dz_mean, DLTensor* dz_logvar, void* stream);
+int b3d_dice_coeff(const DLTensor* y, const DLTensor* y_pred, DLTensor* acc /*fp32 [W*C*3]*/,
+                   DLTensor* out /*fp32 [2] macro, micro*/, void* stream);
+
+/* ---- optimiser + regulariser (util.py:60-84 TF Adam, eps un-scaled; train.py:146 model.losses) ---*/
+int b3d_adam_step(DLTensor* theta, DLTensor* m, DLTensor* v, const DLTensor* g,
+                  DLTensor* state /*fp64 [2] = iterations, learning rate*/, float beta1, float beta2, float eps,
+                  float grad_scale, int tick, void* stream);
+int b3d_l2_losses(const DLTensor* flat, const DLTensor* offsets /*int64 [n+1]*/, DLTensor* out /*[n]*/,
+                  float scale, void* stream);
+int b3d_l2_grad(const DLTensor* flat, DLTensor* grad, const DLTensor* offsets, const DLTensor* gout, float coef,
+                void* stream);
+int b3d_axpy(const DLTensor* flat, DLTensor* grad, long long n, float coef, const DLTensor* gout, void* stream);
+
+/* ---- input Dropout (encoder.py:39,71), concat materialisation, small elementwise helpers --------*/
+int b3d_dropout(const DLTensor* x, DLTensor* y, DLTensor* mask /*nullable*/, float rate, unsigned long long seed,
+                DLTensor* counter /*int64 [1], nullable*/, void* stream);
+int b3d_mul_scale(const DLTensor* a, const DLTensor* b, DLTensor* y, float scale, void* stream);
+int b3d_sigmoid_bwd(const DLTensor* dy, const DLTensor* y, DLTensor* dx, void* stream);
+int b3d_copy_channels(const DLTensor* src, DLTensor* dst, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

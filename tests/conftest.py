@@ -1,0 +1,31 @@
+import importlib
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PKG = "3d-brain-tumor-segmentation_b200"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def b3d():
+    lib = os.path.join(ROOT, PKG, "csrc", "libb3d.so")
+    if not os.path.isfile(lib):
+        import __graft_entry__ as g
+        g.build()
+    return importlib.import_module(PKG)
+
+
+@pytest.fixture(scope="session")
+def dev():
+    import torch
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")

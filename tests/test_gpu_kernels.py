@@ -1,0 +1,238 @@
+"""GPU suite — every C-ABI kernel against the oracle (fp64 CPU restatement) on the same seeded inputs.
+Tolerances: fp32 CUDA-core kernels rel-L2 <= 1e-5; tcgen05 TF32 kernels rel-L2 <= 2e-3 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_model as R
+
+pytestmark = pytest.mark.gpu
+TOL32 = 2e-5
+TOL_TF32 = 2e-3
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def t64(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float64) * scale
+
+
+def dev32(t, dev, grad=False):
+    return t.to(torch.float32).to(dev).requires_grad_(grad)
+
+
+CONV_CASES = [
+    # (spatial, Cin, Cout, k, stride, transposed)
+    ((8, 8, 8), 2, 16, 3, 1, False),
+    ((8, 16, 8), 16, 16, 3, 1, False),
+    ((4, 16, 16), 32, 16, 3, 1, False),
+    ((6, 10, 12), 5, 7, 3, 1, False),
+    ((8, 8, 8), 16, 3, 1, 1, False),
+    ((8, 8, 8), 24, 16, 1, 1, False),
+    ((8, 8, 8), 16, 16, 3, 2, False),
+    ((4, 6, 8), 12, 8, 3, 2, False),
+    ((4, 4, 4), 16, 8, 3, 2, True),
+    ((2, 2, 2), 1, 128, 3, 2, True),
+    ((4, 16, 8), 64, 32, 3, 1, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_conv_fwd_bwd(b3d, dev, case, use_tc):
+    sp, cin, cout, k, stride, tr = case
+    if use_tc and not b3d.ops.tc_supported(k, stride, tr, cin, cout):
+        pytest.skip("shape not on the tcgen05 path")
+    b3d.ops.USE_TC["on"] = use_tc
+    try:
+        B = 2
+        x = t64(B, *sp, cin, seed=1)
+        w = t64(k, k, k, *((cout, cin) if tr else (cin, cout)), seed=2, scale=0.2)
+        bias = t64(cout, seed=3)
+        xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, bias))
+        yr = R.conv3d_transpose_same(xr, wr, br) if tr else R.conv3d_same(xr, wr, br, stride)
+        gy = t64(*yr.shape, seed=4)
+        (yr * gy).sum().backward()
+        xd, wd, bd = dev32(x, dev, True), dev32(w, dev, True), dev32(bias, dev, True)
+        y, stats, gap = b3d.ops.conv3d(xd, wd, bd, stride, tr, 0, 0, True)
+        (y * dev32(gy, dev)).sum().backward()
+        tol = TOL_TF32 if use_tc else TOL32
+        assert rel(y, yr) < tol
+        assert rel(gap, yr.sum(dim=(1, 2, 3))) < max(tol, 1e-4)
+        assert rel(xd.grad, xr.grad) < tol
+        assert rel(wd.grad, wr.grad) < tol
+        assert rel(bd.grad, br.grad) < TOL32 * 10
+    finally:
+        b3d.ops.USE_TC["on"] = True
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 8, 16), (1, 20, 6, 4, 16), (2, 5, 3, 3, 8), (1, 4, 4, 4, 32),
+                                   (2, 2, 2, 2, 64), (1, 16, 16, 16, 128), (3, 1, 1, 1, 8)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_group_norm(b3d, dev, shape, relu):
+    x, ga, be = t64(*shape, seed=5), 1 + 0.3 * t64(shape[-1], seed=6), 0.3 * t64(shape[-1], seed=7)
+    xr, gr, br = (t.clone().requires_grad_(True) for t in (x, ga, be))
+    yr = R.group_norm(xr, gr, br)
+    yr = torch.relu(yr) if relu else yr
+    gy = t64(*shape, seed=8)
+    (yr * gy).sum().backward()
+    xd, gd, bd = dev32(x, dev, True), dev32(ga, dev, True), dev32(be, dev, True)
+    y = b3d.ops.group_norm(xd, gd, bd, None, 8, 1e-5, relu)
+    (y * dev32(gy, dev)).sum().backward()
+    assert rel(y, yr) < TOL32
+    if shape[1] * shape[2] * shape[3] * shape[4] // 8 > 1:      # single-element chunks: dx is 0/0-ish noise
+        assert rel(xd.grad, xr.grad) < 2e-4
+    assert rel(gd.grad, gr.grad) < 1e-4
+    assert rel(bd.grad, br.grad) < 1e-4
+
+
+def test_group_norm_matches_reference_fixture(b3d, dev):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gn_cases.npz"))
+    for i in range(4):
+        x, ga, be = (torch.from_numpy(g[f"{n}{i}"]) for n in ("x", "gamma", "beta"))
+        y = b3d.ops.group_norm(dev32(x, dev), dev32(ga, dev), dev32(be, dev), None, 8, 1e-5, False)
+        assert rel(y, torch.from_numpy(g[f"y{i}"])) < TOL32
+
+
+def test_group_norm_value_errors(b3d, dev):
+    gn = b3d.GroupNormalization(groups=8)
+    with pytest.raises(ValueError, match="cannot be more than the number of channels"):
+        gn(torch.zeros(1, 2, 2, 2, 4, device=dev))
+    gn = b3d.GroupNormalization(groups=8)
+    with pytest.raises(ValueError, match="must be a multiple of the number of channels"):
+        gn(torch.zeros(1, 2, 2, 2, 12, device=dev))
+
+
+@pytest.mark.parametrize("cfg", [((8, 8, 8), 2, 16, 2), ((4, 8, 16), 32, 32, 2), ((4, 4, 4), 64, 128, 8),
+                                 ((3, 3, 3), 16, 16, 2), ((4, 4, 8), 48, 24, 2)])
+def test_resnet_block(b3d, dev, cfg):
+    sp, cin, f, red = cfg
+    shapes = {}
+    pre = "b."
+    full = R.param_shapes()          # borrow the per-block shape recipe
+    for k, v in full.items():
+        if k.startswith("enc.L0.B0."):
+            name = k[len("enc.L0.B0."):]
+            shp = list(v)
+            shapes[pre + name] = shp
+    # rewrite channel dims
+    def fix(name):
+        return {"ptwise.kernel": (1, 1, 1, cin, f), "ptwise.bias": (f,), "dense_relu.kernel": (f, f // red),
+                "dense_sigmoid.kernel": (f // red, f), "spatial.kernel": (1, 1, 1, f, 1),
+                "conv1.kernel": (3, 3, 3, cin, f), "conv1.bias": (f,), "gn1.gamma": (f,), "gn1.beta": (f,),
+                "conv2.kernel": (3, 3, 3, f, f), "conv2.bias": (f,), "gn2.gamma": (f,), "gn2.beta": (f,)}[name]
+    shapes = {pre + n[len(pre):]: fix(n[len(pre):]) for n in shapes}
+    p = R.init_params(shapes, seed=9)
+    x = t64(2, *sp, cin, seed=10)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    xr = x.clone().requires_grad_(True)
+    yr = R.resnet_block(pr, pre, xr)
+    gy = t64(*yr.shape, seed=11)
+    (yr * gy).sum().backward()
+
+    blk = b3d.ResnetBlock(f, reduction=red)
+    xd = dev32(x, dev, True)
+    blk(xd.detach())
+    names = {"ptwise.kernel": blk.conv3d_ptwise.kernel, "ptwise.bias": blk.conv3d_ptwise.bias,
+             "dense_relu.kernel": blk.dense_relu.kernel, "dense_sigmoid.kernel": blk.dense_sigmoid.kernel,
+             "spatial.kernel": blk.spatial.kernel,
+             "conv1.kernel": blk.convs[0][0].kernel, "conv1.bias": blk.convs[0][0].bias,
+             "gn1.gamma": blk.convs[0][1].gamma, "gn1.beta": blk.convs[0][1].beta,
+             "conv2.kernel": blk.convs[1][0].kernel, "conv2.bias": blk.convs[1][0].bias,
+             "gn2.gamma": blk.convs[1][1].gamma, "gn2.beta": blk.convs[1][1].beta}
+    with torch.no_grad():
+        for n, t in names.items():
+            t.copy_(p[pre + n].to(torch.float32))
+    y = blk(xd)
+    (y * dev32(gy, dev)).sum().backward()
+    tol = TOL_TF32
+    assert rel(y, yr) < tol
+    assert rel(xd.grad, xr.grad) < 3 * tol
+    for n, t in names.items():
+        assert rel(t.grad, pr[pre + n].grad) < 5 * tol, n
+
+
+def test_loss_and_dice(b3d, dev):
+    for C, shape in ((3, (2, 6, 5, 7)), (1, (1, 4, 4, 4)), (3, (1, 16, 16, 16))):
+        x, yv = t64(*shape, 2, seed=1), t64(*shape, 2, seed=2)
+        yp = torch.sigmoid(t64(*shape, C, seed=3) * 2)
+        y = (t64(*shape, C, seed=4) > 0.8).double()
+        mu, lv = t64(shape[0], 64, seed=5), t64(shape[0], 64, seed=6) * 0.5
+        ypr, yvr, mur, lvr = (t.clone().requires_grad_(True) for t in (yp, yv, mu, lv))
+        lr_ = R.dice_vae_loss(x, y, ypr, yvr, mur, lvr)
+        (lr_ * 1.7).backward()
+        d = lambda t, g=False: dev32(t, dev, g)
+        ypd, yvd, mud, lvd = d(yp, True), d(yv, True), d(mu, True), d(lv, True)
+        l = b3d.DiceVAELoss()(d(x), d(y), ypd, yvd, mud, lvd)
+        (l * 1.7).backward()
+        assert abs(float(l) - float(lr_)) / abs(float(lr_)) < 1e-5
+        for a, b in ((ypd, ypr), (yvd, yvr), (mud, mur), (lvd, lvr)):
+            assert rel(a.grad, b.grad) < 1e-4
+        macro, micro = b3d.DiceCoefficient()(d(y), d(yp))
+        mr, ur = R.dice_coefficient(y, yp)
+        assert abs(float(macro) - float(mr)) < 1e-5 and abs(float(micro) - float(ur)) < 1e-5
+
+
+def test_dense_and_sample(b3d, dev):
+    for B, K, N, act in ((1, 4096, 128, 0), (2, 64, 512, 1), (3, 37, 5, 1)):
+        x, w, b = t64(B, K, seed=1), t64(K, N, seed=2, scale=0.1), t64(N, seed=3)
+        xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+        yr = R.dense(xr, wr, br)
+        yr = torch.relu(yr) if act else yr
+        gy = t64(B, N, seed=4)
+        (yr * gy).sum().backward()
+        xd, wd, bd = dev32(x, dev, True), dev32(w, dev, True), dev32(b, dev, True)
+        y = b3d.ops.dense(xd, wd, bd, act)
+        (y * dev32(gy, dev)).sum().backward()
+        assert rel(y, yr) < TOL32 and rel(xd.grad, xr.grad) < TOL32
+        assert rel(wd.grad, wr.grad) < TOL32 and rel(bd.grad, br.grad) < TOL32
+    proj, eps = t64(2, 128, seed=5), t64(2, 64, seed=6)
+    pr = proj.clone().requires_grad_(True)
+    zr = pr[:, :64] + torch.exp(0.5 * pr[:, 64:]) * eps
+    (zr.sum() * 2 + (pr[:, :64] ** 2).sum() + pr[:, 64:].exp().sum()).backward()
+    pd = dev32(proj, dev, True)
+    z, zm, zl = b3d.ops.vae_sample(pd, dev32(eps, dev))
+    (z.sum() * 2 + (zm ** 2).sum() + zl.exp().sum()).backward()
+    assert rel(z, zr) < TOL32 and rel(pd.grad, pr.grad) < TOL32
+
+
+def test_adam_matches_tf_form(b3d, dev):
+    n = 1003
+    th, g1, g2 = t64(n, seed=1), t64(n, seed=2), t64(n, seed=3)
+    m, v = torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    ref = th.clone()
+    lr = R.poly_lr(7)
+    R.adam_step_tf(ref, m, v, g1, 1, lr)
+    R.adam_step_tf(ref, m, v, g2, 2, lr)
+    opt = b3d.ScheduledOptim(learning_rate=1e-4)
+    opt(epoch=7)
+    var = dev32(th, dev)
+    opt.apply_gradients([(dev32(g1, dev), var)])
+    opt.apply_gradients([(dev32(g2, dev), var)])
+    assert opt.iterations == 2
+    assert float((var.cpu().double() - ref).abs().max()) < 1e-7
+    assert rel(var - dev32(th, dev), ref - th) < 1e-5
+
+
+def test_concat_and_dropout(b3d, dev):
+    a, b, c = (dev32(t64(2, 3, 4, 5, ch, seed=ch), dev, True) for ch in (4, 6, 16))
+    out = b3d.ops.concat([a, b, c])
+    ref = torch.cat([a.detach(), b.detach(), c.detach()], dim=-1)
+    assert torch.equal(out, ref)
+    g = dev32(t64(*out.shape, seed=9), dev)
+    (out * g).sum().backward()
+    assert torch.equal(a.grad, g[..., :4]) and torch.equal(b.grad, g[..., 4:10]) and torch.equal(c.grad, g[..., 10:])
+    x = torch.ones(1, 32, 32, 32, 2, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    y1 = b3d.ops.dropout(x, 0.2, True, None, 123, cnt)
+    y2 = b3d.ops.dropout(x, 0.2, True, None, 123, cnt)
+    keep = float((y1 > 0).float().mean())
+    assert abs(keep - 0.8) < 0.01 and abs(float(y1.max()) - 1.25) < 1e-6
+    assert not torch.equal(y1, y2) and int(cnt) == 2
+    assert b3d.ops.dropout(x, 0.2, False) is x
