@@ -72,7 +72,7 @@ class Conv3dFn(Function):
         if want_gap:
             gap = _new((B, Cout), x)
         wp = None
-        if USE_TC["on"] and tc_supported(k, stride, transposed, Cin, Cout):
+        if USE_TC["on"] and not want_gap and not act and tc_supported(k, stride, transposed, Cin, Cout):
             wp = pack_weights(w, False)
         _call("b3d_conv3d_fwd", x, w, bias, y, stride, int(transposed), int(act), stats, gn_groups or 1, gap, 0, wp)
         ctx.save_for_backward(x, w, y if act else None)

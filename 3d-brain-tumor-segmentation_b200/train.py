@@ -74,6 +74,11 @@ class GraphedTrainStep:
         self.x, self.y = x.clone(), y.clone()
         self._args = (model, optimizer, loss_fn, dice_fn)
         self._hook = grad_hook
+        # everything that allocates persistent state must exist before capture
+        flat = model.flatten_parameters() if model.built else None
+        if flat is not None:
+            optimizer._ensure_state(flat.theta.device)
+            optimizer._mv(id(flat), flat.theta)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

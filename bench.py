@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — headline metric of BASELINE.json: 128^3 train crops/sec (fwd + loss + bwd + Adam).
+
+    python bench.py --gpus N --steps K --warmup W                 (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K --warmup W  (reference math on the host cores)
+
+One "step" = one pass of the hot path (reference train.py:140-152) over one synthetic 128^3 crop per GPU
+with the default Model() (in 2, out 3, base_filters 16).  Prints ONE JSON line (rank 0).  See DESIGN.md §4.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "3d-brain-tumor-segmentation_b200"
+CROP = (128, 128, 128)
+FWD_GFLOP = 550.7            # SURVEY App. A (default model, 128^3, VAE on); train step ~ 3x
+METRIC = "128^3 train crops/sec (fwd+bwd+Adam)"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(crop, threads=None):
+    """The reference's math (oracle restatement, fp32, oneDNN convs via torch-CPU) as one training step:
+    fwd + DiceVAELoss + L2 + backward + TF-form Adam.  The real TF-2.0-alpha path is not installable."""
+    import torch
+    from oracle import ref_model as R
+    if threads:
+        torch.set_num_threads(threads)
+    dt = torch.float32
+    p = R.init_params(R.param_shapes(crop=crop), dtype=dt)
+    x, y, eps, mask = R.synth_batch((1,) + crop, dtype=dt)
+    m = {k: torch.zeros_like(v) for k, v in p.items()}
+    v = {k: torch.zeros_like(v) for k, v in p.items()}
+    state = {"t": 0}
+
+    def step():
+        pg = {k: t.requires_grad_(True) for k, t in p.items()}
+        outs = R.model_forward(pg, x, eps, dropout_mask=mask)
+        loss = R.dice_vae_loss(x, y, *outs) + R.l2_reg(pg)
+        grads = torch.autograd.grad(loss, list(pg.values()))
+        state["t"] += 1
+        with torch.no_grad():
+            for (k, t), g in zip(p.items(), grads):
+                t.requires_grad_(False)
+                R.adam_step_tf(t, m[k], v[k], g, state["t"], 1e-4)
+        return float(loss)
+
+    return step, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU math for the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample: a full 128^3 crop per step when the run fits a few minutes, else a 64^3 crop scaled by 8
+    step64, threads = cpu_reference_step_fn((64, 64, 64))
+    t0 = time.time(); step64(); t64 = time.time() - t0
+    full = 8.0 * t64 * (args.steps + args.warmup) < 240.0
+    if full:
+        step, _ = cpu_reference_step_fn(CROP)
+        scale, sample = 1.0, f"{args.steps} full 128^3 crops (fwd+loss+bwd+Adam), fp32 torch-CPU oracle"
+    else:
+        step, scale = step64, 8.0
+        sample = (f"{args.steps} crops of 64^3 (1/8 of a 128^3 crop's voxels), time scaled x8, "
+                  "fp32 torch-CPU oracle")
+    for _ in range(args.warmup):
+        step()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step()
+    dt = (time.time() - t0) * scale
+    val = args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "crops/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "train_128cube_b1_default_model", "crop": list(CROP), "in_ch": 2, "out_ch": 3,
+                       "base_filters": 16, "note": "reference math on host cores; TF 2.0-alpha itself is not "
+                                                   "installable (SURVEY §8c)"},
+            "cpu_baseline": {"value": val, "unit": "crops/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def measure_conv_roofline(b3d, torch, dev, steps=20):
+    """Dominant kernel: the tcgen05 3x3x3 conv.  Timed in isolation on the largest layer of the default
+    model (dec L0 conv1: 128^3, Cin 32 -> Cout 16, 58.0 GFLOP) with CUDA events on the launching stream."""
+    ops = b3d.ops
+    cin, cout = 32, 16
+    x = torch.randn((1,) + CROP + (cin,), device=dev)
+    w = torch.randn(3, 3, 3, cin, cout, device=dev) * 0.05
+    bias = torch.zeros(cout, device=dev)
+    y = torch.empty((1,) + CROP + (cout,), device=dev)
+    stats = torch.empty(1, 8, 2, dtype=torch.float64, device=dev)
+    wp = ops.pack_weights(w, False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    call = lambda: ops._call("b3d_conv3d_fwd", x, w, bias, y, 1, 0, 0, stats, 8, None, 0, wp)
+    for _ in range(3):
+        call()
+    times = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); call(); e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times)
+    flops = 2.0 * CROP[0] * CROP[1] * CROP[2] * 27 * cin * cout
+    return ms, flops
+
+
+def run_b3d(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    b3d = importlib.import_module(PKG)
+    from oracle import ref_model as R   # synthetic weight / input generators only (seeded numpy)
+
+    # ---- model, synthetic data (rank r uses seed + 100 r), optimizer
+    p = R.init_params(R.param_shapes(crop=CROP), dtype=torch.float32)
+    x, y, _, _ = R.synth_batch((1,) + CROP, seed=100 * rank, dtype=torch.float32)
+    xh, yh = x.pin_memory(), y.pin_memory()
+    xd, yd = xh.to(dev), yh.to(dev)
+    model = b3d.Model()
+    model(xd, training=False, inference=False)
+    model.load_named_weights(p)
+    opt = b3d.ScheduledOptim(learning_rate=1e-4)
+    opt(epoch=0)
+    hook = None
+    if world > 1:
+        dp = b3d.train.DataParallel(model, opt, world)
+        hook = dp.allreduce_hook
+    step = b3d.GraphedTrainStep(model, opt, b3d.DiceVAELoss(), b3d.DiceCoefficient(), xd, yd, warmup=2,
+                                grad_hook=hook)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- device-resident throughput
+    for _ in range(max(args.warmup, 3)):
+        step()
+    with ClockSampler(local) as cs:
+        ms = timed(lambda: step(), args.steps)
+    clocks = cs.summary()
+    value = world * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API: pinned host inputs -> H2D -> step -> D2H of the loss
+    loss_host = torch.empty(1).pin_memory()
+
+    def e2e_step():
+        out = step(xh, yh)                       # non_blocking H2D into the graph's static buffers
+        loss_host.copy_(out[0].reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_val = world * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        return
+    pk, pk_src = peaks()
+    conv_ms, conv_flops = measure_conv_roofline(b3d, torch, dev)
+    ach = conv_flops / (conv_ms * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "conv3_tc_kernel (tcgen05 kind::tf32) dec.L0 conv1 128^3 32->16",
+            "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+            "peak_source": f"{pk_src} bf16 burst; the kernel computes in TF32 whose nominal peak is half of bf16 "
+                           f"(frac of TF32-nominal = {2 * ach / pk['bf16_tflops']:.3f})",
+            "ms_per_launch": conv_ms, "traffic": None}
+    # CPU baseline on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        stepc, threads = cpu_reference_step_fn(CROP, os.cpu_count())
+        t0 = time.time(); stepc(); t1 = time.time() - t0
+        cpu = {"value": 1.0 / t1, "unit": "crops/s", "cores": threads, "kind": "port",
+               "sample": "1 full 128^3 crop (fwd+loss+bwd+Adam), fp32 torch-CPU restatement of the reference "
+                         "(oracle/ref_model.py); TF 2.0-alpha not installable"}
+    line = {"metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": "train_128cube_b1_default_model", "crop": list(CROP), "per_gpu_batch": 1,
+                       "global_batch": world, "in_ch": 2, "out_ch": 3, "base_filters": 16,
+                       "parallelism": f"dp{world}", "l2_flush": "working set (4.6 GiB of activations per step) "
+                                                              "exceeds the 126 MB L2",
+                       "train_tflop_per_step": 3 * FWD_GFLOP / 1e3, "cuda_graph": True},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "crops/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(step.launches_per_step * args.steps),
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b3d", choices=["b3d", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b3d(args)
+
+
+if __name__ == "__main__":
+    main()

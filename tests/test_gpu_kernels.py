@@ -216,8 +216,8 @@ def test_adam_matches_tf_form(b3d, dev):
     opt.apply_gradients([(dev32(g1, dev), var)])
     opt.apply_gradients([(dev32(g2, dev), var)])
     assert opt.iterations == 2
-    assert float((var.cpu().double() - ref).abs().max()) < 1e-7
-    assert rel(var - dev32(th, dev), ref - th) < 1e-5
+    assert float((var.cpu().double() - ref).abs().max()) < 1e-6
+    assert rel(var - dev32(th, dev), ref - th) < 5e-3      # update ~2e-4 on values ~1 in fp32
 
 
 def test_concat_and_dropout(b3d, dev):
@@ -236,3 +236,54 @@ def test_concat_and_dropout(b3d, dev):
     assert abs(keep - 0.8) < 0.01 and abs(float(y1.max()) - 1.25) < 1e-6
     assert not torch.equal(y1, y2) and int(cnt) == 2
     assert b3d.ops.dropout(x, 0.2, False) is x
+
+
+TC_CASES = [
+    # (B, spatial, Cin, Cout)
+    (1, (8, 16, 16), 16, 16),
+    (2, (4, 16, 8), 8, 32),
+    (1, (6, 32, 24), 32, 64),
+    (1, (5, 24, 20), 64, 128),      # partial tiles in every dim (inference-like 20x24x20)
+    (1, (4, 16, 16), 128, 256),     # N split
+    (1, (16, 16, 16), 512, 128),
+    (1, (3, 7, 9), 16, 48),
+    (1, (32, 32, 32), 16, 16),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tc_conv_vs_oracle_and_generic(b3d, dev, case):
+    """tcgen05 implicit GEMM (TF32) vs the fp64 oracle (<= 2e-3) and vs the fp32 CUDA-core kernel,
+    including the fused GroupNorm statistics and the dgrad (flipped/transposed packing)."""
+    B, sp, cin, cout = case
+    assert b3d.ops.tc_supported(3, 1, False, cin, cout)
+    x = t64(B, *sp, cin, seed=21)
+    w = t64(3, 3, 3, cin, cout, seed=22, scale=(2.0 / (27 * cin)) ** 0.5)
+    bias = t64(cout, seed=23)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = R.conv3d_same(xr, wr, bias, 1)
+    gy = t64(*yr.shape, seed=24)
+    (yr * gy).sum().backward()
+    S = sp[0] * sp[1] * sp[2]
+    groups = 8 if S % 8 == 0 else 0
+    res = {}
+    for tc in (False, True):
+        b3d.ops.USE_TC["on"] = tc
+        try:
+            xd, wd, bd = dev32(x, dev, True), dev32(w, dev, True), dev32(bias, dev, True)
+            y, stats, _ = b3d.ops.conv3d(xd, wd, bd, 1, False, 0, groups, False)
+            (y * dev32(gy, dev)).sum().backward()
+            torch.cuda.synchronize()
+            res[tc] = (y.detach(), stats, xd.grad, wd.grad)
+        finally:
+            b3d.ops.USE_TC["on"] = True
+    for tc, tol in ((False, TOL32), (True, TOL_TF32)):
+        y, stats, dx, dw = res[tc]
+        assert rel(y, yr) < tol, ("y", tc, rel(y, yr))
+        assert rel(dx, xr.grad) < tol, ("dx", tc, rel(dx, xr.grad))
+        assert rel(dw, wr.grad) < tol, ("dw", tc)
+        if groups:
+            ch = yr.detach().reshape(B, groups, -1)
+            ref = torch.stack([ch.sum(-1), (ch ** 2).sum(-1)], dim=-1)
+            assert rel(stats, ref) < max(tol, 1e-4), ("stats", tc)
+    assert rel(res[True][0], res[False][0]) < TOL_TF32
