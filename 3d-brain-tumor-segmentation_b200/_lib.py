@@ -73,7 +73,7 @@ _i, _f, _v, _ll, _ull = C.c_int, C.c_float, C.c_void_p, C.c_longlong, C.c_ulongl
 SIGNATURES = {
     "b3d_conv3d_fwd": "TTTTiiiTiTiTv",
     "b3d_conv3d_dgrad": "TTTiiiTv",
-    "b3d_conv3d_wgrad": "TTTTiiv",
+    "b3d_conv3d_wgrad": "TTTTiiTTv",
     "b3d_conv3d_pack_weights": "TTiv",
     "b3d_gn_stats": "TTiv",
     "b3d_gn_apply": "TTTTTifiv",
@@ -108,6 +108,8 @@ for _name, _sig in SIGNATURES.items():
 lib.b3d_conv3d_tc_supported.argtypes = [_i] * 5
 lib.b3d_conv3d_tc_supported.restype = _i
 lib.b3d_conv3d_packed_elems.argtypes = [_i] * 3
+lib.b3d_conv3d_wgrad_tc_supported.argtypes = [_i] * 5
+lib.b3d_conv3d_wgrad_tc_supported.restype = _i
 
 
 class B3DError(RuntimeError):

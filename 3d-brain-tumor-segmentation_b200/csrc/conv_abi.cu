@@ -165,7 +165,8 @@ extern "C" int b3d_conv3d_dgrad(const DLTensor* dy_, const DLTensor* w_, DLTenso
 }
 
 extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTensor* dw_, DLTensor* dbias_,
-                                int stride, int transposed, void* stream) {
+                                int stride, int transposed, const DLTensor* x_bf16_, const DLTensor* dy_bf16_,
+                                void* stream) {
   TView x, dy, dw;
   int k;
   B3D_TRY(view(x_, DT_F32, 5, true, "x", &x));
@@ -184,8 +185,30 @@ extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTenso
   wg.Ds = (int)sml.shape[1]; wg.Hs = (int)sml.shape[2]; wg.Ws = (int)sml.shape[3]; wg.nB = (int)sml.shape[4];
   wg.k = k; wg.s = stride; wg.pad = stride == 1 ? k / 2 : 0;
   wg.bigp = big.pitch; wg.smallp = sml.pitch;
-  B3D_TRY(launch_conv_wgrad(wg, (const float*)big.p, (const float*)sml.p, (float*)dw.p, s));
-  if (dbias_ != nullptr) {
+  bool bias_done = false;
+  if (x_bf16_ != nullptr && dy_bf16_ != nullptr) {
+    // tensor-core path: bf16 copies (caller-allocated, same shapes, contiguous) are filled here
+    TView xb, yb;
+    B3D_TRY(view(x_bf16_, DT_BF16, 5, false, "x_bf16", &xb));
+    B3D_TRY(view(dy_bf16_, DT_BF16, 5, false, "dy_bf16", &yb));
+    B3D_REQUIRE(!transposed && xb.numel == x.numel && yb.numel == dy.numel, B3D_ERR_SHAPE, "wgrad: bf16 buffer shapes");
+    B3D_REQUIRE(x.pitch == x.shape[4] && dy.pitch == dy.shape[4], B3D_ERR_LAYOUT, "wgrad (tcgen05): contiguous inputs");
+    B3D_REQUIRE(tc_wgrad_supported(wg), B3D_ERR_UNSUPPORTED, "wgrad: shape not on the tcgen05 path");
+    float* db = nullptr;
+    if (dbias_ != nullptr) {
+      TView dbv;
+      B3D_TRY(view(dbias_, DT_F32, 1, false, "dbias", &dbv));
+      B3D_REQUIRE(dbv.numel == dy.shape[4], B3D_ERR_SHAPE, "dbias: expected %lld values", (long long)dy.shape[4]);
+      db = (float*)dbv.p;
+      bias_done = true;
+    }
+    B3D_TRY(launch_cast_bf16((const float*)x.p, xb.p, x.numel / x.shape[4], (int)x.shape[4], nullptr, s));
+    B3D_TRY(launch_cast_bf16((const float*)dy.p, yb.p, dy.numel / dy.shape[4], (int)dy.shape[4], db, s));
+    B3D_TRY(launch_conv_wgrad_tc(wg, xb.p, yb.p, (float*)dw.p, s));
+  } else {
+    B3D_TRY(launch_conv_wgrad(wg, (const float*)big.p, (const float*)sml.p, (float*)dw.p, s));
+  }
+  if (dbias_ != nullptr && !bias_done) {
     TView db;
     B3D_TRY(view(dbias_, DT_F32, 1, false, "dbias", &db));
     B3D_REQUIRE(db.numel == dy.shape[4], B3D_ERR_SHAPE, "dbias: expected %lld values", (long long)dy.shape[4]);
@@ -193,6 +216,14 @@ extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTenso
                           true, s));
   }
   return B3D_OK;
+}
+
+// 1 when the tcgen05 weight-gradient kernel handles a 3x3x3 stride-1 conv of these channel counts
+extern "C" int b3d_conv3d_wgrad_tc_supported(int k, int stride, int transposed, int cin, int cout) {
+  WgradGeom wg;
+  memset(&wg, 0, sizeof(wg));
+  wg.k = k; wg.s = stride; wg.nA = cin; wg.nB = cout; wg.bigp = cin; wg.smallp = cout;
+  return (!transposed && tc_wgrad_supported(wg)) ? 1 : 0;
 }
 
 // 1 when the tcgen05 implicit-GEMM kernel handles a (gather-form) conv of these channel counts

@@ -38,4 +38,8 @@ int launch_conv_tc(const ConvGeom& cg, const float* x, const float* wpacked, con
 size_t tc_packed_weight_elems(int k, int Cin, int Cout);
 int launch_tc_pack_weights(const ConvGeom& cg, const float* w, float* wpacked, cudaStream_t s);
 
+bool tc_wgrad_supported(const WgradGeom& wg);
+int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x_bf16, const void* dy_bf16, float* dw, cudaStream_t s);
+int launch_cast_bf16(const float* src, void* dst, long long nvox, int C, float* colsum, cudaStream_t s);
+
 }  // namespace b3d

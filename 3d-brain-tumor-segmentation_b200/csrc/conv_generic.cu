@@ -221,6 +221,97 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// weight gradient for SMALL channel products (taps*nA*nB <= 1024: the Cin=2 first conv, the Cout<=3
+// output convs, the shallow 1x1x1 convs).  Every thread owns <= 4 outputs (tap,a,b) for the whole
+// kernel and walks the voxels of shared-memory staged tiles; b varies fastest across a warp so the
+// SMALL reads are conflict-free and the BIG reads are broadcasts.
+constexpr int kSmallMaxOut = 4;
+
+__global__ void __launch_bounds__(256)
+    conv_wgrad_small_kernel(WgradGeom wg, const float* __restrict__ big, const float* __restrict__ small,
+                            float* __restrict__ dw, int TD, int TH, int TW, int ntd, int nth, int ntw) {
+  extern __shared__ float sm[];
+  const int taps = wg.k * wg.k * wg.k;
+  const int nout = taps * wg.nA * wg.nB;
+  const int ED = wg.s * (TD - 1) + wg.k, EH = wg.s * (TH - 1) + wg.k, EW = wg.s * (TW - 1) + wg.k;
+  float* sb = sm;                                  // [ED][EH][EW][nA]
+  float* ss = sm + (size_t)ED * EH * EW * wg.nA;   // [TD][TH][TW][nB]
+  int oa[kSmallMaxOut], ob[kSmallMaxOut], ooff[kSmallMaxOut];
+  float acc[kSmallMaxOut];
+#pragma unroll
+  for (int i = 0; i < kSmallMaxOut; ++i) {
+    const int o = threadIdx.x + i * 256;
+    acc[i] = 0.f;
+    if (o < nout) {
+      const int b = o % wg.nB, a = (o / wg.nB) % wg.nA, t = o / (wg.nB * wg.nA);
+      const int tk = t % wg.k, th = (t / wg.k) % wg.k, td = t / (wg.k * wg.k);
+      oa[i] = a; ob[i] = b; ooff[i] = ((td * EH + th) * EW + tk) * wg.nA + a;
+    } else {
+      oa[i] = -1; ob[i] = 0; ooff[i] = 0;
+    }
+  }
+  const int ntiles = wg.B * ntd * nth * ntw;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int q = tile;
+    const int wt = q % ntw; q /= ntw;
+    const int ht = q % nth; q /= nth;
+    const int dt = q % ntd; q /= ntd;
+    const int n = q;
+    const int d0 = dt * TD, h0 = ht * TH, w0 = wt * TW;
+    __syncthreads();
+    // stage BIG (zero outside the volume) and SMALL (zero outside the volume)
+    const int nb_el = ED * EH * EW * wg.nA;
+    for (int i = threadIdx.x; i < nb_el; i += 256) {
+      const int a = i % wg.nA; int r = i / wg.nA;
+      const int ew = r % EW; r /= EW;
+      const int eh = r % EH; const int ed = r / EH;
+      const int id = wg.s * d0 - wg.pad + ed, ih = wg.s * h0 - wg.pad + eh, iw = wg.s * w0 - wg.pad + ew;
+      float v = 0.f;
+      if (id >= 0 && id < wg.Db && ih >= 0 && ih < wg.Hb && iw >= 0 && iw < wg.Wb)
+        v = big[((((long long)n * wg.Db + id) * wg.Hb + ih) * wg.Wb + iw) * wg.bigp + a];
+      sb[i] = v;
+    }
+    const int ns_el = TD * TH * TW * wg.nB;
+    for (int i = threadIdx.x; i < ns_el; i += 256) {
+      const int b = i % wg.nB; int r = i / wg.nB;
+      const int tw = r % TW; r /= TW;
+      const int th = r % TH; const int td = r / TH;
+      const int od = d0 + td, oh = h0 + th, ow = w0 + tw;
+      float v = 0.f;
+      if (od < wg.Ds && oh < wg.Hs && ow < wg.Ws)
+        v = small[((((long long)n * wg.Ds + od) * wg.Hs + oh) * wg.Ws + ow) * wg.smallp + b];
+      ss[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kSmallMaxOut; ++i) {
+      if (oa[i] < 0) continue;
+      float a0 = 0.f, a1 = 0.f;
+      const float* bp = sb + ooff[i];
+      const float* sp = ss + ob[i];
+      for (int td = 0; td < TD; ++td)
+        for (int th = 0; th < TH; ++th) {
+          const float* brow = bp + ((td * wg.s) * EH + th * wg.s) * EW * wg.nA;
+          const float* srow = sp + (td * TH + th) * TW * wg.nB;
+          int tw = 0;
+          for (; tw + 1 < TW; tw += 2) {
+            a0 = fmaf(brow[(tw * wg.s) * wg.nA], srow[tw * wg.nB], a0);
+            a1 = fmaf(brow[((tw + 1) * wg.s) * wg.nA], srow[(tw + 1) * wg.nB], a1);
+          }
+          if (tw < TW) a0 = fmaf(brow[(tw * wg.s) * wg.nA], srow[tw * wg.nB], a0);
+        }
+      acc[i] += a0 + a1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kSmallMaxOut; ++i) {
+    const int o = threadIdx.x + i * 256;
+    if (o < nout) atomicAdd(&dw[o], acc[i]);      // dw[t][a][b] is exactly index o
+  }
+}
+
 // per-channel column sums:  out[c] (+)= sum_n x[n][c]      (bias gradients, GAP)
 __global__ void __launch_bounds__(256)
     colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long N, int C, long long pitch,
@@ -271,6 +362,27 @@ int launch_conv_wgrad(const WgradGeom& wg, const float* big, const float* small,
   if (split > maxsplit) split = (int)maxsplit;
   if (split < 1) split = 1;
   B3D_TRY(cuda_ok(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)taps * wg.nA * wg.nB, s), "memset dw"));
+  if (taps * wg.nA * wg.nB <= 256 * kSmallMaxOut) {
+    const int TD = 4, TH = 8, TW = 16;
+    const int ED = wg.s * (TD - 1) + wg.k, EH = wg.s * (TH - 1) + wg.k, EW = wg.s * (TW - 1) + wg.k;
+    const size_t smem = sizeof(float) * ((size_t)ED * EH * EW * wg.nA + (size_t)TD * TH * TW * wg.nB);
+    if (smem <= 160 * 1024) {
+      static bool attr = false;
+      if (!attr) {
+        B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv_wgrad_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             160 * 1024), "cudaFuncSetAttribute(wgrad_small)"));
+        attr = true;
+      }
+      const int ntd = (wg.Ds + TD - 1) / TD, nth = (wg.Hs + TH - 1) / TH, ntw = (wg.Ws + TW - 1) / TW;
+      const int ntiles = wg.B * ntd * nth * ntw;
+      const int ctas_per_sm = smem > 100 * 1024 ? 1 : 2;
+      int grid = ctas_per_sm * sm_count();
+      if (grid > ntiles) grid = ntiles;
+      conv_wgrad_small_kernel<<<grid, 256, smem, s>>>(wg, big, small, dw, TD, TH, TW, ntd, nth, ntw);
+      B3D_LAUNCH_CHECK("conv_wgrad_small");
+      return B3D_OK;
+    }
+  }
   conv_wgrad_kernel<<<dim3(tiles, taps, split), 256, 0, s>>>(wg, big, small, dw);
   B3D_LAUNCH_CHECK("conv_wgrad");
   return B3D_OK;

@@ -1,0 +1,315 @@
+// b3d — weight gradient of the 3x3x3 stride-1 SAME convolution on the tcgen05 tensor cores:
+//     dw[tap][ci][co] = sum_voxels x[v + tap - 1][ci] * dy[v][co]          (train.py:151, tape.gradient)
+// as 27 shifted GEMMs  D_tap[ci][co] += X_tap^T . dY  with the VOXELS as the contraction dimension:
+//   * A = x halo tile, B = dy tile, both bf16 (fp32 accumulate) in a 16-byte-cell plane layout
+//     plane[c/8][voxel][8 ch], which for a reduction over voxels is the canonical *MN-major*
+//     SWIZZLE_NONE UMMA layout (verified on hardware by tools/umma_probe_bf16.cu; kind::tf32 does not
+//     accept MN-major SWIZZLE_NONE operands — tools/umma_probe.cu — hence bf16 here):
+//     8 consecutive-w voxels = the 8 K-rows of a core matrix (16 B apart), the second K group = the
+//     next h row (LBO = row pitch), channel groups of 8 = MN groups one plane apart (SBO = plane
+//     bytes).  One MMA contracts 16 voxels for M = 128 input channels x N = Cout, and the tap shift is
+//     again only a start-address offset into the resident halo.
+//   * the bf16 copies of x and dy are produced by cast_bf16_kernel below (which also emits the bias
+//     gradient = column sums of dy), so the tiles can be fetched by TMA.
+//   * accumulators D_tap live in TMEM for the whole kernel (TG taps x Cout columns <= 512); taps are
+//     split into groups (27 / 9 / 3 / 1 taps) and input channels into tiles of 128 across CTAs; the
+//     voxel tiles of one (channel tile, tap group) are spread over `nsplit` persistent CTAs and the
+//     partial results are reduced into dw with fp32 atomics at the end (dw pre-zeroed).
+//   * when fewer than 128 input channels remain, the missing MN groups address shared memory past the
+//     real planes (still inside this CTA's allocation, enforced by the host planner); the
+//     corresponding accumulator rows are never read.
+#include "common.cuh"
+#include "conv_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace b3d {
+
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct WgParams {
+  float* dw;
+  int Cin, Cout;
+  int TD, TH, TW, HD, HH, HW;      // tile and x-halo extents (voxels)
+  int px, py;                      // plane bytes of x halo / dy tile
+  int stage_bytes, nstages, xplanes_max;
+  int ntd, nth, ntw, ntiles;
+  int nsplit;
+};
+
+constexpr int kWgSmem = 227 * 1024;
+
+template <int TG>
+__global__ void __launch_bounds__(256, 1)
+    conv3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+                          const WgParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // barriers live at the very end of the allocation (the garbage MN groups never reach them: host planner)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgSmem - 128);
+  uint64_t* full = bars;        // [4]
+  uint64_t* empty = bars + 4;   // [4]
+  uint64_t* done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tg = blockIdx.y;                 // tap group
+  const int cbase = blockIdx.z * 128;        // input-channel tile
+  const int crem = min(128, prm.Cin - cbase);
+  const int xplanes = crem / 8, yplanes = prm.Cout / 8;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < prm.nstages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+    mbar_init(smem_u32(done), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // first tap of this group and the halo origin shift it implies
+  int gkd = 0, gkh = 0, gkw = 0;
+  if (TG == 9) gkd = tg;
+  if (TG == 3) { gkd = tg / 3; gkh = tg % 3; }
+  if (TG == 1) { gkd = tg / 9; gkh = (tg / 3) % 3; gkw = tg % 3; }
+  const int od = (TG == 27) ? -1 : gkd - 1;
+  const int oh = (TG >= 9) ? -1 : gkh - 1;
+  const int ow = (TG >= 3) ? -1 : gkw - 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      const uint32_t bytes = (uint32_t)(xplanes * prm.px + yplanes * prm.py);
+      for (int tile = blockIdx.x; tile < prm.ntiles; tile += prm.nsplit) {
+        int t = tile;
+        const int wt = t % prm.ntw; t /= prm.ntw;
+        const int ht = t % prm.nth; t /= prm.nth;
+        const int dt = t % prm.ntd; t /= prm.ntd;
+        const int b = t;
+        const int w0 = wt * prm.TW, h0 = ht * prm.TH, d0 = dt * prm.TD;
+        mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+        const uint32_t fb = smem_u32(&full[s]);
+        mbar_expect_tx(fb, bytes);
+        const uint32_t xdst = smem_u32(smem + (size_t)s * prm.stage_bytes);
+        const uint32_t ydst = xdst + (uint32_t)(prm.xplanes_max * prm.px);
+        for (int p = 0; p < xplanes; ++p)
+          tma_load_5d(xdst + p * prm.px, &tmx, cbase + 8 * p, w0 + ow, h0 + oh, d0 + od, b, fb);
+        for (int q = 0; q < yplanes; ++q) tma_load_5d(ydst + q * prm.py, &tmy, 8 * q, w0, h0, d0, b, fb);
+        if (++s == prm.nstages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D=f32, A=B=bf16, both MN-major, N=Cout, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(prm.Cout >> 3) << 17) | ((128u >> 4) << 24);
+      int s = 0, ph = 0;
+      uint32_t acc = 0;
+      const int rowc = prm.HW, planec = prm.HH * prm.HW;
+      for (int tile = blockIdx.x; tile < prm.ntiles; tile += prm.nsplit) {
+        mbar_wait(smem_u32(&full[s]), ph);
+        tc_fence_after();
+        const uint32_t xaddr = smem_u32(smem + (size_t)s * prm.stage_bytes);
+        // K = 16 voxels per MMA: 8 along w (16 B apart) x 2 h rows (LBO = row pitch of each operand)
+        const uint64_t adesc0 = make_desc(xaddr, (uint32_t)prm.HW * 16, (uint32_t)prm.px);
+        const uint64_t bdesc0 =
+            make_desc(xaddr + (uint32_t)(prm.xplanes_max * prm.px), (uint32_t)prm.TW * 16, (uint32_t)prm.py);
+        for (int d = 0; d < prm.TD; ++d)
+          for (int h = 0; h < prm.TH; h += 2)
+            for (int w8 = 0; w8 < prm.TW; w8 += 8) {
+              const uint32_t ycell = (uint32_t)((d * prm.TH + h) * prm.TW + w8);
+              const uint32_t xcell = (uint32_t)((d * prm.HH + h) * prm.HW + w8);
+              const uint64_t bdesc = bdesc0 + ycell;
+#pragma unroll
+              for (int t = 0; t < TG; ++t) {
+                const int tkd = (TG == 27) ? t / 9 : 0;
+                const int tkh = (TG >= 9) ? (t / 3) % 3 : 0;
+                const int tkw = (TG >= 3) ? t % 3 : 0;
+                const uint32_t off = xcell + (uint32_t)(tkd * planec + tkh * rowc + tkw);
+                tc_mma_bf16(tmem_base + t * prm.Cout, adesc0 + off, bdesc, idesc, acc);
+              }
+              acc = 1;
+            }
+        tc_commit(smem_u32(&empty[s]));
+        if (++s == prm.nstages) { s = 0; ph ^= 1; }
+      }
+      tc_commit(smem_u32(done));
+    }
+  } else if (warp >= 4) {
+    // final reduction of this CTA's partial dw into global memory
+    const int q = warp - 4;
+    const int ci = cbase + q * 32 + lane;
+    mbar_wait(smem_u32(done), 0);
+    tc_fence_after();
+    const bool has_tiles = blockIdx.x < prm.ntiles;
+#pragma unroll 1
+    for (int t = 0; t < TG; ++t) {
+      const int tap = (TG == 27) ? t : (TG == 9 ? tg * 9 + t : (TG == 3 ? tg * 3 + t : tg));
+      float* dst = prm.dw + ((size_t)tap * prm.Cin + ci) * prm.Cout;
+      for (int j = 0; j < prm.Cout; j += 16) {
+        float v[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + t * prm.Cout + j, v);
+        if (has_tiles && ci < prm.Cin) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dst + j + i, v[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+bool tc_wgrad_supported(const WgradGeom& wg) {
+  return wg.k == 3 && wg.s == 1 && wg.nA % 8 == 0 && wg.nA >= 8 && wg.nB % 16 == 0 && wg.nB >= 16 &&
+         wg.nB <= 256 && wg.bigp % 8 == 0 && wg.smallp % 8 == 0;
+}
+
+static int make_map(CUtensorMap* tm, const void* base, int C, long long pitch, int W, int H, int D, int B,
+                    int bw, int bh, int bd) {
+  EncodeTiledFn enc = tma_encode_fn();
+  B3D_REQUIRE(enc != nullptr, B3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  const cuuint64_t strides[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 2 * W, (cuuint64_t)pitch * 2 * W * H,
+                                 (cuuint64_t)pitch * 2 * W * H * D};
+  const cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B3D_REQUIRE(r == CUDA_SUCCESS, B3D_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return B3D_OK;
+}
+
+int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, float* dw, cudaStream_t s) {
+  B3D_REQUIRE(tc_wgrad_supported(wg), B3D_ERR_UNSUPPORTED, "wgrad: shape not on the tcgen05 path");
+  B3D_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, B3D_ERR_LAYOUT, "wgrad: alignment");
+  const int Cin = wg.nA, Cout = wg.nB;
+  const int TG = 27 * Cout <= 512 ? 27 : (9 * Cout <= 512 ? 9 : (3 * Cout <= 512 ? 3 : 1));
+  const int ntg = 27 / TG;
+  const int nmt = (Cin + 127) / 128;
+  const int xpl = (Cin < 128 ? Cin : 128) / 8;
+  // tile planner: largest tile whose stages fit, with 16 MN groups (M=128 bf16) readable from every stage start
+  static const int cand[][3] = {{1, 4, 8},  {2, 4, 8},  {2, 4, 16}, {2, 8, 16},
+                                {4, 8, 16}, {4, 8, 32}, {4, 16, 32}};   // TH even: a K step spans 2 h rows
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  const int budget = kWgSmem - 128;
+  bool found = false;
+  for (int i = 0; i < (int)(sizeof(cand) / sizeof(cand[0])); ++i) {
+    const int TD = cand[i][0], TH = cand[i][1], TW = cand[i][2];
+    if (found && (TD > wg.Ds * 2 || TH > wg.Hs * 2 || TW > wg.Ws * 2)) continue;   // do not over-tile tiny volumes
+    const int HD = TD + (TG == 27 ? 2 : 0), HH = TH + (TG >= 9 ? 2 : 0), HW = TW + (TG >= 3 ? 2 : 0);
+    const int cells = HD * HH * HW;
+    if (cells % 8 != 0) continue;
+    const int px = cells * 16, py = TD * TH * TW * 16;
+    const long long stage = (long long)xpl * px + (long long)(Cout / 8) * py;
+    for (int ns = 3; ns >= 2; --ns) {
+      const long long last = (long long)(ns - 1) * stage;
+      if (ns * stage <= budget && last + 16LL * px <= budget) {
+        p.TD = TD; p.TH = TH; p.TW = TW; p.HD = HD; p.HH = HH; p.HW = HW;
+        p.px = px; p.py = py; p.stage_bytes = (int)stage; p.nstages = ns;
+        found = true;
+        break;
+      }
+    }
+  }
+  B3D_REQUIRE(found, B3D_ERR_UNSUPPORTED, "wgrad: no tile fits shared memory (Cin=%d Cout=%d)", Cin, Cout);
+  p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.xplanes_max = xpl;
+  p.ntd = (wg.Ds + p.TD - 1) / p.TD; p.nth = (wg.Hs + p.TH - 1) / p.TH; p.ntw = (wg.Ws + p.TW - 1) / p.TW;
+  p.ntiles = wg.B * p.ntd * p.nth * p.ntw;
+  int nsplit = sm_count() / (ntg * nmt);
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > p.ntiles) nsplit = p.ntiles;
+  p.nsplit = nsplit;
+  CUtensorMap tmx, tmy;
+  B3D_TRY(make_map(&tmx, x, Cin, wg.bigp, wg.Wb, wg.Hb, wg.Db, wg.B, p.HW, p.HH, p.HD));
+  B3D_TRY(make_map(&tmy, dy, Cout, wg.smallp, wg.Ws, wg.Hs, wg.Ds, wg.B, p.TW, p.TH, p.TD));
+  B3D_TRY(cuda_ok(cudaMemsetAsync(dw, 0, sizeof(float) * 27 * (size_t)Cin * Cout, s), "memset dw"));
+  dim3 grid((unsigned)nsplit, (unsigned)ntg, (unsigned)nmt);
+#define LAUNCH(T)                                                                                              \
+  do {                                                                                                         \
+    static bool attr = false;                                                                                  \
+    if (!attr) {                                                                                               \
+      B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv3_wgrad_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           kWgSmem), "cudaFuncSetAttribute(wgrad_tc)"));                        \
+      attr = true;                                                                                             \
+    }                                                                                                          \
+    conv3_wgrad_tc_kernel<T><<<grid, 256, kWgSmem, s>>>(tmx, tmy, p);                                          \
+  } while (0)
+  switch (TG) {
+    case 27: LAUNCH(27); break;
+    case 9: LAUNCH(9); break;
+    case 3: LAUNCH(3); break;
+    default: LAUNCH(1); break;
+  }
+#undef LAUNCH
+  B3D_LAUNCH_CHECK("conv3_wgrad_tc");
+  return B3D_OK;
+}
+
+
+// ---- fp32 -> bf16 copies for the tensor-core weight gradient (+ optional column sums = bias gradient)
+// thread -> (voxel, channel octet); the octet of a thread is loop-invariant (blockDim % (C/8) == 0)
+__global__ void cast_bf16_kernel(const float* __restrict__ src, uint4* __restrict__ dst, long long nvox, int C,
+                                 float* __restrict__ colsum) {
+  extern __shared__ float sm[];
+  const int oc = C / 8;
+  const int o = threadIdx.x % oc, vl = threadIdx.x / oc, vpb = blockDim.x / oc;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long v = (long long)blockIdx.x * vpb + vl; v < nvox; v += (long long)gridDim.x * vpb) {
+    const float4 a = ld_stream(reinterpret_cast<const float4*>(src + v * C + o * 8));
+    const float4 b = ld_stream(reinterpret_cast<const float4*>(src + v * C + o * 8) + 1);
+    uint4 r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(a.y), "f"(a.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(a.w), "f"(a.z));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.z) : "f"(b.y), "f"(b.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.w) : "f"(b.w), "f"(b.z));
+    dst[v * oc + o] = r;
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+  if (colsum != nullptr) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&sm[o * 8 + i], acc[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[i], sm[i]);
+  }
+}
+
+int launch_cast_bf16(const float* src, void* dst, long long nvox, int C, float* colsum, cudaStream_t s) {
+  B3D_REQUIRE(C % 8 == 0 && C <= 2048, B3D_ERR_UNSUPPORTED, "cast_bf16: channels must be a multiple of 8");
+  const int oc = C / 8;
+  const int threads = oc >= 256 ? oc : (256 / oc) * oc;
+  const int vpb = threads / oc;
+  long long blocks = (nvox + (long long)vpb * 8 - 1) / ((long long)vpb * 8);
+  const long long cap = 8LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (colsum != nullptr) B3D_TRY(cuda_ok(cudaMemsetAsync(colsum, 0, sizeof(float) * C, s), "memset colsum"));
+  cast_bf16_kernel<<<(unsigned)blocks, threads, sizeof(float) * C, s>>>(src, (uint4*)dst, nvox, C, colsum);
+  B3D_LAUNCH_CHECK("cast_bf16");
+  return B3D_OK;
+}
+
+}  // namespace b3d

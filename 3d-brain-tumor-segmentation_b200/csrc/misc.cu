@@ -331,17 +331,18 @@ __global__ void __launch_bounds__(256)
 }
 __global__ void adam_tick_kernel(double* state) { state[0] += 1.0; }
 
-// per-tensor L2 penalties: out[s] = scale * sum(flat[off[s]..off[s+1])^2)   (one CTA per tensor)
+// per-tensor L2 penalties: out[s] += scale * sum(flat[off[s]..off[s+1])^2)   (grid: slices x tensors)
 __global__ void __launch_bounds__(256)
     l2_losses_kernel(const float* __restrict__ flat, const long long* __restrict__ off, float* __restrict__ out,
                      float scale) {
-  const long long a = off[blockIdx.x], b = off[blockIdx.x + 1];
+  const long long a = off[blockIdx.y], b = off[blockIdx.y + 1];
   float s = 0.f;
-  for (long long i = a + threadIdx.x; i < b; i += blockDim.x) s += flat[i] * flat[i];
+  for (long long i = a + (long long)blockIdx.x * 256 + threadIdx.x; i < b; i += (long long)gridDim.x * 256)
+    s += flat[i] * flat[i];
   __shared__ double red[32];
   double d[1] = {(double)s};
   block_sum<1, double>(d, red);
-  if (threadIdx.x == 0) out[blockIdx.x] = (float)(d[0] * scale);
+  if (threadIdx.x == 0 && d[0] != 0.0) atomicAdd(&out[blockIdx.y], (float)(d[0] * scale));
 }
 // grad[i] += coef * gout * flat[i]  for i < n   (d/dw of scale*sum w^2 with coef = 2*scale)
 __global__ void __launch_bounds__(256)
@@ -353,13 +354,14 @@ __global__ void __launch_bounds__(256)
 }
 
 
-// grad[i] += coef * gout[s] * flat[i]  for i in segment s   (one CTA per tensor)
+// grad[i] += coef * gout[s] * flat[i]  for i in segment s   (grid: slices x tensors)
 __global__ void __launch_bounds__(256)
     l2_grad_kernel(const float* __restrict__ flat, float* __restrict__ grad, const long long* __restrict__ off,
                    const float* __restrict__ gout, float coef) {
-  const long long a = off[blockIdx.x], b = off[blockIdx.x + 1];
-  const float c = coef * gout[blockIdx.x];
-  for (long long i = a + threadIdx.x; i < b; i += blockDim.x) grad[i] += c * flat[i];
+  const long long a = off[blockIdx.y], b = off[blockIdx.y + 1];
+  const float c = coef * gout[blockIdx.y];
+  for (long long i = a + (long long)blockIdx.x * 256 + threadIdx.x; i < b; i += (long long)gridDim.x * 256)
+    grad[i] += c * flat[i];
 }
 
 // dst[n][0:C] (pitch dp) (+)= src[n][0:C] (pitch sp)   — virtual-concat materialisation / slicing
@@ -649,8 +651,9 @@ extern "C" int b3d_l2_losses(const DLTensor* flat_, const DLTensor* offsets_, DL
   B3D_TRY(flat_f32(out_, "out", &out));
   B3D_REQUIRE(off.numel == out.numel + 1, B3D_ERR_SHAPE, "l2_losses: offsets must have n+1 entries");
   if (out.numel == 0) return B3D_OK;
-  l2_losses_kernel<<<(unsigned)out.numel, 256, 0, (cudaStream_t)stream>>>((const float*)f.p, (const long long*)off.p,
-                                                                          (float*)out.p, scale);
+  B3D_TRY(cuda_ok(cudaMemsetAsync(out.p, 0, sizeof(float) * out.numel, (cudaStream_t)stream), "memset l2"));
+  l2_losses_kernel<<<dim3(16, (unsigned)out.numel), 256, 0, (cudaStream_t)stream>>>(
+      (const float*)f.p, (const long long*)off.p, (float*)out.p, scale);
   B3D_LAUNCH_CHECK("l2_losses");
   return B3D_OK;
 }
@@ -725,8 +728,8 @@ extern "C" int b3d_l2_grad(const DLTensor* flat_, DLTensor* grad_, const DLTenso
   B3D_TRY(flat_f32(gout_, "gout", &go));
   B3D_REQUIRE(off.numel == go.numel + 1 && g.numel == f.numel, B3D_ERR_SHAPE, "l2_grad: sizes");
   if (go.numel == 0) return B3D_OK;
-  l2_grad_kernel<<<(unsigned)go.numel, 256, 0, (cudaStream_t)stream>>>((const float*)f.p, (float*)g.p,
-                                                                       (const long long*)off.p, (const float*)go.p, coef);
+  l2_grad_kernel<<<dim3(16, (unsigned)go.numel), 256, 0, (cudaStream_t)stream>>>(
+      (const float*)f.p, (float*)g.p, (const long long*)off.p, (const float*)go.p, coef);
   B3D_LAUNCH_CHECK("l2_grad");
   return B3D_OK;
 }

@@ -103,7 +103,12 @@ class Conv3dFn(Function):
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
             db = _new((dy.shape[-1],), dy) if has_bias else None
-            _call("b3d_conv3d_wgrad", x, dy, dw, db, stride, int(transposed))
+            xb = yb = None
+            if USE_TC["on"] and lib.b3d_conv3d_wgrad_tc_supported(w.shape[0], stride, int(transposed), x.shape[-1],
+                                                                  dy.shape[-1]):
+                xb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+                yb = torch.empty(dy.shape, device=x.device, dtype=torch.bfloat16)
+            _call("b3d_conv3d_wgrad", x, dy, dw, db, stride, int(transposed), xb, yb)
         return dx, dw, db, None, None, None, None, None
 
 

@@ -55,9 +55,12 @@ int b3d_conv3d_fwd(const DLTensor* x, const DLTensor* w, const DLTensor* bias /*
 /* data gradient (what tape.gradient computes for the layer input, train.py:151) */
 int b3d_conv3d_dgrad(const DLTensor* dy, const DLTensor* w, DLTensor* dx, int stride, int transposed,
                      int accumulate, const DLTensor* wpacked, void* stream);
-/* weight (+ bias, nullable) gradient */
+/* weight (+ bias, nullable) gradient.  x_bf16 / dy_bf16 (nullable, bf16, same shapes as x / dy): scratch
+ * buffers; when both are given (and b3d_conv3d_wgrad_tc_supported) they are filled with bf16 copies and the
+ * tcgen05 kernel (bf16 operands, fp32 accumulation) is used, else the fp32 CUDA-core kernel. */
 int b3d_conv3d_wgrad(const DLTensor* x, const DLTensor* dy, DLTensor* dw, DLTensor* dbias, int stride,
-                     int transposed, void* stream);
+                     int transposed, const DLTensor* x_bf16, const DLTensor* dy_bf16, void* stream);
+int b3d_conv3d_wgrad_tc_supported(int k, int stride, int transposed, int cin, int cout);
 int b3d_conv3d_tc_supported(int k, int stride, int transposed, int c_gathered, int c_produced);
 long long b3d_conv3d_packed_elems(int k, int c_gathered, int c_produced);
 int b3d_conv3d_pack_weights(const DLTensor* w, DLTensor* packed, int dgrad, void* stream);
