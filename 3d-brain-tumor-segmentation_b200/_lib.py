@@ -91,7 +91,7 @@ SIGNATURES = {
     "b3d_dense_bwd": "TTTTTTTiv",
     "b3d_vae_sample_fwd": "TTTv",
     "b3d_vae_sample_bwd": "TTTTTTv",
-    "b3d_adam_step": "TTTTTffffiv",
+    "b3d_adam_step": "TTTTTfffffLiv",
     "b3d_l2_losses": "TTTfv",
     "b3d_l2_grad": "TTTTfv",
     "b3d_axpy": "TTLfTv",

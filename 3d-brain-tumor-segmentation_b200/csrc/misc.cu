@@ -295,7 +295,7 @@ __global__ void vae_sample_bwd_kernel(const float* __restrict__ proj, const floa
 __global__ void __launch_bounds__(256)
     adam_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
                 const float* __restrict__ g, long long n, const double* __restrict__ state, float b1, float b2,
-                float eps, float gscale) {
+                float eps, float gscale, float decay, long long n_decay) {
   __shared__ float s_alpha;
   if (threadIdx.x == 0) {
     const double t = state[0] + 1.0, lr = state[1];
@@ -311,8 +311,10 @@ __global__ void __launch_bounds__(256)
     const float4 gg = ld_stream(reinterpret_cast<const float4*>(g) + i);
     float* T = &th.x; float* M = &mm.x; float* V = &vv.x; const float* G = &gg.x;
 #pragma unroll
+    const float dk = (i * 4 < n_decay) ? decay : 0.f;    // regularised tensors are padded to 4 elements
+#pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float gr = G[u] * gscale;
+      const float gr = G[u] * gscale + dk * T[u];
       M[u] = b1 * M[u] + (1.f - b1) * gr;
       V[u] = b2 * V[u] + (1.f - b2) * gr * gr;
       T[u] -= alpha * M[u] / (sqrtf(V[u]) + eps);
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(256)
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (long long e = n4 * 4; e < n; ++e) {
-      const float gr = g[e] * gscale;
+      const float gr = g[e] * gscale + (e < n_decay ? decay : 0.f) * theta[e];
       m[e] = b1 * m[e] + (1.f - b1) * gr;
       v[e] = b2 * v[e] + (1.f - b2) * gr * gr;
       theta[e] -= alpha * m[e] / (sqrtf(v[e]) + eps);
@@ -621,7 +623,8 @@ extern "C" int b3d_vae_sample_bwd(const DLTensor* proj_, const DLTensor* eps_, c
 
 // state: fp64 [2] device tensor = {completed steps t, learning rate}; incremented after the update
 extern "C" int b3d_adam_step(DLTensor* theta_, DLTensor* m_, DLTensor* v_, const DLTensor* g_, DLTensor* state_,
-                             float beta1, float beta2, float eps, float grad_scale, int tick, void* stream) {
+                             float beta1, float beta2, float eps, float grad_scale, float decay, long long n_decay,
+                             int tick, void* stream) {
   TView th, m, v, g, st;
   B3D_TRY(flat_f32(theta_, "theta", &th));
   B3D_TRY(flat_f32(m_, "m", &m));
@@ -634,7 +637,8 @@ extern "C" int b3d_adam_step(DLTensor* theta_, DLTensor* m_, DLTensor* v_, const
               "adam: buffers must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   adam_kernel<<<ew_grid(th.numel, 8), 256, 0, s>>>((float*)th.p, (float*)m.p, (float*)v.p, (const float*)g.p,
-                                                  th.numel, (const double*)st.p, beta1, beta2, eps, grad_scale);
+                                                  th.numel, (const double*)st.p, beta1, beta2, eps, grad_scale, decay,
+                                                  n_decay);
   B3D_LAUNCH_CHECK("adam");
   if (tick) {
     adam_tick_kernel<<<1, 1, 0, s>>>((double*)st.p);

@@ -50,30 +50,111 @@ def reduce_sum(xs):
 
 
 def train_step(model: Model, optimizer: ScheduledOptim, loss_fn: DiceVAELoss, dice_fn: DiceCoefficient, x, y,
-               dropout_mask=None, eps=None, grad_hook=None):
-    """One iteration of train.py:140-152.  Returns (loss, macro_dice, micro_dice) as 0-d device tensors."""
+               dropout_mask=None, eps=None, dp: "DataParallel | None" = None):
+    """One iteration of train.py:140-152.  Returns (loss, macro_dice, micro_dice) as 0-d device tensors.
+
+    With `dp` (one process per GPU) the data gradients are all-reduced bucket by bucket while backward is
+    still running, and the L2-regulariser gradient 2*l*w — identical on every rank — is added inside the
+    fused Adam kernel instead of by autograd, so it is applied once and not averaged."""
     with GradientTape() as tape:
         y_pred, y_vae, z_mean, z_logvar = model(x, training=True, inference=False,
                                                 dropout_mask=dropout_mask, eps=eps)
         loss = loss_fn(x, y, y_pred, y_vae, z_mean, z_logvar)
-        loss = loss + reduce_sum(model.losses)
+        reg = reduce_sum(model.losses)
+        loss = loss + (reg.detach() if dp is not None else reg)
     macro_dice, micro_dice = dice_fn(y, y_pred)
     variables = model.trainable_variables
+    if dp is not None:
+        dp.begin_backward()
     grads = tape.gradient(loss, variables)
-    if grad_hook is not None:
-        grad_hook()
-    optimizer.apply_gradients(zip(grads, variables), flat=model.flat)
+    if dp is not None:
+        dp.finish_backward()
+        optimizer.apply_flat(model.flat, l2_in_step=True)
+    else:
+        optimizer.apply_gradients(zip(grads, variables), flat=model.flat)
     return loss.detach(), macro_dice, micro_dice
+
+
+class DataParallel:
+    """One-process-per-GPU data parallelism for train_step: every rank holds a replica (42.5 MB of fp32
+    weights + Adam state for the default model) and its own crop; the flat gradient buffer is cut into
+    `n_buckets` contiguous ranges that are all-reduced (sum; the 1/N is folded into the Adam kernel) over
+    NCCL / NVLink on a side stream as soon as autograd has produced every gradient of the range, i.e.
+    overlapped with the rest of backward.  GroupNorm and scSE are per-sample, so no other collective exists
+    on the path.  Works under CUDA-graph capture (the collectives are captured on the side stream)."""
+
+    def __init__(self, model: Model, optimizer: ScheduledOptim, world_size: int, n_buckets: int = 4,
+                 process_group=None, overlap: bool = True):
+        import torch.distributed as dist
+        self.dist, self.group, self.world = dist, process_group, world_size
+        self.model, self.flat = model, model.flatten_parameters()
+        optimizer.grad_scale = 1.0 / world_size
+        self.overlap = overlap and self.flat.grad.is_cuda
+        self.side = torch.cuda.Stream() if self.flat.grad.is_cuda else None
+        self.buckets = self.plan_buckets(self.flat, n_buckets)
+        self._pending = [0] * len(self.buckets)
+        self._owner = {}
+        for bi, (lo, hi, members) in enumerate(self.buckets):
+            for t in members:
+                self._owner[id(t)] = bi
+        if self.overlap:
+            for v in self.flat.order:
+                v.tensor.register_post_accumulate_grad_hook(self._on_grad)
+        self._active = False
+
+    @staticmethod
+    def plan_buckets(flat, n_buckets):
+        """Contiguous [lo, hi) ranges of the flat buffer with ~equal sizes, cut at tensor boundaries."""
+        spans = sorted(((flat.spans[id(v.tensor)][0], v.tensor) for v in flat.order), key=lambda t: t[0])
+        target = flat.total / n_buckets
+        buckets, lo, members = [], 0, []
+        for i, (off, t) in enumerate(spans):
+            members.append(t)
+            end = spans[i + 1][0] if i + 1 < len(spans) else flat.total
+            if end - lo >= target or i + 1 == len(spans):
+                buckets.append((lo, end, members))
+                lo, members = end, []
+        return buckets
+
+    def begin_backward(self):
+        self._pending = [len(m) for _, _, m in self.buckets]
+        self._active = True
+
+    def _reduce(self, bi):
+        lo, hi, _ = self.buckets[bi]
+        view = self.flat.grad[lo:hi]
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def _on_grad(self, param):
+        if not self._active:
+            return
+        bi = self._owner[id(param)]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._reduce(bi)
+
+    def finish_backward(self):
+        self._active = False
+        for bi, left in enumerate(self._pending):
+            if left != 0 or not self.overlap:        # no-overlap mode, or a tensor that got no gradient
+                self._reduce(bi)
+        self._pending = [0] * len(self.buckets)
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
 
 
 class GraphedTrainStep:
     """Captures train_step into a CUDA graph: static input buffers, one graph launch per step."""
 
-    def __init__(self, model, optimizer, loss_fn, dice_fn, x, y, warmup=2, grad_hook=None):
+    def __init__(self, model, optimizer, loss_fn, dice_fn, x, y, warmup=2, dp=None):
         self.model, self.optimizer = model, optimizer
         self.x, self.y = x.clone(), y.clone()
         self._args = (model, optimizer, loss_fn, dice_fn)
-        self._hook = grad_hook
         # everything that allocates persistent state must exist before capture
         flat = model.flatten_parameters() if model.built else None
         if flat is not None:
@@ -83,13 +164,13 @@ class GraphedTrainStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                train_step(*self._args, self.x, self.y, grad_hook=grad_hook)
+                train_step(*self._args, self.x, self.y, dp=dp)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         n0 = ops.LAUNCHES["n"]
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = train_step(*self._args, self.x, self.y, grad_hook=grad_hook)
+            self.out = train_step(*self._args, self.x, self.y, dp=dp)
         self.launches_per_step = ops.LAUNCHES["n"] - n0
 
     def __call__(self, x=None, y=None):

@@ -79,12 +79,15 @@ class ScheduledOptim(object):
             self._slots[key] = (torch.zeros_like(like), torch.zeros_like(like))
         return self._slots[key]
 
-    def apply_flat(self, flat):
-        """Fused update of a model's flat parameter buffer from its flat gradient buffer."""
+    def apply_flat(self, flat, l2_in_step=False):
+        """Fused update of a model's flat parameter buffer from its flat gradient buffer.  With
+        `l2_in_step` the regulariser gradient 2*l*w of the first `reg_end` elements is added in the kernel
+        (data-parallel mode: it must not be averaged over ranks)."""
         self._ensure_state(flat.theta.device)
         m, v = self._mv(id(flat), flat.theta)
         ops._call("b3d_adam_step", flat.theta, m, v, flat.grad, self._state, self.beta_1, self.beta_2,
-                  self.epsilon, float(self.grad_scale), 1)
+                  self.epsilon, float(self.grad_scale), 2.0 * float(flat.l2) if l2_in_step else 0.0,
+                  int(flat.reg_end) if l2_in_step else 0, 1)
 
     def apply_gradients(self, grads_and_vars, flat=None):
         gv = list(grads_and_vars)
@@ -96,7 +99,8 @@ class ScheduledOptim(object):
             m, v = self._mv(id(var), var)
             th = var.detach().view(-1)
             ops._call("b3d_adam_step", th, m.view(-1), v.view(-1), g.contiguous().view(-1), self._state,
-                      self.beta_1, self.beta_2, self.epsilon, float(self.grad_scale), int(i == len(gv) - 1))
+                      self.beta_1, self.beta_2, self.epsilon, float(self.grad_scale), 0.0, 0,
+                      int(i == len(gv) - 1))
 
 
 def _is_flat_group(gv):

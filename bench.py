@@ -194,12 +194,8 @@ def run_b3d(args):
     model.load_named_weights(p)
     opt = b3d.ScheduledOptim(learning_rate=1e-4)
     opt(epoch=0)
-    hook = None
-    if world > 1:
-        dp = b3d.train.DataParallel(model, opt, world)
-        hook = dp.allreduce_hook
-    step = b3d.GraphedTrainStep(model, opt, b3d.DiceVAELoss(), b3d.DiceCoefficient(), xd, yd, warmup=2,
-                                grad_hook=hook)
+    dp = b3d.DataParallel(model, opt, world) if world > 1 else None
+    step = b3d.GraphedTrainStep(model, opt, b3d.DiceVAELoss(), b3d.DiceCoefficient(), xd, yd, warmup=2, dp=dp)
 
     def barrier():
         if world > 1:

@@ -122,9 +122,10 @@ int b3d_dice_coeff(const DLTensor* y, const DLTensor* y_pred, DLTensor* acc /*fp
                    DLTensor* out /*fp32 [2] macro, micro*/, void* stream);
 
 /* ---- optimiser + regulariser (util.py:60-84 TF Adam, eps un-scaled; train.py:146 model.losses) ---*/
+/* g_eff = g*grad_scale + decay*theta (first n_decay elements only; decay = 2*l2 in data-parallel mode) */
 int b3d_adam_step(DLTensor* theta, DLTensor* m, DLTensor* v, const DLTensor* g,
                   DLTensor* state /*fp64 [2] = iterations, learning rate*/, float beta1, float beta2, float eps,
-                  float grad_scale, int tick, void* stream);
+                  float grad_scale, float decay, long long n_decay, int tick, void* stream);
 int b3d_l2_losses(const DLTensor* flat, const DLTensor* offsets /*int64 [n+1]*/, DLTensor* out /*[n]*/,
                   float scale, void* stream);
 int b3d_l2_grad(const DLTensor* flat, DLTensor* grad, const DLTensor* offsets, const DLTensor* gout, float coef,

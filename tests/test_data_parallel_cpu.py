@@ -1,0 +1,86 @@
+"""CPU suite, part 3 — host logic of the N>1 path (one process per GPU, flat-gradient bucket all-reduce)
+exercised with world_size=2 over gloo; no CUDA kernels involved."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = "3d-brain-tumor-segmentation_b200"
+
+
+def _make_flat(b3d):
+    kc = b3d.keras_compat
+    torch.manual_seed(0)
+    shapes = [(3, 3, 3, 2, 16), (16,), (16, 8), (5,), (1, 1, 1, 16, 3), (3,), (7, 9)]
+    vs = [kc.Variable(f"v{i}", torch.randn(s).requires_grad_(True), kc.L2(1e-5) if i % 2 == 0 else None)
+          for i, s in enumerate(shapes)]
+    return b3d.model.FlatParams(vs, torch.device("cpu")), vs
+
+
+def test_flat_params_layout(b3d):
+    flat, vs = _make_flat(b3d)
+    # regularised tensors first, every tensor 16-byte aligned, views alias the flat buffers
+    offs = [flat.spans[id(v.tensor)][0] for v in flat.order]
+    assert offs == sorted(offs) and all(o % 4 == 0 for o in offs)
+    assert [v.regularizer is not None for v in flat.order] == [True] * 4 + [False] * 3
+    assert flat.offsets.tolist()[0] == 0 and flat.offsets.tolist()[-1] == flat.reg_end
+    for v in vs:
+        off, n = flat.spans[id(v.tensor)]
+        assert v.tensor.data_ptr() == flat.theta.data_ptr() + 4 * off
+        assert v.tensor.grad.data_ptr() == flat.grad.data_ptr() + 4 * off
+    flat.grad.fill_(1.0)
+    assert all(float(v.tensor.grad.sum()) == v.tensor.numel() for v in vs)
+
+
+def test_bucket_plan_covers_buffer(b3d):
+    flat, _ = _make_flat(b3d)
+    for nb in (1, 2, 3, 16):
+        buckets = b3d.DataParallel.plan_buckets(flat, nb)
+        assert buckets[0][0] == 0 and buckets[-1][1] == flat.total
+        assert all(a[1] == b[0] for a, b in zip(buckets, buckets[1:]))
+        assert sum(len(m) for _, _, m in buckets) == len(flat.order)
+        assert len(buckets) <= max(nb, 1) + 1
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    b3d = importlib.import_module(PKG)
+    flat, vs = _make_flat(b3d)
+
+    class M:
+        def flatten_parameters(self):
+            return flat
+
+    class O:
+        grad_scale = 1.0
+
+    opt = O()
+    dp = b3d.DataParallel(M(), opt, world, n_buckets=3)
+    dp.begin_backward()
+    for i, v in enumerate(vs):                       # "backward": rank-dependent gradients
+        v.tensor.grad.fill_(float((rank + 1) * (i + 1)))
+    dp.finish_backward()
+    expect = [float(sum((r + 1) * (i + 1) for r in range(world))) for i in range(len(vs))]
+    ok = all(torch.all(v.tensor.grad == e) for v, e in zip(vs, expect)) and opt.grad_scale == 1.0 / world
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo(b3d):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

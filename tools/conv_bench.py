@@ -1,0 +1,56 @@
+"""Per-layer timing harness for the tcgen05 conv kernels (fwd = dgrad kernel, and wgrad), CUDA events,
+L2 flushed between launches.  Usage: python tools/conv_bench.py [fwd|wgrad|all] [reps]"""
+import importlib
+import os
+import statistics
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+b3d = importlib.import_module("3d-brain-tumor-segmentation_b200")
+ops = b3d.ops
+dev = torch.device("cuda:0")
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+# (spatial, Cin, Cout) of the default model's 3x3x3 convs, largest first
+SHAPES = [(128, 32, 16), (128, 16, 16), (64, 96, 32), (64, 64, 32), (64, 32, 32), (64, 16, 32),
+          (32, 256, 64), (32, 192, 64), (32, 64, 64), (16, 512, 128), (16, 128, 128)]
+
+
+def timeit(fn):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+for n, cin, cout in SHAPES:
+    x = torch.randn(1, n, n, n, cin, device=dev)
+    dy = torch.randn(1, n, n, n, cout, device=dev)
+    w = torch.randn(3, 3, 3, cin, cout, device=dev) * 0.05
+    bias = torch.zeros(cout, device=dev)
+    y = torch.empty(1, n, n, n, cout, device=dev)
+    stats = torch.empty(1, 8, 2, dtype=torch.float64, device=dev)
+    flops = 2.0 * n ** 3 * 27 * cin * cout
+    line = f"{n:4d}^3 {cin:4d}->{cout:4d}  {flops / 1e9:7.1f} GF "
+    if which in ("fwd", "all"):
+        wp = ops.pack_weights(w, False)
+        ms = timeit(lambda: ops._call("b3d_conv3d_fwd", x, w, bias, y, 1, 0, 0, stats, 8, None, 0, wp))
+        io = 4.0 * n ** 3 * (cin + cout)
+        line += f"| fwd {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s (io {io / ms / 1e6:6.0f} GB/s) "
+    if which in ("wgrad", "all"):
+        dw = torch.empty_like(w)
+        xb = torch.empty(x.shape, device=dev, dtype=torch.bfloat16)
+        yb = torch.empty(dy.shape, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: ops._call("b3d_conv3d_wgrad", x, dy, dw, None, 1, 0, xb, yb))
+        line += f"| wgrad(+casts) {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s "
+    print(line, flush=True)
