@@ -236,7 +236,17 @@ def run_b3d(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e_val = world * args.steps / (ms_e2e / 1e3)
 
+    def finish():
+        # NCCL communicators captured into CUDA graphs make destroy_process_group() hang at teardown:
+        # synchronise, flush and leave without running destructors.
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
+
     if rank != 0:
+        finish()
         return
     pk, pk_src = peaks()
     conv_ms, conv_flops = measure_conv_roofline(b3d, torch, dev)
@@ -268,8 +278,7 @@ def run_b3d(args):
             "gpu_launches": int(step.launches_per_step * args.steps),
             "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
