@@ -21,134 +21,177 @@ namespace b3d {
 constexpr int kGT = 128;    // threads (= output voxels) per CTA in the gather kernel
 constexpr int kCiT = 16;    // input channels staged per weight chunk
 
+// voxel groups (of kGT voxels) walked by one CTA (fewer statistics atomics); chosen by the host so that the
+// grid still covers the machine several times
+
 template <int CO_T>
 __global__ void __launch_bounds__(kGT)
     conv_gather_kernel(ConvGeom cg, const float* __restrict__ x, const float* __restrict__ w,
                        const float* __restrict__ bias, float* __restrict__ y, double* __restrict__ stats,
-                       float* __restrict__ gap) {
+                       float* __restrict__ gap, int kGroupsPerCta) {
   extern __shared__ float ws[];  // [taps][kCiT][CO_T]
+  __shared__ float sgap[CO_T];
+  __shared__ int sgap_b;
   const int taps = cg.k * cg.k * cg.k;
   const long long nvox = (long long)cg.B * cg.Do * cg.Ho * cg.Wo;
-  const long long v = (long long)blockIdx.x * kGT + threadIdx.x;
-  const bool act = v < nvox;
+  const long long S = (long long)cg.Do * cg.Ho * cg.Wo;
   const int co0 = blockIdx.y * CO_T;
-  int ow = 0, oh = 0, od = 0, b = 0;
-  if (act) {
-    long long t = v;
-    ow = (int)(t % cg.Wo); t /= cg.Wo;
-    oh = (int)(t % cg.Ho); t /= cg.Ho;
-    od = (int)(t % cg.Do); t /= cg.Do;
-    b = (int)t;
-  }
-  float acc[CO_T];
-#pragma unroll
-  for (int i = 0; i < CO_T; ++i) acc[i] = 0.f;
-
   const bool vec4 = (cg.Cin % 4 == 0) && (cg.xp % 4 == 0) && (((uintptr_t)x & 15) == 0);
-  const long long xb = (long long)b * cg.Di * cg.Hi * cg.Wi;
+  const bool st4 = (CO_T % 4 == 0) && (cg.yp % 4 == 0) && (co0 + CO_T <= cg.Cout) && (((uintptr_t)y & 15) == 0);
+  // running statistics of this thread (flushed when the GN chunk / sample changes and at the end)
+  int cur_chunk = -1;
+  float s0 = 0.f, s1 = 0.f;
+  if (threadIdx.x < CO_T) sgap[threadIdx.x] = 0.f;
+  if (threadIdx.x == 0) sgap_b = -1;
 
-  for (int ci0 = 0; ci0 < cg.Cin; ci0 += kCiT) {
-    const int nci = min(kCiT, cg.Cin - ci0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < taps * kCiT * CO_T; i += kGT) {
-      const int co = i % CO_T, ci = (i / CO_T) % kCiT, t = i / (CO_T * kCiT);
-      float val = 0.f;
-      if (ci < nci && co0 + co < cg.Cout) {
-        int tw = t;
-        if (cg.flip) tw = taps - 1 - t;
-        val = w[(long long)tw * cg.wtap + (long long)(ci0 + ci) * cg.sw_in + (long long)(co0 + co) * cg.sw_out];
-      }
-      ws[i] = val;
+  for (int grp = 0; grp < kGroupsPerCta; ++grp) {
+    const long long v = ((long long)blockIdx.x * kGroupsPerCta + grp) * kGT + threadIdx.x;
+    if (((long long)blockIdx.x * kGroupsPerCta + grp) * kGT >= nvox) break;      // CTA-uniform
+    const bool act = v < nvox;
+    int ow = 0, oh = 0, od = 0, b = 0;
+    if (act) {
+      long long t = v;
+      ow = (int)(t % cg.Wo); t /= cg.Wo;
+      oh = (int)(t % cg.Ho); t /= cg.Ho;
+      od = (int)(t % cg.Do); t /= cg.Do;
+      b = (int)t;
     }
-    __syncthreads();
-    if (!act) continue;
-    for (int t = 0; t < taps; ++t) {
-      const int tk = t % cg.k, th = (t / cg.k) % cg.k, td = t / (cg.k * cg.k);
-      int id, ih, iw;
-      if (cg.mode == CONV_S1) {
-        id = od + td - cg.pad; ih = oh + th - cg.pad; iw = ow + tk - cg.pad;
-      } else if (cg.mode == CONV_DOWN) {
-        id = 2 * od + td; ih = 2 * oh + th; iw = 2 * ow + tk;
-      } else {
-        id = od - td; ih = oh - th; iw = ow - tk;
-        if ((id | ih | iw) < 0 || ((id | ih | iw) & 1)) continue;
-        id >>= 1; ih >>= 1; iw >>= 1;
+    float acc[CO_T];
+#pragma unroll
+    for (int i = 0; i < CO_T; ++i) acc[i] = 0.f;
+    const long long xb = (long long)b * cg.Di * cg.Hi * cg.Wi;
+
+    for (int ci0 = 0; ci0 < cg.Cin; ci0 += kCiT) {
+      const int nci = min(kCiT, cg.Cin - ci0);
+      if (grp == 0 || cg.Cin > kCiT) {       // weights of a single-chunk layer stay resident across groups
+        __syncthreads();
+        for (int i = threadIdx.x; i < taps * kCiT * CO_T; i += kGT) {
+          const int co = i % CO_T, ci = (i / CO_T) % kCiT, t = i / (CO_T * kCiT);
+          float val = 0.f;
+          if (ci < nci && co0 + co < cg.Cout) {
+            int tw = t;
+            if (cg.flip) tw = taps - 1 - t;
+            val = w[(long long)tw * cg.wtap + (long long)(ci0 + ci) * cg.sw_in + (long long)(co0 + co) * cg.sw_out];
+          }
+          ws[i] = val;
+        }
+        __syncthreads();
       }
-      if (id < 0 || id >= cg.Di || ih < 0 || ih >= cg.Hi || iw < 0 || iw >= cg.Wi) continue;
-      const float* xp = x + ((xb + ((long long)id * cg.Hi + ih) * cg.Wi + iw) * cg.xp + ci0);
-      const float* wt = ws + t * kCiT * CO_T;
-      if (vec4) {
-        for (int ci = 0; ci < nci; ci += 4) {
-          const float4 xv = *reinterpret_cast<const float4*>(xp + ci);
-          const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      if (!act) continue;
+      for (int t = 0; t < taps; ++t) {
+        const int tk = t % cg.k, th = (t / cg.k) % cg.k, td = t / (cg.k * cg.k);
+        int id, ih, iw;
+        if (cg.mode == CONV_S1) {
+          id = od + td - cg.pad; ih = oh + th - cg.pad; iw = ow + tk - cg.pad;
+        } else if (cg.mode == CONV_DOWN) {
+          id = 2 * od + td; ih = 2 * oh + th; iw = 2 * ow + tk;
+        } else {
+          id = od - td; ih = oh - th; iw = ow - tk;
+          if ((id | ih | iw) < 0 || ((id | ih | iw) & 1)) continue;
+          id >>= 1; ih >>= 1; iw >>= 1;
+        }
+        if (id < 0 || id >= cg.Di || ih < 0 || ih >= cg.Hi || iw < 0 || iw >= cg.Wi) continue;
+        const float* xp = x + ((xb + ((long long)id * cg.Hi + ih) * cg.Wi + iw) * cg.xp + ci0);
+        const float* wt = ws + t * kCiT * CO_T;
+        if (vec4) {
+          for (int ci = 0; ci < nci; ci += 4) {
+            const float4 xv = *reinterpret_cast<const float4*>(xp + ci);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 4; ++u) {
 #pragma unroll
-            for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(xs[u], wt[(ci + u) * CO_T + co], acc[co]);
+              for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(xs[u], wt[(ci + u) * CO_T + co], acc[co]);
+            }
+          }
+        } else {
+          for (int ci = 0; ci < nci; ++ci) {
+            const float xv = xp[ci];
+#pragma unroll
+            for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(xv, wt[ci * CO_T + co], acc[co]);
           }
         }
-      } else {
-        for (int ci = 0; ci < nci; ++ci) {
-          const float xv = xp[ci];
-#pragma unroll
-          for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(xv, wt[ci * CO_T + co], acc[co]);
-        }
       }
     }
-  }
 
-  // epilogue: bias, activation, accumulate, store, optional GN chunk stats and GAP sums
-  float s0 = 0.f, s1 = 0.f;
-  if (act) {
-    float* yp = y + v * cg.yp + co0;
+    // epilogue: bias, activation, accumulate, store
+    float t0 = 0.f, t1 = 0.f;
+    if (act) {
+      float* yp = y + v * cg.yp + co0;
 #pragma unroll
-    for (int co = 0; co < CO_T; ++co) {
-      if (co0 + co < cg.Cout) {
-        float r = acc[co] + (bias ? bias[co0 + co] : 0.f);
-        if (cg.act == 1) r = 1.f / (1.f + expf(-r));
-        if (cg.accumulate) r += yp[co];
-        yp[co] = r;
-        acc[co] = r;
-        s0 += r;
-        s1 += r * r;
+      for (int co = 0; co < CO_T; ++co) {
+        if (co0 + co < cg.Cout) {
+          float r = acc[co] + (bias ? bias[co0 + co] : 0.f);
+          if (cg.act == 1) r = 1.f / (1.f + expf(-r));
+          if (cg.accumulate) r += yp[co];
+          acc[co] = r;
+          t0 += r;
+          t1 += r * r;
+        } else {
+          acc[co] = 0.f;
+        }
+      }
+      if (st4) {
+#pragma unroll
+        for (int co = 0; co < CO_T; co += 4)
+          *reinterpret_cast<float4*>(yp + co) = make_float4(acc[co], acc[co + 1], acc[co + 2], acc[co + 3]);
       } else {
-        acc[co] = 0.f;
+#pragma unroll
+        for (int co = 0; co < CO_T; ++co)
+          if (co0 + co < cg.Cout) yp[co] = acc[co];
+      }
+    }
+    if (stats != nullptr && act) {
+      // chunk of a voxel (voxel-aligned chunks guaranteed by the host wrapper)
+      const int chunk = (int)(b * cg.groups + ((v - (long long)b * S) / (S / cg.groups)));
+      if (chunk != cur_chunk) {
+        if (cur_chunk >= 0) {
+          atomicAdd(&stats[2 * cur_chunk], (double)s0);
+          atomicAdd(&stats[2 * cur_chunk + 1], (double)s1);
+        }
+        cur_chunk = chunk; s0 = 0.f; s1 = 0.f;
+      }
+      s0 += t0; s1 += t1;
+    }
+    if (gap != nullptr) {
+      // per-(b, co) sums over voxels: CTA-level accumulation in shared memory, flushed when the sample changes
+      const int b_first = __shfl_sync(0xffffffffu, b, 0);
+      const bool uni = __all_sync(0xffffffffu, b == b_first || !act);
+      __syncthreads();
+      if (threadIdx.x == 0 && sgap_b < 0) sgap_b = b_first;
+      __syncthreads();
+      const bool same = uni && b_first == sgap_b;
+#pragma unroll
+      for (int co = 0; co < CO_T; ++co) {
+        if (co0 + co < cg.Cout) {
+          if (same) {
+            const float a = warp_sum(act ? acc[co] : 0.f);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&sgap[co], a);
+          } else if (act) {
+            atomicAdd(&gap[(long long)b * cg.Cout + co0 + co], acc[co]);
+          }
+        }
       }
     }
   }
   if (stats != nullptr) {
-    // chunk of a voxel (voxel-aligned chunks guaranteed by the host wrapper)
-    const long long S = (long long)cg.Do * cg.Ho * cg.Wo;
-    const int chunk = act ? (int)(b * cg.groups + ((v - (long long)b * S) / (S / cg.groups))) : -1;
-    const int c0 = __shfl_sync(0xffffffffu, chunk, 0);
-    const bool uni = __all_sync(0xffffffffu, chunk == c0 || chunk < 0);
+    const int c0 = __shfl_sync(0xffffffffu, cur_chunk, 0);
+    const bool uni = __all_sync(0xffffffffu, cur_chunk == c0 || cur_chunk < 0);
     if (uni) {
-      const float a0 = warp_sum(s0), a1 = warp_sum(s1);
-      const int cc = __reduce_max_sync(0xffffffffu, chunk);
+      const int cc = __reduce_max_sync(0xffffffffu, cur_chunk);
+      const float a0 = warp_sum(cur_chunk >= 0 ? s0 : 0.f), a1 = warp_sum(cur_chunk >= 0 ? s1 : 0.f);
       if ((threadIdx.x & 31) == 0 && cc >= 0) {
         atomicAdd(&stats[2 * cc], (double)a0);
         atomicAdd(&stats[2 * cc + 1], (double)a1);
       }
-    } else if (act) {
-      atomicAdd(&stats[2 * chunk], (double)s0);
-      atomicAdd(&stats[2 * chunk + 1], (double)s1);
+    } else if (cur_chunk >= 0) {
+      atomicAdd(&stats[2 * cur_chunk], (double)s0);
+      atomicAdd(&stats[2 * cur_chunk + 1], (double)s1);
     }
   }
   if (gap != nullptr) {
-    // per-(b, co) sums over voxels: warp reduce when the warp sits in one sample
-    const int b0 = __shfl_sync(0xffffffffu, b, 0);
-    const bool uni = __all_sync(0xffffffffu, b == b0 || !act);
-#pragma unroll
-    for (int co = 0; co < CO_T; ++co) {
-      if (co0 + co < cg.Cout) {
-        if (uni) {
-          const float a = warp_sum(act ? acc[co] : 0.f);
-          if ((threadIdx.x & 31) == 0) atomicAdd(&gap[(long long)b0 * cg.Cout + co0 + co], a);
-        } else if (act) {
-          atomicAdd(&gap[(long long)b * cg.Cout + co0 + co], acc[co]);
-        }
-      }
-    }
+    __syncthreads();
+    if (threadIdx.x < CO_T && co0 + threadIdx.x < cg.Cout && sgap_b >= 0)
+      atomicAdd(&gap[(long long)sgap_b * cg.Cout + co0 + threadIdx.x], sgap[threadIdx.x]);
   }
 }
 
@@ -338,12 +381,14 @@ int launch_conv_gather(const ConvGeom& cg, const float* x, const float* w, const
                        double* stats, float* gap, cudaStream_t s) {
   const long long nvox = (long long)cg.B * cg.Do * cg.Ho * cg.Wo;
   const int taps = cg.k * cg.k * cg.k;
-  const unsigned gx = (unsigned)((nvox + kGT - 1) / kGT);
+  long long gpc = nvox / ((long long)kGT * 8 * sm_count());
+  gpc = gpc < 1 ? 1 : (gpc > 8 ? 8 : gpc);
+  const unsigned gx = (unsigned)((nvox + (long long)kGT * gpc - 1) / ((long long)kGT * gpc));
 #define LAUNCH(CO)                                                                                         \
   do {                                                                                                     \
     const size_t smem = sizeof(float) * taps * kCiT * CO;                                                  \
     dim3 grid(gx, (cg.Cout + CO - 1) / CO, 1);                                                             \
-    conv_gather_kernel<CO><<<grid, kGT, smem, s>>>(cg, x, w, bias, y, stats, gap);                         \
+    conv_gather_kernel<CO><<<grid, kGT, smem, s>>>(cg, x, w, bias, y, stats, gap, (int)gpc);                         \
   } while (0)
   if (cg.Cout >= 16) LAUNCH(16);
   else if (cg.Cout > 4) LAUNCH(8);

@@ -1,23 +1,27 @@
-// b3d — 3x3x3 stride-1 SAME convolution as an implicit GEMM on the 5th-gen tensor cores
-// (tcgen05.mma kind::tf32, fp32 operands straight from NDHWC activations, accumulators in TMEM).
-// Used for Conv3D forward (reference layers/resnet.py:80-87,96-103) and, with flipped/transposed
-// packed weights, for its data gradient.
+// b3d — stride-1 SAME convolutions (3x3x3 and 1x1x1) as implicit GEMMs on the 5th-gen tensor cores
+// (tcgen05.mma, accumulators in TMEM).  Used for Conv3D forward (reference layers/resnet.py:30-37,
+// 80-87,96-103) and, with flipped/transposed packed weights, for its data gradient.
 //
 // "Shifted GEMM on a resident halo tile":
-//   * a CTA owns an output tile of TD x 16 x (8*NW) voxels.  For each group of 8 input channels it
-//     TMA-loads the (TD+2) x 18 x (8*NW+2) halo ONCE (5-D tensor map over [B,D,H,W,C]; out-of-volume
-//     coordinates are zero-filled by TMA = TF 'SAME' padding) into shared memory as two channel
-//     planes  plane[kc][d'][h'][w'] of 16-byte (4-channel) cells — the canonical K-major SWIZZLE_NONE
-//     UMMA layout with a 16-byte row pitch, so that ANY voxel shift is just a start-address offset.
-//   * every one of the 27 taps is then an MMA whose A descriptor points into that same halo at the
-//     tap's offset:  M = 128 rows = a 16(h) x 8(w) patch (8 consecutive w = one core matrix, SBO = one
-//     halo row), K = 8 channels (LBO = one plane), N = Cout.  No im2col, no re-load per tap: every
-//     input byte crosses L2->SMEM once per tile and is reused by 27 taps x Cout.
-//   * weights are pre-packed (tf32-rounded) into the matching B layout and streamed per (8-channel
-//     chunk, kd) through a 3-stage ring with bulk copies.
-//   * warp-specialised, persistent: warp0 = halo TMA producer, warp1 = single-thread MMA issuer,
-//     warp2 = weight producer (+TMEM alloc), warps4-7 = epilogue (tcgen05.ld -> +bias -> NDHWC store,
-//     GroupNorm chunk statistics); 2 TMEM accumulator stages overlap epilogue(i) with MMA(i+1).
+//   * a CTA owns an output tile of TD x 16 x (8*NW) voxels.  For each chunk of CK input channels
+//     (16 as bf16 / 8 as tf32 = one MMA K step) eight LOADER warps read the (TD+2) x 18 x (8*NW+2)
+//     halo of the fp32 NDHWC activation ONCE with 128-bit loads (zero outside the volume = TF 'SAME'
+//     padding), convert it to the operand type in registers, and store it to shared memory as two
+//     channel planes  plane[d'][h'][w'] of 16-byte cells — the canonical K-major SWIZZLE_NONE UMMA
+//     layout with a 16-byte row pitch, so that ANY voxel shift is just a start-address offset.
+//     (Round-1a used TMA with 16-byte boxes for this; ncu showed ~3 cycles per cell, i.e. the kernel
+//     was TMA-issue-bound; a thread loader is faster and converts to bf16 for free.)
+//   * every tap is then an MMA whose A descriptor points into that same halo at the tap's offset:
+//     M = 128 rows = a 16(h) x 8(w) patch (8 consecutive w = one core matrix, SBO = one halo row),
+//     K = CK channels (LBO = one plane), N = Cout.  No im2col, no re-load per tap.
+//   * weights are pre-packed (bf16 / tf32-rounded) into the matching B layout and streamed one kd slab
+//     (9 taps) at a time through a 3-deep ring with bulk copies (cp.async.bulk + mbarrier complete_tx).
+//   * warp-specialised, persistent: warps 0-3 = epilogue (tcgen05.ld -> +bias -> NDHWC store, fused
+//     GroupNorm chunk statistics or global-average-pool sums), warps 4-11 = loaders, warp 12 = single
+//     thread MMA issuer, warp 13 = weight producer (+TMEM alloc); 2 TMEM accumulator stages overlap
+//     epilogue(i) with MMA(i+1).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "tc_ptx.cuh"
@@ -25,64 +29,98 @@
 namespace b3d {
 
 // ------------------------------------------------------------------------------------------ config
-template <int N_, int TD_, int NW_>
+template <int N_, int TD_, int NW_, int KS_, bool BF16_>
 struct TcCfg {
-  static constexpr int N = N_, TD = TD_, NW = NW_;
+  static constexpr int N = N_, TD = TD_, NW = NW_, KS = KS_;
+  static constexpr bool BF16 = BF16_;
+  static constexpr int T = BF16 ? 8 : 4;              // channels per 16-byte cell
+  static constexpr int CK = 2 * T;                    // channels per chunk = one MMA K step
+  static constexpr int TAPS = KS * KS * KS;
+  static constexpr int HALO = KS / 2;
   static constexpr int TH = 16, TW = 8 * NW, P = TD * NW;
-  static constexpr int HD = TD + 2, HH = TH + 2, HW = TW + 2;
-  static constexpr int NV = HD * HH * HW;             // halo voxels per plane
-  static constexpr int PLANE_BYTES = NV * 16;         // one plane = 4 channels
-  static constexpr int HALO_BYTES = 2 * PLANE_BYTES;  // one stage = 8 channels = one tf32 K step
-  static constexpr int HS = 2;
+  static constexpr int HD = TD + 2 * HALO, HH = TH + 2 * HALO, HW = TW + 2 * HALO;
+  static constexpr int NVC = HD * HH * HW;            // cells per plane
+  static constexpr int PLANE_BYTES = ((NVC * 16 + 127) / 128) * 128;
+  static constexpr int HALO_BYTES = 2 * PLANE_BYTES;
   static constexpr int TAP_BYTES = 2 * N * 16;        // B tile of one tap: 2 planes x N rows x 16 B
-  static constexpr int WST_BYTES = 9 * TAP_BYTES;     // one stage = the 9 (kh,kw) taps of one kd
-  static constexpr int WS = 3;
+  static constexpr int TPS = KS * KS;                 // taps per weight stage (one kd slab; 1 for 1x1x1)
+  static constexpr int WST_BYTES = TPS * TAP_BYTES;
+  static constexpr int WS = (KS == 1) ? 8 : 3;
   static constexpr int ACC_COLS = 256;                // per accumulator stage (P*N <= 256)
-  static constexpr int SMEM = HS * HALO_BYTES + WS * WST_BYTES + 256;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int HS = (3 * HALO_BYTES + WS * WST_BYTES + BAR_BYTES <= 220 * 1024) ? 3 : 2;
+  static constexpr int SMEM = HS * HALO_BYTES + WS * WST_BYTES + BAR_BYTES;
   static_assert(P * N <= ACC_COLS, "accumulators exceed a TMEM stage");
-  static_assert(PLANE_BYTES % 128 == 0, "TMA destination alignment");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 struct TcParams {
-  const float* wp;     // packed weights [nsplit][chunk][kd][9][2][N][4]
+  const float* x;      // fp32 NDHWC input, channel pitch xp
+  const void* wp;      // packed weights [nsplit][chunk][tap][2 planes][N][T]
   const float* bias;   // nullable
   float* y;
-  double* stats;       // nullable
+  double* stats;       // nullable: GroupNorm chunk (sum, sum^2) of y
+  float* gap;          // nullable: per-(b, channel) sums of y
   int B, D, H, W, Cin, Cout;
-  long long yp;        // output channel pitch
+  long long xp, yp;    // channel pitches
   int ntd, nth, ntw, ntiles;
   int accumulate, groups;
   long long vpc;       // voxels per GN chunk
 };
 
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 256-bit streaming load (one full 32-byte sector per lane; sm_100 LDG.E.256)
+__device__ __forceinline__ void ld256(const float* p, float* r) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+constexpr int kLoaderWarps = 8;
+constexpr int kTcThreads = (4 + kLoaderWarps + 2) * 32;   // 4 epilogue + loaders + MMA + weights
+
 template <class C>
-__global__ void __launch_bounds__(256, 1)
-    conv3_tc_kernel(const __grid_constant__ CUtensorMap tmx, const TcParams prm) {
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* halo = smem;
   uint8_t* wst = smem + C::HS * C::HALO_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wst + C::WS * C::WST_BYTES);
-  // barrier map
-  uint64_t* halo_full = bars;               // [HS]
-  uint64_t* halo_empty = bars + 2;          // [HS]
-  uint64_t* w_full = bars + 4;              // [WS]
-  uint64_t* w_empty = bars + 8;             // [WS]
-  uint64_t* acc_full = bars + 12;           // [2]
-  uint64_t* acc_empty = bars + 14;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* halo_full = bars;                  // [HS]  128 loader arrivals
+  uint64_t* halo_empty = bars + 4;             // [HS]  tcgen05.commit
+  uint64_t* w_full = bars + 8;                 // [WS]  expect_tx + bulk copy
+  uint64_t* w_empty = bars + 8 + C::WS;        // [WS]  tcgen05.commit
+  uint64_t* acc_full = bars + 8 + 2 * C::WS;   // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]  4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nchunks = prm.Cin / 8;
+  const int nchunks = prm.Cin / C::CK;
   const int nsp = blockIdx.y;  // N split
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::HS; ++i) { mbar_init(smem_u32(&halo_full[i]), 1); mbar_init(smem_u32(&halo_empty[i]), 1); }
+    for (int i = 0; i < C::HS; ++i) { mbar_init(smem_u32(&halo_full[i]), kLoaderWarps * 32); mbar_init(smem_u32(&halo_empty[i]), 1); }
     for (int i = 0; i < C::WS; ++i) { mbar_init(smem_u32(&w_full[i]), 1); mbar_init(smem_u32(&w_empty[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == kLoaderWarps + 5) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -92,91 +130,165 @@ __global__ void __launch_bounds__(256, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================== halo producer (TMA) =====================
-    if (lane == 0) {
-      int hs = 0, hph = 0;
-      for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
-        int t = tile;
-        const int wt = t % prm.ntw; t /= prm.ntw;
-        const int ht = t % prm.nth; t /= prm.nth;
-        const int dt = t % prm.ntd; t /= prm.ntd;
-        const int b = t;
-        const int w0 = wt * C::TW - 1, h0 = ht * C::TH - 1, d0 = dt * C::TD - 1;
-        for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
-          const uint32_t full = smem_u32(&halo_full[hs]);
-          mbar_expect_tx(full, C::HALO_BYTES);
-          const uint32_t dst = smem_u32(halo + hs * C::HALO_BYTES);
-          tma_load_5d(dst, &tmx, 8 * c, w0, h0, d0, b, full);
-          tma_load_5d(dst + C::PLANE_BYTES, &tmx, 8 * c + 4, w0, h0, d0, b, full);
-          if (++hs == C::HS) { hs = 0; hph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ===================== weight producer (bulk copies) =====================
-    if (lane == 0) {
-      int ws = 0, wph = 0;
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(prm.wp) + (size_t)nsp * nchunks * 3 * C::WST_BYTES;
-      for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
-        for (int c = 0; c < nchunks; ++c) {
-          for (int kd = 0; kd < 3; ++kd) {
-            mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
-            const uint32_t full = smem_u32(&w_full[ws]);
-            mbar_expect_tx(full, C::WST_BYTES);
-            bulk_g2s(smem_u32(wst + ws * C::WST_BYTES), wsrc + (size_t)(c * 3 + kd) * C::WST_BYTES, C::WST_BYTES,
-                     full);
-            if (++ws == C::WS) { ws = 0; wph ^= 1; }
+  if (warp >= 4 && warp < 4 + kLoaderWarps) {
+    // ============ operand loaders: global fp32 -> (bf16|tf32) cells in shared memory ============
+    const int lw = warp - 4;
+    int hs = 0, hph = 0;
+    for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+      int t = tile;
+      const int wt = t % prm.ntw; t /= prm.ntw;
+      const int ht = t % prm.nth; t /= prm.nth;
+      const int dt = t % prm.ntd; t /= prm.ntd;
+      const int b = t;
+      const int w0 = wt * C::TW - C::HALO, h0 = ht * C::TH - C::HALO, d0 = dt * C::TD - C::HALO;
+      const float* xb = prm.x + (long long)b * prm.D * prm.H * prm.W * prm.xp;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
+        uint8_t* dst0 = halo + hs * C::HALO_BYTES;
+        uint8_t* dst1 = dst0 + C::PLANE_BYTES;
+        const float* xc = xb + c * C::CK;
+        // one lane = one halo voxel: the whole CK-channel chunk is fetched with 256-bit loads (full 32-byte
+        // sectors), converted, and written as one 16-byte cell per plane (a warp stores 512 contiguous bytes)
+        constexpr int kVoxPerPass = kLoaderWarps * 32;
+        constexpr int kUnroll = 4;
+        constexpr int kRegs = C::BF16 ? 16 : 8;
+        for (int v0 = lw * 32 + lane; v0 < C::NVC; v0 += kVoxPerPass * kUnroll) {
+          float r[kUnroll][kRegs];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const int v = v0 + u * kVoxPerPass;
+            const int cw = v % C::HW, q = v / C::HW;
+            const int ch = q % C::HH, cd = q / C::HH;
+            const int gd = d0 + cd, gh = h0 + ch, gw = w0 + cw;
+            const bool ok = v < C::NVC && gd >= 0 && gd < prm.D && gh >= 0 && gh < prm.H && gw >= 0 && gw < prm.W;
+#pragma unroll
+            for (int i = 0; i < kRegs; ++i) r[u][i] = 0.f;
+            if (ok) {
+              const float* src = xc + (((long long)gd * prm.H + gh) * prm.W + gw) * prm.xp;
+              ld256(src, r[u]);
+              if (C::BF16) ld256(src + 8, r[u] + 8);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const int v = v0 + u * kVoxPerPass;
+            if (v < C::NVC) {
+              uint4 o0, o1;
+              if (C::BF16) {
+                o0.x = pack_bf16x2(r[u][0], r[u][1]); o0.y = pack_bf16x2(r[u][2], r[u][3]);
+                o0.z = pack_bf16x2(r[u][4], r[u][5]); o0.w = pack_bf16x2(r[u][6], r[u][7]);
+                o1.x = pack_bf16x2(r[u][8], r[u][9]); o1.y = pack_bf16x2(r[u][10], r[u][11]);
+                o1.z = pack_bf16x2(r[u][12], r[u][13]); o1.w = pack_bf16x2(r[u][14], r[u][15]);
+              } else {
+                o0.x = __float_as_uint(r[u][0]); o0.y = __float_as_uint(r[u][1]);
+                o0.z = __float_as_uint(r[u][2]); o0.w = __float_as_uint(r[u][3]);
+                o1.x = __float_as_uint(r[u][4]); o1.y = __float_as_uint(r[u][5]);
+                o1.z = __float_as_uint(r[u][6]); o1.w = __float_as_uint(r[u][7]);
+              }
+              *reinterpret_cast<uint4*>(dst0 + v * 16) = o0;
+              *reinterpret_cast<uint4*>(dst1 + v * 16) = o1;
+            }
           }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA reads
+        mbar_arrive(smem_u32(&halo_full[hs]));
+        if (++hs == C::HS) { hs = 0; hph ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
+  } else if (warp == kLoaderWarps + 5) {
+    // ============ weight producer (bulk copies, one kd slab of taps per stage) ============
     if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, K-major both, N, M=128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C::N >> 3) << 17) | ((128u >> 4) << 24);
-      int hs = 0, hph = 0, ws = 0, wph = 0, it = 0;
-      for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++it) {
-        const int as = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(smem_u32(&acc_empty[as]), aph ^ 1);
+      int ws = 0, wph = 0;
+      const uint8_t* wsrc =
+          reinterpret_cast<const uint8_t*>(prm.wp) + (size_t)nsp * nchunks * C::TAPS * C::TAP_BYTES;
+      constexpr int kStagesPerChunk = C::TAPS / C::TPS;
+      for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+        for (int cs = 0; cs < nchunks * kStagesPerChunk; ++cs) {
+          mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
+          const uint32_t full = smem_u32(&w_full[ws]);
+          mbar_expect_tx(full, C::WST_BYTES);
+          bulk_g2s(smem_u32(wst + ws * C::WST_BYTES), wsrc + (size_t)cs * C::WST_BYTES, C::WST_BYTES, full);
+          if (++ws == C::WS) { ws = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kLoaderWarps + 4) {
+    // ============ MMA issuer: the whole warp runs the (warp-uniform) control flow so that descriptors stay
+    // in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit ============
+    const bool leader = elect_one();
+    // instruction descriptor: D=f32, A=B=(bf16|tf32), K-major both, N, M=128
+    const uint32_t fmt = C::BF16 ? 1u : 2u;
+    const uint32_t idesc =
+        (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C::N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t halo_addr = smem_u32(halo), wst_addr = smem_u32(wst);
+    int hs = 0, hph = 0, ws = 0, wph = 0, it = 0;
+    for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++it) {
+      const int as = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(smem_u32(&acc_empty[as]), aph ^ 1);
+      tc_fence_after();
+      const uint32_t dbase = tmem_base + as * C::ACC_COLS;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(smem_u32(&halo_full[hs]), hph);
         tc_fence_after();
-        const uint32_t dbase = tmem_base + as * C::ACC_COLS;
-        for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(smem_u32(&halo_full[hs]), hph);
-          const uint64_t adesc0 = make_desc(smem_u32(halo + hs * C::HALO_BYTES), C::PLANE_BYTES, C::HW * 16);
-          for (int kd = 0; kd < 3; ++kd) {
-            mbar_wait(smem_u32(&w_full[ws]), wph);
-            tc_fence_after();
-            const uint64_t bdesc0 = make_desc(smem_u32(wst + ws * C::WST_BYTES), C::N * 16, 128);
+        const uint64_t adesc0 = make_desc(halo_addr + hs * C::HALO_BYTES, C::PLANE_BYTES, C::HW * 16);
 #pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9) {
-              const int kh = t9 / 3, kw = t9 % 3;
-              const uint64_t bdesc = bdesc0 + (uint64_t)(t9 * (C::TAP_BYTES >> 4));
-              const uint32_t acc = (c > 0 || kd > 0 || t9 > 0) ? 1u : 0u;
+        for (int st = 0; st < C::TAPS / C::TPS; ++st) {
+          mbar_wait(smem_u32(&w_full[ws]), wph);
+          tc_fence_after();
+          const uint64_t bdesc0 = make_desc(wst_addr + ws * C::WST_BYTES, C::N * 16, 128);
+          if (leader) {
+#pragma unroll
+            for (int tq = 0; tq < C::TPS; ++tq) {
+              const int tap = st * C::TPS + tq;
+              const int kd = tap / (C::KS * C::KS), kh = (tap / C::KS) % C::KS, kw = tap % C::KS;
+              const uint64_t bdesc = bdesc0 + (uint64_t)(tq * (C::TAP_BYTES >> 4));
+              const uint32_t acc = (c > 0 || tap > 0) ? 1u : 0u;
 #pragma unroll
               for (int p = 0; p < C::P; ++p) {
                 const int pd = p / C::NW, pw = p % C::NW;
                 const uint32_t aoff = (uint32_t)(((pd + kd) * C::HH + kh) * C::HW + pw * 8 + kw);
-                tc_mma_tf32(dbase + p * C::N, adesc0 + aoff, bdesc, idesc, acc);
+                if (C::BF16) tc_mma_f16(dbase + p * C::N, adesc0 + aoff, bdesc, idesc, acc);
+                else tc_mma_tf32(dbase + p * C::N, adesc0 + aoff, bdesc, idesc, acc);
               }
             }
             tc_commit(smem_u32(&w_empty[ws]));
-            if (++ws == C::WS) { ws = 0; wph ^= 1; }
           }
-          tc_commit(smem_u32(&halo_empty[hs]));
-          if (++hs == C::HS) { hs = 0; hph ^= 1; }
+          __syncwarp();
+          if (++ws == C::WS) { ws = 0; wph ^= 1; }
         }
-        tc_commit(smem_u32(&acc_full[as]));
+        if (leader) tc_commit(smem_u32(&halo_empty[hs]));
+        __syncwarp();
+        if (++hs == C::HS) { hs = 0; hph ^= 1; }
       }
+      if (leader) tc_commit(smem_u32(&acc_full[as]));
+      __syncwarp();
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue (TMEM -> registers -> NDHWC global) =====================
-    const int q = warp - 4;                 // TMEM lane quarter == warp % 4
+  } else if (warp < 4) {
+    // ============ epilogue (TMEM -> registers -> NDHWC global) ============
+    const int q = warp;                     // TMEM lane quarter == warp % 4
     const int row = q * 32 + lane;          // patch row: h = row/8, w = row%8
     const int ph = row >> 3, pwv = row & 7;
     const long long S = (long long)prm.D * prm.H * prm.W;
+    // global-average-pool partial sums: kept in registers across the tiles of one sample when N <= 64
+    constexpr bool kGapPersist = C::N <= 64;
+    constexpr int NJ = C::N / 16;
+    float gsum[kGapPersist ? NJ : 1][16];
+#pragma unroll
+    for (int j = 0; j < (kGapPersist ? NJ : 1); ++j)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) gsum[j][i] = 0.f;
+    int gap_b = -1;
+    auto flush_gap = [&](int bb) {
+      if (prm.gap == nullptr || bb < 0) return;
+#pragma unroll
+      for (int j = 0; j < (kGapPersist ? NJ : 1); ++j)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = warp_sum(gsum[j][i]);
+          if (lane == 0) atomicAdd(&prm.gap[(long long)bb * prm.Cout + nsp * C::N + j * 16 + i], a);
+          gsum[j][i] = 0.f;
+        }
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++it) {
       const int as = it & 1, aph = (it >> 1) & 1;
@@ -185,41 +297,42 @@ __global__ void __launch_bounds__(256, 1)
       const int ht = t % prm.nth; t /= prm.nth;
       const int dt = t % prm.ntd; t /= prm.ntd;
       const int b = t;
+      if (kGapPersist && b != gap_b) { flush_gap(gap_b); gap_b = b; }
       mbar_wait(smem_u32(&acc_full[as]), aph);
       tc_fence_after();
       int cur_chunk = -1;
       float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float bv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bv[i] = prm.bias != nullptr ? __ldg(prm.bias + nsp * C::N + j * 16 + i) : 0.f;
+        float (&gs)[16] = gsum[kGapPersist ? j : 0];
 #pragma unroll 1
-      for (int p = 0; p < C::P; ++p) {
-        const int pd = p / C::NW, pw = p % C::NW;
-        const int d = dt * C::TD + pd, h = ht * C::TH + ph, w = wt * C::TW + pw * 8 + pwv;
-        const bool valid = d < prm.D && h < prm.H && w < prm.W;
-        const long long vox = ((long long)d * prm.H + h) * prm.W + w;
-        float* yp = prm.y + ((long long)b * S + vox) * prm.yp + (long long)nsp * C::N;
-        if (prm.stats != nullptr && valid) {
-          const int chunk = b * prm.groups + (int)(vox / prm.vpc);
-          if (chunk != cur_chunk) {
-            if (cur_chunk >= 0) {
-              atomicAdd(&prm.stats[2 * cur_chunk], (double)s0);
-              atomicAdd(&prm.stats[2 * cur_chunk + 1], (double)s1);
+        for (int p = 0; p < C::P; ++p) {
+          const int pd = p / C::NW, pw = p % C::NW;
+          const int d = dt * C::TD + pd, h = ht * C::TH + ph, w = wt * C::TW + pw * 8 + pwv;
+          const bool valid = d < prm.D && h < prm.H && w < prm.W;
+          const long long vox = ((long long)d * prm.H + h) * prm.W + w;
+          float* yp = prm.y + ((long long)b * S + vox) * prm.yp + (long long)nsp * C::N + j * 16;
+          if (prm.stats != nullptr && valid) {
+            const int chunk = b * prm.groups + (int)(vox / prm.vpc);
+            if (chunk != cur_chunk) {
+              if (cur_chunk >= 0) {
+                atomicAdd(&prm.stats[2 * cur_chunk], (double)s0);
+                atomicAdd(&prm.stats[2 * cur_chunk + 1], (double)s1);
+              }
+              cur_chunk = chunk; s0 = 0.f; s1 = 0.f;
             }
-            cur_chunk = chunk; s0 = 0.f; s1 = 0.f;
           }
-        }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + p * C::N;
-#pragma unroll
-        for (int j = 0; j < C::N / 16; ++j) {
           float v[16];
-          tc_ld16(taddr + j * 16, v);
+          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + p * C::N + j * 16, v);
           if (valid) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (prm.bias != nullptr) v[i] += __ldg(prm.bias + nsp * C::N + j * 16 + i);
-            }
-            float4* dst = reinterpret_cast<float4*>(yp + j * 16);
+            float4* dst = reinterpret_cast<float4*>(yp);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              float4 o = make_float4(v[4 * i] + bv[4 * i], v[4 * i + 1] + bv[4 * i + 1], v[4 * i + 2] + bv[4 * i + 2],
+                                     v[4 * i + 3] + bv[4 * i + 3]);
               if (prm.accumulate) {
                 const float4 e = dst[i];
                 o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
@@ -227,7 +340,17 @@ __global__ void __launch_bounds__(256, 1)
               dst[i] = o;
               s0 += (o.x + o.y) + (o.z + o.w);
               s1 += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+              gs[4 * i] += o.x; gs[4 * i + 1] += o.y; gs[4 * i + 2] += o.z; gs[4 * i + 3] += o.w;
             }
+          }
+        }
+        if (!kGapPersist && prm.gap != nullptr) {
+          // wide layers: column sums flushed per tile (a tile lies in one sample)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a = warp_sum(gs[i]);
+            if (lane == 0) atomicAdd(&prm.gap[(long long)b * prm.Cout + nsp * C::N + j * 16 + i], a);
+            gs[i] = 0.f;
           }
         }
       }
@@ -251,65 +374,50 @@ __global__ void __launch_bounds__(256, 1)
         }
       }
     }
+    if (kGapPersist) flush_gap(gap_b);
   }
 
   // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == kLoaderWarps + 5) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
 // ------------------------------------------------------------------------------------------ packing
-// wp[ns][c][kd][t9][pl][n][j] = tf32( w[tw(kd*9+t9)*wtap + (8c+4pl+j)*sw_in + (ns*N+n)*sw_out] )
-__global__ void tc_pack_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cin, int Cout, int N,
+// wp[ns][c][tap][pl][n][j] = op( w[tw(tap)*wtap + (CK*c + T*pl + j)*sw_in + (ns*N+n)*sw_out] ),  op = bf16 | tf32
+template <bool BF16>
+__global__ void tc_pack_kernel(const float* __restrict__ w, void* __restrict__ wp, int taps, int Cin, int Cout, int N,
                                long long wtap, int sw_in, int sw_out, int flip) {
-  const long long total = 27LL * Cin * Cout;
-  const int nch = Cin / 8;
+  constexpr int T = BF16 ? 8 : 4;
+  const long long total = (long long)taps * Cin * Cout;
+  const int nch = Cin / (2 * T);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
-    const int j = (int)(r % 4); r /= 4;
+    const int j = (int)(r % T); r /= T;
     const int n = (int)(r % N); r /= N;
     const int pl = (int)(r % 2); r /= 2;
-    const int t9 = (int)(r % 9); r /= 9;
-    const int kd = (int)(r % 3); r /= 3;
+    int tap = (int)(r % taps); r /= taps;
     const int c = (int)(r % nch); r /= nch;
     const int ns = (int)r;
-    int tap = kd * 9 + t9;
-    if (flip) tap = 26 - tap;
-    const int ci = 8 * c + 4 * pl + j, co = ns * N + n;
+    if (flip) tap = taps - 1 - tap;
+    const int ci = 2 * T * c + T * pl + j, co = ns * N + n;
     const float v = w[(long long)tap * wtap + (long long)ci * sw_in + (long long)co * sw_out];
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    wp[i] = __uint_as_float(u);
+    if (BF16) {
+      reinterpret_cast<__nv_bfloat16*>(wp)[i] = __float2bfloat16_rn(v);
+    } else {
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+      reinterpret_cast<float*>(wp)[i] = __uint_as_float(u);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------ host
-static int pick_n(int Cout) {
-  if (Cout % 128 == 0) return 128;
-  if (Cout == 64) return 64;
-  if (Cout == 32) return 32;
-  return 16;
-}
-
-bool tc_conv_supported(const ConvGeom& g) {
-  return g.k == 3 && g.mode == CONV_S1 && g.Cin % 8 == 0 && g.Cout % 16 == 0 && g.Cin >= 8 && g.Cout >= 16;
-}
-
-size_t tc_packed_weight_elems(int k, int Cin, int Cout) { return (size_t)k * k * k * Cin * Cout; }
-
-int launch_tc_pack_weights(const ConvGeom& g, const float* w, float* wp, cudaStream_t s) {
-  B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "pack_weights: shape not on the tcgen05 path");
-  const long long total = 27LL * g.Cin * g.Cout;
-  const unsigned grid = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  tc_pack_kernel<<<grid, 256, 0, s>>>(w, wp, g.Cin, g.Cout, pick_n(g.Cout), g.wtap, g.sw_in, g.sw_out, g.flip);
-  B3D_LAUNCH_CHECK("tc_pack");
-  return B3D_OK;
-}
+static int g_precision_bf16 = 1;   // operand type of the conv fwd/dgrad MMAs: 1 = bf16, 0 = tf32
 
 EncodeTiledFn tma_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -323,56 +431,92 @@ EncodeTiledFn tma_encode_fn() {
   return fn;
 }
 
+static int pick_n(int Cout) {
+  if (Cout % 128 == 0) return 128;
+  if (Cout == 64) return 64;
+  if (Cout == 32) return 32;
+  return 16;
+}
+
+static bool use_bf16(const ConvGeom& g) { return g_precision_bf16 && g.Cin % 16 == 0; }
+
+bool tc_conv_supported(const ConvGeom& g) {
+  return (g.k == 3 || g.k == 1) && g.mode == CONV_S1 && g.Cin % 8 == 0 && g.Cout % 16 == 0 && g.Cin >= 8 &&
+         g.Cout >= 16;
+}
+
+size_t tc_packed_weight_elems(int k, int Cin, int Cout) { return (size_t)k * k * k * Cin * Cout; }
+
+int launch_tc_pack_weights(const ConvGeom& g, const float* w, float* wp, cudaStream_t s) {
+  B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "pack_weights: shape not on the tcgen05 path");
+  const int taps = g.k * g.k * g.k;
+  const long long total = (long long)taps * g.Cin * g.Cout;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  if (use_bf16(g))
+    tc_pack_kernel<true><<<grid, 256, 0, s>>>(w, wp, taps, g.Cin, g.Cout, pick_n(g.Cout), g.wtap, g.sw_in, g.sw_out,
+                                             g.flip);
+  else
+    tc_pack_kernel<false><<<grid, 256, 0, s>>>(w, wp, taps, g.Cin, g.Cout, pick_n(g.Cout), g.wtap, g.sw_in,
+                                              g.sw_out, g.flip);
+  B3D_LAUNCH_CHECK("tc_pack");
+  return B3D_OK;
+}
+
 template <class C>
 static int launch_cfg(const ConvGeom& g, const float* x, const float* wp, const float* bias, float* y,
-                      double* stats, cudaStream_t s) {
-  EncodeTiledFn enc = tma_encode_fn();
-  B3D_REQUIRE(enc != nullptr, B3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  CUtensorMap tm;
-  const cuuint64_t dims[5] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di,
-                              (cuuint64_t)g.B};
-  const cuuint64_t strides[4] = {(cuuint64_t)g.xp * 4, (cuuint64_t)g.xp * 4 * g.Wi,
-                                 (cuuint64_t)g.xp * 4 * g.Wi * g.Hi, (cuuint64_t)g.xp * 4 * g.Wi * g.Hi * g.Di};
-  const cuuint32_t box[5] = {4, (cuuint32_t)C::HW, (cuuint32_t)C::HH, (cuuint32_t)C::HD, 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)x, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  B3D_REQUIRE(r == CUDA_SUCCESS, B3D_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+                      double* stats, float* gap, cudaStream_t s) {
   TcParams p;
-  p.wp = wp; p.bias = bias; p.y = y; p.stats = stats;
-  p.B = g.B; p.D = g.Do; p.H = g.Ho; p.W = g.Wo; p.Cin = g.Cin; p.Cout = g.Cout; p.yp = g.yp;
+  p.x = x; p.wp = wp; p.bias = bias; p.y = y; p.stats = stats; p.gap = gap;
+  p.B = g.B; p.D = g.Do; p.H = g.Ho; p.W = g.Wo; p.Cin = g.Cin; p.Cout = g.Cout; p.xp = g.xp; p.yp = g.yp;
   p.ntd = (g.Do + C::TD - 1) / C::TD; p.nth = (g.Ho + C::TH - 1) / C::TH; p.ntw = (g.Wo + C::TW - 1) / C::TW;
   p.ntiles = g.B * p.ntd * p.nth * p.ntw;
   p.accumulate = g.accumulate; p.groups = g.groups > 0 ? g.groups : 1;
   p.vpc = ((long long)g.Do * g.Ho * g.Wo) / p.groups;
   static bool attr_set = false;
   if (!attr_set) {
-    B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv3_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),
-                    "cudaFuncSetAttribute(conv3_tc)"));
+    B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),
+                    "cudaFuncSetAttribute(conv_tc)"));
     attr_set = true;
   }
   const int nsplit = g.Cout / C::N;
   dim3 grid((unsigned)(p.ntiles < sm_count() ? p.ntiles : sm_count()), (unsigned)nsplit, 1);
-  // N-splits share SMs: keep one persistent CTA per SM in total
-  if (nsplit > 1) grid.x = (grid.x + nsplit - 1) / nsplit;
-  conv3_tc_kernel<C><<<grid, 256, C::SMEM, s>>>(tm, p);
-  B3D_LAUNCH_CHECK("conv3_tc");
+  if (nsplit > 1) grid.x = (grid.x + nsplit - 1) / nsplit;   // keep ~one persistent CTA per SM in total
+  conv_tc_kernel<C><<<grid, kTcThreads, C::SMEM, s>>>(p);
+  B3D_LAUNCH_CHECK("conv_tc");
   return B3D_OK;
+}
+
+template <int KS, bool BF16>
+static int dispatch_n(const ConvGeom& g, const float* x, const float* wp, const float* bias, float* y,
+                      double* stats, float* gap, cudaStream_t s) {
+  switch (pick_n(g.Cout)) {
+    case 128: return launch_cfg<TcCfg<128, 2, 1, KS, BF16>>(g, x, wp, bias, y, stats, gap, s);
+    case 64: return launch_cfg<TcCfg<64, 2, 2, KS, BF16>>(g, x, wp, bias, y, stats, gap, s);
+    case 32: return launch_cfg<TcCfg<32, 4, 2, KS, BF16>>(g, x, wp, bias, y, stats, gap, s);
+    default: return launch_cfg<TcCfg<16, 4, 2, KS, BF16>>(g, x, wp, bias, y, stats, gap, s);
+  }
 }
 
 int launch_conv_tc(const ConvGeom& g, const float* x, const float* wp, const float* bias, float* y, double* stats,
                    float* gap, cudaStream_t s) {
   B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "conv: shape not supported by the tcgen05 path");
-  B3D_REQUIRE(gap == nullptr && g.act == 0, B3D_ERR_UNSUPPORTED, "tcgen05 conv: gap/activation epilogues not built");
-  B3D_REQUIRE(g.xp % 4 == 0 && g.yp % 4 == 0 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)wp) & 15) == 0,
-              B3D_ERR_LAYOUT, "tcgen05 conv: 16-byte alignment required");
-  switch (pick_n(g.Cout)) {
-    case 128: return launch_cfg<TcCfg<128, 2, 1>>(g, x, wp, bias, y, stats, s);
-    case 64: return launch_cfg<TcCfg<64, 2, 2>>(g, x, wp, bias, y, stats, s);
-    case 32: return launch_cfg<TcCfg<32, 4, 2>>(g, x, wp, bias, y, stats, s);
-    default: return launch_cfg<TcCfg<16, 4, 2>>(g, x, wp, bias, y, stats, s);
-  }
+  B3D_REQUIRE(g.act == 0, B3D_ERR_UNSUPPORTED, "tcgen05 conv: activation epilogue not built");
+  B3D_REQUIRE(g.xp % 8 == 0 && g.yp % 4 == 0 && ((uintptr_t)x & 31) == 0 &&
+                  (((uintptr_t)y | (uintptr_t)wp) & 15) == 0,
+              B3D_ERR_LAYOUT, "tcgen05 conv: x must be 32-byte aligned with a channel pitch multiple of 8");
+  const bool bf = use_bf16(g);
+  if (g.k == 3)
+    return bf ? dispatch_n<3, true>(g, x, wp, bias, y, stats, gap, s)
+              : dispatch_n<3, false>(g, x, wp, bias, y, stats, gap, s);
+  return bf ? dispatch_n<1, true>(g, x, wp, bias, y, stats, gap, s)
+            : dispatch_n<1, false>(g, x, wp, bias, y, stats, gap, s);
 }
 
 }  // namespace b3d
+
+// 1 = bf16 operands (default), 0 = tf32 operands for the tcgen05 conv forward / data-gradient kernel
+extern "C" int b3d_set_conv_precision(int bf16) {
+  b3d::g_precision_bf16 = bf16 ? 1 : 0;
+  return 0;
+}
+extern "C" int b3d_get_conv_precision(void) { return b3d::g_precision_bf16; }

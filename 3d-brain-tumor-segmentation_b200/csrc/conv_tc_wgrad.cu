@@ -113,27 +113,31 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // D=f32, A=B=bf16, both MN-major, N=Cout, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(prm.Cout >> 3) << 17) | ((128u >> 4) << 24);
-      int s = 0, ph = 0;
-      uint32_t acc = 0;
-      const int rowc = prm.HW, planec = prm.HH * prm.HW;
-      for (int tile = blockIdx.x; tile < prm.ntiles; tile += prm.nsplit) {
-        mbar_wait(smem_u32(&full[s]), ph);
-        tc_fence_after();
-        const uint32_t xaddr = smem_u32(smem + (size_t)s * prm.stage_bytes);
-        // K = 16 voxels per MMA: 8 along w (16 B apart) x 2 h rows (LBO = row pitch of each operand)
-        const uint64_t adesc0 = make_desc(xaddr, (uint32_t)prm.HW * 16, (uint32_t)prm.px);
-        const uint64_t bdesc0 =
-            make_desc(xaddr + (uint32_t)(prm.xplanes_max * prm.px), (uint32_t)prm.TW * 16, (uint32_t)prm.py);
-        for (int d = 0; d < prm.TD; ++d)
-          for (int h = 0; h < prm.TH; h += 2)
-            for (int w8 = 0; w8 < prm.TW; w8 += 8) {
-              const uint32_t ycell = (uint32_t)((d * prm.TH + h) * prm.TW + w8);
-              const uint32_t xcell = (uint32_t)((d * prm.HH + h) * prm.HW + w8);
-              const uint64_t bdesc = bdesc0 + ycell;
+    // whole warp runs the warp-uniform control flow (descriptors stay in uniform registers); one elected
+    // lane issues the MMAs and commits
+    const bool leader = elect_one();
+    // D=f32, A=B=bf16, both MN-major, N=Cout, M=128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(prm.Cout >> 3) << 17) | ((128u >> 4) << 24);
+    int s = 0, ph = 0;
+    uint32_t acc = 0;
+    const int rowc = prm.HW, planec = prm.HH * prm.HW;
+    const uint32_t smem_base = smem_u32(smem);
+    for (int tile = blockIdx.x; tile < prm.ntiles; tile += prm.nsplit) {
+      mbar_wait(smem_u32(&full[s]), ph);
+      tc_fence_after();
+      const uint32_t xaddr = smem_base + (uint32_t)s * (uint32_t)prm.stage_bytes;
+      // K = 16 voxels per MMA: 8 along w (16 B apart) x 2 h rows (LBO = row pitch of each operand)
+      const uint64_t adesc0 = make_desc(xaddr, (uint32_t)prm.HW * 16, (uint32_t)prm.px);
+      const uint64_t bdesc0 =
+          make_desc(xaddr + (uint32_t)(prm.xplanes_max * prm.px), (uint32_t)prm.TW * 16, (uint32_t)prm.py);
+      for (int d = 0; d < prm.TD; ++d)
+        for (int h = 0; h < prm.TH; h += 2)
+          for (int w8 = 0; w8 < prm.TW; w8 += 8) {
+            const uint32_t ycell = (uint32_t)((d * prm.TH + h) * prm.TW + w8);
+            const uint32_t xcell = (uint32_t)((d * prm.HH + h) * prm.HW + w8);
+            const uint64_t bdesc = bdesc0 + ycell;
+            if (leader) {
 #pragma unroll
               for (int t = 0; t < TG; ++t) {
                 const int tkd = (TG == 27) ? t / 9 : 0;
@@ -142,13 +146,15 @@ __global__ void __launch_bounds__(256, 1)
                 const uint32_t off = xcell + (uint32_t)(tkd * planec + tkh * rowc + tkw);
                 tc_mma_bf16(tmem_base + t * prm.Cout, adesc0 + off, bdesc, idesc, acc);
               }
-              acc = 1;
             }
-        tc_commit(smem_u32(&empty[s]));
-        if (++s == prm.nstages) { s = 0; ph ^= 1; }
-      }
-      tc_commit(smem_u32(done));
+            acc = 1;
+          }
+      if (leader) tc_commit(smem_u32(&empty[s]));
+      __syncwarp();
+      if (++s == prm.nstages) { s = 0; ph ^= 1; }
     }
+    if (leader) tc_commit(smem_u32(done));
+    __syncwarp();
   } else if (warp >= 4) {
     // final reduction of this CTA's partial dw into global memory
     const int q = warp - 4;

@@ -49,6 +49,18 @@ def pack_weights(w: torch.Tensor, dgrad: bool) -> torch.Tensor:
 USE_TC = {"on": True}
 
 
+def set_conv_precision(name: str):
+    """Operand type of the tcgen05 conv forward / data-gradient MMAs: 'bf16' (default) or 'tf32'
+    (fp32 accumulation in TMEM either way; the weight-gradient kernel always uses bf16 operands)."""
+    if name not in ("bf16", "tf32"):
+        raise ValueError(name)
+    lib.b3d_set_conv_precision(1 if name == "bf16" else 0)
+
+
+def get_conv_precision() -> str:
+    return "bf16" if lib.b3d_get_conv_precision() else "tf32"
+
+
 class Conv3dFn(Function):
     """Conv3D / Conv3DTranspose with TF 'SAME' padding (+bias, optional sigmoid), optionally emitting
     GroupNorm chunk statistics and global-average-pool sums of its output from the epilogue."""
@@ -72,7 +84,7 @@ class Conv3dFn(Function):
         if want_gap:
             gap = _new((B, Cout), x)
         wp = None
-        if USE_TC["on"] and not want_gap and not act and tc_supported(k, stride, transposed, Cin, Cout):
+        if USE_TC["on"] and not act and tc_supported(k, stride, transposed, Cin, Cout):
             wp = pack_weights(w, False)
         _call("b3d_conv3d_fwd", x, w, bias, y, stride, int(transposed), int(act), stats, gn_groups or 1, gap, 0, wp)
         ctx.save_for_backward(x, w, y if act else None)

@@ -43,13 +43,28 @@ CONV_CASES = [
 ]
 
 
+MODES = ["fp32", "tf32", "bf16"]      # CUDA-core fp32 | tcgen05 tf32 operands | tcgen05 bf16 operands
+MODE_TOL = {"fp32": TOL32, "tf32": TOL_TF32, "bf16": TOL_BF16}
+
+
+def set_mode(b3d, mode):
+    b3d.ops.USE_TC["on"] = mode != "fp32"
+    b3d.ops.set_conv_precision("tf32" if mode == "tf32" else "bf16")
+
+
+def reset_mode(b3d):
+    b3d.ops.USE_TC["on"] = True
+    b3d.ops.set_conv_precision("bf16")
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("use_tc", [False, True])
-def test_conv_fwd_bwd(b3d, dev, case, use_tc):
+@pytest.mark.parametrize("mode", MODES)
+def test_conv_fwd_bwd(b3d, dev, case, mode):
     sp, cin, cout, k, stride, tr = case
+    use_tc = mode != "fp32"
     if use_tc and not b3d.ops.tc_supported(k, stride, tr, cin, cout):
         pytest.skip("shape not on the tcgen05 path")
-    b3d.ops.USE_TC["on"] = use_tc
+    set_mode(b3d, mode)
     try:
         B = 2
         x = t64(B, *sp, cin, seed=1)
@@ -62,14 +77,14 @@ def test_conv_fwd_bwd(b3d, dev, case, use_tc):
         xd, wd, bd = dev32(x, dev, True), dev32(w, dev, True), dev32(bias, dev, True)
         y, stats, gap = b3d.ops.conv3d(xd, wd, bd, stride, tr, 0, 0, True)
         (y * dev32(gy, dev)).sum().backward()
-        tol = TOL_TF32 if use_tc else TOL32
+        tol = MODE_TOL[mode]
         assert rel(y, yr) < tol
         assert rel(gap, yr.sum(dim=(1, 2, 3))) < max(tol, 1e-4)
         assert rel(xd.grad, xr.grad) < tol
         assert rel(wd.grad, wr.grad) < (TOL_BF16 if use_tc else tol)
         assert rel(bd.grad, br.grad) < TOL32 * 10
     finally:
-        b3d.ops.USE_TC["on"] = True
+        reset_mode(b3d)
 
 
 @pytest.mark.parametrize("shape", [(2, 8, 8, 8, 16), (1, 20, 6, 4, 16), (2, 5, 3, 3, 8), (1, 4, 4, 4, 32),
@@ -110,10 +125,10 @@ def test_group_norm_value_errors(b3d, dev):
         gn(torch.zeros(1, 2, 2, 2, 12, device=dev))
 
 
-@pytest.mark.parametrize("use_tc", [False, True])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("cfg", [((8, 8, 8), 2, 16, 2), ((4, 8, 16), 32, 32, 2), ((4, 4, 4), 64, 128, 8),
                                  ((3, 3, 3), 16, 16, 2), ((4, 4, 8), 48, 24, 2)])
-def test_resnet_block(b3d, dev, cfg, use_tc):
+def test_resnet_block(b3d, dev, cfg, mode):
     """ResnetBlock forward + every gradient vs the fp64 oracle.  fp32 mode (CUDA-core convs) pins the fused
     epilogue / GroupNorm / scSE backward formulas tightly; tensor-core mode (TF32 fwd/dgrad, bf16 wgrad)
     is held to north_star's per-layer tolerance on the output and to a looser bound on gradients, which
@@ -142,7 +157,8 @@ def test_resnet_block(b3d, dev, cfg, use_tc):
     gy = t64(*yr.shape, seed=11)
     (yr * gy).sum().backward()
 
-    b3d.ops.USE_TC["on"] = use_tc
+    use_tc = mode != "fp32"
+    set_mode(b3d, mode)
     blk = b3d.ResnetBlock(f, reduction=red)
     xd = dev32(x, dev, True)
     blk(xd.detach())
@@ -161,11 +177,11 @@ def test_resnet_block(b3d, dev, cfg, use_tc):
         (y * dev32(gy, dev)).sum().backward()
         torch.cuda.synchronize()
     finally:
-        b3d.ops.USE_TC["on"] = True
+        reset_mode(b3d)
     errs = {n: rel(t.grad, pr[pre + n].grad) for n, t in names.items()}
-    print("resnet_block", cfg, use_tc, "y", rel(y, yr), "dx", rel(xd.grad, xr.grad),
+    print("resnet_block", cfg, mode, "y", rel(y, yr), "dx", rel(xd.grad, xr.grad),
           {k: f"{v:.1e}" for k, v in errs.items()})
-    ytol, gtol = (TOL_TF32, 5e-2) if use_tc else (TOL32, 2e-4)
+    ytol, gtol = {"fp32": (TOL32, 2e-4), "tf32": (TOL_TF32, 5e-2), "bf16": (TOL_BF16, 2e-1)}[mode]
     assert rel(y, yr) < ytol
     assert rel(xd.grad, xr.grad) < gtol
     for n, e in errs.items():
@@ -255,6 +271,7 @@ def test_concat_and_dropout(b3d, dev):
 TC_CASES = [
     # (B, spatial, Cin, Cout)
     (1, (8, 16, 16), 16, 16),
+    (1, (4, 16, 8), 24, 16),       # Cin % 16 != 0: tf32 operands even in bf16 mode
     (2, (4, 16, 8), 8, 32),
     (1, (6, 32, 24), 32, 64),
     (1, (5, 24, 20), 64, 128),      # partial tiles in every dim (inference-like 20x24x20)
@@ -281,8 +298,8 @@ def test_tc_conv_vs_oracle_and_generic(b3d, dev, case):
     S = sp[0] * sp[1] * sp[2]
     groups = 8 if S % 8 == 0 else 0
     res = {}
-    for tc in (False, True):
-        b3d.ops.USE_TC["on"] = tc
+    for tc in MODES:
+        set_mode(b3d, tc)
         try:
             xd, wd, bd = dev32(x, dev, True), dev32(w, dev, True), dev32(bias, dev, True)
             y, stats, _ = b3d.ops.conv3d(xd, wd, bd, 1, False, 0, groups, False)
@@ -290,14 +307,14 @@ def test_tc_conv_vs_oracle_and_generic(b3d, dev, case):
             torch.cuda.synchronize()
             res[tc] = (y.detach(), stats, xd.grad, wd.grad)
         finally:
-            b3d.ops.USE_TC["on"] = True
-    for tc, tol in ((False, TOL32), (True, TOL_TF32)):
+            reset_mode(b3d)
+    for tc, tol in MODE_TOL.items():
         y, stats, dx, dw = res[tc]
         assert rel(y, yr) < tol, ("y", tc, rel(y, yr))
         assert rel(dx, xr.grad) < tol, ("dx", tc, rel(dx, xr.grad))
-        assert rel(dw, wr.grad) < (TOL_BF16 if tc else tol), ("dw", tc, rel(dw, wr.grad))
+        assert rel(dw, wr.grad) < (TOL_BF16 if tc != "fp32" else tol), ("dw", tc, rel(dw, wr.grad))
         if groups:
             ch = yr.detach().reshape(B, groups, -1)
             ref = torch.stack([ch.sum(-1), (ch ** 2).sum(-1)], dim=-1)
             assert rel(stats, ref) < max(tol, 1e-4), ("stats", tc)
-    assert rel(res[True][0], res[False][0]) < TOL_TF32
+    assert rel(res["tf32"][0], res["fp32"][0]) < TOL_TF32 and rel(res["bf16"][0], res["fp32"][0]) < TOL_BF16

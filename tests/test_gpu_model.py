@@ -27,8 +27,21 @@ def build(b3d, dev, crop, p, **kw):
     return model, f
 
 
-@pytest.mark.parametrize("use_tc", [False, True])
-def test_model_matches_reference_fixture_16(b3d, dev, use_tc):
+MODES = ["fp32", "tf32", "bf16"]      # CUDA-core fp32 | tcgen05 tf32 operands | tcgen05 bf16 operands
+
+
+def set_mode(b3d, mode):
+    b3d.ops.USE_TC["on"] = mode != "fp32"
+    b3d.ops.set_conv_precision("tf32" if mode == "tf32" else "bf16")
+
+
+def reset_mode(b3d):
+    b3d.ops.USE_TC["on"] = True
+    b3d.ops.set_conv_precision("bf16")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_model_matches_reference_fixture_16(b3d, dev, mode):
     """Against tests/golden/model_16.npz = the reference's own model.py / layers / util.py executed in fp64.
     fp32 mode must reproduce outputs, loss, dice and all 260 gradient norms tightly; tensor-core mode is
     held to north_star's tolerances (per-layer 2e-3, loss 1e-3, argmax 99.9 %)."""
@@ -36,7 +49,8 @@ def test_model_matches_reference_fixture_16(b3d, dev, use_tc):
     crop = (16, 16, 16)
     p = R.init_params(R.param_shapes(crop=crop))
     x, y, eps, mask = R.synth_batch((1,) + crop)
-    b3d.ops.USE_TC["on"] = use_tc
+    use_tc = mode != "fp32"
+    set_mode(b3d, mode)
     try:
         model, f = build(b3d, dev, crop, p)
         assert len(model.trainable_variables) == 260 and len(model.losses) == 168
@@ -48,21 +62,21 @@ def test_model_matches_reference_fixture_16(b3d, dev, use_tc):
         yi = model(f(x), training=False, inference=True)
         torch.cuda.synchronize()
     finally:
-        b3d.ops.USE_TC["on"] = True
-    otol = 2e-3 if use_tc else 2e-5
+        reset_mode(b3d)
+    otol = {"fp32": 2e-5, "tf32": 2e-3, "bf16": 1e-2}[mode]
     for name, o in zip(("y_pred", "y_vae", "z_mean", "z_logvar"), outs):
         assert rel(o, g[name]) < otol, (name, rel(o, g[name]))
     assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < (1e-3 if use_tc else 1e-5)
     assert abs(float(macro) - float(g["macro"])) < 2e-3 and abs(float(micro) - float(g["micro"])) < 2e-3
     nv = model.named_variables()
     names = list(g["grad_names"])
-    ntol = 1e-1 if use_tc else 2e-3          # 16^3 is the ill-conditioned extreme (1-voxel GN chunks)
+    ntol = {"fp32": 2e-3, "tf32": 1e-1, "bf16": 3e-1}[mode]   # 16^3 is the ill-conditioned extreme (1-voxel GN chunks)
     bad = [(k, float(nv[k].grad.norm()), float(r)) for k, r in zip(names, g["grad_norms"])
            if abs(float(nv[k].grad.norm()) - r) > ntol * r + 1e-7]
     assert not bad, bad[:8]
     for k in g.files:
         if k.startswith("grad:"):
-            assert rel(nv[k[5:]].grad, g[k]) < (2e-1 if use_tc else 2e-3), (k, rel(nv[k[5:]].grad, g[k]))
+            assert rel(nv[k[5:]].grad, g[k]) < {"fp32": 2e-3, "tf32": 2e-1, "bf16": 5e-1}[mode], (k, rel(nv[k[5:]].grad, g[k]))
     assert yi[1] is None and yi[2] is None and yi[3] is None
     assert rel(yi[0], g["y_pred_inference"]) < otol
     agree = (yi[0].argmax(-1).cpu() == torch.from_numpy(g["y_pred_inference"]).argmax(-1)).float().mean()
@@ -75,9 +89,9 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-300))
 
 
-@pytest.mark.parametrize("use_tc", [False, True])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("crop", [(32, 48, 16), (64, 64, 64)])
-def test_train_step_matches_oracle(b3d, dev, crop, use_tc):
+def test_train_step_matches_oracle(b3d, dev, crop, mode):
     """One full training step (train.py:140-152) against the fp64 oracle.
 
     fp32 mode (CUDA-core convs) proves wiring and every backward formula tightly; TF32 mode (tcgen05 convs)
@@ -90,7 +104,8 @@ def test_train_step_matches_oracle(b3d, dev, crop, use_tc):
     outs = R.model_forward(pg, x, eps, dropout_mask=mask)
     ref = R.dice_vae_loss(x, y, *outs) + R.l2_reg(pg)
     ref.backward()
-    b3d.ops.USE_TC["on"] = use_tc
+    use_tc = mode != "fp32"
+    set_mode(b3d, mode)
     try:
         model, f = build(b3d, dev, crop, p)
         opt = b3d.ScheduledOptim(learning_rate=1e-4)
@@ -100,7 +115,8 @@ def test_train_step_matches_oracle(b3d, dev, crop, use_tc):
                                             dropout_mask=f(mask), eps=f(eps))
         torch.cuda.synchronize()
     finally:
-        b3d.ops.USE_TC["on"] = True
+        reset_mode(b3d)
+    print(f"crop {crop} {mode}: loss rel err {abs(float(loss) - float(ref)) / float(ref):.2e}")
     assert abs(float(loss) - float(ref)) / float(ref) < 1e-3
     mr, ur = R.dice_coefficient(y, outs[0].detach())
     assert abs(float(macro) - float(mr)) < 2e-3 and abs(float(micro) - float(ur)) < 2e-3
@@ -108,10 +124,11 @@ def test_train_step_matches_oracle(b3d, dev, crop, use_tc):
     errs = sorted(((rel(nv[k].grad, pg[k].grad), k) for k in p), reverse=True)
     coss = sorted((_cos(nv[k].grad, pg[k].grad), k) for k in p)
     med = errs[len(errs) // 2][0]
-    print(f"crop {crop} tc={use_tc}: grad rel-L2 max {errs[0]}, median {med:.2e}; min cosine {coss[0]}")
+    print(f"crop {crop} {mode}: grad rel-L2 max {errs[0]}, median {med:.2e}; min cosine {coss[0]}")
     if use_tc:
-        assert coss[0][0] > 0.97 and coss[len(coss) // 10][0] > 0.995, coss[:5]
-        assert med < 3e-2, med
+        cmin, c10 = (0.97, 0.995) if mode == "tf32" else (0.90, 0.98)
+        assert coss[0][0] > cmin and coss[len(coss) // 10][0] > c10, coss[:5]
+        assert med < (3e-2 if mode == "tf32" else 1e-1), med
     else:
         big = min(crop) >= 64
         assert med < (3e-3 if big else 3e-2), med

@@ -14,6 +14,9 @@ ops = b3d.ops
 dev = torch.device("cuda:0")
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"
+ops.set_conv_precision(prec)
+print("conv precision:", ops.get_conv_precision())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 # (spatial, Cin, Cout) of the default model's 3x3x3 convs, largest first
@@ -45,12 +48,21 @@ for n, cin, cout in SHAPES:
     if which in ("fwd", "all"):
         wp = ops.pack_weights(w, False)
         ms = timeit(lambda: ops._call("b3d_conv3d_fwd", x, w, bias, y, 1, 0, 0, stats, 8, None, 0, wp))
+        ms2 = timeit(lambda: ops._call("b3d_conv3d_fwd", x, w, bias, y, 1, 0, 0, None, 1, None, 0, wp))
         io = 4.0 * n ** 3 * (cin + cout)
-        line += f"| fwd {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s (io {io / ms / 1e6:6.0f} GB/s) "
+        line += (f"| fwd {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s (io {io / ms / 1e6:6.0f} GB/s) "
+                 f"| no-stats {ms2 * 1e3:8.1f} us {flops / ms2 / 1e9:7.1f} TF/s ")
     if which in ("wgrad", "all"):
         dw = torch.empty_like(w)
         xb = torch.empty(x.shape, device=dev, dtype=torch.bfloat16)
         yb = torch.empty(dy.shape, device=dev, dtype=torch.bfloat16)
         ms = timeit(lambda: ops._call("b3d_conv3d_wgrad", x, dy, dw, None, 1, 0, xb, yb))
         line += f"| wgrad(+casts) {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s "
+    if which in ("k1", "all"):
+        w1 = torch.randn(1, 1, 1, cin, cout, device=dev) * 0.05
+        wp1 = ops.pack_weights(w1, False)
+        gap = torch.empty(1, cout, device=dev)
+        ms = timeit(lambda: ops._call("b3d_conv3d_fwd", x, w1, bias, y, 1, 0, 0, None, 1, gap, 0, wp1))
+        io = 4.0 * n ** 3 * (cin + cout)
+        line += f"| 1x1x1+gap {ms * 1e3:8.1f} us (io {io / ms / 1e6:6.0f} GB/s) "
     print(line, flush=True)
