@@ -416,7 +416,12 @@ static int block_geom(const TView& res, int groups, bool has_gn, BlockGeom* gm, 
   gm->cg = has_gn ? F / groups : F;
   const int vstep = kBT / T;
   // ~8 voxel-iterations per thread-group, but enough CTAs to fill the machine
+  // ~16 voxel-iterations per thread-group at least, and no more than ~4 waves of CTAs in total (the reducing
+  // kernels end in a handful of atomics per CTA)
   long long vp = (long long)vstep * 16;
+  const long long cap = (4LL * sm_count() + B * G - 1) / (B * G);
+  const long long need = ((gm->vpc + cap - 1) / cap + vstep - 1) / vstep * vstep;
+  if (need > vp) vp = need;
   gm->vox_per_cta = (int)vp;
   *nchunks = (int)(B * G);
   B3D_REQUIRE(*nchunks <= 65535, B3D_ERR_SHAPE, "batch*groups too large");

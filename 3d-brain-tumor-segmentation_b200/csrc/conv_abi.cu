@@ -119,7 +119,7 @@ int geom_dgrad(ConvGeom& g, const TView& dy, const TView& w, const TView& dx, in
     B3D_REQUIRE(w.shape[3] == g.Cout && w.shape[4] == g.Cin, B3D_ERR_SHAPE, "conv dgrad: kernel/channels mismatch");
     B3D_TRY(spatial_ok(dx, dy, stride, "conv dgrad"));
     g.mode = stride == 1 ? CONV_S1 : CONV_UP;
-    g.flip = stride == 1 ? 1 : 0;
+    g.flip = stride == 1 ? 1 : 0;   // taps reversed; also marks the backward pass for the precision choice
     g.wtap = (long long)g.Cin * g.Cout; g.sw_in = 1; g.sw_out = g.Cin;  // w[t][ci_layer][co_layer]
   } else {
     B3D_REQUIRE(w.shape[3] == g.Cin && w.shape[4] == g.Cout, B3D_ERR_SHAPE, "conv-transpose dgrad: kernel mismatch");

@@ -35,20 +35,23 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restr
                                                            long long L) {
   const int chunk = blockIdx.y;
   const float* xc = x + (long long)chunk * L;
-  const long long base = (long long)blockIdx.x * (kThreads * kIter * VEC);
   float s[2] = {0.f, 0.f};
+  // reducing kernels walk several segments per CTA so that few CTAs contend on one fp64 atomic
+  for (long long base = (long long)blockIdx.x * (kThreads * kIter * VEC); base < L;
+       base += (long long)gridDim.x * (kThreads * kIter * VEC)) {
 #pragma unroll
-  for (int k = 0; k < kIter; ++k) {
-    const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
-    if (e < L) {
-      if (VEC == 4) {
-        const float4 v = ld_stream(reinterpret_cast<const float4*>(xc + e));
-        s[0] += (v.x + v.y) + (v.z + v.w);
-        s[1] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-      } else {
-        const float v = xc[e];
-        s[0] += v;
-        s[1] += v * v;
+    for (int k = 0; k < kIter; ++k) {
+      const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
+      if (e < L) {
+        if (VEC == 4) {
+          const float4 v = ld_stream(reinterpret_cast<const float4*>(xc + e));
+          s[0] += (v.x + v.y) + (v.z + v.w);
+          s[1] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        } else {
+          const float v = xc[e];
+          s[0] += v;
+          s[1] += v * v;
+        }
       }
     }
   }
@@ -118,7 +121,6 @@ __global__ void __launch_bounds__(kThreads)
   float mean, rstd;
   chunk_moments(stats, chunk, 1.0 / (double)gm.L, eps, mean, rstd);
   const long long off = (long long)chunk * gm.L;
-  const long long base = (long long)blockIdx.x * (kThreads * kIter * VEC);
   const int jbase = g * gm.cg;
   const long long goff = (long long)g * gm.L;
   const bool invariant = ((kThreads * VEC) % gm.cg) == 0;
@@ -127,6 +129,8 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
   for (int i = 0; i < VEC; ++i) ag[i] = ab[i] = 0.f;
   int c_first = -1;
+  for (long long base = (long long)blockIdx.x * (kThreads * kIter * VEC); base < gm.L;
+       base += (long long)gridDim.x * (kThreads * kIter * VEC))
 #pragma unroll
   for (int k = 0; k < kIter; ++k) {
     const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
@@ -253,9 +257,15 @@ static int gn_geom(const TView& x, int groups, ChunkGeom* gm, int* nchunks) {
   return B3D_OK;
 }
 
-static inline dim3 gn_grid(const ChunkGeom& gm, int nchunks, int vec) {
+static inline dim3 gn_grid(const ChunkGeom& gm, int nchunks, int vec, bool reducing = false) {
   const long long per = (long long)kThreads * kIter * vec;
-  return dim3((unsigned)((gm.L + per - 1) / per), (unsigned)nchunks, 1);
+  long long gx = (gm.L + per - 1) / per;
+  if (reducing) {                      // grid-stride inside the chunk: <= ~4 waves of CTAs in total
+    long long cap = (4LL * sm_count() + nchunks - 1) / nchunks;
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+  }
+  return dim3((unsigned)gx, (unsigned)nchunks, 1);
 }
 
 static int check_stats(const DLTensor* t, int nchunks, const char* name, TView* v) {
@@ -286,9 +296,9 @@ extern "C" int b3d_gn_stats(const DLTensor* x_, DLTensor* stats_, int groups, vo
   B3D_TRY(cuda_ok(cudaMemsetAsync(st.p, 0, sizeof(double) * 2 * nchunks, s), "memset stats"));
   const bool v4 = (gm.L % 4 == 0) && (((uintptr_t)x.p & 15) == 0);
   if (v4)
-    gn_stats_kernel<4><<<gn_grid(gm, nchunks, 4), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L);
+    gn_stats_kernel<4><<<gn_grid(gm, nchunks, 4, true), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L);
   else
-    gn_stats_kernel<1><<<gn_grid(gm, nchunks, 1), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L);
+    gn_stats_kernel<1><<<gn_grid(gm, nchunks, 1, true), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L);
   B3D_LAUNCH_CHECK("gn_stats");
   return B3D_OK;
 }
@@ -343,7 +353,7 @@ extern "C" int b3d_gn_bwd_reduce(const DLTensor* dy_, const DLTensor* x_, const 
   const bool v4 = (gm.L % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)dy.p) & 15) == 0);
   const size_t smem = sizeof(float) * 2 * gm.cg;
 #define LAUNCH(V, R)                                                                                       \
-  gn_bwd_reduce_kernel<V, R><<<gn_grid(gm, nchunks, V), kThreads, smem, s>>>(                              \
+  gn_bwd_reduce_kernel<V, R><<<gn_grid(gm, nchunks, V, true), kThreads, smem, s>>>(                              \
       (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, \
       (float*)dga.p, (float*)dbe.p, (double*)cs.p, gm, eps)
   if (v4) {

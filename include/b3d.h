@@ -62,8 +62,9 @@ int b3d_conv3d_wgrad(const DLTensor* x, const DLTensor* dy, DLTensor* dw, DLTens
                      int transposed, const DLTensor* x_bf16, const DLTensor* dy_bf16, void* stream);
 int b3d_conv3d_wgrad_tc_supported(int k, int stride, int transposed, int cin, int cout);
 int b3d_conv3d_tc_supported(int k, int stride, int transposed, int c_gathered, int c_produced);
-/* operand type of the tcgen05 conv forward / dgrad MMAs: 1 = bf16 (default), 0 = tf32; fp32 accumulation */
-int b3d_set_conv_precision(int bf16);
+/* operand type of the tcgen05 conv MMAs (1 = bf16, 0 = tf32) for the forward pass and for the data gradient;
+ * defaults: forward tf32, backward bf16; fp32 accumulation either way.  get: bit0 = fwd, bit1 = bwd. */
+int b3d_set_conv_precision(int fwd_bf16, int bwd_bf16);
 int b3d_get_conv_precision(void);
 long long b3d_conv3d_packed_elems(int k, int c_gathered, int c_produced);
 int b3d_conv3d_pack_weights(const DLTensor* w, DLTensor* packed, int dgrad, void* stream);

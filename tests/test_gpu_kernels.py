@@ -49,12 +49,16 @@ MODE_TOL = {"fp32": TOL32, "tf32": TOL_TF32, "bf16": TOL_BF16}
 
 def set_mode(b3d, mode):
     b3d.ops.USE_TC["on"] = mode != "fp32"
-    b3d.ops.set_conv_precision("tf32" if mode == "tf32" else "bf16")
+    if mode == "mixed":                    # the default: tf32 forward, bf16 backward
+        b3d.ops.set_conv_precision("tf32", "bf16")
+    else:
+        p = "tf32" if mode == "tf32" else "bf16"
+        b3d.ops.set_conv_precision(p, p)
 
 
 def reset_mode(b3d):
     b3d.ops.USE_TC["on"] = True
-    b3d.ops.set_conv_precision("bf16")
+    b3d.ops.set_conv_precision("tf32", "bf16")
 
 
 @pytest.mark.parametrize("case", CONV_CASES)

@@ -15,7 +15,7 @@ dev = torch.device("cuda:0")
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"
-ops.set_conv_precision(prec)
+ops.set_conv_precision(prec, prec)
 print("conv precision:", ops.get_conv_precision())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
