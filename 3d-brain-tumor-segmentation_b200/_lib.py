@@ -99,6 +99,8 @@ SIGNATURES = {
     "b3d_mul_scale": "TTTfv",
     "b3d_sigmoid_bwd": "TTTv",
     "b3d_copy_channels": "TTiv",
+    "b3d_flip_normalize": "TTTTiv",
+    "b3d_flip_accumulate": "TTTifiv",
 }
 _CT = {"T": P, "i": _i, "f": _f, "v": _v, "L": _ll, "U": _ull}
 for _name, _sig in SIGNATURES.items():

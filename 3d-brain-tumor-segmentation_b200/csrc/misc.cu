@@ -390,6 +390,44 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// ---- test-time augmentation helpers (reference test.py:105-161) -------------------------------------
+// out[v][c] = (x[flip(v)][c] - mean[c]) / std[c]      (flip bit0 = D, bit1 = H, bit2 = W)
+__global__ void __launch_bounds__(256)
+    flip_normalize_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ sd,
+                          float* __restrict__ out, int D, int H, int W, int C, int flip) {
+  const long long n = (long long)D * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); long long r = i / C;
+    int w = (int)(r % W); r /= W;
+    int h = (int)(r % H); int d = (int)(r / H);
+    if (flip & 1) d = D - 1 - d;
+    if (flip & 2) h = H - 1 - h;
+    if (flip & 4) w = W - 1 - w;
+    const float v = x[(((long long)d * H + h) * W + w) * C + c];
+    out[i] = mean != nullptr ? (v - mean[c]) / sd[c] : v;
+  }
+}
+// acc[v][c] (+)= scale * y[flip(v)][c] * (mask ? mask[v] : 1)
+__global__ void __launch_bounds__(256)
+    flip_accumulate_kernel(const float* __restrict__ y, float* __restrict__ acc, const float* __restrict__ mask,
+                           int D, int H, int W, int C, int flip, float scale, int first) {
+  const long long n = (long long)D * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); long long r = i / C;
+    const long long vox = r;
+    int w = (int)(r % W); r /= W;
+    int h = (int)(r % H); int d = (int)(r / H);
+    if (flip & 1) d = D - 1 - d;
+    if (flip & 2) h = H - 1 - h;
+    if (flip & 4) w = W - 1 - w;
+    float v = scale * y[(((long long)d * H + h) * W + w) * C + c];
+    if (!first) v += acc[i];
+    if (mask != nullptr) v *= mask[vox];
+    acc[i] = v;
+  }
+}
+
 // ================================================================ dropout / elementwise
 __device__ __forceinline__ uint32_t hash_u32(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
@@ -755,5 +793,45 @@ extern "C" int b3d_copy_channels(const DLTensor* src_, DLTensor* dst_, int accum
     copy_channels_kernel<1><<<ew_grid(s.numel, 4), 256, 0, (cudaStream_t)stream>>>(
         (const float*)s.p, (float*)d.p, N, Cc, s.pitch, d.pitch, accumulate);
   B3D_LAUNCH_CHECK("copy_channels");
+  return B3D_OK;
+}
+
+// out = (flip(x) - mean) / std for one [D,H,W,C] volume; mean/std nullable ([C]); flip bits: 1=D 2=H 4=W
+extern "C" int b3d_flip_normalize(const DLTensor* x_, const DLTensor* mean_, const DLTensor* std_, DLTensor* out_,
+                                  int flip, void* stream) {
+  TView x, out, m, sd;
+  B3D_TRY(view(x_, DT_F32, 4, false, "x", &x));
+  B3D_TRY(view(out_, DT_F32, 4, false, "out", &out));
+  B3D_REQUIRE(x.numel == out.numel, B3D_ERR_SHAPE, "flip_normalize: size mismatch");
+  const float *mp = nullptr, *sp = nullptr;
+  if (mean_ != nullptr) {
+    B3D_TRY(flat_f32(mean_, "mean", &m));
+    B3D_TRY(flat_f32(std_, "std", &sd));
+    B3D_REQUIRE(m.numel == x.shape[3] && sd.numel == x.shape[3], B3D_ERR_SHAPE, "flip_normalize: mean/std size");
+    mp = (const float*)m.p; sp = (const float*)sd.p;
+  }
+  flip_normalize_kernel<<<ew_grid(x.numel), 256, 0, (cudaStream_t)stream>>>(
+      (const float*)x.p, mp, sp, (float*)out.p, (int)x.shape[0], (int)x.shape[1], (int)x.shape[2], (int)x.shape[3], flip);
+  B3D_LAUNCH_CHECK("flip_normalize");
+  return B3D_OK;
+}
+
+// acc (+)= scale * flip(y) [* mask]; first=1 overwrites acc; mask nullable ([D,H,W] or [D,H,W,1]), applied to the sum
+extern "C" int b3d_flip_accumulate(const DLTensor* y_, DLTensor* acc_, const DLTensor* mask_, int flip, float scale,
+                                   int first, void* stream) {
+  TView y, acc, mk;
+  B3D_TRY(view(y_, DT_F32, 4, false, "y", &y));
+  B3D_TRY(view(acc_, DT_F32, 4, false, "acc", &acc));
+  B3D_REQUIRE(y.numel == acc.numel, B3D_ERR_SHAPE, "flip_accumulate: size mismatch");
+  const float* mp = nullptr;
+  if (mask_ != nullptr) {
+    B3D_TRY(flat_f32(mask_, "mask", &mk));
+    B3D_REQUIRE(mk.numel == y.numel / y.shape[3], B3D_ERR_SHAPE, "flip_accumulate: mask size");
+    mp = (const float*)mk.p;
+  }
+  flip_accumulate_kernel<<<ew_grid(y.numel), 256, 0, (cudaStream_t)stream>>>(
+      (const float*)y.p, (float*)acc.p, mp, (int)y.shape[0], (int)y.shape[1], (int)y.shape[2], (int)y.shape[3], flip,
+      scale, first);
+  B3D_LAUNCH_CHECK("flip_accumulate");
   return B3D_OK;
 }

@@ -170,6 +170,26 @@ def measure_conv_roofline(b3d, torch, dev, steps=20):
     return ms, flops
 
 
+def measure_inference(b3d, torch, dev, model, reps=3):
+    """BASELINE config 4 (single GPU): one `inference=True` forward (reference test.py:133) of a 155x190x147
+    volume padded to 160x192x160; Mvoxel/s counts ORIGINAL voxels.  VAE branch skipped."""
+    shape = (160, 192, 160)
+    x = torch.randn((1,) + shape + (2,), device=dev)
+    x[:, 155:], x[:, :, 190:], x[:, :, :, 147:] = 0, 0, 0
+    times = []
+    with torch.no_grad():
+        for i in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = model(x, training=False, inference=True)[0]
+            e1.record(); e1.synchronize()
+            if i:
+                times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times)
+    return {"shape_padded": list(shape), "ms_per_forward": ms, "mvoxel_per_s": 155 * 190 * 147 / ms / 1e3,
+            "gflop_per_forward": 1006.8, "note": "eager (no CUDA graph), 1 GPU; 8-flip TTA = 8 such forwards"}
+
+
 def run_b3d(args):
     import torch
     import torch.distributed as dist
@@ -266,7 +286,7 @@ def run_b3d(args):
                          "(oracle/ref_model.py); TF 2.0-alpha not installable"}
     line = {"metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 forward / bf16 backward operands, fp32 accumulate and storage", "data": "synthetic",
             "config": {"workload": "train_128cube_b1_default_model", "crop": list(CROP), "per_gpu_batch": 1,
                        "global_batch": world, "in_ch": 2, "out_ch": 3, "base_filters": 16,
                        "parallelism": f"dp{world}", "l2_flush": "working set (4.6 GiB of activations per step) "
@@ -276,7 +296,8 @@ def run_b3d(args):
             "e2e": {"value": e2e_val, "unit": "crops/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": int(step.launches_per_step * args.steps),
-            "roofline": roof, "cpu_baseline": cpu}
+            "roofline": roof, "cpu_baseline": cpu,
+            "inference": measure_inference(b3d, torch, dev, model) if world == 1 else None}
     print(json.dumps(line), flush=True)
     finish()
 

@@ -143,6 +143,14 @@ int b3d_mul_scale(const DLTensor* a, const DLTensor* b, DLTensor* y, float scale
 int b3d_sigmoid_bwd(const DLTensor* dy, const DLTensor* y, DLTensor* dx, void* stream);
 int b3d_copy_channels(const DLTensor* src, DLTensor* dst, int accumulate, void* stream);
 
+/* ---- test-time augmentation (test.py:105-161): flip bits 1=D 2=H 4=W on one [D,H,W,C] volume ------------
+ * flip_normalize: out = (flip(x) - mean)/std (test.py:107,128; mean/std nullable).
+ * flip_accumulate: acc (+)= scale*flip(y), optionally multiplied by the brain mask (test.py:134,147-151). */
+int b3d_flip_normalize(const DLTensor* x, const DLTensor* mean, const DLTensor* std, DLTensor* out, int flip,
+                       void* stream);
+int b3d_flip_accumulate(const DLTensor* y, DLTensor* acc, const DLTensor* mask, int flip, float scale, int first,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -299,6 +299,25 @@ def pad_to_spatial_res(res: int, x):
     return out, list(shape)
 
 
+def tta_inference(p: Params, x, bmask, mean, std, depth=4, groups=8):
+    """test.py:105-161 with spatial_tta=True, channel_tta=0: normalise, 8 flip subsets (:96-101), inference
+    forward (:133), un-flip (:134), mean (:147-148), brain mask (:151).  x: [D,H,W,C], bmask: [D,H,W,1]."""
+    x = (x - mean) / std
+    x = x.unsqueeze(0)
+    axes = [1, 2, 3]
+    augment = [axes, []]
+    for a in axes:
+        pairs = [b for b in axes if b != a]
+        augment += [[a], pairs]
+    ys = []
+    for flip in augment:
+        aug = torch.flip(x, dims=flip) if flip else x
+        y = model_forward(p, aug, inference=True, depth=depth, groups=groups)[0]
+        ys.append(torch.flip(y, dims=flip) if flip else y)
+    y = torch.cat(ys, dim=0).mean(dim=0, keepdim=True)
+    return (y * bmask.unsqueeze(0))[0]
+
+
 # ----------------------------------------------------------------------------------
 # Deterministic synthetic weights / inputs (SURVEY §8(d))
 # ----------------------------------------------------------------------------------

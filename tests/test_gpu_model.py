@@ -170,3 +170,39 @@ def test_graphed_step_equals_eager(b3d, dev):
     # eps is drawn by torch inside the VAE, so losses differ slightly between the two runs; weights stay close
     assert abs(res[0][0] - res[1][0]) / res[0][0] < 5e-2
     assert rel(res[1][1], res[0][1]) < 1e-2
+
+
+def test_inference_tta_matches_oracle(b3d, dev):
+    """test.py:105-178: pad_to_spatial_res + 8-flip TTA + brain mask on an odd-sized volume (levels 40x48x40 ->
+    5x6x5: partial tensor-core tiles and GroupNorm chunks that are not voxel-aligned), default precision."""
+    crop = (128, 128, 128)                      # only sizes the (unused) VAE un-projection
+    p = R.init_params(R.param_shapes(crop=crop, with_vae=False))
+    g = torch.Generator().manual_seed(5)
+    vol = torch.randn(37, 45, 33, 2, generator=g, dtype=torch.float64) * 40 + 100
+    mask = (vol.max(dim=-1, keepdim=True).values > 80).double()
+    xr, orig = R.pad_to_spatial_res(8, vol)
+    mr, _ = R.pad_to_spatial_res(8, mask)
+    mean, std = torch.tensor([100.0, 98.0], dtype=torch.float64), torch.tensor([40.0, 42.0], dtype=torch.float64)
+    ref = R.tta_inference(p, xr, mr, mean, std)
+
+    model = b3d.Model()
+    f = lambda t: t.to(torch.float32).to(dev)
+    # build on the padded shape with the VAE skipped: inference never touches it
+    with torch.no_grad():
+        model.call(f(xr).unsqueeze(0), training=False, inference=True)
+    model.built = True
+    model.flatten_parameters()
+    nv = model.named_variables()
+    with torch.no_grad():
+        for k, t in nv.items():
+            t.copy_(p[k].to(torch.float32))
+    xp, mp, orig2 = b3d.pad_to_spatial_res(8, f(vol), f(mask))
+    assert tuple(xp.shape) == tuple(xr.shape) == (40, 48, 40, 2) and orig2 == [37, 45, 33]
+    tta = b3d.TestTimeAugmentor(mean.tolist(), std.tolist(), model, 'channels_last')
+    assert len(tta.augment_axes) == 8
+    y = tta(xp, mp)
+    assert rel(y, ref) < 2e-3, rel(y, ref)
+    inside = mr[..., 0].bool()
+    agree = (y.argmax(-1).cpu()[inside] == ref.argmax(-1)[inside]).float().mean()
+    assert float(agree) >= 0.999, float(agree)
+    assert float(y[~inside.to(dev)].abs().max()) == 0.0
