@@ -74,7 +74,7 @@ SIGNATURES = {
     "b3d_conv3d_fwd": "TTTTiiiTiTiTv",
     "b3d_conv3d_dgrad": "TTTiiiTv",
     "b3d_conv3d_wgrad": "TTTTiiTTv",
-    "b3d_conv3d_pack_weights": "TTiv",
+    "b3d_conv3d_pack_weights": "TTiiiv",
     "b3d_gn_stats": "TTiv",
     "b3d_gn_apply": "TTTTTifiv",
     "b3d_gn_bwd_reduce": "TTTTTTTTifiv",
@@ -107,9 +107,9 @@ for _name, _sig in SIGNATURES.items():
     fn = getattr(lib, _name)
     fn.argtypes = [_CT[c] for c in _sig]
     fn.restype = C.c_int
-lib.b3d_conv3d_tc_supported.argtypes = [_i] * 5
+lib.b3d_conv3d_tc_supported.argtypes = [_i] * 6
 lib.b3d_conv3d_tc_supported.restype = _i
-lib.b3d_conv3d_packed_elems.argtypes = [_i] * 3
+lib.b3d_conv3d_packed_elems.argtypes = [_i] * 4
 lib.b3d_conv3d_wgrad_tc_supported.argtypes = [_i] * 5
 lib.b3d_conv3d_wgrad_tc_supported.restype = _i
 lib.b3d_set_conv_precision.argtypes = [_i, _i]

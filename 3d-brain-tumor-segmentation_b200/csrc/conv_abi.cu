@@ -70,8 +70,7 @@ int run(const ConvGeom& g, const TView& x, const TView& w, const float* bias, co
     TView wp;
     B3D_TRY(view(wpacked_, DT_F32, 1, false, "wpacked", &wp));
     B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "conv: shape not supported by the tcgen05 path");
-    B3D_REQUIRE((size_t)wp.numel == tc_packed_weight_elems(g.k, g.Cin, g.Cout), B3D_ERR_SHAPE,
-                "wpacked: wrong size");
+    B3D_REQUIRE((size_t)wp.numel == tc_packed_weight_elems(g), B3D_ERR_SHAPE, "wpacked: wrong size");
     return launch_conv_tc(g, (const float*)x.p, (const float*)wp.p, bias, (float*)y.p, stats, gap, s);
   }
   return launch_conv_gather(g, (const float*)x.p, (const float*)w.p, bias, (float*)y.p, stats, gap, s);
@@ -114,12 +113,12 @@ int geom_dgrad(ConvGeom& g, const TView& dy, const TView& w, const TView& dx, in
   memset(&g, 0, sizeof(g));
   fill_in(g, dy);   // gathered tensor is dy: "Cin" of the gather = Cout of the layer
   fill_out(g, dx);
-  g.k = k; g.pad = k / 2;
+  g.k = k; g.pad = k / 2; g.bwd = 1;
   if (!transposed) {
     B3D_REQUIRE(w.shape[3] == g.Cout && w.shape[4] == g.Cin, B3D_ERR_SHAPE, "conv dgrad: kernel/channels mismatch");
     B3D_TRY(spatial_ok(dx, dy, stride, "conv dgrad"));
     g.mode = stride == 1 ? CONV_S1 : CONV_UP;
-    g.flip = stride == 1 ? 1 : 0;   // taps reversed; also marks the backward pass for the precision choice
+    g.flip = stride == 1 ? 1 : 0;   // taps reversed
     g.wtap = (long long)g.Cin * g.Cout; g.sw_in = 1; g.sw_out = g.Cin;  // w[t][ci_layer][co_layer]
   } else {
     B3D_REQUIRE(w.shape[3] == g.Cin && w.shape[4] == g.Cout, B3D_ERR_SHAPE, "conv-transpose dgrad: kernel mismatch");
@@ -187,11 +186,12 @@ extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTenso
   wg.bigp = big.pitch; wg.smallp = sml.pitch;
   bool bias_done = false;
   if (x_bf16_ != nullptr && dy_bf16_ != nullptr) {
-    // tensor-core path: bf16 copies (caller-allocated, same shapes, contiguous) are filled here
+    // tensor-core path: bf16 copies (caller-allocated, same element counts, contiguous) are filled here; for the
+    // stride-2 family the copy of the BIG tensor is written in space-to-depth order [B, D/2, H/2, W/2, 8*C]
     TView xb, yb;
     B3D_TRY(view(x_bf16_, DT_BF16, 5, false, "x_bf16", &xb));
     B3D_TRY(view(dy_bf16_, DT_BF16, 5, false, "dy_bf16", &yb));
-    B3D_REQUIRE(!transposed && xb.numel == x.numel && yb.numel == dy.numel, B3D_ERR_SHAPE, "wgrad: bf16 buffer shapes");
+    B3D_REQUIRE(xb.numel == x.numel && yb.numel == dy.numel, B3D_ERR_SHAPE, "wgrad: bf16 buffer shapes");
     B3D_REQUIRE(x.pitch == x.shape[4] && dy.pitch == dy.shape[4], B3D_ERR_LAYOUT, "wgrad (tcgen05): contiguous inputs");
     B3D_REQUIRE(tc_wgrad_supported(wg), B3D_ERR_UNSUPPORTED, "wgrad: shape not on the tcgen05 path");
     float* db = nullptr;
@@ -202,9 +202,16 @@ extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTenso
       db = (float*)dbv.p;
       bias_done = true;
     }
-    B3D_TRY(launch_cast_bf16((const float*)x.p, xb.p, x.numel / x.shape[4], (int)x.shape[4], nullptr, s));
-    B3D_TRY(launch_cast_bf16((const float*)dy.p, yb.p, dy.numel / dy.shape[4], (int)dy.shape[4], db, s));
-    B3D_TRY(launch_conv_wgrad_tc(wg, xb.p, yb.p, (float*)dw.p, s));
+    const TView& bigb = transposed ? yb : xb;
+    const TView& smlb = transposed ? xb : yb;
+    float* db_big = transposed ? db : nullptr;     // the bias gradient = column sums of dy, whichever role dy has
+    float* db_sml = transposed ? nullptr : db;
+    if (stride == 2)
+      B3D_TRY(launch_cast_bf16_s2d((const float*)big.p, bigb.p, wg.B, wg.Ds, wg.Hs, wg.Ws, wg.nA, big.pitch, db_big, s));
+    else
+      B3D_TRY(launch_cast_bf16((const float*)big.p, bigb.p, big.numel / big.shape[4], wg.nA, db_big, s));
+    B3D_TRY(launch_cast_bf16((const float*)sml.p, smlb.p, sml.numel / sml.shape[4], wg.nB, db_sml, s));
+    B3D_TRY(launch_conv_wgrad_tc(wg, bigb.p, smlb.p, (float*)dw.p, s));
   } else {
     B3D_TRY(launch_conv_wgrad(wg, (const float*)big.p, (const float*)sml.p, (float*)dw.p, s));
   }
@@ -218,42 +225,59 @@ extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTenso
   return B3D_OK;
 }
 
-// 1 when the tcgen05 weight-gradient kernel handles a 3x3x3 stride-1 conv of these channel counts
+// 1 when the tcgen05 weight-gradient kernel handles a layer with these LAYER channel counts (k in {1,3} stride 1;
+// k3 stride 2 conv / conv-transpose)
 extern "C" int b3d_conv3d_wgrad_tc_supported(int k, int stride, int transposed, int cin, int cout) {
+  if (transposed && stride != 2) return 0;
   WgradGeom wg;
   memset(&wg, 0, sizeof(wg));
-  wg.k = k; wg.s = stride; wg.nA = cin; wg.nB = cout; wg.bigp = cin; wg.smallp = cout;
-  return (!transposed && tc_wgrad_supported(wg)) ? 1 : 0;
+  wg.k = k; wg.s = stride;
+  wg.nA = transposed ? cout : cin; wg.nB = transposed ? cin : cout;
+  wg.bigp = wg.nA; wg.smallp = wg.nB;
+  return tc_wgrad_supported(wg) ? 1 : 0;
 }
 
-// 1 when the tcgen05 implicit-GEMM kernel handles a (gather-form) conv of these channel counts
-extern "C" int b3d_conv3d_tc_supported(int k, int stride, int transposed, int c_gathered, int c_produced) {
-  ConvGeom g;
+namespace {
+// channel roles / weight strides of the gather form for (stride, transposed, dgrad) and kernel dims (.., A, Bc)
+void weight_geom(ConvGeom& g, int k, int stride, int transposed, int dgrad, int A, int Bc) {
   memset(&g, 0, sizeof(g));
-  g.k = k; g.mode = (stride == 1 && !transposed) ? CONV_S1 : CONV_DOWN;
-  g.Cin = c_gathered; g.Cout = c_produced;
-  g.Wo = 8; g.Ho = 16; g.Do = 1; g.B = 1;
+  g.k = k; g.pad = k / 2; g.bwd = dgrad;
+  g.wtap = (long long)A * Bc;
+  // contracted channel = A for (conv fwd, convT dgrad), Bc for (conv dgrad, convT fwd)
+  const bool contract_a = (transposed != 0) == (dgrad != 0);
+  if (contract_a) { g.Cin = A; g.Cout = Bc; g.sw_in = Bc; g.sw_out = 1; }
+  else            { g.Cin = Bc; g.Cout = A; g.sw_in = 1; g.sw_out = Bc; }
+  if (stride == 1) { g.mode = CONV_S1; g.flip = dgrad; }
+  else g.mode = contract_a ? CONV_DOWN : CONV_UP;   // conv s2 fwd & convT dgrad gather DOWN; the other two UP
+}
+}  // namespace
+
+// 1 when the tcgen05 implicit-GEMM kernel handles this pass of a conv whose Keras kernel is (k,k,k,a,b)
+extern "C" int b3d_conv3d_tc_supported(int k, int stride, int transposed, int dgrad, int a, int b) {
+  if (!((stride == 1 && !transposed) || (stride == 2 && k == 3))) return 0;
+  ConvGeom g;
+  weight_geom(g, k, stride, transposed, dgrad, a, b);
   return tc_conv_supported(g) ? 1 : 0;
 }
 
-extern "C" long long b3d_conv3d_packed_elems(int k, int c_gathered, int c_produced) {
-  return (long long)tc_packed_weight_elems(k, c_gathered, c_produced);
+extern "C" long long b3d_conv3d_packed_elems(int k, int stride, int a, int b) {
+  ConvGeom g;
+  weight_geom(g, k, stride, 0, 0, a, b);
+  return (long long)tc_packed_weight_elems(g);
 }
 
-// Re-lays a Keras conv kernel out for the tcgen05 kernel.  dgrad=0: forward operand of Conv3D;
-// dgrad=1: data-gradient operand (taps flipped, channel roles swapped).
-extern "C" int b3d_conv3d_pack_weights(const DLTensor* w_, DLTensor* packed_, int dgrad, void* stream) {
+// Re-lays a Keras conv kernel out for the tcgen05 kernel, for the forward pass (dgrad=0) or the data gradient
+// (dgrad=1) of a Conv3D (transposed=0) / Conv3DTranspose (transposed=1, stride 2) layer.
+extern "C" int b3d_conv3d_pack_weights(const DLTensor* w_, DLTensor* packed_, int stride, int transposed, int dgrad,
+                                       void* stream) {
   TView w, p;
   int k;
   B3D_TRY(weight_view(w_, &w, &k));
   B3D_TRY(view(packed_, DT_F32, 1, false, "packed", &p));
+  B3D_REQUIRE((stride == 1 && !transposed) || (stride == 2 && k == 3), B3D_ERR_UNSUPPORTED,
+              "pack_weights: stride 1, or k=3 stride 2 (conv / conv-transpose)");
   ConvGeom g;
-  memset(&g, 0, sizeof(g));
-  g.k = k; g.mode = CONV_S1;
-  const int A = (int)w.shape[3], Bc = (int)w.shape[4];
-  g.wtap = (long long)A * Bc;
-  if (!dgrad) { g.Cin = A; g.Cout = Bc; g.sw_in = Bc; g.sw_out = 1; g.flip = 0; }
-  else        { g.Cin = Bc; g.Cout = A; g.sw_in = 1; g.sw_out = Bc; g.flip = 1; }
-  B3D_REQUIRE((size_t)p.numel == tc_packed_weight_elems(k, g.Cin, g.Cout), B3D_ERR_SHAPE, "packed: wrong size");
+  weight_geom(g, k, stride, transposed, dgrad, (int)w.shape[3], (int)w.shape[4]);
+  B3D_REQUIRE((size_t)p.numel == tc_packed_weight_elems(g), B3D_ERR_SHAPE, "packed: wrong size");
   return launch_tc_pack_weights(g, (const float*)w.p, (float*)p.p, (cudaStream_t)stream);
 }

@@ -16,6 +16,7 @@ struct ConvGeom {
   int sw_in, sw_out;        // strides of the contracted / produced channel in w
   int act, accumulate;      // 1 = sigmoid; y += result
   int groups;               // GN groups when stats are requested
+  int bwd;                  // 1 = backward pass (operand-precision choice of the tcgen05 path)
 };
 
 // outer-product form:  dw[t][a][b] = sum_{n,o} big[n, s*o+t-pad, a] * small[n, o, b]
@@ -35,11 +36,17 @@ int launch_colsum(const float* x, float* out, long long N, int C, long long pitc
 bool tc_conv_supported(const ConvGeom& cg);
 int launch_conv_tc(const ConvGeom& cg, const float* x, const float* wpacked, const float* bias, float* y,
                    double* stats, float* gap, cudaStream_t s);
-size_t tc_packed_weight_elems(int k, int Cin, int Cout);
+size_t tc_packed_weight_elems(const ConvGeom& cg);
+int launch_pack_s2(const ConvGeom& cg, const float* w, float* wpacked, bool bf16, cudaStream_t s);
 int launch_tc_pack_weights(const ConvGeom& cg, const float* w, float* wpacked, cudaStream_t s);
+
+bool tc_use_bf16(const ConvGeom& g);   // operand type the tcgen05 conv will use for this geometry/pass
+int tc_pick_n(int Cout);               // N tile of the tcgen05 conv for this output-channel count
 
 bool tc_wgrad_supported(const WgradGeom& wg);
 int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x_bf16, const void* dy_bf16, float* dw, cudaStream_t s);
 int launch_cast_bf16(const float* src, void* dst, long long nvox, int C, float* colsum, cudaStream_t s);
+int launch_cast_bf16_s2d(const float* src, void* dst, int B, int D, int H, int W, int C, long long pitch,
+                         float* colsum, cudaStream_t s);
 
 }  // namespace b3d

@@ -1,0 +1,81 @@
+// b3d — the stride-2 family (Conv3D k3 s2 'same' of reference layers/downsample.py:28-35, Conv3DTranspose k3 s2
+// 'same' of layers/upsample.py:28-33, and their gradients) reduced to STRIDE-1 2x2x2 convolutions so that it runs
+// on the tcgen05 kernel of conv_tc.cu:
+//
+//   DOWN-type  y[o] = sum_t x[2o+t] w[t]         (conv s2 forward; data gradient of the transposed conv)
+//       space-to-depth  x'[o][(p,c)] = x[2o+p][c],  p in {0,1}^3   =>   y[o] = sum_{d in {0,1}^3} x'[o+d] W'[d],
+//       W'[d][(p,c)][n] = w[t = 2d+p] (zero where a component of t exceeds 2): 8 taps over 8*C channels.
+//   UP-type    y[2o+p] = sum_{t = p (mod 2)} x[o - (t-p)/2] w[t]   (transposed conv forward; dgrad of conv s2)
+//       y'[o][(p,n)] = sum_{k in {0,1}^3} x[o+k-1] W'[k],  W'[k][c][(p,n)] = w[t = p + 2(1-k)] (zero if > 2),
+//       then depth-to-space  y[2o+p][n] = y'[o][(p,n)] (+bias, + GroupNorm chunk statistics of y).
+//
+// 27 of the 64 (tap, parity) weight blocks are non-zero, i.e. 2.4x padded MMA work — but N (or K) grows 8x, which is
+// exactly what the A-operand-read-bound small-channel layers need, and TF 'SAME' one-sided padding falls
+// out of the zero fill at the volume edge.  Space-to-depth / depth-to-space are pure ADDRESSING: conv_tc.cu's loader
+// reads x[2o+p] for the channel chunk of parity p, its epilogue stores column block (p, n) at y[2o+p][n].  This file
+// holds the weight re-layout for the forward / data-gradient operand; the weight gradient of the family is the
+// KS = 2 case of conv_tc_wgrad.cu.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace b3d {
+
+// packed weights of the 2x2x2 stride-1 conv, in the layout of conv_tc.cu:
+//   wp[ns][chunk][tap8][plane][n][j]   (T = 8 bf16 | 4 tf32 channels per cell, CK = 2T per chunk)
+// DOWN: K' = 8*Cg with k' = p*Cg + cg, N = Cp,   tap d (offsets 0,+1):  w[t = 2d+p]
+// UP  : K  = Cg,  N' = 8*Cp with n' = p*Cp + cp, tap k (offsets -1,0):  w[t = p + 2(1-k)]
+template <bool BF16>
+__global__ void pack_s2_kernel(const float* __restrict__ w, void* __restrict__ wp, int up, int Cg, int Cp, int N,
+                               long long wtap, int sw_in, int sw_out) {
+  constexpr int T = BF16 ? 8 : 4;
+  const int K = up ? Cg : 8 * Cg, NT = up ? 8 * Cp : Cp;
+  const long long total = 8LL * K * NT;
+  const int nch = K / (2 * T);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int j = (int)(r % T); r /= T;
+    const int n = (int)(r % N); r /= N;
+    const int pl = (int)(r % 2); r /= 2;
+    const int tap = (int)(r % 8); r /= 8;
+    const int c = (int)(r % nch); r /= nch;
+    const int ns = (int)r;
+    const int k = 2 * T * c + T * pl + j, nn = ns * N + n;
+    int p, cg, cp;
+    if (up) { cg = k; p = nn / Cp; cp = nn % Cp; }
+    else    { p = k / Cg; cg = k % Cg; cp = nn; }
+    const int kd = tap >> 2, kh = (tap >> 1) & 1, kw = tap & 1;
+    const int pd = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
+    const int td = up ? pd + 2 * (1 - kd) : 2 * kd + pd;
+    const int th = up ? ph + 2 * (1 - kh) : 2 * kh + ph;
+    const int tw = up ? pw + 2 * (1 - kw) : 2 * kw + pw;
+    float v = 0.f;
+    if (td <= 2 && th <= 2 && tw <= 2)
+      v = w[(long long)((td * 3 + th) * 3 + tw) * wtap + (long long)cg * sw_in + (long long)cp * sw_out];
+    if (BF16) {
+      reinterpret_cast<__nv_bfloat16*>(wp)[i] = __float2bfloat16_rn(v);
+    } else {
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+      reinterpret_cast<float*>(wp)[i] = __uint_as_float(u);
+    }
+  }
+}
+
+// packed weights of the equivalent 2x2x2 conv for a DOWN / UP geometry (64 * Cin * Cout elements)
+int launch_pack_s2(const ConvGeom& g, const float* w, float* wp, bool bf16, cudaStream_t s) {
+  const int up = g.mode == CONV_UP ? 1 : 0;
+  const int K = up ? g.Cin : 8 * g.Cin, NT = up ? 8 * g.Cout : g.Cout;
+  const long long total = 8LL * K * NT;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  if (bf16)
+    pack_s2_kernel<true><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out);
+  else
+    pack_s2_kernel<false><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out);
+  B3D_LAUNCH_CHECK("pack_s2");
+  return B3D_OK;
+}
+
+}  // namespace b3d

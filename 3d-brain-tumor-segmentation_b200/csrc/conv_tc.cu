@@ -29,16 +29,16 @@
 namespace b3d {
 
 // ------------------------------------------------------------------------------------------ config
-template <int N_, int TD_, int NW_, int KS_, bool BF16_>
+template <int N_, int TD_, int NW_, int KS_, int HB_, bool BF16_>
 struct TcCfg {
   static constexpr int N = N_, TD = TD_, NW = NW_, KS = KS_;
+  static constexpr int HB = HB_;                      // halo before the tile: tap k reads offset k - HB
   static constexpr bool BF16 = BF16_;
   static constexpr int T = BF16 ? 8 : 4;              // channels per 16-byte cell
   static constexpr int CK = 2 * T;                    // channels per chunk = one MMA K step
   static constexpr int TAPS = KS * KS * KS;
-  static constexpr int HALO = KS / 2;
   static constexpr int TH = 16, TW = 8 * NW, P = TD * NW;
-  static constexpr int HD = TD + 2 * HALO, HH = TH + 2 * HALO, HW = TW + 2 * HALO;
+  static constexpr int HD = TD + KS - 1, HH = TH + KS - 1, HW = TW + KS - 1;
   static constexpr int NVC = HD * HH * HW;            // cells per plane
   static constexpr int PLANE_BYTES = ((NVC * 16 + 127) / 128) * 128;
   static constexpr int HALO_BYTES = 2 * PLANE_BYTES;
@@ -65,7 +65,11 @@ struct TcParams {
   long long xp, yp;    // channel pitches
   int ntd, nth, ntw, ntiles;
   int accumulate, groups;
-  long long vpc;       // voxels per GN chunk
+  long long vpc;       // voxels per GN chunk (of the tensor y is stored as)
+  // stride-2 family (conv_s2.cu): the kernel works on the COARSE grid [D,H,W];
+  //   s2d: x is the fine tensor [B,2D,2H,2W,Csub]; virtual input channel k' = parity*Csub + c  (space-to-depth)
+  //   d2s: y is the fine tensor [B,2D,2H,2W,Csub]; virtual output column n' = parity*Csub + c (depth-to-space)
+  int s2d, d2s, Csub;
 };
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -140,13 +144,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
       const int ht = t % prm.nth; t /= prm.nth;
       const int dt = t % prm.ntd; t /= prm.ntd;
       const int b = t;
-      const int w0 = wt * C::TW - C::HALO, h0 = ht * C::TH - C::HALO, d0 = dt * C::TD - C::HALO;
-      const float* xb = prm.x + (long long)b * prm.D * prm.H * prm.W * prm.xp;
+      const int w0 = wt * C::TW - C::HB, h0 = ht * C::TH - C::HB, d0 = dt * C::TD - C::HB;
+      const float* xb = prm.x + (long long)b * prm.D * prm.H * prm.W * prm.xp * (prm.s2d ? 8 : 1);
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
         uint8_t* dst0 = halo + hs * C::HALO_BYTES;
         uint8_t* dst1 = dst0 + C::PLANE_BYTES;
         const float* xc = xb + c * C::CK;
+        int sp_d = 0, sp_h = 0, sp_w = 0;      // s2d: parity of this chunk's channels
+        if (prm.s2d) {
+          const int par = (c * C::CK) / prm.Csub;
+          xc = xb + (c * C::CK) % prm.Csub;
+          sp_d = par >> 2; sp_h = (par >> 1) & 1; sp_w = par & 1;
+        }
         // one lane = one halo voxel: the whole CK-channel chunk is fetched with 256-bit loads (full 32-byte
         // sectors), converted, and written as one 16-byte cell per plane (a warp stores 512 contiguous bytes)
         constexpr int kVoxPerPass = kLoaderWarps * 32;
@@ -164,7 +174,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
             for (int i = 0; i < kRegs; ++i) r[u][i] = 0.f;
             if (ok) {
-              const float* src = xc + (((long long)gd * prm.H + gh) * prm.W + gw) * prm.xp;
+              const float* src =
+                  prm.s2d ? xc + (((long long)(2 * gd + sp_d) * (2 * prm.H) + (2 * gh + sp_h)) * (2 * prm.W) +
+                                  (2 * gw + sp_w)) * prm.xp
+                          : xc + (((long long)gd * prm.H + gh) * prm.W + gw) * prm.xp;
               ld256(src, r[u]);
               if (C::BF16) ld256(src + 8, r[u] + 8);
             }
@@ -268,7 +281,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
     const int q = warp;                     // TMEM lane quarter == warp % 4
     const int row = q * 32 + lane;          // patch row: h = row/8, w = row%8
     const int ph = row >> 3, pwv = row & 7;
-    const long long S = (long long)prm.D * prm.H * prm.W;
+    const long long S = (long long)prm.D * prm.H * prm.W * (prm.d2s ? 8 : 1);   // voxels of y per sample
     // global-average-pool partial sums: kept in registers across the tiles of one sample when N <= 64
     constexpr bool kGapPersist = C::N <= 64;
     constexpr int NJ = C::N / 16;
@@ -304,17 +317,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
+        // output column block -> (parity, channel offset) when the result is stored depth-to-space
+        int ycol = nsp * C::N + j * 16, ep_d = 0, ep_h = 0, ep_w = 0;
+        if (prm.d2s) {
+          const int par = ycol / prm.Csub;
+          ycol -= par * prm.Csub;
+          ep_d = par >> 2; ep_h = (par >> 1) & 1; ep_w = par & 1;
+        }
         float bv[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) bv[i] = prm.bias != nullptr ? __ldg(prm.bias + nsp * C::N + j * 16 + i) : 0.f;
+        for (int i = 0; i < 16; ++i) bv[i] = prm.bias != nullptr ? __ldg(prm.bias + ycol + i) : 0.f;
         float (&gs)[16] = gsum[kGapPersist ? j : 0];
 #pragma unroll 1
         for (int p = 0; p < C::P; ++p) {
           const int pd = p / C::NW, pw = p % C::NW;
           const int d = dt * C::TD + pd, h = ht * C::TH + ph, w = wt * C::TW + pw * 8 + pwv;
           const bool valid = d < prm.D && h < prm.H && w < prm.W;
-          const long long vox = ((long long)d * prm.H + h) * prm.W + w;
-          float* yp = prm.y + ((long long)b * S + vox) * prm.yp + (long long)nsp * C::N + j * 16;
+          const long long vox =
+              prm.d2s ? ((long long)(2 * d + ep_d) * (2 * prm.H) + (2 * h + ep_h)) * (2 * prm.W) + (2 * w + ep_w)
+                      : ((long long)d * prm.H + h) * prm.W + w;
+          float* yp = prm.y + ((long long)b * S + vox) * prm.yp + ycol;
           if (prm.stats != nullptr && valid) {
             const int chunk = b * prm.groups + (int)(vox / prm.vpc);
             if (chunk != cur_chunk) {
@@ -440,17 +462,41 @@ static int pick_n(int Cout) {
   return 16;
 }
 
-static bool use_bf16(const ConvGeom& g) { return (g.flip ? g_bwd_bf16 : g_fwd_bf16) && g.Cin % 16 == 0; }
-
-bool tc_conv_supported(const ConvGeom& g) {
-  return (g.k == 3 || g.k == 1) && g.mode == CONV_S1 && g.Cin % 8 == 0 && g.Cout % 16 == 0 && g.Cin >= 8 &&
-         g.Cout >= 16;
+// virtual (stride-1) problem of a conv geometry: S1 as is; DOWN / UP = 2x2x2 conv on the coarse grid (conv_s2.cu)
+struct TcProblem {
+  int ks, hb, Cin, Cout, D, H, W, s2d, d2s, Csub;
+};
+static TcProblem tc_problem(const ConvGeom& g) {
+  TcProblem q;
+  memset(&q, 0, sizeof(q));
+  if (g.mode == CONV_S1) {
+    q.ks = g.k; q.hb = g.k == 2 ? g.pad : g.k / 2; q.Cin = g.Cin; q.Cout = g.Cout; q.D = g.Do; q.H = g.Ho; q.W = g.Wo;
+  } else if (g.mode == CONV_DOWN) {
+    q.ks = 2; q.hb = 0; q.Cin = 8 * g.Cin; q.Cout = g.Cout; q.D = g.Do; q.H = g.Ho; q.W = g.Wo;
+    q.s2d = 1; q.Csub = g.Cin;
+  } else {
+    q.ks = 2; q.hb = 1; q.Cin = g.Cin; q.Cout = 8 * g.Cout; q.D = g.Di; q.H = g.Hi; q.W = g.Wi;
+    q.d2s = 1; q.Csub = g.Cout;
+  }
+  return q;
 }
 
-size_t tc_packed_weight_elems(int k, int Cin, int Cout) { return (size_t)k * k * k * Cin * Cout; }
+// g.bwd marks the backward pass (precision choice); chunks of CK channels must not straddle a parity block
+static bool use_bf16(const ConvGeom& g) { return (g.bwd ? g_bwd_bf16 : g_fwd_bf16) && g.Cin % 16 == 0; }
+
+bool tc_conv_supported(const ConvGeom& g) {
+  if (g.mode == CONV_S1)
+    return (g.k == 3 || g.k == 1) && g.Cin % 8 == 0 && g.Cout % 16 == 0 && g.Cin >= 8 && g.Cout >= 16;
+  return g.k == 3 && g.Cin % 8 == 0 && g.Cin >= 8 && g.Cout % 16 == 0 && g.Cout >= 16;
+}
+
+size_t tc_packed_weight_elems(const ConvGeom& g) {
+  return (size_t)(g.mode == CONV_S1 ? g.k * g.k * g.k : 64) * g.Cin * g.Cout;
+}
 
 int launch_tc_pack_weights(const ConvGeom& g, const float* w, float* wp, cudaStream_t s) {
   B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "pack_weights: shape not on the tcgen05 path");
+  if (g.mode != CONV_S1) return launch_pack_s2(g, w, wp, use_bf16(g), s);
   const int taps = g.k * g.k * g.k;
   const long long total = (long long)taps * g.Cin * g.Cout;
   const unsigned grid = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
@@ -465,22 +511,24 @@ int launch_tc_pack_weights(const ConvGeom& g, const float* w, float* wp, cudaStr
 }
 
 template <class C>
-static int launch_cfg(const ConvGeom& g, const float* x, const float* wp, const float* bias, float* y,
-                      double* stats, float* gap, cudaStream_t s) {
+static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, const float* wp, const float* bias,
+                      float* y, double* stats, float* gap, cudaStream_t s) {
   TcParams p;
+  memset(&p, 0, sizeof(p));
   p.x = x; p.wp = wp; p.bias = bias; p.y = y; p.stats = stats; p.gap = gap;
-  p.B = g.B; p.D = g.Do; p.H = g.Ho; p.W = g.Wo; p.Cin = g.Cin; p.Cout = g.Cout; p.xp = g.xp; p.yp = g.yp;
-  p.ntd = (g.Do + C::TD - 1) / C::TD; p.nth = (g.Ho + C::TH - 1) / C::TH; p.ntw = (g.Wo + C::TW - 1) / C::TW;
+  p.B = g.B; p.D = q.D; p.H = q.H; p.W = q.W; p.Cin = q.Cin; p.Cout = q.Cout; p.xp = g.xp; p.yp = g.yp;
+  p.ntd = (q.D + C::TD - 1) / C::TD; p.nth = (q.H + C::TH - 1) / C::TH; p.ntw = (q.W + C::TW - 1) / C::TW;
   p.ntiles = g.B * p.ntd * p.nth * p.ntw;
   p.accumulate = g.accumulate; p.groups = g.groups > 0 ? g.groups : 1;
   p.vpc = ((long long)g.Do * g.Ho * g.Wo) / p.groups;
+  p.s2d = q.s2d; p.d2s = q.d2s; p.Csub = q.Csub;
   static bool attr_set = false;
   if (!attr_set) {
     B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),
                     "cudaFuncSetAttribute(conv_tc)"));
     attr_set = true;
   }
-  const int nsplit = g.Cout / C::N;
+  const int nsplit = q.Cout / C::N;
   dim3 grid((unsigned)(p.ntiles < sm_count() ? p.ntiles : sm_count()), (unsigned)nsplit, 1);
   if (nsplit > 1) grid.x = (grid.x + nsplit - 1) / nsplit;   // keep ~one persistent CTA per SM in total
   conv_tc_kernel<C><<<grid, kTcThreads, C::SMEM, s>>>(p);
@@ -488,17 +536,22 @@ static int launch_cfg(const ConvGeom& g, const float* x, const float* wp, const 
   return B3D_OK;
 }
 
-template <int KS, bool BF16>
-static int dispatch_n(const ConvGeom& g, const float* x, const float* wp, const float* bias, float* y,
-                      double* stats, float* gap, cudaStream_t s) {
-  switch (pick_n(g.Cout)) {
-    case 128: return launch_cfg<TcCfg<128, 2, 1, KS, BF16>>(g, x, wp, bias, y, stats, gap, s);
-    case 64: return launch_cfg<TcCfg<64, 2, 2, KS, BF16>>(g, x, wp, bias, y, stats, gap, s);
-    case 32: return launch_cfg<TcCfg<32, 4, 2, KS, BF16>>(g, x, wp, bias, y, stats, gap, s);
-    default: return launch_cfg<TcCfg<16, 4, 2, KS, BF16>>(g, x, wp, bias, y, stats, gap, s);
+template <int KS, int HB, bool BF16>
+static int dispatch_n(const ConvGeom& g, const TcProblem& q, const float* x, const float* wp, const float* bias,
+                      float* y, double* stats, float* gap, cudaStream_t s) {
+  const int n = pick_n(q.Cout);
+  if (n == 128) return launch_cfg<TcCfg<128, 2, 1, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s);
+  if constexpr (!(KS == 2 && HB == 1)) {   // the depth-to-space form always has N = 8*Cp = multiple of 128
+    if (n == 64) return launch_cfg<TcCfg<64, 2, 2, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s);
+    if (n == 32) return launch_cfg<TcCfg<32, 4, 2, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s);
+    return launch_cfg<TcCfg<16, 4, 2, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s);
   }
+  set_error("tcgen05 conv: unexpected N tile");
+  return B3D_ERR_UNSUPPORTED;
 }
 
+// conv on the tensor cores with pre-packed weights: stride-1 k in {1,3}; stride-2 family (mode DOWN / UP) as a
+// 2x2x2 stride-1 conv over the coarse grid with space-to-depth input / depth-to-space output addressing
 int launch_conv_tc(const ConvGeom& g, const float* x, const float* wp, const float* bias, float* y, double* stats,
                    float* gap, cudaStream_t s) {
   B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "conv: shape not supported by the tcgen05 path");
@@ -506,13 +559,21 @@ int launch_conv_tc(const ConvGeom& g, const float* x, const float* wp, const flo
   B3D_REQUIRE(g.xp % 8 == 0 && g.yp % 4 == 0 && ((uintptr_t)x & 31) == 0 &&
                   (((uintptr_t)y | (uintptr_t)wp) & 15) == 0,
               B3D_ERR_LAYOUT, "tcgen05 conv: x must be 32-byte aligned with a channel pitch multiple of 8");
+  const TcProblem q = tc_problem(g);
+  B3D_REQUIRE(gap == nullptr || g.mode == CONV_S1, B3D_ERR_UNSUPPORTED, "tcgen05 conv: GAP only for stride 1");
   const bool bf = use_bf16(g);
-  if (g.k == 3)
-    return bf ? dispatch_n<3, true>(g, x, wp, bias, y, stats, gap, s)
-              : dispatch_n<3, false>(g, x, wp, bias, y, stats, gap, s);
-  return bf ? dispatch_n<1, true>(g, x, wp, bias, y, stats, gap, s)
-            : dispatch_n<1, false>(g, x, wp, bias, y, stats, gap, s);
+#define B3D_TC_DISPATCH(KS, HB) \
+  return bf ? dispatch_n<KS, HB, true>(g, q, x, wp, bias, y, stats, gap, s) \
+            : dispatch_n<KS, HB, false>(g, q, x, wp, bias, y, stats, gap, s)
+  if (q.ks == 3) { B3D_TC_DISPATCH(3, 1); }
+  if (q.ks == 1) { B3D_TC_DISPATCH(1, 0); }
+  if (q.hb == 1) { B3D_TC_DISPATCH(2, 1); }
+  B3D_TC_DISPATCH(2, 0);
+#undef B3D_TC_DISPATCH
 }
+
+bool tc_use_bf16(const ConvGeom& g) { return use_bf16(g); }
+int tc_pick_n(int Cout) { return pick_n(Cout); }
 
 }  // namespace b3d
 

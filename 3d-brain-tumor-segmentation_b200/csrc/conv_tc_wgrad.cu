@@ -15,6 +15,10 @@
 //     split into groups (27 / 9 / 3 / 1 taps) and input channels into tiles of 128 across CTAs; the
 //     voxel tiles of one (channel tile, tap group) are spread over `nsplit` persistent CTAs and the
 //     partial results are reduced into dw with fp32 atomics at the end (dw pre-zeroed).
+//   * the same kernel runs the 1x1x1 weight gradient (KS = 1: one tap, no halo) and the stride-2 family (KS = 2):
+//     Conv3D k3 s2 / Conv3DTranspose are 2x2x2 stride-1 convs of the space-to-depth "big" tensor (conv_s2.cu), whose
+//     bf16 copy is written directly in [B, D/2, H/2, W/2, 8*C] order by cast_bf16_s2d_kernel; the epilogue scatters
+//     the (coarse tap, parity) blocks back to the 27 taps of dw.  Wide `small` tensors are cut into N tiles.
 //   * when fewer than 128 input channels remain, the missing MN groups address shared memory past the
 //     real planes (still inside this CTA's allocation, enforced by the host planner); the
 //     corresponding accumulator rows are never read.
@@ -38,7 +42,11 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
 
 struct WgParams {
   float* dw;
-  int Cin, Cout;
+  int Cin, Cout;                   // rows (virtual big channels) and columns (small channels) of one tap of dw
+  int NT, nnt;                     // N tile (columns per CTA) and number of N tiles
+  int pad;                         // halo before (1 for k=3, 0 for k in {1,2})
+  int s2_nA;                       // > 0: stride-2 family, Cin = 8*s2_nA rows ordered (parity, channel)
+  int px_bytes;                    // bytes the TMA writes per x plane (px is the 128-byte padded pitch)
   int TD, TH, TW, HD, HH, HW;      // tile and x-halo extents (voxels)
   int px, py;                      // plane bytes of x halo / dy tile
   int stage_bytes, nstages, xplanes_max;
@@ -48,7 +56,7 @@ struct WgParams {
 
 constexpr int kWgSmem = 227 * 1024;
 
-template <int TG>
+template <int KS, int TG>
 __global__ void __launch_bounds__(256, 1)
     conv3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
                           const WgParams prm) {
@@ -61,10 +69,13 @@ __global__ void __launch_bounds__(256, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int TAPS = KS * KS * KS;
+  constexpr bool allD = TG == TAPS, allH = TG >= KS * KS, allW = TG >= KS;   // dims a tap group spans
   const int tg = blockIdx.y;                 // tap group
-  const int cbase = blockIdx.z * 128;        // input-channel tile
+  const int cbase = (blockIdx.z / prm.nnt) * 128;   // input-channel tile
+  const int nb0 = (blockIdx.z % prm.nnt) * prm.NT;  // output-channel tile
   const int crem = min(128, prm.Cin - cbase);
-  const int xplanes = crem / 8, yplanes = prm.Cout / 8;
+  const int xplanes = crem / 8, yplanes = prm.NT / 8;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < prm.nstages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
@@ -83,17 +94,15 @@ __global__ void __launch_bounds__(256, 1)
 
   // first tap of this group and the halo origin shift it implies
   int gkd = 0, gkh = 0, gkw = 0;
-  if (TG == 9) gkd = tg;
-  if (TG == 3) { gkd = tg / 3; gkh = tg % 3; }
-  if (TG == 1) { gkd = tg / 9; gkh = (tg / 3) % 3; gkw = tg % 3; }
-  const int od = (TG == 27) ? -1 : gkd - 1;
-  const int oh = (TG >= 9) ? -1 : gkh - 1;
-  const int ow = (TG >= 3) ? -1 : gkw - 1;
+  if (!allD && allH) gkd = tg;
+  if (!allH && allW) { gkd = tg / KS; gkh = tg % KS; }
+  if (!allW) { gkd = tg / (KS * KS); gkh = (tg / KS) % KS; gkw = tg % KS; }
+  const int od = gkd - prm.pad, oh = gkh - prm.pad, ow = gkw - prm.pad;
 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0, ph = 0;
-      const uint32_t bytes = (uint32_t)(xplanes * prm.px + yplanes * prm.py);
+      const uint32_t bytes = (uint32_t)(xplanes * prm.px_bytes + yplanes * prm.py);
       for (int tile = blockIdx.x; tile < prm.ntiles; tile += prm.nsplit) {
         int t = tile;
         const int wt = t % prm.ntw; t /= prm.ntw;
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(256, 1)
         const uint32_t ydst = xdst + (uint32_t)(prm.xplanes_max * prm.px);
         for (int p = 0; p < xplanes; ++p)
           tma_load_5d(xdst + p * prm.px, &tmx, cbase + 8 * p, w0 + ow, h0 + oh, d0 + od, b, fb);
-        for (int q = 0; q < yplanes; ++q) tma_load_5d(ydst + q * prm.py, &tmy, 8 * q, w0, h0, d0, b, fb);
+        for (int q = 0; q < yplanes; ++q) tma_load_5d(ydst + q * prm.py, &tmy, nb0 + 8 * q, w0, h0, d0, b, fb);
         if (++s == prm.nstages) { s = 0; ph ^= 1; }
       }
     }
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(256, 1)
     const bool leader = elect_one();
     // D=f32, A=B=bf16, both MN-major, N=Cout, M=128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(prm.Cout >> 3) << 17) | ((128u >> 4) << 24);
+                           ((uint32_t)(prm.NT >> 3) << 17) | ((128u >> 4) << 24);
     int s = 0, ph = 0;
     uint32_t acc = 0;
     const int rowc = prm.HW, planec = prm.HH * prm.HW;
@@ -140,11 +149,11 @@ __global__ void __launch_bounds__(256, 1)
             if (leader) {
 #pragma unroll
               for (int t = 0; t < TG; ++t) {
-                const int tkd = (TG == 27) ? t / 9 : 0;
-                const int tkh = (TG >= 9) ? (t / 3) % 3 : 0;
-                const int tkw = (TG >= 3) ? t % 3 : 0;
+                const int tkd = allD ? t / (KS * KS) : 0;
+                const int tkh = allH ? (t / KS) % KS : 0;
+                const int tkw = allW ? t % KS : 0;
                 const uint32_t off = xcell + (uint32_t)(tkd * planec + tkh * rowc + tkw);
-                tc_mma_bf16(tmem_base + t * prm.Cout, adesc0 + off, bdesc, idesc, acc);
+                tc_mma_bf16(tmem_base + t * prm.NT, adesc0 + off, bdesc, idesc, acc);
               }
             }
             acc = 1;
@@ -162,14 +171,24 @@ __global__ void __launch_bounds__(256, 1)
     mbar_wait(smem_u32(done), 0);
     tc_fence_after();
     const bool has_tiles = blockIdx.x < prm.ntiles;
+    // stride-2 family: row ci = (parity, channel); coarse tap d and parity p give the fine tap 2d + p (<= 2)
+    int row = ci, rows = prm.Cin, par = 0;
+    if (prm.s2_nA > 0) { par = ci / prm.s2_nA; row = ci - par * prm.s2_nA; rows = prm.s2_nA; }
 #pragma unroll 1
     for (int t = 0; t < TG; ++t) {
-      const int tap = (TG == 27) ? t : (TG == 9 ? tg * 9 + t : (TG == 3 ? tg * 3 + t : tg));
-      float* dst = prm.dw + ((size_t)tap * prm.Cin + ci) * prm.Cout;
-      for (int j = 0; j < prm.Cout; j += 16) {
+      int tap = allD ? t : (TG == KS * KS ? tg * TG + t : (TG == KS ? tg * KS + t : tg));
+      bool live = has_tiles && ci < prm.Cin;
+      if (prm.s2_nA > 0) {
+        const int td = 2 * (tap >> 2) + (par >> 2), th = 2 * ((tap >> 1) & 1) + ((par >> 1) & 1),
+                  tw = 2 * (tap & 1) + (par & 1);
+        live = live && td <= 2 && th <= 2 && tw <= 2;
+        tap = (td * 3 + th) * 3 + tw;
+      }
+      float* dst = prm.dw + ((size_t)tap * rows + row) * prm.Cout + nb0;
+      for (int j = 0; j < prm.NT; j += 16) {
         float v[16];
-        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + t * prm.Cout + j, v);
-        if (has_tiles && ci < prm.Cin) {
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + t * prm.NT + j, v);
+        if (live) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) atomicAdd(dst + j + i, v[i]);
         }
@@ -184,9 +203,19 @@ __global__ void __launch_bounds__(256, 1)
   }
 }
 
+// N tile (columns of dw per CTA): all taps of a group must fit the 512 TMEM columns
+static int wgrad_ntile(int k, int nB) {
+  const int cap = k == 2 ? 64 : 256;     // k=2: the 8 coarse taps stay resident (8 * 64 = 512 columns)
+  if (nB <= cap) return nB;
+  for (int nt = cap; nt >= 16; nt >>= 1)
+    if (nB % nt == 0) return nt;
+  return 0;
+}
+
 bool tc_wgrad_supported(const WgradGeom& wg) {
-  return wg.k == 3 && wg.s == 1 && wg.nA % 8 == 0 && wg.nA >= 8 && wg.nB % 16 == 0 && wg.nB >= 16 &&
-         wg.nB <= 256 && wg.bigp % 8 == 0 && wg.smallp % 8 == 0;
+  const bool kind = (wg.s == 1 && (wg.k == 3 || wg.k == 1)) || (wg.s == 2 && wg.k == 3);
+  return kind && wg.nA % 8 == 0 && wg.nA >= 8 && wg.nB % 16 == 0 && wg.nB >= 16 &&
+         wgrad_ntile(wg.s == 2 ? 2 : wg.k, wg.nB) > 0 && wg.bigp % 8 == 0 && wg.smallp % 8 == 0;
 }
 
 static int make_map(CUtensorMap* tm, const void* base, int C, long long pitch, int W, int H, int D, int B,
@@ -205,12 +234,19 @@ static int make_map(CUtensorMap* tm, const void* base, int C, long long pitch, i
   return B3D_OK;
 }
 
+// x: bf16 copy of the big tensor — for stride 2 already in space-to-depth order [B, Ds, Hs, Ws, 8*nA]
 int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, float* dw, cudaStream_t s) {
   B3D_REQUIRE(tc_wgrad_supported(wg), B3D_ERR_UNSUPPORTED, "wgrad: shape not on the tcgen05 path");
   B3D_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, B3D_ERR_LAYOUT, "wgrad: alignment");
-  const int Cin = wg.nA, Cout = wg.nB;
-  const int TG = 27 * Cout <= 512 ? 27 : (9 * Cout <= 512 ? 9 : (3 * Cout <= 512 ? 3 : 1));
-  const int ntg = 27 / TG;
+  const bool s2 = wg.s == 2;
+  const int KS = s2 ? 2 : wg.k, TAPS = KS * KS * KS;
+  const int Cin = s2 ? 8 * wg.nA : wg.nA, Cout = wg.nB;
+  const int NT = wgrad_ntile(KS, Cout), nnt = Cout / NT;
+  int TG;
+  if (KS == 3) TG = 27 * NT <= 512 ? 27 : (9 * NT <= 512 ? 9 : (3 * NT <= 512 ? 3 : 1));
+  else TG = TAPS;
+  const int ntg = TAPS / TG;
+  const bool allD = TG == TAPS, allH = TG >= KS * KS, allW = TG >= KS;
   const int nmt = (Cin + 127) / 128;
   const int xpl = (Cin < 128 ? Cin : 128) / 8;
   // tile planner: largest tile whose stages fit, with 16 MN groups (M=128 bf16) readable from every stage start
@@ -223,16 +259,15 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
   for (int i = 0; i < (int)(sizeof(cand) / sizeof(cand[0])); ++i) {
     const int TD = cand[i][0], TH = cand[i][1], TW = cand[i][2];
     if (found && (TD > wg.Ds * 2 || TH > wg.Hs * 2 || TW > wg.Ws * 2)) continue;   // do not over-tile tiny volumes
-    const int HD = TD + (TG == 27 ? 2 : 0), HH = TH + (TG >= 9 ? 2 : 0), HW = TW + (TG >= 3 ? 2 : 0);
+    const int HD = TD + (allD ? KS - 1 : 0), HH = TH + (allH ? KS - 1 : 0), HW = TW + (allW ? KS - 1 : 0);
     const int cells = HD * HH * HW;
-    if (cells % 8 != 0) continue;
-    const int px = cells * 16, py = TD * TH * TW * 16;
-    const long long stage = (long long)xpl * px + (long long)(Cout / 8) * py;
+    const int px = ((cells * 16 + 127) / 128) * 128, py = TD * TH * TW * 16;
+    const long long stage = (((long long)xpl * px + (long long)(NT / 8) * py + 127) / 128) * 128;
     for (int ns = 3; ns >= 2; --ns) {
       const long long last = (long long)(ns - 1) * stage;
       if (ns * stage <= budget && last + 16LL * px <= budget) {
         p.TD = TD; p.TH = TH; p.TW = TW; p.HD = HD; p.HH = HH; p.HW = HW;
-        p.px = px; p.py = py; p.stage_bytes = (int)stage; p.nstages = ns;
+        p.px = px; p.px_bytes = cells * 16; p.py = py; p.stage_bytes = (int)stage; p.nstages = ns;
         found = true;
         break;
       }
@@ -240,33 +275,36 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
   }
   B3D_REQUIRE(found, B3D_ERR_UNSUPPORTED, "wgrad: no tile fits shared memory (Cin=%d Cout=%d)", Cin, Cout);
   p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.xplanes_max = xpl;
+  p.NT = NT; p.nnt = nnt; p.pad = KS == 3 ? 1 : 0; p.s2_nA = s2 ? wg.nA : 0;
   p.ntd = (wg.Ds + p.TD - 1) / p.TD; p.nth = (wg.Hs + p.TH - 1) / p.TH; p.ntw = (wg.Ws + p.TW - 1) / p.TW;
   p.ntiles = wg.B * p.ntd * p.nth * p.ntw;
-  int nsplit = sm_count() / (ntg * nmt);
+  int nsplit = sm_count() / (ntg * nmt * nnt);
   if (nsplit < 1) nsplit = 1;
   if (nsplit > p.ntiles) nsplit = p.ntiles;
   p.nsplit = nsplit;
   CUtensorMap tmx, tmy;
-  B3D_TRY(make_map(&tmx, x, Cin, wg.bigp, wg.Wb, wg.Hb, wg.Db, wg.B, p.HW, p.HH, p.HD));
+  if (s2) B3D_TRY(make_map(&tmx, x, Cin, Cin, wg.Ws, wg.Hs, wg.Ds, wg.B, p.HW, p.HH, p.HD));
+  else    B3D_TRY(make_map(&tmx, x, Cin, wg.bigp, wg.Wb, wg.Hb, wg.Db, wg.B, p.HW, p.HH, p.HD));
   B3D_TRY(make_map(&tmy, dy, Cout, wg.smallp, wg.Ws, wg.Hs, wg.Ds, wg.B, p.TW, p.TH, p.TD));
-  B3D_TRY(cuda_ok(cudaMemsetAsync(dw, 0, sizeof(float) * 27 * (size_t)Cin * Cout, s), "memset dw"));
-  dim3 grid((unsigned)nsplit, (unsigned)ntg, (unsigned)nmt);
-#define LAUNCH(T)                                                                                              \
+  B3D_TRY(cuda_ok(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)wg.k * wg.k * wg.k * wg.nA * Cout, s), "memset dw"));
+  dim3 grid((unsigned)nsplit, (unsigned)ntg, (unsigned)(nmt * nnt));
+#define LAUNCH(K, T)                                                                                           \
   do {                                                                                                         \
     static bool attr = false;                                                                                  \
     if (!attr) {                                                                                               \
-      B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv3_wgrad_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           kWgSmem), "cudaFuncSetAttribute(wgrad_tc)"));                        \
+      B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv3_wgrad_tc_kernel<K, T>,                                         \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem),             \
+                      "cudaFuncSetAttribute(wgrad_tc)"));                                                      \
       attr = true;                                                                                             \
     }                                                                                                          \
-    conv3_wgrad_tc_kernel<T><<<grid, 256, kWgSmem, s>>>(tmx, tmy, p);                                          \
+    conv3_wgrad_tc_kernel<K, T><<<grid, 256, kWgSmem, s>>>(tmx, tmy, p);                                       \
   } while (0)
-  switch (TG) {
-    case 27: LAUNCH(27); break;
-    case 9: LAUNCH(9); break;
-    case 3: LAUNCH(3); break;
-    default: LAUNCH(1); break;
-  }
+  if (KS == 1) LAUNCH(1, 1);
+  else if (KS == 2) LAUNCH(2, 8);
+  else if (TG == 27) LAUNCH(3, 27);
+  else if (TG == 9) LAUNCH(3, 9);
+  else if (TG == 3) LAUNCH(3, 3);
+  else LAUNCH(3, 1);
 #undef LAUNCH
   B3D_LAUNCH_CHECK("conv3_wgrad_tc");
   return B3D_OK;
@@ -301,6 +339,62 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, uint4* __restric
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[i], sm[i]);
   }
+}
+
+// space-to-depth variant: dst [B, D, H, W, (parity, C)] bf16  <-  src [B, 2D, 2H, 2W, C] fp32 (channel pitch `pitch`);
+// thread -> one 8-channel cell of dst, the channel octet of a thread is loop-invariant
+__global__ void cast_bf16_s2d_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int B, int D, int H, int W,
+                                     int C, long long pitch, float* __restrict__ colsum) {
+  extern __shared__ float sm[];
+  const int oc = C / 8;
+  const long long total = (long long)B * D * H * W * 8 * oc;
+  const int o = threadIdx.x % oc;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / oc;
+    const int par = (int)(r % 8); r /= 8;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int d = (int)(r % D); r /= D;
+    const long long vox = (((r * 2 * D + 2 * d + (par >> 2)) * 2 * H + 2 * h + ((par >> 1) & 1)) * 2 * W) + 2 * w +
+                          (par & 1);
+    const float4 a = ld_stream(reinterpret_cast<const float4*>(src + vox * pitch + o * 8));
+    const float4 b = ld_stream(reinterpret_cast<const float4*>(src + vox * pitch + o * 8) + 1);
+    uint4 q;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(a.y), "f"(a.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(a.w), "f"(a.z));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(b.y), "f"(b.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(b.w), "f"(b.z));
+    dst[i] = q;
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+  if (colsum != nullptr) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&sm[o * 8 + i], acc[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&colsum[i], sm[i]);
+  }
+}
+
+int launch_cast_bf16_s2d(const float* src, void* dst, int B, int D, int H, int W, int C, long long pitch,
+                         float* colsum, cudaStream_t s) {
+  B3D_REQUIRE(C % 8 == 0 && C <= 2048, B3D_ERR_UNSUPPORTED, "cast_bf16_s2d: channels must be a multiple of 8");
+  const int oc = C / 8;
+  const int threads = oc >= 256 ? oc : (256 / oc) * oc;
+  const long long total = (long long)B * D * H * W * 8 * oc;
+  long long blocks = (total + (long long)threads * 8 - 1) / ((long long)threads * 8);
+  const long long cap = 8LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (colsum != nullptr) B3D_TRY(cuda_ok(cudaMemsetAsync(colsum, 0, sizeof(float) * C, s), "memset colsum"));
+  cast_bf16_s2d_kernel<<<(unsigned)blocks, threads, sizeof(float) * C, s>>>(src, (uint4*)dst, B, D, H, W, C, pitch,
+                                                                            colsum);
+  B3D_LAUNCH_CHECK("cast_bf16_s2d");
+  return B3D_OK;
 }
 
 int launch_cast_bf16(const float* src, void* dst, long long nvox, int C, float* colsum, cudaStream_t s) {

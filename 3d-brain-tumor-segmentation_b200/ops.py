@@ -32,16 +32,15 @@ def _check(x: torch.Tensor, name="input"):
         raise TypeError(f"b3d: {name} must be float32, got {x.dtype}")
 
 
-def tc_supported(k, stride, transposed, c_gathered, c_produced) -> bool:
-    return bool(lib.b3d_conv3d_tc_supported(k, stride, int(transposed), c_gathered, c_produced))
+def tc_supported(w, stride, transposed, dgrad) -> bool:
+    """Does the tcgen05 kernel run this pass of a layer with Keras kernel `w` (k,k,k,a,b)?"""
+    return bool(lib.b3d_conv3d_tc_supported(w.shape[0], stride, int(transposed), int(dgrad), w.shape[3], w.shape[4]))
 
 
-def pack_weights(w: torch.Tensor, dgrad: bool) -> torch.Tensor:
-    k = w.shape[0]
-    cg, cp = (w.shape[4], w.shape[3]) if dgrad else (w.shape[3], w.shape[4])
-    n = lib.b3d_conv3d_packed_elems(k, cg, cp)
+def pack_weights(w: torch.Tensor, dgrad: bool, stride: int = 1, transposed: bool = False) -> torch.Tensor:
+    n = lib.b3d_conv3d_packed_elems(w.shape[0], stride, w.shape[3], w.shape[4])
     out = _new((n,), w)
-    _call("b3d_conv3d_pack_weights", w, out, int(dgrad))
+    _call("b3d_conv3d_pack_weights", w, out, stride, int(transposed), int(dgrad))
     return out
 
 
@@ -87,8 +86,8 @@ class Conv3dFn(Function):
         if want_gap:
             gap = _new((B, Cout), x)
         wp = None
-        if USE_TC["on"] and not act and tc_supported(k, stride, transposed, Cin, Cout):
-            wp = pack_weights(w, False)
+        if USE_TC["on"] and not act and tc_supported(w, stride, transposed, False):
+            wp = pack_weights(w, False, stride, transposed)
         _call("b3d_conv3d_fwd", x, w, bias, y, stride, int(transposed), int(act), stats, gn_groups or 1, gap, 0, wp)
         ctx.save_for_backward(x, w, y if act else None)
         ctx.cfg = (stride, transposed, act, bias is not None)
@@ -108,12 +107,9 @@ class Conv3dFn(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            k = w.shape[0]
-            cg = w.shape[3] if transposed else w.shape[4]
-            cp = w.shape[4] if transposed else w.shape[3]
             wp = None
-            if USE_TC["on"] and not transposed and tc_supported(k, stride, False, cg, cp):
-                wp = pack_weights(w, True)
+            if USE_TC["on"] and tc_supported(w, stride, transposed, True):
+                wp = pack_weights(w, True, stride, transposed)
             _call("b3d_conv3d_dgrad", dy, w, dx, stride, int(transposed), 0, wp)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)

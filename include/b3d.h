@@ -61,13 +61,17 @@ int b3d_conv3d_dgrad(const DLTensor* dy, const DLTensor* w, DLTensor* dx, int st
 int b3d_conv3d_wgrad(const DLTensor* x, const DLTensor* dy, DLTensor* dw, DLTensor* dbias, int stride,
                      int transposed, const DLTensor* x_bf16, const DLTensor* dy_bf16, void* stream);
 int b3d_conv3d_wgrad_tc_supported(int k, int stride, int transposed, int cin, int cout);
-int b3d_conv3d_tc_supported(int k, int stride, int transposed, int c_gathered, int c_produced);
+/* 1 when the tcgen05 kernel runs the forward (dgrad=0) / data-gradient (dgrad=1) pass of a layer whose Keras
+ * kernel is (k,k,k,a,b): stride-1 k in {1,3}, and the k3 stride-2 family (Conv3D s2, Conv3DTranspose), which is
+ * executed as a 2x2x2 stride-1 conv over the coarse grid with space-to-depth addressing (csrc/conv_s2.cu). */
+int b3d_conv3d_tc_supported(int k, int stride, int transposed, int dgrad, int a, int b);
 /* operand type of the tcgen05 conv MMAs (1 = bf16, 0 = tf32) for the forward pass and for the data gradient;
  * defaults: forward tf32, backward bf16; fp32 accumulation either way.  get: bit0 = fwd, bit1 = bwd. */
 int b3d_set_conv_precision(int fwd_bf16, int bwd_bf16);
 int b3d_get_conv_precision(void);
-long long b3d_conv3d_packed_elems(int k, int c_gathered, int c_produced);
-int b3d_conv3d_pack_weights(const DLTensor* w, DLTensor* packed, int dgrad, void* stream);
+long long b3d_conv3d_packed_elems(int k, int stride, int a, int b);
+int b3d_conv3d_pack_weights(const DLTensor* w, DLTensor* packed, int stride, int transposed, int dgrad,
+                            void* stream);
 
 /* ---- GroupNormalization.call, channels_last semantics (group_norm.py:83-124) -----
  * "group" g = g-th contiguous 1/G chunk of each sample's flat buffer; eps inside sqrt; population

@@ -39,6 +39,13 @@ CONV_CASES = [
     ((4, 6, 8), 12, 8, 3, 2, False),
     ((4, 4, 4), 16, 8, 3, 2, True),
     ((2, 2, 2), 1, 128, 3, 2, True),
+    # stride-2 family on the tcgen05 path (2x2x2 conv over the coarse grid, space-to-depth addressing)
+    ((16, 32, 16), 16, 16, 3, 2, False),
+    ((12, 20, 36), 64, 32, 3, 2, False),
+    ((8, 8, 8), 192, 64, 3, 2, False),
+    ((8, 16, 8), 32, 16, 3, 2, True),
+    ((6, 10, 18), 64, 32, 3, 2, True),
+    ((4, 4, 4), 512, 64, 3, 2, True),
     ((4, 16, 8), 64, 32, 3, 1, False),
 ]
 
@@ -66,7 +73,8 @@ def reset_mode(b3d):
 def test_conv_fwd_bwd(b3d, dev, case, mode):
     sp, cin, cout, k, stride, tr = case
     use_tc = mode != "fp32"
-    if use_tc and not b3d.ops.tc_supported(k, stride, tr, cin, cout):
+    wshape = (k, k, k) + ((cout, cin) if tr else (cin, cout))
+    if use_tc and not b3d.ops.tc_supported(torch.empty(wshape, device="meta"), stride, tr, False):
         pytest.skip("shape not on the tcgen05 path")
     set_mode(b3d, mode)
     try:
@@ -79,11 +87,17 @@ def test_conv_fwd_bwd(b3d, dev, case, mode):
         gy = t64(*yr.shape, seed=4)
         (yr * gy).sum().backward()
         xd, wd, bd = dev32(x, dev, True), dev32(w, dev, True), dev32(bias, dev, True)
-        y, stats, gap = b3d.ops.conv3d(xd, wd, bd, stride, tr, 0, 0, True)
+        S = yr.shape[1] * yr.shape[2] * yr.shape[3]
+        groups = 8 if (S % 8 == 0 and cout % 8 == 0) else 0
+        y, stats, gap = b3d.ops.conv3d(xd, wd, bd, stride, tr, 0, groups, stride == 1)
         (y * dev32(gy, dev)).sum().backward()
         tol = MODE_TOL[mode]
         assert rel(y, yr) < tol
-        assert rel(gap, yr.sum(dim=(1, 2, 3))) < max(tol, 1e-4)
+        if stride == 1:
+            assert rel(gap, yr.sum(dim=(1, 2, 3))) < max(tol, 1e-4)
+        if groups:
+            ch = yr.detach().reshape(B, groups, -1)
+            assert rel(stats, torch.stack([ch.sum(-1), (ch ** 2).sum(-1)], dim=-1)) < max(tol, 1e-4)
         assert rel(xd.grad, xr.grad) < tol
         assert rel(wd.grad, wr.grad) < (TOL_BF16 if use_tc else tol)
         assert rel(bd.grad, br.grad) < TOL32 * 10
@@ -291,7 +305,7 @@ def test_tc_conv_vs_oracle_and_generic(b3d, dev, case):
     """tcgen05 implicit GEMM (TF32) vs the fp64 oracle (<= 2e-3) and vs the fp32 CUDA-core kernel,
     including the fused GroupNorm statistics and the dgrad (flipped/transposed packing)."""
     B, sp, cin, cout = case
-    assert b3d.ops.tc_supported(3, 1, False, cin, cout)
+    assert b3d.ops.tc_supported(torch.empty(3, 3, 3, cin, cout, device="meta"), 1, False, False)
     x = t64(B, *sp, cin, seed=21)
     w = t64(3, 3, 3, cin, cout, seed=22, scale=(2.0 / (27 * cin)) ** 0.5)
     bias = t64(cout, seed=23)
