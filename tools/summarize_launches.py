@@ -17,11 +17,12 @@ s, e = (idx[-2] + 2, idx[-1] + 2) if len(idx) >= 2 else (0, len(rows))
 agg = collections.defaultdict(lambda: [0, 0.0])
 for n, v in zip(names[s:e], vals[s:e]):
     k = re.sub(r"[<(].*", "", n).replace("void ", "")
-    if "conv3_tc_kernel" in n:
-        m = re.search(r"TcCfg<[^>]*>", n)
-        k = "b3d::conv3_tc_kernel " + (m.group(0) if m else "")
+    if "conv_tc_kernel" in n:
+        m = re.search(r"TcCfg<(\d+), *\d+, *\d+, *(\d+), *(\d+), *(\w+)>", n)
+        k = f"b3d::conv_tc_kernel KS={m.group(2)}" + (" (stride-2 family)" if m.group(2) == "2" else "")
     elif "wgrad_tc" in n:
-        k = "b3d::conv3_wgrad_tc_kernel TG=" + re.search(r"<(\d+)>", n).group(1)
+        m = re.search(r"<(\d+), *(\d+)>", n)
+        k = f"b3d::conv3_wgrad_tc_kernel KS={m.group(1)} TG={m.group(2)}"
     elif k.startswith("at::"):
         k = "at:: (torch elementwise: autograd grad accumulation, zeros, stack)"
     agg[k][0] += 1
