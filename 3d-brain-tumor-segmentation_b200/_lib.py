@@ -72,11 +72,14 @@ _i, _f, _v, _ll, _ull = C.c_int, C.c_float, C.c_void_p, C.c_longlong, C.c_ulongl
 # name -> argtypes ('T' = DLTensor*)
 SIGNATURES = {
     "b3d_conv3d_fwd": "TTTTiiiTiTiTv",
+    "b3d_conv3d_fwd_halo": "TTTTiiiiiTTv",
     "b3d_conv3d_dgrad": "TTTiiiTv",
     "b3d_conv3d_wgrad": "TTTTiiTTv",
     "b3d_conv3d_pack_weights": "TTiiiv",
     "b3d_gn_stats": "TTiv",
     "b3d_gn_apply": "TTTTTifiv",
+    "b3d_gn_stats_slab": "TTiLLv",
+    "b3d_gn_apply_slab": "TTTTTifiLLv",
     "b3d_gn_bwd_reduce": "TTTTTTTTifiv",
     "b3d_gn_bwd_apply": "TTTTTTTifiv",
     "b3d_se_fc_fwd": "TTTTTfv",

@@ -11,15 +11,16 @@ struct ConvArgs {
   int k;
 };
 
-int spatial_ok(const TView& big, const TView& small, int stride, const char* what) {
+// big_halo / small_halo: extra depth slices (slab halos) carried by the respective tensor
+int spatial_ok(const TView& big, const TView& small, int stride, const char* what, int big_halo = 0,
+               int small_halo = 0) {
   for (int i = 1; i <= 3; ++i) {
+    const long long nb = big.shape[i] - (i == 1 ? big_halo : 0), ns = small.shape[i] - (i == 1 ? small_halo : 0);
     if (stride == 1) {
-      B3D_REQUIRE(big.shape[i] == small.shape[i], B3D_ERR_SHAPE, "%s: spatial dims differ (dim %d: %lld vs %lld)",
-                  what, i, (long long)big.shape[i], (long long)small.shape[i]);
+      B3D_REQUIRE(nb == ns, B3D_ERR_SHAPE, "%s: spatial dims differ (dim %d: %lld vs %lld)", what, i, nb, ns);
     } else {
-      B3D_REQUIRE(big.shape[i] % 2 == 0 && big.shape[i] == 2 * small.shape[i], B3D_ERR_SHAPE,
-                  "%s: stride-2 needs even sizes with big == 2*small (dim %d: %lld vs %lld)", what, i,
-                  (long long)big.shape[i], (long long)small.shape[i]);
+      B3D_REQUIRE(nb % 2 == 0 && nb == 2 * ns, B3D_ERR_SHAPE,
+                  "%s: stride-2 needs even sizes with big == 2*small (dim %d: %lld vs %lld)", what, i, nb, ns);
     }
   }
   B3D_REQUIRE(big.shape[0] == small.shape[0], B3D_ERR_SHAPE, "%s: batch differs", what);
@@ -87,22 +88,24 @@ int bias_ptr(const DLTensor* bias_, int C, const float** out) {
 }
 
 // geometry of forward / dgrad for the four (stride, transposed) variants
-int geom_fwd(ConvGeom& g, const TView& x, const TView& w, const TView& y, int k, int stride, int transposed) {
+int geom_fwd(ConvGeom& g, const TView& x, const TView& w, const TView& y, int k, int stride, int transposed,
+             int halo_before = 0, int halo_after = 0) {
   memset(&g, 0, sizeof(g));
   fill_in(g, x);
   fill_out(g, y);
-  g.k = k; g.pad = k / 2;
+  g.k = k; g.pad = k / 2; g.doff = halo_before;
+  const int halo = halo_before + halo_after;
   if (!transposed) {
     B3D_REQUIRE(w.shape[3] == g.Cin && w.shape[4] == g.Cout, B3D_ERR_SHAPE,
                 "conv fwd: kernel (..,%lld,%lld) does not match Cin=%d Cout=%d", (long long)w.shape[3],
                 (long long)w.shape[4], g.Cin, g.Cout);
-    B3D_TRY(spatial_ok(x, y, stride, "conv fwd"));
+    B3D_TRY(spatial_ok(x, y, stride, "conv fwd", halo, 0));
     g.mode = stride == 1 ? CONV_S1 : CONV_DOWN;
     g.wtap = (long long)g.Cin * g.Cout; g.sw_in = g.Cout; g.sw_out = 1;
   } else {
     B3D_REQUIRE(w.shape[3] == g.Cout && w.shape[4] == g.Cin, B3D_ERR_SHAPE,
                 "conv-transpose fwd: kernel must be (3,3,3,Cout,Cin)");
-    B3D_TRY(spatial_ok(y, x, 2, "conv-transpose fwd"));
+    B3D_TRY(spatial_ok(y, x, 2, "conv-transpose fwd", 0, halo));
     g.mode = CONV_UP;
     g.wtap = (long long)g.Cin * g.Cout; g.sw_in = 1; g.sw_out = g.Cin;
   }
@@ -131,9 +134,9 @@ int geom_dgrad(ConvGeom& g, const TView& dy, const TView& w, const TView& dx, in
 
 }  // namespace
 
-extern "C" int b3d_conv3d_fwd(const DLTensor* x_, const DLTensor* w_, const DLTensor* bias_, DLTensor* y_,
-                              int stride, int transposed, int act, DLTensor* gn_stats_, int groups,
-                              DLTensor* gap_, int accumulate, const DLTensor* wpacked_, void* stream) {
+static int conv_fwd_impl(const DLTensor* x_, const DLTensor* w_, const DLTensor* bias_, DLTensor* y_, int stride,
+                         int transposed, int act, DLTensor* gn_stats_, int groups, DLTensor* gap_, int accumulate,
+                         const DLTensor* wpacked_, int halo_before, int halo_after, void* stream) {
   TView x, w, y;
   int k;
   B3D_TRY(view(x_, DT_F32, 5, true, "x", &x));
@@ -141,12 +144,33 @@ extern "C" int b3d_conv3d_fwd(const DLTensor* x_, const DLTensor* w_, const DLTe
   B3D_TRY(weight_view(w_, &w, &k));
   B3D_REQUIRE(stride == 1 || (stride == 2 && k == 3), B3D_ERR_UNSUPPORTED, "conv: stride must be 1, or 2 with k=3");
   B3D_REQUIRE(!transposed || stride == 2, B3D_ERR_UNSUPPORTED, "conv-transpose: only k=3 stride=2");
+  B3D_REQUIRE(halo_before >= 0 && halo_after >= 0 && halo_before <= 1 && halo_after <= 1 &&
+                  (halo_before + halo_after == 0 || x.shape[0] == 1),
+              B3D_ERR_ARG, "conv: slab halos are 0 or 1 slice per side, batch 1");
   ConvGeom g;
-  B3D_TRY(geom_fwd(g, x, w, y, k, stride, transposed));
+  B3D_TRY(geom_fwd(g, x, w, y, k, stride, transposed, halo_before, halo_after));
   g.act = act; g.accumulate = accumulate; g.groups = groups;
   const float* bias;
   B3D_TRY(bias_ptr(bias_, g.Cout, &bias));
   return run(g, x, w, bias, y, gn_stats_, groups, gap_, wpacked_, (cudaStream_t)stream);
+}
+
+extern "C" int b3d_conv3d_fwd(const DLTensor* x_, const DLTensor* w_, const DLTensor* bias_, DLTensor* y_,
+                              int stride, int transposed, int act, DLTensor* gn_stats_, int groups,
+                              DLTensor* gap_, int accumulate, const DLTensor* wpacked_, void* stream) {
+  return conv_fwd_impl(x_, w_, bias_, y_, stride, transposed, act, gn_stats_, groups, gap_, accumulate, wpacked_, 0, 0,
+                       stream);
+}
+
+// Depth-slab form for whole-volume inference sharded along D (test.py:133 on a [1,160,192,160,C] volume): x carries
+// halo_before / halo_after (0|1) extra depth slices — the neighbour slabs' boundary slices, zeros at the volume
+// ends — and y only this slab's slices, so that concatenating the slabs' y equals the conv of the whole volume.
+//   conv k3 s1: halos (1,1);  conv k3 s2: (0,1);  conv-transpose: (1,0);  k1: (0,0).
+extern "C" int b3d_conv3d_fwd_halo(const DLTensor* x_, const DLTensor* w_, const DLTensor* bias_, DLTensor* y_,
+                                   int stride, int transposed, int act, int halo_before, int halo_after,
+                                   DLTensor* gap_, const DLTensor* wpacked_, void* stream) {
+  return conv_fwd_impl(x_, w_, bias_, y_, stride, transposed, act, nullptr, 1, gap_, 0, wpacked_, halo_before,
+                       halo_after, stream);
 }
 
 extern "C" int b3d_conv3d_dgrad(const DLTensor* dy_, const DLTensor* w_, DLTensor* dx_, int stride,

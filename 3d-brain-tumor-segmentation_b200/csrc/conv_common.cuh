@@ -17,6 +17,7 @@ struct ConvGeom {
   int act, accumulate;      // 1 = sigmoid; y += result
   int groups;               // GN groups when stats are requested
   int bwd;                  // 1 = backward pass (operand-precision choice of the tcgen05 path)
+  int doff;                 // slab halos: logical input depth slice i lives at buffer slice i + doff (of Di)
 };
 
 // outer-product form:  dw[t][a][b] = sum_{n,o} big[n, s*o+t-pad, a] * small[n, o, b]

@@ -87,9 +87,10 @@ __global__ void __launch_bounds__(kGT)
           id = 2 * od + td; ih = 2 * oh + th; iw = 2 * ow + tk;
         } else {
           id = od - td; ih = oh - th; iw = ow - tk;
-          if ((id | ih | iw) < 0 || ((id | ih | iw) & 1)) continue;
-          id >>= 1; ih >>= 1; iw >>= 1;
+          if ((id | ih | iw) & 1) continue;
+          id >>= 1; ih >>= 1; iw >>= 1;      // arithmetic shifts: -2 -> -1 (a slab's halo slice before the origin)
         }
+        id += cg.doff;
         if (id < 0 || id >= cg.Di || ih < 0 || ih >= cg.Hi || iw < 0 || iw >= cg.Wi) continue;
         const float* xp = x + ((xb + ((long long)id * cg.Hi + ih) * cg.Wi + iw) * cg.xp + ci0);
         const float* wt = ws + t * kCiT * CO_T;

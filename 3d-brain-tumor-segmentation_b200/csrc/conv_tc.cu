@@ -70,6 +70,9 @@ struct TcParams {
   //   s2d: x is the fine tensor [B,2D,2H,2W,Csub]; virtual input channel k' = parity*Csub + c  (space-to-depth)
   //   d2s: y is the fine tensor [B,2D,2H,2W,Csub]; virtual output column n' = parity*Csub + c (depth-to-space)
   int s2d, d2s, Csub;
+  // slab halos (whole-volume inference sharded along D): x holds Din depth slices (its own units: fine for s2d) and
+  // logical slice i lives at buffer slice i + doff; slices outside [0, Din) read as zero
+  int Din, doff;
 };
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
       const int dt = t % prm.ntd; t /= prm.ntd;
       const int b = t;
       const int w0 = wt * C::TW - C::HB, h0 = ht * C::TH - C::HB, d0 = dt * C::TD - C::HB;
-      const float* xb = prm.x + (long long)b * prm.D * prm.H * prm.W * prm.xp * (prm.s2d ? 8 : 1);
+      const float* xb = prm.x + (long long)b * prm.Din * prm.H * prm.W * prm.xp * (prm.s2d ? 4 : 1);
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
         uint8_t* dst0 = halo + hs * C::HALO_BYTES;
@@ -170,14 +173,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
             const int cw = v % C::HW, q = v / C::HW;
             const int ch = q % C::HH, cd = q / C::HH;
             const int gd = d0 + cd, gh = h0 + ch, gw = w0 + cw;
-            const bool ok = v < C::NVC && gd >= 0 && gd < prm.D && gh >= 0 && gh < prm.H && gw >= 0 && gw < prm.W;
+            const int bd = (prm.s2d ? 2 * gd + sp_d : gd) + prm.doff;      // buffer depth slice
+            const bool ok = v < C::NVC && bd >= 0 && bd < prm.Din && gh >= 0 && gh < prm.H && gw >= 0 && gw < prm.W;
 #pragma unroll
             for (int i = 0; i < kRegs; ++i) r[u][i] = 0.f;
             if (ok) {
               const float* src =
-                  prm.s2d ? xc + (((long long)(2 * gd + sp_d) * (2 * prm.H) + (2 * gh + sp_h)) * (2 * prm.W) +
-                                  (2 * gw + sp_w)) * prm.xp
-                          : xc + (((long long)gd * prm.H + gh) * prm.W + gw) * prm.xp;
+                  prm.s2d ? xc + (((long long)bd * (2 * prm.H) + (2 * gh + sp_h)) * (2 * prm.W) + (2 * gw + sp_w)) * prm.xp
+                          : xc + (((long long)bd * prm.H + gh) * prm.W + gw) * prm.xp;
               ld256(src, r[u]);
               if (C::BF16) ld256(src + 8, r[u] + 8);
             }
@@ -475,7 +478,7 @@ static TcProblem tc_problem(const ConvGeom& g) {
     q.ks = 2; q.hb = 0; q.Cin = 8 * g.Cin; q.Cout = g.Cout; q.D = g.Do; q.H = g.Ho; q.W = g.Wo;
     q.s2d = 1; q.Csub = g.Cin;
   } else {
-    q.ks = 2; q.hb = 1; q.Cin = g.Cin; q.Cout = 8 * g.Cout; q.D = g.Di; q.H = g.Hi; q.W = g.Wi;
+    q.ks = 2; q.hb = 1; q.Cin = g.Cin; q.Cout = 8 * g.Cout; q.D = g.Do / 2; q.H = g.Ho / 2; q.W = g.Wo / 2;
     q.d2s = 1; q.Csub = g.Cout;
   }
   return q;
@@ -522,6 +525,7 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   p.accumulate = g.accumulate; p.groups = g.groups > 0 ? g.groups : 1;
   p.vpc = ((long long)g.Do * g.Ho * g.Wo) / p.groups;
   p.s2d = q.s2d; p.d2s = q.d2s; p.Csub = q.Csub;
+  p.Din = g.Di; p.doff = g.doff;
   static bool attr_set = false;
   if (!attr_set) {
     B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),

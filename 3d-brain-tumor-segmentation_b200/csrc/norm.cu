@@ -32,9 +32,13 @@ __device__ __forceinline__ void chunk_moments(const double* __restrict__ stats, 
 // ------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats,
-                                                           long long L) {
+                                                           long long L, long long shift, long long n_local) {
+  // slab form: x holds the flat elements [shift, shift + n_local) of the sample; a CTA covers the part of its
+  // chunk that lies inside (shift = 0, n_local = everything otherwise)
   const int chunk = blockIdx.y;
-  const float* xc = x + (long long)chunk * L;
+  const long long e_lo = max(0LL, shift - (long long)chunk * L), e_hi = min(L, shift + n_local - (long long)chunk * L);
+  if (e_lo >= e_hi) return;
+  const float* xc = x + ((long long)chunk * L - shift);
   float s[2] = {0.f, 0.f};
   // reducing kernels walk several segments per CTA so that few CTAs contend on one fp64 atomic
   for (long long base = (long long)blockIdx.x * (kThreads * kIter * VEC); base < L;
@@ -42,7 +46,7 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restr
 #pragma unroll
     for (int k = 0; k < kIter; ++k) {
       const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
-      if (e < L) {
+      if (e >= e_lo && e < e_hi) {
         if (VEC == 4) {
           const float4 v = ld_stream(reinterpret_cast<const float4*>(xc + e));
           s[0] += (v.x + v.y) + (v.z + v.w);
@@ -68,19 +72,23 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restr
 template <int VEC, bool RELU>
 __global__ void __launch_bounds__(kThreads)
     gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, float* __restrict__ y, ChunkGeom gm, float eps) {
+                    const float* __restrict__ beta, float* __restrict__ y, ChunkGeom gm, float eps,
+                    long long shift, long long n_local) {
   const int chunk = blockIdx.y;
   const int g = chunk % gm.G;
+  const long long e_lo = max(0LL, shift - (long long)chunk * gm.L),
+                  e_hi = min(gm.L, shift + n_local - (long long)chunk * gm.L);   // slab form, see gn_stats_kernel
+  if (e_lo >= e_hi) return;
   float mean, rstd;
   chunk_moments(stats, chunk, 1.0 / (double)gm.L, eps, mean, rstd);
-  const long long off = (long long)chunk * gm.L;
+  const long long off = (long long)chunk * gm.L - shift;
   const long long base = (long long)blockIdx.x * (kThreads * kIter * VEC);
   const int jbase = g * gm.cg;
   const long long goff = (long long)g * gm.L;
 #pragma unroll
   for (int k = 0; k < kIter; ++k) {
     const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
-    if (e < gm.L) {
+    if (e >= e_lo && e < e_hi) {
       const int c0 = (int)((goff + e) % gm.cg);
       if (VEC == 4) {
         const float4 v = ld_stream(reinterpret_cast<const float4*>(x + off + e));
@@ -296,9 +304,11 @@ extern "C" int b3d_gn_stats(const DLTensor* x_, DLTensor* stats_, int groups, vo
   B3D_TRY(cuda_ok(cudaMemsetAsync(st.p, 0, sizeof(double) * 2 * nchunks, s), "memset stats"));
   const bool v4 = (gm.L % 4 == 0) && (((uintptr_t)x.p & 15) == 0);
   if (v4)
-    gn_stats_kernel<4><<<gn_grid(gm, nchunks, 4, true), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L);
+    gn_stats_kernel<4><<<gn_grid(gm, nchunks, 4, true), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L, 0,
+                                                                          x.numel);
   else
-    gn_stats_kernel<1><<<gn_grid(gm, nchunks, 1, true), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L);
+    gn_stats_kernel<1><<<gn_grid(gm, nchunks, 1, true), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L, 0,
+                                                                          x.numel);
   B3D_LAUNCH_CHECK("gn_stats");
   return B3D_OK;
 }
@@ -319,7 +329,8 @@ extern "C" int b3d_gn_apply(const DLTensor* x_, const DLTensor* stats_, const DL
   const bool v4 = (gm.L % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)y.p) & 15) == 0);
 #define LAUNCH(V, R)                                                                                     \
   gn_apply_kernel<V, R><<<gn_grid(gm, nchunks, V), kThreads, 0, s>>>(                                    \
-      (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps)
+      (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, 0,   \
+      x.numel)
   if (v4) {
     if (relu) LAUNCH(4, true); else LAUNCH(4, false);
   } else {
@@ -327,6 +338,69 @@ extern "C" int b3d_gn_apply(const DLTensor* x_, const DLTensor* stats_, const DL
   }
 #undef LAUNCH
   B3D_LAUNCH_CHECK("gn_apply");
+  return B3D_OK;
+}
+
+// ---- depth-slab forms (whole-volume inference sharded along D; batch 1): x is this rank's contiguous part
+// [elem_offset, elem_offset + numel) of a sample with total_elems elements.  gn_stats_slab writes this slab's
+// PARTIAL (sum, sum^2) per chunk of the WHOLE sample (the caller all-reduces them); gn_apply_slab normalises the
+// slab with the reduced statistics.  Chunk boundaries need not coincide with slab boundaries.
+static int slab_geom(const TView& x, int groups, long long elem_offset, long long total_elems, ChunkGeom* gm) {
+  const int C = (int)x.shape[x.ndim - 1];
+  B3D_REQUIRE(groups >= 1 && C >= groups && C % groups == 0, B3D_ERR_SHAPE,
+              "Number of groups (%d) must be a multiple of the number of channels (%d).", groups, C);
+  B3D_REQUIRE(total_elems % groups == 0 && elem_offset >= 0 && elem_offset + x.numel <= total_elems &&
+                  elem_offset % C == 0 && total_elems % C == 0,
+              B3D_ERR_SHAPE, "gn slab: bad offset / total (%lld, %lld)", elem_offset, total_elems);
+  gm->L = total_elems / groups; gm->C = C; gm->cg = C / groups; gm->G = groups; gm->inv_L = 1.0f / (float)gm->L;
+  return B3D_OK;
+}
+
+extern "C" int b3d_gn_stats_slab(const DLTensor* x_, DLTensor* stats_, int groups, long long elem_offset,
+                                 long long total_elems, void* stream) {
+  TView x, st;
+  ChunkGeom gm;
+  B3D_TRY(view(x_, DT_F32, -1, false, "x", &x));
+  B3D_TRY(slab_geom(x, groups, elem_offset, total_elems, &gm));
+  B3D_TRY(check_stats(stats_, groups, "stats", &st));
+  cudaStream_t s = (cudaStream_t)stream;
+  B3D_TRY(cuda_ok(cudaMemsetAsync(st.p, 0, sizeof(double) * 2 * groups, s), "memset stats"));
+  const bool v4 = (gm.L % 4 == 0) && (elem_offset % 4 == 0) && (((uintptr_t)x.p & 15) == 0);
+  if (v4)
+    gn_stats_kernel<4><<<gn_grid(gm, groups, 4, true), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L,
+                                                                         elem_offset, x.numel);
+  else
+    gn_stats_kernel<1><<<gn_grid(gm, groups, 1, true), kThreads, 0, s>>>((const float*)x.p, (double*)st.p, gm.L,
+                                                                         elem_offset, x.numel);
+  B3D_LAUNCH_CHECK("gn_stats_slab");
+  return B3D_OK;
+}
+
+extern "C" int b3d_gn_apply_slab(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
+                                 const DLTensor* beta_, DLTensor* y_, int groups, float eps, int relu,
+                                 long long elem_offset, long long total_elems, void* stream) {
+  TView x, y, st, ga, be;
+  ChunkGeom gm;
+  B3D_TRY(view(x_, DT_F32, -1, false, "x", &x));
+  B3D_TRY(view(y_, DT_F32, -1, false, "y", &y));
+  B3D_REQUIRE(x.numel == y.numel, B3D_ERR_SHAPE, "gn_apply_slab: x/y size mismatch");
+  B3D_TRY(slab_geom(x, groups, elem_offset, total_elems, &gm));
+  B3D_TRY(check_stats(stats_, groups, "stats", &st));
+  B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
+  B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool v4 = (gm.L % 4 == 0) && (elem_offset % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)y.p) & 15) == 0);
+#define LAUNCH(V, R)                                                                                     \
+  gn_apply_kernel<V, R><<<gn_grid(gm, groups, V), kThreads, 0, s>>>(                                     \
+      (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps,     \
+      elem_offset, x.numel)
+  if (v4) {
+    if (relu) LAUNCH(4, true); else LAUNCH(4, false);
+  } else {
+    if (relu) LAUNCH(1, true); else LAUNCH(1, false);
+  }
+#undef LAUNCH
+  B3D_LAUNCH_CHECK("gn_apply_slab");
   return B3D_OK;
 }
 

@@ -9,6 +9,7 @@ import torch
 from torch.autograd import Function
 
 from ._lib import call, lib
+from . import slab as _slab
 
 _f32 = torch.float32
 
@@ -124,6 +125,9 @@ class Conv3dFn(Function):
 
 
 def conv3d(x, w, bias=None, stride=1, transposed=False, act=0, gn_groups=0, want_gap=False):
+    ctx = _slab.current()
+    if ctx is not None:        # depth-slab sharded inference: halo exchange + all-reduced GAP, no fused GN stats
+        return ctx.conv3d(x, w, bias, stride, transposed, act, want_gap)
     return Conv3dFn.apply(x, w, bias, stride, transposed, act, gn_groups, want_gap)
 
 
@@ -164,6 +168,9 @@ class GroupNormFn(Function):
 
 
 def group_norm(x, gamma, beta, stats=None, groups=8, eps=1e-5, relu=False):
+    ctx = _slab.current()
+    if ctx is not None:        # chunk statistics of the WHOLE volume: partial sums + all-reduce
+        return ctx.group_norm(x, gamma, beta, groups, eps, relu)
     return GroupNormFn.apply(x, gamma, beta, stats, groups, eps, relu)
 
 
@@ -176,7 +183,8 @@ class BlockEpilogueFn(Function):
         _check(res)
         res, h2 = res.contiguous(), h2.contiguous()
         B, F = res.shape[0], res.shape[-1]
-        S = res.numel() // (B * F)
+        ctx_s = _slab.current()
+        S = res.numel() // (B * F) if ctx_s is None else ctx_s.global_voxels(res)   # GAP divisor: whole volume
         R = w1.shape[1]
         hidden, chse = _new((B, R), res), _new((B, F), res)
         inv = 1.0 / S

@@ -1,0 +1,322 @@
+"""Whole-volume inference sharded into depth slabs (BASELINE config 4).
+
+The reference runs `model(x, training=False, inference=True)` (/root/reference/test.py:133) on one padded
+[1, 160, 192, 160, C] volume.  Here the volume is cut along D into `world` slabs whose boundaries are multiples of
+2**(depth-1) (so every down/upsampling stays local); each rank runs THE SAME layer code (layers/*.py, model.py) on
+its slab while a `SlabContext` reroutes the three operations whose result depends on other slabs:
+
+  * 3x3x3 convolutions: one-slice halo exchange with the +-1 neighbours before the conv
+      stride 1: (before, after) = (1, 1);  stride 2 (TF 'same' pads 0/1): (0, 1);  Conv3DTranspose: (1, 0);
+      zeros at the volume ends = TF 'SAME' padding.  The conv kernels read the halo slices in place
+      (`b3d_conv3d_fwd_halo`), the output holds only this slab's slices.
+  * GroupNormalization (group_norm.py:83-124): its "groups" are contiguous 1/G chunks of the WHOLE flat volume
+       and do not line up with slabs => every rank reduces partial (sum, sum^2) per global chunk
+      (`b3d_gn_stats_slab`), one all-reduce of 2*G doubles, then `b3d_gn_apply_slab`.
+  * channel squeeze-excitation (resnet.py:45-58): the global-average-pool sums from the pointwise conv's epilogue
+      are all-reduced (F floats) and divided by the global voxel count.
+
+Communication goes through a tiny `Comm` interface with two implementations: `DistComm` (torch.distributed: NCCL
+over NVLink on the GPUs of one box, gloo in the CPU tests) and `ThreadComm` (N virtual ranks = N threads of one
+process sharing one GPU; used to validate the slab arithmetic on a single-GPU box).
+"""
+from __future__ import annotations
+
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+_f32 = torch.float32
+
+
+# ------------------------------------------------------------------------------------------ partition
+def slab_bounds(depth: int, world: int, align: int = 8) -> List[Tuple[int, int]]:
+    """[d0, d1) per rank: `depth // align` units dealt as evenly as possible, larger slabs first
+    (160 slices, 8 ranks, align 8 -> 24,24,24,24,16,16,16,16)."""
+    if depth % align != 0:
+        raise ValueError(f"depth {depth} must be a multiple of {align} (pad_to_spatial_res does that)")
+    units = depth // align
+    if world > units:
+        raise ValueError(f"cannot cut {units} units of {align} slices into {world} slabs")
+    base, extra = divmod(units, world)
+    out, d = [], 0
+    for r in range(world):
+        n = (base + (1 if r < extra else 0)) * align
+        out.append((d, d + n))
+        d += n
+    return out
+
+
+# ------------------------------------------------------------------------------------------ communication
+class Comm:
+    rank: int
+    world: int
+
+    def exchange(self, send_prev, send_next, recv_prev, recv_next) -> None:
+        """Neighbour exchange along the slab axis.  send_prev goes to rank-1 (arrives in its recv_next),
+        send_next to rank+1 (arrives in its recv_prev).  Arguments are None where there is no neighbour or
+        nothing to move; all ranks call with the same pattern."""
+        raise NotImplementedError
+
+    def all_reduce_sum(self, t: torch.Tensor) -> None:
+        raise NotImplementedError
+
+    def all_gather_cat(self, t: torch.Tensor, sizes: Sequence[int]) -> torch.Tensor:
+        """Concatenate the ranks' tensors (dim 1 extents `sizes`) on every rank."""
+        raise NotImplementedError
+
+
+class DistComm(Comm):
+    """torch.distributed backend (NCCL P2P + all-reduce over NVLink/NVSwitch; gloo for the CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def exchange(self, send_prev, send_next, recv_prev, recv_next):
+        d, ops_ = self.dist, []
+        # receives first; every op is posted in one batch (ncclGroupStart/End) so no ordering can deadlock
+        if recv_prev is not None:
+            ops_.append(d.P2POp(d.irecv, recv_prev, self.rank - 1, self.group))
+        if recv_next is not None:
+            ops_.append(d.P2POp(d.irecv, recv_next, self.rank + 1, self.group))
+        if send_prev is not None:
+            ops_.append(d.P2POp(d.isend, send_prev, self.rank - 1, self.group))
+        if send_next is not None:
+            ops_.append(d.P2POp(d.isend, send_next, self.rank + 1, self.group))
+        if ops_:
+            for w in d.batch_isend_irecv(ops_):
+                w.wait()
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def all_gather_cat(self, t, sizes):
+        if self.world == 1:
+            return t
+        parts = [torch.empty((t.shape[0], n) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device) for n in sizes]
+        self.dist.all_gather(parts, t.contiguous(), group=self.group)
+        return torch.cat(parts, dim=1)
+
+
+class _ThreadShared:
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+
+class ThreadComm(Comm):
+    """N virtual ranks = N threads of one process on ONE device (same CUDA stream, so program order across the
+    barrier is also stream order).  Reductions add in rank order, so every rank gets bit-identical sums."""
+
+    def __init__(self, shared: _ThreadShared, rank: int):
+        self.sh, self.rank, self.world = shared, rank, shared.world
+
+    @staticmethod
+    def make(world: int) -> List["ThreadComm"]:
+        sh = _ThreadShared(world)
+        return [ThreadComm(sh, r) for r in range(world)]
+
+    def exchange(self, send_prev, send_next, recv_prev, recv_next):
+        sh = self.sh
+        sh.slots[self.rank] = (send_prev, send_next)
+        sh.barrier.wait()
+        if recv_prev is not None:
+            recv_prev.copy_(sh.slots[self.rank - 1][1])
+        if recv_next is not None:
+            recv_next.copy_(sh.slots[self.rank + 1][0])
+        sh.barrier.wait()
+
+    def all_reduce_sum(self, t):
+        sh = self.sh
+        sh.slots[self.rank] = t.clone()
+        sh.barrier.wait()
+        total = sh.slots[0].clone()
+        for r in range(1, self.world):
+            total += sh.slots[r]
+        sh.barrier.wait()
+        t.copy_(total)
+
+    def all_gather_cat(self, t, sizes):
+        sh = self.sh
+        sh.slots[self.rank] = t
+        sh.barrier.wait()
+        out = torch.cat([sh.slots[r] for r in range(self.world)], dim=1)
+        sh.barrier.wait()
+        return out
+
+
+# ------------------------------------------------------------------------------------------ context
+_TLS = threading.local()
+
+
+def current() -> Optional["SlabContext"]:
+    return getattr(_TLS, "ctx", None)
+
+
+class SlabContext:
+    """Active while a rank runs the model on its slab; consulted by ops.conv3d / group_norm / block_epilogue."""
+
+    def __init__(self, comm: Comm, depth: int, bounds: Optional[Sequence[Tuple[int, int]]] = None, align: int = 8):
+        self.comm = comm
+        self.depth = int(depth)                       # D of the whole (padded) volume at level 0
+        self.bounds = list(bounds) if bounds is not None else slab_bounds(depth, comm.world, align)
+        self.d0, self.d1 = self.bounds[comm.rank]
+        self.local_depth = self.d1 - self.d0
+        self.stats = {"halo_exchanges": 0, "halo_bytes": 0, "all_reduces": 0}
+
+    def __enter__(self):
+        self._prev = current()
+        _TLS.ctx = self
+        return self
+
+    def __exit__(self, *a):
+        _TLS.ctx = self._prev
+
+    # ---- geometry of a local tensor [1, Dl, H, W, C]: which level it is at, its offset in the whole volume
+    def _level(self, dl: int) -> int:
+        lvl, d = 0, self.local_depth
+        while d != dl:
+            if d < dl or d % 2:
+                raise ValueError(f"slab: a tensor with {dl} depth slices is not a level of a {self.local_depth}-slice slab")
+            d //= 2
+            lvl += 1
+        return lvl
+
+    def geometry(self, x: torch.Tensor):
+        """-> (first global depth slice, global depth) at x's resolution level."""
+        if x.shape[0] != 1:
+            raise ValueError("slab inference handles one volume (batch 1) at a time")
+        lvl = self._level(x.shape[1])
+        return self.d0 >> lvl, self.depth >> lvl
+
+    def global_voxels(self, x: torch.Tensor) -> int:
+        _, dg = self.geometry(x)
+        return dg * x.shape[2] * x.shape[3]
+
+    # ---- halo exchange
+    def with_halo(self, x: torch.Tensor, before: int, after: int) -> torch.Tensor:
+        """[1, Dl, H, W, C] -> [1, before + Dl + after, H, W, C] with the neighbours' boundary slices (zeros at the
+        ends of the volume)."""
+        c = self.comm
+        dl = x.shape[1]
+        pad = torch.empty((1, before + dl + after) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+        pad[:, before:before + dl].copy_(x)
+        has_prev, has_next = c.rank > 0, c.rank < c.world - 1
+        if before and not has_prev:
+            pad[:, :before].zero_()
+        if after and not has_next:
+            pad[:, before + dl:].zero_()
+        send_prev = x[:, :after] if (after and has_prev) else None             # my first slices = prev's "after" halo
+        send_next = x[:, dl - before:] if (before and has_next) else None      # my last slices = next's "before" halo
+        recv_prev = pad[:, :before] if (before and has_prev) else None
+        recv_next = pad[:, before + dl:] if (after and has_next) else None
+        c.exchange(send_prev, send_next, recv_prev, recv_next)
+        self.stats["halo_exchanges"] += 1
+        self.stats["halo_bytes"] += sum(t.numel() * 4 for t in (send_prev, send_next) if t is not None)
+        return pad
+
+    # ---- the three rerouted operations (forward only)
+    def conv3d(self, x, w, bias, stride, transposed, act, want_gap):
+        from . import ops
+        ops._check(x)
+        x = x.contiguous()
+        k = w.shape[0]
+        _, dl, H, W_, _ = x.shape
+        if k == 1:
+            before = after = 0
+        elif transposed:
+            before, after = 1, 0
+        elif stride == 2:
+            before, after = 0, 1
+        else:
+            before, after = 1, 1
+        xin = self.with_halo(x, before, after) if before + after else x
+        if transposed:
+            cout, od = w.shape[3], (2 * dl, 2 * H, 2 * W_)
+        else:
+            cout = w.shape[4]
+            od = (dl, H, W_) if stride == 1 else (dl // 2, H // 2, W_ // 2)
+        y = torch.empty((1,) + od + (cout,), dtype=_f32, device=x.device)
+        gap = torch.empty((1, cout), dtype=_f32, device=x.device) if want_gap else None
+        wp = None
+        if ops.USE_TC["on"] and not act and ops.tc_supported(w, stride, transposed, False):
+            wp = ops.pack_weights(w, False, stride, transposed)
+        ops._call("b3d_conv3d_fwd_halo", xin, w, bias, y, stride, int(transposed), int(act), before, after, gap, wp)
+        if gap is not None:
+            self.comm.all_reduce_sum(gap)
+            self.stats["all_reduces"] += 1
+        return y, None, gap
+
+    def group_norm(self, x, gamma, beta, groups, eps, relu):
+        from . import ops
+        ops._check(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        if C < groups:      # reference group_norm.py:51-59
+            raise ValueError(f"Number of groups ({groups}) cannot be more than the number of channels ({C}).")
+        if C % groups != 0:
+            raise ValueError(f"Number of groups ({groups}) must be a multiple of the number of channels ({C}).")
+        g0, dg = self.geometry(x)
+        per_slice = x.shape[2] * x.shape[3] * C
+        off, total = g0 * per_slice, dg * per_slice
+        stats = torch.empty((1, groups, 2), dtype=torch.float64, device=x.device)
+        ops._call("b3d_gn_stats_slab", x, stats, groups, off, total)
+        self.comm.all_reduce_sum(stats)
+        self.stats["all_reduces"] += 1
+        y = torch.empty_like(x)
+        ops._call("b3d_gn_apply_slab", x, stats, gamma, beta, y, groups, float(eps), int(relu), off, total)
+        return y
+
+
+# ------------------------------------------------------------------------------------------ drivers
+def slab_forward(model, x_local: torch.Tensor, ctx: SlabContext) -> torch.Tensor:
+    """This rank's slab of `model(x, training=False, inference=True)[0]` (test.py:133)."""
+    with torch.no_grad(), ctx:
+        return model(x_local, training=False, inference=True)[0]
+
+
+def sharded_inference(model, x: torch.Tensor, comm: Comm, gather: bool = True, align: Optional[int] = None):
+    """x: the WHOLE padded volume [1, D, H, W, C] (every rank holds it, as after loading a case from disk);
+    each rank computes its depth slab; returns the whole prediction (gather=True) or (slab, (d0, d1))."""
+    if align is None:
+        align = 2 ** (len(model.encoder.levels) - 1)
+    ctx = SlabContext(comm, x.shape[1], align=align)
+    y = slab_forward(model, x[:, ctx.d0:ctx.d1].contiguous(), ctx)
+    if not gather:
+        return y, (ctx.d0, ctx.d1)
+    return comm.all_gather_cat(y, [b - a for a, b in ctx.bounds])
+
+
+def run_virtual_ranks(model, x: torch.Tensor, world: int, align: Optional[int] = None):
+    """Single-device validation mode: `world` virtual ranks as threads sharing this device (ThreadComm).
+    Returns (whole prediction, per-rank communication statistics)."""
+    comms = ThreadComm.make(world)
+    if align is None:
+        align = 2 ** (len(model.encoder.levels) - 1)
+    bounds = slab_bounds(x.shape[1], world, align)
+    outs, stats, errs = [None] * world, [None] * world, []
+
+    def work(r):
+        try:
+            if x.is_cuda:
+                torch.cuda.set_device(x.device)
+            ctx = SlabContext(comms[r], x.shape[1], bounds)
+            outs[r] = slab_forward(model, x[:, bounds[r][0]:bounds[r][1]].contiguous(), ctx)
+            stats[r] = ctx.stats
+        except BaseException as e:     # noqa: BLE001 — release the other ranks, then re-raise in the caller
+            errs.append(e)
+            comms[r].sh.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errs:
+        real = [e for e in errs if not isinstance(e, threading.BrokenBarrierError)]
+        raise (real or errs)[0]
+    return torch.cat(outs, dim=1), stats

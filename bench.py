@@ -190,6 +190,38 @@ def measure_inference(b3d, torch, dev, model, reps=3):
             "gflop_per_forward": 1006.8, "note": "eager (no CUDA graph), 1 GPU; 8-flip TTA = 8 such forwards"}
 
 
+def measure_inference_sharded(b3d, torch, dist, dev, model, world, reps=3):
+    """BASELINE config 4 at N GPUs: the padded 160x192x160 volume cut into depth slabs, one per GPU, halo
+    exchange (NCCL P2P over NVLink) before every 3x3x3 conv, all-reduced GroupNorm chunk statistics and SE
+    pooling sums (3d-brain-tumor-segmentation_b200/slab.py).  Time = max over ranks of the slab forward."""
+    shape = (160, 192, 160)
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn((1,) + shape + (2,), generator=g)
+    x[:, 155:], x[:, :, 190:], x[:, :, :, 147:] = 0, 0, 0
+    x = x.to(dev)
+    comm = b3d.DistComm()
+    times, err = [], None
+    for i in range(reps + 1):
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y, (d0, d1) = b3d.sharded_inference(model, x, comm, gather=False)
+        e1.record(); e1.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if i:
+            times.append(float(ms))
+    with torch.no_grad():
+        whole = model(x, training=False, inference=True)[0][:, d0:d1]
+    e = ((y - whole).double().norm() / whole.double().norm()).reshape(1).float()
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    ms = statistics.median(times)
+    return {"shape_padded": list(shape), "n_gpus": world, "ms_per_forward": ms,
+            "mvoxel_per_s": 155 * 190 * 147 / ms / 1e3, "max_rel_l2_vs_unsharded": float(e),
+            "slabs": [b - a for a, b in b3d.slab_bounds(shape[0], world)],
+            "note": "depth-slab sharded, eager; halo exchange + GN/SE all-reduces over NCCL"}
+
+
 def run_b3d(args):
     import torch
     import torch.distributed as dist
@@ -256,6 +288,8 @@ def run_b3d(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e_val = world * args.steps / (ms_e2e / 1e3)
 
+    inf_sharded = measure_inference_sharded(b3d, torch, dist, dev, model, world) if world > 1 else None
+
     def finish():
         # NCCL communicators captured into CUDA graphs make destroy_process_group() hang at teardown:
         # synchronise, flush and leave without running destructors.
@@ -297,7 +331,7 @@ def run_b3d(args):
                     "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": int(step.launches_per_step * args.steps),
             "roofline": roof, "cpu_baseline": cpu,
-            "inference": measure_inference(b3d, torch, dev, model) if world == 1 else None}
+            "inference": measure_inference(b3d, torch, dev, model) if world == 1 else inf_sharded}
     print(json.dumps(line), flush=True)
     finish()
 

@@ -52,6 +52,13 @@ int b3d_abi_version(void);
 int b3d_conv3d_fwd(const DLTensor* x, const DLTensor* w, const DLTensor* bias /*nullable*/, DLTensor* y,
                    int stride, int transposed, int act, DLTensor* gn_stats, int groups, DLTensor* gap,
                    int accumulate, const DLTensor* wpacked, void* stream);
+/* Depth-slab form for whole-volume inference sharded along D (test.py:133 on the padded [1,160,192,160,C] volume,
+ * one slab per GPU): x carries halo_before / halo_after (0|1) extra depth slices — the neighbour slabs' boundary
+ * slices, zeros at the ends of the volume — and y holds only this slab's slices, so that the concatenation of
+ * the slabs' y equals the conv of the whole volume.  conv k3 s1: (1,1); conv k3 s2: (0,1); conv-transpose: (1,0). */
+int b3d_conv3d_fwd_halo(const DLTensor* x, const DLTensor* w, const DLTensor* bias /*nullable*/, DLTensor* y,
+                        int stride, int transposed, int act, int halo_before, int halo_after, DLTensor* gap,
+                        const DLTensor* wpacked, void* stream);
 /* data gradient (what tape.gradient computes for the layer input, train.py:151) */
 int b3d_conv3d_dgrad(const DLTensor* dy, const DLTensor* w, DLTensor* dx, int stride, int transposed,
                      int accumulate, const DLTensor* wpacked, void* stream);
@@ -81,6 +88,14 @@ int b3d_conv3d_pack_weights(const DLTensor* w, DLTensor* packed, int stride, int
 int b3d_gn_stats(const DLTensor* x, DLTensor* stats, int groups, void* stream);
 int b3d_gn_apply(const DLTensor* x, const DLTensor* stats, const DLTensor* gamma, const DLTensor* beta,
                  DLTensor* y, int groups, float eps, int relu, void* stream);
+/* depth-slab forms (batch 1): x = this rank's contiguous part [elem_offset, elem_offset + numel) of a sample of
+ * total_elems elements.  stats_slab writes the slab's PARTIAL (sum, sum^2) per chunk of the WHOLE sample (fp64
+ * [groups, 2]; the caller all-reduces over ranks); apply_slab normalises the slab with the reduced statistics. */
+int b3d_gn_stats_slab(const DLTensor* x, DLTensor* stats, int groups, long long elem_offset, long long total_elems,
+                      void* stream);
+int b3d_gn_apply_slab(const DLTensor* x, const DLTensor* stats, const DLTensor* gamma, const DLTensor* beta,
+                      DLTensor* y, int groups, float eps, int relu, long long elem_offset, long long total_elems,
+                      void* stream);
 int b3d_gn_bwd_reduce(const DLTensor* dy, const DLTensor* x, const DLTensor* stats, const DLTensor* gamma,
                       const DLTensor* beta, DLTensor* dgamma, DLTensor* dbeta, DLTensor* csum /*fp64 [B,G,2]*/,
                       int groups, float eps, int relu, void* stream);
