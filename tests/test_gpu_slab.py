@@ -126,8 +126,10 @@ def test_virtual_rank_slab_inference_equals_whole_volume(b3d, dev, world, shape,
             whole = model(x, training=False, inference=True)[0]
         got, stats = b3d.slab.run_virtual_ranks(model, x, world)
         assert got.shape == whole.shape
-        # same kernels, same per-voxel accumulation order; only the fp64-atomic statistics order differs
-        assert rel(got, whole) < 5e-5, rel(got, whole)
+        # same kernels, same per-voxel accumulation order; only the summation order of the statistics differs.
+        # With tf32 operands those last-bit differences move some conv inputs across a tf32 rounding boundary
+        # (2^-11), so the sharded result is compared at half the north_star per-layer TF32 tolerance.
+        assert rel(got, whole) < (1e-3 if tc else 5e-5), rel(got, whole)
         agree = (got.argmax(-1) == whole.argmax(-1)).float().mean()
         assert float(agree) >= 0.999
         # one exchange per 3x3x3 conv of the inference forward: 26 stride-1 (13 blocks x 2), 3 strided, 3 transposed
