@@ -26,6 +26,15 @@ def _new(shape, like, dtype=_f32):
     return torch.empty(shape, device=like.device, dtype=dtype)
 
 
+def _new_act(shape, like):
+    """Activation that may feed a 3x3x3 conv: under depth-slab inference it is allocated between two spare depth
+    slices so that the halo exchange happens in place (slab.SlabContext.new_activation)."""
+    ctx = _slab.current()
+    if ctx is not None and len(shape) == 5 and shape[0] == 1:
+        return ctx.new_activation(shape, like)
+    return torch.empty(tuple(shape), device=like.device, dtype=_f32)
+
+
 def _check(x: torch.Tensor, name="input"):
     if not x.is_cuda:
         raise RuntimeError(f"b3d: {name} must be a CUDA tensor — there is no CPU path")
@@ -189,7 +198,7 @@ class BlockEpilogueFn(Function):
         hidden, chse = _new((B, R), res), _new((B, F), res)
         inv = 1.0 / S
         _call("b3d_se_fc_fwd", gap_sum, w1, w2, hidden, chse, inv)
-        out = torch.empty_like(res)
+        out = _new_act(res.shape, res)
         has_gn = stats2 is not None
         wsp_v = wsp.reshape(F)
         _call("b3d_block_epilogue_fwd", res, h2, stats2, gamma2 if has_gn else None, beta2 if has_gn else None,
@@ -335,7 +344,7 @@ class ConcatFn(Function):
     @staticmethod
     def forward(ctx, *xs):
         C = [t.shape[-1] for t in xs]
-        out = _new(tuple(xs[0].shape[:-1]) + (sum(C),), xs[0])
+        out = _new_act(tuple(xs[0].shape[:-1]) + (sum(C),), xs[0])
         o = 0
         for t, c in zip(xs, C):
             _call("b3d_copy_channels", t.contiguous(), out[..., o:o + c], 0)

@@ -166,7 +166,8 @@ class SlabContext:
         self.bounds = list(bounds) if bounds is not None else slab_bounds(depth, comm.world, align)
         self.d0, self.d1 = self.bounds[comm.rank]
         self.local_depth = self.d1 - self.d0
-        self.stats = {"halo_exchanges": 0, "halo_bytes": 0, "all_reduces": 0}
+        self.stats = {"halo_exchanges": 0, "halo_bytes": 0, "all_reduces": 0, "halo_copies": 0}
+        self._padded = {}        # data_ptr of an activation -> the [1, Dl+2, H, W, C] buffer it is the interior of
 
     def __enter__(self):
         self._prev = current()
@@ -175,6 +176,16 @@ class SlabContext:
 
     def __exit__(self, *a):
         _TLS.ctx = self._prev
+        self._padded.clear()
+
+    def new_activation(self, shape, like: torch.Tensor) -> torch.Tensor:
+        """Allocate an activation [1, Dl, H, W, C] as the interior of a buffer with one spare depth slice on each
+        side, so that a later halo exchange needs no copy: the neighbours' slices are received in place."""
+        shape = tuple(int(v) for v in shape)
+        parent = torch.empty((1, shape[1] + 2) + shape[2:], dtype=like.dtype, device=like.device)
+        view = parent[:, 1:shape[1] + 1]
+        self._padded[view.data_ptr()] = parent
+        return view
 
     # ---- geometry of a local tensor [1, Dl, H, W, C]: which level it is at, its offset in the whole volume
     def _level(self, dl: int) -> int:
@@ -203,8 +214,13 @@ class SlabContext:
         ends of the volume)."""
         c = self.comm
         dl = x.shape[1]
-        pad = torch.empty((1, before + dl + after) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
-        pad[:, before:before + dl].copy_(x)
+        parent = self._padded.get(x.data_ptr())
+        if parent is not None and tuple(parent.shape) == (1, dl + 2) + tuple(x.shape[2:]) and x.is_contiguous():
+            pad = parent[:, 1 - before:1 + dl + after]          # in place: x already sits between its halo slices
+        else:
+            pad = torch.empty((1, before + dl + after) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+            pad[:, before:before + dl].copy_(x)
+            self.stats["halo_copies"] += 1
         has_prev, has_next = c.rank > 0, c.rank < c.world - 1
         if before and not has_prev:
             pad[:, :before].zero_()
@@ -267,7 +283,7 @@ class SlabContext:
         ops._call("b3d_gn_stats_slab", x, stats, groups, off, total)
         self.comm.all_reduce_sum(stats)
         self.stats["all_reduces"] += 1
-        y = torch.empty_like(x)
+        y = self.new_activation(x.shape, x)
         ops._call("b3d_gn_apply_slab", x, stats, gamma, beta, y, groups, float(eps), int(relu), off, total)
         return y
 
@@ -289,6 +305,45 @@ def sharded_inference(model, x: torch.Tensor, comm: Comm, gather: bool = True, a
     if not gather:
         return y, (ctx.d0, ctx.d1)
     return comm.all_gather_cat(y, [b - a for a, b in ctx.bounds])
+
+
+class GraphedInference:
+    """`model(x, training=False, inference=True)[0]` captured once into a CUDA graph for a fixed input shape and
+    replayed: the ~350 C-ABI calls of a forward become one launch.  With `comm` (a DistComm over NCCL) the input is
+    this rank's depth slab and the halo exchanges / small all-reduces are captured into the graph too."""
+
+    def __init__(self, model, x_example: torch.Tensor, comm: Optional[Comm] = None, depth: Optional[int] = None,
+                 warmup: int = 2):
+        self.x = x_example.clone()
+        self.model = model
+        self.ctx = None
+        if comm is not None:
+            align = 2 ** (len(model.encoder.levels) - 1)
+            self.ctx = SlabContext(comm, depth if depth is not None else x_example.shape[1] * comm.world, align=align)
+            if self.ctx.local_depth != self.x.shape[1]:
+                raise ValueError("GraphedInference: x_example must be this rank's slab")
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._run()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._run()
+
+    def _run(self):
+        if self.ctx is not None:
+            return slab_forward(self.model, self.x, self.ctx)
+        with torch.no_grad():
+            return self.model(self.x, training=False, inference=True)[0]
+
+    def __call__(self, x: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.out
 
 
 def run_virtual_ranks(model, x: torch.Tensor, world: int, align: Optional[int] = None):
