@@ -5,6 +5,7 @@
 namespace b3d {
 
 enum { CONV_S1 = 0, CONV_DOWN = 1, CONV_UP = 2 };
+enum { OP_TF32 = 0, OP_BF16 = 1, OP_F16 = 2 };   // operand type of the tcgen05 conv MMAs
 
 // gather form:  y[b,o,co] = act( sum_{t,ci} x[b,pos(o,t),ci] * w[tw(t)*wtap + ci*sw_in + co*sw_out] + bias[co] )
 struct ConvGeom {
@@ -38,10 +39,10 @@ bool tc_conv_supported(const ConvGeom& cg);
 int launch_conv_tc(const ConvGeom& cg, const float* x, const float* wpacked, const float* bias, float* y,
                    double* stats, float* gap, cudaStream_t s);
 size_t tc_packed_weight_elems(const ConvGeom& cg);
-int launch_pack_s2(const ConvGeom& cg, const float* w, float* wpacked, bool bf16, cudaStream_t s);
+int launch_pack_s2(const ConvGeom& cg, const float* w, float* wpacked, int op, cudaStream_t s);
 int launch_tc_pack_weights(const ConvGeom& cg, const float* w, float* wpacked, cudaStream_t s);
 
-bool tc_use_bf16(const ConvGeom& g);   // operand type the tcgen05 conv will use for this geometry/pass
+int tc_operand_type(const ConvGeom& g);   // OP_* the tcgen05 conv will use for this geometry / pass
 int tc_pick_n(int Cout);               // N tile of the tcgen05 conv for this output-channel count
 
 bool tc_wgrad_supported(const WgradGeom& wg);

@@ -16,6 +16,7 @@
 // holds the weight re-layout for the forward / data-gradient operand; the weight gradient of the family is the
 // KS = 2 case of conv_tc_wgrad.cu.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "conv_common.cuh"
@@ -26,10 +27,10 @@ namespace b3d {
 //   wp[ns][chunk][tap8][plane][n][j]   (T = 8 bf16 | 4 tf32 channels per cell, CK = 2T per chunk)
 // DOWN: K' = 8*Cg with k' = p*Cg + cg, N = Cp,   tap d (offsets 0,+1):  w[t = 2d+p]
 // UP  : K  = Cg,  N' = 8*Cp with n' = p*Cp + cp, tap k (offsets -1,0):  w[t = p + 2(1-k)]
-template <bool BF16>
+template <int OP>
 __global__ void pack_s2_kernel(const float* __restrict__ w, void* __restrict__ wp, int up, int Cg, int Cp, int N,
                                long long wtap, int sw_in, int sw_out) {
-  constexpr int T = BF16 ? 8 : 4;
+  constexpr int T = OP != OP_TF32 ? 8 : 4;
   const int K = up ? Cg : 8 * Cg, NT = up ? 8 * Cp : Cp;
   const long long total = 8LL * K * NT;
   const int nch = K / (2 * T);
@@ -54,8 +55,10 @@ __global__ void pack_s2_kernel(const float* __restrict__ w, void* __restrict__ w
     float v = 0.f;
     if (td <= 2 && th <= 2 && tw <= 2)
       v = w[(long long)((td * 3 + th) * 3 + tw) * wtap + (long long)cg * sw_in + (long long)cp * sw_out];
-    if (BF16) {
+    if (OP == OP_BF16) {
       reinterpret_cast<__nv_bfloat16*>(wp)[i] = __float2bfloat16_rn(v);
+    } else if (OP == OP_F16) {
+      reinterpret_cast<__half*>(wp)[i] = __float2half_rn(v);
     } else {
       uint32_t u;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
@@ -65,15 +68,17 @@ __global__ void pack_s2_kernel(const float* __restrict__ w, void* __restrict__ w
 }
 
 // packed weights of the equivalent 2x2x2 conv for a DOWN / UP geometry (64 * Cin * Cout elements)
-int launch_pack_s2(const ConvGeom& g, const float* w, float* wp, bool bf16, cudaStream_t s) {
+int launch_pack_s2(const ConvGeom& g, const float* w, float* wp, int op, cudaStream_t s) {
   const int up = g.mode == CONV_UP ? 1 : 0;
   const int K = up ? g.Cin : 8 * g.Cin, NT = up ? 8 * g.Cout : g.Cout;
   const long long total = 8LL * K * NT;
   const unsigned grid = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  if (bf16)
-    pack_s2_kernel<true><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out);
+  if (op == OP_BF16)
+    pack_s2_kernel<OP_BF16><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out);
+  else if (op == OP_F16)
+    pack_s2_kernel<OP_F16><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out);
   else
-    pack_s2_kernel<false><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out);
+    pack_s2_kernel<OP_TF32><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out);
   B3D_LAUNCH_CHECK("pack_s2");
   return B3D_OK;
 }

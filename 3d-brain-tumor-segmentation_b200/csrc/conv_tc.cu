@@ -21,6 +21,7 @@
 //     thread MMA issuer, warp 13 = weight producer (+TMEM alloc); 2 TMEM accumulator stages overlap
 //     epilogue(i) with MMA(i+1).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "conv_common.cuh"
@@ -29,11 +30,12 @@
 namespace b3d {
 
 // ------------------------------------------------------------------------------------------ config
-template <int N_, int TD_, int NW_, int KS_, int HB_, bool BF16_>
+template <int N_, int TD_, int NW_, int KS_, int HB_, int OP_>
 struct TcCfg {
   static constexpr int N = N_, TD = TD_, NW = NW_, KS = KS_;
   static constexpr int HB = HB_;                      // halo before the tile: tap k reads offset k - HB
-  static constexpr bool BF16 = BF16_;
+  static constexpr int OP = OP_;                      // operand type: OP_TF32 | OP_BF16 | OP_F16
+  static constexpr bool BF16 = OP_ != OP_TF32;        // 16-bit operands (bf16 or fp16): 8 channels per cell
   static constexpr int T = BF16 ? 8 : 4;              // channels per 16-byte cell
   static constexpr int CK = 2 * T;                    // channels per chunk = one MMA K step
   static constexpr int TAPS = KS * KS * KS;
@@ -98,6 +100,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // saturate: no inf operands
+  return r;
+}
+template <int OP>
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  return OP == OP_F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
 
 constexpr int kLoaderWarps = 8;
@@ -191,10 +203,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
             if (v < C::NVC) {
               uint4 o0, o1;
               if (C::BF16) {
-                o0.x = pack_bf16x2(r[u][0], r[u][1]); o0.y = pack_bf16x2(r[u][2], r[u][3]);
-                o0.z = pack_bf16x2(r[u][4], r[u][5]); o0.w = pack_bf16x2(r[u][6], r[u][7]);
-                o1.x = pack_bf16x2(r[u][8], r[u][9]); o1.y = pack_bf16x2(r[u][10], r[u][11]);
-                o1.z = pack_bf16x2(r[u][12], r[u][13]); o1.w = pack_bf16x2(r[u][14], r[u][15]);
+                o0.x = pack_half2<C::OP>(r[u][0], r[u][1]); o0.y = pack_half2<C::OP>(r[u][2], r[u][3]);
+                o0.z = pack_half2<C::OP>(r[u][4], r[u][5]); o0.w = pack_half2<C::OP>(r[u][6], r[u][7]);
+                o1.x = pack_half2<C::OP>(r[u][8], r[u][9]); o1.y = pack_half2<C::OP>(r[u][10], r[u][11]);
+                o1.z = pack_half2<C::OP>(r[u][12], r[u][13]); o1.w = pack_half2<C::OP>(r[u][14], r[u][15]);
               } else {
                 o0.x = __float_as_uint(r[u][0]); o0.y = __float_as_uint(r[u][1]);
                 o0.z = __float_as_uint(r[u][2]); o0.w = __float_as_uint(r[u][3]);
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
     // in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit ============
     const bool leader = elect_one();
     // instruction descriptor: D=f32, A=B=(bf16|tf32), K-major both, N, M=128
-    const uint32_t fmt = C::BF16 ? 1u : 2u;
+    const uint32_t fmt = C::OP == OP_F16 ? 0u : (C::OP == OP_BF16 ? 1u : 2u);   // kind::f16: 0 = f16, 1 = bf16
     const uint32_t idesc =
         (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C::N >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t halo_addr = smem_u32(halo), wst_addr = smem_u32(wst);
@@ -413,10 +425,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
 
 // ------------------------------------------------------------------------------------------ packing
 // wp[ns][c][tap][pl][n][j] = op( w[tw(tap)*wtap + (CK*c + T*pl + j)*sw_in + (ns*N+n)*sw_out] ),  op = bf16 | tf32
-template <bool BF16>
+template <int OP>
 __global__ void tc_pack_kernel(const float* __restrict__ w, void* __restrict__ wp, int taps, int Cin, int Cout, int N,
                                long long wtap, int sw_in, int sw_out, int flip) {
-  constexpr int T = BF16 ? 8 : 4;
+  constexpr int T = OP != OP_TF32 ? 8 : 4;
   const long long total = (long long)taps * Cin * Cout;
   const int nch = Cin / (2 * T);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -431,8 +443,10 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, void* __restrict__ w
     if (flip) tap = taps - 1 - tap;
     const int ci = 2 * T * c + T * pl + j, co = ns * N + n;
     const float v = w[(long long)tap * wtap + (long long)ci * sw_in + (long long)co * sw_out];
-    if (BF16) {
+    if (OP == OP_BF16) {
       reinterpret_cast<__nv_bfloat16*>(wp)[i] = __float2bfloat16_rn(v);
+    } else if (OP == OP_F16) {
+      reinterpret_cast<__half*>(wp)[i] = __float2half_rn(v);
     } else {
       uint32_t u;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
@@ -444,7 +458,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, void* __restrict__ w
 // ------------------------------------------------------------------------------------------ host
 // operand type of the conv MMAs, per pass: forward defaults to tf32 (north_star's 2e-3 per-layer tolerance,
 // argmax agreement), the data gradient to bf16 (1e-2); fp32 accumulation in TMEM either way
-static int g_fwd_bf16 = 0, g_bwd_bf16 = 1;
+static int g_fwd_op = OP_F16, g_bwd_op = OP_BF16;
 
 EncodeTiledFn tma_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -485,7 +499,10 @@ static TcProblem tc_problem(const ConvGeom& g) {
 }
 
 // g.bwd marks the backward pass (precision choice); chunks of CK channels must not straddle a parity block
-static bool use_bf16(const ConvGeom& g) { return (g.bwd ? g_bwd_bf16 : g_fwd_bf16) && g.Cin % 16 == 0; }
+static int operand_type(const ConvGeom& g) {
+  const int op = g.bwd ? g_bwd_op : g_fwd_op;
+  return (op != OP_TF32 && g.Cin % 16 == 0) ? op : OP_TF32;
+}
 
 bool tc_conv_supported(const ConvGeom& g) {
   if (g.mode == CONV_S1)
@@ -499,16 +516,17 @@ size_t tc_packed_weight_elems(const ConvGeom& g) {
 
 int launch_tc_pack_weights(const ConvGeom& g, const float* w, float* wp, cudaStream_t s) {
   B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "pack_weights: shape not on the tcgen05 path");
-  if (g.mode != CONV_S1) return launch_pack_s2(g, w, wp, use_bf16(g), s);
+  const int op = operand_type(g);
+  if (g.mode != CONV_S1) return launch_pack_s2(g, w, wp, op, s);
   const int taps = g.k * g.k * g.k;
   const long long total = (long long)taps * g.Cin * g.Cout;
   const unsigned grid = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  if (use_bf16(g))
-    tc_pack_kernel<true><<<grid, 256, 0, s>>>(w, wp, taps, g.Cin, g.Cout, pick_n(g.Cout), g.wtap, g.sw_in, g.sw_out,
-                                             g.flip);
-  else
-    tc_pack_kernel<false><<<grid, 256, 0, s>>>(w, wp, taps, g.Cin, g.Cout, pick_n(g.Cout), g.wtap, g.sw_in,
-                                              g.sw_out, g.flip);
+#define B3D_PACK(OPV) \
+  tc_pack_kernel<OPV><<<grid, 256, 0, s>>>(w, wp, taps, g.Cin, g.Cout, pick_n(g.Cout), g.wtap, g.sw_in, g.sw_out, g.flip)
+  if (op == OP_BF16) B3D_PACK(OP_BF16);
+  else if (op == OP_F16) B3D_PACK(OP_F16);
+  else B3D_PACK(OP_TF32);
+#undef B3D_PACK
   B3D_LAUNCH_CHECK("tc_pack");
   return B3D_OK;
 }
@@ -540,7 +558,7 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   return B3D_OK;
 }
 
-template <int KS, int HB, bool BF16>
+template <int KS, int HB, int BF16>
 static int dispatch_n(const ConvGeom& g, const TcProblem& q, const float* x, const float* wp, const float* bias,
                       float* y, double* stats, float* gap, cudaStream_t s) {
   const int n = pick_n(q.Cout);
@@ -565,10 +583,11 @@ int launch_conv_tc(const ConvGeom& g, const float* x, const float* wp, const flo
               B3D_ERR_LAYOUT, "tcgen05 conv: x must be 32-byte aligned with a channel pitch multiple of 8");
   const TcProblem q = tc_problem(g);
   B3D_REQUIRE(gap == nullptr || g.mode == CONV_S1, B3D_ERR_UNSUPPORTED, "tcgen05 conv: GAP only for stride 1");
-  const bool bf = use_bf16(g);
-#define B3D_TC_DISPATCH(KS, HB) \
-  return bf ? dispatch_n<KS, HB, true>(g, q, x, wp, bias, y, stats, gap, s) \
-            : dispatch_n<KS, HB, false>(g, q, x, wp, bias, y, stats, gap, s)
+  const int op = operand_type(g);
+#define B3D_TC_DISPATCH(KS, HB)                                                                   \
+  return op == OP_BF16 ? dispatch_n<KS, HB, OP_BF16>(g, q, x, wp, bias, y, stats, gap, s)          \
+         : op == OP_F16 ? dispatch_n<KS, HB, OP_F16>(g, q, x, wp, bias, y, stats, gap, s)          \
+                        : dispatch_n<KS, HB, OP_TF32>(g, q, x, wp, bias, y, stats, gap, s)
   if (q.ks == 3) { B3D_TC_DISPATCH(3, 1); }
   if (q.ks == 1) { B3D_TC_DISPATCH(1, 0); }
   if (q.hb == 1) { B3D_TC_DISPATCH(2, 1); }
@@ -576,16 +595,19 @@ int launch_conv_tc(const ConvGeom& g, const float* x, const float* wp, const flo
 #undef B3D_TC_DISPATCH
 }
 
-bool tc_use_bf16(const ConvGeom& g) { return use_bf16(g); }
+int tc_operand_type(const ConvGeom& g) { return operand_type(g); }
 int tc_pick_n(int Cout) { return pick_n(Cout); }
 
 }  // namespace b3d
 
-// operand type of the tcgen05 conv kernel: 1 = bf16, 0 = tf32, separately for the forward pass and for the
-// data gradient (selected by the `dgrad` flag of b3d_conv3d_pack_weights / by b3d_conv3d_dgrad)
-extern "C" int b3d_set_conv_precision(int fwd_bf16, int bwd_bf16) {
-  b3d::g_fwd_bf16 = fwd_bf16 ? 1 : 0;
-  b3d::g_bwd_bf16 = bwd_bf16 ? 1 : 0;
+// operand type of the tcgen05 conv MMAs (0 = tf32, 1 = bf16, 2 = fp16), separately for the forward pass and for
+// the data gradient; fp32 accumulation in TMEM either way.  fp16 has TF32's 11-bit significand at bf16's cost
+// (half the shared-memory bytes per MAC) and is used for the FORWARD operands, whose range is bounded by
+// GroupNorm; gradients keep bf16's exponent range.
+extern "C" int b3d_set_conv_precision(int fwd, int bwd) {
+  if (fwd < 0 || fwd > 2 || bwd < 0 || bwd > 2) { b3d::set_error("conv precision: 0 tf32, 1 bf16, 2 fp16"); return B3D_ERR_ARG; }
+  b3d::g_fwd_op = fwd;
+  b3d::g_bwd_op = bwd;
   return 0;
 }
-extern "C" int b3d_get_conv_precision(void) { return b3d::g_fwd_bf16 | (b3d::g_bwd_bf16 << 1); }
+extern "C" int b3d_get_conv_precision(void) { return b3d::g_fwd_op | (b3d::g_bwd_op << 4); }

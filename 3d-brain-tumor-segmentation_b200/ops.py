@@ -58,19 +58,25 @@ def pack_weights(w: torch.Tensor, dgrad: bool, stride: int = 1, transposed: bool
 USE_TC = {"on": True}
 
 
-def set_conv_precision(fwd: str = "tf32", bwd: str = "bf16"):
-    """Operand type of the tcgen05 conv MMAs ('tf32' | 'bf16', fp32 accumulation in TMEM either way), separately
-    for the forward pass and the data gradient.  Default: forward tf32 (north_star: per-layer <= 2e-3, argmax
-    agreement >= 99.9 %), backward bf16 (<= 1e-2).  The weight-gradient kernel always uses bf16 operands."""
+_PREC = {"tf32": 0, "bf16": 1, "fp16": 2}
+_PREC_INV = {v: k for k, v in _PREC.items()}
+
+
+def set_conv_precision(fwd: str = "fp16", bwd: str = "bf16"):
+    """Operand type of the tcgen05 conv MMAs ('tf32' | 'bf16' | 'fp16'; fp32 accumulation in TMEM either way),
+    separately for the forward pass and the data gradient.  Default: forward fp16 — TF32's 11-bit significand
+    (north_star: per-layer <= 2e-3, argmax agreement >= 99.9 %) at half the operand bytes; its narrow exponent
+    is safe for the forward operands (image, GroupNorm outputs, O(1) weights; conversion saturates) — and backward
+    bf16 (<= 1e-2; gradients need the exponent range).  The weight-gradient kernel always uses bf16 operands."""
     for v in (fwd, bwd):
-        if v not in ("bf16", "tf32"):
+        if v not in _PREC:
             raise ValueError(v)
-    lib.b3d_set_conv_precision(int(fwd == "bf16"), int(bwd == "bf16"))
+    lib.b3d_set_conv_precision(_PREC[fwd], _PREC[bwd])
 
 
 def get_conv_precision():
     v = lib.b3d_get_conv_precision()
-    return ("bf16" if v & 1 else "tf32", "bf16" if v & 2 else "tf32")
+    return (_PREC_INV[v & 15], _PREC_INV[v >> 4])
 
 
 class Conv3dFn(Function):

@@ -305,10 +305,9 @@ def run_b3d(args):
     pk, pk_src = peaks()
     conv_ms, conv_flops = measure_conv_roofline(b3d, torch, dev)
     ach = conv_flops / (conv_ms * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "conv3_tc_kernel (tcgen05 kind::tf32) dec.L0 conv1 128^3 32->16",
+    roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::f16, fp16 operands, fp32 accumulate) dec.L0 conv1 128^3 32->16",
             "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-            "peak_source": f"{pk_src} bf16 burst; the kernel computes in TF32 whose nominal peak is half of bf16 "
-                           f"(frac of TF32-nominal = {2 * ach / pk['bf16_tflops']:.3f})",
+            "peak_source": f"{pk_src} dense bf16 burst (cuBLAS 8192^3); 16-bit operands, same tensor-pipe rate",
             "ms_per_launch": conv_ms, "traffic": None}
     # CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
@@ -320,7 +319,7 @@ def run_b3d(args):
                          "(oracle/ref_model.py); TF 2.0-alpha not installable"}
     line = {"metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 forward / bf16 backward operands, fp32 accumulate and storage", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16 forward / bf16 backward operands, fp32 accumulate and storage", "data": "synthetic",
             "config": {"workload": "train_128cube_b1_default_model", "crop": list(CROP), "per_gpu_batch": 1,
                        "global_batch": world, "in_ch": 2, "out_ch": 3, "base_filters": 16,
                        "parallelism": f"dp{world}", "l2_flush": "working set (4.6 GiB of activations per step) "

@@ -50,22 +50,22 @@ CONV_CASES = [
 ]
 
 
-MODES = ["fp32", "tf32", "bf16"]      # CUDA-core fp32 | tcgen05 tf32 operands | tcgen05 bf16 operands
-MODE_TOL = {"fp32": TOL32, "tf32": TOL_TF32, "bf16": TOL_BF16}
+# CUDA-core fp32 | tcgen05 tf32 operands | tcgen05 bf16 operands | tcgen05 fp16 operands (TF32's significand)
+MODES = ["fp32", "tf32", "bf16", "fp16"]
+MODE_TOL = {"fp32": TOL32, "tf32": TOL_TF32, "bf16": TOL_BF16, "fp16": TOL_TF32}
 
 
 def set_mode(b3d, mode):
     b3d.ops.USE_TC["on"] = mode != "fp32"
-    if mode == "mixed":                    # the default: tf32 forward, bf16 backward
-        b3d.ops.set_conv_precision("tf32", "bf16")
-    else:
-        p = "tf32" if mode == "tf32" else "bf16"
-        b3d.ops.set_conv_precision(p, p)
+    if mode == "mixed":                    # the default: fp16 forward, bf16 backward
+        b3d.ops.set_conv_precision("fp16", "bf16")
+    elif mode != "fp32":
+        b3d.ops.set_conv_precision(mode, mode)
 
 
 def reset_mode(b3d):
     b3d.ops.USE_TC["on"] = True
-    b3d.ops.set_conv_precision("tf32", "bf16")
+    b3d.ops.set_conv_precision("fp16", "bf16")
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
@@ -199,7 +199,8 @@ def test_resnet_block(b3d, dev, cfg, mode):
     errs = {n: rel(t.grad, pr[pre + n].grad) for n, t in names.items()}
     print("resnet_block", cfg, mode, "y", rel(y, yr), "dx", rel(xd.grad, xr.grad),
           {k: f"{v:.1e}" for k, v in errs.items()})
-    ytol, gtol = {"fp32": (TOL32, 2e-4), "tf32": (TOL_TF32, 5e-2), "bf16": (TOL_BF16, 2e-1)}[mode]
+    ytol, gtol = {"fp32": (TOL32, 2e-4), "tf32": (TOL_TF32, 5e-2), "bf16": (TOL_BF16, 2e-1),
+                  "fp16": (TOL_TF32, 5e-2)}[mode]
     assert rel(y, yr) < ytol
     assert rel(xd.grad, xr.grad) < gtol
     for n, e in errs.items():
@@ -336,3 +337,4 @@ def test_tc_conv_vs_oracle_and_generic(b3d, dev, case):
             ref = torch.stack([ch.sum(-1), (ch ** 2).sum(-1)], dim=-1)
             assert rel(stats, ref) < max(tol, 1e-4), ("stats", tc)
     assert rel(res["tf32"][0], res["fp32"][0]) < TOL_TF32 and rel(res["bf16"][0], res["fp32"][0]) < TOL_BF16
+    assert rel(res["fp16"][0], res["fp32"][0]) < TOL_TF32

@@ -27,13 +27,13 @@ def build(b3d, dev, crop, p, **kw):
     return model, f
 
 
-MODES = ["fp32", "tf32", "mixed"]     # CUDA-core fp32 | tcgen05 tf32 | default: tf32 forward + bf16 backward
+MODES = ["fp32", "tf32", "mixed"]     # CUDA-core fp32 | tcgen05 tf32 | default: fp16 forward + bf16 backward
 
 
 def set_mode(b3d, mode):
     b3d.ops.USE_TC["on"] = mode != "fp32"
-    if mode == "mixed":                    # the default: tf32 forward, bf16 backward
-        b3d.ops.set_conv_precision("tf32", "bf16")
+    if mode == "mixed":                    # the default: fp16 forward (TF32's significand), bf16 backward
+        b3d.ops.set_conv_precision("fp16", "bf16")
     else:
         p = "tf32" if mode == "tf32" else "bf16"
         b3d.ops.set_conv_precision(p, p)
@@ -41,7 +41,7 @@ def set_mode(b3d, mode):
 
 def reset_mode(b3d):
     b3d.ops.USE_TC["on"] = True
-    b3d.ops.set_conv_precision("tf32", "bf16")
+    b3d.ops.set_conv_precision("fp16", "bf16")
 
 
 @pytest.mark.parametrize("mode", MODES)
