@@ -115,6 +115,8 @@ lib.b3d_conv3d_tc_supported.restype = _i
 lib.b3d_conv3d_packed_elems.argtypes = [_i] * 4
 lib.b3d_conv3d_wgrad_tc_supported.argtypes = [_i] * 5
 lib.b3d_conv3d_wgrad_tc_supported.restype = _i
+lib.b3d_conv3d_wgrad_plan.argtypes = [_i] * 5 + [C.POINTER(_ll), C.POINTER(_ll)]
+lib.b3d_conv3d_wgrad_plan.restype = _i
 lib.b3d_set_conv_precision.argtypes = [_i, _i]
 lib.b3d_get_conv_precision.restype = _i
 

@@ -36,7 +36,7 @@ __device__ __forceinline__ void moments(const double* __restrict__ stats, int ch
 }
 
 // grid: (segments per chunk, B*G).  Each CTA walks vox_per_cta voxels of one chunk.
-template <bool HAS_GN>
+template <bool HAS_GN, int NPL>
 __global__ void __launch_bounds__(kBT)
     block_epilogue_fwd_kernel(const float* __restrict__ res, const float* __restrict__ h2,
                               const double* __restrict__ stats, const float* __restrict__ gamma,
@@ -46,10 +46,10 @@ __global__ void __launch_bounds__(kBT)
   const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
   float mean = 0.f, rstd = 1.f;
   if (HAS_GN) moments(stats, chunk, 1.0 / ((double)gm.vpc * gm.F), eps, mean, rstd);
-  float4 w4[kMaxNPL], c4[kMaxNPL], ga4[kMaxNPL], be4[kMaxNPL];
+  float4 w4[NPL], c4[NPL], ga4[NPL], be4[NPL];
 #pragma unroll
-  for (int q = 0; q < kMaxNPL; ++q)
-    if (q < gm.npl) {
+  for (int q = 0; q < NPL; ++q)
+    {
       const int c = (q * T + lane) * 4;
       w4[q] = *reinterpret_cast<const float4*>(wsp + c);
       c4[q] = *reinterpret_cast<const float4*>(chse + (long long)b * gm.F + c);
@@ -73,11 +73,11 @@ __global__ void __launch_bounds__(kBT)
     const long long v = v0 + (long long)it * vstep + vl;
     const bool act = v < vend;
     const long long eo = (vbase + (act ? v : v0)) * gm.F;
-    float4 r[kMaxNPL], h[kMaxNPL];
+    float4 r[NPL], h[NPL];
     float dot = 0.f;
 #pragma unroll
-    for (int q = 0; q < kMaxNPL; ++q)
-      if (q < gm.npl) {
+    for (int q = 0; q < NPL; ++q)
+      {
         const int c = (q * T + lane) * 4;
         r[q] = ld_stream(reinterpret_cast<const float4*>(res + eo + c));
         h[q] = ld_stream(reinterpret_cast<const float4*>(h2 + eo + c));
@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(kBT)
     const float s = sigmoidf_(dot);
     if (act) {
 #pragma unroll
-      for (int q = 0; q < kMaxNPL; ++q)
-        if (q < gm.npl) {
+      for (int q = 0; q < NPL; ++q)
+        {
           const int c = (q * T + lane) * 4;
           float4 a = h[q];
           if (HAS_GN) {
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kBT)
 
 // Backward pass A — reductions.  Accumulates (atomics; outputs pre-zeroed by the host wrapper):
 //   dchse[b][c] += sum_v do*res ; dwsp[c] += sum_v dlogit*res ; dgamma_j, dbeta_j ; csum[chunk] = (S1,S2)
-template <bool HAS_GN>
+template <bool HAS_GN, int NPL>
 __global__ void __launch_bounds__(kBT)
     block_epilogue_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ res,
                                      const float* __restrict__ h2, const double* __restrict__ stats,
@@ -125,13 +125,13 @@ __global__ void __launch_bounds__(kBT)
   const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
   float mean = 0.f, rstd = 1.f;
   if (HAS_GN) moments(stats, chunk, 1.0 / ((double)gm.vpc * gm.F), eps, mean, rstd);
-  float4 w4[kMaxNPL], ga4[kMaxNPL], be4[kMaxNPL];
-  float acc_c[kMaxNPL][4], acc_w[kMaxNPL][4], acc_g[kMaxNPL][4], acc_b[kMaxNPL][4];
+  float4 w4[NPL], ga4[NPL], be4[NPL];
+  float acc_c[NPL][4], acc_w[NPL][4], acc_g[NPL][4], acc_b[NPL][4];
 #pragma unroll
-  for (int q = 0; q < kMaxNPL; ++q) {
+  for (int q = 0; q < NPL; ++q) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc_c[q][i] = acc_w[q][i] = acc_g[q][i] = acc_b[q][i] = 0.f;
-    if (q < gm.npl) {
+    {
       const int c = (q * T + lane) * 4;
       w4[q] = *reinterpret_cast<const float4*>(wsp + c);
       if (HAS_GN) {
@@ -156,11 +156,11 @@ __global__ void __launch_bounds__(kBT)
     const long long v = v0 + (long long)it * vstep + vl;
     const bool act = v < vend;
     const long long eo = (vbase + (act ? v : v0)) * gm.F;
-    float4 r[kMaxNPL], d[kMaxNPL];
+    float4 r[NPL], d[NPL];
     float dot = 0.f, ds = 0.f;
 #pragma unroll
-    for (int q = 0; q < kMaxNPL; ++q)
-      if (q < gm.npl) {
+    for (int q = 0; q < NPL; ++q)
+      {
         const int c = (q * T + lane) * 4;
         r[q] = ld_stream(reinterpret_cast<const float4*>(res + eo + c));
         d[q] = ld_stream(reinterpret_cast<const float4*>(dout + eo + c));
@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(kBT)
     const float s = sigmoidf_(dot);
     const float dl = ds * s * (1.f - s);
 #pragma unroll
-    for (int q = 0; q < kMaxNPL; ++q)
-      if (q < gm.npl) {
+    for (int q = 0; q < NPL; ++q)
+      {
         const float rr[4] = {r[q].x, r[q].y, r[q].z, r[q].w};
         const float dd[4] = {d[q].x, d[q].y, d[q].z, d[q].w};
 #pragma unroll
@@ -201,20 +201,33 @@ __global__ void __launch_bounds__(kBT)
         }
       }
   }
+  // lanes of a warp with equal (lane % T) hold the same channels: butterfly over the voxel sub-index first, so that
+  // only T lanes per warp touch shared memory
+  const int wl = threadIdx.x & 31;
 #pragma unroll
-  for (int q = 0; q < kMaxNPL; ++q)
-    if (q < gm.npl) {
-      const int c = (q * T + lane) * 4;
+  for (int q = 0; q < NPL; ++q) {
+    const int c = (q * T + lane) * 4;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        atomicAdd(&sm[0 * gm.F + c + i], acc_c[q][i]);
-        atomicAdd(&sm[1 * gm.F + c + i], acc_w[q][i]);
+    for (int i = 0; i < 4; ++i) {
+      float a0 = acc_c[q][i], a1 = acc_w[q][i], a2 = acc_g[q][i], a3 = acc_b[q][i];
+      for (int o = 16; o >= T; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
         if (HAS_GN) {
-          atomicAdd(&sm[2 * gm.F + c + i], acc_g[q][i]);
-          atomicAdd(&sm[3 * gm.F + c + i], acc_b[q][i]);
+          a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+          a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+        }
+      }
+      if (wl < T) {
+        atomicAdd(&sm[0 * gm.F + c + i], a0);
+        atomicAdd(&sm[1 * gm.F + c + i], a1);
+        if (HAS_GN) {
+          atomicAdd(&sm[2 * gm.F + c + i], a2);
+          atomicAdd(&sm[3 * gm.F + c + i], a3);
         }
       }
     }
+  }
   __shared__ double red[64];
   double dd2[2] = {(double)s1, (double)s2};
   block_sum<2, double>(dd2, red);
@@ -234,7 +247,7 @@ __global__ void __launch_bounds__(kBT)
 }
 
 // Backward pass B — elementwise:  dres, dh2
-template <bool HAS_GN>
+template <bool HAS_GN, int NPL>
 __global__ void __launch_bounds__(kBT)
     block_epilogue_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ res,
                                     const float* __restrict__ h2, const double* __restrict__ stats,
@@ -251,10 +264,10 @@ __global__ void __launch_bounds__(kBT)
     m1 = (float)(csum[2 * chunk] / L);
     m2 = (float)(csum[2 * chunk + 1] / L);
   }
-  float4 w4[kMaxNPL], c4[kMaxNPL], g4[kMaxNPL], ga4[kMaxNPL], be4[kMaxNPL];
+  float4 w4[NPL], c4[NPL], g4[NPL], ga4[NPL], be4[NPL];
 #pragma unroll
-  for (int q = 0; q < kMaxNPL; ++q)
-    if (q < gm.npl) {
+  for (int q = 0; q < NPL; ++q)
+    {
       const int c = (q * T + lane) * 4;
       w4[q] = *reinterpret_cast<const float4*>(wsp + c);
       c4[q] = *reinterpret_cast<const float4*>(chse + (long long)b * gm.F + c);
@@ -279,11 +292,11 @@ __global__ void __launch_bounds__(kBT)
     const long long v = v0 + (long long)it * vstep + vl;
     const bool act = v < vend;
     const long long eo = (vbase + (act ? v : v0)) * gm.F;
-    float4 r[kMaxNPL], d[kMaxNPL];
+    float4 r[NPL], d[NPL];
     float dot = 0.f, ds = 0.f;
 #pragma unroll
-    for (int q = 0; q < kMaxNPL; ++q)
-      if (q < gm.npl) {
+    for (int q = 0; q < NPL; ++q)
+      {
         const int c = (q * T + lane) * 4;
         r[q] = ld_stream(reinterpret_cast<const float4*>(res + eo + c));
         d[q] = ld_stream(reinterpret_cast<const float4*>(dout + eo + c));
@@ -296,8 +309,8 @@ __global__ void __launch_bounds__(kBT)
     const float dl = ds * s * (1.f - s);
     if (act) {
 #pragma unroll
-      for (int q = 0; q < kMaxNPL; ++q)
-        if (q < gm.npl) {
+      for (int q = 0; q < NPL; ++q)
+        {
           const int c = (q * T + lane) * 4;
           float4 o;
           o.x = d[q].x * (s + c4[q].x) + dl * w4[q].x + g4[q].x;
@@ -432,6 +445,17 @@ static inline dim3 block_grid(const BlockGeom& gm, int nchunks) {
   return dim3((unsigned)((gm.vpc + gm.vox_per_cta - 1) / gm.vox_per_cta), (unsigned)nchunks, 1);
 }
 
+// instantiate on the exact number of float4 per lane (registers: the accumulator arrays are sized by it)
+#define B3D_NPL(npl, launch)                   \
+  do {                                         \
+    switch (npl) {                             \
+      case 1: { constexpr int kN = 1; launch; } break; \
+      case 2: { constexpr int kN = 2; launch; } break; \
+      case 3: { constexpr int kN = 3; launch; } break; \
+      default: { constexpr int kN = 4; launch; } break; \
+    }                                          \
+  } while (0)
+
 static int vecF(const DLTensor* t, long long n, const char* name, TView* v) {
   B3D_TRY(view(t, DT_F32, -1, false, name, v));
   B3D_REQUIRE(v->numel == n, B3D_ERR_SHAPE, "%s: expected %lld values, got %lld", name, n, (long long)v->numel);
@@ -500,13 +524,13 @@ extern "C" int b3d_block_epilogue_fwd(const DLTensor* res_, const DLTensor* h2_,
     B3D_REQUIRE(st.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats: wrong size");
     B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
     B3D_TRY(vecF(beta_, gm.F, "beta", &be));
-    block_epilogue_fwd_kernel<true><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+    B3D_NPL(gm.npl, (block_epilogue_fwd_kernel<true, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
         (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
-        (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps);
+        (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps)));
   } else {
-    block_epilogue_fwd_kernel<false><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+    B3D_NPL(gm.npl, (block_epilogue_fwd_kernel<false, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
         (const float*)res.p, (const float*)h2.p, nullptr, nullptr, nullptr, (const float*)wsp.p,
-        (const float*)ch.p, (float*)out.p, gm, eps);
+        (const float*)ch.p, (float*)out.p, gm, eps)));
   }
   B3D_LAUNCH_CHECK("block_epilogue_fwd");
   return B3D_OK;
@@ -544,14 +568,14 @@ extern "C" int b3d_block_epilogue_bwd_reduce(const DLTensor* dout_, const DLTens
     B3D_TRY(cuda_ok(cudaMemsetAsync(cs.p, 0, sizeof(double) * 2 * nchunks, s), "memset"));
     B3D_TRY(cuda_ok(cudaMemsetAsync(dga.p, 0, sizeof(float) * gm.F, s), "memset"));
     B3D_TRY(cuda_ok(cudaMemsetAsync(dbe.p, 0, sizeof(float) * gm.F, s), "memset"));
-    block_epilogue_bwd_reduce_kernel<true><<<block_grid(gm, nchunks), kBT, smem, s>>>(
+    B3D_NPL(gm.npl, (block_epilogue_bwd_reduce_kernel<true, kN><<<block_grid(gm, nchunks), kBT, smem, s>>>(
         (const float*)dout.p, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p,
         (const float*)be.p, (const float*)wsp.p, (float*)dch.p, (float*)dws.p, (float*)dga.p, (float*)dbe.p,
-        (double*)cs.p, gm, eps);
+        (double*)cs.p, gm, eps)));
   } else {
-    block_epilogue_bwd_reduce_kernel<false><<<block_grid(gm, nchunks), kBT, smem, s>>>(
+    B3D_NPL(gm.npl, (block_epilogue_bwd_reduce_kernel<false, kN><<<block_grid(gm, nchunks), kBT, smem, s>>>(
         (const float*)dout.p, (const float*)res.p, nullptr, nullptr, nullptr, nullptr, (const float*)wsp.p,
-        (float*)dch.p, (float*)dws.p, nullptr, nullptr, nullptr, gm, eps);
+        (float*)dch.p, (float*)dws.p, nullptr, nullptr, nullptr, gm, eps)));
   }
   B3D_LAUNCH_CHECK("block_epilogue_bwd_reduce");
   return B3D_OK;
@@ -583,14 +607,14 @@ extern "C" int b3d_block_epilogue_bwd_apply(const DLTensor* dout_, const DLTenso
     B3D_REQUIRE(st.numel == 2LL * nchunks && cs.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats/csum: wrong size");
     B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
     B3D_TRY(vecF(beta_, gm.F, "beta", &be));
-    block_epilogue_bwd_apply_kernel<true><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+    B3D_NPL(gm.npl, (block_epilogue_bwd_apply_kernel<true, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
         (const float*)dout.p, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p,
         (const float*)be.p, (const float*)wsp.p, (const float*)ch.p, (const float*)dg.p, (const double*)cs.p,
-        (float*)dres.p, (float*)dh2.p, gm, eps);
+        (float*)dres.p, (float*)dh2.p, gm, eps)));
   } else {
-    block_epilogue_bwd_apply_kernel<false><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+    B3D_NPL(gm.npl, (block_epilogue_bwd_apply_kernel<false, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
         (const float*)dout.p, (const float*)res.p, nullptr, nullptr, nullptr, nullptr, (const float*)wsp.p,
-        (const float*)ch.p, (const float*)dg.p, nullptr, (float*)dres.p, nullptr, gm, eps);
+        (const float*)ch.p, (const float*)dg.p, nullptr, (float*)dres.p, nullptr, gm, eps)));
   }
   B3D_LAUNCH_CHECK("block_epilogue_bwd_apply");
   return B3D_OK;

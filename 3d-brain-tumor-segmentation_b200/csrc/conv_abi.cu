@@ -187,6 +187,32 @@ extern "C" int b3d_conv3d_dgrad(const DLTensor* dy_, const DLTensor* w_, DLTenso
   return run(g, dy, w, nullptr, dx, nullptr, 1, nullptr, wpacked_, (cudaStream_t)stream);
 }
 
+namespace {
+// How the tcgen05 weight gradient of a layer is fed: bf16 channels per voxel of the two scratch copies.
+//   kind 0: not on the tensor cores (fp32 CUDA-core kernel)
+//   kind 1: plain copies (stride 2: the big tensor in space-to-depth order)
+//   kind 2: narrow input  (Cin  < 8): x  tap-stacked to pad8(k^3*Cin)  channels, dy plain   (conv_tc_wgrad.cu)
+//   kind 3: narrow output (Cout < 8): dy tap-stacked to pad8(k^3*Cout) channels, x  plain
+struct WgradPlan { int kind; long long x_ch, dy_ch; };
+WgradPlan wgrad_plan(int k, int stride, int transposed, int cin, int cout) {
+  WgradPlan p = {0, 0, 0};
+  const int taps = k * k * k;
+  auto pad8 = [](int v) { return (v + 7) / 8 * 8; };
+  if (stride == 1 && !transposed && (k == 1 || k == 3)) {
+    if (cin < 8 && cout % 16 == 0 && cout >= 16) { p.kind = 2; p.x_ch = pad8(taps * cin); p.dy_ch = cout; return p; }
+    if (cout < 8 && cin % 16 == 0 && cin >= 16) { p.kind = 3; p.x_ch = cin; p.dy_ch = pad8(taps * cout); return p; }
+  }
+  if (transposed && stride != 2) return p;
+  WgradGeom wg;
+  memset(&wg, 0, sizeof(wg));
+  wg.k = k; wg.s = stride;
+  wg.nA = transposed ? cout : cin; wg.nB = transposed ? cin : cout;
+  wg.bigp = wg.nA; wg.smallp = wg.nB;
+  if (tc_wgrad_supported(wg)) { p.kind = 1; p.x_ch = cin; p.dy_ch = cout; }
+  return p;
+}
+}  // namespace
+
 extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTensor* dw_, DLTensor* dbias_,
                                 int stride, int transposed, const DLTensor* x_bf16_, const DLTensor* dy_bf16_,
                                 void* stream) {
@@ -208,57 +234,77 @@ extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTenso
   wg.Ds = (int)sml.shape[1]; wg.Hs = (int)sml.shape[2]; wg.Ws = (int)sml.shape[3]; wg.nB = (int)sml.shape[4];
   wg.k = k; wg.s = stride; wg.pad = stride == 1 ? k / 2 : 0;
   wg.bigp = big.pitch; wg.smallp = sml.pitch;
+  float* db = nullptr;
+  if (dbias_ != nullptr) {
+    TView dbv;
+    B3D_TRY(view(dbias_, DT_F32, 1, false, "dbias", &dbv));
+    B3D_REQUIRE(dbv.numel == dy.shape[4], B3D_ERR_SHAPE, "dbias: expected %lld values", (long long)dy.shape[4]);
+    db = (float*)dbv.p;
+  }
   bool bias_done = false;
   if (x_bf16_ != nullptr && dy_bf16_ != nullptr) {
-    // tensor-core path: bf16 copies (caller-allocated, same element counts, contiguous) are filled here; for the
-    // stride-2 family the copy of the BIG tensor is written in space-to-depth order [B, D/2, H/2, W/2, 8*C]
+    // tensor-core path: the bf16 scratch copies (caller-allocated, sizes from b3d_conv3d_wgrad_plan) are filled here
+    const int cin = (int)x.shape[4], cout = (int)dy.shape[4];
+    const WgradPlan pl = wgrad_plan(k, stride, transposed, cin, cout);
+    B3D_REQUIRE(pl.kind != 0, B3D_ERR_UNSUPPORTED, "wgrad: shape not on the tcgen05 path");
     TView xb, yb;
-    B3D_TRY(view(x_bf16_, DT_BF16, 5, false, "x_bf16", &xb));
-    B3D_TRY(view(dy_bf16_, DT_BF16, 5, false, "dy_bf16", &yb));
-    B3D_REQUIRE(xb.numel == x.numel && yb.numel == dy.numel, B3D_ERR_SHAPE, "wgrad: bf16 buffer shapes");
-    B3D_REQUIRE(x.pitch == x.shape[4] && dy.pitch == dy.shape[4], B3D_ERR_LAYOUT, "wgrad (tcgen05): contiguous inputs");
-    B3D_REQUIRE(tc_wgrad_supported(wg), B3D_ERR_UNSUPPORTED, "wgrad: shape not on the tcgen05 path");
-    float* db = nullptr;
-    if (dbias_ != nullptr) {
-      TView dbv;
-      B3D_TRY(view(dbias_, DT_F32, 1, false, "dbias", &dbv));
-      B3D_REQUIRE(dbv.numel == dy.shape[4], B3D_ERR_SHAPE, "dbias: expected %lld values", (long long)dy.shape[4]);
-      db = (float*)dbv.p;
-      bias_done = true;
+    B3D_TRY(view(x_bf16_, DT_BF16, -1, false, "x_bf16", &xb));
+    B3D_TRY(view(dy_bf16_, DT_BF16, -1, false, "dy_bf16", &yb));
+    const long long nvx = x.numel / cin, nvy = dy.numel / cout;
+    B3D_REQUIRE(xb.numel == nvx * pl.x_ch && yb.numel == nvy * pl.dy_ch, B3D_ERR_SHAPE,
+                "wgrad: bf16 scratch sizes (expected %lld and %lld elements)", nvx * pl.x_ch, nvy * pl.dy_ch);
+    if (pl.kind == 1) {
+      B3D_REQUIRE(x.pitch == x.shape[4] && dy.pitch == dy.shape[4], B3D_ERR_LAYOUT, "wgrad (tcgen05): contiguous inputs");
+      const TView& bigb = transposed ? yb : xb;
+      const TView& smlb = transposed ? xb : yb;
+      float* db_big = transposed ? db : nullptr;     // the bias gradient = column sums of dy, whichever role it has
+      float* db_sml = transposed ? nullptr : db;
+      if (stride == 2)
+        B3D_TRY(launch_cast_bf16_s2d((const float*)big.p, bigb.p, wg.B, wg.Ds, wg.Hs, wg.Ws, wg.nA, big.pitch, db_big, s));
+      else
+        B3D_TRY(launch_cast_bf16((const float*)big.p, bigb.p, big.numel / big.shape[4], wg.nA, db_big, s));
+      B3D_TRY(launch_cast_bf16((const float*)sml.p, smlb.p, sml.numel / sml.shape[4], wg.nB, db_sml, s));
+      B3D_TRY(launch_conv_wgrad_tc(wg, bigb.p, smlb.p, (float*)dw.p, s));
+      bias_done = db != nullptr;
+    } else {
+      // narrow layer: all taps of the narrow tensor stacked into the M dimension of a single 1x1x1-style GEMM
+      const bool nx = pl.kind == 2;
+      const TView& nar = nx ? x : dy;       // stacked (narrow) tensor
+      const TView& wid = nx ? dy : x;       // plain (wide) tensor
+      B3D_REQUIRE(wid.pitch == wid.shape[4], B3D_ERR_LAYOUT, "wgrad (tcgen05): contiguous inputs");
+      const int cn = (int)nar.shape[4], nA = (int)(nx ? pl.x_ch : pl.dy_ch);
+      B3D_TRY(launch_cast_stack_bf16((const float*)nar.p, (nx ? xb : yb).p, wg.B, wg.Db, wg.Hb, wg.Wb, cn, nar.pitch, k,
+                                     nx ? 1 : -1, nA, s));
+      B3D_TRY(launch_cast_bf16((const float*)wid.p, (nx ? yb : xb).p, wid.numel / wid.shape[4], (int)wid.shape[4],
+                               nx ? db : nullptr, s));
+      WgradGeom w1 = wg;
+      w1.k = 1; w1.s = 1; w1.pad = 0; w1.nA = nA; w1.nB = (int)wid.shape[4]; w1.bigp = nA; w1.smallp = w1.nB;
+      B3D_TRY(launch_conv_wgrad_tc(w1, (nx ? xb : yb).p, (nx ? yb : xb).p, (float*)dw.p, s, k * k * k * cn,
+                                   nx ? 0 : cn, dw.numel));
+      bias_done = nx && db != nullptr;
     }
-    const TView& bigb = transposed ? yb : xb;
-    const TView& smlb = transposed ? xb : yb;
-    float* db_big = transposed ? db : nullptr;     // the bias gradient = column sums of dy, whichever role dy has
-    float* db_sml = transposed ? nullptr : db;
-    if (stride == 2)
-      B3D_TRY(launch_cast_bf16_s2d((const float*)big.p, bigb.p, wg.B, wg.Ds, wg.Hs, wg.Ws, wg.nA, big.pitch, db_big, s));
-    else
-      B3D_TRY(launch_cast_bf16((const float*)big.p, bigb.p, big.numel / big.shape[4], wg.nA, db_big, s));
-    B3D_TRY(launch_cast_bf16((const float*)sml.p, smlb.p, sml.numel / sml.shape[4], wg.nB, db_sml, s));
-    B3D_TRY(launch_conv_wgrad_tc(wg, bigb.p, smlb.p, (float*)dw.p, s));
   } else {
     B3D_TRY(launch_conv_wgrad(wg, (const float*)big.p, (const float*)sml.p, (float*)dw.p, s));
   }
-  if (dbias_ != nullptr && !bias_done) {
-    TView db;
-    B3D_TRY(view(dbias_, DT_F32, 1, false, "dbias", &db));
-    B3D_REQUIRE(db.numel == dy.shape[4], B3D_ERR_SHAPE, "dbias: expected %lld values", (long long)dy.shape[4]);
-    B3D_TRY(launch_colsum((const float*)dy.p, (float*)db.p, dy.numel / dy.shape[4], (int)dy.shape[4], dy.pitch,
-                          true, s));
-  }
+  if (db != nullptr && !bias_done)
+    B3D_TRY(launch_colsum((const float*)dy.p, db, dy.numel / dy.shape[4], (int)dy.shape[4], dy.pitch, true, s));
   return B3D_OK;
+}
+
+// bf16 scratch the tcgen05 weight gradient of a layer needs: channels per voxel of the x / dy copies (both 0 when
+// the layer's weight gradient runs on the CUDA cores).  Returns the plan kind (see WgradPlan).
+extern "C" int b3d_conv3d_wgrad_plan(int k, int stride, int transposed, int cin, int cout, long long* x_ch,
+                                     long long* dy_ch) {
+  const WgradPlan p = wgrad_plan(k, stride, transposed, cin, cout);
+  if (x_ch != nullptr) *x_ch = p.x_ch;
+  if (dy_ch != nullptr) *dy_ch = p.dy_ch;
+  return p.kind;
 }
 
 // 1 when the tcgen05 weight-gradient kernel handles a layer with these LAYER channel counts (k in {1,3} stride 1;
 // k3 stride 2 conv / conv-transpose)
 extern "C" int b3d_conv3d_wgrad_tc_supported(int k, int stride, int transposed, int cin, int cout) {
-  if (transposed && stride != 2) return 0;
-  WgradGeom wg;
-  memset(&wg, 0, sizeof(wg));
-  wg.k = k; wg.s = stride;
-  wg.nA = transposed ? cout : cin; wg.nB = transposed ? cin : cout;
-  wg.bigp = wg.nA; wg.smallp = wg.nB;
-  return tc_wgrad_supported(wg) ? 1 : 0;
+  return wgrad_plan(k, stride, transposed, cin, cout).kind != 0 ? 1 : 0;
 }
 
 namespace {

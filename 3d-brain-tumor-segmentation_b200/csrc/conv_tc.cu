@@ -75,6 +75,9 @@ struct TcParams {
   // slab halos (whole-volume inference sharded along D): x holds Din depth slices (its own units: fine for s2d) and
   // logical slice i lives at buffer slice i + doff; slices outside [0, Din) read as zero
   int Din, doff;
+  // channel padding: Cin / Cout above are the padded (virtual) counts the MMAs run on; the tensors hold cin_real /
+  // cout_real channels (first conv: 2 input channels; output convs: 2-3 classes).  act: 1 = sigmoid epilogue.
+  int cin_real, cout_real, act;
 };
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -189,7 +192,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
             const bool ok = v < C::NVC && bd >= 0 && bd < prm.Din && gh >= 0 && gh < prm.H && gw >= 0 && gw < prm.W;
 #pragma unroll
             for (int i = 0; i < kRegs; ++i) r[u][i] = 0.f;
-            if (ok) {
+            if (ok && prm.cin_real < C::CK) {
+              // narrow input (fewer real channels than one K step): scalar loads, zero padding stays in r[]
+              const float* src = xc + (((long long)bd * prm.H + gh) * prm.W + gw) * prm.xp;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < prm.cin_real) r[u][i] = __ldg(src + i);
+            } else if (ok) {
               const float* src =
                   prm.s2d ? xc + (((long long)bd * (2 * prm.H) + (2 * gh + sp_h)) * (2 * prm.W) + (2 * gw + sp_w)) * prm.xp
                           : xc + (((long long)bd * prm.H + gh) * prm.W + gw) * prm.xp;
@@ -313,7 +322,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float a = warp_sum(gsum[j][i]);
-          if (lane == 0) atomicAdd(&prm.gap[(long long)bb * prm.Cout + nsp * C::N + j * 16 + i], a);
+          if (lane == 0 && nsp * C::N + j * 16 + i < prm.cout_real)
+            atomicAdd(&prm.gap[(long long)bb * prm.cout_real + nsp * C::N + j * 16 + i], a);
           gsum[j][i] = 0.f;
         }
     };
@@ -339,9 +349,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
           ycol -= par * prm.Csub;
           ep_d = par >> 2; ep_h = (par >> 1) & 1; ep_w = par & 1;
         }
+        const int ncol = min(16, prm.cout_real - (nsp * C::N + j * 16));    // real output channels in this block
+        if (ncol <= 0) continue;
         float bv[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) bv[i] = prm.bias != nullptr ? __ldg(prm.bias + ycol + i) : 0.f;
+        for (int i = 0; i < 16; ++i) bv[i] = (prm.bias != nullptr && i < ncol) ? __ldg(prm.bias + ycol + i) : 0.f;
         float (&gs)[16] = gsum[kGapPersist ? j : 0];
 #pragma unroll 1
         for (int p = 0; p < C::P; ++p) {
@@ -364,12 +376,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
           }
           float v[16];
           tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + p * C::N + j * 16, v);
-          if (valid) {
+          if (valid && ncol < 16) {
+            // narrow output (Cout < 16: the 2-3 channel output convs): scalar stores, optional sigmoid
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < ncol) {
+                float o = v[i] + bv[i];
+                if (prm.act == 1) o = 1.f / (1.f + expf(-o));
+                if (prm.accumulate) o += yp[i];
+                yp[i] = o;
+                s0 += o;
+                s1 += o * o;
+                gs[i] += o;
+              }
+          } else if (valid) {
             float4* dst = reinterpret_cast<float4*>(yp);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float4 o = make_float4(v[4 * i] + bv[4 * i], v[4 * i + 1] + bv[4 * i + 1], v[4 * i + 2] + bv[4 * i + 2],
                                      v[4 * i + 3] + bv[4 * i + 3]);
+              if (prm.act == 1) {
+                o.x = 1.f / (1.f + expf(-o.x)); o.y = 1.f / (1.f + expf(-o.y));
+                o.z = 1.f / (1.f + expf(-o.z)); o.w = 1.f / (1.f + expf(-o.w));
+              }
               if (prm.accumulate) {
                 const float4 e = dst[i];
                 o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
@@ -386,7 +415,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float a = warp_sum(gs[i]);
-            if (lane == 0) atomicAdd(&prm.gap[(long long)b * prm.Cout + nsp * C::N + j * 16 + i], a);
+            if (lane == 0 && nsp * C::N + j * 16 + i < prm.cout_real)
+              atomicAdd(&prm.gap[(long long)b * prm.cout_real + nsp * C::N + j * 16 + i], a);
             gs[i] = 0.f;
           }
         }
@@ -427,7 +457,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
 // wp[ns][c][tap][pl][n][j] = op( w[tw(tap)*wtap + (CK*c + T*pl + j)*sw_in + (ns*N+n)*sw_out] ),  op = bf16 | tf32
 template <int OP>
 __global__ void tc_pack_kernel(const float* __restrict__ w, void* __restrict__ wp, int taps, int Cin, int Cout, int N,
-                               long long wtap, int sw_in, int sw_out, int flip) {
+                               long long wtap, int sw_in, int sw_out, int flip, int cin_real, int cout_real) {
   constexpr int T = OP != OP_TF32 ? 8 : 4;
   const long long total = (long long)taps * Cin * Cout;
   const int nch = Cin / (2 * T);
@@ -442,7 +472,8 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, void* __restrict__ w
     const int ns = (int)r;
     if (flip) tap = taps - 1 - tap;
     const int ci = 2 * T * c + T * pl + j, co = ns * N + n;
-    const float v = w[(long long)tap * wtap + (long long)ci * sw_in + (long long)co * sw_out];
+    const float v = (ci < cin_real && co < cout_real)
+                        ? w[(long long)tap * wtap + (long long)ci * sw_in + (long long)co * sw_out] : 0.f;
     if (OP == OP_BF16) {
       reinterpret_cast<__nv_bfloat16*>(wp)[i] = __float2bfloat16_rn(v);
     } else if (OP == OP_F16) {
@@ -479,6 +510,17 @@ static int pick_n(int Cout) {
   return 16;
 }
 
+// 16-bit operands need whole 16-channel K steps: Cin % 16 == 0, or a narrow input (Cin < 8) zero-padded to 16
+static int operand_type(const ConvGeom& g) {
+  const int op = g.bwd ? g_bwd_op : g_fwd_op;
+  return (op != OP_TF32 && (g.Cin % 16 == 0 || (g.mode == CONV_S1 && g.Cin < 8))) ? op : OP_TF32;
+}
+static int pad_cin(const ConvGeom& g) {
+  const int ck = operand_type(g) == OP_TF32 ? 8 : 16;
+  return (g.Cin + ck - 1) / ck * ck;
+}
+static int pad_cout(int c) { return (c + 15) / 16 * 16; }
+
 // virtual (stride-1) problem of a conv geometry: S1 as is; DOWN / UP = 2x2x2 conv on the coarse grid (conv_s2.cu)
 struct TcProblem {
   int ks, hb, Cin, Cout, D, H, W, s2d, d2s, Csub;
@@ -487,7 +529,8 @@ static TcProblem tc_problem(const ConvGeom& g) {
   TcProblem q;
   memset(&q, 0, sizeof(q));
   if (g.mode == CONV_S1) {
-    q.ks = g.k; q.hb = g.k == 2 ? g.pad : g.k / 2; q.Cin = g.Cin; q.Cout = g.Cout; q.D = g.Do; q.H = g.Ho; q.W = g.Wo;
+    q.ks = g.k; q.hb = g.k == 2 ? g.pad : g.k / 2; q.Cin = pad_cin(g); q.Cout = pad_cout(g.Cout);
+    q.D = g.Do; q.H = g.Ho; q.W = g.Wo;
   } else if (g.mode == CONV_DOWN) {
     q.ks = 2; q.hb = 0; q.Cin = 8 * g.Cin; q.Cout = g.Cout; q.D = g.Do; q.H = g.Ho; q.W = g.Wo;
     q.s2d = 1; q.Csub = g.Cin;
@@ -499,30 +542,28 @@ static TcProblem tc_problem(const ConvGeom& g) {
 }
 
 // g.bwd marks the backward pass (precision choice); chunks of CK channels must not straddle a parity block
-static int operand_type(const ConvGeom& g) {
-  const int op = g.bwd ? g_bwd_op : g_fwd_op;
-  return (op != OP_TF32 && g.Cin % 16 == 0) ? op : OP_TF32;
-}
-
 bool tc_conv_supported(const ConvGeom& g) {
-  if (g.mode == CONV_S1)
-    return (g.k == 3 || g.k == 1) && g.Cin % 8 == 0 && g.Cout % 16 == 0 && g.Cin >= 8 && g.Cout >= 16;
+  if (g.mode == CONV_S1)     // narrow inputs (Cin < 8) / outputs (Cout < 16) run zero-padded to one K step / N tile
+    return (g.k == 3 || g.k == 1) && g.Cin >= 1 && g.Cout >= 1 && (g.Cin % 8 == 0 || g.Cin < 8) &&
+           (g.Cout % 16 == 0 || g.Cout < 16);
   return g.k == 3 && g.Cin % 8 == 0 && g.Cin >= 8 && g.Cout % 16 == 0 && g.Cout >= 16;
 }
 
 size_t tc_packed_weight_elems(const ConvGeom& g) {
-  return (size_t)(g.mode == CONV_S1 ? g.k * g.k * g.k : 64) * g.Cin * g.Cout;
+  if (g.mode != CONV_S1) return (size_t)64 * g.Cin * g.Cout;
+  return (size_t)g.k * g.k * g.k * ((g.Cin + 15) / 16 * 16) * pad_cout(g.Cout);   // room for either operand type
 }
 
 int launch_tc_pack_weights(const ConvGeom& g, const float* w, float* wp, cudaStream_t s) {
   B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "pack_weights: shape not on the tcgen05 path");
   const int op = operand_type(g);
   if (g.mode != CONV_S1) return launch_pack_s2(g, w, wp, op, s);
-  const int taps = g.k * g.k * g.k;
-  const long long total = (long long)taps * g.Cin * g.Cout;
+  const int taps = g.k * g.k * g.k, cin = pad_cin(g), cout = pad_cout(g.Cout);
+  const long long total = (long long)taps * cin * cout;
   const unsigned grid = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-#define B3D_PACK(OPV) \
-  tc_pack_kernel<OPV><<<grid, 256, 0, s>>>(w, wp, taps, g.Cin, g.Cout, pick_n(g.Cout), g.wtap, g.sw_in, g.sw_out, g.flip)
+#define B3D_PACK(OPV)                                                                                          \
+  tc_pack_kernel<OPV><<<grid, 256, 0, s>>>(w, wp, taps, cin, cout, pick_n(cout), g.wtap, g.sw_in, g.sw_out, g.flip, \
+                                           g.Cin, g.Cout)
   if (op == OP_BF16) B3D_PACK(OP_BF16);
   else if (op == OP_F16) B3D_PACK(OP_F16);
   else B3D_PACK(OP_TF32);
@@ -544,6 +585,7 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   p.vpc = ((long long)g.Do * g.Ho * g.Wo) / p.groups;
   p.s2d = q.s2d; p.d2s = q.d2s; p.Csub = q.Csub;
   p.Din = g.Di; p.doff = g.doff;
+  p.cin_real = g.mode == CONV_S1 ? g.Cin : q.Cin; p.cout_real = g.mode == CONV_S1 ? g.Cout : q.Cout; p.act = g.act;
   static bool attr_set = false;
   if (!attr_set) {
     B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),
@@ -577,10 +619,13 @@ static int dispatch_n(const ConvGeom& g, const TcProblem& q, const float* x, con
 int launch_conv_tc(const ConvGeom& g, const float* x, const float* wp, const float* bias, float* y, double* stats,
                    float* gap, cudaStream_t s) {
   B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "conv: shape not supported by the tcgen05 path");
-  B3D_REQUIRE(g.act == 0, B3D_ERR_UNSUPPORTED, "tcgen05 conv: activation epilogue not built");
-  B3D_REQUIRE(g.xp % 8 == 0 && g.yp % 4 == 0 && ((uintptr_t)x & 31) == 0 &&
-                  (((uintptr_t)y | (uintptr_t)wp) & 15) == 0,
-              B3D_ERR_LAYOUT, "tcgen05 conv: x must be 32-byte aligned with a channel pitch multiple of 8");
+  B3D_REQUIRE(g.act == 0 || (g.act == 1 && g.mode == CONV_S1), B3D_ERR_UNSUPPORTED,
+              "tcgen05 conv: only the sigmoid epilogue of stride-1 convs is built");
+  B3D_REQUIRE(g.Cin < 8 || (g.xp % 8 == 0 && ((uintptr_t)x & 31) == 0), B3D_ERR_LAYOUT,
+              "tcgen05 conv: x must be 32-byte aligned with a channel pitch multiple of 8");
+  B3D_REQUIRE(g.Cout < 16 || (g.yp % 4 == 0 && ((uintptr_t)y & 15) == 0), B3D_ERR_LAYOUT,
+              "tcgen05 conv: y must be 16-byte aligned with a channel pitch multiple of 4");
+  B3D_REQUIRE(((uintptr_t)wp & 15) == 0, B3D_ERR_LAYOUT, "tcgen05 conv: packed weights must be 16-byte aligned");
   const TcProblem q = tc_problem(g);
   B3D_REQUIRE(gap == nullptr || g.mode == CONV_S1, B3D_ERR_UNSUPPORTED, "tcgen05 conv: GAP only for stride 1");
   const int op = operand_type(g);

@@ -47,6 +47,10 @@ struct WgParams {
   int pad;                         // halo before (1 for k=3, 0 for k in {1,2})
   int s2_nA;                       // > 0: stride-2 family, Cin = 8*s2_nA rows ordered (parity, channel)
   int px_bytes;                    // bytes the TMA writes per x plane (px is the 128-byte padded pitch)
+  int M;                           // MMA M: 128, or 64 when <= 64 rows exist (half the A-operand shared-memory reads)
+  int rows_real;                   // rows of dw actually written (stacked narrow operands are zero-padded to 8)
+  int tr_cn;                       // > 0: rows are (tap, c) of a stacked narrow dy with tr_cn channels and the columns are
+                                   //      the layer's input channels: write dw[tap][column][c] (see cast_stack_bf16)
   int TD, TH, TW, HD, HH, HW;      // tile and x-halo extents (voxels)
   int px, py;                      // plane bytes of x halo / dy tile
   int stage_bytes, nstages, xplanes_max;
@@ -72,9 +76,9 @@ __global__ void __launch_bounds__(256, 1)
   constexpr int TAPS = KS * KS * KS;
   constexpr bool allD = TG == TAPS, allH = TG >= KS * KS, allW = TG >= KS;   // dims a tap group spans
   const int tg = blockIdx.y;                 // tap group
-  const int cbase = (blockIdx.z / prm.nnt) * 128;   // input-channel tile
+  const int cbase = (blockIdx.z / prm.nnt) * prm.M;   // input-channel tile
   const int nb0 = (blockIdx.z % prm.nnt) * prm.NT;  // output-channel tile
-  const int crem = min(128, prm.Cin - cbase);
+  const int crem = min(prm.M, prm.Cin - cbase);
   const int xplanes = crem / 8, yplanes = prm.NT / 8;
 
   if (threadIdx.x == 0) {
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(256, 1)
     const bool leader = elect_one();
     // D=f32, A=B=bf16, both MN-major, N=Cout, M=128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(prm.NT >> 3) << 17) | ((128u >> 4) << 24);
+                           ((uint32_t)(prm.NT >> 3) << 17) | (((uint32_t)prm.M >> 4) << 24);
     int s = 0, ph = 0;
     uint32_t acc = 0;
     const int rowc = prm.HW, planec = prm.HH * prm.HW;
@@ -166,8 +170,9 @@ __global__ void __launch_bounds__(256, 1)
     __syncwarp();
   } else if (warp >= 4) {
     // final reduction of this CTA's partial dw into global memory
+    // accumulator row r lives in TMEM lane r (M = 128) or lane 32*(r/16) + r%16 (M = 64; tools/umma_probe_m64.cu)
     const int q = warp - 4;
-    const int ci = cbase + q * 32 + lane;
+    const int ci = prm.M == 128 ? cbase + q * 32 + lane : (lane < 16 ? cbase + q * 16 + lane : prm.Cin);
     mbar_wait(smem_u32(done), 0);
     tc_fence_after();
     const bool has_tiles = blockIdx.x < prm.ntiles;
@@ -177,7 +182,7 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll 1
     for (int t = 0; t < TG; ++t) {
       int tap = allD ? t : (TG == KS * KS ? tg * TG + t : (TG == KS ? tg * KS + t : tg));
-      bool live = has_tiles && ci < prm.Cin;
+      bool live = has_tiles && ci < prm.rows_real;
       if (prm.s2_nA > 0) {
         const int td = 2 * (tap >> 2) + (par >> 2), th = 2 * ((tap >> 1) & 1) + ((par >> 1) & 1),
                   tw = 2 * (tap & 1) + (par & 1);
@@ -188,7 +193,12 @@ __global__ void __launch_bounds__(256, 1)
       for (int j = 0; j < prm.NT; j += 16) {
         float v[16];
         tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + t * prm.NT + j, v);
-        if (live) {
+        if (live && prm.tr_cn > 0) {
+          const int tt = row / prm.tr_cn, cc = row - tt * prm.tr_cn;     // row = (tap, narrow channel)
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            atomicAdd(prm.dw + ((size_t)tt * prm.Cout + nb0 + j + i) * prm.tr_cn + cc, v[i]);
+        } else if (live) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) atomicAdd(dst + j + i, v[i]);
         }
@@ -235,7 +245,9 @@ static int make_map(CUtensorMap* tm, const void* base, int C, long long pitch, i
 }
 
 // x: bf16 copy of the big tensor — for stride 2 already in space-to-depth order [B, Ds, Hs, Ws, 8*nA]
-int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, float* dw, cudaStream_t s) {
+// rows_real / tr_cn: see WgParams (0 / 0 for ordinary layers); dw_elems: size of dw to clear
+int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, float* dw, cudaStream_t s,
+                         int rows_real, int tr_cn, long long dw_elems) {
   B3D_REQUIRE(tc_wgrad_supported(wg), B3D_ERR_UNSUPPORTED, "wgrad: shape not on the tcgen05 path");
   B3D_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, B3D_ERR_LAYOUT, "wgrad: alignment");
   const bool s2 = wg.s == 2;
@@ -247,8 +259,9 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
   else TG = TAPS;
   const int ntg = TAPS / TG;
   const bool allD = TG == TAPS, allH = TG >= KS * KS, allW = TG >= KS;
-  const int nmt = (Cin + 127) / 128;
-  const int xpl = (Cin < 128 ? Cin : 128) / 8;
+  const int M = Cin <= 64 ? 64 : 128;
+  const int nmt = (Cin + M - 1) / M;
+  const int xpl = (Cin < M ? Cin : M) / 8;
   // tile planner: largest tile whose stages fit, with 16 MN groups (M=128 bf16) readable from every stage start
   static const int cand[][3] = {{1, 4, 8},  {2, 4, 8},  {2, 4, 16}, {2, 8, 16},
                                 {4, 8, 16}, {4, 8, 32}, {4, 16, 32}};   // TH even: a K step spans 2 h rows
@@ -265,7 +278,7 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
     const long long stage = (((long long)xpl * px + (long long)(NT / 8) * py + 127) / 128) * 128;
     for (int ns = 3; ns >= 2; --ns) {
       const long long last = (long long)(ns - 1) * stage;
-      if (ns * stage <= budget && last + 16LL * px <= budget) {
+      if (ns * stage <= budget && last + (long long)(M / 8) * px <= budget) {
         p.TD = TD; p.TH = TH; p.TW = TW; p.HD = HD; p.HH = HH; p.HW = HW;
         p.px = px; p.px_bytes = cells * 16; p.py = py; p.stage_bytes = (int)stage; p.nstages = ns;
         found = true;
@@ -276,6 +289,7 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
   B3D_REQUIRE(found, B3D_ERR_UNSUPPORTED, "wgrad: no tile fits shared memory (Cin=%d Cout=%d)", Cin, Cout);
   p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.xplanes_max = xpl;
   p.NT = NT; p.nnt = nnt; p.pad = KS == 3 ? 1 : 0; p.s2_nA = s2 ? wg.nA : 0;
+  p.M = M; p.rows_real = rows_real > 0 ? rows_real : Cin; p.tr_cn = tr_cn;
   p.ntd = (wg.Ds + p.TD - 1) / p.TD; p.nth = (wg.Hs + p.TH - 1) / p.TH; p.ntw = (wg.Ws + p.TW - 1) / p.TW;
   p.ntiles = wg.B * p.ntd * p.nth * p.ntw;
   int nsplit = sm_count() / (ntg * nmt * nnt);
@@ -286,7 +300,8 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
   if (s2) B3D_TRY(make_map(&tmx, x, Cin, Cin, wg.Ws, wg.Hs, wg.Ds, wg.B, p.HW, p.HH, p.HD));
   else    B3D_TRY(make_map(&tmx, x, Cin, wg.bigp, wg.Wb, wg.Hb, wg.Db, wg.B, p.HW, p.HH, p.HD));
   B3D_TRY(make_map(&tmy, dy, Cout, wg.smallp, wg.Ws, wg.Hs, wg.Ds, wg.B, p.TW, p.TH, p.TD));
-  B3D_TRY(cuda_ok(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)wg.k * wg.k * wg.k * wg.nA * Cout, s), "memset dw"));
+  const size_t dw_n = dw_elems > 0 ? (size_t)dw_elems : (size_t)wg.k * wg.k * wg.k * wg.nA * Cout;
+  B3D_TRY(cuda_ok(cudaMemsetAsync(dw, 0, sizeof(float) * dw_n, s), "memset dw"));
   dim3 grid((unsigned)nsplit, (unsigned)ntg, (unsigned)(nmt * nnt));
 #define LAUNCH(K, T)                                                                                           \
   do {                                                                                                         \
@@ -394,6 +409,55 @@ int launch_cast_bf16_s2d(const float* src, void* dst, int B, int D, int H, int W
   cast_bf16_s2d_kernel<<<(unsigned)blocks, threads, sizeof(float) * C, s>>>(src, (uint4*)dst, B, D, H, W, C, pitch,
                                                                             colsum);
   B3D_LAUNCH_CHECK("cast_bf16_s2d");
+  return B3D_OK;
+}
+
+// "tap-stacked" bf16 copy of a NARROW tensor (Cn < 8 channels: the 2-channel input volume, the 2-3 channel
+// gradients of the output convs):  dst[v][(t, c)] = src[v + sgn*(t - pad)][c]  for the k^3 taps t, zero outside the
+// volume and in the padding up to nA = 8*ceil(k^3*Cn/8) channels.  The weight gradient of such a layer is then ONE
+// K = voxels GEMM (the KS = 1 case of conv3_wgrad_tc_kernel) with all taps in the M dimension instead of k^3 MMAs
+// whose M = 128 rows hold 2 real channels.  sgn = +1 stacks the layer input x (rows (t, ci)); sgn = -1 stacks dy
+// (dw[t][ci][co] = sum_u x[u][ci] dy[u - (t - pad)][co], rows (t, co)).  thread -> one 16-byte cell.
+__global__ void cast_stack_bf16_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int B, int D, int H,
+                                       int W, int Cn, long long pitch, int k, int sgn, int nA) {
+  const int cells = nA / 8, pad = k / 2, rows = k * k * k * Cn;
+  const long long total = (long long)B * D * H * W * cells;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cell = (int)(i % cells);
+    long long r = i / cells;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int d = (int)(r % D); r /= D;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int row = cell * 8 + e;
+      v[e] = 0.f;
+      if (row < rows) {
+        const int t = row / Cn, c = row - t * Cn;
+        const int dd = d + sgn * (t / (k * k) - pad), hh = h + sgn * ((t / k) % k - pad), ww = w + sgn * (t % k - pad);
+        if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
+          v[e] = __ldg(src + ((((long long)r * D + dd) * H + hh) * W + ww) * pitch + c);
+      }
+    }
+    uint4 q;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v[3]), "f"(v[2]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(v[5]), "f"(v[4]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(v[7]), "f"(v[6]));
+    dst[i] = q;
+  }
+}
+
+int launch_cast_stack_bf16(const float* src, void* dst, int B, int D, int H, int W, int Cn, long long pitch, int k,
+                           int sgn, int nA, cudaStream_t s) {
+  const long long total = (long long)B * D * H * W * (nA / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = 32LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  cast_stack_bf16_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, (uint4*)dst, B, D, H, W, Cn, pitch, k, sgn, nA);
+  B3D_LAUNCH_CHECK("cast_stack_bf16");
   return B3D_OK;
 }
 

@@ -12,6 +12,7 @@ namespace b3d {
 
 constexpr int kThreads = 256;
 constexpr int kIter = 8;  // float4 per thread per CTA
+constexpr int kIterR = 4; // ... in the two-operand reducing kernel (register budget)
 
 struct ChunkGeom {
   long long L;     // elements per chunk
@@ -40,24 +41,30 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restr
   if (e_lo >= e_hi) return;
   const float* xc = x + ((long long)chunk * L - shift);
   float s[2] = {0.f, 0.f};
-  // reducing kernels walk several segments per CTA so that few CTAs contend on one fp64 atomic
+  // reducing kernels walk several segments per CTA so that few CTAs contend on one fp64 atomic; all kIter loads
+  // of a step are issued before the first use
   for (long long base = (long long)blockIdx.x * (kThreads * kIter * VEC); base < L;
        base += (long long)gridDim.x * (kThreads * kIter * VEC)) {
+    float v[kIter][VEC];
 #pragma unroll
     for (int k = 0; k < kIter; ++k) {
       const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
-      if (e >= e_lo && e < e_hi) {
-        if (VEC == 4) {
-          const float4 v = ld_stream(reinterpret_cast<const float4*>(xc + e));
-          s[0] += (v.x + v.y) + (v.z + v.w);
-          s[1] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-        } else {
-          const float v = xc[e];
-          s[0] += v;
-          s[1] += v * v;
-        }
+      const bool in = e >= e_lo && e < e_hi;
+      if (VEC == 4) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in) t = ld_stream(reinterpret_cast<const float4*>(xc + e));
+        v[k][0] = t.x; v[k][VEC > 1 ? 1 : 0] = t.y; v[k][VEC > 2 ? 2 : 0] = t.z; v[k][VEC > 3 ? 3 : 0] = t.w;
+      } else {
+        v[k][0] = in ? xc[e] : 0.f;
       }
     }
+#pragma unroll
+    for (int k = 0; k < kIter; ++k)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        s[0] += v[k][i];
+        s[1] += v[k][i] * v[k][i];
+      }
   }
   __shared__ double red[64];
   double d[2] = {(double)s[0], (double)s[1]};
@@ -85,26 +92,34 @@ __global__ void __launch_bounds__(kThreads)
   const long long base = (long long)blockIdx.x * (kThreads * kIter * VEC);
   const int jbase = g * gm.cg;
   const long long goff = (long long)g * gm.L;
+  float in[kIter][4];
+#pragma unroll
+  for (int k = 0; k < kIter; ++k) {
+    const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
+    if (e >= e_lo && e < e_hi) {
+      if (VEC == 4) {
+        const float4 v = ld_stream(reinterpret_cast<const float4*>(x + off + e));
+        in[k][0] = v.x; in[k][1] = v.y; in[k][2] = v.z; in[k][3] = v.w;
+      } else {
+        in[k][0] = x[off + e];
+      }
+    }
+  }
 #pragma unroll
   for (int k = 0; k < kIter; ++k) {
     const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
     if (e >= e_lo && e < e_hi) {
       const int c0 = (int)((goff + e) % gm.cg);
-      if (VEC == 4) {
-        const float4 v = ld_stream(reinterpret_cast<const float4*>(x + off + e));
-        float in[4] = {v.x, v.y, v.z, v.w}, o[4];
+      float o[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int j = c0 + i;
-          j = j >= gm.cg ? j % gm.cg : j;
-          float t = (in[i] - mean) * rstd * __ldg(gamma + jbase + j) + __ldg(beta + jbase + j);
-          o[i] = RELU ? fmaxf(t, 0.f) : t;
-        }
-        st_stream(reinterpret_cast<float4*>(y + off + e), make_float4(o[0], o[1], o[2], o[3]));
-      } else {
-        float t = (x[off + e] - mean) * rstd * __ldg(gamma + jbase + c0) + __ldg(beta + jbase + c0);
-        y[off + e] = RELU ? fmaxf(t, 0.f) : t;
+      for (int i = 0; i < VEC; ++i) {
+        int j = c0 + i;
+        j = j >= gm.cg ? j % gm.cg : j;
+        const float t = (in[k][i] - mean) * rstd * __ldg(gamma + jbase + j) + __ldg(beta + jbase + j);
+        o[i] = RELU ? fmaxf(t, 0.f) : t;
       }
+      if (VEC == 4) st_stream(reinterpret_cast<float4*>(y + off + e), make_float4(o[0], o[1], o[2], o[3]));
+      else y[off + e] = o[0];
     }
   }
 }
@@ -136,52 +151,74 @@ __global__ void __launch_bounds__(kThreads)
   float ag[VEC], ab[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) ag[i] = ab[i] = 0.f;
-  int c_first = -1;
-  for (long long base = (long long)blockIdx.x * (kThreads * kIter * VEC); base < gm.L;
-       base += (long long)gridDim.x * (kThreads * kIter * VEC))
+  // affine index of this thread's first element: loop-invariant when cg | kThreads*VEC
+  const int c_first = (int)((goff + (long long)blockIdx.x * (kThreads * kIterR * VEC) + threadIdx.x * VEC) % gm.cg);
+  for (long long base = (long long)blockIdx.x * (kThreads * kIterR * VEC); base < gm.L;
+       base += (long long)gridDim.x * (kThreads * kIterR * VEC)) {
+    // all loads of the step are issued before any use (memory-level parallelism: 2*kIterR 128-bit loads / thread)
+    float dv[kIterR][4], xv[kIterR][4];
 #pragma unroll
-  for (int k = 0; k < kIter; ++k) {
-    const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
-    if (e < gm.L) {
-      const int c0 = (int)((goff + e) % gm.cg);
-      if (c_first < 0) c_first = c0;
-      float dv[4], xv[4];
-      if (VEC == 4) {
-        const float4 a = ld_stream(reinterpret_cast<const float4*>(dy + off + e));
-        const float4 b = ld_stream(reinterpret_cast<const float4*>(x + off + e));
-        dv[0] = a.x, dv[1] = a.y, dv[2] = a.z, dv[3] = a.w;
-        xv[0] = b.x, xv[1] = b.y, xv[2] = b.z, xv[3] = b.w;
-      } else {
-        dv[0] = dy[off + e];
-        xv[0] = x[off + e];
-      }
+    for (int k = 0; k < kIterR; ++k) {
+      const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        int j = c0 + i;
-        j = j >= gm.cg ? j % gm.cg : j;
-        const float ga = __ldg(gamma + jbase + j);
-        const float xh = (xv[i] - mean) * rstd;
-        float gq = dv[i];
-        if (RELU) gq = (xh * ga + __ldg(beta + jbase + j)) > 0.f ? gq : 0.f;
-        const float h = gq * ga;
-        s1 += h;
-        s2 += h * xh;
-        if (invariant) {
-          ag[i] += gq * xh;
-          ab[i] += gq;
+      for (int i = 0; i < 4; ++i) dv[k][i] = xv[k][i] = 0.f;
+      if (e < gm.L) {
+        if (VEC == 4) {
+          const float4 a = ld_stream(reinterpret_cast<const float4*>(dy + off + e));
+          const float4 b = ld_stream(reinterpret_cast<const float4*>(x + off + e));
+          dv[k][0] = a.x, dv[k][1] = a.y, dv[k][2] = a.z, dv[k][3] = a.w;
+          xv[k][0] = b.x, xv[k][1] = b.y, xv[k][2] = b.z, xv[k][3] = b.w;
         } else {
-          atomicAdd(&sg[j], gq * xh);
-          atomicAdd(&sb[j], gq);
+          dv[k][0] = dy[off + e];
+          xv[k][0] = x[off + e];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kIterR; ++k) {
+      const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
+      if (e < gm.L) {
+        const int c0 = invariant ? c_first : (int)((goff + e) % gm.cg);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          int j = c0 + i;
+          j = j >= gm.cg ? j % gm.cg : j;
+          const float ga = __ldg(gamma + jbase + j);
+          const float xh = (xv[k][i] - mean) * rstd;
+          float gq = dv[k][i];
+          if (RELU) gq = (xh * ga + __ldg(beta + jbase + j)) > 0.f ? gq : 0.f;
+          const float h = gq * ga;
+          s1 += h;
+          s2 += h * xh;
+          if (invariant) {
+            ag[i] += gq * xh;
+            ab[i] += gq;
+          } else {
+            atomicAdd(&sg[j], gq * xh);
+            atomicAdd(&sb[j], gq);
+          }
         }
       }
     }
   }
-  if (invariant && c_first >= 0) {
+  if (invariant) {
+    // lanes whose first elements are congruent mod cg hold the same affine indices: for power-of-two cg <= 128 that
+    // is every P = max(1, cg/VEC)-th lane, so a butterfly over the lane offsets >= P leaves the warp totals in
+    // lanes [0, P) and only those touch shared memory
+    int P = 32;
+    if ((gm.cg & (gm.cg - 1)) == 0 && gm.cg <= 32 * VEC) P = gm.cg / VEC > 0 ? gm.cg / VEC : 1;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const int j = (c_first + i) % gm.cg;
-      atomicAdd(&sg[j], ag[i]);
-      atomicAdd(&sb[j], ab[i]);
+      float a = ag[i], b = ab[i];
+      for (int o = 16; o >= P; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if ((threadIdx.x & 31) < P) {
+        const int j = (c_first + i) % gm.cg;
+        atomicAdd(&sg[j], a);
+        atomicAdd(&sb[j], b);
+      }
     }
   }
   __shared__ double red[64];

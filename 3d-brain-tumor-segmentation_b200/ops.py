@@ -8,6 +8,8 @@ from __future__ import annotations
 import torch
 from torch.autograd import Function
 
+from ctypes import byref as _byref, c_longlong as _ll
+
 from ._lib import call, lib
 from . import slab as _slab
 
@@ -102,7 +104,7 @@ class Conv3dFn(Function):
         if want_gap:
             gap = _new((B, Cout), x)
         wp = None
-        if USE_TC["on"] and not act and tc_supported(w, stride, transposed, False):
+        if USE_TC["on"] and (not act or stride == 1) and tc_supported(w, stride, transposed, False):
             wp = pack_weights(w, False, stride, transposed)
         _call("b3d_conv3d_fwd", x, w, bias, y, stride, int(transposed), int(act), stats, gn_groups or 1, gap, 0, wp)
         ctx.save_for_backward(x, w, y if act else None)
@@ -131,10 +133,12 @@ class Conv3dFn(Function):
             dw = torch.empty_like(w)
             db = _new((dy.shape[-1],), dy) if has_bias else None
             xb = yb = None
-            if USE_TC["on"] and lib.b3d_conv3d_wgrad_tc_supported(w.shape[0], stride, int(transposed), x.shape[-1],
-                                                                  dy.shape[-1]):
-                xb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-                yb = torch.empty(dy.shape, device=x.device, dtype=torch.bfloat16)
+            if USE_TC["on"]:
+                xc, yc = _ll(), _ll()
+                if lib.b3d_conv3d_wgrad_plan(w.shape[0], stride, int(transposed), x.shape[-1], dy.shape[-1],
+                                             _byref(xc), _byref(yc)):
+                    xb = torch.empty(x.numel() // x.shape[-1] * xc.value, device=x.device, dtype=torch.bfloat16)
+                    yb = torch.empty(dy.numel() // dy.shape[-1] * yc.value, device=x.device, dtype=torch.bfloat16)
             _call("b3d_conv3d_wgrad", x, dy, dw, db, stride, int(transposed), xb, yb)
         return dx, dw, db, None, None, None, None, None
 

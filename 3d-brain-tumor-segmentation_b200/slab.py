@@ -259,7 +259,7 @@ class SlabContext:
         y = torch.empty((1,) + od + (cout,), dtype=_f32, device=x.device)
         gap = torch.empty((1, cout), dtype=_f32, device=x.device) if want_gap else None
         wp = None
-        if ops.USE_TC["on"] and not act and ops.tc_supported(w, stride, transposed, False):
+        if ops.USE_TC["on"] and (not act or stride == 1) and ops.tc_supported(w, stride, transposed, False):
             wp = ops.pack_weights(w, False, stride, transposed)
         ops._call("b3d_conv3d_fwd_halo", xin, w, bias, y, stride, int(transposed), int(act), before, after, gap, wp)
         if gap is not None:

@@ -62,12 +62,16 @@ int b3d_conv3d_fwd_halo(const DLTensor* x, const DLTensor* w, const DLTensor* bi
 /* data gradient (what tape.gradient computes for the layer input, train.py:151) */
 int b3d_conv3d_dgrad(const DLTensor* dy, const DLTensor* w, DLTensor* dx, int stride, int transposed,
                      int accumulate, const DLTensor* wpacked, void* stream);
-/* weight (+ bias, nullable) gradient.  x_bf16 / dy_bf16 (nullable, bf16, same shapes as x / dy): scratch
- * buffers; when both are given (and b3d_conv3d_wgrad_tc_supported) they are filled with bf16 copies and the
+/* weight (+ bias, nullable) gradient.  x_bf16 / dy_bf16 (nullable, bf16): scratch buffers of
+ * voxels * (channels per voxel reported by b3d_conv3d_wgrad_plan) elements; when both are given they are filled
+ * with bf16 copies of x / dy (space-to-depth order for stride 2, all taps stacked for narrow tensors) and the
  * tcgen05 kernel (bf16 operands, fp32 accumulation) is used, else the fp32 CUDA-core kernel. */
 int b3d_conv3d_wgrad(const DLTensor* x, const DLTensor* dy, DLTensor* dw, DLTensor* dbias, int stride,
                      int transposed, const DLTensor* x_bf16, const DLTensor* dy_bf16, void* stream);
 int b3d_conv3d_wgrad_tc_supported(int k, int stride, int transposed, int cin, int cout);
+/* returns 0 (CUDA cores), 1 (plain copies), 2 / 3 (narrow input / output: tap-stacked copy); *x_ch, *dy_ch
+ * receive the bf16 channels per voxel of the two scratch buffers */
+int b3d_conv3d_wgrad_plan(int k, int stride, int transposed, int cin, int cout, long long* x_ch, long long* dy_ch);
 /* 1 when the tcgen05 kernel runs the forward (dgrad=0) / data-gradient (dgrad=1) pass of a layer whose Keras
  * kernel is (k,k,k,a,b): stride-1 k in {1,3}, and the k3 stride-2 family (Conv3D s2, Conv3DTranspose), which is
  * executed as a 2x2x2 stride-1 conv over the coarse grid with space-to-depth addressing (csrc/conv_s2.cu). */

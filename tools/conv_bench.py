@@ -20,7 +20,7 @@ print("conv precision:", ops.get_conv_precision())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 # (spatial, Cin, Cout) of the default model's 3x3x3 convs, largest first
-SHAPES = [(128, 32, 16), (128, 16, 16), (64, 96, 32), (64, 64, 32), (64, 32, 32), (64, 16, 32),
+SHAPES = [(128, 2, 16), (128, 16, 2), (128, 32, 16), (128, 16, 16), (64, 96, 32), (64, 64, 32), (64, 32, 32), (64, 16, 32),
           (32, 256, 64), (32, 192, 64), (32, 64, 64), (16, 512, 128), (16, 128, 128)]
 
 
@@ -47,18 +47,22 @@ for n, cin, cout in SHAPES:
     line = f"{n:4d}^3 {cin:4d}->{cout:4d}  {flops / 1e9:7.1f} GF "
     if which in ("fwd", "all"):
         wp = ops.pack_weights(w, False)
-        ms = timeit(lambda: ops._call("b3d_conv3d_fwd", x, w, bias, y, 1, 0, 0, stats, 8, None, 0, wp))
+        st = stats if cout % 8 == 0 else None
+        ms = timeit(lambda: ops._call("b3d_conv3d_fwd", x, w, bias, y, 1, 0, 0, st, 8, None, 0, wp))
         ms2 = timeit(lambda: ops._call("b3d_conv3d_fwd", x, w, bias, y, 1, 0, 0, None, 1, None, 0, wp))
         io = 4.0 * n ** 3 * (cin + cout)
         line += (f"| fwd {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s (io {io / ms / 1e6:6.0f} GB/s) "
                  f"| no-stats {ms2 * 1e3:8.1f} us {flops / ms2 / 1e9:7.1f} TF/s ")
     if which in ("wgrad", "all"):
         dw = torch.empty_like(w)
-        xb = torch.empty(x.shape, device=dev, dtype=torch.bfloat16)
-        yb = torch.empty(dy.shape, device=dev, dtype=torch.bfloat16)
+        import ctypes
+        xc, yc = ctypes.c_longlong(), ctypes.c_longlong()
+        assert b3d._lib.lib.b3d_conv3d_wgrad_plan(3, 1, 0, cin, cout, ctypes.byref(xc), ctypes.byref(yc))
+        xb = torch.empty(n ** 3 * xc.value, device=dev, dtype=torch.bfloat16)
+        yb = torch.empty(n ** 3 * yc.value, device=dev, dtype=torch.bfloat16)
         ms = timeit(lambda: ops._call("b3d_conv3d_wgrad", x, dy, dw, None, 1, 0, xb, yb))
         line += f"| wgrad(+casts) {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s "
-    if which in ("k1", "all"):
+    if which in ("k1", "all") and cin >= 8 and cout >= 16:
         w1 = torch.randn(1, 1, 1, cin, cout, device=dev) * 0.05
         wp1 = ops.pack_weights(w1, False)
         gap = torch.empty(1, cout, device=dev)
