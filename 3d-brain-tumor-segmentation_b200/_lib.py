@@ -74,7 +74,7 @@ SIGNATURES = {
     "b3d_conv3d_fwd": "TTTTiiiTiTiTv",
     "b3d_conv3d_fwd_halo": "TTTTiiiiiTTv",
     "b3d_conv3d_dgrad": "TTTiiiTv",
-    "b3d_conv3d_wgrad": "TTTTiiTTv",
+    "b3d_conv3d_wgrad": "TTTTiiTTiv",
     "b3d_conv3d_pack_weights": "TTiiiv",
     "b3d_gn_stats": "TTiv",
     "b3d_gn_apply": "TTTTTifiv",

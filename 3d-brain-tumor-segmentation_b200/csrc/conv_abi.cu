@@ -215,7 +215,7 @@ WgradPlan wgrad_plan(int k, int stride, int transposed, int cin, int cout) {
 
 extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTensor* dw_, DLTensor* dbias_,
                                 int stride, int transposed, const DLTensor* x_bf16_, const DLTensor* dy_bf16_,
-                                void* stream) {
+                                int x_bf16_ready, void* stream) {
   TView x, dy, dw;
   int k;
   B3D_TRY(view(x_, DT_F32, 5, true, "x", &x));
@@ -259,11 +259,14 @@ extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTenso
       const TView& smlb = transposed ? xb : yb;
       float* db_big = transposed ? db : nullptr;     // the bias gradient = column sums of dy, whichever role it has
       float* db_sml = transposed ? nullptr : db;
+      // x_bf16_ready: the caller already holds the plain bf16 copy of x (two convs of a ResnetBlock share their input)
+      const bool skip_big = x_bf16_ready && !transposed && stride == 1, skip_sml = x_bf16_ready && transposed;
       if (stride == 2)
         B3D_TRY(launch_cast_bf16_s2d((const float*)big.p, bigb.p, wg.B, wg.Ds, wg.Hs, wg.Ws, wg.nA, big.pitch, db_big, s));
-      else
+      else if (!skip_big)
         B3D_TRY(launch_cast_bf16((const float*)big.p, bigb.p, big.numel / big.shape[4], wg.nA, db_big, s));
-      B3D_TRY(launch_cast_bf16((const float*)sml.p, smlb.p, sml.numel / sml.shape[4], wg.nB, db_sml, s));
+      if (!skip_sml)
+        B3D_TRY(launch_cast_bf16((const float*)sml.p, smlb.p, sml.numel / sml.shape[4], wg.nB, db_sml, s));
       B3D_TRY(launch_conv_wgrad_tc(wg, bigb.p, smlb.p, (float*)dw.p, s));
       bias_done = db != nullptr;
     } else {

@@ -197,6 +197,88 @@ __global__ void __launch_bounds__(kGT)
 }
 
 // ------------------------------------------------------------------------------------------
+// Gather form for FEW output voxels with a LONG reduction (the VAE bottleneck: 16^3 x 512 -> 8^3 x 8 strided conv,
+// 16^3 x 128 -> 8^3 x 1 data gradient of the first transposed conv): one CTA per output voxel, the (tap, ci)
+// reduction is spread over the threads (coalesced over ci), then reduced through shared memory.
+constexpr int kSkT = 256, kSkCo = 8;
+
+__global__ void __launch_bounds__(kSkT)
+    conv_gather_splitk_kernel(ConvGeom cg, const float* __restrict__ x, const float* __restrict__ w,
+                              const float* __restrict__ bias, float* __restrict__ y) {
+  __shared__ float red[kSkCo][kSkT / 32];
+  const int taps = cg.k * cg.k * cg.k;
+  long long v = blockIdx.x;
+  const int ow = (int)(v % cg.Wo); v /= cg.Wo;
+  const int oh = (int)(v % cg.Ho); v /= cg.Ho;
+  const int od = (int)(v % cg.Do); v /= cg.Do;
+  const int b = (int)v;
+  const int co0 = blockIdx.y * kSkCo;
+  float acc[kSkCo];
+#pragma unroll
+  for (int i = 0; i < kSkCo; ++i) acc[i] = 0.f;
+  const long long xb = (long long)b * cg.Di * cg.Hi * cg.Wi;
+  for (int t = 0; t < taps; ++t) {
+    const int tk = t % cg.k, th = (t / cg.k) % cg.k, td = t / (cg.k * cg.k);
+    int id, ih, iw;
+    if (cg.mode == CONV_S1) {
+      id = od + td - cg.pad; ih = oh + th - cg.pad; iw = ow + tk - cg.pad;
+    } else if (cg.mode == CONV_DOWN) {
+      id = 2 * od + td; ih = 2 * oh + th; iw = 2 * ow + tk;
+    } else {
+      id = od - td; ih = oh - th; iw = ow - tk;
+      if ((id | ih | iw) & 1) continue;
+      id >>= 1; ih >>= 1; iw >>= 1;
+    }
+    id += cg.doff;
+    if (id < 0 || id >= cg.Di || ih < 0 || ih >= cg.Hi || iw < 0 || iw >= cg.Wi) continue;   // CTA-uniform
+    const float* xp = x + (xb + ((long long)id * cg.Hi + ih) * cg.Wi + iw) * cg.xp;
+    const int tw = cg.flip ? taps - 1 - t : t;
+    const float* wt = w + (long long)tw * cg.wtap;
+    for (int ci = threadIdx.x; ci < cg.Cin; ci += kSkT) {
+      const float xv = xp[ci];
+      const float* wr = wt + (long long)ci * cg.sw_in + (long long)co0 * cg.sw_out;
+#pragma unroll
+      for (int i = 0; i < kSkCo; ++i)
+        if (co0 + i < cg.Cout) acc[i] = fmaf(xv, wr[(long long)i * cg.sw_out], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kSkCo; ++i) {
+    const float a = warp_sum(acc[i]);
+    if ((threadIdx.x & 31) == 0) red[i][threadIdx.x >> 5] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < kSkCo && co0 + threadIdx.x < cg.Cout) {
+    float r = 0.f;
+#pragma unroll
+    for (int j = 0; j < kSkT / 32; ++j) r += red[threadIdx.x][j];
+    r += bias ? bias[co0 + threadIdx.x] : 0.f;
+    if (cg.act == 1) r = 1.f / (1.f + expf(-r));
+    float* yp = y + (long long)blockIdx.x * cg.yp + co0 + threadIdx.x;
+    if (cg.accumulate) r += *yp;
+    *yp = r;
+  }
+}
+
+// GroupNorm chunk statistics of a small tensor (one CTA per chunk)
+__global__ void __launch_bounds__(256) small_stats_kernel(const float* __restrict__ y, double* __restrict__ stats,
+                                                         long long L) {
+  __shared__ double red[64];
+  const float* yc = y + (long long)blockIdx.x * L;
+  double d[2] = {0.0, 0.0};
+  for (long long e = threadIdx.x; e < L; e += 256) {
+    const double v = yc[e];
+    d[0] += v;
+    d[1] += v * v;
+  }
+  block_sum<2, double>(d, red);
+  if (threadIdx.x == 0) {
+    stats[2 * blockIdx.x] = d[0];
+    stats[2 * blockIdx.x + 1] = d[1];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // weight gradient, outer-product form.  CTA tile 32(a) x 32(b); K = voxels, staged 32 at a time.
 constexpr int kWT = 32, kWK = 32;
 
@@ -370,6 +452,19 @@ __global__ void __launch_bounds__(256)
     float a = 0.f;
     for (long long e = e0 + threadIdx.x; e < e1; e += 256) a += x[e];
     atomicAdd(&sm[threadIdx.x % C], a);
+  } else if (C <= 8) {
+    // narrow tensors (the 2-3 channel gradients of the output convs): one thread per row
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long r = r0 + threadIdx.x; r < r1; r += 256)
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < C) a[c] += x[r * pitch + c];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < C) {
+        const float t = warp_sum(a[c]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sm[c], t);
+      }
   } else {
     for (long long r = r0; r < r1; ++r)
       for (int c = threadIdx.x; c < C; c += 256) sm[c] += x[r * pitch + c];  // thread-private columns
@@ -382,6 +477,19 @@ int launch_conv_gather(const ConvGeom& cg, const float* x, const float* w, const
                        double* stats, float* gap, cudaStream_t s) {
   const long long nvox = (long long)cg.B * cg.Do * cg.Ho * cg.Wo;
   const int taps = cg.k * cg.k * cg.k;
+  if (nvox <= 4096 && (long long)taps * cg.Cin >= 1024 && gap == nullptr &&
+      (stats == nullptr || cg.yp == cg.Cout)) {
+    // few outputs, long reductions: one CTA per output voxel (the voxel-per-thread kernel would run on 4 CTAs)
+    dim3 grid((unsigned)nvox, (unsigned)((cg.Cout + kSkCo - 1) / kSkCo), 1);
+    conv_gather_splitk_kernel<<<grid, kSkT, 0, s>>>(cg, x, w, bias, y);
+    B3D_LAUNCH_CHECK("conv_gather_splitk");
+    if (stats != nullptr) {
+      const long long S = (long long)cg.Do * cg.Ho * cg.Wo;
+      small_stats_kernel<<<cg.B * cg.groups, 256, 0, s>>>(y, stats, S * cg.Cout / cg.groups);
+      B3D_LAUNCH_CHECK("small_stats");
+    }
+    return B3D_OK;
+  }
   long long gpc = nvox / ((long long)kGT * 8 * sm_count());
   gpc = gpc < 1 ? 1 : (gpc > 8 ? 8 : gpc);
   const unsigned gx = (unsigned)((nvox + (long long)kGT * gpc - 1) / ((long long)kGT * gpc));

@@ -29,9 +29,9 @@ namespace b3d {
 // UP  : K  = Cg,  N' = 8*Cp with n' = p*Cp + cp, tap k (offsets -1,0):  w[t = p + 2(1-k)]
 template <int OP>
 __global__ void pack_s2_kernel(const float* __restrict__ w, void* __restrict__ wp, int up, int Cg, int Cp, int N,
-                               long long wtap, int sw_in, int sw_out) {
+                               long long wtap, int sw_in, int sw_out, int NTdown) {
   constexpr int T = OP != OP_TF32 ? 8 : 4;
-  const int K = up ? Cg : 8 * Cg, NT = up ? 8 * Cp : Cp;
+  const int K = up ? Cg : 8 * Cg, NT = up ? 8 * Cp : NTdown;    // NTdown = Cp padded to the N tile (>= 16)
   const long long total = 8LL * K * NT;
   const int nch = K / (2 * T);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -53,7 +53,7 @@ __global__ void pack_s2_kernel(const float* __restrict__ w, void* __restrict__ w
     const int th = up ? ph + 2 * (1 - kh) : 2 * kh + ph;
     const int tw = up ? pw + 2 * (1 - kw) : 2 * kw + pw;
     float v = 0.f;
-    if (td <= 2 && th <= 2 && tw <= 2)
+    if (td <= 2 && th <= 2 && tw <= 2 && cp < Cp)
       v = w[(long long)((td * 3 + th) * 3 + tw) * wtap + (long long)cg * sw_in + (long long)cp * sw_out];
     if (OP == OP_BF16) {
       reinterpret_cast<__nv_bfloat16*>(wp)[i] = __float2bfloat16_rn(v);
@@ -70,15 +70,19 @@ __global__ void pack_s2_kernel(const float* __restrict__ w, void* __restrict__ w
 // packed weights of the equivalent 2x2x2 conv for a DOWN / UP geometry (64 * Cin * Cout elements)
 int launch_pack_s2(const ConvGeom& g, const float* w, float* wp, int op, cudaStream_t s) {
   const int up = g.mode == CONV_UP ? 1 : 0;
-  const int K = up ? g.Cin : 8 * g.Cin, NT = up ? 8 * g.Cout : g.Cout;
+  const int ntd = (g.Cout + 15) / 16 * 16;
+  const int K = up ? g.Cin : 8 * g.Cin, NT = up ? 8 * g.Cout : ntd;
   const long long total = 8LL * K * NT;
   const unsigned grid = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   if (op == OP_BF16)
-    pack_s2_kernel<OP_BF16><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out);
+    pack_s2_kernel<OP_BF16><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out,
+                                              ntd);
   else if (op == OP_F16)
-    pack_s2_kernel<OP_F16><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out);
+    pack_s2_kernel<OP_F16><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out,
+                                              ntd);
   else
-    pack_s2_kernel<OP_TF32><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out);
+    pack_s2_kernel<OP_TF32><<<grid, 256, 0, s>>>(w, wp, up, g.Cin, g.Cout, tc_pick_n(NT), g.wtap, g.sw_in, g.sw_out,
+                                              ntd);
   B3D_LAUNCH_CHECK("pack_s2");
   return B3D_OK;
 }

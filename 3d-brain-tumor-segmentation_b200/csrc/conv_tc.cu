@@ -503,10 +503,10 @@ EncodeTiledFn tma_encode_fn() {
   return fn;
 }
 
-static int pick_n(int Cout) {
+static int pick_n(int Cout) {      // widest N tile that divides the (16-padded) output channels
   if (Cout % 128 == 0) return 128;
-  if (Cout == 64) return 64;
-  if (Cout == 32) return 32;
+  if (Cout % 64 == 0) return 64;
+  if (Cout % 32 == 0) return 32;
   return 16;
 }
 
@@ -532,7 +532,7 @@ static TcProblem tc_problem(const ConvGeom& g) {
     q.ks = g.k; q.hb = g.k == 2 ? g.pad : g.k / 2; q.Cin = pad_cin(g); q.Cout = pad_cout(g.Cout);
     q.D = g.Do; q.H = g.Ho; q.W = g.Wo;
   } else if (g.mode == CONV_DOWN) {
-    q.ks = 2; q.hb = 0; q.Cin = 8 * g.Cin; q.Cout = g.Cout; q.D = g.Do; q.H = g.Ho; q.W = g.Wo;
+    q.ks = 2; q.hb = 0; q.Cin = 8 * g.Cin; q.Cout = pad_cout(g.Cout); q.D = g.Do; q.H = g.Ho; q.W = g.Wo;
     q.s2d = 1; q.Csub = g.Cin;
   } else {
     q.ks = 2; q.hb = 1; q.Cin = g.Cin; q.Cout = 8 * g.Cout; q.D = g.Do / 2; q.H = g.Ho / 2; q.W = g.Wo / 2;
@@ -546,11 +546,13 @@ bool tc_conv_supported(const ConvGeom& g) {
   if (g.mode == CONV_S1)     // narrow inputs (Cin < 8) / outputs (Cout < 16) run zero-padded to one K step / N tile
     return (g.k == 3 || g.k == 1) && g.Cin >= 1 && g.Cout >= 1 && (g.Cin % 8 == 0 || g.Cin < 8) &&
            (g.Cout % 16 == 0 || g.Cout < 16);
+  // stride-2 family.  (Narrow outputs only occur in the VAE bottleneck, 16^3 -> 8^3 x 8 and 16^3 x 128 -> 8^3 x 1:
+  // a few hundred output voxels with a long reduction — those run on conv_gather_splitk_kernel instead.)
   return g.k == 3 && g.Cin % 8 == 0 && g.Cin >= 8 && g.Cout % 16 == 0 && g.Cout >= 16;
 }
 
 size_t tc_packed_weight_elems(const ConvGeom& g) {
-  if (g.mode != CONV_S1) return (size_t)64 * g.Cin * g.Cout;
+  if (g.mode != CONV_S1) return (size_t)64 * pad_cout(g.Cin) * pad_cout(g.Cout);   // symmetric in the channel roles
   return (size_t)g.k * g.k * g.k * ((g.Cin + 15) / 16 * 16) * pad_cout(g.Cout);   // room for either operand type
 }
 
@@ -585,7 +587,7 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   p.vpc = ((long long)g.Do * g.Ho * g.Wo) / p.groups;
   p.s2d = q.s2d; p.d2s = q.d2s; p.Csub = q.Csub;
   p.Din = g.Di; p.doff = g.doff;
-  p.cin_real = g.mode == CONV_S1 ? g.Cin : q.Cin; p.cout_real = g.mode == CONV_S1 ? g.Cout : q.Cout; p.act = g.act;
+  p.cin_real = g.mode == CONV_S1 ? g.Cin : q.Cin; p.cout_real = g.mode == CONV_UP ? q.Cout : g.Cout; p.act = g.act;
   static bool attr_set = false;
   if (!attr_set) {
     B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM),

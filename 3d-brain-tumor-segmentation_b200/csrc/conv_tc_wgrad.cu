@@ -22,6 +22,8 @@
 //   * when fewer than 128 input channels remain, the missing MN groups address shared memory past the
 //     real planes (still inside this CTA's allocation, enforced by the host planner); the
 //     corresponding accumulator rows are never read.
+#include <limits.h>
+
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "tc_ptx.cuh"
@@ -418,45 +420,82 @@ int launch_cast_bf16_s2d(const float* src, void* dst, int B, int D, int H, int W
 // K = voxels GEMM (the KS = 1 case of conv3_wgrad_tc_kernel) with all taps in the M dimension instead of k^3 MMAs
 // whose M = 128 rows hold 2 real channels.  sgn = +1 stacks the layer input x (rows (t, ci)); sgn = -1 stacks dy
 // (dw[t][ci][co] = sum_u x[u][ci] dy[u - (t - pad)][co], rows (t, co)).  thread -> one 16-byte cell.
-__global__ void cast_stack_bf16_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int B, int D, int H,
-                                       int W, int Cn, long long pitch, int k, int sgn, int nA) {
+constexpr int kStD = 4, kStH = 8, kStW = 32;     // voxel tile of the stacking kernel
+__global__ void __launch_bounds__(256)
+    cast_stack_bf16_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int B, int D, int H, int W, int Cn,
+                           long long pitch, int k, int sgn, int nA, int ntd, int nth, int ntw) {
+  extern __shared__ float sh[];                  // halo tile [kStD+2p][kStH+2p][kStW+2p][Cn], zero outside the volume
+  __shared__ int lut[256];                       // stacked row -> offset inside the halo tile (-1: zero padding)
   const int cells = nA / 8, pad = k / 2, rows = k * k * k * Cn;
-  const long long total = (long long)B * D * H * W * cells;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cell = (int)(i % cells);
-    long long r = i / cells;
-    const int w = (int)(r % W); r /= W;
-    const int h = (int)(r % H); r /= H;
-    const int d = (int)(r % D); r /= D;
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int row = cell * 8 + e;
-      v[e] = 0.f;
-      if (row < rows) {
-        const int t = row / Cn, c = row - t * Cn;
-        const int dd = d + sgn * (t / (k * k) - pad), hh = h + sgn * ((t / k) % k - pad), ww = w + sgn * (t % k - pad);
-        if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
-          v[e] = __ldg(src + ((((long long)r * D + dd) * H + hh) * W + ww) * pitch + c);
-      }
+  const int ED = kStD + 2 * pad, EH = kStH + 2 * pad, EW = kStW + 2 * pad;
+  const int ntiles = B * ntd * nth * ntw;
+  for (int row = threadIdx.x; row < nA; row += 256) {
+    int off = INT_MIN;
+    if (row < rows) {
+      const int t = row / Cn, c = row - t * Cn;
+      const int od = sgn * (t / (k * k) - pad), oh = sgn * ((t / k) % k - pad), ow = sgn * (t % k - pad);
+      off = ((od * EH + oh) * EW + ow) * Cn + c;
     }
-    uint4 q;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v[1]), "f"(v[0]));
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v[3]), "f"(v[2]));
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(v[5]), "f"(v[4]));
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(v[7]), "f"(v[6]));
-    dst[i] = q;
+    lut[row] = off;
+  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int q = tile;
+    const int wt = q % ntw; q /= ntw;
+    const int ht = q % nth; q /= nth;
+    const int dt = q % ntd; q /= ntd;
+    const int b = q, d0 = dt * kStD, h0 = ht * kStH, w0 = wt * kStW;
+    __syncthreads();
+    for (int i = threadIdx.x; i < ED * EH * EW * Cn; i += 256) {
+      const int c = i % Cn; int r = i / Cn;
+      const int ew = r % EW; r /= EW;
+      const int eh = r % EH; const int ed = r / EH;
+      const int dd = d0 + ed - pad, hh = h0 + eh - pad, ww = w0 + ew - pad;
+      float v = 0.f;
+      if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
+        v = __ldg(src + ((((long long)b * D + dd) * H + hh) * W + ww) * pitch + c);
+      sh[i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kStD * kStH * kStW * cells; i += 256) {
+      const int cell = i % cells; int r = i / cells;
+      const int lw = r % kStW; r /= kStW;
+      const int lh = r % kStH; const int ld = r / kStH;
+      const int d = d0 + ld, h = h0 + lh, w = w0 + lw;
+      if (d >= D || h >= H || w >= W) continue;
+      const int base = (((ld + pad) * EH + (lh + pad)) * EW + (lw + pad)) * Cn;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int off = lut[cell * 8 + e];
+        v[e] = off == INT_MIN ? 0.f : sh[base + off];
+      }
+      uint4 o;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(v[1]), "f"(v[0]));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v[3]), "f"(v[2]));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(v[5]), "f"(v[4]));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(v[7]), "f"(v[6]));
+      dst[((((long long)b * D + d) * H + h) * W + w) * cells + cell] = o;
+    }
   }
 }
 
 int launch_cast_stack_bf16(const float* src, void* dst, int B, int D, int H, int W, int Cn, long long pitch, int k,
                            int sgn, int nA, cudaStream_t s) {
-  const long long total = (long long)B * D * H * W * (nA / 8);
-  long long blocks = (total + 255) / 256;
-  const long long cap = 32LL * sm_count();
-  if (blocks > cap) blocks = cap;
-  cast_stack_bf16_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, (uint4*)dst, B, D, H, W, Cn, pitch, k, sgn, nA);
+  B3D_REQUIRE(Cn >= 1 && Cn < 8 && nA % 8 == 0 && nA <= 256, B3D_ERR_UNSUPPORTED,
+              "cast_stack: narrow tensors only (1..7 channels)");
+  const int pad = k / 2;
+  const size_t smem = sizeof(float) * (size_t)(kStD + 2 * pad) * (kStH + 2 * pad) * (kStW + 2 * pad) * Cn;
+  static bool attr = false;
+  if (!attr) {
+    B3D_TRY(cuda_ok(cudaFuncSetAttribute(cast_stack_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024),
+                    "cudaFuncSetAttribute(cast_stack)"));
+    attr = true;
+  }
+  const int ntd = (D + kStD - 1) / kStD, nth = (H + kStH - 1) / kStH, ntw = (W + kStW - 1) / kStW;
+  const long long ntiles = (long long)B * ntd * nth * ntw;
+  const long long cap = 4LL * sm_count();
+  cast_stack_bf16_kernel<<<(unsigned)(ntiles < cap ? ntiles : cap), 256, smem, s>>>(src, (uint4*)dst, B, D, H, W, Cn,
+                                                                                   pitch, k, sgn, nA, ntd, nth, ntw);
   B3D_LAUNCH_CHECK("cast_stack_bf16");
   return B3D_OK;
 }

@@ -80,9 +80,9 @@ class ResnetBlock(Layer):
 
     def call(self, inputs, training=None):
         g = self.groups
-        res, _, gap = self.conv3d_ptwise.call(inputs, want_gap=True, aux=True)
+        res, _, gap = self.conv3d_ptwise.call(inputs, want_gap=True, aux=True, share_x=True)
         (conv1, norm1, _), (conv2, norm2, _) = self.convs
-        h1, st1, _ = conv1.call(inputs, gn_groups=g, aux=True)
+        h1, st1, _ = conv1.call(inputs, gn_groups=g, aux=True, share_x=True)
         a1 = norm1.call(h1, stats=st1, relu=True)
         h2, st2, _ = conv2.call(a1, gn_groups=g, aux=True)
         if st2 is None:                                   # chunk boundaries not voxel-aligned: unfused GN2

@@ -82,6 +82,20 @@ class FlatParams:
     def zero_grad(self):
         self.grad.zero_()
 
+    def notify(self, tensor):
+        """A backward kernel has written `tensor`'s gradient straight into the flat buffer (ops.direct_param_grads):
+        tell the data-parallel bucket scheduler, which autograd's post-accumulate hooks would otherwise do."""
+        cb = getattr(self, "grad_ready_cb", None)
+        if cb is not None:
+            cb(tensor)
+
+    def add_l2_grad(self):
+        """grad += 2*l*w over the regularised tensors (what autograd does through model.losses, train.py:146)."""
+        if self.n_reg:
+            if getattr(self, "_ones_reg", None) is None:
+                self._ones_reg = torch.ones(self.n_reg, device=self.theta.device, dtype=torch.float32)
+            ops._call("b3d_l2_grad", self.theta, self.grad, self.offsets, self._ones_reg, 2.0 * float(self.l2))
+
     def attach_grads(self):
         for v in self.order:
             off, n = self.spans[id(v.tensor)]

@@ -56,6 +56,43 @@ def pack_weights(w: torch.Tensor, dgrad: bool, stride: int = 1, transposed: bool
     return out
 
 
+# ---- direct parameter gradients ------------------------------------------------------------------------------
+# Every trainable tensor of a Model is a view of one flat buffer and its .grad a view of the matching flat gradient
+# buffer (model.FlatParams).  Inside `direct_param_grads(flat)` the backward kernels write weight / bias / affine
+# gradients straight into those views and return None to autograd, which removes ~260 tiny "grad += g" launches
+# per step; each parameter is used once per forward, so "write" and "accumulate" coincide (the buffer is zeroed at
+# the start of the step, the L2-regulariser gradient is added afterwards by one kernel).
+_DIRECT = {"flat": None}
+
+
+class direct_param_grads:
+    def __init__(self, flat):
+        self.flat = flat
+
+    def __enter__(self):
+        self.prev = _DIRECT["flat"]
+        _DIRECT["flat"] = self.flat
+
+    def __exit__(self, *a):
+        _DIRECT["flat"] = self.prev
+        return False
+
+
+def _grad_target(p, shape=None):
+    """(tensor to write the gradient of parameter p into, direct?)"""
+    flat = _DIRECT["flat"]
+    if flat is not None and p is not None and getattr(p, "_b3d_flat", None) is flat and p.grad is not None:
+        return (p.grad if shape is None else p.grad.reshape(shape)), True
+    if p is None:
+        return None, False
+    return torch.empty(p.shape if shape is None else shape, device=p.device, dtype=p.dtype), False
+
+
+def _grad_done(p, direct):
+    if direct:
+        _DIRECT["flat"].notify(p)
+
+
 # set False to force the CUDA-core kernels everywhere (used by tests to cross-check the tcgen05 path)
 USE_TC = {"on": True}
 
@@ -86,7 +123,8 @@ class Conv3dFn(Function):
     GroupNorm chunk statistics and global-average-pool sums of its output from the epilogue."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, stride, transposed, act, gn_groups, want_gap):
+    def forward(ctx, x, w, bias, stride, transposed, act, gn_groups, want_gap, share_x=False):
+        ctx.share_x = bool(share_x)
         _check(x)
         x = x.contiguous()
         B, D, H, W_, Cin = x.shape
@@ -109,6 +147,7 @@ class Conv3dFn(Function):
         _call("b3d_conv3d_fwd", x, w, bias, y, stride, int(transposed), int(act), stats, gn_groups or 1, gap, 0, wp)
         ctx.save_for_backward(x, w, y if act else None)
         ctx.cfg = (stride, transposed, act, bias is not None)
+        ctx.params = (w, bias)
         outs = (y, stats, gap)
         ctx.mark_non_differentiable(*[t for t in (stats, gap) if t is not None])
         return outs
@@ -130,24 +169,43 @@ class Conv3dFn(Function):
                 wp = pack_weights(w, True, stride, transposed)
             _call("b3d_conv3d_dgrad", dy, w, dx, stride, int(transposed), 0, wp)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(w)
-            db = _new((dy.shape[-1],), dy) if has_bias else None
+            pw, pb = ctx.params
+            dw, dw_direct = _grad_target(pw)
+            db, db_direct = _grad_target(pb) if has_bias else (None, False)
             xb = yb = None
+            ready = 0
             if USE_TC["on"]:
                 xc, yc = _ll(), _ll()
-                if lib.b3d_conv3d_wgrad_plan(w.shape[0], stride, int(transposed), x.shape[-1], dy.shape[-1],
-                                             _byref(xc), _byref(yc)):
-                    xb = torch.empty(x.numel() // x.shape[-1] * xc.value, device=x.device, dtype=torch.bfloat16)
+                kind = lib.b3d_conv3d_wgrad_plan(w.shape[0], stride, int(transposed), x.shape[-1], dy.shape[-1],
+                                                 _byref(xc), _byref(yc))
+                if kind:
+                    # the two convs of a ResnetBlock (pointwise + first 3x3x3) read the same input: its plain bf16
+                    # copy is made by whichever weight gradient runs first and handed to the other
+                    key = (x.data_ptr(), tuple(x.shape)) if (kind == 1 and stride == 1 and ctx.share_x) else None
+                    xb = _XB_CACHE.pop(key, None) if key is not None else None
+                    if xb is not None:
+                        ready = 1
+                    else:
+                        xb = torch.empty(x.numel() // x.shape[-1] * xc.value, device=x.device, dtype=torch.bfloat16)
+                        if key is not None:
+                            _XB_CACHE[key] = xb
                     yb = torch.empty(dy.numel() // dy.shape[-1] * yc.value, device=x.device, dtype=torch.bfloat16)
-            _call("b3d_conv3d_wgrad", x, dy, dw, db, stride, int(transposed), xb, yb)
-        return dx, dw, db, None, None, None, None, None
+            _call("b3d_conv3d_wgrad", x, dy, dw, db, stride, int(transposed), xb, yb, ready)
+            _grad_done(pw, dw_direct)
+            _grad_done(pb, db_direct)
+            dw, db = (None if dw_direct else dw), (None if db_direct else db)
+        return dx, dw, db, None, None, None, None, None, None
 
 
-def conv3d(x, w, bias=None, stride=1, transposed=False, act=0, gn_groups=0, want_gap=False):
+# bf16 copies of conv inputs shared between two weight gradients of one backward pass (cleared every step)
+_XB_CACHE = {}
+
+
+def conv3d(x, w, bias=None, stride=1, transposed=False, act=0, gn_groups=0, want_gap=False, share_x=False):
     ctx = _slab.current()
     if ctx is not None:        # depth-slab sharded inference: halo exchange + all-reduced GAP, no fused GN stats
         return ctx.conv3d(x, w, bias, stride, transposed, act, want_gap)
-    return Conv3dFn.apply(x, w, bias, stride, transposed, act, gn_groups, want_gap)
+    return Conv3dFn.apply(x, w, bias, stride, transposed, act, gn_groups, want_gap, share_x)
 
 
 class GroupNormFn(Function):
@@ -171,6 +229,7 @@ class GroupNormFn(Function):
         _call("b3d_gn_apply", x, stats, gamma, beta, y, groups, float(eps), int(relu))
         ctx.save_for_backward(x, gamma, beta, stats)
         ctx.cfg = (groups, float(eps), int(relu))
+        ctx.params = (gamma, beta)
         return y
 
     @staticmethod
@@ -178,12 +237,16 @@ class GroupNormFn(Function):
         x, gamma, beta, stats = ctx.saved_tensors
         groups, eps, relu = ctx.cfg
         dy = dy.contiguous()
-        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+        pg, pb = ctx.params
+        dgamma, dg_direct = _grad_target(pg)
+        dbeta, db_direct = _grad_target(pb)
         csum = torch.empty_like(stats)
         _call("b3d_gn_bwd_reduce", dy, x, stats, gamma, beta, dgamma, dbeta, csum, groups, eps, relu)
+        _grad_done(pg, dg_direct)
+        _grad_done(pb, db_direct)
         dx = torch.empty_like(x)
         _call("b3d_gn_bwd_apply", dy, x, stats, gamma, beta, csum, dx, groups, eps, relu)
-        return dx, dgamma, dbeta, None, None, None, None
+        return dx, (None if dg_direct else dgamma), (None if db_direct else dbeta), None, None, None, None
 
 
 def group_norm(x, gamma, beta, stats=None, groups=8, eps=1e-5, relu=False):
@@ -215,6 +278,7 @@ class BlockEpilogueFn(Function):
               wsp_v, chse, out, groups, float(eps), int(has_gn))
         ctx.save_for_backward(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, hidden, chse)
         ctx.cfg = (groups, float(eps), has_gn, inv)
+        ctx.params = (gamma2, beta2, wsp, w1, w2)
         return out
 
     @staticmethod
@@ -224,15 +288,19 @@ class BlockEpilogueFn(Function):
         dout = dout.contiguous()
         B, F = res.shape[0], res.shape[-1]
         wsp_v = wsp.reshape(F)
-        dchse, dwsp = _new((B, F), res), _new((F,), res)
-        dgamma = torch.empty_like(gamma2) if has_gn else None
-        dbeta = torch.empty_like(beta2) if has_gn else None
+        pg, pb, pwsp, pw1, pw2 = ctx.params
+        dchse = _new((B, F), res)
+        dwsp, dwsp_direct = _grad_target(pwsp, (F,))
+        dgamma, dg_direct = _grad_target(pg) if has_gn else (None, False)
+        dbeta, db_direct = _grad_target(pb) if has_gn else (None, False)
         csum = torch.empty_like(stats2) if has_gn else None
         _call("b3d_block_epilogue_bwd_reduce", dout, res, h2 if has_gn else None, stats2,
               gamma2 if has_gn else None, beta2 if has_gn else None, wsp_v, dchse, dwsp, dgamma, dbeta, csum,
               groups, eps, int(has_gn))
-        dw1, dw2, dgap = torch.empty_like(w1), torch.empty_like(w2), _new((B, F), res)
+        (dw1, dw1_direct), (dw2, dw2_direct), dgap = _grad_target(pw1), _grad_target(pw2), _new((B, F), res)
         _call("b3d_se_fc_bwd", gap_sum, w1, w2, hidden, chse, dchse, dw1, dw2, dgap, inv)
+        for p_, d_ in ((pwsp, dwsp_direct), (pg, dg_direct), (pb, db_direct), (pw1, dw1_direct), (pw2, dw2_direct)):
+            _grad_done(p_, d_)
         dres = torch.empty_like(res)
         dh2 = torch.empty_like(h2) if has_gn else None
         _call("b3d_block_epilogue_bwd_apply", dout, res, h2 if has_gn else None, stats2,
@@ -240,7 +308,9 @@ class BlockEpilogueFn(Function):
               groups, eps, int(has_gn))
         if not has_gn:
             dh2 = dout
-        return dres, dh2, None, dgamma, dbeta, dwsp.reshape(wsp.shape), None, dw1, dw2, None, None
+        return (dres, dh2, None, None if dg_direct else dgamma, None if db_direct else dbeta,
+                None if dwsp_direct else dwsp.reshape(wsp.shape), None, None if dw1_direct else dw1,
+                None if dw2_direct else dw2, None, None)
 
 
 def block_epilogue(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups=8, eps=1e-5):
@@ -256,6 +326,7 @@ class DenseFn(Function):
         _call("b3d_dense_fwd", x, w, b, y, int(act))
         ctx.save_for_backward(x, w, y)
         ctx.cfg = (int(act), b is not None)
+        ctx.params = (w, b)
         return y
 
     @staticmethod
@@ -264,10 +335,13 @@ class DenseFn(Function):
         act, has_b = ctx.cfg
         dy = dy.contiguous()
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w)
-        db = _new((w.shape[1],), w) if has_b else None
+        pw, pb = ctx.params
+        dw, dw_direct = _grad_target(pw)
+        db, db_direct = _grad_target(pb) if has_b else (None, False)
         _call("b3d_dense_bwd", x, w, y, dy, dx, dw, db, act)
-        return dx, dw, db, None
+        _grad_done(pw, dw_direct)
+        _grad_done(pb, db_direct)
+        return dx, (None if dw_direct else dw), (None if db_direct else db), None
 
 
 def dense(x, w, b=None, act=0):

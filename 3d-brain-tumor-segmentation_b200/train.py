@@ -32,7 +32,9 @@ class GradientTape:
     def __exit__(self, *a):
         return False
 
-    def gradient(self, loss, variables, model: Optional[Model] = None):
+    def gradient(self, loss, variables, model: Optional[Model] = None, direct: bool = False):
+        """`direct`: the backward kernels write parameter gradients straight into the model's flat gradient
+        buffer (ops.direct_param_grads) instead of handing them to autograd's accumulation."""
         flat = getattr(variables[0], "_b3d_flat", None)
         if flat is not None:
             flat.zero_grad()
@@ -40,7 +42,13 @@ class GradientTape:
         else:
             for v in variables:
                 v.grad = None
-        loss.backward()
+        ops._XB_CACHE.clear()
+        if direct and flat is not None:
+            with ops.direct_param_grads(flat):
+                loss.backward()
+        else:
+            loss.backward()
+        ops._XB_CACHE.clear()
         return [v.grad for v in variables]
 
 
@@ -59,18 +67,21 @@ def train_step(model: Model, optimizer: ScheduledOptim, loss_fn: DiceVAELoss, di
     with GradientTape() as tape:
         y_pred, y_vae, z_mean, z_logvar = model(x, training=True, inference=False,
                                                 dropout_mask=dropout_mask, eps=eps)
-        loss = loss_fn(x, y, y_pred, y_vae, z_mean, z_logvar)
+        data_loss = loss_fn(x, y, y_pred, y_vae, z_mean, z_logvar)
         reg = reduce_sum(model.losses)
-        loss = loss + (reg.detach() if dp is not None else reg)
+        loss = data_loss + reg.detach()
     macro_dice, micro_dice = dice_fn(y, y_pred)
     variables = model.trainable_variables
     if dp is not None:
         dp.begin_backward()
-    grads = tape.gradient(loss, variables)
+    # the regulariser's gradient 2*l*w is a single pass over the flat buffer: after backward (one GPU), or inside
+    # the Adam kernel (data parallel: it must not be averaged over ranks)
+    grads = tape.gradient(data_loss, variables, direct=True)
     if dp is not None:
         dp.finish_backward()
         optimizer.apply_flat(model.flat, l2_in_step=True)
     else:
+        model.flat.add_l2_grad()
         optimizer.apply_gradients(zip(grads, variables), flat=model.flat)
     return loss.detach(), macro_dice, micro_dice
 
@@ -100,6 +111,7 @@ class DataParallel:
         if self.overlap:
             for v in self.flat.order:
                 v.tensor.register_post_accumulate_grad_hook(self._on_grad)
+            self.flat.grad_ready_cb = self._on_grad      # gradients written directly by the backward kernels
         self._active = False
 
     @staticmethod

@@ -65,9 +65,11 @@ int b3d_conv3d_dgrad(const DLTensor* dy, const DLTensor* w, DLTensor* dx, int st
 /* weight (+ bias, nullable) gradient.  x_bf16 / dy_bf16 (nullable, bf16): scratch buffers of
  * voxels * (channels per voxel reported by b3d_conv3d_wgrad_plan) elements; when both are given they are filled
  * with bf16 copies of x / dy (space-to-depth order for stride 2, all taps stacked for narrow tensors) and the
- * tcgen05 kernel (bf16 operands, fp32 accumulation) is used, else the fp32 CUDA-core kernel. */
+ * tcgen05 kernel (bf16 operands, fp32 accumulation) is used, else the fp32 CUDA-core kernel.
+ * x_bf16_ready != 0: x_bf16 already holds the plain bf16 copy of x (stride-1 layers sharing their input). */
 int b3d_conv3d_wgrad(const DLTensor* x, const DLTensor* dy, DLTensor* dw, DLTensor* dbias, int stride,
-                     int transposed, const DLTensor* x_bf16, const DLTensor* dy_bf16, void* stream);
+                     int transposed, const DLTensor* x_bf16, const DLTensor* dy_bf16, int x_bf16_ready,
+                     void* stream);
 int b3d_conv3d_wgrad_tc_supported(int k, int stride, int transposed, int cin, int cout);
 /* returns 0 (CUDA cores), 1 (plain copies), 2 / 3 (narrow input / output: tap-stacked copy); *x_ch, *dy_ch
  * receive the bf16 channels per voxel of the two scratch buffers */

@@ -46,6 +46,7 @@ CONV_CASES = [
     ((8, 16, 8), 32, 16, 3, 2, True),
     ((6, 10, 18), 64, 32, 3, 2, True),
     ((4, 4, 4), 512, 64, 3, 2, True),
+    ((4, 4, 4), 512, 8, 3, 2, False),          # VAE bottleneck: few outputs, long reduction (split-reduction kernel)
     ((4, 16, 8), 64, 32, 3, 1, False),
 ]
 

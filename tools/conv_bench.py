@@ -60,7 +60,7 @@ for n, cin, cout in SHAPES:
         assert b3d._lib.lib.b3d_conv3d_wgrad_plan(3, 1, 0, cin, cout, ctypes.byref(xc), ctypes.byref(yc))
         xb = torch.empty(n ** 3 * xc.value, device=dev, dtype=torch.bfloat16)
         yb = torch.empty(n ** 3 * yc.value, device=dev, dtype=torch.bfloat16)
-        ms = timeit(lambda: ops._call("b3d_conv3d_wgrad", x, dy, dw, None, 1, 0, xb, yb))
+        ms = timeit(lambda: ops._call("b3d_conv3d_wgrad", x, dy, dw, None, 1, 0, xb, yb, 0))
         line += f"| wgrad(+casts) {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s "
     if which in ("k1", "all") and cin >= 8 and cout >= 16:
         w1 = torch.randn(1, 1, 1, cin, cout, device=dev) * 0.05
