@@ -208,3 +208,42 @@ def test_inference_tta_matches_oracle(b3d, dev):
     agree = (y.argmax(-1).cpu()[inside] == ref.argmax(-1)[inside]).float().mean()
     assert float(agree) >= 0.999, float(agree)
     assert float(y[~inside.to(dev)].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("mode", ["fp32", "mixed"])
+def test_skull_strip_variant_matches_oracle(b3d, dev, mode):
+    """BASELINE config 5: the skull-stripping model (in_ch=1, out_ch=1; /root/reference/args.py skull-strip
+    defaults) — one training step and the inference forward against the fp64 oracle.  Exercises the narrow-channel
+    paths end to end (1-channel input conv, 1-channel output conv and VAE output, their gradients)."""
+    crop = (32, 32, 48)
+    p = R.init_params(R.param_shapes(in_ch=1, out_ch=1, crop=crop))
+    x, y, eps, mask = R.synth_batch((1,) + crop, in_ch=1, out_ch=1)
+    pg = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    outs = R.model_forward(pg, x, eps, dropout_mask=mask)
+    ref = R.dice_vae_loss(x, y, *outs) + R.l2_reg(pg)
+    ref.backward()
+    yi_ref = R.model_forward(p, x, eps, inference=True)[0]
+    set_mode(b3d, mode)
+    try:
+        model, f = build(b3d, dev, crop, p, in_ch=1, out_ch=1)
+        with torch.no_grad():
+            yi = model(f(x), training=False, inference=True)[0]
+        opt = b3d.ScheduledOptim(learning_rate=1e-4)
+        opt(epoch=0)
+        loss, macro, micro = b3d.train_step(model, opt, b3d.DiceVAELoss(), b3d.DiceCoefficient(), f(x), f(y),
+                                            dropout_mask=f(mask), eps=f(eps))
+        torch.cuda.synchronize()
+    finally:
+        reset_mode(b3d)
+    tol = 2e-5 if mode == "fp32" else 2e-3
+    assert rel(yi, yi_ref) < tol, rel(yi, yi_ref)
+    assert abs(float(loss) - float(ref)) / float(ref) < 1e-3
+    nv = model.named_variables()
+    errs = sorted(((rel(nv[k].grad, pg[k].grad), k) for k in p), reverse=True)
+    coss = sorted((_cos(nv[k].grad, pg[k].grad), k) for k in p)
+    print(f"skull-strip {mode}: loss rel {abs(float(loss) - float(ref)) / float(ref):.2e}, worst grad {errs[0]}, "
+          f"min cos {coss[0]}")
+    if mode == "fp32":
+        assert errs[len(errs) // 2][0] < 3e-2 and errs[0][0] < 2e-1, errs[:5]
+    else:
+        assert coss[0][0] > 0.90 and coss[len(coss) // 10][0] > 0.98, coss[:5]

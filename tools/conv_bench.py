@@ -36,6 +36,8 @@ def timeit(fn):
     return statistics.median(ts)
 
 
+if len(sys.argv) > 4:      # e.g. "128,32,16": only this shape (ncu captures)
+    SHAPES = [tuple(int(v) for v in sys.argv[4].split(","))]
 for n, cin, cout in SHAPES:
     x = torch.randn(1, n, n, n, cin, device=dev)
     dy = torch.randn(1, n, n, n, cout, device=dev)
