@@ -15,7 +15,7 @@ from .layers import (GroupNormalization, ResnetBlock, ConvDownsample, MaxDownsam
 from .model import Model  # noqa: F401
 from .util import DiceVAELoss, DiceCoefficient, ScheduledOptim  # noqa: F401
 from . import train, infer, slab  # noqa: F401
-from .slab import (SlabContext, DistComm, ThreadComm, slab_bounds, sharded_inference,  # noqa: F401
+from .slab import (SlabContext, DistComm, PeerComm, ThreadComm, slab_bounds, sharded_inference,  # noqa: F401
                    GraphedInference)
 from .infer import TestTimeAugmentor, pad_to_spatial_res  # noqa: F401
 from .train import GradientTape, train_step, GraphedTrainStep, DataParallel, reduce_sum  # noqa: F401

@@ -102,6 +102,9 @@ SIGNATURES = {
     "b3d_mul_scale": "TTTfv",
     "b3d_sigmoid_bwd": "TTTv",
     "b3d_copy_channels": "TTiv",
+    "b3d_halo_exchange": "TTTTLLTTiLv",
+    "b3d_peer_allreduce": "TTiTTiv",
+    "b3d_epoch_tick": "Tv",
     "b3d_flip_normalize": "TTTTiv",
     "b3d_flip_accumulate": "TTTifiv",
 }
@@ -118,6 +121,8 @@ lib.b3d_conv3d_wgrad_tc_supported.restype = _i
 lib.b3d_conv3d_wgrad_plan.argtypes = [_i] * 5 + [C.POINTER(_ll), C.POINTER(_ll)]
 lib.b3d_conv3d_wgrad_plan.restype = _i
 lib.b3d_set_conv_precision.argtypes = [_i, _i]
+lib.b3d_slab_sym_bytes.argtypes = [_ll]
+lib.b3d_slab_sym_bytes.restype = _ll
 lib.b3d_get_conv_precision.restype = _i
 
 

@@ -78,6 +78,11 @@ struct TcParams {
   // channel padding: Cin / Cout above are the padded (virtual) counts the MMAs run on; the tensors hold cin_real /
   // cout_real channels (first conv: 2 input channels; output convs: 2-3 classes).  act: 1 = sigmoid epilogue.
   int cin_real, cout_real, act;
+  // split-K (small volumes with long reductions: far fewer tiles than SMs): blockIdx.z owns `kchunks` consecutive K
+  // chunks and stores its partial result into slice z of a workspace (`y` points at it, `ws_slice` elements per
+  // slice); conv_finish_kernel then sums the slices and applies bias / statistics / GAP
+  int ksplit, kchunks;
+  long long ws_slice;
 };
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -133,7 +138,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nchunks = prm.Cin / C::CK;
+  const int nchunks_all = prm.Cin / C::CK;
+  const int c_begin = blockIdx.z * prm.kchunks;
+  const int nchunks = min(prm.kchunks, nchunks_all - c_begin);   // this CTA's K chunks: [c_begin, c_begin + nchunks)
   const int nsp = blockIdx.y;  // N split
 
   if (threadIdx.x == 0) {
@@ -168,11 +175,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
         mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
         uint8_t* dst0 = halo + hs * C::HALO_BYTES;
         uint8_t* dst1 = dst0 + C::PLANE_BYTES;
-        const float* xc = xb + c * C::CK;
+        const int cg = c_begin + c;              // global K-chunk index
+        const float* xc = xb + cg * C::CK;
         int sp_d = 0, sp_h = 0, sp_w = 0;      // s2d: parity of this chunk's channels
         if (prm.s2d) {
-          const int par = (c * C::CK) / prm.Csub;
-          xc = xb + (c * C::CK) % prm.Csub;
+          const int par = (cg * C::CK) / prm.Csub;
+          xc = xb + (cg * C::CK) % prm.Csub;
           sp_d = par >> 2; sp_h = (par >> 1) & 1; sp_w = par & 1;
         }
         // one lane = one halo voxel: the whole CK-channel chunk is fetched with 256-bit loads (full 32-byte
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
     if (lane == 0) {
       int ws = 0, wph = 0;
       const uint8_t* wsrc =
-          reinterpret_cast<const uint8_t*>(prm.wp) + (size_t)nsp * nchunks * C::TAPS * C::TAP_BYTES;
+          reinterpret_cast<const uint8_t*>(prm.wp) + ((size_t)nsp * nchunks_all + c_begin) * C::TAPS * C::TAP_BYTES;
       constexpr int kStagesPerChunk = C::TAPS / C::TPS;
       for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
         for (int cs = 0; cs < nchunks * kStagesPerChunk; ++cs) {
@@ -376,7 +384,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
           }
           float v[16];
           tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + p * C::N + j * 16, v);
-          if (valid && ncol < 16) {
+          if (valid && prm.ksplit > 1) {
+            // partial sums of this K range -> workspace slice blockIdx.z
+            float4* dst = reinterpret_cast<float4*>(yp + (long long)blockIdx.z * prm.ws_slice);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else if (valid && ncol < 16) {
             // narrow output (Cout < 16: the 2-3 channel output convs): scalar stores, optional sigmoid
 #pragma unroll
             for (int i = 0; i < 16; ++i)
@@ -451,6 +464,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+}
+
+// ------------------------------------------------------------------------------------------ split-K epilogue
+// y = sum of the split-K workspace slices + bias, with the GroupNorm chunk statistics and per-channel sums of y.
+// grid = (B * G, segments): blockIdx.x = contiguous chunk of a sample (G = groups, or 8 pseudo-chunks), blockIdx.y
+// = 8192-element segment of it; statistics / GAP are accumulated with atomics into buffers zeroed by the caller.
+__global__ void __launch_bounds__(256)
+    conv_finish_kernel(float* __restrict__ y, const float* __restrict__ ws, int ksplit, long long ws_slice,
+                       const float* __restrict__ bias, double* __restrict__ stats, float* __restrict__ gap,
+                       long long L, int C, int G) {
+  extern __shared__ float sgap[];                  // [C]
+  __shared__ double red[64];
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  for (int i = threadIdx.x; i < C; i += 256) sgap[i] = 0.f;
+  __syncthreads();
+  const long long off = ((long long)b * G + g) * L;
+  float* yc = y + off;
+  const long long e0 = (long long)g * L;           // element offset inside the sample (channel = (e0 + e) % C)
+  double d[2] = {0.0, 0.0};
+  const long long seg0 = (long long)blockIdx.y * 8192, seg1 = min(L, seg0 + 8192);
+  for (long long e = seg0 + threadIdx.x * 4LL; e < seg1; e += 256 * 4) {
+    float4 v = ld_stream(reinterpret_cast<const float4*>(ws + off + e));
+    for (int z = 1; z < ksplit; ++z) {
+      const float4 t = ld_stream(reinterpret_cast<const float4*>(ws + (long long)z * ws_slice + off + e));
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    const int c = (int)((e0 + e) % C);
+    if (bias != nullptr) { v.x += bias[c]; v.y += bias[c + 1]; v.z += bias[c + 2]; v.w += bias[c + 3]; }
+    *reinterpret_cast<float4*>(yc + e) = v;
+    d[0] += (double)((v.x + v.y) + (v.z + v.w));
+    d[1] += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+    if (gap != nullptr) {
+      atomicAdd(&sgap[c], v.x); atomicAdd(&sgap[c + 1], v.y); atomicAdd(&sgap[c + 2], v.z); atomicAdd(&sgap[c + 3], v.w);
+    }
+  }
+  block_sum<2, double>(d, red);
+  if (stats != nullptr && threadIdx.x == 0) {      // G == groups when statistics are requested
+    atomicAdd(&stats[2 * blockIdx.x], d[0]);
+    atomicAdd(&stats[2 * blockIdx.x + 1], d[1]);
+  }
+  __syncthreads();
+  if (gap != nullptr)
+    for (int i = threadIdx.x; i < C; i += 256) atomicAdd(&gap[(long long)b * C + i], sgap[i]);
 }
 
 // ------------------------------------------------------------------------------------------ packing
@@ -574,6 +630,21 @@ int launch_tc_pack_weights(const ConvGeom& g, const float* w, float* wp, cudaStr
   return B3D_OK;
 }
 
+// split-K workspace: 64 MB per device, allocated lazily (never while the stream is being captured)
+constexpr long long kSplitWsElems = 16LL << 20;
+static float* splitk_workspace(cudaStream_t s) {
+  static float* ws[16] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return nullptr;
+  if (ws[dev] == nullptr) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+    if (cudaMalloc(&ws[dev], sizeof(float) * kSplitWsElems) != cudaSuccess) { cudaGetLastError(); ws[dev] = nullptr; }
+  }
+  return ws[dev];
+}
+
 template <class C>
 static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, const float* wp, const float* bias,
                       float* y, double* stats, float* gap, cudaStream_t s) {
@@ -597,8 +668,40 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   const int nsplit = q.Cout / C::N;
   dim3 grid((unsigned)(p.ntiles < sm_count() ? p.ntiles : sm_count()), (unsigned)nsplit, 1);
   if (nsplit > 1) grid.x = (grid.x + nsplit - 1) / nsplit;   // keep ~one persistent CTA per SM in total
+  // split-K: small volumes (the 16^3 level, thin inference slabs) give far fewer tiles than SMs while their
+  // reductions are the longest of the net (Cin up to 512): spread the K chunks over blockIdx.z.  Partial results go
+  // through a per-device workspace that is allocated on first use (outside CUDA-graph capture) and kept.
+  const int nchunks = q.Cin / C::CK;
+  const long long S = (long long)g.Do * g.Ho * g.Wo;
+  const long long out_elems = (long long)g.B * S * g.Cout;
+  p.ksplit = 1; p.kchunks = nchunks; p.ws_slice = 0;
+  const int ctas = (int)(grid.x * grid.y);
+  float* ws = nullptr;
+  if (ctas * 4 <= sm_count() && nchunks >= 8 && g.act == 0 && !g.accumulate && g.Cout % 16 == 0 && g.yp == g.Cout &&
+      (S * g.Cout) % 32 == 0 && (stats == nullptr || p.groups == 8 || S % p.groups == 0)) {
+    int ks = sm_count() / ctas;
+    if (ks > nchunks / 4) ks = nchunks / 4;
+    if (ks > 8) ks = 8;
+    while (ks >= 2 && ks * out_elems > kSplitWsElems) --ks;
+    if (ks >= 2 && (ws = splitk_workspace(s)) != nullptr) {
+      p.kchunks = (nchunks + ks - 1) / ks;
+      p.ksplit = (nchunks + p.kchunks - 1) / p.kchunks;
+    }
+  }
+  if (p.ksplit > 1) {
+    grid.z = (unsigned)p.ksplit;
+    p.bias = nullptr; p.stats = nullptr; p.gap = nullptr;
+    p.y = ws; p.ws_slice = out_elems;
+  }
   conv_tc_kernel<C><<<grid, kTcThreads, C::SMEM, s>>>(p);
   B3D_LAUNCH_CHECK("conv_tc");
+  if (p.ksplit > 1) {
+    const int G = stats != nullptr ? (g.groups > 0 ? g.groups : 1) : 8;
+    const long long L = S * g.Cout / G;
+    conv_finish_kernel<<<dim3(g.B * G, (unsigned)((L + 8191) / 8192)), 256, sizeof(float) * g.Cout, s>>>(
+        y, ws, p.ksplit, out_elems, bias, stats, gap, L, g.Cout, G);
+    B3D_LAUNCH_CHECK("conv_finish");
+  }
   return B3D_OK;
 }
 

@@ -101,6 +101,65 @@ class DistComm(Comm):
         return torch.cat(parts, dim=1)
 
 
+class PeerComm(Comm):
+    """NVLink peer-memory backend: every rank allocates one symmetric buffer (torch symmetric memory: cuMem allocation
+    mapped into all peers of the box), boundary slices are stored straight into the neighbour's mailbox by a copy
+    kernel and published / awaited with system-scope release / acquire flags; small reductions are one-kernel
+    all-to-all sums (csrc/slab_comm.cu).  No NCCL call on the data path, everything is CUDA-graph capturable."""
+
+    def __init__(self, group=None, mailbox_bytes: int = 8 << 20):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from ._lib import lib
+        self.dist = dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.mailbox_bytes = int(mailbox_bytes)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nbytes = int(lib.b3d_slab_sym_bytes(self.mailbox_bytes))
+        self.sym = symm.empty(nbytes // 4, dtype=_f32, device=dev)
+        self.sym.zero_()
+        torch.cuda.synchronize()
+        self.hdl = symm.rendezvous(self.sym, self.group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.peers = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self.prev_base = ptrs[self.rank - 1] if self.rank > 0 else 0
+        self.next_base = ptrs[self.rank + 1] if self.rank < self.world - 1 else 0
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.hseq = self.aseq = 0
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+
+    def begin_forward(self):
+        """Called once per forward (SlabContext.__enter__): new epoch, sequence numbers restart."""
+        from . import ops
+        ops._call("b3d_epoch_tick", self.epoch)
+        self.hseq = self.aseq = 0
+
+    def exchange(self, send_prev, send_next, recv_prev, recv_next):
+        from . import ops
+        if self.world == 1:
+            return
+        c = lambda t: None if t is None else t.contiguous()
+        ops._call("b3d_halo_exchange", c(send_prev), c(send_next), recv_prev, recv_next, self.prev_base, self.next_base,
+                  self.sym, self.epoch, self.hseq, self.mailbox_bytes)
+        self.hseq += 1
+
+    def all_reduce_sum(self, t):
+        from . import ops
+        if self.world == 1:
+            return
+        ops._call("b3d_peer_allreduce", t, self.peers, self.rank, self.sym, self.epoch, self.aseq)
+        self.aseq += 1
+
+    def all_gather_cat(self, t, sizes):
+        if self.world == 1:
+            return t
+        parts = [torch.empty((t.shape[0], n) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device) for n in sizes]
+        self.dist.all_gather(parts, t.contiguous(), group=self.group)
+        return torch.cat(parts, dim=1)
+
+
 class _ThreadShared:
     def __init__(self, world):
         self.world = world
@@ -172,6 +231,8 @@ class SlabContext:
     def __enter__(self):
         self._prev = current()
         _TLS.ctx = self
+        if hasattr(self.comm, "begin_forward"):
+            self.comm.begin_forward()
         return self
 
     def __exit__(self, *a):

@@ -185,9 +185,18 @@ def measure_inference(b3d, torch, dev, model, reps=3):
             e1.record(); e1.synchronize()
             if i:
                 times.append(e0.elapsed_time(e1))
+    ms_eager = statistics.median(times)
+    gi = b3d.GraphedInference(model, x)
+    times = []
+    for i in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); gi(); e1.record(); e1.synchronize()
+        if i:
+            times.append(e0.elapsed_time(e1))
     ms = statistics.median(times)
     return {"shape_padded": list(shape), "ms_per_forward": ms, "mvoxel_per_s": 155 * 190 * 147 / ms / 1e3,
-            "gflop_per_forward": 1006.8, "note": "eager (no CUDA graph), 1 GPU; 8-flip TTA = 8 such forwards"}
+            "ms_per_forward_eager": ms_eager, "gflop_per_forward": 1006.8,
+            "note": "CUDA-graph replay of model(x, inference=True), 1 GPU; 8-flip TTA = 8 such forwards"}
 
 
 def measure_inference_sharded(b3d, torch, dist, dev, model, world, reps=3):
@@ -200,12 +209,14 @@ def measure_inference_sharded(b3d, torch, dist, dev, model, world, reps=3):
     x[:, 155:], x[:, :, 190:], x[:, :, :, 147:] = 0, 0, 0
     x = x.to(dev)
     comm = b3d.DistComm()
+    d0, d1 = b3d.slab_bounds(shape[0], world)[comm.rank]
+    gi = b3d.GraphedInference(model, x[:, d0:d1].contiguous(), comm, depth=shape[0])   # halo exchanges captured too
     times, err = [], None
     for i in range(reps + 1):
         dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        y, (d0, d1) = b3d.sharded_inference(model, x, comm, gather=False)
+        y = gi()
         e1.record(); e1.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -219,7 +230,7 @@ def measure_inference_sharded(b3d, torch, dist, dev, model, world, reps=3):
     return {"shape_padded": list(shape), "n_gpus": world, "ms_per_forward": ms,
             "mvoxel_per_s": 155 * 190 * 147 / ms / 1e3, "max_rel_l2_vs_unsharded": float(e),
             "slabs": [b - a for a, b in b3d.slab_bounds(shape[0], world)],
-            "note": "depth-slab sharded, eager; halo exchange + GN/SE all-reduces over NCCL"}
+            "note": "depth-slab sharded, one CUDA graph per rank incl. the NCCL halo exchanges and GN/SE all-reduces"}
 
 
 def run_b3d(args):
@@ -308,7 +319,8 @@ def run_b3d(args):
     roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::f16, fp16 operands, fp32 accumulate) dec.L0 conv1 128^3 32->16",
             "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
             "peak_source": f"{pk_src} dense bf16 burst (cuBLAS 8192^3); 16-bit operands, same tensor-pipe rate",
-            "ms_per_launch": conv_ms, "traffic": None}
+            "ms_per_launch": conv_ms, "traffic": 363.6e6, "traffic_unit": "bytes/launch (dram read+write, ncu --set full, "
+            "profiles/r01_ncu_conv_tc_fp16_128cube_32to16.csv; algorithmic 402.7e6)"}
     # CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

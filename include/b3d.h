@@ -168,6 +168,22 @@ int b3d_mul_scale(const DLTensor* a, const DLTensor* b, DLTensor* y, float scale
 int b3d_sigmoid_bwd(const DLTensor* dy, const DLTensor* y, DLTensor* dx, void* stream);
 int b3d_copy_channels(const DLTensor* src, DLTensor* dst, int accumulate, void* stream);
 
+/* ---- depth-slab sharded inference over NVLink peer memory (csrc/slab_comm.cu; host side slab.PeerComm) -----------
+ * Every rank owns one symmetric buffer of b3d_slab_sym_bytes(mailbox_bytes) bytes mapped into its peers.
+ * halo_exchange: my first / last boundary slices (send_prev / send_next, nullable) are stored into the neighbours'
+ *   mailboxes and published with a system-scope release store; theirs are awaited (acquire spin on my own flags) and
+ *   copied to recv_prev / recv_next (nullable).  prev_base / next_base: device addresses of the neighbours' symmetric
+ *   buffers (0 = no neighbour).  epoch: int64 [1] device counter ticked once per forward (b3d_epoch_tick), seq: index
+ *   of this exchange inside the forward.  peer_allreduce: in-place sum over all ranks (rank order, bit-identical
+ *   everywhere) of <= 512 bytes of fp32 / fp64 (GroupNorm chunk statistics, SE pooling sums). */
+long long b3d_slab_sym_bytes(long long mailbox_bytes);
+int b3d_halo_exchange(const DLTensor* send_prev, const DLTensor* send_next, DLTensor* recv_prev, DLTensor* recv_next,
+                      long long prev_base, long long next_base, DLTensor* sym, const DLTensor* epoch, int seq,
+                      long long mailbox_bytes, void* stream);
+int b3d_peer_allreduce(DLTensor* x, const DLTensor* peers /*int64 [world]*/, int rank, DLTensor* sym,
+                       const DLTensor* epoch, int seq, void* stream);
+int b3d_epoch_tick(DLTensor* epoch, void* stream);
+
 /* ---- test-time augmentation (test.py:105-161): flip bits 1=D 2=H 4=W on one [D,H,W,C] volume ------------
  * flip_normalize: out = (flip(x) - mean)/std (test.py:107,128; mean/std nullable).
  * flip_accumulate: acc (+)= scale*flip(y), optionally multiplied by the brain mask (test.py:134,147-151). */

@@ -17,6 +17,7 @@ b3d = importlib.import_module("3d-brain-tumor-segmentation_b200")
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 mode = sys.argv[2] if len(sys.argv) > 2 else "both"
+backend = sys.argv[3] if len(sys.argv) > 3 else "nccl"       # nccl | peer (NVLink peer-memory kernels)
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -37,7 +38,7 @@ g = torch.Generator().manual_seed(123)
 x = torch.randn((1,) + shape + (2,), generator=g)
 x[:, 155:], x[:, :, 190:], x[:, :, :, 147:] = 0, 0, 0
 x = x.to(dev)
-comm = b3d.DistComm()
+comm = b3d.PeerComm() if (backend == "peer" and world > 1) else b3d.DistComm()
 bounds = b3d.slab_bounds(shape[0], world)
 d0, d1 = bounds[rank]
 with torch.no_grad():
@@ -59,7 +60,7 @@ def timed(fn):
     return statistics.median(ts), float(err)
 
 
-res = {"n_gpus": world, "slabs": [b - a for a, b in bounds]}
+res = {"n_gpus": world, "backend": backend, "slabs": [b - a for a, b in bounds]}
 if mode in ("eager", "both"):
     ms, err = timed(lambda: b3d.sharded_inference(model, x, comm, gather=False)[0])
     res["eager"] = {"ms": ms, "mvoxel_per_s": 155 * 190 * 147 / ms / 1e3, "rel_l2_vs_unsharded": err}
