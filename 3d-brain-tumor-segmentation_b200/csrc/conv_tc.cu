@@ -677,7 +677,7 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   p.ksplit = 1; p.kchunks = nchunks; p.ws_slice = 0;
   const int ctas = (int)(grid.x * grid.y);
   float* ws = nullptr;
-  if (ctas * 4 <= sm_count() && nchunks >= 8 && g.act == 0 && !g.accumulate && g.Cout % 16 == 0 && g.yp == g.Cout &&
+  if (ctas * 2 <= sm_count() && nchunks >= 8 && g.act == 0 && !g.accumulate && g.Cout % 16 == 0 && g.yp == g.Cout &&
       (S * g.Cout) % 32 == 0 && (stats == nullptr || p.groups == 8 || S % p.groups == 0)) {
     int ks = sm_count() / ctas;
     if (ks > nchunks / 4) ks = nchunks / 4;
