@@ -102,6 +102,10 @@ SIGNATURES = {
     "b3d_mul_scale": "TTTfv",
     "b3d_sigmoid_bwd": "TTTv",
     "b3d_copy_channels": "TTiv",
+    "b3d_maxpool2_fwd": "TTv",
+    "b3d_maxpool2_bwd": "TTTv",
+    "b3d_upsample2_fwd": "TTv",
+    "b3d_upsample2_bwd": "TTv",
     "b3d_halo_exchange": "TTTTLLTTiLv",
     "b3d_peer_allreduce": "TTiTTiv",
     "b3d_epoch_tick": "Tv",

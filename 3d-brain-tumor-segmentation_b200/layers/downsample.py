@@ -44,6 +44,21 @@ class ConvDownsample(Layer):
 
 
 class MaxDownsample(Layer):
-    def __init__(self, data_format='channels_last', **kwargs):
+    """MaxPooling3D(pool_size=2, strides=2, padding='same') (downsample.py:51-70): no weights, the channel count is
+    kept (the `filters` the Encoder passes is swallowed by **kwargs, as in the reference)."""
+
+    def __init__(self,
+                 data_format='channels_last',
+                 **kwargs):
         super().__init__()
-        raise NotImplementedError("b3d: MaxDownsample is a non-default variant listed under SURVEY §8(f)")
+        from ..keras_compat import _require_channels_last
+        _require_channels_last(data_format)
+        self.config = super().get_config()
+        self.config.update({'data_format': data_format})
+
+    def call(self, inputs, training=None):
+        from .. import ops
+        return ops.max_pool2(inputs)
+
+    def get_config(self):
+        return self.config

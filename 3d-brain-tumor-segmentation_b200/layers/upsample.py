@@ -1,5 +1,5 @@
 """Upsampling layers — surface of /root/reference/layers/upsample.py (:7-11 factory, :14-46 ConvUpsample)."""
-from ..keras_compat import Layer, Conv3DTranspose
+from ..keras_compat import Layer, Conv3D, Conv3DTranspose, L2
 from .group_norm import GroupNormalization
 
 
@@ -45,6 +45,29 @@ class ConvUpsample(Layer):
 
 
 class LinearUpsample(Layer):
-    def __init__(self, filters, data_format='channels_last', l2_scale=1e-5, **kwargs):
+    """Conv3D(filters, 1x1x1; he_normal, L2, bias) -> UpSampling3D(size=2) (upsample.py:49-79).  Keras'
+    UpSampling3D repeats voxels (nearest neighbour) despite the layer's name; no GroupNorm, no activation."""
+
+    def __init__(self,
+                 filters,
+                 data_format='channels_last',
+                 l2_scale=1e-5,
+                 **kwargs):
         super().__init__()
-        raise NotImplementedError("b3d: LinearUpsample is a non-default variant listed under SURVEY §8(f)")
+        self.config = super().get_config()
+        self.config.update({'filters': filters,
+                            'data_format': data_format,
+                            'l2_scale': l2_scale})
+        self.ptwise = Conv3D(filters=filters, kernel_size=1, strides=1, padding='same', data_format=data_format,
+                             kernel_regularizer=L2(l2_scale), kernel_initializer='he_normal')
+
+    def build(self, input_shape, device):
+        self.ptwise.build(input_shape, device)
+        self.built = True
+
+    def call(self, inputs, training=None):
+        from .. import ops
+        return ops.upsample2(self.ptwise.call(inputs))
+
+    def get_config(self):
+        return self.config

@@ -202,6 +202,10 @@ class Model(Layer):
                 out[pre + f"gn{i+1}.beta"] = norm.beta
 
         def rs(l, pre):
+            if not hasattr(l, "conv"):                       # MaxDownsample (no weights) / LinearUpsample
+                if hasattr(l, "ptwise"):
+                    out[pre + "ptwise.kernel"], out[pre + "ptwise.bias"] = l.ptwise.kernel, l.ptwise.bias
+                return
             out[pre + "conv.kernel"] = l.conv.kernel
             out[pre + "conv.bias"] = l.conv.bias
             out[pre + "norm.gamma"] = l.norm.gamma

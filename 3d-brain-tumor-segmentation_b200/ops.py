@@ -422,6 +422,56 @@ def dice_coefficient(y_true, y_pred):
     return out[0], out[1]
 
 
+class MaxPool2Fn(Function):
+    """tf.keras.layers.MaxPooling3D(pool_size=2, strides=2, padding='same') on even sizes (downsample.py:58-62);
+    the gradient goes to the first maximum of each 2x2x2 window."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _check(x)
+        x = x.contiguous()
+        B, D, H, W, C = x.shape
+        y = _new((B, D // 2, H // 2, W // 2, C), x)
+        _call("b3d_maxpool2_fwd", x, y)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        _call("b3d_maxpool2_bwd", x, dy.contiguous(), dx)
+        return dx
+
+
+def max_pool2(x):
+    return MaxPool2Fn.apply(x)
+
+
+class Upsample2Fn(Function):
+    """tf.keras.layers.UpSampling3D(size=2): nearest-neighbour repetition (upsample.py:71-73)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _check(x)
+        x = x.contiguous()
+        B, D, H, W, C = x.shape
+        y = _new((B, 2 * D, 2 * H, 2 * W, C), x)
+        _call("b3d_upsample2_fwd", x, y)
+        ctx.shape = tuple(x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = _new(ctx.shape, dy)
+        _call("b3d_upsample2_bwd", dy.contiguous(), dx)
+        return dx
+
+
+def upsample2(x):
+    return Upsample2Fn.apply(x)
+
+
 class ConcatFn(Function):
     """Channel concat (encoder.py:85,91; decoder.py:75) materialised by strided copies."""
 

@@ -208,7 +208,10 @@ def measure_inference_sharded(b3d, torch, dist, dev, model, world, reps=3):
     x = torch.randn((1,) + shape + (2,), generator=g)
     x[:, 155:], x[:, :, 190:], x[:, :, :, 147:] = 0, 0, 0
     x = x.to(dev)
-    comm = b3d.DistComm()
+    try:
+        comm, backend = b3d.PeerComm(), "NVLink peer-memory kernels (csrc/slab_comm.cu)"
+    except Exception as e:                      # noqa: BLE001 — symmetric memory unavailable: NCCL P2P / all-reduce
+        comm, backend = b3d.DistComm(), f"NCCL (peer memory unavailable: {type(e).__name__})"
     d0, d1 = b3d.slab_bounds(shape[0], world)[comm.rank]
     gi = b3d.GraphedInference(model, x[:, d0:d1].contiguous(), comm, depth=shape[0])   # halo exchanges captured too
     times, err = [], None
@@ -230,7 +233,8 @@ def measure_inference_sharded(b3d, torch, dist, dev, model, world, reps=3):
     return {"shape_padded": list(shape), "n_gpus": world, "ms_per_forward": ms,
             "mvoxel_per_s": 155 * 190 * 147 / ms / 1e3, "max_rel_l2_vs_unsharded": float(e),
             "slabs": [b - a for a, b in b3d.slab_bounds(shape[0], world)],
-            "note": "depth-slab sharded, one CUDA graph per rank incl. the NCCL halo exchanges and GN/SE all-reduces"}
+            "comm": backend,
+            "note": "depth-slab sharded, one CUDA graph per rank incl. the halo exchanges and GN/SE all-reduces"}
 
 
 def run_b3d(args):

@@ -168,6 +168,14 @@ int b3d_mul_scale(const DLTensor* a, const DLTensor* b, DLTensor* y, float scale
 int b3d_sigmoid_bwd(const DLTensor* dy, const DLTensor* y, DLTensor* dx, void* stream);
 int b3d_copy_channels(const DLTensor* src, DLTensor* dst, int accumulate, void* stream);
 
+/* ---- non-default resampling variants (csrc/resample.cu): MaxDownsample = MaxPooling3D(2, 2, 'same')
+ * (downsample.py:51-70; even sizes, gradient to the first maximum of each window) and the UpSampling3D(size 2)
+ * nearest-neighbour step of LinearUpsample (upsample.py:49-79).  NDHWC fp32, channels % 4 == 0. */
+int b3d_maxpool2_fwd(const DLTensor* x, DLTensor* y, void* stream);
+int b3d_maxpool2_bwd(const DLTensor* x, const DLTensor* dy, DLTensor* dx, void* stream);
+int b3d_upsample2_fwd(const DLTensor* x, DLTensor* y, void* stream);
+int b3d_upsample2_bwd(const DLTensor* dy, DLTensor* dx, void* stream);
+
 /* ---- depth-slab sharded inference over NVLink peer memory (csrc/slab_comm.cu; host side slab.PeerComm) -----------
  * Every rank owns one symmetric buffer of b3d_slab_sym_bytes(mailbox_bytes) bytes mapped into its peers.
  * halo_exchange: my first / last boundary slices (send_prev / send_next, nullable) are stored into the neighbours'

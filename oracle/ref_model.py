@@ -144,15 +144,34 @@ def resnet_block(p: Params, pre: str, x: torch.Tensor, groups: int = 8) -> torch
     return res + h                                                                     # :137
 
 
+def max_pool2_same(x):
+    """layers/downsample.py:58-62, :64-66: MaxPooling3D(pool_size=2, strides=2, padding='same'), channels_last.
+    TF 'SAME' pads max(ceil(n/2)*2 - n, 0) after (with -inf); for even sizes there is no padding."""
+    xc = x.permute(0, 4, 1, 2, 3)
+    pd, ph, pw = [(-n) % 2 for n in x.shape[1:4]]
+    if pd or ph or pw:
+        xc = torch.nn.functional.pad(xc, (0, pw, 0, ph, 0, pd), value=float("-inf"))
+    return torch.nn.functional.max_pool3d(xc, 2, 2).permute(0, 2, 3, 4, 1)
+
+
+def upsample2_nearest(x):
+    """layers/upsample.py:71-73: UpSampling3D(size=2) repeats every voxel 2x2x2 (nearest neighbour)."""
+    return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+
+
 def conv_downsample(p: Params, pre: str, x, groups=8):
-    """layers/downsample.py:41-45"""
+    """layers/downsample.py:41-45 (ConvDownsample); :64-66 (MaxDownsample: no weights => no keys under `pre`)"""
+    if pre + "conv.kernel" not in p:
+        return max_pool2_same(x)
     x = conv3d_same(x, p[pre + "conv.kernel"], p[pre + "conv.bias"], stride=2)
     x = group_norm(x, p[pre + "norm.gamma"], p[pre + "norm.beta"], groups)
     return torch.relu(x)
 
 
 def conv_upsample(p: Params, pre: str, x, groups=8):
-    """layers/upsample.py:39-43"""
+    """layers/upsample.py:39-43 (ConvUpsample); :75-78 (LinearUpsample: 1x1x1 conv then UpSampling3D)"""
+    if pre + "ptwise.kernel" in p:
+        return upsample2_nearest(conv3d_same(x, p[pre + "ptwise.kernel"], p[pre + "ptwise.bias"]))
     x = conv3d_transpose_same(x, p[pre + "conv.kernel"], p[pre + "conv.bias"])
     x = group_norm(x, p[pre + "norm.gamma"], p[pre + "norm.beta"], groups)
     return torch.relu(x)
@@ -322,7 +341,7 @@ def tta_inference(p: Params, x, bmask, mean, std, depth=4, groups=8):
 # Deterministic synthetic weights / inputs
 # ----------------------------------------------------------------------------------
 def param_shapes(in_ch=2, out_ch=3, base_filters=16, depth=4, reduction=2, crop=(128, 128, 128),
-                 with_vae=True) -> Dict[str, Tuple[int, ...]]:
+                 with_vae=True, downsampling="conv", upsampling="conv") -> Dict[str, Tuple[int, ...]]:
     """Shapes of all trainable tensors in Keras layouts, keyed by this repo's names."""
     s: Dict[str, Tuple[int, ...]] = {}
 
@@ -341,13 +360,20 @@ def param_shapes(in_ch=2, out_ch=3, base_filters=16, depth=4, reduction=2, crop=
         s[pre + "gn2.gamma"] = (f,)
         s[pre + "gn2.beta"] = (f,)
 
-    def down(pre, cin, f):
+    def down(pre, cin, f, kind=None):
+        if (kind or downsampling) == "max":          # MaxDownsample: no weights, channels kept
+            return cin
         s[pre + "conv.kernel"] = (3, 3, 3, cin, f)
         s[pre + "conv.bias"] = (f,)
         s[pre + "norm.gamma"] = (f,)
         s[pre + "norm.beta"] = (f,)
+        return f
 
     def up(pre, cin, f):
+        if upsampling == "linear":         # LinearUpsample: 1x1x1 conv (+bias), no norm
+            s[pre + "ptwise.kernel"] = (1, 1, 1, cin, f)
+            s[pre + "ptwise.bias"] = (f,)
+            return
         s[pre + "conv.kernel"] = (3, 3, 3, f, cin)
         s[pre + "conv.bias"] = (f,)
         s[pre + "norm.gamma"] = (f,)
@@ -360,8 +386,7 @@ def param_shapes(in_ch=2, out_ch=3, base_filters=16, depth=4, reduction=2, crop=
             block(f"enc.L{i}.B{j}.", cin if j == 0 else (j + 1) * f, f)
         cin = f if i == 0 else (i + 1) * f
         if i < depth - 1:
-            down(f"enc.L{i}.down.", cin, f)
-            cin = f
+            cin = down(f"enc.L{i}.down.", cin, f)
     bott = cin
     res_ch = [base_filters if i == 0 else (i + 1) * base_filters * 2 ** i for i in range(depth)]
     c = bott
@@ -374,8 +399,8 @@ def param_shapes(in_ch=2, out_ch=3, base_filters=16, depth=4, reduction=2, crop=
     s["dec.out.bias"] = (out_ch,)
     if with_vae:
         d, h, w = [n // 2 ** (depth - 1) for n in crop]
-        f = base_filters // 2
-        down("vae.down.", bott, f)
+        # model.py:49-57 does not forward `downsampling` to the VAE: its extra downsample is always the conv variant
+        f = down("vae.down.", bott, base_filters // 2, kind="conv")
         flat = (d // 2) * (h // 2) * (w // 2) * f
         s["vae.proj.kernel"] = (flat, base_filters * 2 ** (depth - 1))
         s["vae.proj.bias"] = (base_filters * 2 ** (depth - 1),)

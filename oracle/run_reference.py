@@ -62,6 +62,11 @@ def _load_block(blk, p, pre):
 
 
 def _load_resample(layer, p, pre):
+    if not hasattr(layer, "conv"):                  # MaxDownsample (no weights) / LinearUpsample (1x1x1 conv)
+        if hasattr(layer, "ptwise"):
+            _set(layer.ptwise, "kernel", p[pre + "ptwise.kernel"])
+            _set(layer.ptwise, "bias", p[pre + "ptwise.bias"])
+        return
     _set(layer.conv, "kernel", p[pre + "conv.kernel"])
     _set(layer.conv, "bias", p[pre + "conv.bias"])
     _set(layer.norm, "gamma", p[pre + "norm.gamma"])
@@ -143,6 +148,10 @@ class ReferenceRunner:
                 out[pre + f"gn{i+1}.beta"] = norm.beta
 
         def rs(l, pre):
+            if not hasattr(l, "conv"):
+                if hasattr(l, "ptwise"):
+                    out[pre + "ptwise.kernel"], out[pre + "ptwise.bias"] = l.ptwise.kernel, l.ptwise.bias
+                return
             out[pre + "conv.kernel"] = l.conv.kernel
             out[pre + "conv.bias"] = l.conv.bias
             out[pre + "norm.gamma"] = l.norm.gamma

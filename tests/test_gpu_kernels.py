@@ -339,3 +339,40 @@ def test_tc_conv_vs_oracle_and_generic(b3d, dev, case):
             assert rel(stats, ref) < max(tol, 1e-4), ("stats", tc)
     assert rel(res["tf32"][0], res["fp32"][0]) < TOL_TF32 and rel(res["bf16"][0], res["fp32"][0]) < TOL_BF16
     assert rel(res["fp16"][0], res["fp32"][0]) < TOL_TF32
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 6, 8, 16), (1, 8, 8, 8, 4), (1, 2, 2, 2, 64)])
+def test_max_downsample_and_linear_upsample_layers(b3d, dev, shape):
+    """MaxDownsample (downsample.py:51-70) and LinearUpsample (upsample.py:49-79) against the oracle, forward and
+    gradients; ties in a pooling window send the gradient to the first maximum, as torch / TF do."""
+    x = t64(*shape, seed=31)
+    x[0, :2, :2, :2, 0] = 1.5                                  # a window of ties
+    xr = x.clone().requires_grad_(True)
+    yr = R.max_pool2_same(xr)
+    gy = t64(*yr.shape, seed=32)
+    (yr * gy).sum().backward()
+    xd = dev32(x, dev, True)
+    y = b3d.MaxDownsample()(xd)
+    (y * dev32(gy, dev)).sum().backward()
+    assert rel(y, yr) < 1e-7 and rel(xd.grad, xr.grad) < 1e-7
+    # LinearUpsample: 1x1x1 conv (fp32 mode for a tight bound) + nearest-neighbour x2
+    b3d.ops.USE_TC["on"] = False
+    try:
+        f = 8
+        w, bias = t64(1, 1, 1, shape[-1], f, seed=33, scale=0.3), t64(f, seed=34)
+        xr2, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+        yr2 = R.upsample2_nearest(R.conv3d_same(xr2, wr, br))
+        gy2 = t64(*yr2.shape, seed=35)
+        (yr2 * gy2).sum().backward()
+        up = b3d.LinearUpsample(filters=f)
+        xd2 = dev32(x, dev, True)
+        up(xd2.detach())
+        with torch.no_grad():
+            up.ptwise.kernel.copy_(w.float())
+            up.ptwise.bias.copy_(bias.float())
+        y2 = up(xd2)
+        (y2 * dev32(gy2, dev)).sum().backward()
+        assert rel(y2, yr2) < TOL32 and rel(xd2.grad, xr2.grad) < TOL32
+        assert rel(up.ptwise.kernel.grad, wr.grad) < TOL32 and rel(up.ptwise.bias.grad, br.grad) < TOL32
+    finally:
+        b3d.ops.USE_TC["on"] = True

@@ -247,3 +247,31 @@ def test_skull_strip_variant_matches_oracle(b3d, dev, mode):
         assert errs[len(errs) // 2][0] < 3e-2 and errs[0][0] < 2e-1, errs[:5]
     else:
         assert coss[0][0] > 0.90 and coss[len(coss) // 10][0] > 0.98, coss[:5]
+
+
+@pytest.mark.parametrize("down,up", [("max", "linear"), ("max", "conv"), ("conv", "linear")])
+def test_resampling_variants_model_matches_oracle(b3d, dev, down, up):
+    """Model(downsampling='max' | upsampling='linear') (args.py:137-141 choices): one training step in fp32 mode
+    against the fp64 oracle (which tests/test_oracle.py pins on the reference's own layer code)."""
+    crop = (32, 32, 16)
+    p = R.init_params(R.param_shapes(crop=crop, downsampling=down, upsampling=up))
+    x, y, eps, mask = R.synth_batch((1,) + crop)
+    pg = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    outs = R.model_forward(pg, x, eps, dropout_mask=mask)
+    ref = R.dice_vae_loss(x, y, *outs) + R.l2_reg(pg)
+    ref.backward()
+    set_mode(b3d, "fp32")
+    try:
+        model, f = build(b3d, dev, crop, p, downsampling=down, upsampling=up)
+        assert set(model.named_variables()) == set(p)
+        opt = b3d.ScheduledOptim(learning_rate=1e-4)
+        opt(epoch=0)
+        loss, _, _ = b3d.train_step(model, opt, b3d.DiceVAELoss(), b3d.DiceCoefficient(), f(x), f(y),
+                                    dropout_mask=f(mask), eps=f(eps))
+        torch.cuda.synchronize()
+    finally:
+        reset_mode(b3d)
+    assert abs(float(loss) - float(ref)) / float(ref) < 1e-4
+    nv = model.named_variables()
+    errs = sorted(((rel(nv[k].grad, pg[k].grad), k) for k in p), reverse=True)
+    assert errs[len(errs) // 2][0] < 3e-2 and errs[0][0] < 2e-1, errs[:5]
