@@ -31,7 +31,12 @@ class TestTimeAugmentor(object):
     """Handles full inference on input with test-time augmentation (test.py:75-161)."""
     __test__ = False   # not a pytest class
 
-    def __init__(self, mean, std, model, model_data_format, spatial_tta=True, channel_tta=0, threshold=0.5):
+    def __init__(self, mean, std, model, model_data_format, spatial_tta=True, channel_tta=0, threshold=0.5,
+                 group=None):
+        """`group` (B200-side addition, not in the reference): a torch.distributed process group — the flips are
+        dealt round-robin to its ranks (replica mode: every GPU runs whole-volume forwards, no halo exchange) and
+        the partial means are summed with one all-reduce; every rank returns the full result."""
+        self.group = group
         if model_data_format != 'channels_last':
             raise NotImplementedError("b3d: channels_first is listed under SURVEY §8(f)")
         if channel_tta:
@@ -66,16 +71,27 @@ class TestTimeAugmentor(object):
             mean, std = mean.expand(x.shape[-1]).contiguous(), std.expand(x.shape[-1]).contiguous()
         bmask = bmask.to(torch.float32).contiguous()
         n = len(self.augment_axes)
+        rank, world = 0, 1
+        if self.group is not None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        mine = list(range(rank, n, world))              # this rank's flips
         aug = torch.empty_like(x)
         acc = None
         with torch.no_grad():
-            for i, flip in enumerate(self.augment_axes):
-                bits = self._bits(flip)
+            for j, i in enumerate(mine):
+                bits = self._bits(self.augment_axes[i])
                 ops._call("b3d_flip_normalize", x, mean, std, aug, bits)           # test.py:107,128
                 y, *_ = self.model(aug.unsqueeze(0), training=False, inference=True)   # test.py:133
                 y = y[0]
                 if acc is None:
                     acc = torch.empty_like(y)
-                last = i == n - 1
-                ops._call("b3d_flip_accumulate", y, acc, bmask if last else None, bits, 1.0 / n, int(i == 0))
+                last = world == 1 and j == len(mine) - 1     # single rank: the brain mask rides on the last pass
+                ops._call("b3d_flip_accumulate", y, acc, bmask if last else None, bits, 1.0 / n, int(j == 0))
+            if world > 1:
+                if acc is None:                              # more ranks than flips
+                    y0 = self.model(aug.unsqueeze(0) * 0, training=False, inference=True)[0][0]
+                    acc = torch.zeros_like(y0)
+                dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+                ops._call("b3d_mul_scale", acc, bmask.expand_as(acc).contiguous(), acc, 1.0)   # test.py:147-151
         return acc

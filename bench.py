@@ -237,6 +237,31 @@ def measure_inference_sharded(b3d, torch, dist, dev, model, world, reps=3):
             "note": "depth-slab sharded, one CUDA graph per rank incl. the halo exchanges and GN/SE all-reduces"}
 
 
+def measure_tta(b3d, torch, dist, dev, model, world, reps=2):
+    """8-flip test-time augmentation of one padded volume (reference test.py:105-161).  N GPUs: replica mode — the
+    flips are dealt to the ranks (whole-volume forwards, no halo exchange), one all-reduce of the class maps."""
+    shape = (160, 192, 160)
+    g = torch.Generator().manual_seed(321)
+    x = torch.randn(shape + (2,), generator=g).to(dev)
+    mask = torch.ones(shape + (1,), device=dev)
+    tta = b3d.TestTimeAugmentor(0.0, 1.0, model, "channels_last", group=dist.group.WORLD if world > 1 else None)
+    times = []
+    for i in range(reps + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); tta(x, mask); e1.record(); e1.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if i:
+            times.append(float(ms))
+    ms = statistics.median(times)
+    return {"ms_per_volume": ms, "mvoxel_per_s": 155 * 190 * 147 / ms / 1e3, "flips": 8,
+            "mode": "replicas: flips dealt to ranks + 1 all-reduce" if world > 1 else "8 sequential forwards"}
+
+
 def run_b3d(args):
     import torch
     import torch.distributed as dist
@@ -304,6 +329,7 @@ def run_b3d(args):
     e2e_val = world * args.steps / (ms_e2e / 1e3)
 
     inf_sharded = measure_inference_sharded(b3d, torch, dist, dev, model, world) if world > 1 else None
+    tta = measure_tta(b3d, torch, dist, dev, model, world)
 
     def finish():
         # NCCL communicators captured into CUDA graphs make destroy_process_group() hang at teardown:
@@ -346,7 +372,8 @@ def run_b3d(args):
                     "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": int(step.launches_per_step * args.steps),
             "roofline": roof, "cpu_baseline": cpu,
-            "inference": measure_inference(b3d, torch, dev, model) if world == 1 else inf_sharded}
+            "inference": measure_inference(b3d, torch, dev, model) if world == 1 else inf_sharded,
+            "inference_tta": tta}
     print(json.dumps(line), flush=True)
     finish()
 
