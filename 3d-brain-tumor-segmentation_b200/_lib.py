@@ -102,6 +102,8 @@ SIGNATURES = {
     "b3d_mul_scale": "TTTfv",
     "b3d_sigmoid_bwd": "TTTv",
     "b3d_copy_channels": "TTiv",
+    "b3d_channel_moments": "TTv",
+    "b3d_augment_crop": "TTTTTTTiiiiv",
     "b3d_maxpool2_fwd": "TTv",
     "b3d_maxpool2_bwd": "TTTv",
     "b3d_upsample2_fwd": "TTv",

@@ -233,6 +233,23 @@ class Model(Layer):
             out["vae.out.kernel"], out["vae.out.bias"] = v.out.kernel, v.out.bias
         return out
 
+    # ---- checkpoints (train.py:99-100 load_weights, :199-201 save_weights).  h5py is not in this image, so the file is
+    # a NumPy .npz with this repo's structural names (Keras layouts, fp32) plus the `epoch` variable (model.py:29);
+    # oracle/run_reference.py::load_params holds the mapping to the reference's attribute tree.
+    def save_weights(self, filepath):
+        import numpy as np
+        arrs = {k: t.detach().cpu().numpy() for k, t in self.named_variables().items()}
+        arrs["__epoch__"] = np.asarray(int(self.epoch), dtype=np.int64)
+        with open(filepath, "wb") as f:
+            np.savez(f, **arrs)
+
+    def load_weights(self, filepath):
+        import numpy as np
+        with np.load(filepath) as z:
+            self.load_named_weights({k: torch.from_numpy(z[k]) for k in z.files if k != "__epoch__"})
+            if "__epoch__" in z.files:
+                self.epoch.assign(int(z["__epoch__"]))
+
     def load_named_weights(self, params):
         nv = self.named_variables()
         missing = set(nv) - set(params)

@@ -192,3 +192,37 @@ class GraphedTrainStep:
             self.y.copy_(y, non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+class TrainLog:
+    """The CSV log of the reference's training loop (train.py:117-127 header, :184-195 one row per epoch) and its
+    best-validation-Dice checkpoint / patience rule (train.py:197-208)."""
+    HEADER = ['epoch', 'lr', 'train_loss', 'train_macro_dice', 'train_micro_dice', 'val_loss', 'val_macro_dice',
+              'val_micro_dice']
+
+    def __init__(self, save_folder=None, patience=10):
+        import os
+        self.save_folder, self.patience_limit = save_folder, patience
+        self.best_val_dice, self.patience = 0.0, 0
+        if save_folder:
+            os.makedirs(save_folder, exist_ok=True)
+            with open(os.path.join(save_folder, 'train.log'), 'w') as f:
+                f.write(','.join(self.HEADER) + '\n')
+
+    def end_epoch(self, epoch, lr, train, val, model=None):
+        """train / val: (loss, macro_dice, micro_dice).  Returns False when training should stop (patience)."""
+        import os
+        if self.save_folder:
+            with open(os.path.join(self.save_folder, 'train.log'), 'a') as f:
+                f.write(','.join(str(float(v)) if i else str(int(v))
+                                 for i, v in enumerate([epoch, lr, *train, *val])) + '\n')
+        if float(val[1]) > self.best_val_dice:
+            self.best_val_dice, self.patience = float(val[1]), 0
+            if self.save_folder and model is not None:
+                model.epoch.assign(epoch)
+                model.save_weights(os.path.join(self.save_folder, 'chkpt.npz'))
+            return True
+        if self.patience == self.patience_limit:
+            return False
+        self.patience += 1
+        return True

@@ -168,6 +168,16 @@ int b3d_mul_scale(const DLTensor* a, const DLTensor* b, DLTensor* y, float scale
 int b3d_sigmoid_bwd(const DLTensor* dy, const DLTensor* y, DLTensor* dx, void* stream);
 int b3d_copy_channels(const DLTensor* src, DLTensor* dst, int accumulate, void* stream);
 
+/* ---- training-example pipeline of tf.data's map function (train.py:12-47 parse_example) on the device ----------
+ * channel_moments: x [D,H,W,C<=8] -> fp64 [C,2] (sum, sum of squares).  augment_crop: x += shift*sqrt(var); x *= scale
+ * (train.py:20-24), crop window at (off_d, off_h, off_w) (train.py:27-28), flips of the crop (bit a = axis a,
+ * train.py:31-35), labels y [D,H,W,1] -> one-hot without the background class (train.py:41-44).  The random draws
+ * are the caller's. */
+int b3d_channel_moments(const DLTensor* x, DLTensor* sums, void* stream);
+int b3d_augment_crop(const DLTensor* x, const DLTensor* y, const DLTensor* sums, const DLTensor* shift,
+                     const DLTensor* scale, DLTensor* x_out, DLTensor* y_out, int off_d, int off_h, int off_w,
+                     int flip, void* stream);
+
 /* ---- non-default resampling variants (csrc/resample.cu): MaxDownsample = MaxPooling3D(2, 2, 'same')
  * (downsample.py:51-70; even sizes, gradient to the first maximum of each window) and the UpSampling3D(size 2)
  * nearest-neighbour step of LinearUpsample (upsample.py:49-79).  NDHWC fp32, channels % 4 == 0. */

@@ -456,3 +456,22 @@ def synth_batch(shape=(1, 128, 128, 128), in_ch=2, out_ch=3, latent=64, seed=0, 
     mask = (np.random.default_rng(seed + 4).random(shape + (in_ch,)) < 0.8).astype(np.float64)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
     return t(x), t(y), t(eps), t(mask)
+
+
+# ----------------------------------------------------------------------------------
+# train.py:12-47 (parse_example of the tf.data pipeline), with the random draws as arguments
+# ----------------------------------------------------------------------------------
+def augment_example(x, y, crop_size, out_ch, shift, scale, offset, flips):
+    """x [H,W,D,C], y [H,W,D,1] -> (crop of the intensity-augmented x, one-hot labels without background)."""
+    var = x.var(dim=(0, 1, 2), unbiased=False, keepdim=True)            # :20 tf.nn.moments
+    x = (x + shift.reshape(1, 1, 1, -1) * torch.sqrt(var)) * scale.reshape(1, 1, 1, -1)   # :23-24
+    xy = torch.cat([x, y.to(x.dtype)], dim=-1)                          # :27
+    o = offset
+    xy = xy[o[0]:o[0] + crop_size[0], o[1]:o[1] + crop_size[1], o[2]:o[2] + crop_size[2]]   # :28 random_crop
+    for axis in (0, 1, 2):                                              # :31-35
+        if flips[axis]:
+            xy = torch.flip(xy, dims=[axis])
+    xc, yc = xy[..., :-1], xy[..., -1]                                  # :37
+    lab = yc.to(torch.int64)                                            # :41
+    onehot = torch.nn.functional.one_hot(lab, out_ch + 1).to(x.dtype)   # :42
+    return xc.contiguous(), onehot[..., 1:].contiguous()                # :43

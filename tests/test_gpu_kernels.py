@@ -376,3 +376,30 @@ def test_max_downsample_and_linear_upsample_layers(b3d, dev, shape):
         assert rel(up.ptwise.kernel.grad, wr.grad) < TOL32 and rel(up.ptwise.bias.grad, br.grad) < TOL32
     finally:
         b3d.ops.USE_TC["on"] = True
+
+
+@pytest.mark.parametrize("case", [((20, 24, 18), 2, 3, (8, 16, 8), (3, 5, 7), (True, False, True)),
+                                  ((16, 16, 16), 1, 1, (16, 16, 16), (0, 0, 0), (False, True, False)),
+                                  ((12, 10, 14), 4, 3, (8, 8, 8), (4, 2, 6), (False, False, False))])
+def test_gpu_example_pipeline_matches_oracle(b3d, dev, case):
+    """train.py:12-47 (tf.data parse_example): intensity shift/scale from the channel variance, crop, flips, one-hot
+    labels without background — the fused device pipeline against the oracle restatement with the same draws."""
+    vol, C, K, crop, off, flips = case
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(*vol, C, generator=g, dtype=torch.float64) * 2 + 0.5
+    y = torch.randint(0, K + 1, vol + (1,), generator=g).double()
+    shift = torch.rand(C, generator=g, dtype=torch.float64) * 0.2 - 0.1
+    scale = torch.rand(C, generator=g, dtype=torch.float64) * 0.2 + 0.9
+    xr, yr = R.augment_example(x, y, crop, K, shift, scale, off, flips)
+    xo, yo = b3d.parse_example(dev32(x, dev), dev32(y, dev), crop, K, shift=shift.float(), scale=scale.float(),
+                               offset=off, flips=flips)
+    assert xo.shape == xr.shape and yo.shape == yr.shape
+    assert rel(xo, xr) < 1e-6
+    assert torch.equal(yo.cpu().double(), yr)
+    # random draws: shapes, ranges, determinism of the generator
+    ds = b3d.VolumeDataset([(dev32(x, dev), dev32(y, dev))] * 3, batch_size=2, crop_size=crop, out_ch=K, seed=5)
+    batches = list(ds)
+    assert [b[0].shape[0] for b in batches] == [2, 1] and batches[0][0].shape[1:] == tuple(crop) + (C,)
+    assert batches[0][1].shape[1:] == tuple(crop) + (K,) and float(batches[0][1].sum(-1).max()) <= 1.0
+    ds2 = b3d.VolumeDataset([(dev32(x, dev), dev32(y, dev))] * 3, batch_size=2, crop_size=crop, out_ch=K, seed=5)
+    assert torch.equal(next(iter(ds2))[0], batches[0][0])

@@ -275,3 +275,31 @@ def test_resampling_variants_model_matches_oracle(b3d, dev, down, up):
     nv = model.named_variables()
     errs = sorted(((rel(nv[k].grad, pg[k].grad), k) for k in p), reverse=True)
     assert errs[len(errs) // 2][0] < 3e-2 and errs[0][0] < 2e-1, errs[:5]
+
+
+def test_checkpoint_roundtrip_and_train_log(b3d, dev, tmp_path):
+    """save_weights / load_weights (train.py:99-100, :199-201) and the CSV log + patience rule (train.py:117-127,
+    :184-208): a reloaded model reproduces the outputs (up to the summation order of the statistics atomics) and
+    resumes from the saved epoch."""
+    crop = (16, 16, 16)
+    p = R.init_params(R.param_shapes(crop=crop))
+    x, _, eps, _ = R.synth_batch((1,) + crop)
+    model, f = build(b3d, dev, crop, p)
+    log = b3d.TrainLog(str(tmp_path), patience=1)
+    assert log.end_epoch(3, 1e-4, (1.0, 0.2, 0.3), (0.9, 0.25, 0.3), model)          # improvement -> checkpoint
+    assert log.end_epoch(4, 1e-4, (1.0, 0.2, 0.3), (0.9, 0.20, 0.3), model)          # patience 0 -> 1
+    assert not log.end_epoch(5, 1e-4, (1.0, 0.2, 0.3), (0.9, 0.20, 0.3), model)      # patience exhausted
+    rows = open(tmp_path / "train.log").read().strip().split("\n")
+    assert rows[0].split(",") == b3d.TrainLog.HEADER and len(rows) == 4 and rows[1].startswith("3,")
+    with torch.no_grad():
+        y0 = model(f(x), training=False, inference=True)[0]
+    b3d.keras_compat.set_seed(77)
+    other = b3d.Model()
+    other(torch.zeros((1,) + crop + (2,), device=dev), training=False, inference=False)
+    other.load_weights(str(tmp_path / "chkpt.npz"))
+    assert int(other.epoch) == 3
+    nv0, nv1 = model.named_variables(), other.named_variables()
+    assert all(torch.equal(nv0[k], nv1[k]) for k in nv0)
+    with torch.no_grad():
+        y1 = other(f(x), training=False, inference=True)[0]
+    assert rel(y1, y0) < 1e-3
