@@ -78,6 +78,10 @@ SIGNATURES = {
     "b3d_conv3d_pack_weights": "TTiiiv",
     "b3d_gn_stats": "TTiv",
     "b3d_gn_apply": "TTTTTifiv",
+    "b3d_gn_channel_stats": "TTiv",
+    "b3d_gn_channel_apply": "TTTTTifiv",
+    "b3d_gn_channel_bwd": "TTTTTTTTTifiv",
+    "b3d_relayout": "TTiv",
     "b3d_gn_stats_slab": "TTiLLv",
     "b3d_gn_apply_slab": "TTTTTifiLLv",
     "b3d_gn_bwd_reduce": "TTTTTTTTifiv",
@@ -89,7 +93,7 @@ SIGNATURES = {
     "b3d_block_epilogue_bwd_apply": "TTTTTTTTTTTTifiv",
     "b3d_loss_fwd": "TTTTTTTTv",
     "b3d_loss_bwd": "TTTTTTTTTTTTv",
-    "b3d_dice_coeff": "TTTTv",
+    "b3d_dice_coeff": "TTTTiv",
     "b3d_dense_fwd": "TTTTiv",
     "b3d_dense_bwd": "TTTTTTTiv",
     "b3d_vae_sample_fwd": "TTTv",

@@ -190,15 +190,31 @@ __global__ void __launch_bounds__(256)
     if (sm[i] != 0.f) atomicAdd(&acc[i], sm[i]);
 }
 
-__global__ void dice_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, int W, int C) {
+// reduce_w = 0: the reference's channels_last macro average over the [W, C]-shaped ratio (util.py:36 reduces axes
+// (0,1,2) only); reduce_w = 1: its channels_first form, sums over all of batch and space per class
+__global__ void dice_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, int W, int C,
+                                     int reduce_w) {
   if (threadIdx.x == 0) {
     double macro = 0.0, si = 0.0, sp = 0.0, st = 0.0;
-    for (int i = 0; i < W * C; ++i) {
-      const double I = acc[3 * i], P = acc[3 * i + 1], T = acc[3 * i + 2];
-      macro += (2.0 * I + 1.0) / (P + T + 1.0);
-      si += I; sp += P; st += T;
+    if (reduce_w) {
+      for (int c = 0; c < C; ++c) {
+        double I = 0.0, P = 0.0, T = 0.0;
+        for (int w = 0; w < W; ++w) {
+          const int i = w * C + c;
+          I += acc[3 * i]; P += acc[3 * i + 1]; T += acc[3 * i + 2];
+        }
+        macro += (2.0 * I + 1.0) / (P + T + 1.0);
+        si += I; sp += P; st += T;
+      }
+      out[0] = (float)(macro / C);
+    } else {
+      for (int i = 0; i < W * C; ++i) {
+        const double I = acc[3 * i], P = acc[3 * i + 1], T = acc[3 * i + 2];
+        macro += (2.0 * I + 1.0) / (P + T + 1.0);
+        si += I; sp += P; st += T;
+      }
+      out[0] = (float)(macro / (W * C));
     }
-    out[0] = (float)(macro / (W * C));
     out[1] = (float)(si / (sp + st));
   }
 }
@@ -563,7 +579,7 @@ extern "C" int b3d_loss_bwd(const DLTensor* x_, const DLTensor* y_, const DLTens
 
 // acc: fp32 [W*C*3] workspace (overwritten); out: fp32 [2] = macro, micro
 extern "C" int b3d_dice_coeff(const DLTensor* y_, const DLTensor* ypred_, DLTensor* acc_, DLTensor* out_,
-                              void* stream) {
+                              int reduce_w, void* stream) {
   TView y, yp, acc, out;
   B3D_TRY(view(y_, DT_F32, 5, false, "y", &y));
   B3D_TRY(view(ypred_, DT_F32, 5, false, "y_pred", &yp));
@@ -580,7 +596,7 @@ extern "C" int b3d_dice_coeff(const DLTensor* y_, const DLTensor* ypred_, DLTens
   DISPATCH_C(C, (dice_coeff_kernel<kC><<<grid, 256, smem, s>>>((const float*)y.p, (const float*)yp.p, nrows, W,
                                                                 (float*)acc.p)));
   B3D_LAUNCH_CHECK("dice_coeff");
-  dice_finalize_kernel<<<1, 32, 0, s>>>((const float*)acc.p, (float*)out.p, W, C);
+  dice_finalize_kernel<<<1, 32, 0, s>>>((const float*)acc.p, (float*)out.p, W, C, reduce_w);
   B3D_LAUNCH_CHECK("dice_finalize");
   return B3D_OK;
 }

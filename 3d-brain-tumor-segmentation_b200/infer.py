@@ -38,7 +38,8 @@ class TestTimeAugmentor(object):
         the partial means are summed with one all-reduce; every rank returns the full result."""
         self.group = group
         if model_data_format != 'channels_last':
-            raise NotImplementedError("b3d: channels_first is listed under SURVEY §8(f)")
+            raise NotImplementedError("b3d TestTimeAugmentor: feed channels_last volumes (the flips / mask kernels are "
+                                      "NDHWC); a channels_first Model can be wrapped with ops.to_channels_first")
         if channel_tta:
             raise NotImplementedError("b3d: channel_tta (test.py:137-145 is itself broken in the reference, App. C)")
         self.mean, self.std, self.model = mean, std, model

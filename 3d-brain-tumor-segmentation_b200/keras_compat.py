@@ -65,6 +65,41 @@ class Variable:
         self.name, self.tensor, self.regularizer = name, tensor, regularizer
 
 
+import threading
+
+_LAYOUT = threading.local()
+
+
+def _internal_layout() -> bool:
+    return getattr(_LAYOUT, "depth", 0) > 0
+
+
+class internal_layout:
+    """Inside: tensors are in the internal NDHWC storage even when the layers were built with
+    data_format='channels_first' (only the outermost public call converts NCDHW <-> NDHWC)."""
+
+    def __enter__(self):
+        _LAYOUT.depth = getattr(_LAYOUT, "depth", 0) + 1
+
+    def __exit__(self, *a):
+        _LAYOUT.depth -= 1
+        return False
+
+
+def map5d(v, fn):
+    if isinstance(v, torch.Tensor):
+        return fn(v) if v.dim() == 5 else v
+    if isinstance(v, (list, tuple)):
+        return type(v)(map5d(u, fn) for u in v)
+    return v
+
+
+def check_data_format(data_format):
+    if data_format not in ('channels_last', 'channels_first'):
+        raise ValueError(f"data_format must be 'channels_last' or 'channels_first', got {data_format!r}")
+    return data_format
+
+
 class Layer:
     def __init__(self, name: Optional[str] = None, **kwargs):
         self.name = name or type(self).__name__.lower()
@@ -73,10 +108,18 @@ class Layer:
 
     # ---- Keras protocol
     def __call__(self, inputs, *args, **kwargs):
-        if not self.built:
-            self.build(_shape_of(inputs), _device_of(inputs))
-            self.built = True
-        return self.call(inputs, *args, **kwargs)
+        # data_format='channels_first': the public surface takes / returns NCDHW tensors; storage inside is NDHWC
+        # (the semantic difference — true channel GroupNorm — lives in the kernels, not in the layout)
+        convert = getattr(self, "data_format", "channels_last") == "channels_first" and not _internal_layout()
+        if convert:
+            inputs = map5d(inputs, ops.to_channels_last)
+            kwargs = {k: map5d(v, ops.to_channels_last) for k, v in kwargs.items()}
+        with internal_layout():
+            if not self.built:
+                self.build(_shape_of(inputs), _device_of(inputs))
+                self.built = True
+            out = self.call(inputs, *args, **kwargs)
+        return map5d(out, ops.to_channels_first) if convert else out
 
     def build(self, input_shape, device):
         pass
@@ -147,11 +190,8 @@ def _device_of(x):
 from . import ops  # noqa: E402
 
 
-def _require_channels_last(data_format):
-    if data_format != "channels_last":
-        raise NotImplementedError(
-            "b3d: only data_format='channels_last' (the reference's CPU/oracle layout) is built so far; "
-            "channels_first is listed under SURVEY §8(f).")
+def _require_channels_last(data_format):      # validates only: both layouts are served (Layer.__call__)
+    check_data_format(data_format)
 
 
 class Conv3D(Layer):
@@ -161,7 +201,7 @@ class Conv3D(Layer):
                  activation=None, use_bias=True, kernel_initializer="glorot_uniform", kernel_regularizer=None,
                  **kw):
         super().__init__(**kw)
-        _require_channels_last(data_format)
+        self.data_format = check_data_format(data_format)
         if padding != "same":
             raise NotImplementedError("b3d Conv3D: only padding='same'")
         if activation not in (None, "sigmoid"):
@@ -191,7 +231,7 @@ class Conv3DTranspose(Layer):
     def __init__(self, filters, kernel_size=3, strides=2, padding="same", data_format="channels_last",
                  kernel_initializer="glorot_uniform", **kw):
         super().__init__(**kw)
-        _require_channels_last(data_format)
+        self.data_format = check_data_format(data_format)
         if (kernel_size, strides, padding) != (3, 2, "same"):
             raise NotImplementedError("b3d Conv3DTranspose: only kernel_size=3, strides=2, padding='same'")
         self.filters, self.kernel_initializer = filters, kernel_initializer

@@ -18,6 +18,7 @@ class Decoder(Layer):
                  out_ch=3):
         super().__init__()
         self.config = super().get_config()
+        self.data_format = data_format
         self.config.update({'data_format': data_format,
                             'groups': groups,
                             'reduction': reduction,

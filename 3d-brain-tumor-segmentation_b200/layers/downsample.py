@@ -26,9 +26,10 @@ class ConvDownsample(Layer):
                             'groups': groups,
                             'l2_scale': l2_scale})
         self.groups = groups
+        self.data_format = data_format
         self.conv = Conv3D(filters=filters, kernel_size=3, strides=2, padding='same', data_format=data_format,
                            kernel_regularizer=L2(l2_scale), kernel_initializer='he_normal')
-        self.norm = GroupNormalization(groups=groups, axis=-1)
+        self.norm = GroupNormalization(groups=groups, axis=-1 if data_format == 'channels_last' else 1)
 
     def build(self, input_shape, device):
         self.conv.build(input_shape, device)
@@ -36,7 +37,7 @@ class ConvDownsample(Layer):
         self.built = True
 
     def call(self, inputs, training=None):
-        h, st, _ = self.conv.call(inputs, gn_groups=self.groups, aux=True)
+        h, st, _ = self.conv.call(inputs, gn_groups=0 if self.norm.channel_mode else self.groups, aux=True)
         return self.norm.call(h, stats=st, relu=True)
 
     def get_config(self):
@@ -51,8 +52,8 @@ class MaxDownsample(Layer):
                  data_format='channels_last',
                  **kwargs):
         super().__init__()
-        from ..keras_compat import _require_channels_last
-        _require_channels_last(data_format)
+        from ..keras_compat import check_data_format
+        self.data_format = check_data_format(data_format)
         self.config = super().get_config()
         self.config.update({'data_format': data_format})
 

@@ -47,6 +47,7 @@ class Encoder(Layer):
                  depth=4):
         super().__init__()
         self.config = super().get_config()
+        self.data_format = data_format
         self.config.update({'data_format': data_format,
                             'groups': groups,
                             'reduction': reduction,

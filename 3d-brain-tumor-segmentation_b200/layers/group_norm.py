@@ -27,6 +27,9 @@ class GroupNormalization(Layer):
         super().__init__(**kwargs)
         self.supports_masking = True
         self.groups, self.axis, self.epsilon = groups, axis, epsilon
+        # axis=1 = the reference's channels_first construction (true channel groups, NCDHW public tensors)
+        self.channel_mode = axis == 1
+        self.data_format = 'channels_first' if axis == 1 else 'channels_last'
         self.center, self.scale = center, scale
         self.beta_initializer, self.gamma_initializer = beta_initializer, gamma_initializer
         self.beta_regularizer, self.gamma_regularizer = beta_regularizer, gamma_regularizer
@@ -34,9 +37,9 @@ class GroupNormalization(Layer):
         self.gamma = self.beta = None
 
     def build(self, input_shape, device):
-        if self.axis not in (-1, len(input_shape) - 1):
-            raise NotImplementedError("b3d GroupNormalization: only axis=-1 (channels_last) is built so far")
-        dim = input_shape[self.axis]
+        if self.axis not in (-1, 1, len(input_shape) - 1):
+            raise NotImplementedError("b3d GroupNormalization: axis must be -1 (channels_last) or 1 (channels_first)")
+        dim = input_shape[-1]                      # storage is NDHWC in both cases (Layer.__call__ converts)
         if dim is None:
             raise ValueError('Axis ' + str(self.axis) + ' of input tensor should have a defined dimension '
                              'but the layer received an input with shape ' + str(input_shape) + '.')
@@ -61,7 +64,8 @@ class GroupNormalization(Layer):
     def call(self, inputs, training=None, stats=None, relu=False, **kwargs):
         gamma = self.gamma if self.scale else self._gamma_const
         beta = self.beta if self.center else self._beta_const
-        return ops.group_norm(inputs, gamma, beta, stats, self.groups, self.epsilon, relu)
+        return ops.group_norm(inputs, gamma, beta, None if self.channel_mode else stats, self.groups, self.epsilon,
+                              relu, channel_mode=self.channel_mode)
 
     def get_config(self):
         config = {

@@ -35,6 +35,8 @@ class ResnetBlock(Layer):
                             'l2_scale': l2_scale,
                             'groups': groups})
         self.filters, self.groups = filters, groups
+        self.data_format = data_format
+        self._fused_stats = data_format == 'channels_last'     # chunk statistics from the conv epilogue (F1 only)
 
         self.conv3d_ptwise = Conv3D(filters=filters, kernel_size=1, strides=1, padding='same',
                                     data_format=data_format, kernel_regularizer=L2(l2_scale),
@@ -60,7 +62,7 @@ class ResnetBlock(Layer):
             self.convs.append([Conv3D(filters=filters, kernel_size=3, strides=1, padding='same',
                                       data_format=data_format, kernel_regularizer=L2(l2_scale),
                                       kernel_initializer='he_normal'),
-                               GroupNormalization(groups=groups, axis=-1,
+                               GroupNormalization(groups=groups, axis=-1 if data_format == 'channels_last' else 1,
                                                   beta_initializer='zeros', gamma_initializer=gamma_init,
                                                   beta_regularizer=L2(l2_scale), gamma_regularizer=L2(l2_scale)),
                                _Activation('relu')])
@@ -79,7 +81,7 @@ class ResnetBlock(Layer):
         self.built = True
 
     def call(self, inputs, training=None):
-        g = self.groups
+        g = self.groups if self._fused_stats else 0
         res, _, gap = self.conv3d_ptwise.call(inputs, want_gap=True, aux=True, share_x=True)
         (conv1, norm1, _), (conv2, norm2, _) = self.convs
         h1, st1, _ = conv1.call(inputs, gn_groups=g, aux=True, share_x=True)
@@ -88,9 +90,9 @@ class ResnetBlock(Layer):
         if st2 is None:                                   # chunk boundaries not voxel-aligned: unfused GN2
             a2 = norm2.call(h2, relu=True)
             return ops.block_epilogue(res, a2, None, None, None, self.spatial.kernel, gap,
-                                      self.dense_relu.kernel, self.dense_sigmoid.kernel, g, norm2.epsilon)
+                                      self.dense_relu.kernel, self.dense_sigmoid.kernel, self.groups, norm2.epsilon)
         return ops.block_epilogue(res, h2, st2, norm2.gamma, norm2.beta, self.spatial.kernel, gap,
-                                  self.dense_relu.kernel, self.dense_sigmoid.kernel, g, norm2.epsilon)
+                                  self.dense_relu.kernel, self.dense_sigmoid.kernel, self.groups, norm2.epsilon)
 
     def get_config(self):
         return self.config

@@ -27,9 +27,10 @@ class ConvUpsample(Layer):
                             'groups': groups,
                             'l2_scale': l2_scale})
         self.groups = groups
+        self.data_format = data_format
         self.conv = Conv3DTranspose(filters=filters, kernel_size=3, strides=2, padding='same',
                                     data_format=data_format)
-        self.norm = GroupNormalization(groups=groups, axis=-1)
+        self.norm = GroupNormalization(groups=groups, axis=-1 if data_format == 'channels_last' else 1)
 
     def build(self, input_shape, device):
         self.conv.build(input_shape, device)
@@ -37,7 +38,7 @@ class ConvUpsample(Layer):
         self.built = True
 
     def call(self, inputs, training=None):
-        h, st = self.conv.call(inputs, gn_groups=self.groups, aux=True)
+        h, st = self.conv.call(inputs, gn_groups=0 if self.norm.channel_mode else self.groups, aux=True)
         return self.norm.call(h, stats=st, relu=True)
 
     def get_config(self):
@@ -58,6 +59,7 @@ class LinearUpsample(Layer):
         self.config.update({'filters': filters,
                             'data_format': data_format,
                             'l2_scale': l2_scale})
+        self.data_format = data_format
         self.ptwise = Conv3D(filters=filters, kernel_size=1, strides=1, padding='same', data_format=data_format,
                              kernel_regularizer=L2(l2_scale), kernel_initializer='he_normal')
 

@@ -134,6 +134,8 @@ class Model(Layer):
                  in_ch=2,
                  out_ch=3):
         super().__init__()
+        from .keras_compat import check_data_format
+        self.data_format = check_data_format(data_format)
         self.epoch = _EpochVariable(0)
         self.encoder = Encoder(data_format=data_format, groups=groups, reduction=reduction, l2_scale=l2_scale,
                                dropout=dropout, downsampling=downsampling, base_filters=base_filters, depth=depth)
@@ -146,6 +148,14 @@ class Model(Layer):
 
     # ---- Keras protocol
     def __call__(self, inputs, training=None, inference=None, **kw):
+        from .keras_compat import internal_layout, _internal_layout, map5d
+        if self.data_format == 'channels_first' and not _internal_layout():
+            # public tensors are NCDHW (model.py:58 under args.py's GPU default); storage inside is NDHWC
+            inputs = ops.to_channels_last(inputs)
+            kw = {k: map5d(v, ops.to_channels_last) for k, v in kw.items()}
+            with internal_layout():
+                out = self.__call__(inputs, training=training, inference=inference, **kw)
+            return map5d(out, ops.to_channels_first)
         if not self.built:
             # the reference builds all weights with a first call on zeros (train.py:96); here the first
             # call does a weight-creating dry run, then re-homes every tensor into the flat buffer

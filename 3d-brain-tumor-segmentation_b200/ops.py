@@ -249,11 +249,78 @@ class GroupNormFn(Function):
         return dx, (None if dg_direct else dgamma), (None if db_direct else dbeta), None, None, None, None
 
 
-def group_norm(x, gamma, beta, stats=None, groups=8, eps=1e-5, relu=False):
+class GroupNormChannelFn(Function):
+    """GroupNormalization with TRUE channel groups (reference data_format='channels_first': group_norm.py axis=1)
+    on NDHWC storage (csrc/norm_channel.cu), optional fused ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, relu):
+        _check(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        if C < groups:
+            raise ValueError(f"Number of groups ({groups}) cannot be more than the number of channels ({C}).")
+        if C % groups != 0:
+            raise ValueError(f"Number of groups ({groups}) must be a multiple of the number of channels ({C}).")
+        stats = _new((x.shape[0], groups, 2), x, torch.float64)
+        _call("b3d_gn_channel_stats", x, stats, groups)
+        y = _new_act(x.shape, x)
+        _call("b3d_gn_channel_apply", x, stats, gamma, beta, y, groups, float(eps), int(relu))
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.cfg = (groups, float(eps), int(relu))
+        ctx.params = (gamma, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, stats = ctx.saved_tensors
+        groups, eps, relu = ctx.cfg
+        pg, pb = ctx.params
+        dgamma, dg_direct = _grad_target(pg)
+        dbeta, db_direct = _grad_target(pb)
+        csum, dx = torch.empty_like(stats), torch.empty_like(x)
+        _call("b3d_gn_channel_bwd", dy.contiguous(), x, stats, gamma, beta, dgamma, dbeta, csum, dx, groups, eps, relu)
+        _grad_done(pg, dg_direct)
+        _grad_done(pb, db_direct)
+        return dx, (None if dg_direct else dgamma), (None if db_direct else dbeta), None, None, None
+
+
+def group_norm(x, gamma, beta, stats=None, groups=8, eps=1e-5, relu=False, channel_mode=False):
     ctx = _slab.current()
+    if channel_mode:
+        if ctx is not None:
+            raise NotImplementedError("b3d: depth-slab inference is built for the channels_last GroupNorm semantics")
+        return GroupNormChannelFn.apply(x, gamma, beta, groups, eps, relu)
     if ctx is not None:        # chunk statistics of the WHOLE volume: partial sums + all-reduce
         return ctx.group_norm(x, gamma, beta, groups, eps, relu)
     return GroupNormFn.apply(x, gamma, beta, stats, groups, eps, relu)
+
+
+class RelayoutFn(Function):
+    """NCDHW <-> NDHWC copy at the boundary of the channels_first API surface (differentiable)."""
+
+    @staticmethod
+    def forward(ctx, x, to_last):
+        _check(x)
+        x = x.contiguous()
+        B = x.shape[0]
+        shape = (B,) + tuple(x.shape[2:]) + (x.shape[1],) if to_last else (B, x.shape[4]) + tuple(x.shape[1:4])
+        y = _new(shape, x)
+        _call("b3d_relayout", x, y, int(to_last))
+        ctx.to_last = to_last
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return RelayoutFn.apply(dy, not ctx.to_last), None
+
+
+def to_channels_last(x):
+    return RelayoutFn.apply(x, True)
+
+
+def to_channels_first(x):
+    return RelayoutFn.apply(x, False)
 
 
 class BlockEpilogueFn(Function):
@@ -411,14 +478,14 @@ def dice_vae_loss(x, y, y_pred, y_vae=None, z_mean=None, z_logvar=None):
     return DiceVAELossFn.apply(x, y, y_pred, y_vae, z_mean, z_logvar)
 
 
-def dice_coefficient(y_true, y_pred):
-    """util.py:35-57 -> (macro, micro) as 0-d tensors (no gradient)."""
+def dice_coefficient(y_true, y_pred, reduce_w=False):
+    """util.py:35-57 -> (macro, micro) as 0-d tensors (no gradient).  reduce_w: the channels_first macro average."""
     _check(y_pred, "y_pred")
     y_true, y_pred = y_true.contiguous(), y_pred.detach().contiguous()
     W, C = y_pred.shape[3], y_pred.shape[4]
     acc = _new((W * C * 3,), y_pred)
     out = _new((2,), y_pred)
-    _call("b3d_dice_coeff", y_true, y_pred, acc, out)
+    _call("b3d_dice_coeff", y_true, y_pred, acc, out, int(reduce_w))
     return out[0], out[1]
 
 

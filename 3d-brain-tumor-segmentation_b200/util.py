@@ -12,11 +12,14 @@ class DiceVAELoss(object):
     + 0.1*mean(mu^2 + exp(logvar) - logvar - 1)  — one reduction pass (csrc/misc.cu)."""
 
     def __init__(self, name='custom_loss', data_format='channels_last', **kwargs):
-        if data_format != 'channels_last':
-            raise NotImplementedError("b3d: channels_first is listed under SURVEY §8(f)")
-        self.axis = (0, 1, 2, 3)
+        from .keras_compat import check_data_format
+        self.data_format = check_data_format(data_format)
+        self.axis = (0, 1, 2, 3) if data_format == 'channels_last' else (0, 2, 3, 4)
 
     def __call__(self, x, y, y_pred, y_vae, z_mean, z_logvar, sample_weight=None):
+        if self.data_format == 'channels_first':       # NCDHW arguments: the sums are layout-independent
+            from .keras_compat import map5d
+            x, y, y_pred, y_vae = (map5d(t, ops.to_channels_last) for t in (x, y, y_pred, y_vae))
         return ops.dice_vae_loss(x, y, y_pred, y_vae, z_mean, z_logvar)
 
 
@@ -25,12 +28,14 @@ class DiceCoefficient(object):
     un-reduced W axis (util.py:36,50-54)."""
 
     def __init__(self, name='dice_coefficient', data_format='channels_last'):
-        if data_format != 'channels_last':
-            raise NotImplementedError("b3d: channels_first is listed under SURVEY §8(f)")
+        from .keras_compat import check_data_format
         self.name = name
-        self.data_format = data_format
+        self.data_format = check_data_format(data_format)
 
     def __call__(self, y_true, y_pred):
+        if self.data_format == 'channels_first':       # util.py:36: axes (0,2,3,4) -> one ratio per class
+            y_true, y_pred = ops.to_channels_last(y_true), ops.to_channels_last(y_pred.detach())
+            return ops.dice_coefficient(y_true, y_pred, reduce_w=True)
         return ops.dice_coefficient(y_true, y_pred)
 
 

@@ -109,6 +109,18 @@ int b3d_gn_bwd_apply(const DLTensor* dy, const DLTensor* x, const DLTensor* stat
                      const DLTensor* beta, const DLTensor* csum, DLTensor* dx, int groups, float eps, int relu,
                      void* stream);
 
+/* ---- GroupNormalization with TRUE channel groups — the reference's data_format='channels_first' semantics
+ * (group_norm.py axis=1: group g = channels [g*C/G, (g+1)*C/G) of every voxel), on the same NDHWC storage
+ * (csrc/norm_channel.cu).  stats / csum: fp64 [B, G, 2].  gn_channel_bwd runs the reduction pass (dgamma, dbeta,
+ * csum) and the elementwise pass (dx).  relayout: NCDHW <-> NDHWC copies for the channels_first API surface. */
+int b3d_gn_channel_stats(const DLTensor* x, DLTensor* stats, int groups, void* stream);
+int b3d_gn_channel_apply(const DLTensor* x, const DLTensor* stats, const DLTensor* gamma, const DLTensor* beta,
+                         DLTensor* y, int groups, float eps, int relu, void* stream);
+int b3d_gn_channel_bwd(const DLTensor* dy, const DLTensor* x, const DLTensor* stats, const DLTensor* gamma,
+                       const DLTensor* beta, DLTensor* dgamma, DLTensor* dbeta, DLTensor* csum, DLTensor* dx,
+                       int groups, float eps, int relu, void* stream);
+int b3d_relayout(const DLTensor* src, DLTensor* dst, int to_channels_last, void* stream);
+
 /* ---- ResnetBlock epilogue (resnet.py:121-137) --------------------------------------------------
  * chse = sigmoid(relu(gap_sum*inv_vox . W1) . W2);  out = res*(sigmoid(res.w_sp)+chse) + relu(GN2(h2)).
  * has_gn=0: h2 is already normalised+activated (stats/gamma/beta NULL). */
@@ -148,7 +160,8 @@ int b3d_loss_bwd(const DLTensor* x, const DLTensor* y, const DLTensor* y_pred, c
                  const DLTensor* z_mean, const DLTensor* z_logvar, const DLTensor* sums, const DLTensor* gout,
                  DLTensor* dy_pred, DLTensor* dy_vae, DLTensor* dz_mean, DLTensor* dz_logvar, void* stream);
 int b3d_dice_coeff(const DLTensor* y, const DLTensor* y_pred, DLTensor* acc /*fp32 [W*C*3]*/,
-                   DLTensor* out /*fp32 [2] macro, micro*/, void* stream);
+                   DLTensor* out /*fp32 [2] macro, micro*/, int reduce_w /*1: channels_first macro (util.py:36)*/,
+                   void* stream);
 
 /* ---- optimiser + regulariser (util.py:60-84 TF Adam, eps un-scaled; train.py:146 model.losses) ---*/
 /* g_eff = g*grad_scale + decay*theta (first n_decay elements only; decay = 2*l2 in data-parallel mode) */

@@ -79,11 +79,35 @@ def dense(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.
 # ----------------------------------------------------------------------------------
 # layers/group_norm.py:83-124
 # ----------------------------------------------------------------------------------
+# data_format='channels_first' semantics on channels_last-stored tensors: the reference then builds its layers with
+# GroupNormalization(axis=1) (resnet.py:89, downsample.py:36, upsample.py:34), i.e. TRUE channel groups, while every
+# other op is layout-agnostic.  The oracle keeps its NDHWC storage; inside `channels_first_semantics()` group_norm
+# evaluates the literal restatement on the NCDHW view with axis=1.
+_CF = {"on": False}
+
+
+class channels_first_semantics:
+    def __enter__(self):
+        self.prev = _CF["on"]
+        _CF["on"] = True
+
+    def __exit__(self, *a):
+        _CF["on"] = self.prev
+        return False
+
+
 def group_norm(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
                groups: int = 8, eps: float = 1e-5, axis: int = -1) -> torch.Tensor:
     """Literal restatement of GroupNormalization.call: raw reshape of [B,...,C] to
     [B,G,...,C/G] (no transpose, group_norm.py:84-100), moments over axes 2.. (:105),
     division by sqrt(var+eps) (:107), gamma/beta reshaped to broadcast_shape (:114-122)."""
+    if _CF["on"] and x.dim() == 5 and axis in (-1, 4):
+        out = _group_norm_literal(x.permute(0, 4, 1, 2, 3).contiguous(), gamma, beta, groups, eps, 1)
+        return out.permute(0, 2, 3, 4, 1).contiguous()
+    return _group_norm_literal(x, gamma, beta, groups, eps, axis)
+
+
+def _group_norm_literal(x, gamma, beta, groups, eps, axis):
     shape = list(x.shape)
     nd = len(shape)
     ax = axis % nd
@@ -259,15 +283,17 @@ def dice_vae_loss(x, y, y_pred, y_vae, z_mean, z_logvar):
     return dice + 0.1 * l2 + 0.1 * kld
 
 
-def dice_coefficient(y_true, y_pred):
-    """util.py:35-57 (channels_last).  NB the macro average reduces axes (0,1,2) only, so the
-    ratio is [W, C]-shaped before the mean — kept, it is the reference's number."""
+def dice_coefficient(y_true, y_pred, data_format="channels_last"):
+    """util.py:35-57 on channels_last-stored tensors.  NB for data_format='channels_last' the macro average reduces
+    axes (0,1,2) only, so the ratio is [W, C]-shaped before the mean — kept, it is the reference's
+    number; for 'channels_first' the reference reduces (0,2,3,4), i.e. all of batch and space (util.py:36)."""
     mask = (y_pred.max(dim=-1, keepdim=True).values > 0.5).to(y_pred.dtype)
     C = y_pred.shape[-1]
     hard = F.one_hot(y_pred.argmax(dim=-1), C).to(y_pred.dtype) * mask
-    inter = (hard * y_true).sum(dim=(0, 1, 2))
-    pred = hard.sum(dim=(0, 1, 2))
-    true = y_true.sum(dim=(0, 1, 2))
+    axes = (0, 1, 2) if data_format == "channels_last" else (0, 1, 2, 3)
+    inter = (hard * y_true).sum(dim=axes)
+    pred = hard.sum(dim=axes)
+    true = y_true.sum(dim=axes)
     macro = ((2.0 * inter + 1.0) / (pred + true + 1.0)).mean()
     micro = (hard * y_true).sum() / (hard.sum() + y_true.sum())
     return macro, micro

@@ -403,3 +403,30 @@ def test_gpu_example_pipeline_matches_oracle(b3d, dev, case):
     assert batches[0][1].shape[1:] == tuple(crop) + (K,) and float(batches[0][1].sum(-1).max()) <= 1.0
     ds2 = b3d.VolumeDataset([(dev32(x, dev), dev32(y, dev))] * 3, batch_size=2, crop_size=crop, out_ch=K, seed=5)
     assert torch.equal(next(iter(ds2))[0], batches[0][0])
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 8, 16), (1, 6, 5, 7, 32), (1, 4, 4, 4, 192), (2, 3, 3, 3, 8)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_group_norm_channels_first_semantics(b3d, dev, shape, relu):
+    """GroupNormalization(axis=1) — true channel groups, the reference's data_format='channels_first' behaviour
+    (group_norm.py:83-124) — on NCDHW public tensors, forward and all gradients vs the oracle."""
+    x, ga, be = t64(*shape, seed=51), 1 + 0.3 * t64(shape[-1], seed=52), 0.3 * t64(shape[-1], seed=53)
+    xr, gr, br = (t.clone().requires_grad_(True) for t in (x, ga, be))
+    with R.channels_first_semantics():
+        yr = R.group_norm(xr, gr, br)
+    yr = torch.relu(yr) if relu else yr
+    gy = t64(*shape, seed=54)
+    (yr * gy).sum().backward()
+    cf = lambda t: t.permute(0, 4, 1, 2, 3).contiguous()
+    gn = b3d.GroupNormalization(groups=8, axis=1)
+    xd = dev32(cf(x), dev, True)                       # NCDHW in, NCDHW out
+    gn(xd.detach())
+    with torch.no_grad():
+        gn.gamma.copy_(ga.float())
+        gn.beta.copy_(be.float())
+    y = gn(xd, relu=relu)
+    assert tuple(y.shape) == tuple(cf(x).shape)
+    (y * dev32(cf(gy), dev)).sum().backward()
+    assert rel(y, cf(yr)) < TOL32
+    assert rel(xd.grad, cf(xr.grad)) < 2e-4
+    assert rel(gn.gamma.grad, gr.grad) < 1e-4 and rel(gn.beta.grad, br.grad) < 1e-4

@@ -303,3 +303,54 @@ def test_checkpoint_roundtrip_and_train_log(b3d, dev, tmp_path):
     with torch.no_grad():
         y1 = other(f(x), training=False, inference=True)[0]
     assert rel(y1, y0) < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["fp32", "mixed"])
+def test_channels_first_model_matches_oracle(b3d, dev, mode):
+    """Model(data_format='channels_first') — the reference's GPU default (args.py:121-123): NCDHW tensors, true
+    channel GroupNorm, loss axes (0,2,3,4), per-class Dice.  One training step and the inference forward against the
+    oracle's channels_first semantics (pinned live on the reference code in tests/test_oracle.py)."""
+    crop = (32, 32, 16)
+    p = R.init_params(R.param_shapes(crop=crop))
+    x, y, eps, mask = R.synth_batch((1,) + crop)
+    cf = lambda t: t.permute(0, 4, 1, 2, 3).contiguous()
+    pg = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    with R.channels_first_semantics():
+        outs = R.model_forward(pg, x, eps, dropout_mask=mask)
+        ref = R.dice_vae_loss(x, y, *outs) + R.l2_reg(pg)
+        yi_ref = R.model_forward(p, x, eps, inference=True)[0]
+    ref.backward()
+    mr, ur = R.dice_coefficient(y, outs[0].detach(), data_format="channels_first")
+    set_mode(b3d, mode)
+    try:
+        f = lambda t: cf(t).to(torch.float32).to(dev)
+        model = b3d.Model(data_format='channels_first')
+        model(torch.zeros((1, 2) + crop, device=dev), training=False, inference=False)
+        model.load_named_weights(p)
+        with torch.no_grad():
+            yi = model(f(x), training=False, inference=True)[0]
+        assert tuple(yi.shape) == (1, 3) + crop
+        opt = b3d.ScheduledOptim(learning_rate=1e-4)
+        opt(epoch=0)
+        loss, macro, micro = b3d.train_step(model, opt, b3d.DiceVAELoss(data_format='channels_first'),
+                                            b3d.DiceCoefficient(data_format='channels_first'), f(x), f(y),
+                                            dropout_mask=f(mask), eps=eps.float().to(dev))
+        torch.cuda.synchronize()
+    finally:
+        reset_mode(b3d)
+    tol = 2e-5 if mode == "fp32" else 2e-3
+    assert rel(yi, cf(yi_ref)) < tol, rel(yi, cf(yi_ref))
+    assert abs(float(loss) - float(ref)) / float(ref) < 1e-3
+    assert abs(float(macro) - float(mr)) < 2e-3 and abs(float(micro) - float(ur)) < 2e-3
+    nv = model.named_variables()
+    # a bias in front of a one-channel-per-group GroupNorm (vae.down: 8 channels, 8 groups) has an exactly zero
+    # gradient: compare it absolutely, everything else relatively
+    live = [k for k in p if float(pg[k].grad.norm()) > 1e-9]
+    assert all(float(nv[k].grad.norm()) < 1e-6 for k in p if k not in live)
+    errs = sorted(((rel(nv[k].grad, pg[k].grad), k) for k in live), reverse=True)
+    coss = sorted((_cos(nv[k].grad, pg[k].grad), k) for k in live)
+    print(f"channels_first {mode}: worst grad {errs[0]}, min cos {coss[0]}")
+    if mode == "fp32":
+        assert errs[len(errs) // 2][0] < 3e-3 and errs[0][0] < 5e-2, errs[:5]
+    else:
+        assert coss[0][0] > 0.90 and coss[len(coss) // 10][0] > 0.98, coss[:5]
