@@ -120,6 +120,24 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return OP == OP_F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
 
+// add a warp's running GroupNorm sums to stats[chunk]: one pair of fp64 atomics per warp when all its lanes are in the
+// same chunk (the common case), per lane otherwise.  Must be called by all 32 lanes.
+__device__ __noinline__ void flush_stats(double* stats, int cur_chunk, float s0, float s1, int lane) {
+  const int cc = __reduce_max_sync(0xffffffffu, cur_chunk);
+  if (cc < 0) return;                                               // nothing accumulated anywhere in the warp
+  const bool uni = __all_sync(0xffffffffu, cur_chunk == cc || cur_chunk < 0);
+  if (uni) {
+    const float a0 = warp_sum(cur_chunk >= 0 ? s0 : 0.f), a1 = warp_sum(cur_chunk >= 0 ? s1 : 0.f);
+    if (lane == 0) {
+      atomicAdd(&stats[2 * cc], (double)a0);
+      atomicAdd(&stats[2 * cc + 1], (double)a1);
+    }
+  } else if (cur_chunk >= 0) {
+    atomicAdd(&stats[2 * cur_chunk], (double)s0);
+    atomicAdd(&stats[2 * cur_chunk + 1], (double)s1);
+  }
+}
+
 constexpr int kLoaderWarps = 8;
 constexpr int kTcThreads = (4 + kLoaderWarps + 2) * 32;   // 4 epilogue + loaders + MMA + weights
 
@@ -372,15 +390,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
               prm.d2s ? ((long long)(2 * d + ep_d) * (2 * prm.H) + (2 * h + ep_h)) * (2 * prm.W) + (2 * w + ep_w)
                       : ((long long)d * prm.H + h) * prm.W + w;
           float* yp = prm.y + ((long long)b * S + vox) * prm.yp + ycol;
-          if (prm.stats != nullptr && valid) {
-            const int chunk = b * prm.groups + (int)(vox / prm.vpc);
-            if (chunk != cur_chunk) {
-              if (cur_chunk >= 0) {
-                atomicAdd(&prm.stats[2 * cur_chunk], (double)s0);
-                atomicAdd(&prm.stats[2 * cur_chunk + 1], (double)s1);
-              }
-              cur_chunk = chunk; s0 = 0.f; s1 = 0.f;
+          if (prm.stats != nullptr) {
+            // the GroupNorm chunk of this patch's voxels; when any lane moves on to another chunk the whole warp
+            // flushes its running sums (warp-reduced: two fp64 atomics per warp, not per lane)
+            const int chunk = valid ? b * prm.groups + (int)(vox / prm.vpc) : cur_chunk;
+            if (__any_sync(0xffffffffu, chunk != cur_chunk && cur_chunk >= 0)) {
+              flush_stats(prm.stats, cur_chunk, s0, s1, lane);
+              cur_chunk = -1; s0 = 0.f; s1 = 0.f;
             }
+            if (valid) cur_chunk = chunk;
           }
           float v[16];
           tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + p * C::N + j * 16, v);
@@ -438,21 +456,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
-      if (prm.stats != nullptr) {
-        const int c0 = __shfl_sync(0xffffffffu, cur_chunk, 0);
-        const bool uni = __all_sync(0xffffffffu, cur_chunk == c0 || cur_chunk < 0);
-        if (uni) {
-          const int cc = __reduce_max_sync(0xffffffffu, cur_chunk);
-          const float a0 = warp_sum(cur_chunk >= 0 ? s0 : 0.f), a1 = warp_sum(cur_chunk >= 0 ? s1 : 0.f);
-          if (lane == 0 && cc >= 0) {
-            atomicAdd(&prm.stats[2 * cc], (double)a0);
-            atomicAdd(&prm.stats[2 * cc + 1], (double)a1);
-          }
-        } else if (cur_chunk >= 0) {
-          atomicAdd(&prm.stats[2 * cur_chunk], (double)s0);
-          atomicAdd(&prm.stats[2 * cur_chunk + 1], (double)s1);
-        }
-      }
+      if (prm.stats != nullptr) flush_stats(prm.stats, cur_chunk, s0, s1, lane);
     }
     if (kGapPersist) flush_gap(gap_b);
   }
