@@ -92,6 +92,19 @@ __global__ void __launch_bounds__(kThreads)
   const long long base = (long long)blockIdx.x * (kThreads * kIter * VEC);
   const int jbase = g * gm.cg;
   const long long goff = (long long)g * gm.L;
+  // affine index of element e: (goff + e) % cg.  When cg | kThreads*VEC it is the same for every element a thread
+  // touches, so scale = rstd*gamma_j and beta_j are fetched once (no per-element modulo / loads)
+  const bool invariant = ((kThreads * VEC) % gm.cg) == 0;
+  float sc[4] = {0.f, 0.f, 0.f, 0.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+  if (invariant) {
+    const int c_first = (int)((goff + base + threadIdx.x * VEC) % gm.cg);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int j = (c_first + i) % gm.cg;
+      sc[i] = rstd * __ldg(gamma + jbase + j);
+      sh[i] = __ldg(beta + jbase + j);
+    }
+  }
   float in[kIter][4];
 #pragma unroll
   for (int k = 0; k < kIter; ++k) {
@@ -109,14 +122,22 @@ __global__ void __launch_bounds__(kThreads)
   for (int k = 0; k < kIter; ++k) {
     const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
     if (e >= e_lo && e < e_hi) {
-      const int c0 = (int)((goff + e) % gm.cg);
       float o[4];
+      if (invariant) {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        int j = c0 + i;
-        j = j >= gm.cg ? j % gm.cg : j;
-        const float t = (in[k][i] - mean) * rstd * __ldg(gamma + jbase + j) + __ldg(beta + jbase + j);
-        o[i] = RELU ? fmaxf(t, 0.f) : t;
+        for (int i = 0; i < VEC; ++i) {
+          const float t = fmaf(in[k][i] - mean, sc[i], sh[i]);     // (x - mean) first: no cancellation
+          o[i] = RELU ? fmaxf(t, 0.f) : t;
+        }
+      } else {
+        const int c0 = (int)((goff + e) % gm.cg);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          int j = c0 + i;
+          j = j >= gm.cg ? j % gm.cg : j;
+          const float t = (in[k][i] - mean) * rstd * __ldg(gamma + jbase + j) + __ldg(beta + jbase + j);
+          o[i] = RELU ? fmaxf(t, 0.f) : t;
+        }
       }
       if (VEC == 4) st_stream(reinterpret_cast<float4*>(y + off + e), make_float4(o[0], o[1], o[2], o[3]));
       else y[off + e] = o[0];
