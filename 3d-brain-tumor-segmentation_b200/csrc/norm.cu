@@ -271,11 +271,21 @@ __global__ void __launch_bounds__(kThreads)
   const long long base = (long long)blockIdx.x * (kThreads * kIter * VEC);
   const int jbase = g * gm.cg;
   const long long goff = (long long)g * gm.L;
+  const bool invariant = ((kThreads * VEC) % gm.cg) == 0;       // see gn_apply_kernel
+  const int c_first = (int)((goff + base + threadIdx.x * VEC) % gm.cg);
+  float gai[4] = {0.f, 0.f, 0.f, 0.f}, bei[4] = {0.f, 0.f, 0.f, 0.f};
+  if (invariant) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      gai[i] = __ldg(gamma + jbase + (c_first + i) % gm.cg);
+      bei[i] = __ldg(beta + jbase + (c_first + i) % gm.cg);
+    }
+  }
 #pragma unroll
   for (int k = 0; k < kIter; ++k) {
     const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
     if (e < gm.L) {
-      const int c0 = (int)((goff + e) % gm.cg);
+      const int c0 = invariant ? c_first : (int)((goff + e) % gm.cg);
       float dv[4], xv[4], o[4];
       if (VEC == 4) {
         const float4 a = ld_stream(reinterpret_cast<const float4*>(dy + off + e));
@@ -288,12 +298,18 @@ __global__ void __launch_bounds__(kThreads)
       }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        int j = c0 + i;
-        j = j >= gm.cg ? j % gm.cg : j;
-        const float ga = __ldg(gamma + jbase + j);
+        float ga, be;
+        if (invariant) {
+          ga = gai[i]; be = bei[i];
+        } else {
+          int j = c0 + i;
+          j = j >= gm.cg ? j % gm.cg : j;
+          ga = __ldg(gamma + jbase + j);
+          be = __ldg(beta + jbase + j);
+        }
         const float xh = (xv[i] - mean) * rstd;
         float gq = dv[i];
-        if (RELU) gq = (xh * ga + __ldg(beta + jbase + j)) > 0.f ? gq : 0.f;
+        if (RELU) gq = (xh * ga + be) > 0.f ? gq : 0.f;
         o[i] = rstd * (gq * ga - m1 - xh * m2);
       }
       if (VEC == 4)
