@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256)
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n4 = n_seg / 4;
+#pragma unroll 4
   for (long long i = tid; i < n4; i += stride) {
     const float4 a = ld_stream(reinterpret_cast<const float4*>(yp) + i);
     const float4 b = ld_stream(reinterpret_cast<const float4*>(y) + i);
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256)
   float sse = 0.f;
   if (x != nullptr) {
     const long long m4 = n_rec / 4;
+#pragma unroll 4
     for (long long i = tid; i < m4; i += stride) {
       const float4 a = ld_stream(reinterpret_cast<const float4*>(x) + i);
       const float4 b = ld_stream(reinterpret_cast<const float4*>(yv) + i);
@@ -63,17 +65,17 @@ __global__ void __launch_bounds__(256)
   if (mu != nullptr && blockIdx.x == 0)
     for (int i = threadIdx.x; i < n_lat; i += blockDim.x) kl += mu[i] * mu[i] + expf(lv[i]) - lv[i] - 1.0f;
 
-  __shared__ double red[32 * (3 * C + 2)];
-  double v[3 * C + 2];
+  __shared__ float red[32 * (3 * C + 2)];
+  float v[3 * C + 2];
 #pragma unroll
   for (int c = 0; c < C; ++c) { v[c] = I[c]; v[C + c] = P[c]; v[2 * C + c] = T[c]; }
   v[3 * C] = sse;
   v[3 * C + 1] = kl;
-  block_sum<3 * C + 2, double>(v, red);
+  block_sum<3 * C + 2, float>(v, red);          // per-CTA partials in fp32 (<= 1e5 terms each), fp64 across CTAs
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < 3 * C + 2; ++i)
-      if (v[i] != 0.0) atomicAdd(&sums[i], v[i]);
+      if (v[i] != 0.f) atomicAdd(&sums[i], (double)v[i]);
   }
 }
 
@@ -162,27 +164,44 @@ __global__ void __launch_bounds__(256)
   extern __shared__ float sm[];  // [W][C][3]
   for (int i = threadIdx.x; i < W * C * 3; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
-  for (long long r = blockIdx.x; r < nrows; r += gridDim.x) {
-    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+  // thread -> fixed w column (w = tid % W), rows dealt to the blockDim/W thread groups of all CTAs; per-thread
+  // register accumulators, merged into shared memory once at the end.  (W > blockDim: columns are strided.)
+  const int rpb = blockDim.x >= W ? blockDim.x / W : 1;             // rows in flight per CTA
+  const int wl = threadIdx.x % W, rl = threadIdx.x / W;
+  const bool active = rl < rpb;
+  for (int w = wl; w < W && active; w += blockDim.x >= W ? W : blockDim.x) {
+    float a0[C], a1[C], a2[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) a0[c] = a1[c] = a2[c] = 0.f;
+#pragma unroll 4
+    for (long long r = (long long)blockIdx.x * rpb + rl; r < nrows; r += (long long)gridDim.x * rpb) {
       const long long e = (r * W + w) * C;
       float p[C], t[C];
       int am = 0;
       float mx = -1e30f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        p[c] = yp[e + c];
-        t[c] = y[e + c];
-        if (p[c] > mx) { mx = p[c]; am = c; }   // first maximum, like tf.argmax
+        p[c] = __ldg(yp + e + c);
+        t[c] = __ldg(y + e + c);
       }
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        if (p[c] > mx) { mx = p[c]; am = c; }   // first maximum, like tf.argmax
       const float on = mx > 0.5f ? 1.f : 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const float h = (c == am) ? on : 0.f;
-        float* a = sm + (w * C + c) * 3;
-        a[0] += h * t[c];   // each (w) column is owned by one thread of this CTA
-        a[1] += h;
-        a[2] += t[c];
+        a0[c] += h * t[c];
+        a1[c] += h;
+        a2[c] += t[c];
       }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float* a = sm + (w * C + c) * 3;
+      atomicAdd(a, a0[c]);
+      atomicAdd(a + 1, a1[c]);
+      atomicAdd(a + 2, a2[c]);
     }
   }
   __syncthreads();
@@ -527,7 +546,8 @@ extern "C" int b3d_loss_fwd(const DLTensor* x_, const DLTensor* y_, const DLTens
   B3D_REQUIRE(out.numel == 4, B3D_ERR_SHAPE, "out: expected 4 floats");
   cudaStream_t s = (cudaStream_t)stream;
   B3D_TRY(cuda_ok(cudaMemsetAsync(sums.p, 0, sizeof(double) * sums.numel, s), "memset sums"));
-  const unsigned grid = ew_grid(yp.numel, 16);
+  unsigned grid = ew_grid(yp.numel, 16);
+  if (grid > 4u * (unsigned)sm_count()) grid = 4u * (unsigned)sm_count();   // each CTA ends in 3C+2 fp64 atomics
   DISPATCH_C(C, (loss_fwd_kernel<kC><<<grid, 256, 0, s>>>(
                     (const float*)yp.p, (const float*)y.p, yp.numel, vae ? (const float*)x.p : nullptr,
                     vae ? (const float*)yv.p : nullptr, vae ? x.numel : 0, vae ? (const float*)mu.p : nullptr,
@@ -591,7 +611,7 @@ extern "C" int b3d_dice_coeff(const DLTensor* y_, const DLTensor* ypred_, DLTens
   cudaStream_t s = (cudaStream_t)stream;
   B3D_TRY(cuda_ok(cudaMemsetAsync(acc.p, 0, sizeof(float) * acc.numel, s), "memset acc"));
   const long long nrows = yp.numel / ((long long)W * C);
-  unsigned grid = (unsigned)(nrows < 8LL * sm_count() ? nrows : 8LL * sm_count());
+  unsigned grid = (unsigned)(nrows < 4LL * sm_count() ? nrows : 4LL * sm_count());
   const size_t smem = sizeof(float) * W * C * 3;
   DISPATCH_C(C, (dice_coeff_kernel<kC><<<grid, 256, smem, s>>>((const float*)y.p, (const float*)yp.p, nrows, W,
                                                                 (float*)acc.p)));
