@@ -156,3 +156,55 @@ def test_slab_inference_matches_oracle(b3d, dev):
         assert rel(got, yr) < 2e-5, rel(got, yr)
     finally:
         ops.USE_TC["on"] = True
+
+
+def _peer_worker(rank, world, port, q):
+    import importlib
+    import os
+    import sys
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    b3d = importlib.import_module("3d-brain-tumor-segmentation_b200")
+    try:
+        model = _built_model(b3d, dev)                     # same seed => same weights on every rank
+        x = t32(1, 32, 32, 16, 2, seed=11, dev=dev)
+        with torch.no_grad():
+            whole = model(x, training=False, inference=True)[0]
+        res = {}
+        for name, comm in (("peer", b3d.PeerComm(mailbox_bytes=1 << 20)), ("nccl", b3d.DistComm())):
+            y, (d0, d1) = b3d.sharded_inference(model, x, comm, gather=False)
+            res[name] = rel(y, whole[:, d0:d1])
+            # twice more through one CUDA graph (epoch counter / sequence numbers advance on replay)
+            if name == "peer":
+                gi = b3d.GraphedInference(model, x[:, d0:d1].contiguous(), comm, depth=x.shape[1])
+                gi(); res["peer_graph"] = rel(gi(), whole[:, d0:d1])
+        q.put((rank, res))
+    except BaseException as e:      # noqa: BLE001
+        q.put((rank, repr(e)))
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_peer_memory_comm_two_gpus():
+    """PeerComm (NVLink peer-memory halo exchange + small all-reduces, csrc/slab_comm.cu) and DistComm (NCCL) on two
+    real GPUs against the un-sharded forward, eagerly and through a replayed CUDA graph."""
+    import os
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for r in (0, 1):
+        assert isinstance(out[r], dict), out[r]
+        assert all(v < 1e-3 for v in out[r].values()), out
