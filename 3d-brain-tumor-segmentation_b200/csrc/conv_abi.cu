@@ -187,6 +187,10 @@ extern "C" int b3d_conv3d_dgrad(const DLTensor* dy_, const DLTensor* w_, DLTenso
   return run(g, dy, w, nullptr, dx, nullptr, 1, nullptr, wpacked_, (cudaStream_t)stream);
 }
 
+// TS-mode weight gradient (conv_tc_wgrad_ts.cu) on / off — b3d_set_wgrad_ts, default on
+static int g_wgrad_ts = 1;
+extern "C" int b3d_set_wgrad_ts(int on) { g_wgrad_ts = on ? 1 : 0; return 0; }
+
 namespace {
 // How the tcgen05 weight gradient of a layer is fed: bf16 channels per voxel of the two scratch copies.
 //   kind 0: not on the tensor cores (fp32 CUDA-core kernel)
@@ -261,13 +265,20 @@ extern "C" int b3d_conv3d_wgrad(const DLTensor* x_, const DLTensor* dy_, DLTenso
       float* db_sml = transposed ? nullptr : db;
       // x_bf16_ready: the caller already holds the plain bf16 copy of x (two convs of a ResnetBlock share their input)
       const bool skip_big = x_bf16_ready && !transposed && stride == 1, skip_sml = x_bf16_ready && transposed;
+      // narrow outputs (Cout <= 32, the 128^3 / 64^3 levels): TS-mode kernel, dy copied in its transposed block order
+      const bool ts = g_wgrad_ts && !transposed && stride == 1 && tc_wgrad_ts_supported(wg);
       if (stride == 2)
         B3D_TRY(launch_cast_bf16_s2d((const float*)big.p, bigb.p, wg.B, wg.Ds, wg.Hs, wg.Ws, wg.nA, big.pitch, db_big, s));
       else if (!skip_big)
         B3D_TRY(launch_cast_bf16((const float*)big.p, bigb.p, big.numel / big.shape[4], wg.nA, db_big, s));
-      if (!skip_sml)
-        B3D_TRY(launch_cast_bf16((const float*)sml.p, smlb.p, sml.numel / sml.shape[4], wg.nB, db_sml, s));
-      B3D_TRY(launch_conv_wgrad_tc(wg, bigb.p, smlb.p, (float*)dw.p, s));
+      if (ts) {
+        B3D_TRY(launch_cast_bf16_t8((const float*)sml.p, smlb.p, sml.numel / sml.shape[4], wg.nB, db_sml, s));
+        B3D_TRY(launch_conv_wgrad_ts(wg, bigb.p, smlb.p, (float*)dw.p, s));
+      } else {
+        if (!skip_sml)
+          B3D_TRY(launch_cast_bf16((const float*)sml.p, smlb.p, sml.numel / sml.shape[4], wg.nB, db_sml, s));
+        B3D_TRY(launch_conv_wgrad_tc(wg, bigb.p, smlb.p, (float*)dw.p, s));
+      }
       bias_done = db != nullptr;
     } else {
       // narrow layer: all taps of the narrow tensor stacked into the M dimension of a single 1x1x1-style GEMM

@@ -48,6 +48,10 @@ int tc_pick_n(int Cout);               // N tile of the tcgen05 conv for this ou
 bool tc_wgrad_supported(const WgradGeom& wg);
 int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x_bf16, const void* dy_bf16, float* dw, cudaStream_t s,
                          int rows_real = 0, int tr_cn = 0, long long dw_elems = 0);
+// TS-mode weight gradient for narrow outputs (conv_tc_wgrad_ts.cu)
+bool tc_wgrad_ts_supported(const WgradGeom& wg);
+int launch_conv_wgrad_ts(const WgradGeom& wg, const void* x_bf16, const void* dyT_bf16, float* dw, cudaStream_t s);
+int launch_cast_bf16_t8(const float* src, void* dst, long long nvox, int C, float* colsum, cudaStream_t s);
 int launch_cast_stack_bf16(const float* src, void* dst, int B, int D, int H, int W, int Cn, long long pitch, int k,
                            int sgn, int nA, cudaStream_t s);
 int launch_cast_bf16(const float* src, void* dst, long long nvox, int C, float* colsum, cudaStream_t s);

@@ -71,6 +71,9 @@ int b3d_conv3d_wgrad(const DLTensor* x, const DLTensor* dy, DLTensor* dw, DLTens
                      int transposed, const DLTensor* x_bf16, const DLTensor* dy_bf16, int x_bf16_ready,
                      void* stream);
 int b3d_conv3d_wgrad_tc_supported(int k, int stride, int transposed, int cin, int cout);
+/* narrow-output 3x3x3 layers (Cout <= 32) use the TS-mode kernel (A operand in tensor memory, csrc/conv_tc_wgrad_ts.cu)
+ * unless switched off (A/B comparisons, tests) */
+int b3d_set_wgrad_ts(int on);
 /* returns 0 (CUDA cores), 1 (plain copies), 2 / 3 (narrow input / output: tap-stacked copy); *x_ch, *dy_ch
  * receive the bf16 channels per voxel of the two scratch buffers */
 int b3d_conv3d_wgrad_plan(int k, int stride, int transposed, int cin, int cout, long long* x_ch, long long* dy_ch);

@@ -74,7 +74,7 @@ def test_model_matches_reference_fixture_16(b3d, dev, mode):
     assert abs(float(macro) - float(g["macro"])) < 2e-3 and abs(float(micro) - float(g["micro"])) < 2e-3
     nv = model.named_variables()
     names = list(g["grad_names"])
-    ntol = {"fp32": 2e-3, "tf32": 1e-1, "mixed": 3e-1}[mode]   # 16^3 is the ill-conditioned extreme (1-voxel GN chunks)
+    ntol = {"fp32": 2e-3, "tf32": 2e-1, "mixed": 3e-1}[mode]   # 16^3 is the ill-conditioned extreme (1-voxel GN chunks)
     bad = [(k, float(nv[k].grad.norm()), float(r)) for k, r in zip(names, g["grad_norms"])
            if abs(float(nv[k].grad.norm()) - r) > ntol * r + 1e-7]
     assert not bad, bad[:8]
