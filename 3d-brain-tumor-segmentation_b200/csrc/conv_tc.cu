@@ -139,7 +139,11 @@ __device__ __noinline__ void flush_stats(double* stats, int cur_chunk, float s0,
 }
 
 constexpr int kLoaderWarps = 8;
-constexpr int kTcThreads = (4 + kLoaderWarps + 2) * 32;   // 4 epilogue + loaders + MMA + weights
+// Number of MMA-issuing warps (each owns the patches p = its index mod kMmaWarps).  One warp can issue a tcgen05.mma
+// only every ~50 cycles (profiles/r01_umma_rate.txt), but measured with 2 issuers this kernel does not get faster (the
+// shifted-tile A fetch from shared memory, ~56 cycles per N = 16 MMA here, is the limit, not the issue rate): 1.
+constexpr int kMmaWarps = 1;
+constexpr int kTcThreads = (4 + kLoaderWarps + 2 + (kMmaWarps - 1)) * 32;   // 4 epilogue + loaders + MMA + weights + MMA
 
 template <class C>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams prm) {
@@ -162,9 +166,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
   const int nsp = blockIdx.y;  // N split
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::HS; ++i) { mbar_init(smem_u32(&halo_full[i]), kLoaderWarps * 32); mbar_init(smem_u32(&halo_empty[i]), 1); }
-    for (int i = 0; i < C::WS; ++i) { mbar_init(smem_u32(&w_full[i]), 1); mbar_init(smem_u32(&w_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
+    for (int i = 0; i < C::HS; ++i) { mbar_init(smem_u32(&halo_full[i]), kLoaderWarps * 32); mbar_init(smem_u32(&halo_empty[i]), kMmaWarps); }
+    for (int i = 0; i < C::WS; ++i) { mbar_init(smem_u32(&w_full[i]), 1); mbar_init(smem_u32(&w_empty[i]), kMmaWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), kMmaWarps); mbar_init(smem_u32(&acc_empty[i]), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kLoaderWarps + 5) {
@@ -275,9 +279,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
         }
       }
     }
-  } else if (warp == kLoaderWarps + 4) {
+  } else if (warp == kLoaderWarps + 4 || warp >= kLoaderWarps + 6) {
     // ============ MMA issuer: the whole warp runs the (warp-uniform) control flow so that descriptors stay
     // in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit ============
+    const int mw = warp == kLoaderWarps + 4 ? 0 : warp - (kLoaderWarps + 5);   // which issuing warp: patches p = mw (mod kMmaWarps)
     const bool leader = elect_one();
     // instruction descriptor: D=f32, A=B=(bf16|tf32), K-major both, N, M=128
     const uint32_t fmt = C::OP == OP_F16 ? 0u : (C::OP == OP_BF16 ? 1u : 2u);   // kind::f16: 0 = f16, 1 = bf16
@@ -308,6 +313,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
               const uint32_t acc = (c > 0 || tap > 0) ? 1u : 0u;
 #pragma unroll
               for (int p = 0; p < C::P; ++p) {
+                if ((p % kMmaWarps) != mw) continue;
                 const int pd = p / C::NW, pw = p % C::NW;
                 const uint32_t aoff = (uint32_t)(((pd + kd) * C::HH + kh) * C::HW + pw * 8 + kw);
                 if (C::BF16) tc_mma_f16(dbase + p * C::N, adesc0 + aoff, bdesc, idesc, acc);
