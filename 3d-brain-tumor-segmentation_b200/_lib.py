@@ -76,6 +76,7 @@ SIGNATURES = {
     "b3d_conv3d_dgrad": "TTTiiiTv",
     "b3d_conv3d_wgrad": "TTTTiiTTiv",
     "b3d_conv3d_pack_weights": "TTiiiv",
+    "b3d_conv3d_pack_many": "TiLv",
     "b3d_gn_stats": "TTiv",
     "b3d_gn_apply": "TTTTTifiv",
     "b3d_gn_channel_stats": "TTiv",
@@ -131,6 +132,9 @@ lib.b3d_conv3d_wgrad_tc_supported.restype = _i
 lib.b3d_conv3d_wgrad_plan.argtypes = [_i] * 5 + [C.POINTER(_ll), C.POINTER(_ll)]
 lib.b3d_conv3d_wgrad_plan.restype = _i
 lib.b3d_set_conv_precision.argtypes = [_i, _i]
+lib.b3d_conv3d_pack_job.argtypes = [P, P, _i, _i, _i, _ll, _v, C.POINTER(_ll)]
+lib.b3d_conv3d_pack_job.restype = _i
+lib.b3d_conv3d_pack_job_bytes.restype = _i
 lib.b3d_slab_sym_bytes.argtypes = [_ll]
 lib.b3d_slab_sym_bytes.restype = _ll
 lib.b3d_get_conv_precision.restype = _i

@@ -365,3 +365,37 @@ extern "C" int b3d_conv3d_pack_weights(const DLTensor* w_, DLTensor* packed_, in
   B3D_REQUIRE((size_t)p.numel == tc_packed_weight_elems(g), B3D_ERR_SHAPE, "packed: wrong size");
   return launch_tc_pack_weights(g, (const float*)w.p, (float*)p.p, (cudaStream_t)stream);
 }
+
+// Batched form: b3d_conv3d_pack_job writes the table entry of one layer (b3d_conv3d_pack_job_bytes() bytes, host
+// memory) and returns the number of 256-thread blocks it needs in *blocks; the caller sets block0 = running sum via
+// the `block0` argument, uploads the concatenated entries and calls b3d_conv3d_pack_many once per optimiser step.
+extern "C" int b3d_conv3d_pack_job_bytes(void) { return (int)sizeof(PackJob); }
+
+extern "C" int b3d_conv3d_pack_job(const DLTensor* w_, DLTensor* packed_, int stride, int transposed, int dgrad,
+                                   long long block0, void* job_out, long long* blocks) {
+  TView w, p;
+  int k;
+  B3D_TRY(weight_view(w_, &w, &k));
+  B3D_TRY(view(packed_, DT_F32, 1, false, "packed", &p));
+  B3D_REQUIRE(job_out != nullptr && blocks != nullptr, B3D_ERR_ARG, "pack_job: null output");
+  B3D_REQUIRE((stride == 1 && !transposed) || (stride == 2 && k == 3), B3D_ERR_UNSUPPORTED,
+              "pack_job: stride 1, or k=3 stride 2 (conv / conv-transpose)");
+  ConvGeom g;
+  weight_geom(g, k, stride, transposed, dgrad, (int)w.shape[3], (int)w.shape[4]);
+  B3D_REQUIRE((size_t)p.numel == tc_packed_weight_elems(g), B3D_ERR_SHAPE, "packed: wrong size");
+  PackJob jb;
+  B3D_TRY(tc_pack_job(g, (const float*)w.p, (float*)p.p, &jb));
+  jb.block0 = block0;
+  memcpy(job_out, &jb, sizeof(jb));
+  *blocks = tc_pack_job_blocks(jb);
+  return B3D_OK;
+}
+
+extern "C" int b3d_conv3d_pack_many(const DLTensor* jobs_, int njobs, long long blocks, void* stream) {
+  TView t;
+  static_assert(sizeof(PackJob) % 8 == 0, "PackJob tables travel as int64 tensors");
+  B3D_TRY(view(jobs_, DT_I64, 1, false, "jobs", &t));
+  B3D_REQUIRE(njobs >= 0 && t.numel * 8 >= (long long)njobs * (long long)sizeof(PackJob), B3D_ERR_SHAPE,
+              "pack_many: table too small");
+  return launch_tc_pack_many((const PackJob*)t.p, njobs, blocks, (cudaStream_t)stream);
+}

@@ -42,6 +42,52 @@ size_t tc_packed_weight_elems(const ConvGeom& cg);
 int launch_pack_s2(const ConvGeom& cg, const float* w, float* wpacked, int op, cudaStream_t s);
 int launch_tc_pack_weights(const ConvGeom& cg, const float* w, float* wpacked, cudaStream_t s);
 
+// one layer's operand re-layout as a table entry of pack_many_kernel (conv_tc.cu): all layers in one launch
+struct PackJob {
+  const float* w;           // Keras-layout weights
+  void* wp;                 // packed operand
+  long long total;          // packed elements
+  long long block0;         // first block of this job in the batched grid
+  long long wtap;
+  int s2, op, up, taps;     // stride-2 family?, OP_*, UP-type (s2), taps (S1)
+  int Cin, Cout, N;         // S1: padded channel counts, N tile;  s2: real Cg, Cp, N tile
+  int sw_in, sw_out;
+  int aux;                  // S1: flip;  s2: NTdown
+  int cin_real, cout_real;  // S1 zero-padding bounds
+};
+int tc_pack_job(const ConvGeom& cg, const float* w, float* wpacked, PackJob* job);
+long long tc_pack_job_blocks(const PackJob& job);
+int launch_tc_pack_many(const PackJob* jobs_dev, int njobs, long long blocks, cudaStream_t s);
+
+#ifdef __CUDACC__
+// element i of the packed 2x2x2 stride-1 operand of a DOWN / UP geometry (layout and index algebra: conv_s2.cu)
+__device__ __forceinline__ float pack_s2_elem(const float* __restrict__ w, long long i, int T, int up, int Cg, int Cp,
+                                              int N, long long wtap, int sw_in, int sw_out, int NTdown) {
+  const int K = up ? Cg : 8 * Cg;
+  const int nch = K / (2 * T);
+  long long r = i;
+  const int j = (int)(r % T); r /= T;
+  const int n = (int)(r % N); r /= N;
+  const int pl = (int)(r % 2); r /= 2;
+  const int tap = (int)(r % 8); r /= 8;
+  const int c = (int)(r % nch); r /= nch;
+  const int ns = (int)r;
+  const int k = 2 * T * c + T * pl + j, nn = ns * N + n;
+  int p, cg, cp;
+  if (up) { cg = k; p = nn / Cp; cp = nn % Cp; }
+  else    { p = k / Cg; cg = k % Cg; cp = nn; }
+  const int kd = tap >> 2, kh = (tap >> 1) & 1, kw = tap & 1;
+  const int pd = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
+  const int td = up ? pd + 2 * (1 - kd) : 2 * kd + pd;
+  const int th = up ? ph + 2 * (1 - kh) : 2 * kh + ph;
+  const int tw = up ? pw + 2 * (1 - kw) : 2 * kw + pw;
+  (void)NTdown;
+  if (td <= 2 && th <= 2 && tw <= 2 && cp < Cp)
+    return w[(long long)((td * 3 + th) * 3 + tw) * wtap + (long long)cg * sw_in + (long long)cp * sw_out];
+  return 0.f;
+}
+#endif
+
 int tc_operand_type(const ConvGeom& g);   // OP_* the tcgen05 conv will use for this geometry / pass
 int tc_pick_n(int Cout);               // N tile of the tcgen05 conv for this output-channel count
 

@@ -33,28 +33,9 @@ __global__ void pack_s2_kernel(const float* __restrict__ w, void* __restrict__ w
   constexpr int T = OP != OP_TF32 ? 8 : 4;
   const int K = up ? Cg : 8 * Cg, NT = up ? 8 * Cp : NTdown;    // NTdown = Cp padded to the N tile (>= 16)
   const long long total = 8LL * K * NT;
-  const int nch = K / (2 * T);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    long long r = i;
-    const int j = (int)(r % T); r /= T;
-    const int n = (int)(r % N); r /= N;
-    const int pl = (int)(r % 2); r /= 2;
-    const int tap = (int)(r % 8); r /= 8;
-    const int c = (int)(r % nch); r /= nch;
-    const int ns = (int)r;
-    const int k = 2 * T * c + T * pl + j, nn = ns * N + n;
-    int p, cg, cp;
-    if (up) { cg = k; p = nn / Cp; cp = nn % Cp; }
-    else    { p = k / Cg; cg = k % Cg; cp = nn; }
-    const int kd = tap >> 2, kh = (tap >> 1) & 1, kw = tap & 1;
-    const int pd = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
-    const int td = up ? pd + 2 * (1 - kd) : 2 * kd + pd;
-    const int th = up ? ph + 2 * (1 - kh) : 2 * kh + ph;
-    const int tw = up ? pw + 2 * (1 - kw) : 2 * kw + pw;
-    float v = 0.f;
-    if (td <= 2 && th <= 2 && tw <= 2 && cp < Cp)
-      v = w[(long long)((td * 3 + th) * 3 + tw) * wtap + (long long)cg * sw_in + (long long)cp * sw_out];
+    const float v = pack_s2_elem(w, i, T, up, Cg, Cp, N, wtap, sw_in, sw_out, NTdown);
     if (OP == OP_BF16) {
       reinterpret_cast<__nv_bfloat16*>(wp)[i] = __float2bfloat16_rn(v);
     } else if (OP == OP_F16) {

@@ -521,34 +521,67 @@ __global__ void __launch_bounds__(256)
 
 // ------------------------------------------------------------------------------------------ packing
 // wp[ns][c][tap][pl][n][j] = op( w[tw(tap)*wtap + (CK*c + T*pl + j)*sw_in + (ns*N+n)*sw_out] ),  op = bf16 | tf32
+__device__ __forceinline__ float pack_s1_elem(const float* __restrict__ w, long long i, int T, int taps, int Cin, int N,
+                                              long long wtap, int sw_in, int sw_out, int flip, int cin_real,
+                                              int cout_real) {
+  const int nch = Cin / (2 * T);
+  long long r = i;
+  const int j = (int)(r % T); r /= T;
+  const int n = (int)(r % N); r /= N;
+  const int pl = (int)(r % 2); r /= 2;
+  int tap = (int)(r % taps); r /= taps;
+  const int c = (int)(r % nch); r /= nch;
+  const int ns = (int)r;
+  if (flip) tap = taps - 1 - tap;
+  const int ci = 2 * T * c + T * pl + j, co = ns * N + n;
+  return (ci < cin_real && co < cout_real)
+             ? w[(long long)tap * wtap + (long long)ci * sw_in + (long long)co * sw_out] : 0.f;
+}
+
+template <int OP>
+__device__ __forceinline__ void pack_store(void* __restrict__ wp, long long i, float v) {
+  if (OP == OP_BF16) {
+    reinterpret_cast<__nv_bfloat16*>(wp)[i] = __float2bfloat16_rn(v);
+  } else if (OP == OP_F16) {
+    reinterpret_cast<__half*>(wp)[i] = __float2half_rn(v);
+  } else {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    reinterpret_cast<float*>(wp)[i] = __uint_as_float(u);
+  }
+}
+
 template <int OP>
 __global__ void tc_pack_kernel(const float* __restrict__ w, void* __restrict__ wp, int taps, int Cin, int Cout, int N,
                                long long wtap, int sw_in, int sw_out, int flip, int cin_real, int cout_real) {
   constexpr int T = OP != OP_TF32 ? 8 : 4;
   const long long total = (long long)taps * Cin * Cout;
-  const int nch = Cin / (2 * T);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long r = i;
-    const int j = (int)(r % T); r /= T;
-    const int n = (int)(r % N); r /= N;
-    const int pl = (int)(r % 2); r /= 2;
-    int tap = (int)(r % taps); r /= taps;
-    const int c = (int)(r % nch); r /= nch;
-    const int ns = (int)r;
-    if (flip) tap = taps - 1 - tap;
-    const int ci = 2 * T * c + T * pl + j, co = ns * N + n;
-    const float v = (ci < cin_real && co < cout_real)
-                        ? w[(long long)tap * wtap + (long long)ci * sw_in + (long long)co * sw_out] : 0.f;
-    if (OP == OP_BF16) {
-      reinterpret_cast<__nv_bfloat16*>(wp)[i] = __float2bfloat16_rn(v);
-    } else if (OP == OP_F16) {
-      reinterpret_cast<__half*>(wp)[i] = __float2half_rn(v);
-    } else {
-      uint32_t u;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-      reinterpret_cast<float*>(wp)[i] = __uint_as_float(u);
-    }
+       i += (long long)gridDim.x * blockDim.x)
+    pack_store<OP>(wp, i, pack_s1_elem(w, i, T, taps, Cin, N, wtap, sw_in, sw_out, flip, cin_real, cout_real));
+}
+
+// every layer's operand re-layout in ONE launch (after the optimiser step): block -> job by binary search over the
+// jobs' first-block table, kPackPerBlock elements per block
+constexpr int kPackPerBlock = 2048;
+__global__ void __launch_bounds__(256) pack_many_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block0 <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackJob jb = jobs[lo];
+  const long long base = ((long long)blockIdx.x - jb.block0) * kPackPerBlock;
+  const int T = jb.op != OP_TF32 ? 8 : 4;
+  for (int e = threadIdx.x; e < kPackPerBlock; e += 256) {
+    const long long i = base + e;
+    if (i >= jb.total) break;
+    const float v = jb.s2 ? pack_s2_elem(jb.w, i, T, jb.up, jb.Cin, jb.Cout, jb.N, jb.wtap, jb.sw_in, jb.sw_out, jb.aux)
+                          : pack_s1_elem(jb.w, i, T, jb.taps, jb.Cin, jb.N, jb.wtap, jb.sw_in, jb.sw_out, jb.aux,
+                                         jb.cin_real, jb.cout_real);
+    if (jb.op == OP_BF16) pack_store<OP_BF16>(jb.wp, i, v);
+    else if (jb.op == OP_F16) pack_store<OP_F16>(jb.wp, i, v);
+    else pack_store<OP_TF32>(jb.wp, i, v);
   }
 }
 
@@ -620,6 +653,35 @@ bool tc_conv_supported(const ConvGeom& g) {
 size_t tc_packed_weight_elems(const ConvGeom& g) {
   if (g.mode != CONV_S1) return (size_t)64 * pad_cout(g.Cin) * pad_cout(g.Cout);   // symmetric in the channel roles
   return (size_t)g.k * g.k * g.k * ((g.Cin + 15) / 16 * 16) * pad_cout(g.Cout);   // room for either operand type
+}
+
+// the re-layout of one layer as a PackJob (block0 is filled in by the caller); the single place that knows the
+// parameters of both pack kernels
+int tc_pack_job(const ConvGeom& g, const float* w, float* wp, PackJob* jb) {
+  B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "pack_weights: shape not on the tcgen05 path");
+  memset(jb, 0, sizeof(*jb));
+  jb->w = w; jb->wp = wp; jb->op = operand_type(g);
+  jb->wtap = g.wtap; jb->sw_in = g.sw_in; jb->sw_out = g.sw_out;
+  if (g.mode != CONV_S1) {
+    const int up = g.mode == CONV_UP ? 1 : 0;
+    const int ntd = (g.Cout + 15) / 16 * 16;
+    const int K = up ? g.Cin : 8 * g.Cin, NT = up ? 8 * g.Cout : ntd;
+    jb->s2 = 1; jb->up = up; jb->Cin = g.Cin; jb->Cout = g.Cout; jb->N = tc_pick_n(NT); jb->aux = ntd;
+    jb->total = 8LL * K * NT;
+  } else {
+    jb->taps = g.k * g.k * g.k; jb->Cin = pad_cin(g); jb->Cout = pad_cout(g.Cout); jb->N = pick_n(jb->Cout);
+    jb->aux = g.flip; jb->cin_real = g.Cin; jb->cout_real = g.Cout;
+    jb->total = (long long)jb->taps * jb->Cin * jb->Cout;
+  }
+  return B3D_OK;
+}
+long long tc_pack_job_blocks(const PackJob& jb) { return (jb.total + kPackPerBlock - 1) / kPackPerBlock; }
+
+int launch_tc_pack_many(const PackJob* jobs_dev, int njobs, long long blocks, cudaStream_t s) {
+  if (njobs <= 0 || blocks <= 0) return B3D_OK;
+  pack_many_kernel<<<(unsigned)blocks, 256, 0, s>>>(jobs_dev, njobs);
+  B3D_LAUNCH_CHECK("pack_many");
+  return B3D_OK;
 }
 
 int launch_tc_pack_weights(const ConvGeom& g, const float* w, float* wp, cudaStream_t s) {

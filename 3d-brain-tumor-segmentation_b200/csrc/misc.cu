@@ -213,29 +213,40 @@ __global__ void __launch_bounds__(256)
 // (0,1,2) only); reduce_w = 1: its channels_first form, sums over all of batch and space per class
 __global__ void dice_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, int W, int C,
                                      int reduce_w) {
-  if (threadIdx.x == 0) {
-    double macro = 0.0, si = 0.0, sp = 0.0, st = 0.0;
-    if (reduce_w) {
-      for (int c = 0; c < C; ++c) {
-        double I = 0.0, P = 0.0, T = 0.0;
-        for (int w = 0; w < W; ++w) {
-          const int i = w * C + c;
-          I += acc[3 * i]; P += acc[3 * i + 1]; T += acc[3 * i + 2];
-        }
-        macro += (2.0 * I + 1.0) / (P + T + 1.0);
-        si += I; sp += P; st += T;
+  // one warp; lanes stride over the [W, C] table, fp64 partial sums combined by shuffles
+  const int lane = threadIdx.x;
+  double macro = 0.0, si = 0.0, sp = 0.0, st = 0.0;
+  if (reduce_w) {
+    for (int c = 0; c < C; ++c) {
+      double I = 0.0, P = 0.0, T = 0.0;
+      for (int w = lane; w < W; w += 32) {
+        const int i = w * C + c;
+        I += acc[3 * i]; P += acc[3 * i + 1]; T += acc[3 * i + 2];
       }
-      out[0] = (float)(macro / C);
-    } else {
-      for (int i = 0; i < W * C; ++i) {
-        const double I = acc[3 * i], P = acc[3 * i + 1], T = acc[3 * i + 2];
-        macro += (2.0 * I + 1.0) / (P + T + 1.0);
-        si += I; sp += P; st += T;
+      for (int o = 16; o; o >>= 1) {
+        I += __shfl_xor_sync(0xffffffffu, I, o);
+        P += __shfl_xor_sync(0xffffffffu, P, o);
+        T += __shfl_xor_sync(0xffffffffu, T, o);
       }
-      out[0] = (float)(macro / (W * C));
+      macro += (2.0 * I + 1.0) / (P + T + 1.0);
+      si += I; sp += P; st += T;
     }
-    out[1] = (float)(si / (sp + st));
+    if (lane == 0) out[0] = (float)(macro / C);
+  } else {
+    for (int i = lane; i < W * C; i += 32) {
+      const double I = acc[3 * i], P = acc[3 * i + 1], T = acc[3 * i + 2];
+      macro += (2.0 * I + 1.0) / (P + T + 1.0);
+      si += I; sp += P; st += T;
+    }
+    for (int o = 16; o; o >>= 1) {
+      macro += __shfl_xor_sync(0xffffffffu, macro, o);
+      si += __shfl_xor_sync(0xffffffffu, si, o);
+      sp += __shfl_xor_sync(0xffffffffu, sp, o);
+      st += __shfl_xor_sync(0xffffffffu, st, o);
+    }
+    if (lane == 0) out[0] = (float)(macro / (W * C));
   }
+  if (lane == 0) out[1] = (float)(si / (sp + st));
 }
 
 // ================================================================ dense (Flatten->Dense, Dense relu)
@@ -373,6 +384,7 @@ __global__ void __launch_bounds__(256)
     l2_losses_kernel(const float* __restrict__ flat, const long long* __restrict__ off, float* __restrict__ out,
                      float scale) {
   const long long a = off[blockIdx.y], b = off[blockIdx.y + 1];
+  if (a + (long long)blockIdx.x * 256 >= b) return;        // short tensor: the first slices cover it
   float s = 0.f;
   for (long long i = a + (long long)blockIdx.x * 256 + threadIdx.x; i < b; i += (long long)gridDim.x * 256)
     s += flat[i] * flat[i];
@@ -730,7 +742,7 @@ extern "C" int b3d_l2_losses(const DLTensor* flat_, const DLTensor* offsets_, DL
   B3D_REQUIRE(off.numel == out.numel + 1, B3D_ERR_SHAPE, "l2_losses: offsets must have n+1 entries");
   if (out.numel == 0) return B3D_OK;
   B3D_TRY(cuda_ok(cudaMemsetAsync(out.p, 0, sizeof(float) * out.numel, (cudaStream_t)stream), "memset l2"));
-  l2_losses_kernel<<<dim3(16, (unsigned)out.numel), 256, 0, (cudaStream_t)stream>>>(
+  l2_losses_kernel<<<dim3(128, (unsigned)out.numel), 256, 0, (cudaStream_t)stream>>>(
       (const float*)f.p, (const long long*)off.p, (float*)out.p, scale);
   B3D_LAUNCH_CHECK("l2_losses");
   return B3D_OK;
@@ -806,7 +818,7 @@ extern "C" int b3d_l2_grad(const DLTensor* flat_, DLTensor* grad_, const DLTenso
   B3D_TRY(flat_f32(gout_, "gout", &go));
   B3D_REQUIRE(off.numel == go.numel + 1 && g.numel == f.numel, B3D_ERR_SHAPE, "l2_grad: sizes");
   if (go.numel == 0) return B3D_OK;
-  l2_grad_kernel<<<dim3(16, (unsigned)go.numel), 256, 0, (cudaStream_t)stream>>>(
+  l2_grad_kernel<<<dim3(128, (unsigned)go.numel), 256, 0, (cudaStream_t)stream>>>(
       (const float*)f.p, (float*)g.p, (const long long*)off.p, (const float*)go.p, coef);
   B3D_LAUNCH_CHECK("l2_grad");
   return B3D_OK;

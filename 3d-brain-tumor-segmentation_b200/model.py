@@ -78,6 +78,10 @@ class FlatParams:
         # segment table of the regularised tensors (padding belongs to the preceding tensor; it stays 0)
         self.offsets = torch.tensor(seg, dtype=torch.int64, device=device)
         self.total = total
+        # persistent packed conv operands (ops.pack_weights / ops.repack_all) and their staleness epoch
+        self.packs = {}
+        self.pack_table = None
+        self.epoch = 0
 
     def zero_grad(self):
         self.grad.zero_()
@@ -92,9 +96,8 @@ class FlatParams:
     def add_l2_grad(self):
         """grad += 2*l*w over the regularised tensors (what autograd does through model.losses, train.py:146)."""
         if self.n_reg:
-            if getattr(self, "_ones_reg", None) is None:
-                self._ones_reg = torch.ones(self.n_reg, device=self.theta.device, dtype=torch.float32)
-            ops._call("b3d_l2_grad", self.theta, self.grad, self.offsets, self._ones_reg, 2.0 * float(self.l2))
+            # the regularised tensors are the head of the flat buffer and their padding is zero: one axpy over it
+            ops._call("b3d_axpy", self.theta, self.grad, int(self.reg_end), 2.0 * float(self.l2), None)
 
     def attach_grads(self):
         for v in self.order:
@@ -271,3 +274,5 @@ class Model(Layer):
                 if tuple(src.shape) != tuple(t.shape):
                     raise ValueError(f"{k}: shape {tuple(src.shape)} != {tuple(t.shape)}")
                 t.copy_(src.to(device=t.device, dtype=t.dtype))
+        if self._flat is not None:
+            ops.repack_all(self._flat)       # captured inference graphs read the persistent packed operands

@@ -50,10 +50,81 @@ def tc_supported(w, stride, transposed, dgrad) -> bool:
 
 
 def pack_weights(w: torch.Tensor, dgrad: bool, stride: int = 1, transposed: bool = False) -> torch.Tensor:
-    n = lib.b3d_conv3d_packed_elems(w.shape[0], stride, w.shape[3], w.shape[4])
-    out = _new((n,), w)
-    _call("b3d_conv3d_pack_weights", w, out, stride, int(transposed), int(dgrad))
-    return out
+    """Operand layout of Keras kernel `w` for one pass of the tcgen05 conv.  Weights of a Model (views of its flat
+    buffer) keep ONE persistent packed buffer per pass: it is refreshed for all layers together by
+    `repack_all(flat)` right after the optimiser step (one launch instead of ~120 per training step, none per
+    inference forward), or singly here when the stamp shows the weights were changed some other way."""
+    flat = getattr(w, "_b3d_flat", None)
+    if flat is None:
+        out = _new((lib.b3d_conv3d_packed_elems(w.shape[0], stride, w.shape[3], w.shape[4]),), w)
+        _call("b3d_conv3d_pack_weights", w, out, stride, int(transposed), int(dgrad))
+        return out
+    e = flat.packs.get((id(w), bool(dgrad), int(stride), bool(transposed)))
+    if e is None:
+        e = _register_pack(flat, w, dgrad, stride, transposed)
+        if not dgrad and tc_supported(w, stride, transposed, True):
+            # the data-gradient operand is registered with the forward one, so that the job table is complete (and
+            # can be uploaded) before anything is captured into a CUDA graph
+            _register_pack(flat, w, True, stride, transposed)
+    stamp = _pack_stamp(flat, w)
+    if e["stamp"] != stamp:
+        _call("b3d_conv3d_pack_weights", w, e["buf"], *e["cfg"])
+        e["stamp"] = stamp
+    return e["buf"]
+
+
+def _register_pack(flat, w, dgrad, stride, transposed):
+    key = (id(w), bool(dgrad), int(stride), bool(transposed))
+    if key not in flat.packs:
+        buf = _new((lib.b3d_conv3d_packed_elems(w.shape[0], stride, w.shape[3], w.shape[4]),), w)
+        flat.packs[key] = {"w": w, "buf": buf, "cfg": (int(stride), int(transposed), int(dgrad)), "stamp": None}
+        flat.pack_table = None
+    return flat.packs[key]
+
+
+_PREC_EPOCH = {"n": 0}       # bumped by set_conv_precision: the packed operand type depends on it
+
+
+def _pack_stamp(flat, w):
+    return (w._version, flat.theta._version, flat.epoch, _PREC_EPOCH["n"])
+
+
+def ensure_pack_table(flat):
+    """Device table of pack jobs for all registered operands of `flat` (rebuilt when a layer registers or the
+    operand precision changes).  Uploading it is a host->device copy: it has to exist before graph capture."""
+    if flat.pack_table is not None and flat.pack_table[3] == _PREC_EPOCH["n"]:
+        return flat.pack_table
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("b3d: a conv layer registered its packed operand during CUDA-graph capture; run the "
+                           "model once (or call ops.ensure_pack_table(model.flat)) before capturing")
+    import ctypes as C
+    from ._lib import dl
+    entries = list(flat.packs.values())
+    nb = lib.b3d_conv3d_pack_job_bytes()
+    host = (C.c_char * (nb * len(entries)))()
+    blocks, got = 0, _ll()
+    for i, e in enumerate(entries):
+        pw, hw = dl(e["w"])
+        pb, hb = dl(e["buf"])
+        rc = lib.b3d_conv3d_pack_job(pw, pb, *e["cfg"], blocks, C.byref(host, i * nb), _byref(got))
+        if rc != 0:
+            raise RuntimeError("b3d_conv3d_pack_job failed: " + lib.b3d_last_error().decode())
+        blocks += got.value
+    tab = torch.frombuffer(bytearray(bytes(host)), dtype=torch.int64).to(flat.theta.device)
+    flat.pack_table = (tab, len(entries), blocks, _PREC_EPOCH["n"], entries)
+    return flat.pack_table
+
+
+def repack_all(flat):
+    """The weights of `flat` have just been changed by a kernel (Adam): refresh every registered packed operand with
+    ONE launch (csrc/conv_tc.cu pack_many_kernel).  Captured at the end of the graphed training step."""
+    flat.epoch += 1
+    if not flat.packs:
+        return
+    tab, n, blocks, _, entries = ensure_pack_table(flat)
+    _call("b3d_conv3d_pack_many", tab, n, blocks)
+    for e in entries:
+        e["stamp"] = _pack_stamp(flat, e["w"])
 
 
 # ---- direct parameter gradients ------------------------------------------------------------------------------
@@ -111,6 +182,7 @@ def set_conv_precision(fwd: str = "fp16", bwd: str = "bf16"):
         if v not in _PREC:
             raise ValueError(v)
     lib.b3d_set_conv_precision(_PREC[fwd], _PREC[bwd])
+    _PREC_EPOCH["n"] += 1
 
 
 def get_conv_precision():
@@ -144,6 +216,8 @@ class Conv3dFn(Function):
         wp = None
         if USE_TC["on"] and (not act or stride == 1) and tc_supported(w, stride, transposed, False):
             wp = pack_weights(w, False, stride, transposed)
+        elif USE_TC["on"] and getattr(w, "_b3d_flat", None) is not None and tc_supported(w, stride, transposed, True):
+            _register_pack(w._b3d_flat, w, True, stride, transposed)     # forward on CUDA cores, data gradient on TC
         _call("b3d_conv3d_fwd", x, w, bias, y, stride, int(transposed), int(act), stats, gn_groups or 1, gap, 0, wp)
         ctx.save_for_backward(x, w, y if act else None)
         ctx.cfg = (stride, transposed, act, bias is not None)

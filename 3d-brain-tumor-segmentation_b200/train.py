@@ -179,6 +179,8 @@ class GraphedTrainStep:
                 train_step(*self._args, self.x, self.y, dp=dp)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        if model.flat is not None and model.flat.packs:
+            ops.ensure_pack_table(model.flat)
         n0 = ops.LAUNCHES["n"]
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

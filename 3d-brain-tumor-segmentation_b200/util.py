@@ -93,6 +93,7 @@ class ScheduledOptim(object):
         ops._call("b3d_adam_step", flat.theta, m, v, flat.grad, self._state, self.beta_1, self.beta_2,
                   self.epsilon, float(self.grad_scale), 2.0 * float(flat.l2) if l2_in_step else 0.0,
                   int(flat.reg_end) if l2_in_step else 0, 1)
+        ops.repack_all(flat)          # packed conv operands follow the weights (one launch)
 
     def apply_gradients(self, grads_and_vars, flat=None):
         gv = list(grads_and_vars)
@@ -106,6 +107,9 @@ class ScheduledOptim(object):
             ops._call("b3d_adam_step", th, m.view(-1), v.view(-1), g.contiguous().view(-1), self._state,
                       self.beta_1, self.beta_2, self.epsilon, float(self.grad_scale), 0.0, 0,
                       int(i == len(gv) - 1))
+            vf = getattr(var, "_b3d_flat", None)
+            if vf is not None:
+                vf.epoch += 1         # packed conv operands of this model are stale (re-made at next use)
 
 
 def _is_flat_group(gv):

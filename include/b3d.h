@@ -88,6 +88,15 @@ int b3d_get_conv_precision(void);
 long long b3d_conv3d_packed_elems(int k, int stride, int a, int b);
 int b3d_conv3d_pack_weights(const DLTensor* w, DLTensor* packed, int stride, int transposed, int dgrad,
                             void* stream);
+/* Batched re-layout, one launch for every layer of a model (run after the optimiser step; the reference has no
+ * counterpart — Keras hands cuDNN the HWIO kernel every call).  b3d_conv3d_pack_job writes the table entry of one
+ * layer/pass into `job_out` (host memory, b3d_conv3d_pack_job_bytes() bytes) with `block0` = the sum of *blocks of
+ * the entries before it; the concatenated entries, uploaded as an int64 device tensor, drive b3d_conv3d_pack_many
+ * (`blocks` = the total).  The entries hold the device pointers of w / packed: both must stay where they are. */
+int b3d_conv3d_pack_job_bytes(void);
+int b3d_conv3d_pack_job(const DLTensor* w, DLTensor* packed, int stride, int transposed, int dgrad,
+                        long long block0, void* job_out, long long* blocks);
+int b3d_conv3d_pack_many(const DLTensor* jobs /*int64 table*/, int njobs, long long blocks, void* stream);
 
 /* ---- GroupNormalization.call, channels_last semantics (group_norm.py:83-124) -----
  * "group" g = g-th contiguous 1/G chunk of each sample's flat buffer; eps inside sqrt; population

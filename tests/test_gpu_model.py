@@ -174,6 +174,51 @@ def test_graphed_step_equals_eager(b3d, dev):
     assert rel(res[1][1], res[0][1]) < 1e-2
 
 
+def test_batched_repack_tracks_the_weights(b3d, dev):
+    """The persistent packed conv operands (ops.pack_weights) are refreshed by ONE batched launch after the Adam
+    step (ops.repack_all): after training steps, a precision switch and a weight load, every one of them must equal
+    a fresh per-layer pack of the current weights — for the forward and the data-gradient operand of every layer."""
+    crop = (32, 32, 32)
+    p = R.init_params(R.param_shapes(crop=crop))
+    x, y, _, _ = R.synth_batch((1,) + crop)
+    model, f = build(b3d, dev, crop, p, dropout=0.0)
+    opt = b3d.ScheduledOptim(learning_rate=1e-3)
+    opt(epoch=0)
+    args = (model, opt, b3d.DiceVAELoss(), b3d.DiceCoefficient())
+    flat, ops = model.flat, b3d.ops
+
+    def check(expect_fresh):
+        n = 0
+        for (wid, dgrad, stride, transposed), e in flat.packs.items():
+            w = e["w"]
+            ref = e["buf"].clone()       # buffers have room for either operand type: the unused tail is arbitrary
+            ops._call("b3d_conv3d_pack_weights", w, ref, stride, int(transposed), int(dgrad))
+            used = ops.pack_weights(w, dgrad, stride, transposed)        # what the next conv call would read
+            assert used.data_ptr() == e["buf"].data_ptr()
+            assert torch.equal(used.view(torch.int32), ref.view(torch.int32)), (tuple(w.shape), dgrad, stride)
+            n += 1
+        assert n >= 60, n
+    try:
+        for _ in range(2):
+            b3d.train_step(*args, f(x), f(y))
+        n0 = ops.LAUNCHES["n"]
+        check(True)                                      # stamps are fresh: pack_weights launches nothing
+        assert ops.LAUNCHES["n"] - n0 == len(flat.packs)        # only this test's own reference packs
+        ops.set_conv_precision("tf32", "tf32")           # operand type changes -> table and buffers are re-made
+        check(False)
+        b3d.train_step(*args, f(x), f(y))
+        check(True)
+        ops.set_conv_precision("fp16", "bf16")
+        model.load_named_weights(p)                      # load_weights path repacks too
+        check(True)
+        theta_before = flat.theta.clone()
+        flat.theta.mul_(0.5)                             # a torch-side in-place change is seen through the stamp
+        check(False)
+        flat.theta.copy_(theta_before)
+    finally:
+        reset_mode(b3d)
+
+
 def test_inference_tta_matches_oracle(b3d, dev):
     """test.py:105-178: pad_to_spatial_res + 8-flip TTA + brain mask on an odd-sized volume (levels 40x48x40 ->
     5x6x5: partial tensor-core tiles and GroupNorm chunks that are not voxel-aligned), default precision."""
