@@ -341,6 +341,27 @@ def test_tc_conv_vs_oracle_and_generic(b3d, dev, case):
     assert rel(res["fp16"][0], res["fp32"][0]) < TOL_TF32
 
 
+@pytest.mark.parametrize("k,cin,cout", [(3, 16, 16), (1, 32, 16), (3, 64, 32)])
+def test_dgrad_accumulate_epilogue(b3d, dev, k, cin, cout):
+    """b3d_conv3d_dgrad(accumulate=1) adds the data gradient to what `dx` already holds (include/b3d.h), on the
+    tcgen05 path and on the CUDA-core path."""
+    ops = b3d.ops
+    dy = dev32(t64(1, 16, 24, 32, cout, seed=71), dev)
+    w = dev32(t64(k, k, k, cin, cout, seed=72, scale=0.1), dev)
+    base = dev32(t64(1, 16, 24, 32, cin, seed=73), dev)
+    for tc in (True, False):
+        wp = ops.pack_weights(w, True, 1, False) if tc else None
+        if tc:
+            assert ops.tc_supported(w, 1, False, True)
+        plain = torch.empty_like(base)
+        ops._call("b3d_conv3d_dgrad", dy, w, plain, 1, 0, 0, wp)
+        acc = base.clone()
+        ops._call("b3d_conv3d_dgrad", dy, w, acc, 1, 0, 1, wp)
+        torch.cuda.synchronize()
+        assert float(plain.abs().max()) > 0
+        assert float((acc - (base + plain)).abs().max()) <= 1e-6 * float(plain.abs().max()) + 1e-6, (tc,)
+
+
 @pytest.mark.parametrize("shape", [(2, 4, 6, 8, 16), (1, 8, 8, 8, 4), (1, 2, 2, 2, 64)])
 def test_max_downsample_and_linear_upsample_layers(b3d, dev, shape):
     """MaxDownsample (downsample.py:51-70) and LinearUpsample (upsample.py:49-79) against the oracle, forward and
