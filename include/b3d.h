@@ -8,8 +8,12 @@
  * Conventions
  *  - every tensor argument is a BORROWED `const DLTensor*` (include/b3d_dlpack.h); a
  *    `DLManagedTensor*` from `to_dlpack` may be passed as-is.  The callee never frees, never
- *    retains past return (+ stream order), and never allocates device memory: outputs and
- *    workspaces are caller-allocated.  NULL is allowed only where marked "nullable".
+ *    retains past return (+ stream order); outputs and workspaces are caller-allocated.  NULL is
+ *    allowed only where marked "nullable".  The ONE allocation the library makes itself is a 64 MB
+ *    split-K workspace per device, created on the first convolution call that wants it (never
+ *    while the stream is capturing) and shared by all streams of that device: convolution calls
+ *    on one device must therefore be ordered with respect to each other (one compute stream per
+ *    device — the execution model of DESIGN.md section 5).
  *  - tensors must live on a CUDA device (kDLCUDA) — there is NO CPU path — and be fp32 unless
  *    stated otherwise; activations are channels_last [B, D, H, W, C], compact row-major
  *    (conv inputs/outputs may be channel slices of a wider NDHWC buffer); weights use the Keras
@@ -17,7 +21,8 @@
  *  - `void* stream` is a cudaStream_t; all work is enqueued on it, nothing synchronises, so
  *    every call is CUDA-graph capturable.
  *  - return 0 on success, a negative B3D_ERR_* code otherwise; `b3d_last_error()` returns the
- *    thread-local message.  No exceptions cross the ABI; no global mutable state.
+ *    thread-local message.  No exceptions cross the ABI.  Process-wide state is limited to the
+ *    two settings below (b3d_set_conv_precision, b3d_set_wgrad_ts) and the split-K workspace.
  */
 #ifndef B3D_H_
 #define B3D_H_
@@ -81,9 +86,10 @@ int b3d_conv3d_wgrad_plan(int k, int stride, int transposed, int cin, int cout, 
  * kernel is (k,k,k,a,b): stride-1 k in {1,3}, and the k3 stride-2 family (Conv3D s2, Conv3DTranspose), which is
  * executed as a 2x2x2 stride-1 conv over the coarse grid with space-to-depth addressing (csrc/conv_s2.cu). */
 int b3d_conv3d_tc_supported(int k, int stride, int transposed, int dgrad, int a, int b);
-/* operand type of the tcgen05 conv MMAs (1 = bf16, 0 = tf32) for the forward pass and for the data gradient;
- * defaults: forward tf32, backward bf16; fp32 accumulation either way.  get: bit0 = fwd, bit1 = bwd. */
-int b3d_set_conv_precision(int fwd_bf16, int bwd_bf16);
+/* operand type of the tcgen05 conv MMAs (0 = tf32, 1 = bf16, 2 = fp16) for the forward pass and for the data
+ * gradient; defaults: forward fp16 (TF32's 11-bit significand), backward bf16; fp32 accumulation either way.
+ * Packed weights depend on it: re-pack after a change.  get: fwd | bwd << 4. */
+int b3d_set_conv_precision(int fwd_op, int bwd_op);
 int b3d_get_conv_precision(void);
 long long b3d_conv3d_packed_elems(int k, int stride, int a, int b);
 int b3d_conv3d_pack_weights(const DLTensor* w, DLTensor* packed, int stride, int transposed, int dgrad,
