@@ -132,6 +132,8 @@ lib.b3d_conv3d_wgrad_tc_supported.restype = _i
 lib.b3d_conv3d_wgrad_plan.argtypes = [_i] * 5 + [C.POINTER(_ll), C.POINTER(_ll)]
 lib.b3d_conv3d_wgrad_plan.restype = _i
 lib.b3d_set_conv_precision.argtypes = [_i, _i]
+lib.b3d_set_conv_kdfold.argtypes = [_i]
+lib.b3d_set_conv_kdfold.restype = _i
 lib.b3d_conv3d_pack_job.argtypes = [P, P, _i, _i, _i, _ll, _v, C.POINTER(_ll)]
 lib.b3d_conv3d_pack_job.restype = _i
 lib.b3d_conv3d_pack_job_bytes.restype = _i

@@ -20,6 +20,16 @@
 //     GroupNorm chunk statistics or global-average-pool sums), warps 4-11 = loaders, warp 12 = single
 //     thread MMA issuer, warp 13 = weight producer (+TMEM alloc); 2 TMEM accumulator stages overlap
 //     epilogue(i) with MMA(i+1).
+//
+// "kd-folded" variant (TcCfg::FOLD, 3x3x3, Cout tile 16 | 32): the cost of a small-N SS-mode tcgen05.mma is the fetch
+// of its 4 KB A tile from shared memory (~40-56 cycles whatever N is, profiles/r01_umma_rate.txt), so the narrow
+// layers are bound by the NUMBER of MMAs.  Folding the depth taps into N cuts that number 2-2.4x: for every INPUT
+// depth slice z of the halo and every (kh, kw), ONE MMA multiplies the slice's patch with [W(kd=2) | W(kd=1) | W(kd=0)]
+// (N' = 3N columns), and its D block lands on the accumulators of the three OUTPUT slices z-2, z-1, z (relative to the
+// halo), which are adjacent column blocks in TMEM:  9 (TD+2) MMAs per chunk and patch column instead of 27 TD.
+// Accumulator blocks are first touched by the kd = 0 column block of the first (chunk, kh, kw) step — issued as its
+// own N-wide MMA with accumulate = 0 next to a 2N-wide one for the other two blocks; two blocks at either end of the
+// TMEM column range receive the out-of-tile contributions and are never read.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -30,9 +40,11 @@
 namespace b3d {
 
 // ------------------------------------------------------------------------------------------ config
-template <int N_, int TD_, int NW_, int KS_, int HB_, int OP_>
+template <int N_, int TD_, int NW_, int KS_, int HB_, int OP_, int FOLD_ = 0>
 struct TcCfg {
   static constexpr int N = N_, TD = TD_, NW = NW_, KS = KS_;
+  static constexpr bool FOLD = FOLD_ != 0;            // depth taps folded into N (see the header comment)
+  static constexpr int NB = FOLD ? 3 * N : N;         // rows of one B tile = N of one (unsplit) MMA
   static constexpr int HB = HB_;                      // halo before the tile: tap k reads offset k - HB
   static constexpr int OP = OP_;                      // operand type: OP_TF32 | OP_BF16 | OP_F16
   static constexpr bool BF16 = OP_ != OP_TF32;        // 16-bit operands (bf16 or fp16): 8 channels per cell
@@ -45,14 +57,19 @@ struct TcCfg {
   static constexpr int PLANE_BYTES = ((NVC * 16 + 127) / 128) * 128;
   static constexpr int HALO_BYTES = 2 * PLANE_BYTES;
   static constexpr int TAP_BYTES = 2 * N * 16;        // B tile of one tap: 2 planes x N rows x 16 B
-  static constexpr int TPS = KS * KS;                 // taps per weight stage (one kd slab; 1 for 1x1x1)
+  static constexpr int TPS = KS * KS;                 // taps per weight stage (one kd slab; 1 for 1x1x1;
+                                                      // FOLD: one kh row = 3 (kh, kw) tiles of 3N rows)
   static constexpr int WST_BYTES = TPS * TAP_BYTES;
   static constexpr int WS = (KS == 1) ? 8 : 3;
   static constexpr int ACC_COLS = 256;                // per accumulator stage (P*N <= 256)
   static constexpr int BAR_BYTES = 512;
   static constexpr int HS = (3 * HALO_BYTES + WS * WST_BYTES + BAR_BYTES <= 220 * 1024) ? 3 : 2;
   static constexpr int SMEM = HS * HALO_BYTES + WS * WST_BYTES + BAR_BYTES;
-  static_assert(P * N <= ACC_COLS, "accumulators exceed a TMEM stage");
+  static constexpr int ACC_BLOCKS = FOLD ? NW * (TD + 4) : P;     // N-column accumulator blocks per stage
+  static_assert(ACC_BLOCKS * N <= ACC_COLS, "accumulators exceed a TMEM stage");
+  static_assert(!FOLD || (KS == 3 && HB == 1 && BF16 && (N == 16 || N == 32)), "kd-folded variant: 3x3x3, 16-bit, N 16|32");
+  // TMEM column block of output patch (pd, pw) within a stage
+  static constexpr __host__ __device__ int acc_block(int pd, int pw) { return FOLD ? pw * (TD + 4) + pd + 2 : pd * NW + pw; }
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -303,8 +320,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
         for (int st = 0; st < C::TAPS / C::TPS; ++st) {
           mbar_wait(smem_u32(&w_full[ws]), wph);
           tc_fence_after();
-          const uint64_t bdesc0 = make_desc(wst_addr + ws * C::WST_BYTES, C::N * 16, 128);
+          const uint64_t bdesc0 = make_desc(wst_addr + ws * C::WST_BYTES, C::NB * 16, 128);
           if (leader) {
+            if constexpr (C::FOLD) {
+              // stage st = kernel row kh; per (kh, kw) one B tile of 3N rows [kd=2 | kd=1 | kd=0]
+              const int kh = st;
+              constexpr uint32_t idesc_hi = (1u << 4) | ((128u >> 4) << 24);
+              const uint32_t idf = idesc_hi | (fmt << 7) | (fmt << 10);
+              const uint32_t id3 = idf | ((uint32_t)(3 * C::N >> 3) << 17), id2 = idf | ((uint32_t)(2 * C::N >> 3) << 17);
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint64_t bdesc = bdesc0 + (uint64_t)(kw * (3 * C::TAP_BYTES >> 4));
+                const bool first = c == 0 && st == 0 && kw == 0;
+#pragma unroll
+                for (int zi = 0; zi < C::HD; ++zi) {
+#pragma unroll
+                  for (int pw = 0; pw < C::NW; ++pw) {
+                    const uint32_t aoff = (uint32_t)((zi * C::HH + kh) * C::HW + pw * 8 + kw);
+                    const uint32_t dcol = dbase + (uint32_t)((pw * (C::TD + 4) + zi) * C::N);   // blocks of pd = zi-2..zi
+                    if (!first) {
+                      tc_mma_f16(dcol, adesc0 + aoff, bdesc, id3, 1u);
+                    } else {
+                      tc_mma_f16(dcol, adesc0 + aoff, bdesc, id2, 1u);                              // kd = 2, 1
+                      tc_mma_f16(dcol + 2 * C::N, adesc0 + aoff, bdesc + (uint64_t)(2 * C::N), idesc, 0u);   // kd = 0
+                    }
+                  }
+                }
+              }
+            } else {
 #pragma unroll
             for (int tq = 0; tq < C::TPS; ++tq) {
               const int tap = st * C::TPS + tq;
@@ -319,6 +362,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
                 if (C::BF16) tc_mma_f16(dbase + p * C::N, adesc0 + aoff, bdesc, idesc, acc);
                 else tc_mma_tf32(dbase + p * C::N, adesc0 + aoff, bdesc, idesc, acc);
               }
+            }
             }
             tc_commit(smem_u32(&w_empty[ws]));
           }
@@ -407,7 +451,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
             if (valid) cur_chunk = chunk;
           }
           float v[16];
-          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + p * C::N + j * 16, v);
+          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + (C::FOLD ? C::acc_block(pd, pw) : p) * C::N + j * 16, v);
           if (valid && prm.ksplit > 1) {
             // partial sums of this K range -> workspace slice blockIdx.z
             float4* dst = reinterpret_cast<float4*>(yp + (long long)blockIdx.z * prm.ws_slice);
@@ -538,6 +582,26 @@ __device__ __forceinline__ float pack_s1_elem(const float* __restrict__ w, long 
              ? w[(long long)tap * wtap + (long long)ci * sw_in + (long long)co * sw_out] : 0.f;
 }
 
+// kd-folded layout (TcCfg::FOLD): wp[ns][c][kh*3+kw][pl][(2-kd)*N + n][j] — per (kh, kw) one B tile of 3N rows
+__device__ __forceinline__ float pack_s1_fold_elem(const float* __restrict__ w, long long i, int T, int Cin, int N,
+                                                   long long wtap, int sw_in, int sw_out, int flip, int cin_real,
+                                                   int cout_real) {
+  const int nch = Cin / (2 * T);
+  long long r = i;
+  const int j = (int)(r % T); r /= T;
+  const int nn = (int)(r % (3 * N)); r /= 3 * N;
+  const int pl = (int)(r % 2); r /= 2;
+  const int khw = (int)(r % 9); r /= 9;
+  const int c = (int)(r % nch); r /= nch;
+  const int ns = (int)r;
+  const int kd = 2 - nn / N, n = nn % N;
+  int tap = kd * 9 + khw;
+  if (flip) tap = 26 - tap;
+  const int ci = 2 * T * c + T * pl + j, co = ns * N + n;
+  return (ci < cin_real && co < cout_real)
+             ? w[(long long)tap * wtap + (long long)ci * sw_in + (long long)co * sw_out] : 0.f;
+}
+
 template <int OP>
 __device__ __forceinline__ void pack_store(void* __restrict__ wp, long long i, float v) {
   if (OP == OP_BF16) {
@@ -553,12 +617,14 @@ __device__ __forceinline__ void pack_store(void* __restrict__ wp, long long i, f
 
 template <int OP>
 __global__ void tc_pack_kernel(const float* __restrict__ w, void* __restrict__ wp, int taps, int Cin, int Cout, int N,
-                               long long wtap, int sw_in, int sw_out, int flip, int cin_real, int cout_real) {
+                               long long wtap, int sw_in, int sw_out, int flip, int cin_real, int cout_real,
+                               int fold) {
   constexpr int T = OP != OP_TF32 ? 8 : 4;
   const long long total = (long long)taps * Cin * Cout;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x)
-    pack_store<OP>(wp, i, pack_s1_elem(w, i, T, taps, Cin, N, wtap, sw_in, sw_out, flip, cin_real, cout_real));
+    pack_store<OP>(wp, i, fold ? pack_s1_fold_elem(w, i, T, Cin, N, wtap, sw_in, sw_out, flip, cin_real, cout_real)
+                               : pack_s1_elem(w, i, T, taps, Cin, N, wtap, sw_in, sw_out, flip, cin_real, cout_real));
 }
 
 // every layer's operand re-layout in ONE launch (after the optimiser step): block -> job by binary search over the
@@ -576,9 +642,12 @@ __global__ void __launch_bounds__(256) pack_many_kernel(const PackJob* __restric
   for (int e = threadIdx.x; e < kPackPerBlock; e += 256) {
     const long long i = base + e;
     if (i >= jb.total) break;
-    const float v = jb.s2 ? pack_s2_elem(jb.w, i, T, jb.up, jb.Cin, jb.Cout, jb.N, jb.wtap, jb.sw_in, jb.sw_out, jb.aux)
-                          : pack_s1_elem(jb.w, i, T, jb.taps, jb.Cin, jb.N, jb.wtap, jb.sw_in, jb.sw_out, jb.aux,
-                                         jb.cin_real, jb.cout_real);
+    const float v =
+        jb.s2 == 1 ? pack_s2_elem(jb.w, i, T, jb.up, jb.Cin, jb.Cout, jb.N, jb.wtap, jb.sw_in, jb.sw_out, jb.aux)
+        : jb.s2 == 2 ? pack_s1_fold_elem(jb.w, i, T, jb.Cin, jb.N, jb.wtap, jb.sw_in, jb.sw_out, jb.aux, jb.cin_real,
+                                         jb.cout_real)
+                     : pack_s1_elem(jb.w, i, T, jb.taps, jb.Cin, jb.N, jb.wtap, jb.sw_in, jb.sw_out, jb.aux,
+                                    jb.cin_real, jb.cout_real);
     if (jb.op == OP_BF16) pack_store<OP_BF16>(jb.wp, i, v);
     else if (jb.op == OP_F16) pack_store<OP_F16>(jb.wp, i, v);
     else pack_store<OP_TF32>(jb.wp, i, v);
@@ -619,6 +688,15 @@ static int pad_cin(const ConvGeom& g) {
   return (g.Cin + ck - 1) / ck * ck;
 }
 static int pad_cout(int c) { return (c + 15) / 16 * 16; }
+
+// kd-folded variant of the 3x3x3 kernel (TcCfg::FOLD): narrow output tiles with 16-bit operands.  Off by default
+// until it has been validated and timed on hardware (b3d_set_conv_kdfold); the packed weight layout depends on it.
+static int g_kdfold = 0;
+static bool use_fold(const ConvGeom& g) {
+  if (!g_kdfold || g.mode != CONV_S1 || g.k != 3 || operand_type(g) == OP_TF32) return false;
+  const int n = pick_n(pad_cout(g.Cout));
+  return n == 16 || n == 32;
+}
 
 // virtual (stride-1) problem of a conv geometry: S1 as is; DOWN / UP = 2x2x2 conv on the coarse grid (conv_s2.cu)
 struct TcProblem {
@@ -672,6 +750,7 @@ int tc_pack_job(const ConvGeom& g, const float* w, float* wp, PackJob* jb) {
     jb->taps = g.k * g.k * g.k; jb->Cin = pad_cin(g); jb->Cout = pad_cout(g.Cout); jb->N = pick_n(jb->Cout);
     jb->aux = g.flip; jb->cin_real = g.Cin; jb->cout_real = g.Cout;
     jb->total = (long long)jb->taps * jb->Cin * jb->Cout;
+    if (use_fold(g)) jb->s2 = 2;
   }
   return B3D_OK;
 }
@@ -693,7 +772,7 @@ int launch_tc_pack_weights(const ConvGeom& g, const float* w, float* wp, cudaStr
   const unsigned grid = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
 #define B3D_PACK(OPV)                                                                                          \
   tc_pack_kernel<OPV><<<grid, 256, 0, s>>>(w, wp, taps, cin, cout, pick_n(cout), g.wtap, g.sw_in, g.sw_out, g.flip, \
-                                           g.Cin, g.Cout)
+                                           g.Cin, g.Cout, use_fold(g) ? 1 : 0)
   if (op == OP_BF16) B3D_PACK(OP_BF16);
   else if (op == OP_F16) B3D_PACK(OP_F16);
   else B3D_PACK(OP_TF32);
@@ -781,6 +860,12 @@ template <int KS, int HB, int BF16>
 static int dispatch_n(const ConvGeom& g, const TcProblem& q, const float* x, const float* wp, const float* bias,
                       float* y, double* stats, float* gap, cudaStream_t s) {
   const int n = pick_n(q.Cout);
+  if constexpr (KS == 3 && HB == 1 && BF16 != OP_TF32) {
+    if (use_fold(g)) {
+      if (n == 16) return launch_cfg<TcCfg<16, 8, 1, KS, HB, BF16, 1>>(g, q, x, wp, bias, y, stats, gap, s);
+      return launch_cfg<TcCfg<32, 4, 1, KS, HB, BF16, 1>>(g, q, x, wp, bias, y, stats, gap, s);
+    }
+  }
   if (n == 128) return launch_cfg<TcCfg<128, 2, 1, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s);
   if constexpr (!(KS == 2 && HB == 1)) {   // the depth-to-space form always has N = 8*Cp = multiple of 128
     if (n == 64) return launch_cfg<TcCfg<64, 2, 2, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s);
@@ -833,3 +918,11 @@ extern "C" int b3d_set_conv_precision(int fwd, int bwd) {
   return 0;
 }
 extern "C" int b3d_get_conv_precision(void) { return b3d::g_fwd_op | (b3d::g_bwd_op << 4); }
+
+// kd-folded 3x3x3 kernel for output tiles of 16 / 32 channels (see the header comment of this file).  Changes the
+// packed weight layout of those layers: re-pack after switching.  Returns the previous setting.
+extern "C" int b3d_set_conv_kdfold(int on) {
+  const int prev = b3d::g_kdfold;
+  b3d::g_kdfold = on ? 1 : 0;
+  return prev;
+}

@@ -185,6 +185,15 @@ def set_conv_precision(fwd: str = "fp16", bwd: str = "bf16"):
     _PREC_EPOCH["n"] += 1
 
 
+def set_kd_fold(on: bool) -> bool:
+    """Switch the kd-folded 3x3x3 kernel for 16 / 32-channel output tiles (csrc/conv_tc.cu header) on or off; the
+    packed operands of those layers change layout, so every registered pack is marked stale.  Returns the previous
+    setting."""
+    prev = bool(lib.b3d_set_conv_kdfold(int(bool(on))))
+    _PREC_EPOCH["n"] += 1
+    return prev
+
+
 def get_conv_precision():
     v = lib.b3d_get_conv_precision()
     return (_PREC_INV[v & 15], _PREC_INV[v >> 4])

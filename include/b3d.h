@@ -22,7 +22,7 @@
  *    every call is CUDA-graph capturable.
  *  - return 0 on success, a negative B3D_ERR_* code otherwise; `b3d_last_error()` returns the
  *    thread-local message.  No exceptions cross the ABI.  Process-wide state is limited to the
- *    two settings below (b3d_set_conv_precision, b3d_set_wgrad_ts) and the split-K workspace.
+ *    settings below (b3d_set_conv_precision, b3d_set_conv_kdfold, b3d_set_wgrad_ts) and the split-K workspace.
  */
 #ifndef B3D_H_
 #define B3D_H_
@@ -91,6 +91,10 @@ int b3d_conv3d_tc_supported(int k, int stride, int transposed, int dgrad, int a,
  * Packed weights depend on it: re-pack after a change.  get: fwd | bwd << 4. */
 int b3d_set_conv_precision(int fwd_op, int bwd_op);
 int b3d_get_conv_precision(void);
+/* kd-folded variant of the 3x3x3 tcgen05 kernel for output tiles of 16 / 32 channels (depth taps folded into the MMA
+ * N dimension: 2-2.4x fewer small-N MMAs; csrc/conv_tc.cu).  Process-wide, default off; changes the packed weight
+ * layout of those layers (re-pack after switching).  Returns the previous setting. */
+int b3d_set_conv_kdfold(int on);
 long long b3d_conv3d_packed_elems(int k, int stride, int a, int b);
 int b3d_conv3d_pack_weights(const DLTensor* w, DLTensor* packed, int stride, int transposed, int dgrad,
                             void* stream);

@@ -18,8 +18,9 @@ agg = collections.defaultdict(lambda: [0, 0.0])
 for n, v in zip(names[s:e], vals[s:e]):
     k = re.sub(r"[<(].*", "", n).replace("void ", "")
     if "conv_tc_kernel" in n:
-        m = re.search(r"TcCfg<(\d+), *\d+, *\d+, *(\d+), *(\d+), *(\w+)>", n)
-        k = f"b3d::conv_tc_kernel KS={m.group(2)}" + (" (stride-2 family)" if m.group(2) == "2" else "")
+        m = re.search(r"TcCfg<(\d+), *\d+, *\d+, *(\d+), *(\d+), *(\w+)(?:, *(\d+))?>", n)
+        k = f"b3d::conv_tc_kernel KS={m.group(2)}" + (" (stride-2 family)" if m.group(2) == "2" else "") + \
+            (" kd-folded" if m.group(5) == "1" else "")
     elif "wgrad_tc" in n:
         m = re.search(r"<(\d+), *(\d+)>", n)
         k = f"b3d::conv3_wgrad_tc_kernel KS={m.group(1)} TG={m.group(2)}"
