@@ -350,11 +350,13 @@ def run_b3d(args):
     pk, pk_src = peaks()
     conv_ms, conv_flops = measure_conv_roofline(b3d, torch, dev)
     ach = conv_flops / (conv_ms * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::f16, fp16 operands, fp32 accumulate) dec.L0 conv1 128^3 32->16",
+    roof = {"bound": "tensor", "kernel": "conv_tc_kernel, kd-folded variant (tcgen05 kind::f16, fp16 operands, fp32 accumulate) dec.L0 conv1 "
+                                                 "128^3 32->16",
             "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
             "peak_source": f"{pk_src} dense bf16 burst (cuBLAS 8192^3); 16-bit operands, same tensor-pipe rate",
             "ms_per_launch": conv_ms, "traffic": 363.6e6, "traffic_unit": "bytes/launch (dram read+write, ncu --set full, "
-            "profiles/r01_ncu_conv_tc_fp16_128cube_32to16.csv; algorithmic 402.7e6)"}
+            "profiles/r01_ncu_conv_tc_fp16_128cube_32to16.csv = the capture of the unfolded variant, the "
+            "kd-folded one reads the same tensors through a 8x16x8 tile; algorithmic 402.7e6)"}
     # CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
