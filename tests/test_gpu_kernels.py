@@ -341,6 +341,41 @@ def test_tc_conv_vs_oracle_and_generic(b3d, dev, case):
     assert rel(res["fp16"][0], res["fp32"][0]) < TOL_TF32
 
 
+KD_FOLD_CASES = [((1, 16, 32, 16), 16, 16, 0), ((1, 5, 24, 20), 32, 16, 0), ((2, 8, 16, 16), 16, 32, 0),
+                 ((1, 12, 20, 9), 2, 16, 0), ((1, 9, 17, 11), 16, 3, 1), ((1, 4, 16, 16), 32, 96, 0)]
+
+
+@pytest.mark.parametrize("case", KD_FOLD_CASES)
+def test_kd_folded_conv_equals_unfolded(b3d, dev, case):
+    """The kd-folded 3x3x3 tcgen05 kernel (depth taps folded into the MMA N dimension, csrc/conv_tc.cu) against the
+    unfolded one on the same operands: only the fp32 summation order differs.  Forward (+bias, sigmoid, GroupNorm
+    statistics) and data gradient; full and partial tiles, narrow inputs / outputs, N splits."""
+    ops = b3d.ops
+    (B, D, H, W), cin, cout, act = case
+    x = dev32(t64(B, D, H, W, cin, seed=81), dev)
+    w = dev32(t64(3, 3, 3, cin, cout, seed=82, scale=(2.0 / (27 * cin)) ** 0.5), dev)
+    bias, dy = dev32(t64(cout, seed=83), dev), dev32(t64(B, D, H, W, cout, seed=84), dev)
+    groups = 8 if (D * H * W) % 8 == 0 and cout % 8 == 0 else 0
+
+    def run():
+        y, stats, _ = ops.conv3d(x, w, bias, 1, False, act, groups, False)
+        dx = torch.empty_like(x)
+        ops._call("b3d_conv3d_dgrad", dy, w, dx, 1, 0, 0, ops.pack_weights(w, True, 1, False))
+        torch.cuda.synchronize()
+        return y, stats, dx
+
+    prev = ops.set_kd_fold(False)
+    try:
+        ref = run()
+        ops.set_kd_fold(True)
+        got = run()
+    finally:
+        ops.set_kd_fold(prev)
+    assert rel(got[0], ref[0]) < 1e-5 and rel(got[2], ref[2]) < 1e-5, (rel(got[0], ref[0]), rel(got[2], ref[2]))
+    if groups:
+        assert rel(got[1], ref[1]) < 1e-6
+
+
 @pytest.mark.parametrize("k,cin,cout", [(3, 16, 16), (1, 32, 16), (3, 64, 32)])
 def test_dgrad_accumulate_epilogue(b3d, dev, k, cin, cout):
     """b3d_conv3d_dgrad(accumulate=1) adds the data gradient to what `dx` already holds (include/b3d.h), on the
