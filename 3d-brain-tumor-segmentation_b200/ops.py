@@ -177,7 +177,8 @@ def set_conv_precision(fwd: str = "fp16", bwd: str = "bf16"):
     separately for the forward pass and the data gradient.  Default: forward fp16 — TF32's 11-bit significand
     (north_star: per-layer <= 2e-3, argmax agreement >= 99.9 %) at half the operand bytes; its narrow exponent
     is safe for the forward operands (image, GroupNorm outputs, O(1) weights; conversion saturates) — and backward
-    bf16 (<= 1e-2; gradients need the exponent range).  The weight-gradient kernel always uses bf16 operands."""
+    bf16 (<= 1e-2; gradients need the exponent range).  The weight-gradient kernel always uses bf16 operands.
+    Packed operands are re-made at their next use; CUDA graphs captured before the change must be re-captured."""
     for v in (fwd, bwd):
         if v not in _PREC:
             raise ValueError(v)
@@ -187,8 +188,9 @@ def set_conv_precision(fwd: str = "fp16", bwd: str = "bf16"):
 
 def set_kd_fold(on: bool) -> bool:
     """Switch the kd-folded 3x3x3 kernel for 16 / 32-channel output tiles (csrc/conv_tc.cu header) on or off; the
-    packed operands of those layers change layout, so every registered pack is marked stale.  Returns the previous
-    setting."""
+    packed operands of those layers change layout, so every registered pack is marked stale (CUDA graphs captured
+    before the switch keep launching the old kernel variant on the re-laid-out buffers: re-capture them).  Returns
+    the previous setting."""
     prev = bool(lib.b3d_set_conv_kdfold(int(bool(on))))
     _PREC_EPOCH["n"] += 1
     return prev
