@@ -196,6 +196,12 @@ def set_kd_fold(on: bool) -> bool:
     return prev
 
 
+# A/B switch for measurements (bench.py, tools/): B3D_KD_FOLD=0 runs the unfolded 3x3x3 kernel everywhere
+import os as _os
+if _os.environ.get("B3D_KD_FOLD") is not None:
+    set_kd_fold(_os.environ["B3D_KD_FOLD"] not in ("0", "", "off", "false"))
+
+
 def get_conv_precision():
     v = lib.b3d_get_conv_precision()
     return (_PREC_INV[v & 15], _PREC_INV[v >> 4])
