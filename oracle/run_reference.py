@@ -99,6 +99,30 @@ def load_params(model, p, depth=4, with_vae=True):
         _set(v.out, "bias", p["vae.out.bias"])
 
 
+def import_reference_test_module():
+    """The reference's inference script test.py (TestTimeAugmentor :75-161, pad_to_spatial_res :164-178) as a module.
+    It is loaded by path (a bare `import test` would find CPython's own `test` package) with an empty stand-in for
+    nibabel, which is not in this image and is only used by the NIfTI reader/writer functions."""
+    import importlib.util
+    import types
+    _import_reference()
+    sys.modules.setdefault("nibabel", types.ModuleType("nibabel"))
+    spec = importlib.util.spec_from_file_location("b3d_reference_test_py", os.path.join(REF, "test.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def import_reference_train_module():
+    """The reference's train.py (prepare_dataset :12-68 with its per-example map function) as a module, by path."""
+    import importlib.util
+    _import_reference()
+    spec = importlib.util.spec_from_file_location("b3d_reference_train_py", os.path.join(REF, "train.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 class ReferenceRunner:
     """Builds the reference Model(**model_args) on the shim and loads `params` (this repo's names)."""
 

@@ -113,6 +113,20 @@ def zeros(shape, dtype=None):
     return _torch.zeros(list(shape), dtype=DTYPE)
 
 
+def transpose(x, perm):
+    return _t(x).permute(*[int(a) for a in perm])
+
+
+def pad(x, paddings, mode='CONSTANT', constant_values=0.0):
+    """tf.pad, CONSTANT mode: paddings[d] = [before, after] per dimension (used by the reference's test.py:164-178)."""
+    assert mode == 'CONSTANT'
+    x = _t(x)
+    flat = []
+    for before, after in reversed([[int(a), int(b)] for a, b in paddings]):     # F.pad lists the LAST dim first
+        flat += [before, after]
+    return _F.pad(x, flat, mode='constant', value=float(constant_values))
+
+
 class _Math:
     sqrt = staticmethod(_torch.sqrt)
     exp = staticmethod(_torch.exp)
@@ -146,10 +160,101 @@ class _Random:
             return self.injected_normal
         return _torch.randn(list(shape), generator=self._gen, dtype=DTYPE)
 
+    # test hook: a list of tensors handed out in call order by uniform() (the data pipeline's draws)
+    injected_uniform = None
+
     def uniform(self, shape, lo=0.0, hi=1.0):
+        if self.injected_uniform is not None:
+            v = _torch.as_tensor(self.injected_uniform.pop(0), dtype=DTYPE)
+            assert list(v.shape) == list(shape), (v.shape, shape)
+            return v
         return lo + (hi - lo) * _torch.rand(list(shape), generator=self._gen, dtype=DTYPE)
 
 
 random = _Random()
+
+
+def cond(pred, true_fn, false_fn):
+    return true_fn() if bool(pred) else false_fn()
+
+
+def split(x, sizes, axis=0):
+    return list(_torch.split(_t(x), [int(v) for v in sizes], dim=axis))
+
+
+class _Image:
+    # test hook: crop offset used instead of a random one
+    injected_offset = None
+
+    def random_crop(self, x, size):
+        size = [int(v) for v in size]
+        off = self.injected_offset
+        if off is None:
+            off = [int(_torch.randint(0, x.shape[i] - size[i] + 1, (1,), generator=random._gen)) for i in range(len(size))]
+        off = list(off) + [0] * (len(size) - len(off))
+        return x[tuple(slice(o, o + n) for o, n in zip(off, size))]
+
+
+image = _Image()
+
+
+class _IO:
+    """Stand-in for the TFRecord proto parsing of train.py:15,49-51: a 'serialized example' is already a dict of
+    flat tensors, parse_single_example hands its entries back."""
+
+    class FixedLenFeature:
+        def __init__(self, shape, dtype):
+            self.shape, self.dtype = shape, dtype
+
+    @staticmethod
+    def parse_single_example(proto, desc):
+        out = {}
+        for k, f in desc.items():
+            v = _t(proto[k]).reshape(-1)
+            assert v.numel() == int(f.shape[0]), (k, v.numel(), f.shape)
+            out[k] = v
+        return out
+
+
+io = _IO()
+
+
+class _Dataset:
+    def __init__(self, records, fn=None, batch=None):
+        self.records, self.fn, self.nbatch = records, fn, batch
+
+    def shuffle(self, buffer_size):
+        return self
+
+    def map(self, map_func, num_parallel_calls=None):
+        return _Dataset(self.records, map_func, self.nbatch)
+
+    def batch(self, batch_size):
+        return _Dataset(self.records, self.fn, int(batch_size))
+
+    def prefetch(self, buffer_size):
+        return self
+
+    def __iter__(self):
+        items = [self.fn(r) if self.fn else r for r in self.records]
+        n = self.nbatch or 1
+        for i in range(0, len(items), n):
+            chunk = items[i:i + n]
+            yield tuple(_torch.stack([c[j] for c in chunk]) for j in range(len(chunk[0])))
+
+
+class _Data:
+    # test hook: the "file contents" every TFRecordDataset yields, one dict per file
+    injected_records = None
+
+    class experimental:
+        AUTOTUNE = -1
+
+    def TFRecordDataset(self, files):
+        assert self.injected_records is not None and len(self.injected_records) == len(files)
+        return _Dataset(list(self.injected_records))
+
+
+data = _Data()
 
 from . import keras  # noqa: E402,F401
