@@ -42,9 +42,76 @@ def _same_pads(n: int, k: int, s: int) -> Tuple[int, int]:
     return before, total - before
 
 
-def conv3d_same(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1) -> torch.Tensor:
-    """tf.keras.layers.Conv3D(padding='same') on NDHWC input (call sites resnet.py:80-87,
-    downsample.py:28-35, decoder.py:55-63, vae.py:92-99).  Cross-correlation, no flip."""
+# Operand-rounding emulation ("error model" of the mixed-precision tensor-core path, used only to DERIVE the tolerances
+# of the GPU parity tests — tests/test_gpu_baseline_shapes.py): inside `operand_rounding(fwd, bwd, wgrad)` every conv that
+# the CUDA path runs on the tensor cores rounds its two operands to the stated type before the (fp32/fp64) contraction:
+# forward x,w -> `fwd`; data gradient dy,w -> `bwd`; weight gradient x,dy -> `wgrad`.  Accumulation, bias and everything
+# that is not a conv stay in the run's dtype.  With all three None the functions below are the plain restatement.
+_ROUND = {"fwd": None, "bwd": None, "wgrad": None}
+
+
+class operand_rounding:
+    def __init__(self, fwd="fp16", bwd="bf16", wgrad="bf16"):
+        self.new = {"fwd": fwd, "bwd": bwd, "wgrad": wgrad}
+
+    def __enter__(self):
+        self.prev = dict(_ROUND)
+        _ROUND.update(self.new)
+
+    def __exit__(self, *a):
+        _ROUND.update(self.prev)
+        return False
+
+
+def round_operand(t: torch.Tensor, kind: Optional[str]) -> torch.Tensor:
+    """Round-to-nearest-even to the significand / range of `kind` ('fp16' saturating, 'bf16', 'tf32'), same dtype out."""
+    if kind is None:
+        return t
+    if kind == "fp16":
+        return t.clamp(-65504.0, 65504.0).to(torch.float16).to(t.dtype)
+    if kind == "bf16":
+        return t.to(torch.bfloat16).to(t.dtype)
+    if kind == "tf32":                     # 10 explicit significand bits, fp32 exponent (cvt.rna: ties away; rn here)
+        i = t.to(torch.float32).contiguous().view(torch.int32)
+        i = (i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF
+        return i.view(torch.float32).to(t.dtype)
+    raise ValueError(kind)
+
+
+class _RoundedConv(torch.autograd.Function):
+    """y = fn(rnd_fwd(x), rnd_fwd(w)) + b;  dx from (rnd_bwd(dy), rnd_bwd(w));  dw from (rnd_wg(x), rnd_wg(dy))."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, fn):
+        ctx.fn, ctx.kinds, ctx.has_b = fn, dict(_ROUND), b is not None
+        ctx.save_for_backward(x, w)
+        y = fn(round_operand(x, _ROUND["fwd"]), round_operand(w, _ROUND["fwd"]))
+        return y if b is None else y + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        k = ctx.kinds
+        dx = dw = db = None
+        with torch.enable_grad():
+            if ctx.needs_input_grad[0]:
+                x1 = torch.zeros_like(x).requires_grad_(True)          # the conv is linear in x
+                dx, = torch.autograd.grad(ctx.fn(x1, round_operand(w, k["bwd"])), x1, round_operand(dy, k["bwd"]))
+            if ctx.needs_input_grad[1]:
+                w1 = torch.zeros_like(w).requires_grad_(True)
+                dw, = torch.autograd.grad(ctx.fn(round_operand(x, k["wgrad"]), w1), w1, round_operand(dy, k["wgrad"]))
+        if ctx.has_b and ctx.needs_input_grad[2]:
+            db = dy.sum(dim=(0, 1, 2, 3))
+        return dx, dw, db, None
+
+
+def _on_tensor_cores(cin: int, cout: int, stride2: bool) -> bool:
+    """Which convs the CUDA path runs with 16-bit operands (csrc/conv_tc.cu tc_conv_supported): all of them except the
+    two tiny stride-2-family layers of the VAE bottleneck (16^3x512 -> 8^3x8, 8^3x1 -> 16^3x128: fp32 CUDA cores)."""
+    return not (stride2 and min(cin, cout) < 16)
+
+
+def _conv3d_same_raw(x, w, stride):
     k = w.shape[0]
     xc = x.permute(0, 4, 1, 2, 3)
     pads = []
@@ -53,22 +120,34 @@ def conv3d_same(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], str
         pads += [pb, pa]
     xc = F.pad(xc, pads)
     wc = w.permute(4, 3, 0, 1, 2)
-    y = F.conv3d(xc, wc, b, stride=stride)
-    return y.permute(0, 2, 3, 4, 1)
+    return F.conv3d(xc, wc, None, stride=stride).permute(0, 2, 3, 4, 1)
+
+
+def conv3d_same(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1) -> torch.Tensor:
+    """tf.keras.layers.Conv3D(padding='same') on NDHWC input (call sites resnet.py:80-87,
+    downsample.py:28-35, decoder.py:55-63, vae.py:92-99).  Cross-correlation, no flip."""
+    if any(v is not None for v in _ROUND.values()) and _on_tensor_cores(w.shape[3], w.shape[4], stride == 2):
+        return _RoundedConv.apply(x, w, b, lambda a, k: _conv3d_same_raw(a, k, stride))
+    y = _conv3d_same_raw(x, w, stride)
+    return y if b is None else y + b
+
+
+def _conv3d_transpose_raw(x, w):
+    xc = x.permute(0, 4, 1, 2, 3)
+    wc = w.permute(4, 3, 0, 1, 2)  # (Cin, Cout, kd,kh,kw) as conv_transpose3d expects
+    y = F.conv_transpose3d(xc, wc, None, stride=2, padding=0)
+    d, h, ww = x.shape[1:4]
+    return y[:, :, : 2 * d, : 2 * h, : 2 * ww].permute(0, 2, 3, 4, 1)
 
 
 def conv3d_transpose_same(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
     """tf.keras.layers.Conv3DTranspose(kernel 3, strides 2, padding 'same') (upsample.py:28-33):
     the exact adjoint (conv3d_backprop_input) of the SAME/stride-2 conv with filter
     (kd,kh,kw,Cout,Cin); output spatial = 2*in."""
-    xc = x.permute(0, 4, 1, 2, 3)
-    wc = w.permute(4, 3, 0, 1, 2)  # (Cin, Cout, kd,kh,kw) as conv_transpose3d expects
-    y = F.conv_transpose3d(xc, wc, None, stride=2, padding=0)
-    d, h, ww = x.shape[1:4]
-    y = y[:, :, : 2 * d, : 2 * h, : 2 * ww]
-    if b is not None:
-        y = y + b.view(1, -1, 1, 1, 1)
-    return y.permute(0, 2, 3, 4, 1)
+    if any(v is not None for v in _ROUND.values()) and _on_tensor_cores(w.shape[4], w.shape[3], True):
+        return _RoundedConv.apply(x, w, b, _conv3d_transpose_raw)
+    y = _conv3d_transpose_raw(x, w)
+    return y if b is None else y + b
 
 
 def dense(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
@@ -364,124 +443,14 @@ def tta_inference(p: Params, x, bmask, mean, std, depth=4, groups=8):
 
 
 # ----------------------------------------------------------------------------------
-# Deterministic synthetic weights / inputs
+# Deterministic synthetic weights / inputs live in the neutral top-level module `synthdata`
+# (bench.py / smoke() use them without importing oracle/); re-exported here for the tests.
 # ----------------------------------------------------------------------------------
-def param_shapes(in_ch=2, out_ch=3, base_filters=16, depth=4, reduction=2, crop=(128, 128, 128),
-                 with_vae=True, downsampling="conv", upsampling="conv") -> Dict[str, Tuple[int, ...]]:
-    """Shapes of all trainable tensors in Keras layouts, keyed by this repo's names."""
-    s: Dict[str, Tuple[int, ...]] = {}
+import os as _os
+import sys as _sys
 
-    def block(pre, cin, f):
-        s[pre + "ptwise.kernel"] = (1, 1, 1, cin, f)
-        s[pre + "ptwise.bias"] = (f,)
-        s[pre + "dense_relu.kernel"] = (f, f // reduction)
-        s[pre + "dense_sigmoid.kernel"] = (f // reduction, f)
-        s[pre + "spatial.kernel"] = (1, 1, 1, f, 1)
-        s[pre + "conv1.kernel"] = (3, 3, 3, cin, f)
-        s[pre + "conv1.bias"] = (f,)
-        s[pre + "gn1.gamma"] = (f,)
-        s[pre + "gn1.beta"] = (f,)
-        s[pre + "conv2.kernel"] = (3, 3, 3, f, f)
-        s[pre + "conv2.bias"] = (f,)
-        s[pre + "gn2.gamma"] = (f,)
-        s[pre + "gn2.beta"] = (f,)
-
-    def down(pre, cin, f, kind=None):
-        if (kind or downsampling) == "max":          # MaxDownsample: no weights, channels kept
-            return cin
-        s[pre + "conv.kernel"] = (3, 3, 3, cin, f)
-        s[pre + "conv.bias"] = (f,)
-        s[pre + "norm.gamma"] = (f,)
-        s[pre + "norm.beta"] = (f,)
-        return f
-
-    def up(pre, cin, f):
-        if upsampling == "linear":         # LinearUpsample: 1x1x1 conv (+bias), no norm
-            s[pre + "ptwise.kernel"] = (1, 1, 1, cin, f)
-            s[pre + "ptwise.bias"] = (f,)
-            return
-        s[pre + "conv.kernel"] = (3, 3, 3, f, cin)
-        s[pre + "conv.bias"] = (f,)
-        s[pre + "norm.gamma"] = (f,)
-        s[pre + "norm.beta"] = (f,)
-
-    cin = in_ch
-    for i in range(depth):
-        f = base_filters * 2 ** i
-        for j in range(i + 1):
-            block(f"enc.L{i}.B{j}.", cin if j == 0 else (j + 1) * f, f)
-        cin = f if i == 0 else (i + 1) * f
-        if i < depth - 1:
-            cin = down(f"enc.L{i}.down.", cin, f)
-    bott = cin
-    res_ch = [base_filters if i == 0 else (i + 1) * base_filters * 2 ** i for i in range(depth)]
-    c = bott
-    for i in range(depth - 2, -1, -1):
-        f = base_filters * 2 ** i
-        up(f"dec.L{i}.up.", c, f)
-        block(f"dec.L{i}.block.", res_ch[i] + f, f)
-        c = f
-    s["dec.out.kernel"] = (1, 1, 1, c, out_ch)
-    s["dec.out.bias"] = (out_ch,)
-    if with_vae:
-        d, h, w = [n // 2 ** (depth - 1) for n in crop]
-        # model.py:49-57 does not forward `downsampling` to the VAE: its extra downsample is always the conv variant
-        f = down("vae.down.", bott, base_filters // 2, kind="conv")
-        flat = (d // 2) * (h // 2) * (w // 2) * f
-        s["vae.proj.kernel"] = (flat, base_filters * 2 ** (depth - 1))
-        s["vae.proj.bias"] = (base_filters * 2 ** (depth - 1),)
-        latent = base_filters * 2 ** (depth - 2)
-        s["vae.unproj.kernel"] = (latent, d * h * w // 8)
-        s["vae.unproj.bias"] = (d * h * w // 8,)
-        up("vae.up.", 1, base_filters * 2 ** (depth - 1))
-        c = base_filters * 2 ** (depth - 1)
-        for i in range(depth - 2, -1, -1):
-            f = base_filters * 2 ** i
-            up(f"vae.L{i}.up.", c, f)
-            block(f"vae.L{i}.block.", f, f)
-            c = f
-        s["vae.out.kernel"] = (3, 3, 3, c, in_ch)
-        s["vae.out.bias"] = (in_ch,)
-    return s
-
-
-def init_params(shapes: Dict[str, Tuple[int, ...]], seed=2, dtype=torch.float64) -> Params:
-    """Synthetic weights of the reference's scale: kernels ~ N(0, 2/fan_in)
-    (he-like), GN gamma 1+0.1N (incl. gn2, whose reference init 0 would kill the conv branch, F4),
-    beta 0.1N, biases 0.01N."""
-    rng = np.random.default_rng(seed)
-    p: Params = {}
-    for k, shp in shapes.items():
-        if k.endswith("kernel"):
-            if len(shp) == 5:
-                fan_in = shp[0] * shp[1] * shp[2] * shp[3]
-                if ".up.conv." in k:  # transpose conv: (k,k,k,Cout,Cin)
-                    fan_in = shp[0] * shp[1] * shp[2] * shp[4] / 8.0  # ~27/8 taps hit per output
-            else:
-                fan_in = shp[0]
-            a = rng.standard_normal(shp) * math.sqrt(2.0 / fan_in)
-        elif k.endswith("gamma"):
-            a = 1.0 + 0.1 * rng.standard_normal(shp)
-        elif k.endswith("beta"):
-            a = 0.1 * rng.standard_normal(shp)
-        else:
-            a = 0.01 * rng.standard_normal(shp)
-        p[k] = torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
-    return p
-
-
-def synth_batch(shape=(1, 128, 128, 128), in_ch=2, out_ch=3, latent=64, seed=0, dtype=torch.float64):
-    """x ~ N(0,1) seed; y: iid labels p=(0.85,0.05,..) one-hot minus background; eps ~ N(0,1);
-    dropout mask Bernoulli(0.8)."""
-    rng = np.random.default_rng(seed)
-    x = rng.standard_normal(shape + (in_ch,))
-    pr = [0.85] + [0.15 / out_ch] * out_ch
-    lab = np.random.default_rng(seed + 1).choice(out_ch + 1, size=shape, p=pr)
-    y = np.stack([(lab == c + 1) for c in range(out_ch)], axis=-1).astype(np.float64)
-    eps = np.random.default_rng(seed + 3).standard_normal((shape[0], latent))
-    mask = (np.random.default_rng(seed + 4).random(shape + (in_ch,)) < 0.8).astype(np.float64)
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
-    return t(x), t(y), t(eps), t(mask)
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+from synthdata import param_shapes, init_params, synth_batch  # noqa: E402,F401
 
 
 # ----------------------------------------------------------------------------------
