@@ -118,6 +118,18 @@ SIGNATURES = {
     "b3d_epoch_tick": "Tv",
     "b3d_flip_normalize": "TTTTiv",
     "b3d_flip_accumulate": "TTTifiv",
+    # P16 operand twins (csrc/p16.cu) and the entry points that produce / consume them
+    "b3d_p16_pack": "TTTv",
+    "b3d_p16_unpack": "TTv",
+    "b3d_p16_copy_planes": "TTiv",
+    "b3d_colsum": "TTv",
+    "b3d_conv3d_fwd_p16": "TTTTTTTiiiTiTiTv",
+    "b3d_conv3d_dgrad_p16": "TTTiiiTv",
+    "b3d_conv3d_wgrad_p16": "TTTTTTiiTv",
+    "b3d_gn_apply_p16": "TTTTTTifiv",
+    "b3d_gn_bwd_apply_p16": "TTTTTTTTTifiv",
+    "b3d_block_epilogue_fwd_p16": "TTTTTTTTTifiv",
+    "b3d_block_epilogue_bwd_apply_p16": "TTTTTTTTTTTTTTTTifiv",
 }
 _CT = {"T": P, "i": _i, "f": _f, "v": _v, "L": _ll, "U": _ull}
 for _name, _sig in SIGNATURES.items():
@@ -140,6 +152,8 @@ lib.b3d_conv3d_pack_job_bytes.restype = _i
 lib.b3d_slab_sym_bytes.argtypes = [_ll]
 lib.b3d_slab_sym_bytes.restype = _ll
 lib.b3d_get_conv_precision.restype = _i
+lib.b3d_conv3d_wgrad_p16_plan.argtypes = [_i] * 6
+lib.b3d_conv3d_wgrad_p16_plan.restype = _i
 
 
 class B3DError(RuntimeError):

@@ -20,6 +20,26 @@ struct BlockGeom {
   int vox_per_cta;    // voxels handled by one CTA
 };
 
+// P16 twin output (common.cuh): half cell (4 channels) of voxel `vox` (index inside sample b) at channel c
+struct P16Out {
+  uint2* p;         // nullptr: no twin
+  unsigned W, C8;   // voxels per row, channel octets
+  unsigned rows;    // D*H rows per sample
+  int bf16;
+};
+__device__ __forceinline__ void p16_store4(const P16Out& o, long long b, unsigned vox, int c, const float4& v) {
+  const unsigned row = vox / o.W, w = vox - row * o.W;
+  uint2 q;
+  if (o.bf16) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v.w), "f"(v.z));
+  } else {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v.w), "f"(v.z));
+  }
+  o.p[((((unsigned long long)b * o.rows + row) * o.C8 + (c >> 3)) * o.W + w) * 2 + ((c >> 2) & 1)] = q;
+}
+
 __device__ __forceinline__ float group_sum(float v, int T) {
   for (int o = T >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -41,7 +61,8 @@ __global__ void __launch_bounds__(kBT)
     block_epilogue_fwd_kernel(const float* __restrict__ res, const float* __restrict__ h2,
                               const double* __restrict__ stats, const float* __restrict__ gamma,
                               const float* __restrict__ beta, const float* __restrict__ wsp,
-                              const float* __restrict__ chse, float* __restrict__ out, BlockGeom gm, float eps) {
+                              const float* __restrict__ chse, float* __restrict__ out, BlockGeom gm, float eps,
+                              P16Out out16) {
   const int chunk = blockIdx.y, b = chunk / gm.G, g = chunk % gm.G;
   const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
   float mean = 0.f, rstd = 1.f;
@@ -102,7 +123,8 @@ __global__ void __launch_bounds__(kBT)
           o.y = r[q].y * (s + c4[q].y) + a.y;
           o.z = r[q].z * (s + c4[q].z) + a.z;
           o.w = r[q].w * (s + c4[q].w) + a.w;
-          st_stream(reinterpret_cast<float4*>(out + eo + c), o);
+          if (out != nullptr) st_stream(reinterpret_cast<float4*>(out + eo + c), o);
+          if (out16.p != nullptr) p16_store4(out16, b, (unsigned)((long long)g * gm.vpc + v), c, o);
         }
     }
   }
@@ -254,7 +276,17 @@ __global__ void __launch_bounds__(kBT)
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ wsp, const float* __restrict__ chse,
                                     const float* __restrict__ dgap, const double* __restrict__ csum,
-                                    float* __restrict__ dres, float* __restrict__ dh2, BlockGeom gm, float eps) {
+                                    float* __restrict__ dres, float* __restrict__ dh2, BlockGeom gm, float eps,
+                                    P16Out dres16, P16Out dh216, float* __restrict__ dbias_res,
+                                    float* __restrict__ dbias_h2) {
+  extern __shared__ float sdb[];      // [2][F]: column sums of dres / dh2 (bias gradients of the pointwise / second conv)
+  if (dbias_res != nullptr) {
+    for (int i = threadIdx.x; i < 2 * gm.F; i += kBT) sdb[i] = 0.f;
+    __syncthreads();
+  }
+  float4 acc_r[NPL], acc_h[NPL];
+#pragma unroll
+  for (int q = 0; q < NPL; ++q) acc_r[q] = acc_h[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int chunk = blockIdx.y, b = chunk / gm.G, g = chunk % gm.G;
   const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
   float mean = 0.f, rstd = 1.f, m1 = 0.f, m2 = 0.f;
@@ -317,7 +349,10 @@ __global__ void __launch_bounds__(kBT)
           o.y = d[q].y * (s + c4[q].y) + dl * w4[q].y + g4[q].y;
           o.z = d[q].z * (s + c4[q].z) + dl * w4[q].z + g4[q].z;
           o.w = d[q].w * (s + c4[q].w) + dl * w4[q].w + g4[q].w;
-          st_stream(reinterpret_cast<float4*>(dres + eo + c), o);
+          if (dres != nullptr) st_stream(reinterpret_cast<float4*>(dres + eo + c), o);
+          const unsigned vs = (unsigned)((long long)g * gm.vpc + v);
+          if (dres16.p != nullptr) p16_store4(dres16, b, vs, c, o);
+          acc_r[q].x += o.x; acc_r[q].y += o.y; acc_r[q].z += o.z; acc_r[q].w += o.w;
           if (HAS_GN) {
             const float4 hv = ld_stream(reinterpret_cast<const float4*>(h2 + eo + c));
             const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
@@ -331,9 +366,31 @@ __global__ void __launch_bounds__(kBT)
               const float gq = (xh * ga[i] + be[i]) > 0.f ? dd[i] : 0.f;
               oo[i] = rstd * (gq * ga[i] - m1 - xh * m2);
             }
-            st_stream(reinterpret_cast<float4*>(dh2 + eo + c), make_float4(oo[0], oo[1], oo[2], oo[3]));
+            const float4 o2 = make_float4(oo[0], oo[1], oo[2], oo[3]);
+            if (dh2 != nullptr) st_stream(reinterpret_cast<float4*>(dh2 + eo + c), o2);
+            if (dh216.p != nullptr) p16_store4(dh216, b, vs, c, o2);
+            acc_h[q].x += o2.x; acc_h[q].y += o2.y; acc_h[q].z += o2.z; acc_h[q].w += o2.w;
           }
         }
+    }
+  }
+  if (dbias_res != nullptr) {
+    // lanes of a warp with equal (lane % T) hold the same channels: butterfly over the voxel sub-index first
+    const int wl = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < NPL; ++q) {
+      const int c = (q * T + lane) * 4;
+      float a[8] = {acc_r[q].x, acc_r[q].y, acc_r[q].z, acc_r[q].w, acc_h[q].x, acc_h[q].y, acc_h[q].z, acc_h[q].w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        for (int o = 16; o >= T; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+        if (wl < T) atomicAdd(&sdb[(i >> 2) * gm.F + c + (i & 3)], a[i]);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < gm.F; c += kBT) {
+      atomicAdd(&dbias_res[c], sdb[c]);
+      if (HAS_GN && dbias_h2 != nullptr) atomicAdd(&dbias_h2[c], sdb[gm.F + c]);
     }
   }
 }
@@ -462,6 +519,18 @@ static int vecF(const DLTensor* t, long long n, const char* name, TView* v) {
   return B3D_OK;
 }
 
+static int p16_out(const DLTensor* twin_, const TView& x, P16Out* o) {
+  o->p = nullptr;
+  if (twin_ == nullptr) return B3D_OK;
+  P16View v;
+  B3D_TRY(view_p16(twin_, "twin", &v));
+  B3D_REQUIRE(x.ndim == 5 && v.B == x.shape[0] && v.D == x.shape[1] && v.H == x.shape[2] && v.W == x.shape[3] &&
+                  8 * v.C8 == x.shape[4], B3D_ERR_SHAPE, "twin: must be the [B, D, H, C/8, W, 8] form of the fp32 tensor");
+  B3D_REQUIRE((long long)v.D * v.H * v.W < (1LL << 32), B3D_ERR_UNSUPPORTED, "twin: sample too large");
+  o->p = (uint2*)v.p; o->W = (unsigned)v.W; o->C8 = (unsigned)v.C8; o->rows = (unsigned)(v.D * v.H); o->bf16 = v.bf16;
+  return B3D_OK;
+}
+
 }  // namespace b3d
 
 using namespace b3d;
@@ -504,17 +573,24 @@ extern "C" int b3d_se_fc_bwd(const DLTensor* gap_sum_, const DLTensor* w1_, cons
   return B3D_OK;
 }
 
-extern "C" int b3d_block_epilogue_fwd(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
-                                      const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
-                                      const DLTensor* chse_, DLTensor* out_, int groups, float eps, int has_gn,
-                                      void* stream) {
+static int block_fwd_impl(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
+                          const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
+                          const DLTensor* chse_, DLTensor* out_, DLTensor* out16_, int groups, float eps, int has_gn,
+                          void* stream) {
   TView res, h2, out, st, ga, be, wsp, ch;
   BlockGeom gm;
   int nchunks;
   B3D_TRY(view(res_, DT_F32, -1, false, "res", &res));
   B3D_TRY(view(h2_, DT_F32, -1, false, "h2", &h2));
-  B3D_TRY(view(out_, DT_F32, -1, false, "out", &out));
-  B3D_REQUIRE(res.numel == h2.numel && res.numel == out.numel, B3D_ERR_SHAPE, "block epilogue: size mismatch");
+  B3D_REQUIRE(out_ != nullptr || out16_ != nullptr, B3D_ERR_ARG, "block epilogue: no output");
+  out.p = nullptr;
+  if (out_ != nullptr) {
+    B3D_TRY(view(out_, DT_F32, -1, false, "out", &out));
+    B3D_REQUIRE(res.numel == out.numel, B3D_ERR_SHAPE, "block epilogue: size mismatch");
+  }
+  B3D_REQUIRE(res.numel == h2.numel, B3D_ERR_SHAPE, "block epilogue: size mismatch");
+  P16Out o16;
+  B3D_TRY(p16_out(out16_, res, &o16));
   B3D_TRY(block_geom(res, groups, has_gn != 0, &gm, &nchunks));
   B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
   B3D_TRY(vecF(chse_, res.shape[0] * gm.F, "chse", &ch));
@@ -526,14 +602,29 @@ extern "C" int b3d_block_epilogue_fwd(const DLTensor* res_, const DLTensor* h2_,
     B3D_TRY(vecF(beta_, gm.F, "beta", &be));
     B3D_NPL(gm.npl, (block_epilogue_fwd_kernel<true, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
         (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
-        (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps)));
+        (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps, o16)));
   } else {
     B3D_NPL(gm.npl, (block_epilogue_fwd_kernel<false, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
         (const float*)res.p, (const float*)h2.p, nullptr, nullptr, nullptr, (const float*)wsp.p,
-        (const float*)ch.p, (float*)out.p, gm, eps)));
+        (const float*)ch.p, (float*)out.p, gm, eps, o16)));
   }
   B3D_LAUNCH_CHECK("block_epilogue_fwd");
   return B3D_OK;
+}
+
+extern "C" int b3d_block_epilogue_fwd(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
+                                      const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
+                                      const DLTensor* chse_, DLTensor* out_, int groups, float eps, int has_gn,
+                                      void* stream) {
+  return block_fwd_impl(res_, h2_, stats_, gamma_, beta_, wsp_, chse_, out_, nullptr, groups, eps, has_gn, stream);
+}
+
+// out16: fp16 P16 twin of the block output for the convs that consume it; `out` may then be NULL
+extern "C" int b3d_block_epilogue_fwd_p16(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
+                                          const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
+                                          const DLTensor* chse_, DLTensor* out_, DLTensor* out16_, int groups,
+                                          float eps, int has_gn, void* stream) {
+  return block_fwd_impl(res_, h2_, stats_, gamma_, beta_, wsp_, chse_, out_, out16_, groups, eps, has_gn, stream);
 }
 
 extern "C" int b3d_block_epilogue_bwd_reduce(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,
@@ -581,41 +672,90 @@ extern "C" int b3d_block_epilogue_bwd_reduce(const DLTensor* dout_, const DLTens
   return B3D_OK;
 }
 
-extern "C" int b3d_block_epilogue_bwd_apply(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,
-                                            const DLTensor* stats_, const DLTensor* gamma_,
-                                            const DLTensor* beta_, const DLTensor* wsp_, const DLTensor* chse_,
-                                            const DLTensor* dgap_, const DLTensor* csum_, DLTensor* dres_,
-                                            DLTensor* dh2_, int groups, float eps, int has_gn, void* stream) {
+static int block_bwd_apply_impl(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,
+                                const DLTensor* stats_, const DLTensor* gamma_,
+                                const DLTensor* beta_, const DLTensor* wsp_, const DLTensor* chse_,
+                                const DLTensor* dgap_, const DLTensor* csum_, DLTensor* dres_,
+                                DLTensor* dh2_, DLTensor* dres16_, DLTensor* dh216_, DLTensor* dbias_res_,
+                                DLTensor* dbias_h2_, int groups, float eps, int has_gn, void* stream) {
   TView dout, res, h2, st, ga, be, wsp, ch, dg, cs, dres, dh2;
   BlockGeom gm;
   int nchunks;
   B3D_TRY(view(dout_, DT_F32, -1, false, "dout", &dout));
   B3D_TRY(view(res_, DT_F32, -1, false, "res", &res));
-  B3D_TRY(view(dres_, DT_F32, -1, false, "dres", &dres));
-  B3D_REQUIRE(res.numel == dout.numel && res.numel == dres.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+  B3D_REQUIRE(dres_ != nullptr || dres16_ != nullptr, B3D_ERR_ARG, "block epilogue bwd: no dres output");
+  dres.p = nullptr; dh2.p = nullptr;
+  if (dres_ != nullptr) {
+    B3D_TRY(view(dres_, DT_F32, -1, false, "dres", &dres));
+    B3D_REQUIRE(res.numel == dres.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+  }
+  B3D_REQUIRE(res.numel == dout.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+  P16Out r16, h16;
+  B3D_TRY(p16_out(dres16_, res, &r16));
+  B3D_TRY(p16_out(dh216_, res, &h16));
+  float *dbr = nullptr, *dbh = nullptr;
   B3D_TRY(block_geom(res, groups, has_gn != 0, &gm, &nchunks));
   B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
   B3D_TRY(vecF(chse_, res.shape[0] * gm.F, "chse", &ch));
   B3D_TRY(vecF(dgap_, res.shape[0] * gm.F, "dgap", &dg));
   cudaStream_t s = (cudaStream_t)stream;
+  if (dbias_res_ != nullptr) {
+    TView t;
+    B3D_TRY(vecF(dbias_res_, gm.F, "dbias_res", &t));
+    dbr = (float*)t.p;
+    B3D_TRY(cuda_ok(cudaMemsetAsync(dbr, 0, sizeof(float) * gm.F, s), "memset"));
+    if (dbias_h2_ != nullptr) {
+      B3D_TRY(vecF(dbias_h2_, gm.F, "dbias_h2", &t));
+      dbh = (float*)t.p;
+      B3D_TRY(cuda_ok(cudaMemsetAsync(dbh, 0, sizeof(float) * gm.F, s), "memset"));
+    }
+  }
+  const size_t smem = dbr != nullptr ? sizeof(float) * 2 * gm.F : 0;
   if (has_gn) {
     B3D_TRY(view(h2_, DT_F32, -1, false, "h2", &h2));
-    B3D_TRY(view(dh2_, DT_F32, -1, false, "dh2", &dh2));
-    B3D_REQUIRE(res.numel == h2.numel && res.numel == dh2.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+    B3D_REQUIRE(dh2_ != nullptr || dh216_ != nullptr, B3D_ERR_ARG, "block epilogue bwd: no dh2 output");
+    if (dh2_ != nullptr) {
+      B3D_TRY(view(dh2_, DT_F32, -1, false, "dh2", &dh2));
+      B3D_REQUIRE(res.numel == dh2.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+    }
+    B3D_REQUIRE(res.numel == h2.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
     B3D_TRY(view(stats_, DT_F64, -1, false, "stats", &st));
     B3D_TRY(view(csum_, DT_F64, -1, false, "csum", &cs));
     B3D_REQUIRE(st.numel == 2LL * nchunks && cs.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats/csum: wrong size");
     B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
     B3D_TRY(vecF(beta_, gm.F, "beta", &be));
-    B3D_NPL(gm.npl, (block_epilogue_bwd_apply_kernel<true, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+    B3D_NPL(gm.npl, (block_epilogue_bwd_apply_kernel<true, kN><<<block_grid(gm, nchunks), kBT, smem, s>>>(
         (const float*)dout.p, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p,
         (const float*)be.p, (const float*)wsp.p, (const float*)ch.p, (const float*)dg.p, (const double*)cs.p,
-        (float*)dres.p, (float*)dh2.p, gm, eps)));
+        (float*)dres.p, (float*)dh2.p, gm, eps, r16, h16, dbr, dbh)));
   } else {
-    B3D_NPL(gm.npl, (block_epilogue_bwd_apply_kernel<false, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+    B3D_NPL(gm.npl, (block_epilogue_bwd_apply_kernel<false, kN><<<block_grid(gm, nchunks), kBT, smem, s>>>(
         (const float*)dout.p, (const float*)res.p, nullptr, nullptr, nullptr, nullptr, (const float*)wsp.p,
-        (const float*)ch.p, (const float*)dg.p, nullptr, (float*)dres.p, nullptr, gm, eps)));
+        (const float*)ch.p, (const float*)dg.p, nullptr, (float*)dres.p, nullptr, gm, eps, r16, h16, dbr, nullptr)));
   }
   B3D_LAUNCH_CHECK("block_epilogue_bwd_apply");
   return B3D_OK;
+}
+
+extern "C" int b3d_block_epilogue_bwd_apply(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,
+                                            const DLTensor* stats_, const DLTensor* gamma_,
+                                            const DLTensor* beta_, const DLTensor* wsp_, const DLTensor* chse_,
+                                            const DLTensor* dgap_, const DLTensor* csum_, DLTensor* dres_,
+                                            DLTensor* dh2_, int groups, float eps, int has_gn, void* stream) {
+  return block_bwd_apply_impl(dout_, res_, h2_, stats_, gamma_, beta_, wsp_, chse_, dgap_, csum_, dres_, dh2_, nullptr,
+                              nullptr, nullptr, nullptr, groups, eps, has_gn, stream);
+}
+
+// dres16 / dh216 (nullable): bf16 P16 twins of the two gradients for the data / weight gradients of the pointwise and the
+// second 3x3x3 conv; dbias_res / dbias_h2 (nullable): their column sums = those convs' bias gradients.  dres / dh2 may be
+// NULL when only the twins are wanted.
+extern "C" int b3d_block_epilogue_bwd_apply_p16(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,
+                                                const DLTensor* stats_, const DLTensor* gamma_,
+                                                const DLTensor* beta_, const DLTensor* wsp_, const DLTensor* chse_,
+                                                const DLTensor* dgap_, const DLTensor* csum_, DLTensor* dres_,
+                                                DLTensor* dh2_, DLTensor* dres16_, DLTensor* dh216_,
+                                                DLTensor* dbias_res_, DLTensor* dbias_h2_, int groups, float eps,
+                                                int has_gn, void* stream) {
+  return block_bwd_apply_impl(dout_, res_, h2_, stats_, gamma_, beta_, wsp_, chse_, dgap_, csum_, dres_, dh2_, dres16_,
+                              dh216_, dbias_res_, dbias_h2_, groups, eps, has_gn, stream);
 }

@@ -20,7 +20,7 @@ int view(const DLTensor* t, int dtype, int ndim, bool allow_pitch, const char* n
               "%s: tensor must live on a CUDA device (device_type=%d); b3d has no CPU path", name,
               (int)t->device.device_type);
   static const struct { uint8_t code, bits; } kDT[] = {
-      {kDLFloat, 32}, {kDLFloat, 64}, {kDLInt, 64}, {kDLBfloat, 16}};
+      {kDLFloat, 32}, {kDLFloat, 64}, {kDLInt, 64}, {kDLBfloat, 16}, {kDLFloat, 16}};
   B3D_REQUIRE(t->dtype.code == kDT[dtype].code && t->dtype.bits == kDT[dtype].bits && t->dtype.lanes == 1,
               B3D_ERR_DTYPE, "%s: wrong dtype (code=%d bits=%d), expected code=%d bits=%d", name,
               (int)t->dtype.code, (int)t->dtype.bits, (int)kDT[dtype].code, (int)kDT[dtype].bits);
@@ -67,6 +67,21 @@ int view(const DLTensor* t, int dtype, int ndim, bool allow_pitch, const char* n
     out->pitch = pitch;
   }
   out->p = (char*)t->data + t->byte_offset;
+  return B3D_OK;
+}
+
+int view_p16(const DLTensor* t, const char* name, P16View* out) {
+  B3D_REQUIRE(t != nullptr, B3D_ERR_ARG, "%s: null tensor", name);
+  B3D_REQUIRE(t->dtype.bits == 16 && t->dtype.lanes == 1 && (t->dtype.code == kDLBfloat || t->dtype.code == kDLFloat),
+              B3D_ERR_DTYPE, "%s: P16 operands are fp16 or bf16", name);
+  TView v;
+  B3D_TRY(view(t, t->dtype.code == kDLBfloat ? DT_BF16 : DT_F16, 6, false, name, &v));
+  B3D_REQUIRE(v.shape[5] == 8, B3D_ERR_LAYOUT, "%s: P16 layout is [B, D, H, C/8, W, 8]", name);
+  B3D_REQUIRE(((uintptr_t)v.p & 15) == 0, B3D_ERR_LAYOUT, "%s: P16 operands must be 16-byte aligned", name);
+  out->p = v.p;
+  out->B = (int)v.shape[0]; out->D = (int)v.shape[1]; out->H = (int)v.shape[2]; out->C8 = (int)v.shape[3];
+  out->W = (int)v.shape[4];
+  out->bf16 = t->dtype.code == kDLBfloat ? 1 : 0;
   return B3D_OK;
 }
 

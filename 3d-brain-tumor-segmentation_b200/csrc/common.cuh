@@ -31,12 +31,22 @@ struct TView {
 };
 
 // dtype codes
-enum { DT_F32 = 0, DT_F64 = 1, DT_I64 = 2, DT_BF16 = 3 };
+enum { DT_F32 = 0, DT_F64 = 1, DT_I64 = 2, DT_BF16 = 3, DT_F16 = 4 };
 
 // Validates: CUDA device, dtype, ndim, and compact row-major strides; if allow_pitch, the last
 // dim may be a channel slice of a wider NDHWC buffer (stride[last]==1, outer strides compact
 // w.r.t. a pitch >= shape[last]).
 int view(const DLTensor* t, int dtype, int ndim, bool allow_pitch, const char* name, TView* out);
+
+// "P16" operand twin of an activation / gradient tensor: 16-bit [B, D, H, C/8, W, 8] — channel
+// octets as planes inside every (d, h) row, so that a halo row of one plane is W*16 contiguous bytes (wide TMA rows)
+// and a voxel's 8 channels are one 16-byte UMMA cell.  fp16 for forward activations, bf16 for gradients.
+struct P16View {
+  void* p = nullptr;
+  int B = 0, D = 0, H = 0, W = 0, C8 = 0;   // C = 8 * C8 channels
+  int bf16 = 0;                            // 1 = bf16, 0 = fp16
+};
+int view_p16(const DLTensor* t, const char* name, P16View* out);
 
 inline int cuda_ok(cudaError_t e, const char* what) {
   if (e != cudaSuccess) {

@@ -46,7 +46,8 @@ void fill_out(ConvGeom& g, const TView& y) {
 }
 
 int run(const ConvGeom& g, const TView& x, const TView& w, const float* bias, const TView& y,
-        const DLTensor* stats_, int groups, const DLTensor* gap_, const DLTensor* wpacked_, cudaStream_t s) {
+        const DLTensor* stats_, int groups, const DLTensor* gap_, const DLTensor* wpacked_, cudaStream_t s,
+        const TcSources* srcs = nullptr) {
   double* stats = nullptr;
   float* gap = nullptr;
   if (stats_ != nullptr) {
@@ -72,8 +73,9 @@ int run(const ConvGeom& g, const TView& x, const TView& w, const float* bias, co
     B3D_TRY(view(wpacked_, DT_F32, 1, false, "wpacked", &wp));
     B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "conv: shape not supported by the tcgen05 path");
     B3D_REQUIRE((size_t)wp.numel == tc_packed_weight_elems(g), B3D_ERR_SHAPE, "wpacked: wrong size");
-    return launch_conv_tc(g, (const float*)x.p, (const float*)wp.p, bias, (float*)y.p, stats, gap, s);
+    return launch_conv_tc(g, (const float*)x.p, (const float*)wp.p, bias, (float*)y.p, stats, gap, s, srcs);
   }
+  B3D_REQUIRE(srcs == nullptr, B3D_ERR_UNSUPPORTED, "conv (P16 operands): only the tcgen05 path (wpacked required)");
   return launch_conv_gather(g, (const float*)x.p, (const float*)w.p, bias, (float*)y.p, stats, gap, s);
 }
 
@@ -398,4 +400,172 @@ extern "C" int b3d_conv3d_pack_many(const DLTensor* jobs_, int njobs, long long 
   B3D_REQUIRE(njobs >= 0 && t.numel * 8 >= (long long)njobs * (long long)sizeof(PackJob), B3D_ERR_SHAPE,
               "pack_many: table too small");
   return launch_tc_pack_many((const PackJob*)t.p, njobs, blocks, (cudaStream_t)stream);
+}
+
+
+// ================================================================================================ P16 operand forms
+// The same three passes with the conv INPUT operands given as P16 twins (16-bit [B, D, H, C/8, W, 8], common.cuh) written
+// by the producing kernels: no conversion in the loaders (TMA boxes for stride-1 addressing), no cast passes before the
+// weight gradient, and channel concatenation (encoder.py:85,91, decoder.py:75) as a list of sources instead of a copy.
+namespace {
+
+int p16_sources(const DLTensor* const xs[4], TcSources* src, P16View* first, int* ctot) {
+  memset(src, 0, sizeof(*src));
+  *ctot = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (xs[i] == nullptr) break;
+    P16View v;
+    B3D_TRY(view_p16(xs[i], "x (P16)", &v));
+    if (i == 0) *first = v;
+    B3D_REQUIRE(v.B == first->B && v.D == first->D && v.H == first->H && v.W == first->W && v.bf16 == first->bf16,
+                B3D_ERR_SHAPE, "conv (P16): concatenated sources must agree in batch, space and type");
+    src->p[i] = v.p; src->C[i] = 8 * v.C8; src->n = i + 1;
+    *ctot += 8 * v.C8;
+  }
+  B3D_REQUIRE(src->n >= 1, B3D_ERR_ARG, "conv (P16): at least one source");
+  src->bf16 = first->bf16;
+  return B3D_OK;
+}
+
+// a TView standing for the (virtual) NDHWC tensor the P16 sources represent
+TView virtual_view(const P16View& v, int C) {
+  TView t;
+  t.p = v.p; t.ndim = 5;
+  t.shape[0] = v.B; t.shape[1] = v.D; t.shape[2] = v.H; t.shape[3] = v.W; t.shape[4] = C;
+  t.pitch = C; t.numel = (int64_t)v.B * v.D * v.H * v.W * C;
+  return t;
+}
+
+}  // namespace
+
+extern "C" int b3d_conv3d_fwd_p16(const DLTensor* x0_, const DLTensor* x1_, const DLTensor* x2_, const DLTensor* x3_,
+                                  const DLTensor* w_, const DLTensor* bias_, DLTensor* y_, int stride, int transposed,
+                                  int act, DLTensor* gn_stats_, int groups, DLTensor* gap_, int accumulate,
+                                  const DLTensor* wpacked_, void* stream) {
+  const DLTensor* xs[4] = {x0_, x1_, x2_, x3_};
+  TcSources src;
+  P16View first;
+  int ctot;
+  B3D_TRY(p16_sources(xs, &src, &first, &ctot));
+  TView w, y;
+  int k;
+  B3D_TRY(view(y_, DT_F32, 5, true, "y", &y));
+  B3D_TRY(weight_view(w_, &w, &k));
+  B3D_REQUIRE(stride == 1 || (stride == 2 && k == 3), B3D_ERR_UNSUPPORTED, "conv: stride must be 1, or 2 with k=3");
+  B3D_REQUIRE(!transposed || stride == 2, B3D_ERR_UNSUPPORTED, "conv-transpose: only k=3 stride=2");
+  B3D_REQUIRE(wpacked_ != nullptr, B3D_ERR_ARG, "conv (P16): packed weights required (tcgen05 path only)");
+  const TView x = virtual_view(first, ctot);
+  ConvGeom g;
+  B3D_TRY(geom_fwd(g, x, w, y, k, stride, transposed));
+  g.act = act; g.accumulate = accumulate; g.groups = groups;
+  const float* bias;
+  B3D_TRY(bias_ptr(bias_, g.Cout, &bias));
+  return run(g, x, w, bias, y, gn_stats_, groups, gap_, wpacked_, (cudaStream_t)stream, &src);
+}
+
+extern "C" int b3d_conv3d_dgrad_p16(const DLTensor* dy_, const DLTensor* w_, DLTensor* dx_, int stride, int transposed,
+                                    int accumulate, const DLTensor* wpacked_, void* stream) {
+  const DLTensor* xs[4] = {dy_, nullptr, nullptr, nullptr};
+  TcSources src;
+  P16View first;
+  int ctot;
+  B3D_TRY(p16_sources(xs, &src, &first, &ctot));
+  TView w, dx;
+  int k;
+  B3D_TRY(view(dx_, DT_F32, 5, true, "dx", &dx));
+  B3D_TRY(weight_view(w_, &w, &k));
+  B3D_REQUIRE(stride == 1 || (stride == 2 && k == 3), B3D_ERR_UNSUPPORTED, "conv: stride must be 1, or 2 with k=3");
+  B3D_REQUIRE(wpacked_ != nullptr, B3D_ERR_ARG, "conv (P16): packed weights required (tcgen05 path only)");
+  const TView dy = virtual_view(first, ctot);
+  ConvGeom g;
+  B3D_TRY(geom_dgrad(g, dy, w, dx, k, stride, transposed));
+  g.accumulate = accumulate;
+  return run(g, dy, w, nullptr, dx, nullptr, 1, nullptr, wpacked_, (cudaStream_t)stream, &src);
+}
+
+// How the P16 weight gradient of a layer runs: 0 = not on this path (narrow layers, odd channel counts), 1 = straight
+// from the operands, 2 = needs a 16-bit scratch of numel(big tensor) elements (stride-2 family: space-to-depth copy),
+// 3 = needs a 16-bit scratch of numel(dy) elements (TS-mode kernel: voxel-transposed dy).  `w_sp` = W of dy.
+extern "C" int b3d_conv3d_wgrad_p16_plan(int k, int stride, int transposed, int cin, int cout, int w_sp) {
+  const WgradPlan p = wgrad_plan(k, stride, transposed, cin, cout);
+  if (p.kind != 1 || cin % 8 != 0 || cout % 8 != 0) return 0;
+  if (stride == 2) return 2;
+  WgradGeom wg;
+  memset(&wg, 0, sizeof(wg));
+  wg.k = k; wg.s = 1; wg.nA = cin; wg.nB = cout; wg.bigp = cin; wg.smallp = cout; wg.Ws = w_sp;
+  return (g_wgrad_ts && tc_wgrad_ts_supported(wg)) ? 3 : 1;
+}
+
+// dw of a Conv3D (x = layer input, up to 4 concatenated P16 sources; dy = P16 gradient of the output) or of a
+// Conv3DTranspose (transposed = 1: single source).  The bias gradient is NOT produced here: on this path it is emitted
+// by the kernel that writes dy (b3d_gn_bwd_apply / b3d_block_epilogue_bwd_apply, `dbias`).
+extern "C" int b3d_conv3d_wgrad_p16(const DLTensor* x0_, const DLTensor* x1_, const DLTensor* x2_, const DLTensor* x3_,
+                                    const DLTensor* dy_, DLTensor* dw_, int stride, int transposed, DLTensor* scratch_,
+                                    void* stream) {
+  const DLTensor* xs[4] = {x0_, x1_, x2_, x3_};
+  TcSources src;
+  P16View xf, dy;
+  int cin;
+  B3D_TRY(p16_sources(xs, &src, &xf, &cin));
+  B3D_TRY(view_p16(dy_, "dy (P16)", &dy));
+  TView dw;
+  int k;
+  B3D_TRY(weight_view(dw_, &dw, &k));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int cout = 8 * dy.C8;
+  B3D_REQUIRE(!transposed || src.n == 1, B3D_ERR_UNSUPPORTED, "wgrad (P16): conv-transpose takes one source");
+  const int plan = b3d_conv3d_wgrad_p16_plan(k, stride, transposed, cin, cout, dy.W);
+  B3D_REQUIRE(plan != 0, B3D_ERR_UNSUPPORTED, "wgrad (P16): layer not on this path (k=%d s=%d %d->%d)", k, stride, cin, cout);
+  const P16View& big = transposed ? dy : xf;
+  const P16View& sml = transposed ? xf : dy;
+  const int cbig = transposed ? cout : cin, csml = transposed ? cin : cout;
+  B3D_REQUIRE(dw.shape[3] == cbig && dw.shape[4] == csml, B3D_ERR_SHAPE, "wgrad (P16): dw channel dims");
+  B3D_REQUIRE(big.B == sml.B && big.D == stride * sml.D && big.H == stride * sml.H && big.W == stride * sml.W,
+              B3D_ERR_SHAPE, "wgrad (P16): spatial dims");
+  WgradGeom wg;
+  memset(&wg, 0, sizeof(wg));
+  wg.B = big.B; wg.Db = big.D; wg.Hb = big.H; wg.Wb = big.W; wg.nA = cbig;
+  wg.Ds = sml.D; wg.Hs = sml.H; wg.Ws = sml.W; wg.nB = csml;
+  wg.k = k; wg.s = stride; wg.pad = stride == 1 ? k / 2 : 0;
+  wg.bigp = cbig; wg.smallp = csml;
+  void* scratch = nullptr;
+  long long scratch_n = 0;
+  if (scratch_ != nullptr) {
+    TView sc;
+    B3D_TRY(view(scratch_, scratch_->dtype.code == kDLBfloat ? DT_BF16 : DT_F16, -1, false, "scratch", &sc));
+    scratch = sc.p; scratch_n = sc.numel;
+    B3D_REQUIRE(((uintptr_t)scratch & 15) == 0, B3D_ERR_LAYOUT, "scratch: alignment");
+  }
+  WgP16 wp;
+  memset(&wp, 0, sizeof(wp));
+  wp.small = sml.p; wp.small_bf16 = sml.bf16; wp.big_bf16 = big.bf16;
+  if (plan == 2) {
+    const long long need = (long long)big.B * big.D * big.H * big.W * cbig;
+    B3D_REQUIRE(scratch != nullptr && scratch_n >= need, B3D_ERR_ARG, "wgrad (P16, stride 2): scratch of %lld elements", need);
+    int c8off = 0;
+    const int c8tot = cbig / 8;
+    if (transposed) {
+      B3D_TRY(launch_p16_s2d(big.p, scratch, big.B, sml.D, sml.H, sml.W, big.C8, 0, c8tot, s));
+    } else {
+      for (int i = 0; i < src.n; ++i) {
+        B3D_TRY(launch_p16_s2d(src.p[i], scratch, big.B, sml.D, sml.H, sml.W, src.C[i] / 8, c8off, c8tot, s));
+        c8off += src.C[i] / 8;
+      }
+    }
+    wp.n = 1; wp.big[0] = scratch; wp.C[0] = 8 * cbig;
+    return launch_conv_wgrad_tc(wg, scratch, sml.p, (float*)dw.p, s, 0, 0, 0, &wp);
+  }
+  if (plan == 3) {
+    const long long need = (long long)dy.B * dy.D * dy.H * dy.W * cout;
+    B3D_REQUIRE(scratch != nullptr && scratch_n >= need, B3D_ERR_ARG, "wgrad (P16, TS): scratch of %lld elements", need);
+    B3D_REQUIRE(src.n == 1, B3D_ERR_UNSUPPORTED, "wgrad (P16, TS): one source");
+    B3D_TRY(launch_p16_t8(dy.p, scratch, (long long)dy.B * dy.D * dy.H, dy.W, dy.C8, s));
+    return launch_conv_wgrad_ts(wg, xf.p, scratch, (float*)dw.p, s, 1, xf.bf16 ? 0 : 1);
+  }
+  if (transposed) { wp.n = 1; wp.big[0] = big.p; wp.C[0] = cbig; }
+  else {
+    wp.n = src.n;
+    for (int i = 0; i < src.n; ++i) { wp.big[i] = src.p[i]; wp.C[i] = src.C[i]; }
+  }
+  return launch_conv_wgrad_tc(wg, big.p, sml.p, (float*)dw.p, s, 0, 0, 0, &wp);
 }

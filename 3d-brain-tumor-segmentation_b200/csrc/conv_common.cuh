@@ -36,8 +36,16 @@ int launch_colsum(const float* x, float* out, long long N, int C, long long pitc
 
 // tcgen05 path (conv_tc.cu).  Returns true when the shape is handled there.
 bool tc_conv_supported(const ConvGeom& cg);
+// P16 input operand of the tcgen05 conv: up to 4 source tensors [B, Di, Hi, C_i/8, Wi, 8] (16-bit) whose channels are
+// concatenated virtually (encoder.py:85,91 / decoder.py:75 without a copy); all fp16 (forward) or all bf16 (backward)
+struct TcSources {
+  int n;
+  const void* p[4];
+  int C[4];
+  int bf16;
+};
 int launch_conv_tc(const ConvGeom& cg, const float* x, const float* wpacked, const float* bias, float* y,
-                   double* stats, float* gap, cudaStream_t s);
+                   double* stats, float* gap, cudaStream_t s, const TcSources* srcs = nullptr);
 size_t tc_packed_weight_elems(const ConvGeom& cg);
 int launch_pack_s2(const ConvGeom& cg, const float* w, float* wpacked, int op, cudaStream_t s);
 int launch_tc_pack_weights(const ConvGeom& cg, const float* w, float* wpacked, cudaStream_t s);
@@ -92,11 +100,24 @@ int tc_operand_type(const ConvGeom& g);   // OP_* the tcgen05 conv will use for 
 int tc_pick_n(int Cout);               // N tile of the tcgen05 conv for this output-channel count
 
 bool tc_wgrad_supported(const WgradGeom& wg);
+// P16 operands of the weight gradient: `big` = up to 4 sources concatenating to the big tensor's channels (for the
+// stride-2 family: ONE coarse space-to-depth tensor, launch_p16_s2d), `small` = one tensor
+struct WgP16 {
+  int n;
+  const void* big[4];
+  int C[4];
+  int big_bf16;
+  const void* small;
+  int small_bf16;
+};
 int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x_bf16, const void* dy_bf16, float* dw, cudaStream_t s,
-                         int rows_real = 0, int tr_cn = 0, long long dw_elems = 0);
+                         int rows_real = 0, int tr_cn = 0, long long dw_elems = 0, const WgP16* p16 = nullptr);
+int launch_p16_s2d(const void* src, void* dst, int B, int D, int H, int W, int C8, int c8off, int C8tot, cudaStream_t s);
+int launch_p16_t8(const void* src, void* dst, long long rows, int W, int C8, cudaStream_t s);
 // TS-mode weight gradient for narrow outputs (conv_tc_wgrad_ts.cu)
 bool tc_wgrad_ts_supported(const WgradGeom& wg);
-int launch_conv_wgrad_ts(const WgradGeom& wg, const void* x_bf16, const void* dyT_bf16, float* dw, cudaStream_t s);
+int launch_conv_wgrad_ts(const WgradGeom& wg, const void* x_bf16, const void* dyT_bf16, float* dw, cudaStream_t s,
+                         int x_p16 = 0, int x_f16 = 0);
 int launch_cast_bf16_t8(const float* src, void* dst, long long nvox, int C, float* colsum, cudaStream_t s);
 int launch_cast_stack_bf16(const float* src, void* dst, int B, int D, int H, int W, int Cn, long long pitch, int k,
                            int sgn, int nA, cudaStream_t s);

@@ -53,9 +53,14 @@ struct TcCfg {
   static constexpr int TAPS = KS * KS * KS;
   static constexpr int TH = 16, TW = 8 * NW, P = TD * NW;
   static constexpr int HD = TD + KS - 1, HH = TH + KS - 1, HW = TW + KS - 1;
-  static constexpr int NVC = HD * HH * HW;            // cells per plane
-  static constexpr int PLANE_BYTES = ((NVC * 16 + 127) / 128) * 128;
-  static constexpr int HALO_BYTES = 2 * PLANE_BYTES;
+  static constexpr int NVC = HD * HH * HW;            // halo voxels (cells per plane)
+  // halo stage in shared memory: [HD][HH][2 planes][HW] 16-byte cells — the two channel octets of a K chunk sit side
+  // by side inside every (d, h) row, which is exactly what ONE 5-D TMA box {8*HW, 2, HH, HD, 1} of a P16 operand
+  // delivers; the thread loader writes the same layout.  UMMA: LBO (K direction = plane) = HW cells, SBO (next 8-row
+  // group = next h row) = RP cells; a tap (kd, kh, kw) is a start-address offset of ((kd*HH + kh)*RP + kw) cells.
+  static constexpr int RP = 2 * HW;                   // row pitch in cells
+  static constexpr int HALO_TX = HD * HH * RP * 16;   // bytes one TMA box writes
+  static constexpr int HALO_BYTES = ((HALO_TX + 127) / 128) * 128;
   static constexpr int TAP_BYTES = 2 * N * 16;        // B tile of one tap: 2 planes x N rows x 16 B
   static constexpr int TPS = KS * KS;                 // taps per weight stage (one kd slab; 1 for 1x1x1;
                                                       // FOLD: one kh row = 3 (kh, kw) tiles of 3N rows)
@@ -100,6 +105,18 @@ struct TcParams {
   // slice); conv_finish_kernel then sums the slices and applies bias / statistics / GAP
   int ksplit, kchunks;
   long long ws_slice;
+  // P16 input operand (16-bit [B, D, H, C/8, W, 8] twins, see common.cuh): x16 = 1 -> `src` holds up to 4 source
+  // tensors whose channels are concatenated virtually (K chunk -> source by `cend`, the cumulative channel ends);
+  // tma = 1 -> the halo of a chunk is fetched by one TMA box from the source's tensor map (stride-1 addressing),
+  // otherwise (space-to-depth addressing of the stride-2 family) by the loader warps with 16-byte loads.
+  int x16, tma, nsrc;
+  const void* src[4];
+  int cend[4];         // cumulative channel count after source i (of the concatenated input)
+  int sc8[4];          // channel octets (planes) of source i
+};
+
+struct alignas(64) TcMaps {
+  CUtensorMap m[4];
 };
 
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -163,7 +180,7 @@ constexpr int kMmaWarps = 1;
 constexpr int kTcThreads = (4 + kLoaderWarps + 2 + (kMmaWarps - 1)) * 32;   // 4 epilogue + loaders + MMA + weights + MMA
 
 template <class C>
-__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams prm) {
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams prm, const __grid_constant__ TcMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* halo = smem;
   uint8_t* wst = smem + C::HS * C::HALO_BYTES;
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
   const int nsp = blockIdx.y;  // N split
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::HS; ++i) { mbar_init(smem_u32(&halo_full[i]), kLoaderWarps * 32); mbar_init(smem_u32(&halo_empty[i]), kMmaWarps); }
+    for (int i = 0; i < C::HS; ++i) { mbar_init(smem_u32(&halo_full[i]), prm.tma ? 1 : kLoaderWarps * 32); mbar_init(smem_u32(&halo_empty[i]), kMmaWarps); }
     for (int i = 0; i < C::WS; ++i) { mbar_init(smem_u32(&w_full[i]), 1); mbar_init(smem_u32(&w_empty[i]), kMmaWarps); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), kMmaWarps); mbar_init(smem_u32(&acc_empty[i]), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -198,7 +215,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 4 + kLoaderWarps) {
+  if (warp >= 4 && warp < 4 + kLoaderWarps && prm.tma) {
+    // ============ operand loader, TMA form: one elected thread fetches the halo of every K chunk as ONE 5-D box
+    // {8*HW, 2 planes, HH, HD, 1} of the source's P16 tensor map (zero fill outside the volume = TF 'SAME' padding)
+    if (warp == 4 && lane == 0) {
+      int hs = 0, hph = 0;
+      for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int wt = t % prm.ntw; t /= prm.ntw;
+        const int ht = t % prm.nth; t /= prm.nth;
+        const int dt = t % prm.ntd; t /= prm.ntd;
+        const int b = t;
+        const int w0 = wt * C::TW - C::HB, h0 = ht * C::TH - C::HB, d0 = dt * C::TD - C::HB + prm.doff;
+        for (int c = 0; c < nchunks; ++c) {
+          const int ch0 = (c_begin + c) * C::CK;                 // first channel of the chunk in the concatenated input
+          int si = 0;
+          while (si + 1 < prm.nsrc && ch0 >= prm.cend[si]) ++si;
+          const int pl = (ch0 - (si > 0 ? prm.cend[si - 1] : 0)) >> 3;
+          mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
+          const uint32_t full = smem_u32(&halo_full[hs]);
+          mbar_expect_tx(full, C::HALO_TX);
+          tma_load_5d(smem_u32(halo + hs * C::HALO_BYTES), &maps.m[si], 8 * w0, pl, h0, d0, b, full);
+          if (++hs == C::HS) { hs = 0; hph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + kLoaderWarps) {
     // ============ operand loaders: global fp32 -> (bf16|tf32) cells in shared memory ============
     const int lw = warp - 4;
     int hs = 0, hph = 0;
@@ -213,19 +255,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
         uint8_t* dst0 = halo + hs * C::HALO_BYTES;
-        uint8_t* dst1 = dst0 + C::PLANE_BYTES;
         const int cg = c_begin + c;              // global K-chunk index
         const float* xc = xb + cg * C::CK;
         int sp_d = 0, sp_h = 0, sp_w = 0;      // s2d: parity of this chunk's channels
+        int chv = cg * C::CK;                  // first (virtual) channel of the chunk inside the source tensor(s)
         if (prm.s2d) {
           const int par = (cg * C::CK) / prm.Csub;
-          xc = xb + (cg * C::CK) % prm.Csub;
+          chv = (cg * C::CK) % prm.Csub;
+          xc = xb + chv;
           sp_d = par >> 2; sp_h = (par >> 1) & 1; sp_w = par & 1;
         }
-        // one lane = one halo voxel: the whole CK-channel chunk is fetched with 256-bit loads (full 32-byte
-        // sectors), converted, and written as one 16-byte cell per plane (a warp stores 512 contiguous bytes)
         constexpr int kVoxPerPass = kLoaderWarps * 32;
         constexpr int kUnroll = 4;
+        if (C::BF16 && prm.x16) {
+          // P16 source (16-bit twins, possibly a virtual concat of several tensors): a voxel's chunk is two 16-byte
+          // cells one plane (W cells) apart; no conversion
+          int si = 0;
+          while (si + 1 < prm.nsrc && chv >= prm.cend[si]) ++si;
+          const int pl = (chv - (si > 0 ? prm.cend[si - 1] : 0)) >> 3, c8 = prm.sc8[si];
+          const int fs = prm.s2d ? 2 : 1;
+          const long long Hf = (long long)prm.H * fs, Wf = (long long)prm.W * fs;
+          const uint4* xs = reinterpret_cast<const uint4*>(prm.src[si]) + (long long)b * prm.Din * Hf * c8 * Wf;
+          for (int v0 = lw * 32 + lane; v0 < C::NVC; v0 += kVoxPerPass * kUnroll) {
+            uint4 q[kUnroll][2];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+              const int v = v0 + u * kVoxPerPass;
+              const int cw = v % C::HW, q2 = v / C::HW;
+              const int ch = q2 % C::HH, cd = q2 / C::HH;
+              const int gd = d0 + cd, gh = h0 + ch, gw = w0 + cw;
+              const int bd = (prm.s2d ? 2 * gd + sp_d : gd) + prm.doff;
+              const bool ok = v < C::NVC && bd >= 0 && bd < prm.Din && gh >= 0 && gh < prm.H && gw >= 0 && gw < prm.W;
+              q[u][0] = q[u][1] = make_uint4(0u, 0u, 0u, 0u);
+              if (ok) {
+                const long long hh = prm.s2d ? 2 * gh + sp_h : gh, ww = prm.s2d ? 2 * gw + sp_w : gw;
+                const uint4* sp = xs + (((long long)bd * Hf + hh) * c8 + pl) * Wf + ww;
+                q[u][0] = __ldg(sp);
+                q[u][1] = __ldg(sp + Wf);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+              const int v = v0 + u * kVoxPerPass;
+              if (v < C::NVC) {
+                const int cw = v % C::HW, row = v / C::HW;
+                uint8_t* d = dst0 + (row * C::RP + cw) * 16;
+                *reinterpret_cast<uint4*>(d) = q[u][0];
+                *reinterpret_cast<uint4*>(d + C::HW * 16) = q[u][1];
+              }
+            }
+          }
+        } else {
+        // one lane = one halo voxel: the whole CK-channel chunk is fetched with 256-bit loads (full 32-byte
+        // sectors), converted, and written as one 16-byte cell per plane (a warp stores 512 contiguous bytes)
         constexpr int kRegs = C::BF16 ? 16 : 8;
         for (int v0 = lw * 32 + lane; v0 < C::NVC; v0 += kVoxPerPass * kUnroll) {
           float r[kUnroll][kRegs];
@@ -269,10 +351,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
                 o1.x = __float_as_uint(r[u][4]); o1.y = __float_as_uint(r[u][5]);
                 o1.z = __float_as_uint(r[u][6]); o1.w = __float_as_uint(r[u][7]);
               }
-              *reinterpret_cast<uint4*>(dst0 + v * 16) = o0;
-              *reinterpret_cast<uint4*>(dst1 + v * 16) = o1;
+              const int cw = v % C::HW, row = v / C::HW;
+              uint8_t* d = dst0 + (row * C::RP + cw) * 16;
+              *reinterpret_cast<uint4*>(d) = o0;
+              *reinterpret_cast<uint4*>(d + C::HW * 16) = o1;
             }
           }
+        }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> UMMA reads
         mbar_arrive(smem_u32(&halo_full[hs]));
@@ -315,7 +400,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(smem_u32(&halo_full[hs]), hph);
         tc_fence_after();
-        const uint64_t adesc0 = make_desc(halo_addr + hs * C::HALO_BYTES, C::PLANE_BYTES, C::HW * 16);
+        const uint64_t adesc0 = make_desc(halo_addr + hs * C::HALO_BYTES, C::HW * 16, C::RP * 16);
 #pragma unroll
         for (int st = 0; st < C::TAPS / C::TPS; ++st) {
           mbar_wait(smem_u32(&w_full[ws]), wph);
@@ -326,17 +411,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
               // stage st = kernel row kh; per (kh, kw) one B tile of 3N rows [kd=2 | kd=1 | kd=0]
               const int kh = st;
               constexpr uint32_t idesc_hi = (1u << 4) | ((128u >> 4) << 24);
+              constexpr int kFoldG0 = (C::HD + 2) / 3, kFoldG1 = (C::HD + 1) / 3;      // slices = 0, 1 (mod 3)
               const uint32_t idf = idesc_hi | (fmt << 7) | (fmt << 10);
               const uint32_t id3 = idf | ((uint32_t)(3 * C::N >> 3) << 17), id2 = idf | ((uint32_t)(2 * C::N >> 3) << 17);
 #pragma unroll
               for (int kw = 0; kw < 3; ++kw) {
                 const uint64_t bdesc = bdesc0 + (uint64_t)(kw * (3 * C::TAP_BYTES >> 4));
                 const bool first = c == 0 && st == 0 && kw == 0;
+                // issue order: an MMA writes the accumulator blocks zi .. zi+2, so slices zi, zi+1 overlap in two of
+                // them and back-to-back issue would chain every MMA on the completion of the previous one; walking the
+                // slices with stride 3 (0,3,6,.. 1,4,7,.. 2,5,8,..) makes consecutive MMAs touch disjoint blocks.  The
+                // very first step of a tile keeps the natural order: it also INITIALISES block zi+2 (accumulate = 0)
+                // before slices zi+1, zi+2 add to it.
 #pragma unroll
-                for (int zi = 0; zi < C::HD; ++zi) {
+                for (int zj = 0; zj < C::HD; ++zj) {
+                  const int zi = first ? zj : (zj < kFoldG0 ? 3 * zj : (zj < kFoldG0 + kFoldG1 ? 3 * (zj - kFoldG0) + 1
+                                                                                              : 3 * (zj - kFoldG0 - kFoldG1) + 2));
 #pragma unroll
                   for (int pw = 0; pw < C::NW; ++pw) {
-                    const uint32_t aoff = (uint32_t)((zi * C::HH + kh) * C::HW + pw * 8 + kw);
+                    const uint32_t aoff = (uint32_t)((zi * C::HH + kh) * C::RP + pw * 8 + kw);
                     const uint32_t dcol = dbase + (uint32_t)((pw * (C::TD + 4) + zi) * C::N);   // blocks of pd = zi-2..zi
                     if (!first) {
                       tc_mma_f16(dcol, adesc0 + aoff, bdesc, id3, 1u);
@@ -358,7 +451,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
               for (int p = 0; p < C::P; ++p) {
                 if ((p % kMmaWarps) != mw) continue;
                 const int pd = p / C::NW, pw = p % C::NW;
-                const uint32_t aoff = (uint32_t)(((pd + kd) * C::HH + kh) * C::HW + pw * 8 + kw);
+                const uint32_t aoff = (uint32_t)(((pd + kd) * C::HH + kh) * C::RP + pw * 8 + kw);
                 if (C::BF16) tc_mma_f16(dbase + p * C::N, adesc0 + aoff, bdesc, idesc, acc);
                 else tc_mma_tf32(dbase + p * C::N, adesc0 + aoff, bdesc, idesc, acc);
               }
@@ -796,11 +889,51 @@ static float* splitk_workspace(cudaStream_t s) {
   return ws[dev];
 }
 
+// tensor map of a P16 operand [B, D, H, C/8, W, 8] for boxes {8*bw, planes, bh, bd, 1}: dims (W*8, C/8, H, D, B)
+int make_p16_map(CUtensorMap* tm, const void* base, int bf16, int B, int D, int H, int W, int C8, int bw, int planes,
+                 int bh, int bd) {
+  EncodeTiledFn enc = tma_encode_fn();
+  B3D_REQUIRE(enc != nullptr, B3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  B3D_REQUIRE(8 * bw <= 256 && planes <= 256 && bh <= 256 && bd <= 256, B3D_ERR_UNSUPPORTED, "P16 map: box too large");
+  const cuuint64_t row = (cuuint64_t)W * 16;
+  const cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)C8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  const cuuint64_t strides[4] = {row, row * C8, row * C8 * H, row * C8 * H * D};
+  const cuuint32_t box[5] = {(cuuint32_t)(8 * bw), (cuuint32_t)planes, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)base,
+                         dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B3D_REQUIRE(r == CUDA_SUCCESS, B3D_ERR_CUDA, "cuTensorMapEncodeTiled(P16) failed (%d)", (int)r);
+  return B3D_OK;
+}
+
 template <class C>
 static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, const float* wp, const float* bias,
-                      float* y, double* stats, float* gap, cudaStream_t s) {
+                      float* y, double* stats, float* gap, cudaStream_t s, const TcSources* srcs) {
   TcParams p;
   memset(&p, 0, sizeof(p));
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (srcs != nullptr) {
+    if constexpr (!C::BF16) {
+      set_error("tcgen05 conv: P16 operands need a 16-bit operand type");
+      return B3D_ERR_UNSUPPORTED;
+    } else {
+      B3D_REQUIRE((C::OP == OP_BF16) == (srcs->bf16 != 0), B3D_ERR_DTYPE,
+                  "tcgen05 conv: P16 operand type (%s) does not match the pass's MMA operand type",
+                  srcs->bf16 ? "bf16" : "fp16");
+      p.x16 = 1; p.nsrc = srcs->n; p.tma = q.s2d ? 0 : 1;
+      int cum = 0;
+      for (int i = 0; i < srcs->n; ++i) {
+        B3D_REQUIRE(srcs->C[i] % 16 == 0, B3D_ERR_UNSUPPORTED, "tcgen05 conv: P16 sources need channels %% 16 == 0");
+        cum += srcs->C[i];
+        p.src[i] = srcs->p[i]; p.cend[i] = cum; p.sc8[i] = srcs->C[i] / 8;
+        if (p.tma)
+          B3D_TRY(make_p16_map(&maps.m[i], srcs->p[i], srcs->bf16, g.B, g.Di, g.Hi, g.Wi, srcs->C[i] / 8, C::HW, 2, C::HH,
+                               C::HD));
+      }
+    }
+  }
   p.x = x; p.wp = wp; p.bias = bias; p.y = y; p.stats = stats; p.gap = gap;
   p.B = g.B; p.D = q.D; p.H = q.H; p.W = q.W; p.Cin = q.Cin; p.Cout = q.Cout; p.xp = g.xp; p.yp = g.yp;
   p.ntd = (q.D + C::TD - 1) / C::TD; p.nth = (q.H + C::TH - 1) / C::TH; p.ntw = (q.W + C::TW - 1) / C::TW;
@@ -844,7 +977,7 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
     p.bias = nullptr; p.stats = nullptr; p.gap = nullptr;
     p.y = ws; p.ws_slice = out_elems;
   }
-  conv_tc_kernel<C><<<grid, kTcThreads, C::SMEM, s>>>(p);
+  conv_tc_kernel<C><<<grid, kTcThreads, C::SMEM, s>>>(p, maps);
   B3D_LAUNCH_CHECK("conv_tc");
   if (p.ksplit > 1) {
     const int G = stats != nullptr ? (g.groups > 0 ? g.groups : 1) : 8;
@@ -858,19 +991,19 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
 
 template <int KS, int HB, int BF16>
 static int dispatch_n(const ConvGeom& g, const TcProblem& q, const float* x, const float* wp, const float* bias,
-                      float* y, double* stats, float* gap, cudaStream_t s) {
+                      float* y, double* stats, float* gap, cudaStream_t s, const TcSources* srcs) {
   const int n = pick_n(q.Cout);
   if constexpr (KS == 3 && HB == 1 && BF16 != OP_TF32) {
     if (use_fold(g)) {
-      if (n == 16) return launch_cfg<TcCfg<16, 8, 1, KS, HB, BF16, 1>>(g, q, x, wp, bias, y, stats, gap, s);
-      return launch_cfg<TcCfg<32, 4, 1, KS, HB, BF16, 1>>(g, q, x, wp, bias, y, stats, gap, s);
+      if (n == 16) return launch_cfg<TcCfg<16, 8, 1, KS, HB, BF16, 1>>(g, q, x, wp, bias, y, stats, gap, s, srcs);
+      return launch_cfg<TcCfg<32, 4, 1, KS, HB, BF16, 1>>(g, q, x, wp, bias, y, stats, gap, s, srcs);
     }
   }
-  if (n == 128) return launch_cfg<TcCfg<128, 2, 1, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s);
+  if (n == 128) return launch_cfg<TcCfg<128, 2, 1, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s, srcs);
   if constexpr (!(KS == 2 && HB == 1)) {   // the depth-to-space form always has N = 8*Cp = multiple of 128
-    if (n == 64) return launch_cfg<TcCfg<64, 2, 2, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s);
-    if (n == 32) return launch_cfg<TcCfg<32, 4, 2, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s);
-    return launch_cfg<TcCfg<16, 4, 2, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s);
+    if (n == 64) return launch_cfg<TcCfg<64, 2, 2, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s, srcs);
+    if (n == 32) return launch_cfg<TcCfg<32, 4, 2, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s, srcs);
+    return launch_cfg<TcCfg<16, 4, 2, KS, HB, BF16>>(g, q, x, wp, bias, y, stats, gap, s, srcs);
   }
   set_error("tcgen05 conv: unexpected N tile");
   return B3D_ERR_UNSUPPORTED;
@@ -879,11 +1012,11 @@ static int dispatch_n(const ConvGeom& g, const TcProblem& q, const float* x, con
 // conv on the tensor cores with pre-packed weights: stride-1 k in {1,3}; stride-2 family (mode DOWN / UP) as a
 // 2x2x2 stride-1 conv over the coarse grid with space-to-depth input / depth-to-space output addressing
 int launch_conv_tc(const ConvGeom& g, const float* x, const float* wp, const float* bias, float* y, double* stats,
-                   float* gap, cudaStream_t s) {
+                   float* gap, cudaStream_t s, const TcSources* srcs) {
   B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "conv: shape not supported by the tcgen05 path");
   B3D_REQUIRE(g.act == 0 || (g.act == 1 && g.mode == CONV_S1), B3D_ERR_UNSUPPORTED,
               "tcgen05 conv: only the sigmoid epilogue of stride-1 convs is built");
-  B3D_REQUIRE(g.Cin < 8 || (g.xp % 8 == 0 && ((uintptr_t)x & 31) == 0), B3D_ERR_LAYOUT,
+  B3D_REQUIRE(srcs != nullptr || g.Cin < 8 || (g.xp % 8 == 0 && ((uintptr_t)x & 31) == 0), B3D_ERR_LAYOUT,
               "tcgen05 conv: x must be 32-byte aligned with a channel pitch multiple of 8");
   B3D_REQUIRE(g.Cout < 16 || (g.yp % 4 == 0 && ((uintptr_t)y & 15) == 0), B3D_ERR_LAYOUT,
               "tcgen05 conv: y must be 16-byte aligned with a channel pitch multiple of 4");
@@ -892,9 +1025,9 @@ int launch_conv_tc(const ConvGeom& g, const float* x, const float* wp, const flo
   B3D_REQUIRE(gap == nullptr || g.mode == CONV_S1, B3D_ERR_UNSUPPORTED, "tcgen05 conv: GAP only for stride 1");
   const int op = operand_type(g);
 #define B3D_TC_DISPATCH(KS, HB)                                                                   \
-  return op == OP_BF16 ? dispatch_n<KS, HB, OP_BF16>(g, q, x, wp, bias, y, stats, gap, s)          \
-         : op == OP_F16 ? dispatch_n<KS, HB, OP_F16>(g, q, x, wp, bias, y, stats, gap, s)          \
-                        : dispatch_n<KS, HB, OP_TF32>(g, q, x, wp, bias, y, stats, gap, s)
+  return op == OP_BF16 ? dispatch_n<KS, HB, OP_BF16>(g, q, x, wp, bias, y, stats, gap, s, srcs)          \
+         : op == OP_F16 ? dispatch_n<KS, HB, OP_F16>(g, q, x, wp, bias, y, stats, gap, s, srcs)          \
+                        : dispatch_n<KS, HB, OP_TF32>(g, q, x, wp, bias, y, stats, gap, s, srcs)
   if (q.ks == 3) { B3D_TC_DISPATCH(3, 1); }
   if (q.ks == 1) { B3D_TC_DISPATCH(1, 0); }
   if (q.hb == 1) { B3D_TC_DISPATCH(2, 1); }

@@ -58,14 +58,23 @@ struct WgParams {
   int stage_bytes, nstages, xplanes_max;
   int ntd, nth, ntw, ntiles;
   int nsplit;
+  // P16 operands (common.cuh): every plane is fetched by its own TMA box {8*HW, 1, HH, HD, 1} from the tensor map of
+  // the source that holds it (virtual concat of up to 4 big tensors: cend8 = cumulative channel octets)
+  int p16, nsrc;
+  int cend8[4];
+  int a_f16, b_f16;                // operand formats of kind::f16: 1 = fp16, 0 = bf16 (they may differ)
+};
+
+struct alignas(64) WgMaps {
+  CUtensorMap x[4];
+  CUtensorMap y;
 };
 
 constexpr int kWgSmem = 227 * 1024;
 
 template <int KS, int TG>
 __global__ void __launch_bounds__(256, 1)
-    conv3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
-                          const WgParams prm) {
+    conv3_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // barriers live at the very end of the allocation (the garbage MN groups never reach them: host planner)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgSmem - 128);
@@ -121,9 +130,21 @@ __global__ void __launch_bounds__(256, 1)
         mbar_expect_tx(fb, bytes);
         const uint32_t xdst = smem_u32(smem + (size_t)s * prm.stage_bytes);
         const uint32_t ydst = xdst + (uint32_t)(prm.xplanes_max * prm.px);
-        for (int p = 0; p < xplanes; ++p)
-          tma_load_5d(xdst + p * prm.px, &tmx, cbase + 8 * p, w0 + ow, h0 + oh, d0 + od, b, fb);
-        for (int q = 0; q < yplanes; ++q) tma_load_5d(ydst + q * prm.py, &tmy, nb0 + 8 * q, w0, h0, d0, b, fb);
+        if (prm.p16) {
+          for (int p = 0; p < xplanes; ++p) {
+            const int gp = (cbase >> 3) + p;
+            int si = 0;
+            while (si + 1 < prm.nsrc && gp >= prm.cend8[si]) ++si;
+            tma_load_5d(xdst + p * prm.px, &maps.x[si], 8 * (w0 + ow), gp - (si > 0 ? prm.cend8[si - 1] : 0), h0 + oh,
+                        d0 + od, b, fb);
+          }
+          for (int q = 0; q < yplanes; ++q)
+            tma_load_5d(ydst + q * prm.py, &maps.y, 8 * w0, (nb0 >> 3) + q, h0, d0, b, fb);
+        } else {
+          for (int p = 0; p < xplanes; ++p)
+            tma_load_5d(xdst + p * prm.px, &maps.x[0], cbase + 8 * p, w0 + ow, h0 + oh, d0 + od, b, fb);
+          for (int q = 0; q < yplanes; ++q) tma_load_5d(ydst + q * prm.py, &maps.y, nb0 + 8 * q, w0, h0, d0, b, fb);
+        }
         if (++s == prm.nstages) { s = 0; ph ^= 1; }
       }
     }
@@ -132,8 +153,9 @@ __global__ void __launch_bounds__(256, 1)
     // lane issues the MMAs and commits
     const bool leader = elect_one();
     // D=f32, A=B=bf16, both MN-major, N=Cout, M=128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(prm.NT >> 3) << 17) | (((uint32_t)prm.M >> 4) << 24);
+    // (A = x: fp16 when it is the forward activation twin, prm.a_f16; B = dy: bf16)
+    const uint32_t idesc = (1u << 4) | ((prm.a_f16 ? 0u : 1u) << 7) | ((prm.b_f16 ? 0u : 1u) << 10) | (1u << 15) |
+                           (1u << 16) | ((uint32_t)(prm.NT >> 3) << 17) | (((uint32_t)prm.M >> 4) << 24);
     int s = 0, ph = 0;
     uint32_t acc = 0;
     const int rowc = prm.HW, planec = prm.HH * prm.HW;
@@ -249,10 +271,11 @@ static int make_map(CUtensorMap* tm, const void* base, int C, long long pitch, i
 // x: bf16 copy of the big tensor — for stride 2 already in space-to-depth order [B, Ds, Hs, Ws, 8*nA]
 // rows_real / tr_cn: see WgParams (0 / 0 for ordinary layers); dw_elems: size of dw to clear
 int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, float* dw, cudaStream_t s,
-                         int rows_real, int tr_cn, long long dw_elems) {
+                         int rows_real, int tr_cn, long long dw_elems, const WgP16* p16) {
   B3D_REQUIRE(tc_wgrad_supported(wg), B3D_ERR_UNSUPPORTED, "wgrad: shape not on the tcgen05 path");
   B3D_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, B3D_ERR_LAYOUT, "wgrad: alignment");
   const bool s2 = wg.s == 2;
+  B3D_REQUIRE(p16 == nullptr || (rows_real == 0 && tr_cn == 0), B3D_ERR_UNSUPPORTED, "wgrad (P16): plain layers only");
   const int KS = s2 ? 2 : wg.k, TAPS = KS * KS * KS;
   const int Cin = s2 ? 8 * wg.nA : wg.nA, Cout = wg.nB;
   const int NT = wgrad_ntile(KS, Cout), nnt = Cout / NT;
@@ -298,10 +321,25 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
   if (nsplit < 1) nsplit = 1;
   if (nsplit > p.ntiles) nsplit = p.ntiles;
   p.nsplit = nsplit;
-  CUtensorMap tmx, tmy;
-  if (s2) B3D_TRY(make_map(&tmx, x, Cin, Cin, wg.Ws, wg.Hs, wg.Ds, wg.B, p.HW, p.HH, p.HD));
-  else    B3D_TRY(make_map(&tmx, x, Cin, wg.bigp, wg.Wb, wg.Hb, wg.Db, wg.B, p.HW, p.HH, p.HD));
-  B3D_TRY(make_map(&tmy, dy, Cout, wg.smallp, wg.Ws, wg.Hs, wg.Ds, wg.B, p.TW, p.TH, p.TD));
+  WgMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (p16 != nullptr) {
+    // big: the sources concatenate to Cin channels (stride 2: ONE coarse space-to-depth tensor with 8*nA channels)
+    p.p16 = 1; p.nsrc = p16->n; p.a_f16 = p16->big_bf16 ? 0 : 1; p.b_f16 = p16->small_bf16 ? 0 : 1;
+    int cum = 0;
+    for (int i = 0; i < p16->n; ++i) {
+      cum += p16->C[i] / 8;
+      p.cend8[i] = cum;
+      B3D_TRY(make_p16_map(&maps.x[i], p16->big[i], p16->big_bf16, wg.B, s2 ? wg.Ds : wg.Db, s2 ? wg.Hs : wg.Hb,
+                           s2 ? wg.Ws : wg.Wb, p16->C[i] / 8, p.HW, 1, p.HH, p.HD));
+    }
+    B3D_REQUIRE(cum * 8 == Cin, B3D_ERR_SHAPE, "wgrad (P16): sources hold %d channels, expected %d", cum * 8, Cin);
+    B3D_TRY(make_p16_map(&maps.y, p16->small, p16->small_bf16, wg.B, wg.Ds, wg.Hs, wg.Ws, Cout / 8, p.TW, 1, p.TH, p.TD));
+  } else {
+    if (s2) B3D_TRY(make_map(&maps.x[0], x, Cin, Cin, wg.Ws, wg.Hs, wg.Ds, wg.B, p.HW, p.HH, p.HD));
+    else    B3D_TRY(make_map(&maps.x[0], x, Cin, wg.bigp, wg.Wb, wg.Hb, wg.Db, wg.B, p.HW, p.HH, p.HD));
+    B3D_TRY(make_map(&maps.y, dy, Cout, wg.smallp, wg.Ws, wg.Hs, wg.Ds, wg.B, p.TW, p.TH, p.TD));
+  }
   const size_t dw_n = dw_elems > 0 ? (size_t)dw_elems : (size_t)wg.k * wg.k * wg.k * wg.nA * Cout;
   B3D_TRY(cuda_ok(cudaMemsetAsync(dw, 0, sizeof(float) * dw_n, s), "memset dw"));
   dim3 grid((unsigned)nsplit, (unsigned)ntg, (unsigned)(nmt * nnt));
@@ -314,7 +352,7 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
                       "cudaFuncSetAttribute(wgrad_tc)"));                                                      \
       attr = true;                                                                                             \
     }                                                                                                          \
-    conv3_wgrad_tc_kernel<K, T><<<grid, 256, kWgSmem, s>>>(tmx, tmy, p);                                       \
+    conv3_wgrad_tc_kernel<K, T><<<grid, 256, kWgSmem, s>>>(maps, p);                                       \
   } while (0)
   if (KS == 1) LAUNCH(1, 1);
   else if (KS == 2) LAUNCH(2, 8);

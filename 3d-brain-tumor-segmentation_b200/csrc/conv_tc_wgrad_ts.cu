@@ -34,6 +34,7 @@ struct TsParams {
   int stage_bytes, nstages;
   int ntd, nth, ntw, ntiles, nsplit;
   int D;                           // depth of one sample (dyT folds the batch into its depth dimension)
+  int x_p16, x_f16;                // x is a P16 operand (per-plane boxes {8*HW, 1, HH, HD, 1}); its type is fp16
 };
 
 __device__ __forceinline__ void tc_mma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
@@ -104,7 +105,10 @@ __global__ void __launch_bounds__(kTsThreads, 1)
         mbar_expect_tx(fb, bytes);
         const uint32_t xdst = smem_u32(smem + (size_t)s * prm.stage_bytes);
         const uint32_t ydst = xdst + (uint32_t)(xplanes * prm.px);
-        for (int p = 0; p < xplanes; ++p) tma_load_5d(xdst + p * prm.px, &tmx, 8 * p, w0 + ow, h0 + oh, d0 + od, b, fb);
+        for (int p = 0; p < xplanes; ++p) {
+          if (prm.x_p16) tma_load_5d(xdst + p * prm.px, &tmx, 8 * (w0 + ow), p, h0 + oh, d0 + od, b, fb);
+          else tma_load_5d(xdst + p * prm.px, &tmx, 8 * p, w0 + ow, h0 + oh, d0 + od, b, fb);
+        }
         tma_load_5d(ydst, &tmy, 0, 0, w0 / 8, h0, b * prm.D + d0, fb);      // dyT: (8, Cout, W/8, H, B*D)
         if (++s == prm.nstages) { s = 0; ph ^= 1; }
       }
@@ -114,8 +118,8 @@ __global__ void __launch_bounds__(kTsThreads, 1)
     const int iw = warp - 2;
     const bool leader = elect_one();
     // D = f32, A = B = bf16, A K-major (TMEM), B MN-major, N = Cin, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(prm.Cin >> 3) << 17) |
-                           ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | ((prm.x_f16 ? 0u : 1u) << 10) | (1u << 16) |
+                           ((uint32_t)(prm.Cin >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_col = tmem_base + kTsAccCols + iw * 8;
     int s = 0, ph = 0;
     uint32_t acc = 0;
@@ -193,7 +197,8 @@ bool tc_wgrad_ts_supported(const WgradGeom& wg) {
 }
 
 // x: plain bf16 copy [B, D, H, W, Cin]; dyT: bf16 copy in [B*D][H][W/8][Cout][8] order (launch_cast_bf16_t8)
-int launch_conv_wgrad_ts(const WgradGeom& wg, const void* x, const void* dyT, float* dw, cudaStream_t s) {
+int launch_conv_wgrad_ts(const WgradGeom& wg, const void* x, const void* dyT, float* dw, cudaStream_t s, int x_p16,
+                         int x_f16) {
   B3D_REQUIRE(tc_wgrad_ts_supported(wg), B3D_ERR_UNSUPPORTED, "wgrad (TS): shape not supported");
   B3D_REQUIRE((((uintptr_t)x | (uintptr_t)dyT | (uintptr_t)dw) & 15) == 0, B3D_ERR_LAYOUT, "wgrad (TS): alignment");
   const int Cin = wg.nA, Cout = wg.nB;
@@ -224,7 +229,7 @@ int launch_conv_wgrad_ts(const WgradGeom& wg, const void* x, const void* dyT, fl
       }
   }
   B3D_REQUIRE(found, B3D_ERR_UNSUPPORTED, "wgrad (TS): no tile fits shared memory (Cin=%d Cout=%d)", Cin, Cout);
-  p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.D = wg.Ds;
+  p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.D = wg.Ds; p.x_p16 = x_p16; p.x_f16 = x_f16;
   p.ntd = (wg.Ds + p.TD - 1) / p.TD; p.nth = (wg.Hs + p.TH - 1) / p.TH; p.ntw = (wg.Ws + p.TW - 1) / p.TW;
   p.ntiles = wg.B * p.ntd * p.nth * p.ntw;
   int nsplit = sm_count() / ntg;
@@ -234,7 +239,9 @@ int launch_conv_wgrad_ts(const WgradGeom& wg, const void* x, const void* dyT, fl
   EncodeTiledFn enc = tma_encode_fn();
   B3D_REQUIRE(enc != nullptr, B3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   CUtensorMap tmx, tmy;
-  {
+  if (x_p16) {
+    B3D_TRY(make_p16_map(&tmx, x, x_f16 ? 0 : 1, wg.B, wg.Db, wg.Hb, wg.Wb, Cin / 8, p.HW, 1, p.HH, p.HD));
+  } else {
     const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)wg.Wb, (cuuint64_t)wg.Hb, (cuuint64_t)wg.Db, (cuuint64_t)wg.B};
     const cuuint64_t st[4] = {(cuuint64_t)wg.bigp * 2, (cuuint64_t)wg.bigp * 2 * wg.Wb,
                               (cuuint64_t)wg.bigp * 2 * wg.Wb * wg.Hb, (cuuint64_t)wg.bigp * 2 * wg.Wb * wg.Hb * wg.Db};

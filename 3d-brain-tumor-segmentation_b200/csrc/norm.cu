@@ -30,6 +30,28 @@ __device__ __forceinline__ void chunk_moments(const double* __restrict__ stats, 
   rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// P16 twin output (common.cuh): where the 4 consecutive channels starting at flat element `ea` of sample `b` live in a
+// [B, D*H, C/8, W, 8] 16-bit tensor, as an 8-byte half cell.  C % 8 == 0, ea % 4 == 0.
+struct P16Out {
+  uint2* p;         // nullptr: no twin
+  unsigned W, C;    // voxels per row, channels
+  unsigned rows;    // D*H rows per sample
+  int bf16;
+};
+__device__ __forceinline__ void p16_store4(const P16Out& o, long long b, unsigned ea, const float (&v)[4]) {
+  const unsigned vox = ea / o.C, c = ea - vox * o.C;
+  const unsigned row = vox / o.W, w = vox - row * o.W;
+  uint2 q;
+  if (o.bf16) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v[3]), "f"(v[2]));
+  } else {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v[3]), "f"(v[2]));
+  }
+  o.p[((((unsigned long long)b * o.rows + row) * (o.C >> 3) + (c >> 3)) * o.W + w) * 2 + ((c >> 2) & 1)] = q;
+}
+
 // ------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats,
@@ -80,7 +102,7 @@ template <int VEC, bool RELU>
 __global__ void __launch_bounds__(kThreads)
     gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float* __restrict__ y, ChunkGeom gm, float eps,
-                    long long shift, long long n_local) {
+                    long long shift, long long n_local, P16Out y16) {
   const int chunk = blockIdx.y;
   const int g = chunk % gm.G;
   const long long e_lo = max(0LL, shift - (long long)chunk * gm.L),
@@ -139,8 +161,11 @@ __global__ void __launch_bounds__(kThreads)
           o[i] = RELU ? fmaxf(t, 0.f) : t;
         }
       }
-      if (VEC == 4) st_stream(reinterpret_cast<float4*>(y + off + e), make_float4(o[0], o[1], o[2], o[3]));
-      else y[off + e] = o[0];
+      if (y != nullptr) {
+        if (VEC == 4) st_stream(reinterpret_cast<float4*>(y + off + e), make_float4(o[0], o[1], o[2], o[3]));
+        else y[off + e] = o[0];
+      }
+      if (VEC == 4 && y16.p != nullptr) p16_store4(y16, chunk / gm.G, (unsigned)(goff + e), o);
     }
   }
 }
@@ -260,7 +285,14 @@ template <int VEC, bool RELU>
 __global__ void __launch_bounds__(kThreads)
     gn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const double* __restrict__ stats,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                        const double* __restrict__ csum, float* __restrict__ dx, ChunkGeom gm, float eps) {
+                        const double* __restrict__ csum, float* __restrict__ dx, ChunkGeom gm, float eps,
+                        P16Out dx16, float* __restrict__ dbias) {
+  extern __shared__ float sdb[];      // [C] column sums of dx (the bias gradient of the conv that produced x)
+  if (dbias != nullptr) {
+    for (int i = threadIdx.x; i < gm.C; i += kThreads) sdb[i] = 0.f;
+    __syncthreads();
+  }
+  float db[4] = {0.f, 0.f, 0.f, 0.f};
   const int chunk = blockIdx.y;
   const int g = chunk % gm.G;
   float mean, rstd;
@@ -312,11 +344,25 @@ __global__ void __launch_bounds__(kThreads)
         if (RELU) gq = (xh * ga + be) > 0.f ? gq : 0.f;
         o[i] = rstd * (gq * ga - m1 - xh * m2);
       }
-      if (VEC == 4)
-        st_stream(reinterpret_cast<float4*>(dx + off + e), make_float4(o[0], o[1], o[2], o[3]));
-      else
-        dx[off + e] = o[0];
+      if (dx != nullptr) {
+        if (VEC == 4)
+          st_stream(reinterpret_cast<float4*>(dx + off + e), make_float4(o[0], o[1], o[2], o[3]));
+        else
+          dx[off + e] = o[0];
+      }
+      if (VEC == 4 && dx16.p != nullptr) p16_store4(dx16, chunk / gm.G, (unsigned)(goff + e), o);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) db[i] += o[i];
     }
+  }
+  if (dbias != nullptr) {
+    // channels of a thread's elements are loop-invariant (the host requires C | kThreads * VEC)
+    const int c0 = (int)((goff + base + threadIdx.x * VEC) % gm.C);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) atomicAdd(&sdb[(c0 + i) % gm.C], db[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < gm.C; i += kThreads)
+      if (sdb[i] != 0.f) atomicAdd(&dbias[i], sdb[i]);
   }
 }
 
@@ -387,24 +433,45 @@ extern "C" int b3d_gn_stats(const DLTensor* x_, DLTensor* stats_, int groups, vo
   return B3D_OK;
 }
 
-extern "C" int b3d_gn_apply(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
-                            const DLTensor* beta_, DLTensor* y_, int groups, float eps, int relu, void* stream) {
+// twin_: nullable P16 [B, D, H, C/8, W, 8] (fp16 | bf16) copy of y for the tcgen05 convs that consume it; y_ may then be
+// NULL (the fp32 result is not materialised)
+static int p16_out(const DLTensor* twin_, const TView& x, P16Out* o) {
+  o->p = nullptr;
+  if (twin_ == nullptr) return B3D_OK;
+  P16View v;
+  B3D_TRY(view_p16(twin_, "twin", &v));
+  B3D_REQUIRE(x.ndim == 5 && v.B == x.shape[0] && v.D == x.shape[1] && v.H == x.shape[2] && v.W == x.shape[3] &&
+                  8 * v.C8 == x.shape[4], B3D_ERR_SHAPE, "twin: must be the [B, D, H, C/8, W, 8] form of the fp32 tensor");
+  B3D_REQUIRE(x.numel / x.shape[0] < (1LL << 32), B3D_ERR_UNSUPPORTED, "twin: sample too large");
+  o->p = (uint2*)v.p; o->W = (unsigned)v.W; o->C = 8u * v.C8; o->rows = (unsigned)(v.D * v.H); o->bf16 = v.bf16;
+  return B3D_OK;
+}
+
+static int gn_apply_impl(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_, const DLTensor* beta_,
+                         DLTensor* y_, DLTensor* y16_, int groups, float eps, int relu, void* stream) {
   TView x, y, st, ga, be;
   ChunkGeom gm;
   int nchunks;
   B3D_TRY(view(x_, DT_F32, -1, false, "x", &x));
-  B3D_TRY(view(y_, DT_F32, -1, false, "y", &y));
-  B3D_REQUIRE(x.numel == y.numel, B3D_ERR_SHAPE, "gn_apply: x/y size mismatch");
+  B3D_REQUIRE(y_ != nullptr || y16_ != nullptr, B3D_ERR_ARG, "gn_apply: no output");
+  y.p = nullptr;
+  if (y_ != nullptr) {
+    B3D_TRY(view(y_, DT_F32, -1, false, "y", &y));
+    B3D_REQUIRE(x.numel == y.numel, B3D_ERR_SHAPE, "gn_apply: x/y size mismatch");
+  }
   B3D_TRY(gn_geom(x, groups, &gm, &nchunks));
   B3D_TRY(check_stats(stats_, nchunks, "stats", &st));
   B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
   B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
+  P16Out o16;
+  B3D_TRY(p16_out(y16_, x, &o16));
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 = (gm.L % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)y.p) & 15) == 0);
+  B3D_REQUIRE(v4 || o16.p == nullptr, B3D_ERR_LAYOUT, "gn_apply: the P16 twin needs 16-byte aligned chunks");
 #define LAUNCH(V, R)                                                                                     \
   gn_apply_kernel<V, R><<<gn_grid(gm, nchunks, V), kThreads, 0, s>>>(                                    \
       (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, 0,   \
-      x.numel)
+      x.numel, o16)
   if (v4) {
     if (relu) LAUNCH(4, true); else LAUNCH(4, false);
   } else {
@@ -413,6 +480,17 @@ extern "C" int b3d_gn_apply(const DLTensor* x_, const DLTensor* stats_, const DL
 #undef LAUNCH
   B3D_LAUNCH_CHECK("gn_apply");
   return B3D_OK;
+}
+
+extern "C" int b3d_gn_apply(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
+                            const DLTensor* beta_, DLTensor* y_, int groups, float eps, int relu, void* stream) {
+  return gn_apply_impl(x_, stats_, gamma_, beta_, y_, nullptr, groups, eps, relu, stream);
+}
+
+extern "C" int b3d_gn_apply_p16(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
+                                const DLTensor* beta_, DLTensor* y_, DLTensor* y16_, int groups, float eps, int relu,
+                                void* stream) {
+  return gn_apply_impl(x_, stats_, gamma_, beta_, y_, y16_, groups, eps, relu, stream);
 }
 
 // ---- depth-slab forms (whole-volume inference sharded along D; batch 1): x is this rank's contiguous part
@@ -467,7 +545,7 @@ extern "C" int b3d_gn_apply_slab(const DLTensor* x_, const DLTensor* stats_, con
 #define LAUNCH(V, R)                                                                                     \
   gn_apply_kernel<V, R><<<gn_grid(gm, groups, V), kThreads, 0, s>>>(                                     \
       (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps,     \
-      elem_offset, x.numel)
+      elem_offset, x.numel, P16Out{nullptr, 0, 0, 0, 0})
   if (v4) {
     if (relu) LAUNCH(4, true); else LAUNCH(4, false);
   } else {
@@ -514,28 +592,46 @@ extern "C" int b3d_gn_bwd_reduce(const DLTensor* dy_, const DLTensor* x_, const 
   return B3D_OK;
 }
 
-extern "C" int b3d_gn_bwd_apply(const DLTensor* dy_, const DLTensor* x_, const DLTensor* stats_,
-                                const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* csum_,
-                                DLTensor* dx_, int groups, float eps, int relu, void* stream) {
+static int gn_bwd_apply_impl(const DLTensor* dy_, const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
+                             const DLTensor* beta_, const DLTensor* csum_, DLTensor* dx_, DLTensor* dx16_,
+                             DLTensor* dbias_, int groups, float eps, int relu, void* stream) {
   TView x, dy, dx, st, ga, be, cs;
   ChunkGeom gm;
   int nchunks;
   B3D_TRY(view(x_, DT_F32, -1, false, "x", &x));
   B3D_TRY(view(dy_, DT_F32, -1, false, "dy", &dy));
-  B3D_TRY(view(dx_, DT_F32, -1, false, "dx", &dx));
-  B3D_REQUIRE(x.numel == dy.numel && x.numel == dx.numel, B3D_ERR_SHAPE, "gn_bwd_apply: size mismatch");
+  B3D_REQUIRE(dx_ != nullptr || dx16_ != nullptr, B3D_ERR_ARG, "gn_bwd_apply: no output");
+  dx.p = nullptr;
+  if (dx_ != nullptr) {
+    B3D_TRY(view(dx_, DT_F32, -1, false, "dx", &dx));
+    B3D_REQUIRE(x.numel == dx.numel, B3D_ERR_SHAPE, "gn_bwd_apply: size mismatch");
+  }
+  B3D_REQUIRE(x.numel == dy.numel, B3D_ERR_SHAPE, "gn_bwd_apply: size mismatch");
   B3D_TRY(gn_geom(x, groups, &gm, &nchunks));
   B3D_TRY(check_stats(stats_, nchunks, "stats", &st));
   B3D_TRY(check_stats(csum_, nchunks, "csum", &cs));
   B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
   B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
+  P16Out o16;
+  B3D_TRY(p16_out(dx16_, x, &o16));
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 =
       (gm.L % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)dy.p | (uintptr_t)dx.p) & 15) == 0);
+  B3D_REQUIRE(v4 || o16.p == nullptr, B3D_ERR_LAYOUT, "gn_bwd_apply: the P16 twin needs 16-byte aligned chunks");
+  float* db = nullptr;
+  if (dbias_ != nullptr) {
+    TView dbv;
+    B3D_TRY(check_affine(dbias_, gm.C, "dbias", &dbv));
+    B3D_REQUIRE(v4 && (kThreads * 4) % gm.C == 0 && gm.L % gm.C == 0, B3D_ERR_UNSUPPORTED,
+                "gn_bwd_apply: fused bias gradient needs C | %d and voxel-aligned chunks", kThreads * 4);
+    db = (float*)dbv.p;
+    B3D_TRY(cuda_ok(cudaMemsetAsync(db, 0, sizeof(float) * gm.C, s), "memset dbias"));
+  }
+  const size_t smem = db != nullptr ? sizeof(float) * gm.C : 0;
 #define LAUNCH(V, R)                                                                                       \
-  gn_bwd_apply_kernel<V, R><<<gn_grid(gm, nchunks, V), kThreads, 0, s>>>(                                  \
+  gn_bwd_apply_kernel<V, R><<<gn_grid(gm, nchunks, V), kThreads, smem, s>>>(                               \
       (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, \
-      (const double*)cs.p, (float*)dx.p, gm, eps)
+      (const double*)cs.p, (float*)dx.p, gm, eps, o16, db)
   if (v4) {
     if (relu) LAUNCH(4, true); else LAUNCH(4, false);
   } else {
@@ -544,4 +640,19 @@ extern "C" int b3d_gn_bwd_apply(const DLTensor* dy_, const DLTensor* x_, const D
 #undef LAUNCH
   B3D_LAUNCH_CHECK("gn_bwd_apply");
   return B3D_OK;
+}
+
+extern "C" int b3d_gn_bwd_apply(const DLTensor* dy_, const DLTensor* x_, const DLTensor* stats_,
+                                const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* csum_,
+                                DLTensor* dx_, int groups, float eps, int relu, void* stream) {
+  return gn_bwd_apply_impl(dy_, x_, stats_, gamma_, beta_, csum_, dx_, nullptr, nullptr, groups, eps, relu, stream);
+}
+
+// dx16 (nullable): bf16 P16 twin of dx for the data / weight gradient of the conv that produced x; dbias (nullable): fp32
+// [C] column sums of dx = that conv's bias gradient.  dx may be NULL when only the twin is wanted.
+extern "C" int b3d_gn_bwd_apply_p16(const DLTensor* dy_, const DLTensor* x_, const DLTensor* stats_,
+                                    const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* csum_,
+                                    DLTensor* dx_, DLTensor* dx16_, DLTensor* dbias_, int groups, float eps, int relu,
+                                    void* stream) {
+  return gn_bwd_apply_impl(dy_, x_, stats_, gamma_, beta_, csum_, dx_, dx16_, dbias_, groups, eps, relu, stream);
 }

@@ -103,5 +103,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn tma_encode_fn();
+// tensor map of a P16 operand [B, D, H, C/8, W, 8] (common.cuh) for boxes {8*bw, planes, bh, bd, 1} (conv_tc.cu)
+int make_p16_map(CUtensorMap* tm, const void* base, int bf16, int B, int D, int H, int W, int C8, int bw, int planes,
+                 int bh, int bd);
 
 }  // namespace b3d

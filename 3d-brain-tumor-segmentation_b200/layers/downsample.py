@@ -38,7 +38,8 @@ class ConvDownsample(Layer):
 
     def call(self, inputs, training=None):
         h, st, _ = self.conv.call(inputs, gn_groups=0 if self.norm.channel_mode else self.groups, aux=True)
-        return self.norm.call(h, stats=st, relu=True)
+        from .. import ops
+        return self.norm.call(h, stats=st, relu=True, operand_only=ops.FUSED["on"])
 
     def get_config(self):
         return self.config

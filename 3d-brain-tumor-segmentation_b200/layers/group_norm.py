@@ -61,11 +61,13 @@ class GroupNormalization(Layer):
             self._beta_const = torch.zeros(dim, device=device)
         self.built = True
 
-    def call(self, inputs, training=None, stats=None, relu=False, **kwargs):
+    def call(self, inputs, training=None, stats=None, relu=False, operand_only=False, **kwargs):
+        """operand_only: every consumer of the result is a conv, which reads its 16-bit P16 twin — the fp32 form is not
+        materialised (ops.virtual).  Only the fused callers (ResnetBlock, resampling layers inside a Model) ask for it."""
         gamma = self.gamma if self.scale else self._gamma_const
         beta = self.beta if self.center else self._beta_const
         return ops.group_norm(inputs, gamma, beta, None if self.channel_mode else stats, self.groups, self.epsilon,
-                              relu, channel_mode=self.channel_mode)
+                              relu, channel_mode=self.channel_mode, operand_only=operand_only)
 
     def get_config(self):
         config = {

@@ -36,6 +36,9 @@ class ResnetBlock(Layer):
                             'groups': groups})
         self.filters, self.groups = filters, groups
         self.data_format = data_format
+        # set by Decoder / VariationalAutoencoder on the block whose output feeds a narrow (2-3 channel) output conv: that
+        # conv's weight gradient takes fp32 operands, so the output is kept in fp32 next to its 16-bit twin
+        self.keep_f32_output = False
         self._fused_stats = data_format == 'channels_last'     # chunk statistics from the conv epilogue (F1 only)
 
         self.conv3d_ptwise = Conv3D(filters=filters, kernel_size=1, strides=1, padding='same',
@@ -85,14 +88,16 @@ class ResnetBlock(Layer):
         res, _, gap = self.conv3d_ptwise.call(inputs, want_gap=True, aux=True, share_x=True)
         (conv1, norm1, _), (conv2, norm2, _) = self.convs
         h1, st1, _ = conv1.call(inputs, gn_groups=g, aux=True, share_x=True)
-        a1 = norm1.call(h1, stats=st1, relu=True)
+        a1 = norm1.call(h1, stats=st1, relu=True, operand_only=True)      # only conv2 reads it: 16-bit twin only
         h2, st2, _ = conv2.call(a1, gn_groups=g, aux=True)
         if st2 is None:                                   # chunk boundaries not voxel-aligned: unfused GN2
             a2 = norm2.call(h2, relu=True)
             return ops.block_epilogue(res, a2, None, None, None, self.spatial.kernel, gap,
-                                      self.dense_relu.kernel, self.dense_sigmoid.kernel, self.groups, norm2.epsilon)
+                                      self.dense_relu.kernel, self.dense_sigmoid.kernel, self.groups, norm2.epsilon,
+                                      keep_f32=self.keep_f32_output)
         return ops.block_epilogue(res, h2, st2, norm2.gamma, norm2.beta, self.spatial.kernel, gap,
-                                  self.dense_relu.kernel, self.dense_sigmoid.kernel, self.groups, norm2.epsilon)
+                                  self.dense_relu.kernel, self.dense_sigmoid.kernel, self.groups, norm2.epsilon,
+                                  keep_f32=self.keep_f32_output)
 
     def get_config(self):
         return self.config

@@ -39,7 +39,8 @@ class ConvUpsample(Layer):
 
     def call(self, inputs, training=None):
         h, st = self.conv.call(inputs, gn_groups=0 if self.norm.channel_mode else self.groups, aux=True)
-        return self.norm.call(h, stats=st, relu=True)
+        from .. import ops
+        return self.norm.call(h, stats=st, relu=True, operand_only=ops.FUSED["on"])
 
     def get_config(self):
         return self.config

@@ -172,11 +172,14 @@ class Model(Layer):
         # Inference mode does not evaluate the VAE branch (model.py:60)
         assert (not inference or not training), \
             'Cannot run training and inference modes simultaneously.'
-        residuals = self.encoder(inputs, training=training, dropout_mask=dropout_mask)
-        y_pred = self.decoder((residuals[-1], residuals[:-1]), training=training)
-        if inference:
-            return (y_pred, None, None, None)
-        y_vae, z_mean, z_logvar = self.vae(residuals[-1], training=training, eps=eps)
+        # inside the model every layer output is consumed by convs only: blocks and resampling layers hand over 16-bit
+        # operand twins instead of fp32 tensors and channel concatenation is a list of sources (ops.fused_scope)
+        with ops.fused_scope():
+            residuals = self.encoder(inputs, training=training, dropout_mask=dropout_mask)
+            y_pred = self.decoder((residuals[-1], residuals[:-1]), training=training)
+            if inference:
+                return (y_pred, None, None, None)
+            y_vae, z_mean, z_logvar = self.vae(residuals[-1], training=training, eps=eps)
         return (y_pred, y_vae, z_mean, z_logvar)
 
     # ---- flat parameter storage

@@ -168,6 +168,92 @@ def _grad_done(p, direct):
 USE_TC = {"on": True}
 
 
+# ---- P16 operand twins -------------------------------------------------------------------------------------------
+# Every tensor that feeds a tcgen05 conv exists as a 16-bit "P16" twin [B, D, H, C/8, W, 8] (csrc/p16.cu) written by the
+# kernel that PRODUCES it (GroupNorm apply, block epilogue, their backward kernels): fp16 for forward activations, bf16
+# for gradients.  The convs read the twins (TMA boxes, no conversion, channel concatenation = a list of sources) and
+# the weight gradients read them directly — no cast passes.  Where every consumer of a tensor is a conv, its fp32 form
+# is not materialised at all: the autograd-visible tensor is then a zero-stride placeholder of the logical shape
+# (`_b3d_virtual`) that carries the twin(s); `materialize()` rebuilds fp32 for the rare consumer that needs it.
+P16 = {"on": True}
+# inside a Model forward (`fused_scope`) layer outputs are consumed by convs only, so blocks / resampling layers emit
+# twin-only outputs and channel concatenation is virtual; outside (layers used on their own) outputs stay real fp32
+FUSED = {"on": False}
+
+
+class fused_scope:
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = FUSED["on"]
+        FUSED["on"] = self.on
+
+    def __exit__(self, *a):
+        FUSED["on"] = self.prev
+        return False
+
+
+_TWIN_DT = {"fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+def twin_dtype(bwd: bool):
+    """16-bit type of the operand twins of a pass (None: the pass does not run with 16-bit operands)."""
+    if not (P16["on"] and USE_TC["on"]) or _slab.current() is not None:
+        return None
+    return _TWIN_DT.get(get_conv_precision()[1 if bwd else 0])
+
+
+def p16_empty(shape5, like, dtype):
+    B, D, H, W, C = shape5
+    return torch.empty((B, D, H, C // 8, W, 8), device=like.device, dtype=dtype)
+
+
+def p16_ok(shape5) -> bool:
+    return len(shape5) == 5 and shape5[-1] % 16 == 0 and shape5[-1] >= 16
+
+
+def virtual(shape5, like, twins):
+    """Autograd-visible placeholder (no memory) of logical fp32 shape `shape5` carrying P16 twin(s)."""
+    t = torch.empty(1, device=like.device, dtype=_f32).expand(tuple(shape5))
+    t._b3d_virtual = True
+    t._p16_list = list(twins)
+    return t
+
+
+def is_virtual(t) -> bool:
+    return getattr(t, "_b3d_virtual", False)
+
+
+def sources(t):
+    """P16 twins whose channel concatenation is `t` (None: the tensor has no twin)."""
+    l = getattr(t, "_p16_list", None)
+    if l is not None:
+        return l
+    tw = getattr(t, "_p16", None)
+    return None if tw is None else [tw]
+
+
+def to_p16(x, dtype, colsum=None):
+    out = p16_empty(x.shape, x, dtype)
+    _call("b3d_p16_pack", x, out, colsum)
+    return out
+
+
+def materialize(t):
+    """fp32 NDHWC form of a possibly-virtual tensor (conversion kernel; only legacy / narrow-layer consumers)."""
+    if not is_virtual(t):
+        return t.contiguous()
+    srcs = t._p16_list
+    out = torch.empty(tuple(t.shape), device=srcs[0].device, dtype=_f32)
+    o = 0
+    for sp in srcs:
+        c = sp.shape[3] * 8
+        _call("b3d_p16_unpack", sp, out[..., o:o + c])
+        o += c
+    return out
+
+
 _PREC = {"tf32": 0, "bf16": 1, "fp16": 2}
 _PREC_INV = {v: k for k, v in _PREC.items()}
 
@@ -207,15 +293,46 @@ def get_conv_precision():
     return (_PREC_INV[v & 15], _PREC_INV[v >> 4])
 
 
+def _materialize_from(shape, srcs):
+    out = torch.empty(tuple(shape), device=srcs[0].device, dtype=_f32)
+    o = 0
+    for sp in srcs:
+        c = sp.shape[3] * 8
+        _call("b3d_p16_unpack", sp, out[..., o:o + c])
+        o += c
+    return out
+
+
+def _pad4(l):
+    return list(l) + [None] * (4 - len(l))
+
+
+def _p16_cat(srcs):
+    """One P16 tensor holding the channel concatenation of `srcs` (plane-range copies; only where a kernel takes a
+    single source: the small operand of a transposed conv's weight gradient)."""
+    if len(srcs) == 1:
+        return srcs[0]
+    B, D, H, _, W, _ = srcs[0].shape
+    out = torch.empty((B, D, H, sum(t.shape[3] for t in srcs), W, 8), device=srcs[0].device, dtype=srcs[0].dtype)
+    o = 0
+    for t in srcs:
+        _call("b3d_p16_copy_planes", t, out, o)
+        o += t.shape[3]
+    return out
+
+
 class Conv3dFn(Function):
     """Conv3D / Conv3DTranspose with TF 'SAME' padding (+bias, optional sigmoid), optionally emitting
-    GroupNorm chunk statistics and global-average-pool sums of its output from the epilogue."""
+    GroupNorm chunk statistics and global-average-pool sums of its output from the epilogue.
+
+    Operands: when the input carries P16 twins (`sources(x)`: one, or several = a virtual channel concat) and the
+    layer runs on the tensor cores with 16-bit operands, the kernels read the twins (b3d_conv3d_*_p16); the incoming
+    gradient likewise (twin + bias gradient attached by the kernel that produced it, else packed here once for both
+    the data and the weight gradient).  Everything else takes the fp32 entry points."""
 
     @staticmethod
     def forward(ctx, x, w, bias, stride, transposed, act, gn_groups, want_gap, share_x=False):
         ctx.share_x = bool(share_x)
-        _check(x)
-        x = x.contiguous()
         B, D, H, W_, Cin = x.shape
         k = w.shape[0]
         if transposed:
@@ -223,22 +340,40 @@ class Conv3dFn(Function):
         else:
             Cout = w.shape[4]
             od = (D, H, W_) if stride == 1 else (D // 2, H // 2, W_ // 2)
-        y = _new((B,) + od + (Cout,), x)
+        tc = USE_TC["on"] and (not act or stride == 1) and tc_supported(w, stride, transposed, False)
+        srcs = sources(x)
+        td = twin_dtype(False)
+        use16 = bool(tc and srcs is not None and td is not None and len(srcs) <= 4 and srcs[0].dtype == td)
+        if not use16:
+            x = materialize(x)
+            _check(x)
+        y = _new((B,) + od + (Cout,), w)
         S = od[0] * od[1] * od[2]
         stats = gap = None
         if gn_groups and Cout % gn_groups == 0 and S % gn_groups == 0:
-            stats = _new((B, gn_groups, 2), x, torch.float64)
+            stats = _new((B, gn_groups, 2), w, torch.float64)
         if want_gap:
-            gap = _new((B, Cout), x)
+            gap = _new((B, Cout), w)
         wp = None
-        if USE_TC["on"] and (not act or stride == 1) and tc_supported(w, stride, transposed, False):
+        if tc:
             wp = pack_weights(w, False, stride, transposed)
         elif USE_TC["on"] and getattr(w, "_b3d_flat", None) is not None and tc_supported(w, stride, transposed, True):
             _register_pack(w._b3d_flat, w, True, stride, transposed)     # forward on CUDA cores, data gradient on TC
-        _call("b3d_conv3d_fwd", x, w, bias, y, stride, int(transposed), int(act), stats, gn_groups or 1, gap, 0, wp)
-        ctx.save_for_backward(x, w, y if act else None)
+        if use16:
+            _call("b3d_conv3d_fwd_p16", *_pad4(srcs), w, bias, y, stride, int(transposed), int(act), stats,
+                  gn_groups or 1, gap, 0, wp)
+        else:
+            _call("b3d_conv3d_fwd", x, w, bias, y, stride, int(transposed), int(act), stats, gn_groups or 1, gap, 0, wp)
+        ctx.save_for_backward(None if use16 and is_virtual(x) else x, w, y if act else None)
+        ctx.srcs = srcs if srcs is not None and td is not None and srcs[0].dtype == td else None
+        ctx.xshape = tuple(x.shape)
         ctx.cfg = (stride, transposed, act, bias is not None)
         ctx.params = (w, bias)
+        y._b3d_bias = bias          # lets the kernel that will produce dy write this conv's bias gradient (column sums)
+        # ... and tells it whether this conv's backward can work from a bf16 twin of dy alone
+        ctx.f32_grad = not (ctx.srcs is not None and twin_dtype(True) is not None and lib.b3d_conv3d_wgrad_p16_plan(
+            k, stride, int(transposed), Cin, Cout, od[2]) != 0)
+        y._b3d_f32_grad = ctx.f32_grad
         outs = (y, stats, gap)
         ctx.mark_non_differentiable(*[t for t in (stats, gap) if t is not None])
         return outs
@@ -246,49 +381,91 @@ class Conv3dFn(Function):
     @staticmethod
     def backward(ctx, dy, _ds, _dg):
         x, w, y = ctx.saved_tensors
+        srcs = ctx.srcs
         stride, transposed, act, has_bias = ctx.cfg
-        dy = dy.contiguous()
+        dy16 = getattr(dy, "_p16", None)
+        dbias = getattr(dy, "_dbias", None)          # (tensor, written directly into the flat gradient buffer?)
+        td = twin_dtype(True)
+        if dy16 is not None and dy16.dtype != td:
+            dy16 = None
         if act:
+            dy = materialize(dy)
             t = torch.empty_like(dy)
             _call("b3d_sigmoid_bwd", dy, y, t)
-            dy = t
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            wp = None
-            if USE_TC["on"] and tc_supported(w, stride, transposed, True):
-                wp = pack_weights(w, True, stride, transposed)
-            _call("b3d_conv3d_dgrad", dy, w, dx, stride, int(transposed), 0, wp)
-        if ctx.needs_input_grad[1]:
-            pw, pb = ctx.params
+            dy, dy16, dbias = t, None, None
+        k, cin, cout = w.shape[0], ctx.xshape[-1], dy.shape[-1]
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        tcd = bool(need_dx and USE_TC["on"] and tc_supported(w, stride, transposed, True))
+        plan = 0
+        if need_dw and td is not None and srcs is not None and USE_TC["on"]:
+            plan = lib.b3d_conv3d_wgrad_p16_plan(k, stride, int(transposed), cin, cout, dy.shape[3])
+        pw, pb = ctx.params
+        db = db_direct = None
+        if need_dw and has_bias:
+            if dbias is not None:
+                db, db_direct = dbias
+            else:
+                db, db_direct = _grad_target(pb)
+        bias_done = dbias is not None
+        if dy16 is None and td is not None and p16_ok(dy.shape) and (plan or (tcd and is_virtual(dy))):
+            # no twin came with the gradient (several consumers were summed by autograd, or a fp32 producer): one packing
+            # pass serves the data gradient and the weight gradient and yields the bias gradient on the way
+            dy16 = to_p16(materialize(dy), td, db if (need_dw and has_bias and not bias_done) else None)
+            bias_done = bias_done or (need_dw and has_bias)
+        dx = dw = None
+        if need_dx:
+            dx = torch.empty(ctx.xshape, device=w.device, dtype=_f32)
+            wp = pack_weights(w, True, stride, transposed) if tcd else None
+            if tcd and dy16 is not None:
+                _call("b3d_conv3d_dgrad_p16", dy16, w, dx, stride, int(transposed), 0, wp)
+            else:
+                dy = materialize(dy)
+                _call("b3d_conv3d_dgrad", dy, w, dx, stride, int(transposed), 0, wp)
+        if need_dw:
             dw, dw_direct = _grad_target(pw)
-            db, db_direct = _grad_target(pb) if has_bias else (None, False)
-            xb = yb = None
-            ready = 0
-            if USE_TC["on"]:
-                xc, yc = _ll(), _ll()
-                kind = lib.b3d_conv3d_wgrad_plan(w.shape[0], stride, int(transposed), x.shape[-1], dy.shape[-1],
-                                                 _byref(xc), _byref(yc))
-                if kind:
-                    # the two convs of a ResnetBlock (pointwise + first 3x3x3) read the same input: its plain bf16
-                    # copy is made by whichever weight gradient runs first and handed to the other
-                    key = (x.data_ptr(), tuple(x.shape)) if (kind == 1 and stride == 1 and ctx.share_x) else None
-                    xb = _XB_CACHE.pop(key, None) if key is not None else None
-                    if xb is not None:
-                        ready = 1
-                    else:
-                        xb = torch.empty(x.numel() // x.shape[-1] * xc.value, device=x.device, dtype=torch.bfloat16)
-                        if key is not None:
-                            _XB_CACHE[key] = xb
-                    yb = torch.empty(dy.numel() // dy.shape[-1] * yc.value, device=x.device, dtype=torch.bfloat16)
-            _call("b3d_conv3d_wgrad", x, dy, dw, db, stride, int(transposed), xb, yb, ready)
+            if plan and dy16 is not None:
+                scratch = None
+                if plan == 2:
+                    big = dy16 if transposed else srcs[0]
+                    n = dy16.numel() if transposed else sum(t.numel() for t in srcs)
+                    scratch = torch.empty(n, device=w.device, dtype=big.dtype)
+                elif plan == 3:
+                    scratch = torch.empty(dy16.numel(), device=w.device, dtype=dy16.dtype)
+                xs = [_p16_cat(srcs)] if transposed else srcs
+                _call("b3d_conv3d_wgrad_p16", *_pad4(xs), dy16, dw, stride, int(transposed), scratch)
+                if has_bias and not bias_done:
+                    _call("b3d_colsum", materialize(dy), db)
+            else:
+                if x is None:
+                    x = _materialize_from(ctx.xshape, srcs)
+                dy = materialize(dy)
+                xb = yb = None
+                ready = 0
+                if USE_TC["on"]:
+                    xc, yc = _ll(), _ll()
+                    kind = lib.b3d_conv3d_wgrad_plan(k, stride, int(transposed), cin, cout, _byref(xc), _byref(yc))
+                    if kind:
+                        # the two convs of a ResnetBlock (pointwise + first 3x3x3) read the same input: its plain bf16
+                        # copy is made by whichever weight gradient runs first and handed to the other
+                        key = (x.data_ptr(), tuple(x.shape)) if (kind == 1 and stride == 1 and ctx.share_x) else None
+                        xb = _XB_CACHE.pop(key, None) if key is not None else None
+                        if xb is not None:
+                            ready = 1
+                        else:
+                            xb = torch.empty(x.numel() // x.shape[-1] * xc.value, device=x.device, dtype=torch.bfloat16)
+                            if key is not None:
+                                _XB_CACHE[key] = xb
+                        yb = torch.empty(dy.numel() // dy.shape[-1] * yc.value, device=x.device, dtype=torch.bfloat16)
+                _call("b3d_conv3d_wgrad", x, dy, dw, None if bias_done else db, stride, int(transposed), xb, yb, ready)
             _grad_done(pw, dw_direct)
-            _grad_done(pb, db_direct)
-            dw, db = (None if dw_direct else dw), (None if db_direct else db)
+            if has_bias:
+                _grad_done(pb, db_direct)
+            dw, db = (None if dw_direct else dw), (None if (db_direct or not has_bias) else db)
         return dx, dw, db, None, None, None, None, None, None
 
 
-# bf16 copies of conv inputs shared between two weight gradients of one backward pass (cleared every step)
+# bf16 copies of conv inputs shared between two weight gradients of one backward pass (fp32 entry points only;
+# cleared every step)
 _XB_CACHE = {}
 
 
@@ -301,12 +478,19 @@ def conv3d(x, w, bias=None, stride=1, transposed=False, act=0, gn_groups=0, want
 
 class GroupNormFn(Function):
     """GroupNormalization.call (+ optional fused ReLU) with the reference's channels_last semantics
-    (layers/group_norm.py:83-124).  `stats` may come from the producing conv's epilogue."""
+    (layers/group_norm.py:83-124).  `stats` may come from the producing conv's epilogue.
+
+    Returns (y, y16): y16 = fp16 P16 twin for the convs that consume y (None when the tensor cannot feed the tensor
+    cores); with `operand_only` y itself is a placeholder (`ops.virtual`).  Backward emits dx likewise: a bf16 twin
+    for the data / weight gradient of the conv that produced x plus that conv's bias gradient, and — x being a raw
+    conv output with exactly one consumer — no fp32 dx at all when the twin can be used."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, stats, groups, eps, relu):
+    def forward(ctx, x, gamma, beta, stats, groups, eps, relu, operand_only=False):
+        ctx.bias_param = getattr(x, "_b3d_bias", None)
+        ctx.f32_grad = getattr(x, "_b3d_f32_grad", True)
+        x = materialize(x)
         _check(x)
-        x = x.contiguous()
         C = x.shape[-1]
         # reference group_norm.py:51-59
         if C < groups:
@@ -316,18 +500,30 @@ class GroupNormFn(Function):
         if stats is None:
             stats = _new((x.shape[0], groups, 2), x, torch.float64)
             _call("b3d_gn_stats", x, stats, groups)
-        y = torch.empty_like(x)
-        _call("b3d_gn_apply", x, stats, gamma, beta, y, groups, float(eps), int(relu))
+        td = twin_dtype(False)
+        L = x.numel() // x.shape[0] // groups
+        twin = td is not None and p16_ok(x.shape) and L % 4 == 0
+        y16 = p16_empty(x.shape, x, td) if twin else None
+        y = None if (twin and operand_only) else torch.empty_like(x)
+        if twin:
+            _call("b3d_gn_apply_p16", x, stats, gamma, beta, y, y16, groups, float(eps), int(relu))
+        else:
+            _call("b3d_gn_apply", x, stats, gamma, beta, y, groups, float(eps), int(relu))
+        if y is None:
+            y = virtual(x.shape, x, [y16])
         ctx.save_for_backward(x, gamma, beta, stats)
         ctx.cfg = (groups, float(eps), int(relu))
         ctx.params = (gamma, beta)
-        return y
+        if y16 is None:
+            return y, None
+        ctx.mark_non_differentiable(y16)
+        return y, y16
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _d16=None):
         x, gamma, beta, stats = ctx.saved_tensors
         groups, eps, relu = ctx.cfg
-        dy = dy.contiguous()
+        dy = materialize(dy)
         pg, pb = ctx.params
         dgamma, dg_direct = _grad_target(pg)
         dbeta, db_direct = _grad_target(pb)
@@ -335,9 +531,28 @@ class GroupNormFn(Function):
         _call("b3d_gn_bwd_reduce", dy, x, stats, gamma, beta, dgamma, dbeta, csum, groups, eps, relu)
         _grad_done(pg, dg_direct)
         _grad_done(pb, db_direct)
-        dx = torch.empty_like(x)
-        _call("b3d_gn_bwd_apply", dy, x, stats, gamma, beta, csum, dx, groups, eps, relu)
-        return dx, (None if dg_direct else dgamma), (None if db_direct else dbeta), None, None, None, None
+        td = twin_dtype(True)
+        C = x.shape[-1]
+        L = x.numel() // x.shape[0] // groups
+        twin = td is not None and p16_ok(x.shape) and L % 4 == 0
+        if twin:
+            dx16 = p16_empty(x.shape, x, td)
+            bias = ctx.bias_param
+            fused_bias = bias is not None and 1024 % C == 0 and L % C == 0
+            dbias = _grad_target(bias) if fused_bias else None
+            # the producing conv takes its weight gradient through the fp32 entry point (narrow layers): keep fp32 too
+            dx = torch.empty_like(x) if ctx.f32_grad else None
+            _call("b3d_gn_bwd_apply_p16", dy, x, stats, gamma, beta, csum, dx, dx16, dbias[0] if fused_bias else None,
+                  groups, eps, relu)
+            if dx is None:
+                dx = virtual(x.shape, x, [dx16])
+            dx._p16 = dx16
+            if fused_bias:
+                dx._dbias = dbias
+        else:
+            dx = torch.empty_like(x)
+            _call("b3d_gn_bwd_apply", dy, x, stats, gamma, beta, csum, dx, groups, eps, relu)
+        return dx, (None if dg_direct else dgamma), (None if db_direct else dbeta), None, None, None, None, None
 
 
 class GroupNormChannelFn(Function):
@@ -376,7 +591,7 @@ class GroupNormChannelFn(Function):
         return dx, (None if dg_direct else dgamma), (None if db_direct else dbeta), None, None, None
 
 
-def group_norm(x, gamma, beta, stats=None, groups=8, eps=1e-5, relu=False, channel_mode=False):
+def group_norm(x, gamma, beta, stats=None, groups=8, eps=1e-5, relu=False, channel_mode=False, operand_only=False):
     ctx = _slab.current()
     if channel_mode:
         if ctx is not None:
@@ -384,7 +599,10 @@ def group_norm(x, gamma, beta, stats=None, groups=8, eps=1e-5, relu=False, chann
         return GroupNormChannelFn.apply(x, gamma, beta, groups, eps, relu)
     if ctx is not None:        # chunk statistics of the WHOLE volume: partial sums + all-reduce
         return ctx.group_norm(x, gamma, beta, groups, eps, relu)
-    return GroupNormFn.apply(x, gamma, beta, stats, groups, eps, relu)
+    y, y16 = GroupNormFn.apply(x, gamma, beta, stats, groups, eps, relu, bool(operand_only))
+    if y16 is not None and not is_virtual(y):
+        y._p16 = y16
+    return y
 
 
 class RelayoutFn(Function):
@@ -416,12 +634,15 @@ def to_channels_first(x):
 
 class BlockEpilogueFn(Function):
     """out = res*(sigmoid(res.w_sp) + chse) + relu(GN2(h2)),  chse = sigmoid(relu(mean(res) W1) W2)
-    (layers/resnet.py:121-137).  With stats2=None, `h2` is taken as already normalised+activated."""
+    (layers/resnet.py:121-137).  With stats2=None, `h2` is taken as already normalised+activated.
+    Returns (out, out16) like GroupNormFn; backward emits dres / dh2 as bf16 twins (+ the bias gradients of the
+    pointwise and the second conv) when those convs can use them."""
 
     @staticmethod
-    def forward(ctx, res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps):
+    def forward(ctx, res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps, operand_only=False):
         _check(res)
-        res, h2 = res.contiguous(), h2.contiguous()
+        attrs = [(getattr(t, "_b3d_bias", None), getattr(t, "_b3d_f32_grad", True)) for t in (res, h2)]
+        res, h2 = res.contiguous(), materialize(h2)
         B, F = res.shape[0], res.shape[-1]
         ctx_s = _slab.current()
         S = res.numel() // (B * F) if ctx_s is None else ctx_s.global_voxels(res)   # GAP divisor: whole volume
@@ -429,21 +650,37 @@ class BlockEpilogueFn(Function):
         hidden, chse = _new((B, R), res), _new((B, F), res)
         inv = 1.0 / S
         _call("b3d_se_fc_fwd", gap_sum, w1, w2, hidden, chse, inv)
-        out = _new_act(res.shape, res)
         has_gn = stats2 is not None
         wsp_v = wsp.reshape(F)
-        _call("b3d_block_epilogue_fwd", res, h2, stats2, gamma2 if has_gn else None, beta2 if has_gn else None,
-              wsp_v, chse, out, groups, float(eps), int(has_gn))
+        td = twin_dtype(False)
+        twin = td is not None and p16_ok(res.shape)
+        if twin:
+            out16 = p16_empty(res.shape, res, td)
+            out = None if operand_only else torch.empty_like(res)
+            _call("b3d_block_epilogue_fwd_p16", res, h2, stats2, gamma2 if has_gn else None, beta2 if has_gn else None,
+                  wsp_v, chse, out, out16, groups, float(eps), int(has_gn))
+            if out is None:
+                out = virtual(res.shape, res, [out16])
+        else:
+            out16 = None
+            out = _new_act(res.shape, res)
+            _call("b3d_block_epilogue_fwd", res, h2, stats2, gamma2 if has_gn else None, beta2 if has_gn else None,
+                  wsp_v, chse, out, groups, float(eps), int(has_gn))
         ctx.save_for_backward(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, hidden, chse)
         ctx.cfg = (groups, float(eps), has_gn, inv)
         ctx.params = (gamma2, beta2, wsp, w1, w2)
-        return out
+        ctx.bias_params = (attrs[0][0], attrs[1][0])
+        ctx.f32_grads = (attrs[0][1], attrs[1][1])
+        if out16 is None:
+            return out, None
+        ctx.mark_non_differentiable(out16)
+        return out, out16
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, _d16=None):
         res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, hidden, chse = ctx.saved_tensors
         groups, eps, has_gn, inv = ctx.cfg
-        dout = dout.contiguous()
+        dout = materialize(dout)
         B, F = res.shape[0], res.shape[-1]
         wsp_v = wsp.reshape(F)
         pg, pb, pwsp, pw1, pw2 = ctx.params
@@ -459,20 +696,46 @@ class BlockEpilogueFn(Function):
         _call("b3d_se_fc_bwd", gap_sum, w1, w2, hidden, chse, dchse, dw1, dw2, dgap, inv)
         for p_, d_ in ((pwsp, dwsp_direct), (pg, dg_direct), (pb, db_direct), (pw1, dw1_direct), (pw2, dw2_direct)):
             _grad_done(p_, d_)
-        dres = torch.empty_like(res)
-        dh2 = torch.empty_like(h2) if has_gn else None
-        _call("b3d_block_epilogue_bwd_apply", dout, res, h2 if has_gn else None, stats2,
-              gamma2 if has_gn else None, beta2 if has_gn else None, wsp_v, chse, dgap, csum, dres, dh2,
-              groups, eps, int(has_gn))
-        if not has_gn:
-            dh2 = dout
+        td = twin_dtype(True)
+        twin = td is not None and p16_ok(res.shape) and has_gn
+        if twin:
+            b_res, b_h2 = ctx.bias_params
+            fused_bias = b_res is not None and b_h2 is not None
+            dres16, dh216 = p16_empty(res.shape, res, td), p16_empty(res.shape, res, td)
+            # the first block's pointwise conv (2 input channels) takes its weight gradient through the fp32 entry point
+            dres = torch.empty_like(res) if ctx.f32_grads[0] else None
+            dh2 = torch.empty_like(res) if ctx.f32_grads[1] else None
+            tb_res = _grad_target(b_res) if fused_bias else None
+            tb_h2 = _grad_target(b_h2) if fused_bias else None
+            _call("b3d_block_epilogue_bwd_apply_p16", dout, res, h2, stats2, gamma2, beta2, wsp_v, chse, dgap, csum,
+                  dres, dh2, dres16, dh216, tb_res[0] if fused_bias else None, tb_h2[0] if fused_bias else None,
+                  groups, eps, 1)
+            if dres is None:
+                dres = virtual(res.shape, res, [dres16])
+            if dh2 is None:
+                dh2 = virtual(res.shape, res, [dh216])
+            dres._p16, dh2._p16 = dres16, dh216
+            if fused_bias:
+                dres._dbias, dh2._dbias = tb_res, tb_h2
+        else:
+            dres = torch.empty_like(res)
+            dh2 = torch.empty_like(h2) if has_gn else None
+            _call("b3d_block_epilogue_bwd_apply", dout, res, h2 if has_gn else None, stats2,
+                  gamma2 if has_gn else None, beta2 if has_gn else None, wsp_v, chse, dgap, csum, dres, dh2,
+                  groups, eps, int(has_gn))
+            if not has_gn:
+                dh2 = dout
         return (dres, dh2, None, None if dg_direct else dgamma, None if db_direct else dbeta,
                 None if dwsp_direct else dwsp.reshape(wsp.shape), None, None if dw1_direct else dw1,
-                None if dw2_direct else dw2, None, None)
+                None if dw2_direct else dw2, None, None, None)
 
 
-def block_epilogue(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups=8, eps=1e-5):
-    return BlockEpilogueFn.apply(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps)
+def block_epilogue(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups=8, eps=1e-5, keep_f32=False):
+    operand_only = FUSED["on"] and _slab.current() is None and not keep_f32
+    out, out16 = BlockEpilogueFn.apply(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps, operand_only)
+    if out16 is not None and not is_virtual(out):
+        out._p16 = out16
+    return out
 
 
 class DenseFn(Function):
@@ -586,8 +849,8 @@ class MaxPool2Fn(Function):
 
     @staticmethod
     def forward(ctx, x):
+        x = materialize(x)
         _check(x)
-        x = x.contiguous()
         B, D, H, W, C = x.shape
         y = _new((B, D // 2, H // 2, W // 2, C), x)
         _call("b3d_maxpool2_fwd", x, y)
@@ -611,8 +874,8 @@ class Upsample2Fn(Function):
 
     @staticmethod
     def forward(ctx, x):
+        x = materialize(x)
         _check(x)
-        x = x.contiguous()
         B, D, H, W, C = x.shape
         y = _new((B, 2 * D, 2 * H, 2 * W, C), x)
         _call("b3d_upsample2_fwd", x, y)
@@ -635,6 +898,7 @@ class ConcatFn(Function):
 
     @staticmethod
     def forward(ctx, *xs):
+        xs = [materialize(t) for t in xs]
         C = [t.shape[-1] for t in xs]
         out = _new_act(tuple(xs[0].shape[:-1]) + (sum(C),), xs[0])
         o = 0
@@ -646,7 +910,7 @@ class ConcatFn(Function):
 
     @staticmethod
     def backward(ctx, d):
-        d = d.contiguous()
+        d = materialize(d)
         outs, o = [], 0
         for i, c in enumerate(ctx.C):
             if ctx.needs_input_grad[i]:
@@ -659,7 +923,34 @@ class ConcatFn(Function):
         return tuple(outs)
 
 
+class VirtualConcatFn(Function):
+    """Channel concat of tensors that carry P16 twins, without a copy: the result is a placeholder listing the sources
+    (the convs take up to 4 of them as K segments); the gradient of the concatenated tensor is handed back as channel
+    slices (views) of the data gradient the consuming conv wrote."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        C = [t.shape[-1] for t in xs]
+        twins = [tw for t in xs for tw in sources(t)]
+        ctx.C = C
+        return virtual(tuple(xs[0].shape[:-1]) + (sum(C),), twins[0], twins)
+
+    @staticmethod
+    def backward(ctx, d):
+        d = materialize(d)
+        outs, o = [], 0
+        for i, c in enumerate(ctx.C):
+            outs.append(d[..., o:o + c] if ctx.needs_input_grad[i] else None)
+            o += c
+        return tuple(outs)
+
+
 def concat(xs):
+    td = twin_dtype(False)
+    if FUSED["on"] and td is not None:
+        srcs = [sources(t) for t in xs]
+        if all(l is not None and all(tw.dtype == td for tw in l) for l in srcs) and sum(len(l) for l in srcs) <= 4:
+            return VirtualConcatFn.apply(*xs)
     return ConcatFn.apply(*xs)
 
 

@@ -245,6 +245,53 @@ int b3d_flip_normalize(const DLTensor* x, const DLTensor* mean, const DLTensor* 
 int b3d_flip_accumulate(const DLTensor* y, DLTensor* acc, const DLTensor* mask, int flip, float scale, int first,
                         void* stream);
 
+/* ---- P16 operand twins -------------------------------------------------------------------------------------------
+ * A "P16" tensor is the 16-bit copy of an activation (fp16) or gradient (bf16) in the layout the tcgen05 conv kernels
+ * consume directly: [B, D, H, C/8, W, 8] (DLPack ndim 6, dtype f16 | bf16, compact).  Channel octets are planes inside
+ * every (d, h) row: a voxel's 8 channels are one 16-byte UMMA cell and a halo row of one plane is W*16 contiguous bytes,
+ * so whole halos are fetched as wide TMA rows.  The twins are written by the kernels that PRODUCE conv operands (the
+ * *_p16 forms of GroupNorm apply / block epilogue and their backward kernels below) — there is no cast pass on the
+ * training step, and a channel concatenation (encoder.py:85,91; decoder.py:75) is a list of up to 4 sources. */
+int b3d_p16_pack(const DLTensor* x /*fp32 NDHWC, C % 8 == 0, may be a channel slice*/, DLTensor* dst /*P16*/,
+                 DLTensor* colsum /*nullable fp32 [C]: per-channel sums of x*/, void* stream);
+int b3d_p16_unpack(const DLTensor* src /*P16*/, DLTensor* y /*fp32 NDHWC, may be a channel slice*/, void* stream);
+int b3d_p16_copy_planes(const DLTensor* src /*P16*/, DLTensor* dst /*P16, wider*/, int c8off, void* stream);
+int b3d_colsum(const DLTensor* x /*fp32 NDHWC*/, DLTensor* out /*fp32 [C]*/, void* stream);
+/* the three conv passes with P16 input operands (same semantics as b3d_conv3d_fwd / _dgrad / _wgrad; tcgen05 path only:
+ * wpacked is required).  x0..x3: the sources whose channels are concatenated (x1..x3 nullable), all fp16 (forward
+ * operand type fp16) or all bf16.  The weight gradient does NOT produce the bias gradient on this path: it is emitted
+ * by the kernel that writes dy (`dbias` of b3d_gn_bwd_apply_p16 / b3d_block_epilogue_bwd_apply_p16, `colsum` of
+ * b3d_p16_pack).  scratch (nullable, 16-bit, 1-D): see b3d_conv3d_wgrad_p16_plan. */
+int b3d_conv3d_fwd_p16(const DLTensor* x0, const DLTensor* x1, const DLTensor* x2, const DLTensor* x3, const DLTensor* w,
+                       const DLTensor* bias /*nullable*/, DLTensor* y, int stride, int transposed, int act,
+                       DLTensor* gn_stats, int groups, DLTensor* gap, int accumulate, const DLTensor* wpacked,
+                       void* stream);
+int b3d_conv3d_dgrad_p16(const DLTensor* dy /*P16*/, const DLTensor* w, DLTensor* dx, int stride, int transposed,
+                         int accumulate, const DLTensor* wpacked, void* stream);
+int b3d_conv3d_wgrad_p16(const DLTensor* x0, const DLTensor* x1, const DLTensor* x2, const DLTensor* x3,
+                         const DLTensor* dy /*P16*/, DLTensor* dw, int stride, int transposed, DLTensor* scratch,
+                         void* stream);
+/* 0: the layer's weight gradient is not on the P16 path; 1: straight from the operands; 2: needs a 16-bit scratch of
+ * numel(big tensor) elements (stride-2 family); 3: of numel(dy) elements (TS-mode kernel).  w_sp = W of dy. */
+int b3d_conv3d_wgrad_p16_plan(int k, int stride, int transposed, int cin, int cout, int w_sp);
+/* GroupNorm apply / backward-apply and block epilogue forward / backward-apply with twin outputs.  The fp32 outputs
+ * (y, dx, out, dres, dh2) are nullable: NULL = only the twin is written (every consumer is a conv).  dbias* (nullable,
+ * fp32 [C]): column sums of the gradient written = the bias gradient of the conv that produced the kernel's input. */
+int b3d_gn_apply_p16(const DLTensor* x, const DLTensor* stats, const DLTensor* gamma, const DLTensor* beta, DLTensor* y,
+                     DLTensor* y16, int groups, float eps, int relu, void* stream);
+int b3d_gn_bwd_apply_p16(const DLTensor* dy, const DLTensor* x, const DLTensor* stats, const DLTensor* gamma,
+                         const DLTensor* beta, const DLTensor* csum, DLTensor* dx, DLTensor* dx16, DLTensor* dbias,
+                         int groups, float eps, int relu, void* stream);
+int b3d_block_epilogue_fwd_p16(const DLTensor* res, const DLTensor* h2, const DLTensor* stats, const DLTensor* gamma,
+                               const DLTensor* beta, const DLTensor* wsp, const DLTensor* chse, DLTensor* out,
+                               DLTensor* out16, int groups, float eps, int has_gn, void* stream);
+int b3d_block_epilogue_bwd_apply_p16(const DLTensor* dout, const DLTensor* res, const DLTensor* h2,
+                                     const DLTensor* stats, const DLTensor* gamma, const DLTensor* beta,
+                                     const DLTensor* wsp, const DLTensor* chse, const DLTensor* dgap,
+                                     const DLTensor* csum, DLTensor* dres, DLTensor* dh2, DLTensor* dres16,
+                                     DLTensor* dh216, DLTensor* dbias_res, DLTensor* dbias_h2, int groups, float eps,
+                                     int has_gn, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

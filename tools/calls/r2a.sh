@@ -10,3 +10,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 timeout 300 python tools/conv_bench.py all 5 fp16 > gpurun_out/r2a/conv_bench.txt 2>&1
 nvidia-smi > gpurun_out/r2a/smi.txt
 ls -la gpurun_out/r2a
+# 4. the new BASELINE-shape parity tests on the round-1 kernels (calibration of the derived bounds)
+timeout 900 python -m pytest tests/test_gpu_baseline_shapes.py -x -q -s > gpurun_out/r2a/baseline_tests.log 2>&1
+tail -5 gpurun_out/r2a/baseline_tests.log
