@@ -94,6 +94,8 @@ SIGNATURES = {
     "b3d_block_epilogue_bwd_apply": "TTTTTTTTTTTTifiv",
     "b3d_loss_fwd": "TTTTTTTTv",
     "b3d_loss_bwd": "TTTTTTTTTTTTv",
+    "b3d_loss_finalize": "TTLLv",
+    "b3d_loss_bwd_dp": "TTTTTTTTTTTTiv",
     "b3d_dice_coeff": "TTTTiv",
     "b3d_dense_fwd": "TTTTiv",
     "b3d_dense_bwd": "TTTTTTTiv",
@@ -126,9 +128,9 @@ SIGNATURES = {
     "b3d_conv3d_fwd_p16": "TTTTTTTiiiTiTiTv",
     "b3d_conv3d_dgrad_p16": "TTTiiiTv",
     "b3d_conv3d_wgrad_p16": "TTTTTTiiTv",
-    "b3d_gn_apply_p16": "TTTTTTifiv",
+    "b3d_gn_apply_p16": "TTTTTTTifiv",
     "b3d_gn_bwd_apply_p16": "TTTTTTTTTifiv",
-    "b3d_block_epilogue_fwd_p16": "TTTTTTTTTifiv",
+    "b3d_block_epilogue_fwd_p16": "TTTTTTTTTTifiv",
     "b3d_block_epilogue_bwd_apply_p16": "TTTTTTTTTTTTTTTTifiv",
 }
 _CT = {"T": P, "i": _i, "f": _f, "v": _v, "L": _ll, "U": _ull}

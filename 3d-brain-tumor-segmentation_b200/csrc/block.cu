@@ -26,9 +26,22 @@ struct P16Out {
   unsigned W, C8;   // voxels per row, channel octets
   unsigned rows;    // D*H rows per sample
   int bf16;
+  uint2* p2;        // optional second twin, always bf16 (see norm.cu)
 };
-__device__ __forceinline__ void p16_store4(const P16Out& o, long long b, unsigned vox, int c, const float4& v) {
-  const unsigned row = vox / o.W, w = vox - row * o.W;
+// (row, w) of a voxel: one division per thread at the start, then advanced by the kernel's voxel stride
+struct P16Pos { unsigned row, w; };
+__device__ __forceinline__ P16Pos p16_pos(const P16Out& o, unsigned vox) {
+  P16Pos k;
+  k.row = vox / o.W;
+  k.w = vox - k.row * o.W;
+  return k;
+}
+__device__ __forceinline__ void p16_advance(const P16Out& o, P16Pos& k, unsigned dv) {
+  k.w += dv;
+  while (k.w >= o.W) { k.w -= o.W; ++k.row; }
+}
+__device__ __forceinline__ void p16_store4(const P16Out& o, long long b, const P16Pos& k, int c, const float4& v) {
+  const unsigned row = k.row, w = k.w;
   uint2 q;
   if (o.bf16) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v.y), "f"(v.x));
@@ -37,7 +50,13 @@ __device__ __forceinline__ void p16_store4(const P16Out& o, long long b, unsigne
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v.y), "f"(v.x));
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v.w), "f"(v.z));
   }
-  o.p[((((unsigned long long)b * o.rows + row) * o.C8 + (c >> 3)) * o.W + w) * 2 + ((c >> 2) & 1)] = q;
+  const unsigned long long idx = ((((unsigned long long)b * o.rows + row) * o.C8 + (c >> 3)) * o.W + w) * 2 + ((c >> 2) & 1);
+  o.p[idx] = q;
+  if (o.p2 != nullptr) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v.w), "f"(v.z));
+    o.p2[idx] = q;
+  }
 }
 
 __device__ __forceinline__ float group_sum(float v, int T) {
@@ -90,6 +109,8 @@ __global__ void __launch_bounds__(kBT)
   const long long vend = min(v0 + gm.vox_per_cta, gm.vpc);
   const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
   const int iters = (int)((vend - v0 + vstep - 1) / vstep);   // CTA-uniform: whole warps stay in the shuffles
+  P16Pos pos = {0, 0};
+  if (out16.p != nullptr) pos = p16_pos(out16, (unsigned)((long long)g * gm.vpc + v0 + vl));
   for (int it = 0; it < iters; ++it) {
     const long long v = v0 + (long long)it * vstep + vl;
     const bool act = v < vend;
@@ -124,9 +145,10 @@ __global__ void __launch_bounds__(kBT)
           o.z = r[q].z * (s + c4[q].z) + a.z;
           o.w = r[q].w * (s + c4[q].w) + a.w;
           if (out != nullptr) st_stream(reinterpret_cast<float4*>(out + eo + c), o);
-          if (out16.p != nullptr) p16_store4(out16, b, (unsigned)((long long)g * gm.vpc + v), c, o);
+          if (out16.p != nullptr) p16_store4(out16, b, pos, c, o);
         }
     }
+    if (out16.p != nullptr) p16_advance(out16, pos, (unsigned)vstep);
   }
 }
 
@@ -320,6 +342,9 @@ __global__ void __launch_bounds__(kBT)
   const long long vend = min(v0 + gm.vox_per_cta, gm.vpc);
   const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
   const int iters = (int)((vend - v0 + vstep - 1) / vstep);   // CTA-uniform: whole warps stay in the shuffles
+  P16Pos pos = {0, 0};
+  const P16Out& any16 = dres16.p != nullptr ? dres16 : dh216;
+  if (any16.p != nullptr) pos = p16_pos(any16, (unsigned)((long long)g * gm.vpc + v0 + vl));
   for (int it = 0; it < iters; ++it) {
     const long long v = v0 + (long long)it * vstep + vl;
     const bool act = v < vend;
@@ -350,8 +375,7 @@ __global__ void __launch_bounds__(kBT)
           o.z = d[q].z * (s + c4[q].z) + dl * w4[q].z + g4[q].z;
           o.w = d[q].w * (s + c4[q].w) + dl * w4[q].w + g4[q].w;
           if (dres != nullptr) st_stream(reinterpret_cast<float4*>(dres + eo + c), o);
-          const unsigned vs = (unsigned)((long long)g * gm.vpc + v);
-          if (dres16.p != nullptr) p16_store4(dres16, b, vs, c, o);
+          if (dres16.p != nullptr) p16_store4(dres16, b, pos, c, o);
           acc_r[q].x += o.x; acc_r[q].y += o.y; acc_r[q].z += o.z; acc_r[q].w += o.w;
           if (HAS_GN) {
             const float4 hv = ld_stream(reinterpret_cast<const float4*>(h2 + eo + c));
@@ -368,11 +392,12 @@ __global__ void __launch_bounds__(kBT)
             }
             const float4 o2 = make_float4(oo[0], oo[1], oo[2], oo[3]);
             if (dh2 != nullptr) st_stream(reinterpret_cast<float4*>(dh2 + eo + c), o2);
-            if (dh216.p != nullptr) p16_store4(dh216, b, vs, c, o2);
+            if (dh216.p != nullptr) p16_store4(dh216, b, pos, c, o2);
             acc_h[q].x += o2.x; acc_h[q].y += o2.y; acc_h[q].z += o2.z; acc_h[q].w += o2.w;
           }
         }
     }
+    if (any16.p != nullptr) p16_advance(any16, pos, (unsigned)vstep);
   }
   if (dbias_res != nullptr) {
     // lanes of a warp with equal (lane % T) hold the same channels: butterfly over the voxel sub-index first
@@ -519,9 +544,17 @@ static int vecF(const DLTensor* t, long long n, const char* name, TView* v) {
   return B3D_OK;
 }
 
-static int p16_out(const DLTensor* twin_, const TView& x, P16Out* o) {
-  o->p = nullptr;
+static int p16_out(const DLTensor* twin_, const TView& x, P16Out* o, const DLTensor* twin2_ = nullptr) {
+  o->p = nullptr; o->p2 = nullptr;
   if (twin_ == nullptr) return B3D_OK;
+  if (twin2_ != nullptr) {
+    P16View v2;
+    B3D_TRY(view_p16(twin2_, "twin (bf16)", &v2));
+    B3D_REQUIRE(v2.bf16 && twin_->ndim == 6 && twin2_->ndim == 6, B3D_ERR_DTYPE, "second twin must be bf16");
+    for (int i = 0; i < 6; ++i)
+      B3D_REQUIRE(twin_->shape[i] == twin2_->shape[i], B3D_ERR_SHAPE, "twins differ in shape");
+    o->p2 = (uint2*)v2.p;
+  }
   P16View v;
   B3D_TRY(view_p16(twin_, "twin", &v));
   B3D_REQUIRE(x.ndim == 5 && v.B == x.shape[0] && v.D == x.shape[1] && v.H == x.shape[2] && v.W == x.shape[3] &&
@@ -575,8 +608,8 @@ extern "C" int b3d_se_fc_bwd(const DLTensor* gap_sum_, const DLTensor* w1_, cons
 
 static int block_fwd_impl(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
                           const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
-                          const DLTensor* chse_, DLTensor* out_, DLTensor* out16_, int groups, float eps, int has_gn,
-                          void* stream) {
+                          const DLTensor* chse_, DLTensor* out_, DLTensor* out16_, DLTensor* out16b_, int groups, float eps,
+                          int has_gn, void* stream) {
   TView res, h2, out, st, ga, be, wsp, ch;
   BlockGeom gm;
   int nchunks;
@@ -590,7 +623,7 @@ static int block_fwd_impl(const DLTensor* res_, const DLTensor* h2_, const DLTen
   }
   B3D_REQUIRE(res.numel == h2.numel, B3D_ERR_SHAPE, "block epilogue: size mismatch");
   P16Out o16;
-  B3D_TRY(p16_out(out16_, res, &o16));
+  B3D_TRY(p16_out(out16_, res, &o16, out16b_));
   B3D_TRY(block_geom(res, groups, has_gn != 0, &gm, &nchunks));
   B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
   B3D_TRY(vecF(chse_, res.shape[0] * gm.F, "chse", &ch));
@@ -616,15 +649,16 @@ extern "C" int b3d_block_epilogue_fwd(const DLTensor* res_, const DLTensor* h2_,
                                       const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
                                       const DLTensor* chse_, DLTensor* out_, int groups, float eps, int has_gn,
                                       void* stream) {
-  return block_fwd_impl(res_, h2_, stats_, gamma_, beta_, wsp_, chse_, out_, nullptr, groups, eps, has_gn, stream);
+  return block_fwd_impl(res_, h2_, stats_, gamma_, beta_, wsp_, chse_, out_, nullptr, nullptr, groups, eps, has_gn, stream);
 }
 
-// out16: fp16 P16 twin of the block output for the convs that consume it; `out` may then be NULL
+// out16: P16 twin of the block output for the convs that consume it (`out` may then be NULL); out16b (nullable): second,
+// bf16 twin for their weight gradients when out16 is fp16
 extern "C" int b3d_block_epilogue_fwd_p16(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
                                           const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
-                                          const DLTensor* chse_, DLTensor* out_, DLTensor* out16_, int groups,
-                                          float eps, int has_gn, void* stream) {
-  return block_fwd_impl(res_, h2_, stats_, gamma_, beta_, wsp_, chse_, out_, out16_, groups, eps, has_gn, stream);
+                                          const DLTensor* chse_, DLTensor* out_, DLTensor* out16_, DLTensor* out16b_,
+                                          int groups, float eps, int has_gn, void* stream) {
+  return block_fwd_impl(res_, h2_, stats_, gamma_, beta_, wsp_, chse_, out_, out16_, out16b_, groups, eps, has_gn, stream);
 }
 
 extern "C" int b3d_block_epilogue_bwd_reduce(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,

@@ -514,6 +514,9 @@ extern "C" int b3d_conv3d_wgrad_p16(const DLTensor* x0_, const DLTensor* x1_, co
   cudaStream_t s = (cudaStream_t)stream;
   const int cout = 8 * dy.C8;
   B3D_REQUIRE(!transposed || src.n == 1, B3D_ERR_UNSUPPORTED, "wgrad (P16): conv-transpose takes one source");
+  B3D_REQUIRE(xf.bf16 && dy.bf16, B3D_ERR_DTYPE,
+              "wgrad (P16): bf16 twins of both operands (kind::f16 takes one operand type; forward activations carry a "
+              "second, bf16 twin for this pass)");
   const int plan = b3d_conv3d_wgrad_p16_plan(k, stride, transposed, cin, cout, dy.W);
   B3D_REQUIRE(plan != 0, B3D_ERR_UNSUPPORTED, "wgrad (P16): layer not on this path (k=%d s=%d %d->%d)", k, stride, cin, cout);
   const P16View& big = transposed ? dy : xf;
@@ -560,7 +563,7 @@ extern "C" int b3d_conv3d_wgrad_p16(const DLTensor* x0_, const DLTensor* x1_, co
     B3D_REQUIRE(scratch != nullptr && scratch_n >= need, B3D_ERR_ARG, "wgrad (P16, TS): scratch of %lld elements", need);
     B3D_REQUIRE(src.n == 1, B3D_ERR_UNSUPPORTED, "wgrad (P16, TS): one source");
     B3D_TRY(launch_p16_t8(dy.p, scratch, (long long)dy.B * dy.D * dy.H, dy.W, dy.C8, s));
-    return launch_conv_wgrad_ts(wg, xf.p, scratch, (float*)dw.p, s, 1, xf.bf16 ? 0 : 1);
+    return launch_conv_wgrad_ts(wg, xf.p, scratch, (float*)dw.p, s, 1, 0);
   }
   if (transposed) { wp.n = 1; wp.big[0] = big.p; wp.C[0] = cbig; }
   else {

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
 
   if (warp >= 4 && warp < 4 + kLoaderWarps && prm.tma) {
     // ============ operand loader, TMA form: one elected thread fetches the halo of every K chunk as ONE 5-D box
-    // {8*HW, 2 planes, HH, HD, 1} of the source's P16 tensor map (zero fill outside the volume = TF 'SAME' padding)
+    // {HW voxels, 2 planes, HH, HD, 1} of the source's P16 tensor map (zero fill outside the volume = TF 'SAME' padding)
     if (warp == 4 && lane == 0) {
       int hs = 0, hph = 0;
       for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
           mbar_wait(smem_u32(&halo_empty[hs]), hph ^ 1);
           const uint32_t full = smem_u32(&halo_full[hs]);
           mbar_expect_tx(full, C::HALO_TX);
-          tma_load_5d(smem_u32(halo + hs * C::HALO_BYTES), &maps.m[si], 8 * w0, pl, h0, d0, b, full);
+          tma_load_5d(smem_u32(halo + hs * C::HALO_BYTES), &maps.m[si], 4 * w0, pl, h0, d0, b, full);
           if (++hs == C::HS) { hs = 0; hph ^= 1; }
         }
       }
@@ -889,18 +889,21 @@ static float* splitk_workspace(cudaStream_t s) {
   return ws[dev];
 }
 
-// tensor map of a P16 operand [B, D, H, C/8, W, 8] for boxes {8*bw, planes, bh, bd, 1}: dims (W*8, C/8, H, D, B)
+// tensor map of a P16 operand [B, D, H, C/8, W, 8] for boxes of bw voxels x `planes` x bh x bd: the innermost dimension
+// is the (w, 8 channels) run of a plane row counted in 32-bit words (4 per 16-byte cell; a box extent is limited to 256
+// ELEMENTS, so words instead of halves allow rows of up to 64 voxels) -> dims (4W, C/8, H, D, B), coordinate 4*w.
 int make_p16_map(CUtensorMap* tm, const void* base, int bf16, int B, int D, int H, int W, int C8, int bw, int planes,
                  int bh, int bd) {
+  (void)bf16;
   EncodeTiledFn enc = tma_encode_fn();
   B3D_REQUIRE(enc != nullptr, B3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  B3D_REQUIRE(8 * bw <= 256 && planes <= 256 && bh <= 256 && bd <= 256, B3D_ERR_UNSUPPORTED, "P16 map: box too large");
+  B3D_REQUIRE(4 * bw <= 256 && planes <= 256 && bh <= 256 && bd <= 256, B3D_ERR_UNSUPPORTED, "P16 map: box too large");
   const cuuint64_t row = (cuuint64_t)W * 16;
-  const cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)C8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  const cuuint64_t dims[5] = {(cuuint64_t)W * 4, (cuuint64_t)C8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
   const cuuint64_t strides[4] = {row, row * C8, row * C8 * H, row * C8 * H * D};
-  const cuuint32_t box[5] = {(cuuint32_t)(8 * bw), (cuuint32_t)planes, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  const cuuint32_t box[5] = {(cuuint32_t)(4 * bw), (cuuint32_t)planes, (cuuint32_t)bh, (cuuint32_t)bd, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)base,
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, (void*)base,
                          dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B3D_REQUIRE(r == CUDA_SUCCESS, B3D_ERR_CUDA, "cuTensorMapEncodeTiled(P16) failed (%d)", (int)r);

@@ -62,7 +62,6 @@ struct WgParams {
   // the source that holds it (virtual concat of up to 4 big tensors: cend8 = cumulative channel octets)
   int p16, nsrc;
   int cend8[4];
-  int a_f16, b_f16;                // operand formats of kind::f16: 1 = fp16, 0 = bf16 (they may differ)
 };
 
 struct alignas(64) WgMaps {
@@ -135,11 +134,11 @@ __global__ void __launch_bounds__(256, 1)
             const int gp = (cbase >> 3) + p;
             int si = 0;
             while (si + 1 < prm.nsrc && gp >= prm.cend8[si]) ++si;
-            tma_load_5d(xdst + p * prm.px, &maps.x[si], 8 * (w0 + ow), gp - (si > 0 ? prm.cend8[si - 1] : 0), h0 + oh,
+            tma_load_5d(xdst + p * prm.px, &maps.x[si], 4 * (w0 + ow), gp - (si > 0 ? prm.cend8[si - 1] : 0), h0 + oh,
                         d0 + od, b, fb);
           }
           for (int q = 0; q < yplanes; ++q)
-            tma_load_5d(ydst + q * prm.py, &maps.y, 8 * w0, (nb0 >> 3) + q, h0, d0, b, fb);
+            tma_load_5d(ydst + q * prm.py, &maps.y, 4 * w0, (nb0 >> 3) + q, h0, d0, b, fb);
         } else {
           for (int p = 0; p < xplanes; ++p)
             tma_load_5d(xdst + p * prm.px, &maps.x[0], cbase + 8 * p, w0 + ow, h0 + oh, d0 + od, b, fb);
@@ -153,9 +152,8 @@ __global__ void __launch_bounds__(256, 1)
     // lane issues the MMAs and commits
     const bool leader = elect_one();
     // D=f32, A=B=bf16, both MN-major, N=Cout, M=128
-    // (A = x: fp16 when it is the forward activation twin, prm.a_f16; B = dy: bf16)
-    const uint32_t idesc = (1u << 4) | ((prm.a_f16 ? 0u : 1u) << 7) | ((prm.b_f16 ? 0u : 1u) << 10) | (1u << 15) |
-                           (1u << 16) | ((uint32_t)(prm.NT >> 3) << 17) | (((uint32_t)prm.M >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(prm.NT >> 3) << 17) | (((uint32_t)prm.M >> 4) << 24);
     int s = 0, ph = 0;
     uint32_t acc = 0;
     const int rowc = prm.HW, planec = prm.HH * prm.HW;
@@ -325,7 +323,10 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
   memset(&maps, 0, sizeof(maps));
   if (p16 != nullptr) {
     // big: the sources concatenate to Cin channels (stride 2: ONE coarse space-to-depth tensor with 8*nA channels)
-    p.p16 = 1; p.nsrc = p16->n; p.a_f16 = p16->big_bf16 ? 0 : 1; p.b_f16 = p16->small_bf16 ? 0 : 1;
+    // kind::f16 takes ONE operand type for A and B (mixing f16 with bf16 is an illegal instruction on sm_100a — tried):
+    // the weight gradient reads bf16 twins of both tensors
+    B3D_REQUIRE(p16->big_bf16 && p16->small_bf16, B3D_ERR_DTYPE, "wgrad (P16): both operands must be bf16 twins");
+    p.p16 = 1; p.nsrc = p16->n;
     int cum = 0;
     for (int i = 0; i < p16->n; ++i) {
       cum += p16->C[i] / 8;

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kTsThreads, 1)
         const uint32_t xdst = smem_u32(smem + (size_t)s * prm.stage_bytes);
         const uint32_t ydst = xdst + (uint32_t)(xplanes * prm.px);
         for (int p = 0; p < xplanes; ++p) {
-          if (prm.x_p16) tma_load_5d(xdst + p * prm.px, &tmx, 8 * (w0 + ow), p, h0 + oh, d0 + od, b, fb);
+          if (prm.x_p16) tma_load_5d(xdst + p * prm.px, &tmx, 4 * (w0 + ow), p, h0 + oh, d0 + od, b, fb);
           else tma_load_5d(xdst + p * prm.px, &tmx, 8 * p, w0 + ow, h0 + oh, d0 + od, b, fb);
         }
         tma_load_5d(ydst, &tmy, 0, 0, w0 / 8, h0, b * prm.D + d0, fb);      // dyT: (8, Cout, W/8, H, B*D)
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(kTsThreads, 1)
     const int iw = warp - 2;
     const bool leader = elect_one();
     // D = f32, A = B = bf16, A K-major (TMEM), B MN-major, N = Cin, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | ((prm.x_f16 ? 0u : 1u) << 10) | (1u << 16) |
-                           ((uint32_t)(prm.Cin >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(prm.Cin >> 3) << 17) |
+                           ((128u >> 4) << 24);
     const uint32_t a_col = tmem_base + kTsAccCols + iw * 8;
     int s = 0, ph = 0;
     uint32_t acc = 0;

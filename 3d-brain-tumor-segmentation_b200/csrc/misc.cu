@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(256)
                     const float* __restrict__ x, const float* __restrict__ yv, long long n_rec,
                     const float* __restrict__ mu, const float* __restrict__ lv, int n_lat,
                     const double* __restrict__ sums, const float* __restrict__ gout, float* __restrict__ dyp,
-                    float* __restrict__ dyv, float* __restrict__ dmu, float* __restrict__ dlv) {
+                    float* __restrict__ dyv, float* __restrict__ dmu, float* __restrict__ dlv, float aux_scale) {
+  // aux_scale = 1 / replicas: with the batch-global objective of data-parallel training (`sums` all-reduced over the
+  // ranks) the two means run over `replicas` times as many elements as this rank holds
   const float g = gout[0];
   float ka[C], kb[C];  // d/dyp = ka*y + kb*yp
 #pragma unroll
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(256)
       dyp[e] = ka[ch] * y[e] + kb[ch] * yp[e];
     }
   if (x != nullptr) {
-    const float k = -0.2f * g / (float)n_rec;
+    const float k = -0.2f * g * aux_scale / (float)n_rec;
     const long long m4 = n_rec / 4;
     for (long long i = tid; i < m4; i += stride) {
       const float4 a = ld_stream(reinterpret_cast<const float4*>(x) + i);
@@ -150,8 +152,8 @@ __global__ void __launch_bounds__(256)
   }
   if (mu != nullptr && blockIdx.x == 0)
     for (int i = threadIdx.x; i < n_lat; i += blockDim.x) {
-      dmu[i] = 0.2f * g * mu[i] / (float)n_lat;
-      dlv[i] = 0.1f * g * (expf(lv[i]) - 1.0f) / (float)n_lat;
+      dmu[i] = 0.2f * g * aux_scale * mu[i] / (float)n_lat;
+      dlv[i] = 0.1f * g * aux_scale * (expf(lv[i]) - 1.0f) / (float)n_lat;
     }
 }
 
@@ -571,11 +573,12 @@ extern "C" int b3d_loss_fwd(const DLTensor* x_, const DLTensor* y_, const DLTens
   return B3D_OK;
 }
 
-extern "C" int b3d_loss_bwd(const DLTensor* x_, const DLTensor* y_, const DLTensor* ypred_, const DLTensor* yvae_,
-                            const DLTensor* zmean_, const DLTensor* zlogvar_, const DLTensor* sums_,
-                            const DLTensor* gout_, DLTensor* dypred_, DLTensor* dyvae_, DLTensor* dzmean_,
-                            DLTensor* dzlogvar_, void* stream) {
+static int loss_bwd_impl(const DLTensor* x_, const DLTensor* y_, const DLTensor* ypred_, const DLTensor* yvae_,
+                         const DLTensor* zmean_, const DLTensor* zlogvar_, const DLTensor* sums_,
+                         const DLTensor* gout_, DLTensor* dypred_, DLTensor* dyvae_, DLTensor* dzmean_,
+                         DLTensor* dzlogvar_, int replicas, void* stream) {
   TView y, yp, x, yv, mu, lv, sums, g, dyp, dyv, dmu, dlv;
+  B3D_REQUIRE(replicas >= 1, B3D_ERR_ARG, "loss bwd: replicas >= 1");
   B3D_TRY(flat_f32(y_, "y", &y));
   B3D_TRY(flat_f32(ypred_, "y_pred", &yp));
   B3D_TRY(flat_f32(dypred_, "dy_pred", &dyp));
@@ -604,9 +607,45 @@ extern "C" int b3d_loss_bwd(const DLTensor* x_, const DLTensor* y_, const DLTens
                     vae ? (const float*)yv.p : nullptr, vae ? x.numel : 0, vae ? (const float*)mu.p : nullptr,
                     vae ? (const float*)lv.p : nullptr, vae ? (int)mu.numel : 0, (const double*)sums.p,
                     (const float*)g.p, (float*)dyp.p, vae ? (float*)dyv.p : nullptr, vae ? (float*)dmu.p : nullptr,
-                    vae ? (float*)dlv.p : nullptr)));
+                    vae ? (float*)dlv.p : nullptr, 1.0f / (float)replicas)));
   B3D_LAUNCH_CHECK("loss_bwd");
   return B3D_OK;
+}
+
+extern "C" int b3d_loss_bwd(const DLTensor* x_, const DLTensor* y_, const DLTensor* ypred_, const DLTensor* yvae_,
+                            const DLTensor* zmean_, const DLTensor* zlogvar_, const DLTensor* sums_,
+                            const DLTensor* gout_, DLTensor* dypred_, DLTensor* dyvae_, DLTensor* dzmean_,
+                            DLTensor* dzlogvar_, void* stream) {
+  return loss_bwd_impl(x_, y_, ypred_, yvae_, zmean_, zlogvar_, sums_, gout_, dypred_, dyvae_, dzmean_, dzlogvar_, 1,
+                       stream);
+}
+
+// Batch-global objective under data parallelism (util.py:11,18-20 sums I, P, T over the batch axis): every
+// rank runs b3d_loss_fwd on its crops, the 3C+2 fp64 `sums` are all-reduced (sum) over the `replicas` ranks, then
+// b3d_loss_finalize turns the global sums into the loss of the whole batch and b3d_loss_bwd_dp yields this rank's part of
+// its gradient (Dice terms from the global sums; the two means divided by the global element counts).
+extern "C" int b3d_loss_finalize(const DLTensor* sums_, DLTensor* out_, long long n_rec_total, long long n_lat_total,
+                                 void* stream) {
+  TView sums, out;
+  B3D_TRY(view(sums_, DT_F64, 1, false, "sums", &sums));
+  B3D_TRY(flat_f32(out_, "out", &out));
+  B3D_REQUIRE(out.numel == 4 && sums.numel >= 5 && (sums.numel - 2) % 3 == 0, B3D_ERR_SHAPE,
+              "loss_finalize: sums [3C+2] fp64, out [4] fp32");
+  const int C = (int)((sums.numel - 2) / 3);
+  const bool vae = n_rec_total > 0;
+  loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const double*)sums.p, (float*)out.p, C,
+                                                            vae ? 1.0 / (double)n_rec_total : 0.0,
+                                                            vae ? 1.0 / (double)n_lat_total : 0.0, vae ? 1 : 0);
+  B3D_LAUNCH_CHECK("loss_finalize");
+  return B3D_OK;
+}
+
+extern "C" int b3d_loss_bwd_dp(const DLTensor* x_, const DLTensor* y_, const DLTensor* ypred_, const DLTensor* yvae_,
+                               const DLTensor* zmean_, const DLTensor* zlogvar_, const DLTensor* sums_,
+                               const DLTensor* gout_, DLTensor* dypred_, DLTensor* dyvae_, DLTensor* dzmean_,
+                               DLTensor* dzlogvar_, int replicas, void* stream) {
+  return loss_bwd_impl(x_, y_, ypred_, yvae_, zmean_, zlogvar_, sums_, gout_, dypred_, dyvae_, dzmean_, dzlogvar_,
+                       replicas, stream);
 }
 
 // acc: fp32 [W*C*3] workspace (overwritten); out: fp32 [2] = macro, micro

@@ -37,10 +37,32 @@ struct P16Out {
   unsigned W, C;    // voxels per row, channels
   unsigned rows;    // D*H rows per sample
   int bf16;
+  uint2* p2;        // optional second twin, always bf16 (forward activations: fp16 for the conv, bf16 for the weight
+                    // gradient, whose MMA takes one operand type for A and B)
 };
-__device__ __forceinline__ void p16_store4(const P16Out& o, long long b, unsigned ea, const float (&v)[4]) {
+// Position of a thread's float4 inside the twin: computed once per thread (two divisions) and then ADVANCED by the
+// kernel's fixed element stride (kThreads * VEC per iteration, a multiple of C for every layer of this model), so the
+// streaming loop carries no division.
+struct P16Cursor {
+  unsigned long long rowbase;   // (b * rows + row) * C8 + c8
+  unsigned w, half;             // voxel inside the row, which half of the 16-byte cell
+  unsigned dv;                  // voxels per step (0: stride not a multiple of C -> recompute from the element index)
+};
+__device__ __forceinline__ P16Cursor p16_cursor(const P16Out& o, long long b, unsigned ea, unsigned step_elems) {
   const unsigned vox = ea / o.C, c = ea - vox * o.C;
-  const unsigned row = vox / o.W, w = vox - row * o.W;
+  const unsigned row = vox / o.W;
+  P16Cursor k;
+  k.rowbase = ((unsigned long long)b * o.rows + row) * (o.C >> 3) + (c >> 3);
+  k.w = vox - row * o.W;
+  k.half = (c >> 2) & 1;
+  k.dv = (step_elems % o.C == 0) ? step_elems / o.C : 0;
+  return k;
+}
+__device__ __forceinline__ void p16_advance(const P16Out& o, P16Cursor& k) {
+  k.w += k.dv;
+  while (k.w >= o.W) { k.w -= o.W; k.rowbase += (o.C >> 3); }
+}
+__device__ __forceinline__ void p16_store4(const P16Out& o, const P16Cursor& k, const float (&v)[4]) {
   uint2 q;
   if (o.bf16) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v[1]), "f"(v[0]));
@@ -49,7 +71,13 @@ __device__ __forceinline__ void p16_store4(const P16Out& o, long long b, unsigne
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v[1]), "f"(v[0]));
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v[3]), "f"(v[2]));
   }
-  o.p[((((unsigned long long)b * o.rows + row) * (o.C >> 3) + (c >> 3)) * o.W + w) * 2 + ((c >> 2) & 1)] = q;
+  const unsigned long long idx = (k.rowbase * o.W + k.w) * 2 + k.half;
+  o.p[idx] = q;
+  if (o.p2 != nullptr) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v[3]), "f"(v[2]));
+    o.p2[idx] = q;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -127,6 +155,9 @@ __global__ void __launch_bounds__(kThreads)
       sh[i] = __ldg(beta + jbase + j);
     }
   }
+  P16Cursor cur = {0, 0, 0, 0};
+  if (VEC == 4 && y16.p != nullptr)
+    cur = p16_cursor(y16, chunk / gm.G, (unsigned)(goff + base + threadIdx.x * VEC), kThreads * VEC);
   float in[kIter][4];
 #pragma unroll
   for (int k = 0; k < kIter; ++k) {
@@ -165,8 +196,12 @@ __global__ void __launch_bounds__(kThreads)
         if (VEC == 4) st_stream(reinterpret_cast<float4*>(y + off + e), make_float4(o[0], o[1], o[2], o[3]));
         else y[off + e] = o[0];
       }
-      if (VEC == 4 && y16.p != nullptr) p16_store4(y16, chunk / gm.G, (unsigned)(goff + e), o);
+      if (VEC == 4 && y16.p != nullptr) {
+        if (cur.dv == 0) cur = p16_cursor(y16, chunk / gm.G, (unsigned)(goff + e), 0);
+        p16_store4(y16, cur, o);
+      }
     }
+    if (VEC == 4 && y16.p != nullptr) p16_advance(y16, cur);
   }
 }
 
@@ -313,6 +348,9 @@ __global__ void __launch_bounds__(kThreads)
       bei[i] = __ldg(beta + jbase + (c_first + i) % gm.cg);
     }
   }
+  P16Cursor cur = {0, 0, 0, 0};
+  if (VEC == 4 && dx16.p != nullptr)
+    cur = p16_cursor(dx16, chunk / gm.G, (unsigned)(goff + base + threadIdx.x * VEC), kThreads * VEC);
 #pragma unroll
   for (int k = 0; k < kIter; ++k) {
     const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
@@ -350,10 +388,14 @@ __global__ void __launch_bounds__(kThreads)
         else
           dx[off + e] = o[0];
       }
-      if (VEC == 4 && dx16.p != nullptr) p16_store4(dx16, chunk / gm.G, (unsigned)(goff + e), o);
+      if (VEC == 4 && dx16.p != nullptr) {
+        if (cur.dv == 0) cur = p16_cursor(dx16, chunk / gm.G, (unsigned)(goff + e), 0);
+        p16_store4(dx16, cur, o);
+      }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) db[i] += o[i];
     }
+    if (VEC == 4 && dx16.p != nullptr) p16_advance(dx16, cur);
   }
   if (dbias != nullptr) {
     // channels of a thread's elements are loop-invariant (the host requires C | kThreads * VEC)
@@ -435,9 +477,17 @@ extern "C" int b3d_gn_stats(const DLTensor* x_, DLTensor* stats_, int groups, vo
 
 // twin_: nullable P16 [B, D, H, C/8, W, 8] (fp16 | bf16) copy of y for the tcgen05 convs that consume it; y_ may then be
 // NULL (the fp32 result is not materialised)
-static int p16_out(const DLTensor* twin_, const TView& x, P16Out* o) {
-  o->p = nullptr;
+static int p16_out(const DLTensor* twin_, const TView& x, P16Out* o, const DLTensor* twin2_ = nullptr) {
+  o->p = nullptr; o->p2 = nullptr;
   if (twin_ == nullptr) return B3D_OK;
+  if (twin2_ != nullptr) {
+    P16View v2;
+    B3D_TRY(view_p16(twin2_, "twin (bf16)", &v2));
+    B3D_REQUIRE(v2.bf16 && twin_->ndim == 6 && twin2_->ndim == 6, B3D_ERR_DTYPE, "second twin must be bf16");
+    for (int i = 0; i < 6; ++i)
+      B3D_REQUIRE(twin_->shape[i] == twin2_->shape[i], B3D_ERR_SHAPE, "twins differ in shape");
+    o->p2 = (uint2*)v2.p;
+  }
   P16View v;
   B3D_TRY(view_p16(twin_, "twin", &v));
   B3D_REQUIRE(x.ndim == 5 && v.B == x.shape[0] && v.D == x.shape[1] && v.H == x.shape[2] && v.W == x.shape[3] &&
@@ -448,7 +498,7 @@ static int p16_out(const DLTensor* twin_, const TView& x, P16Out* o) {
 }
 
 static int gn_apply_impl(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_, const DLTensor* beta_,
-                         DLTensor* y_, DLTensor* y16_, int groups, float eps, int relu, void* stream) {
+                         DLTensor* y_, DLTensor* y16_, DLTensor* y16b_, int groups, float eps, int relu, void* stream) {
   TView x, y, st, ga, be;
   ChunkGeom gm;
   int nchunks;
@@ -464,7 +514,7 @@ static int gn_apply_impl(const DLTensor* x_, const DLTensor* stats_, const DLTen
   B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
   B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
   P16Out o16;
-  B3D_TRY(p16_out(y16_, x, &o16));
+  B3D_TRY(p16_out(y16_, x, &o16, y16b_));
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 = (gm.L % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)y.p) & 15) == 0);
   B3D_REQUIRE(v4 || o16.p == nullptr, B3D_ERR_LAYOUT, "gn_apply: the P16 twin needs 16-byte aligned chunks");
@@ -484,13 +534,13 @@ static int gn_apply_impl(const DLTensor* x_, const DLTensor* stats_, const DLTen
 
 extern "C" int b3d_gn_apply(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
                             const DLTensor* beta_, DLTensor* y_, int groups, float eps, int relu, void* stream) {
-  return gn_apply_impl(x_, stats_, gamma_, beta_, y_, nullptr, groups, eps, relu, stream);
+  return gn_apply_impl(x_, stats_, gamma_, beta_, y_, nullptr, nullptr, groups, eps, relu, stream);
 }
 
 extern "C" int b3d_gn_apply_p16(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
-                                const DLTensor* beta_, DLTensor* y_, DLTensor* y16_, int groups, float eps, int relu,
-                                void* stream) {
-  return gn_apply_impl(x_, stats_, gamma_, beta_, y_, y16_, groups, eps, relu, stream);
+                                const DLTensor* beta_, DLTensor* y_, DLTensor* y16_, DLTensor* y16b_, int groups,
+                                float eps, int relu, void* stream) {
+  return gn_apply_impl(x_, stats_, gamma_, beta_, y_, y16_, y16b_, groups, eps, relu, stream);
 }
 
 // ---- depth-slab forms (whole-volume inference sharded along D; batch 1): x is this rank's contiguous part
@@ -545,7 +595,7 @@ extern "C" int b3d_gn_apply_slab(const DLTensor* x_, const DLTensor* stats_, con
 #define LAUNCH(V, R)                                                                                     \
   gn_apply_kernel<V, R><<<gn_grid(gm, groups, V), kThreads, 0, s>>>(                                     \
       (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps,     \
-      elem_offset, x.numel, P16Out{nullptr, 0, 0, 0, 0})
+      elem_offset, x.numel, P16Out{nullptr, 0, 0, 0, 0, nullptr})
   if (v4) {
     if (relu) LAUNCH(4, true); else LAUNCH(4, false);
   } else {

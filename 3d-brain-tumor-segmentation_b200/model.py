@@ -46,7 +46,10 @@ class FlatParams:
     """All trainable tensors of a model as views of one buffer; `grad` is the matching flat gradient."""
 
     def __init__(self, variables, device):
-        reg = [v for v in variables if v.regularizer is not None]
+        # regularised tensors first, grouped by their L2 coefficient (stable: attribute order inside a group), so that
+        # every group is one contiguous range of the flat buffer.  Model(l2_scale=X) gives two groups: the VAE's
+        # ConvDownsample swallows its kernel_regularizer kwarg and keeps the default 1e-5 (vae.py:53-57)
+        reg = sorted((v for v in variables if v.regularizer is not None), key=lambda v: v.regularizer.l)
         unreg = [v for v in variables if v.regularizer is None]
         self.order = reg + unreg
         pad = lambda n: (n + 3) // 4 * 4          # keep every tensor 16-byte aligned
@@ -71,12 +74,17 @@ class FlatParams:
         self.n_reg = len(reg)
         self.reg_end = seg[-1]
         self.reg_tensors = [v.tensor for v in reg]
-        ls = {v.regularizer.l for v in reg}
-        if len(ls) > 1:
-            raise NotImplementedError("b3d: per-tensor L2 scales must all be equal")
-        self.l2 = ls.pop() if ls else 0.0
+        # (first tensor, one past the last tensor, coefficient) of every run of equal coefficients
+        self.l2_groups = []
+        for i, v in enumerate(reg):
+            if self.l2_groups and self.l2_groups[-1][2] == v.regularizer.l:
+                self.l2_groups[-1][1] = i + 1
+            else:
+                self.l2_groups.append([i, i + 1, v.regularizer.l])
+        self.l2 = self.l2_groups[0][2] if len(self.l2_groups) == 1 else None     # single coefficient: fused fast paths
         # segment table of the regularised tensors (padding belongs to the preceding tensor; it stays 0)
         self.offsets = torch.tensor(seg, dtype=torch.int64, device=device)
+        self._seg = seg
         self.total = total
         # persistent packed conv operands (ops.pack_weights / ops.repack_all) and their staleness epoch
         self.packs = {}
@@ -93,11 +101,13 @@ class FlatParams:
         if cb is not None:
             cb(tensor)
 
-    def add_l2_grad(self):
-        """grad += 2*l*w over the regularised tensors (what autograd does through model.losses, train.py:146)."""
-        if self.n_reg:
-            # the regularised tensors are the head of the flat buffer and their padding is zero: one axpy over it
-            ops._call("b3d_axpy", self.theta, self.grad, int(self.reg_end), 2.0 * float(self.l2), None)
+    def add_l2_grad(self, scale=1.0):
+        """grad += scale*2*l*w over the regularised tensors (what autograd does through model.losses, train.py:146)."""
+        seg = self._seg
+        for t0, t1, l in self.l2_groups:
+            # a group is a contiguous range of the flat buffer and its padding is zero: one axpy over it
+            lo, hi = seg[t0], seg[t1]
+            ops._call("b3d_axpy", self.theta[lo:hi], self.grad[lo:hi], int(hi - lo), 2.0 * float(l) * scale, None)
 
     def attach_grads(self):
         for v in self.order:
@@ -112,14 +122,17 @@ class _L2LossesFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, flat: FlatParams, *params):
         out = torch.empty(flat.n_reg, device=flat.theta.device, dtype=torch.float32)
-        ops._call("b3d_l2_losses", flat.theta, flat.offsets, out, float(flat.l2))
+        for t0, t1, l in flat.l2_groups:
+            ops._call("b3d_l2_losses", flat.theta, flat.offsets[t0:t1 + 1], out[t0:t1], float(l))
         ctx.flat = flat
         return out
 
     @staticmethod
     def backward(ctx, gout):
         flat = ctx.flat
-        ops._call("b3d_l2_grad", flat.theta, flat.grad, flat.offsets, gout.contiguous(), 2.0 * float(flat.l2))
+        gout = gout.contiguous()
+        for t0, t1, l in flat.l2_groups:
+            ops._call("b3d_l2_grad", flat.theta, flat.grad, flat.offsets[t0:t1 + 1], gout[t0:t1], 2.0 * float(l))
         return (None,) * (1 + flat.n_reg)
 
 

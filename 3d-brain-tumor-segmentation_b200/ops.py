@@ -19,9 +19,43 @@ _f32 = torch.float32
 LAUNCHES = {"n": 0}
 
 
+# per-call device timing for bench.py's in-step aggregates (eager steps only: events cannot be read inside a graph)
+_PROF = {"on": False, "rows": [], "tag": None}
+
+
+class profile_calls:
+    """with profile_calls() as rows: ... -> rows = [(abi name, tag, start event, end event)], tag = (class, FLOPs) set
+    by the conv wrappers.  CUDA events on the launching stream around every C-ABI call."""
+
+    def __enter__(self):
+        _PROF["on"], _PROF["rows"] = True, []
+        return _PROF["rows"]
+
+    def __exit__(self, *a):
+        _PROF["on"] = False
+        return False
+
+
 def _call(name, *a):
     LAUNCHES["n"] += 1
-    return call(name, *a)
+    if not _PROF["on"]:
+        return call(name, *a)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = call(name, *a)
+    e1.record()
+    _PROF["rows"].append((name, _PROF["tag"], e0, e1))
+    _PROF["tag"] = None
+    return rc
+
+
+def _tag_conv(w, nvox_out, stride, transposed):
+    """(kernel class, FLOPs) of one conv pass for profile_calls: 2 * output voxels * taps * Cin * Cout (transposed: input
+    voxels), SURVEY section 8(d)."""
+    if _PROF["on"]:
+        k = w.shape[0]
+        cls = "k1" if k == 1 else ("s2" if stride == 2 else "k3")
+        _PROF["tag"] = (cls, 2.0 * nvox_out * k ** 3 * w.shape[3] * w.shape[4])
 
 
 def _new(shape, like, dtype=_f32):
@@ -178,7 +212,21 @@ USE_TC = {"on": True}
 P16 = {"on": True}
 # inside a Model forward (`fused_scope`) layer outputs are consumed by convs only, so blocks / resampling layers emit
 # twin-only outputs and channel concatenation is virtual; outside (layers used on their own) outputs stay real fp32
-FUSED = {"on": False}
+import threading as _threading
+
+
+class _Fused(_threading.local):
+    """Per-thread flag (the virtual ranks of slab inference run the model in threads)."""
+    on = False
+
+    def __getitem__(self, k):
+        return self.on
+
+    def __setitem__(self, k, v):
+        self.on = bool(v)
+
+
+FUSED = _Fused()
 
 
 class fused_scope:
@@ -213,12 +261,47 @@ def p16_ok(shape5) -> bool:
     return len(shape5) == 5 and shape5[-1] % 16 == 0 and shape5[-1] >= 16
 
 
-def virtual(shape5, like, twins):
-    """Autograd-visible placeholder (no memory) of logical fp32 shape `shape5` carrying P16 twin(s)."""
+def virtual(shape5, like, twins, wtwins=None):
+    """Autograd-visible placeholder (no memory) of logical fp32 shape `shape5` carrying P16 twin(s): `twins` in the
+    operand type of the pass that produced it, `wtwins` the bf16 set for weight gradients (tcgen05 kind::f16 takes one
+    operand type for both operands, gradients are bf16 => forward activations carry a bf16 twin next to the fp16 one)."""
     t = torch.empty(1, device=like.device, dtype=_f32).expand(tuple(shape5))
     t._b3d_virtual = True
     t._p16_list = list(twins)
+    t._p16w_list = list(wtwins) if wtwins is not None else None
     return t
+
+
+def _attach(t, y16, y16b):
+    """Twins of a REAL fp32 tensor."""
+    t._p16 = y16
+    t._p16w = y16b if y16b is not None else (y16 if y16.dtype == torch.bfloat16 else None)
+
+
+def sources_w(t):
+    """bf16 twins for the weight gradient of a conv reading `t` (None: not available)."""
+    if is_virtual(t):
+        l = t._p16w_list
+        if l is None and t._p16_list and t._p16_list[0].dtype == torch.bfloat16:
+            l = t._p16_list
+        return l
+    l = getattr(t, "_p16w_list", None)
+    if l is not None:
+        return l
+    tw = getattr(t, "_p16w", None)
+    return None if tw is None else [tw]
+
+
+def want_wgrad_twin(td, grad_enabled):
+    """A second (bf16) twin is written when the forward operand type is fp16 and a backward pass will follow.
+    (`grad_enabled` is sampled by the caller OUTSIDE the autograd Function: inside `forward` grad mode is always off.)"""
+    return td == torch.float16 and bool(grad_enabled)
+
+
+def _grad_placeholder(like):
+    """What a backward returns for an input whose gradient exists only as a twin in the producer's mailbox: a zero-stride
+    tensor of the right shape (no memory, never read)."""
+    return torch.empty(1, device=like.device, dtype=_f32).expand(like.shape)
 
 
 def is_virtual(t) -> bool:
@@ -293,6 +376,14 @@ def get_conv_precision():
     return (_PREC_INV[v & 15], _PREC_INV[v >> 4])
 
 
+class _LazyGrad:
+    """A gradient that exists only as its bf16 twin: `materialize()` unpacks it for the rare fp32 consumer."""
+    _b3d_virtual = True
+
+    def __init__(self, shape, twin):
+        self.shape, self._p16_list = tuple(shape), [twin]
+
+
 def _materialize_from(shape, srcs):
     out = torch.empty(tuple(shape), device=srcs[0].device, dtype=_f32)
     o = 0
@@ -332,6 +423,7 @@ class Conv3dFn(Function):
 
     @staticmethod
     def forward(ctx, x, w, bias, stride, transposed, act, gn_groups, want_gap, share_x=False):
+        ctx.set_materialize_grads(False)       # no zero tensors for the statistics / pooling outputs in backward
         ctx.share_x = bool(share_x)
         B, D, H, W_, Cin = x.shape
         k = w.shape[0]
@@ -359,6 +451,8 @@ class Conv3dFn(Function):
             wp = pack_weights(w, False, stride, transposed)
         elif USE_TC["on"] and getattr(w, "_b3d_flat", None) is not None and tc_supported(w, stride, transposed, True):
             _register_pack(w._b3d_flat, w, True, stride, transposed)     # forward on CUDA cores, data gradient on TC
+        nv = B * (D * H * W_ if transposed else S)      # voxels the FLOP formula counts (transposed: input voxels)
+        _tag_conv(w, nv, stride, transposed)
         if use16:
             _call("b3d_conv3d_fwd_p16", *_pad4(srcs), w, bias, y, stride, int(transposed), int(act), stats,
                   gn_groups or 1, gap, 0, wp)
@@ -366,28 +460,39 @@ class Conv3dFn(Function):
             _call("b3d_conv3d_fwd", x, w, bias, y, stride, int(transposed), int(act), stats, gn_groups or 1, gap, 0, wp)
         ctx.save_for_backward(None if use16 and is_virtual(x) else x, w, y if act else None)
         ctx.srcs = srcs if srcs is not None and td is not None and srcs[0].dtype == td else None
+        ctx.srcs_w = sources_w(x) if ctx.srcs is not None else None
         ctx.xshape = tuple(x.shape)
+        ctx.nv = nv
         ctx.cfg = (stride, transposed, act, bias is not None)
         ctx.params = (w, bias)
-        y._b3d_bias = bias          # lets the kernel that will produce dy write this conv's bias gradient (column sums)
-        # ... and tells it whether this conv's backward can work from a bf16 twin of dy alone
-        ctx.f32_grad = not (ctx.srcs is not None and twin_dtype(True) is not None and lib.b3d_conv3d_wgrad_p16_plan(
+        # Mailbox shared with the ONE consumer of y (GroupNorm or the block epilogue; they pick it up in their forward):
+        # it tells that kernel's backward which bias to write the column sums of dy into and whether this conv's
+        # backward can work from a bf16 twin of dy alone, and carries the twin / bias gradient back to this conv's
+        # backward.  (Python attributes on the gradient tensors themselves do not survive the autograd engine.)
+        f32_grad = not (ctx.srcs_w is not None and twin_dtype(True) == torch.bfloat16 and lib.b3d_conv3d_wgrad_p16_plan(
             k, stride, int(transposed), Cin, Cout, od[2]) != 0)
-        y._b3d_f32_grad = ctx.f32_grad
+        ctx.mb = y._b3d_mb = {"bias": bias, "f32_grad": f32_grad}
         outs = (y, stats, gap)
         ctx.mark_non_differentiable(*[t for t in (stats, gap) if t is not None])
         return outs
 
     @staticmethod
     def backward(ctx, dy, _ds, _dg):
+        if dy is None:                         # output unused by the loss (grads are not zero-materialised)
+            return (None,) * 9
         x, w, y = ctx.saved_tensors
         srcs = ctx.srcs
         stride, transposed, act, has_bias = ctx.cfg
-        dy16 = getattr(dy, "_p16", None)
-        dbias = getattr(dy, "_dbias", None)          # (tensor, written directly into the flat gradient buffer?)
+        mb = ctx.mb
+        dy16 = mb.pop("dy16", None)                  # bf16 twin of dy left by the kernel that produced dy
+        dbias = mb.pop("dbias", None)                # (tensor, written directly into the flat gradient buffer?)
+        dy_real = mb.pop("dy_real", True)            # False: `dy` is a placeholder, only the twin holds the gradient
         td = twin_dtype(True)
         if dy16 is not None and dy16.dtype != td:
-            dy16 = None
+            dy = dy if dy_real else _materialize_from(dy.shape, [dy16])
+            dy16, dy_real = None, True
+        if not dy_real:
+            dy = _LazyGrad(dy.shape, dy16)
         if act:
             dy = materialize(dy)
             t = torch.empty_like(dy)
@@ -397,7 +502,8 @@ class Conv3dFn(Function):
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         tcd = bool(need_dx and USE_TC["on"] and tc_supported(w, stride, transposed, True))
         plan = 0
-        if need_dw and td is not None and srcs is not None and USE_TC["on"]:
+        srcs_w = ctx.srcs_w
+        if need_dw and td == torch.bfloat16 and srcs_w is not None and USE_TC["on"]:
             plan = lib.b3d_conv3d_wgrad_p16_plan(k, stride, int(transposed), cin, cout, dy.shape[3])
         pw, pb = ctx.params
         db = db_direct = None
@@ -416,6 +522,7 @@ class Conv3dFn(Function):
         if need_dx:
             dx = torch.empty(ctx.xshape, device=w.device, dtype=_f32)
             wp = pack_weights(w, True, stride, transposed) if tcd else None
+            _tag_conv(w, ctx.nv, stride, transposed)
             if tcd and dy16 is not None:
                 _call("b3d_conv3d_dgrad_p16", dy16, w, dx, stride, int(transposed), 0, wp)
             else:
@@ -426,12 +533,12 @@ class Conv3dFn(Function):
             if plan and dy16 is not None:
                 scratch = None
                 if plan == 2:
-                    big = dy16 if transposed else srcs[0]
-                    n = dy16.numel() if transposed else sum(t.numel() for t in srcs)
-                    scratch = torch.empty(n, device=w.device, dtype=big.dtype)
+                    n = dy16.numel() if transposed else sum(t.numel() for t in srcs_w)
+                    scratch = torch.empty(n, device=w.device, dtype=torch.bfloat16)
                 elif plan == 3:
-                    scratch = torch.empty(dy16.numel(), device=w.device, dtype=dy16.dtype)
-                xs = [_p16_cat(srcs)] if transposed else srcs
+                    scratch = torch.empty(dy16.numel(), device=w.device, dtype=torch.bfloat16)
+                xs = [_p16_cat(srcs_w)] if transposed else srcs_w
+                _tag_conv(w, ctx.nv, stride, transposed)
                 _call("b3d_conv3d_wgrad_p16", *_pad4(xs), dy16, dw, stride, int(transposed), scratch)
                 if has_bias and not bias_done:
                     _call("b3d_colsum", materialize(dy), db)
@@ -456,6 +563,7 @@ class Conv3dFn(Function):
                             if key is not None:
                                 _XB_CACHE[key] = xb
                         yb = torch.empty(dy.numel() // dy.shape[-1] * yc.value, device=x.device, dtype=torch.bfloat16)
+                _tag_conv(w, ctx.nv, stride, transposed)
                 _call("b3d_conv3d_wgrad", x, dy, dw, None if bias_done else db, stride, int(transposed), xb, yb, ready)
             _grad_done(pw, dw_direct)
             if has_bias:
@@ -486,9 +594,9 @@ class GroupNormFn(Function):
     conv output with exactly one consumer — no fp32 dx at all when the twin can be used."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, stats, groups, eps, relu, operand_only=False):
-        ctx.bias_param = getattr(x, "_b3d_bias", None)
-        ctx.f32_grad = getattr(x, "_b3d_f32_grad", True)
+    def forward(ctx, x, gamma, beta, stats, groups, eps, relu, operand_only=False, grad_enabled=True):
+        ctx.set_materialize_grads(False)       # the twin outputs get no gradient: do not let autograd zero-fill them
+        ctx.mb = getattr(x, "_b3d_mb", None)         # mailbox of the conv that produced x (see Conv3dFn.forward)
         x = materialize(x)
         _check(x)
         C = x.shape[-1]
@@ -504,23 +612,26 @@ class GroupNormFn(Function):
         L = x.numel() // x.shape[0] // groups
         twin = td is not None and p16_ok(x.shape) and L % 4 == 0
         y16 = p16_empty(x.shape, x, td) if twin else None
+        y16b = p16_empty(x.shape, x, torch.bfloat16) if twin and want_wgrad_twin(td, grad_enabled) else None
         y = None if (twin and operand_only) else torch.empty_like(x)
         if twin:
-            _call("b3d_gn_apply_p16", x, stats, gamma, beta, y, y16, groups, float(eps), int(relu))
+            _call("b3d_gn_apply_p16", x, stats, gamma, beta, y, y16, y16b, groups, float(eps), int(relu))
         else:
             _call("b3d_gn_apply", x, stats, gamma, beta, y, groups, float(eps), int(relu))
         if y is None:
-            y = virtual(x.shape, x, [y16])
+            y = virtual(x.shape, x, [y16], [y16b] if y16b is not None else None)
         ctx.save_for_backward(x, gamma, beta, stats)
         ctx.cfg = (groups, float(eps), int(relu))
         ctx.params = (gamma, beta)
         if y16 is None:
-            return y, None
-        ctx.mark_non_differentiable(y16)
-        return y, y16
+            return y, None, None
+        ctx.mark_non_differentiable(*[t for t in (y16, y16b) if t is not None])
+        return y, y16, y16b
 
     @staticmethod
-    def backward(ctx, dy, _d16=None):
+    def backward(ctx, dy, _d16=None, _d16b=None):
+        if dy is None:
+            return (None,) * 9
         x, gamma, beta, stats = ctx.saved_tensors
         groups, eps, relu = ctx.cfg
         dy = materialize(dy)
@@ -534,25 +645,24 @@ class GroupNormFn(Function):
         td = twin_dtype(True)
         C = x.shape[-1]
         L = x.numel() // x.shape[0] // groups
-        twin = td is not None and p16_ok(x.shape) and L % 4 == 0
+        mb = ctx.mb
+        twin = td is not None and p16_ok(x.shape) and L % 4 == 0 and mb is not None
         if twin:
             dx16 = p16_empty(x.shape, x, td)
-            bias = ctx.bias_param
+            bias = mb["bias"]
             fused_bias = bias is not None and 1024 % C == 0 and L % C == 0
             dbias = _grad_target(bias) if fused_bias else None
             # the producing conv takes its weight gradient through the fp32 entry point (narrow layers): keep fp32 too
-            dx = torch.empty_like(x) if ctx.f32_grad else None
+            dx = torch.empty_like(x) if mb["f32_grad"] else None
             _call("b3d_gn_bwd_apply_p16", dy, x, stats, gamma, beta, csum, dx, dx16, dbias[0] if fused_bias else None,
                   groups, eps, relu)
+            mb["dy16"], mb["dbias"], mb["dy_real"] = dx16, dbias, dx is not None
             if dx is None:
-                dx = virtual(x.shape, x, [dx16])
-            dx._p16 = dx16
-            if fused_bias:
-                dx._dbias = dbias
+                dx = _grad_placeholder(x)
         else:
             dx = torch.empty_like(x)
             _call("b3d_gn_bwd_apply", dy, x, stats, gamma, beta, csum, dx, groups, eps, relu)
-        return dx, (None if dg_direct else dgamma), (None if db_direct else dbeta), None, None, None, None, None
+        return dx, (None if dg_direct else dgamma), (None if db_direct else dbeta), None, None, None, None, None, None
 
 
 class GroupNormChannelFn(Function):
@@ -599,9 +709,10 @@ def group_norm(x, gamma, beta, stats=None, groups=8, eps=1e-5, relu=False, chann
         return GroupNormChannelFn.apply(x, gamma, beta, groups, eps, relu)
     if ctx is not None:        # chunk statistics of the WHOLE volume: partial sums + all-reduce
         return ctx.group_norm(x, gamma, beta, groups, eps, relu)
-    y, y16 = GroupNormFn.apply(x, gamma, beta, stats, groups, eps, relu, bool(operand_only))
+    y, y16, y16b = GroupNormFn.apply(x, gamma, beta, stats, groups, eps, relu, bool(operand_only),
+                                     torch.is_grad_enabled())
     if y16 is not None and not is_virtual(y):
-        y._p16 = y16
+        _attach(y, y16, y16b)
     return y
 
 
@@ -639,9 +750,11 @@ class BlockEpilogueFn(Function):
     pointwise and the second conv) when those convs can use them."""
 
     @staticmethod
-    def forward(ctx, res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps, operand_only=False):
+    def forward(ctx, res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps, operand_only=False,
+                grad_enabled=True):
+        ctx.set_materialize_grads(False)
         _check(res)
-        attrs = [(getattr(t, "_b3d_bias", None), getattr(t, "_b3d_f32_grad", True)) for t in (res, h2)]
+        ctx.mbs = (getattr(res, "_b3d_mb", None), getattr(h2, "_b3d_mb", None))
         res, h2 = res.contiguous(), materialize(h2)
         B, F = res.shape[0], res.shape[-1]
         ctx_s = _slab.current()
@@ -656,28 +769,29 @@ class BlockEpilogueFn(Function):
         twin = td is not None and p16_ok(res.shape)
         if twin:
             out16 = p16_empty(res.shape, res, td)
+            out16b = p16_empty(res.shape, res, torch.bfloat16) if want_wgrad_twin(td, grad_enabled) else None
             out = None if operand_only else torch.empty_like(res)
             _call("b3d_block_epilogue_fwd_p16", res, h2, stats2, gamma2 if has_gn else None, beta2 if has_gn else None,
-                  wsp_v, chse, out, out16, groups, float(eps), int(has_gn))
+                  wsp_v, chse, out, out16, out16b, groups, float(eps), int(has_gn))
             if out is None:
-                out = virtual(res.shape, res, [out16])
+                out = virtual(res.shape, res, [out16], [out16b] if out16b is not None else None)
         else:
-            out16 = None
+            out16 = out16b = None
             out = _new_act(res.shape, res)
             _call("b3d_block_epilogue_fwd", res, h2, stats2, gamma2 if has_gn else None, beta2 if has_gn else None,
                   wsp_v, chse, out, groups, float(eps), int(has_gn))
         ctx.save_for_backward(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, hidden, chse)
         ctx.cfg = (groups, float(eps), has_gn, inv)
         ctx.params = (gamma2, beta2, wsp, w1, w2)
-        ctx.bias_params = (attrs[0][0], attrs[1][0])
-        ctx.f32_grads = (attrs[0][1], attrs[1][1])
         if out16 is None:
-            return out, None
-        ctx.mark_non_differentiable(out16)
-        return out, out16
+            return out, None, None
+        ctx.mark_non_differentiable(*[t for t in (out16, out16b) if t is not None])
+        return out, out16, out16b
 
     @staticmethod
-    def backward(ctx, dout, _d16=None):
+    def backward(ctx, dout, _d16=None, _d16b=None):
+        if dout is None:
+            return (None,) * 13
         res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, hidden, chse = ctx.saved_tensors
         groups, eps, has_gn, inv = ctx.cfg
         dout = materialize(dout)
@@ -697,26 +811,26 @@ class BlockEpilogueFn(Function):
         for p_, d_ in ((pwsp, dwsp_direct), (pg, dg_direct), (pb, db_direct), (pw1, dw1_direct), (pw2, dw2_direct)):
             _grad_done(p_, d_)
         td = twin_dtype(True)
-        twin = td is not None and p16_ok(res.shape) and has_gn
+        mb_res, mb_h2 = ctx.mbs
+        twin = td is not None and p16_ok(res.shape) and has_gn and mb_res is not None and mb_h2 is not None
         if twin:
-            b_res, b_h2 = ctx.bias_params
+            b_res, b_h2 = mb_res["bias"], mb_h2["bias"]
             fused_bias = b_res is not None and b_h2 is not None
             dres16, dh216 = p16_empty(res.shape, res, td), p16_empty(res.shape, res, td)
             # the first block's pointwise conv (2 input channels) takes its weight gradient through the fp32 entry point
-            dres = torch.empty_like(res) if ctx.f32_grads[0] else None
-            dh2 = torch.empty_like(res) if ctx.f32_grads[1] else None
+            dres = torch.empty_like(res) if mb_res["f32_grad"] else None
+            dh2 = torch.empty_like(res) if mb_h2["f32_grad"] else None
             tb_res = _grad_target(b_res) if fused_bias else None
             tb_h2 = _grad_target(b_h2) if fused_bias else None
             _call("b3d_block_epilogue_bwd_apply_p16", dout, res, h2, stats2, gamma2, beta2, wsp_v, chse, dgap, csum,
                   dres, dh2, dres16, dh216, tb_res[0] if fused_bias else None, tb_h2[0] if fused_bias else None,
                   groups, eps, 1)
+            mb_res["dy16"], mb_res["dbias"], mb_res["dy_real"] = dres16, tb_res, dres is not None
+            mb_h2["dy16"], mb_h2["dbias"], mb_h2["dy_real"] = dh216, tb_h2, dh2 is not None
             if dres is None:
-                dres = virtual(res.shape, res, [dres16])
+                dres = _grad_placeholder(res)
             if dh2 is None:
-                dh2 = virtual(res.shape, res, [dh216])
-            dres._p16, dh2._p16 = dres16, dh216
-            if fused_bias:
-                dres._dbias, dh2._dbias = tb_res, tb_h2
+                dh2 = _grad_placeholder(res)
         else:
             dres = torch.empty_like(res)
             dh2 = torch.empty_like(h2) if has_gn else None
@@ -727,14 +841,15 @@ class BlockEpilogueFn(Function):
                 dh2 = dout
         return (dres, dh2, None, None if dg_direct else dgamma, None if db_direct else dbeta,
                 None if dwsp_direct else dwsp.reshape(wsp.shape), None, None if dw1_direct else dw1,
-                None if dw2_direct else dw2, None, None, None)
+                None if dw2_direct else dw2, None, None, None, None)
 
 
 def block_epilogue(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups=8, eps=1e-5, keep_f32=False):
     operand_only = FUSED["on"] and _slab.current() is None and not keep_f32
-    out, out16 = BlockEpilogueFn.apply(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps, operand_only)
+    out, out16, out16b = BlockEpilogueFn.apply(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps,
+                                               operand_only, torch.is_grad_enabled())
     if out16 is not None and not is_virtual(out):
-        out._p16 = out16
+        _attach(out, out16, out16b)
     return out
 
 
@@ -797,10 +912,14 @@ def vae_sample(proj, eps):
 
 
 class DiceVAELossFn(Function):
-    """util.py:13-24 as one reduction pass + a scalar finalize; backward is one elementwise pass."""
+    """util.py:13-24 as one reduction pass + a scalar finalize; backward is one elementwise pass.
+
+    `dp` = (process group, world size): the batch-global objective under data parallelism — the reference sums I, P, T
+    over the batch axis (util.py:11,18-20), so with one crop per rank the 3C+2 partial sums are all-reduced before the
+    loss is formed; every rank then holds the loss of the WHOLE batch and backward yields its part of that gradient."""
 
     @staticmethod
-    def forward(ctx, x, y, y_pred, y_vae, z_mean, z_logvar):
+    def forward(ctx, x, y, y_pred, y_vae, z_mean, z_logvar, dp=None):
         _check(y_pred, "y_pred")
         C = y_pred.shape[-1]
         vae = y_vae is not None
@@ -810,6 +929,13 @@ class DiceVAELossFn(Function):
         out = _new((4,), y_pred)
         _call("b3d_loss_fwd", x if vae else None, y, y_pred, y_vae, z_mean if vae else None,
               z_logvar if vae else None, sums, out)
+        ctx.replicas = 1
+        if dp is not None and dp[1] > 1:
+            import torch.distributed as dist
+            group, world = dp
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            _call("b3d_loss_finalize", sums, out, world * x.numel() if vae else 0, world * z_mean.numel() if vae else 0)
+            ctx.replicas = world
         ctx.save_for_backward(x if vae else None, y, y_pred, y_vae, z_mean if vae else None,
                               z_logvar if vae else None, sums)
         ctx.parts = out
@@ -824,12 +950,15 @@ class DiceVAELossFn(Function):
         dyv = torch.empty_like(y_vae) if vae else None
         dmu = torch.empty_like(z_mean) if vae else None
         dlv = torch.empty_like(z_logvar) if vae else None
-        _call("b3d_loss_bwd", x, y, y_pred, y_vae, z_mean, z_logvar, sums, g, dyp, dyv, dmu, dlv)
-        return None, None, dyp, dyv, dmu, dlv
+        if ctx.replicas > 1:
+            _call("b3d_loss_bwd_dp", x, y, y_pred, y_vae, z_mean, z_logvar, sums, g, dyp, dyv, dmu, dlv, ctx.replicas)
+        else:
+            _call("b3d_loss_bwd", x, y, y_pred, y_vae, z_mean, z_logvar, sums, g, dyp, dyv, dmu, dlv)
+        return None, None, dyp, dyv, dmu, dlv, None
 
 
-def dice_vae_loss(x, y, y_pred, y_vae=None, z_mean=None, z_logvar=None):
-    return DiceVAELossFn.apply(x, y, y_pred, y_vae, z_mean, z_logvar)
+def dice_vae_loss(x, y, y_pred, y_vae=None, z_mean=None, z_logvar=None, dp=None):
+    return DiceVAELossFn.apply(x, y, y_pred, y_vae, z_mean, z_logvar, dp)
 
 
 def dice_coefficient(y_true, y_pred, reduce_w=False):
@@ -932,8 +1061,10 @@ class VirtualConcatFn(Function):
     def forward(ctx, *xs):
         C = [t.shape[-1] for t in xs]
         twins = [tw for t in xs for tw in sources(t)]
+        wl = [sources_w(t) for t in xs]
+        wtwins = [tw for l in wl for tw in l] if all(l is not None for l in wl) else None
         ctx.C = C
-        return virtual(tuple(xs[0].shape[:-1]) + (sum(C),), twins[0], twins)
+        return virtual(tuple(xs[0].shape[:-1]) + (sum(C),), twins[0], twins, wtwins)
 
     @staticmethod
     def backward(ctx, d):

@@ -95,11 +95,41 @@ class DataParallel:
     on the path.  Works under CUDA-graph capture (the collectives are captured on the side stream)."""
 
     def __init__(self, model: Model, optimizer: ScheduledOptim, world_size: int, n_buckets: int = 4,
-                 process_group=None, overlap: bool = True):
+                 process_group=None, overlap: bool = True, objective: str = "replica_mean", loss_fn=None,
+                 sync_weights: bool = True):
+        """objective (SURVEY F6 — the reference's Dice sums over the batch axis, util.py:11,18-20):
+          'replica_mean'  every rank optimises the loss of its own crop(s); gradients are averaged — the mean of
+                          per-crop DiceVAE losses (what `--batch_size 1` training sees, averaged over N crops);
+          'global_batch'  the reference's `--batch_size N` objective: `loss_fn` all-reduces its 3C+2 partial sums in the
+                          forward (one tiny collective), every rank holds the loss of the whole batch, gradients are
+                          SUMMED.  Pass the DiceVAELoss instance as `loss_fn`.
+        sync_weights: broadcast rank 0's parameters (and check nothing else diverged) so that replicas cannot start
+        from different weights silently."""
         import torch.distributed as dist
+        if objective not in ("replica_mean", "global_batch"):
+            raise ValueError(objective)
         self.dist, self.group, self.world = dist, process_group, world_size
         self.model, self.flat = model, model.flatten_parameters()
-        optimizer.grad_scale = 1.0 / world_size
+        self.objective = objective
+        if objective == "global_batch":
+            if loss_fn is None:
+                raise ValueError("objective='global_batch' needs the DiceVAELoss instance (loss_fn=)")
+            loss_fn.dp = (process_group, world_size)
+            optimizer.grad_scale = 1.0
+        else:
+            optimizer.grad_scale = 1.0 / world_size
+        if sync_weights and world_size > 1 and dist.is_initialized():
+            dist.broadcast(self.flat.theta, 0, group=process_group)
+            for mv in getattr(optimizer, "_slots", {}).get(id(self.flat), ()):
+                dist.broadcast(mv, 0, group=process_group)
+            if getattr(optimizer, "_state", None) is not None:
+                dist.broadcast(optimizer._state, 0, group=process_group)
+            if self.flat.theta.is_cuda:
+                ops.repack_all(self.flat)
+            # different crops need different dropout masks: fold the rank into the dropout seed
+            drop = getattr(getattr(model, "encoder", None), "dropout", None)
+            if drop is not None:
+                drop.seed = (int(drop.seed) + 7919 * dist.get_rank(process_group)) & 0x7FFFFFFF
         self.overlap = overlap and self.flat.grad.is_cuda
         self.side = torch.cuda.Stream() if self.flat.grad.is_cuda else None
         self.buckets = self.plan_buckets(self.flat, n_buckets)
@@ -172,6 +202,10 @@ class GraphedTrainStep:
         if flat is not None:
             optimizer._ensure_state(flat.theta.device)
             optimizer._mv(id(flat), flat.theta)
+        # the warm-up steps (allocator / lazy-initialisation warm-up before capture) must not train: weights, Adam
+        # moments, step count and the dropout counter are snapshotted and restored, so that building the graphed step
+        # leaves the training state exactly where it was
+        snap = self._snapshot(flat, optimizer, model) if (flat is not None and warmup > 0) else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -179,6 +213,8 @@ class GraphedTrainStep:
                 train_step(*self._args, self.x, self.y, dp=dp)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        if snap is not None:
+            self._restore(snap, flat, optimizer, model)
         if model.flat is not None and model.flat.packs:
             ops.ensure_pack_table(model.flat)
         n0 = ops.LAUNCHES["n"]
@@ -186,6 +222,25 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.out = train_step(*self._args, self.x, self.y, dp=dp)
         self.launches_per_step = ops.LAUNCHES["n"] - n0
+
+    @staticmethod
+    def _snapshot(flat, optimizer, model):
+        m, v = optimizer._mv(id(flat), flat.theta)
+        drop = getattr(getattr(model, "encoder", None), "dropout", None)
+        cnt = getattr(drop, "_counter", None)
+        return (flat.theta.clone(), m.clone(), v.clone(), optimizer._state.clone(), None if cnt is None else cnt.clone())
+
+    @staticmethod
+    def _restore(snap, flat, optimizer, model):
+        th, m0, v0, st, cnt = snap
+        m, v = optimizer._mv(id(flat), flat.theta)
+        with torch.no_grad():
+            flat.theta.copy_(th); m.copy_(m0); v.copy_(v0); optimizer._state.copy_(st)
+            drop = getattr(getattr(model, "encoder", None), "dropout", None)
+            if cnt is not None and getattr(drop, "_counter", None) is not None:
+                drop._counter.copy_(cnt)
+        ops.repack_all(flat)
+        torch.cuda.synchronize()
 
     def __call__(self, x=None, y=None):
         if x is not None:

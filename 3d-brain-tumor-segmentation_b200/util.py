@@ -15,12 +15,15 @@ class DiceVAELoss(object):
         from .keras_compat import check_data_format
         self.data_format = check_data_format(data_format)
         self.axis = (0, 1, 2, 3) if data_format == 'channels_last' else (0, 2, 3, 4)
+        # data parallelism with the reference's batch-global Dice: (process group, world size), set by
+        # train.DataParallel(objective='global_batch'); None = this process's batch is the whole batch
+        self.dp = None
 
     def __call__(self, x, y, y_pred, y_vae, z_mean, z_logvar, sample_weight=None):
         if self.data_format == 'channels_first':       # NCDHW arguments: the sums are layout-independent
             from .keras_compat import map5d
             x, y, y_pred, y_vae = (map5d(t, ops.to_channels_last) for t in (x, y, y_pred, y_vae))
-        return ops.dice_vae_loss(x, y, y_pred, y_vae, z_mean, z_logvar)
+        return ops.dice_vae_loss(x, y, y_pred, y_vae, z_mean, z_logvar, self.dp)
 
 
 class DiceCoefficient(object):
@@ -90,9 +93,14 @@ class ScheduledOptim(object):
         (data-parallel mode: it must not be averaged over ranks)."""
         self._ensure_state(flat.theta.device)
         m, v = self._mv(id(flat), flat.theta)
+        fused = l2_in_step and flat.l2 is not None
+        if l2_in_step and not fused:
+            # several L2 coefficients (Model(l2_scale != 1e-5)): the kernel fuses one range only, so the regulariser
+            # gradient is added per group before the step, pre-multiplied by 1/grad_scale (the kernel scales g)
+            flat.add_l2_grad(1.0 / float(self.grad_scale))
         ops._call("b3d_adam_step", flat.theta, m, v, flat.grad, self._state, self.beta_1, self.beta_2,
-                  self.epsilon, float(self.grad_scale), 2.0 * float(flat.l2) if l2_in_step else 0.0,
-                  int(flat.reg_end) if l2_in_step else 0, 1)
+                  self.epsilon, float(self.grad_scale), 2.0 * float(flat.l2) if fused else 0.0,
+                  int(flat.reg_end) if fused else 0, 1)
         ops.repack_all(flat)          # packed conv operands follow the weights (one launch)
 
     def apply_gradients(self, grads_and_vars, flat=None):

@@ -104,33 +104,31 @@ def cpu_reference_step_fn(crop, threads=None):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU math for the path on this box's host cores."""
+    """--impl reference: the reference's own CPU math for the path on this box's host cores, ALWAYS on the stated
+    configuration (full 128^3 crop).  When the host is too slow for `--steps K --warmup W` full crops within the time
+    budget, fewer steps are timed (never a smaller crop): `steps` in the line is what was actually timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # bounded sample: a full 128^3 crop per step when the run fits a few minutes, else a 64^3 crop scaled by 8
-    step64, threads = cpu_reference_step_fn((64, 64, 64))
-    t0 = time.time(); step64(); t64 = time.time() - t0
-    full = 8.0 * t64 * (args.steps + args.warmup) < 240.0
-    if full:
-        step, _ = cpu_reference_step_fn(CROP)
-        scale, sample = 1.0, f"{args.steps} full 128^3 crops (fwd+loss+bwd+Adam), fp32 torch-CPU oracle"
-    else:
-        step, scale = step64, 8.0
-        sample = (f"{args.steps} crops of 64^3 (1/8 of a 128^3 crop's voxels), time scaled x8, "
-                  "fp32 torch-CPU oracle")
-    for _ in range(args.warmup):
+    step, threads = cpu_reference_step_fn(CROP)
+    t0 = time.time(); step(); t1 = time.time() - t0          # first step: also the probe (untimed warm-up)
+    budget = float(os.environ.get("B3D_REF_BUDGET_S", "200"))
+    warm = max(0, min(args.warmup - 1, int(0.2 * budget / t1)))
+    steps = max(1, min(args.steps, int((budget - (1 + warm) * t1) / t1)))
+    for _ in range(warm):
         step()
     t0 = time.time()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
-    dt = (time.time() - t0) * scale
-    val = args.steps / dt
+    dt = time.time() - t0
+    val = steps / dt
+    sample = (f"{steps} full 128^3 crops (fwd+loss+bwd+Adam), fp32 torch-CPU oracle"
+              + ("" if steps == args.steps else f"; {args.steps} requested, bounded by a {budget:.0f} s budget"))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "crops/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "steps": steps, "warmup": 1 + warm, "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "train_128cube_b1_default_model", "crop": list(CROP), "in_ch": 2, "out_ch": 3,
@@ -145,7 +143,8 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 def measure_conv_roofline(b3d, torch, dev, steps=20):
     """Dominant kernel: the tcgen05 3x3x3 conv.  Timed in isolation on the largest layer of the default
-    model (dec L0 conv1: 128^3, Cin 32 -> Cout 16, 58.0 GFLOP) with CUDA events on the launching stream."""
+    model (dec L0 conv1: 128^3, Cin 32 -> Cout 16, 58.0 GFLOP) with CUDA events on the launching stream, fed the way
+    the training step feeds it: the input as two 16-channel fp16 P16 twins (decoder.py:75 concat as a source list)."""
     ops = b3d.ops
     cin, cout = 32, 16
     x = torch.randn((1,) + CROP + (cin,), device=dev)
@@ -154,8 +153,9 @@ def measure_conv_roofline(b3d, torch, dev, steps=20):
     y = torch.empty((1,) + CROP + (cout,), device=dev)
     stats = torch.empty(1, 8, 2, dtype=torch.float64, device=dev)
     wp = ops.pack_weights(w, False)
+    tw = [ops.to_p16(x[..., :16].contiguous(), torch.float16), ops.to_p16(x[..., 16:].contiguous(), torch.float16)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    call = lambda: ops._call("b3d_conv3d_fwd", x, w, bias, y, 1, 0, 0, stats, 8, None, 0, wp)
+    call = lambda: ops._call("b3d_conv3d_fwd_p16", tw[0], tw[1], None, None, w, bias, y, 1, 0, 0, stats, 8, None, 0, wp)
     for _ in range(3):
         call()
     times = []
@@ -166,8 +166,102 @@ def measure_conv_roofline(b3d, torch, dev, steps=20):
         e1.synchronize()
         times.append(e0.elapsed_time(e1))
     ms = statistics.median(times)
-    flops = 2.0 * CROP[0] * CROP[1] * CROP[2] * 27 * cin * cout
-    return ms, flops
+    vox = CROP[0] * CROP[1] * CROP[2]
+    flops = 2.0 * vox * 27 * cin * cout
+    alg_bytes = vox * (2.0 * cin + 4.0 * cout)          # fp16 operand read once + fp32 result written once
+    return ms, flops, alg_bytes
+
+
+def roofline_capture():
+    """ncu evidence of the kernel `roofline` reports (committed under profiles/, produced by tools/ncu_summary.py from
+    the `ncu --set full` capture of the SAME kernel variant on the same layer): dram traffic and both tensor-pipe
+    readings.  None when the file is missing."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_kernel.json")))
+    except Exception:
+        return None
+
+
+def measure_step_classes(b3d, torch, model, opt, xd, yd, pk):
+    """In-step aggregates: one EAGER training step with CUDA events around every C-ABI call
+    (ops.profile_calls), summed per kernel class.  Conv classes carry their algorithmic FLOPs -> achieved TF/s inside
+    the step, next to the tensor peak measured for a kernel inside a long step (bf16_tflops_sustained)."""
+    ops = b3d.ops
+    args = (model, opt, b3d.DiceVAELoss(), b3d.DiceCoefficient())
+    b3d.train_step(*args, xd, yd)
+    torch.cuda.synchronize()
+    with ops.profile_calls() as rows:
+        b3d.train_step(*args, xd, yd)
+        torch.cuda.synchronize()
+    agg = {}
+    for name, tag, e0, e1 in rows:
+        ms = e0.elapsed_time(e1)
+        key = name.replace("b3d_", "")
+        if tag is not None:
+            pas = "wgrad" if "wgrad" in name else ("dgrad" if "dgrad" in name else "fwd")
+            key = f"conv_{tag[0]}_{pas}"
+        a = agg.setdefault(key, [0, 0.0, 0.0])
+        a[0] += 1; a[1] += ms; a[2] += tag[1] if tag is not None else 0.0
+    tot = sum(v[1] for v in agg.values())
+    conv = {k: v for k, v in agg.items() if k.startswith("conv_")}
+    cls = lambda pre: [v for k, v in conv.items() if k.startswith(pre)]
+    tf = lambda vs: (sum(v[2] for v in vs) / 1e12) / (sum(v[1] for v in vs) / 1e3) if vs and sum(v[1] for v in vs) > 0 else None
+    k3 = [v for k, v in conv.items() if k.startswith("conv_k3_") and not k.endswith("wgrad")]
+    out = {"how": "one eager step, CUDA events around every C-ABI call (includes the call's memsets / helper kernels)",
+           "abi_calls": len(rows), "sum_ms": tot,
+           "k3_fwd_dgrad_tflops": tf(k3), "k3_wgrad_tflops": tf(cls("conv_k3_wgrad")),
+           "all_conv_tflops": tf(list(conv.values())),
+           "conv_ms": sum(v[1] for v in conv.values()), "conv_gflop": sum(v[2] for v in conv.values()) / 1e9,
+           "peak_tflops_sustained": pk.get("bf16_tflops_sustained"),
+           "top": [{"call": k, "n": v[0], "ms": round(v[1], 3)} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]]}
+    if out["all_conv_tflops"] and pk.get("bf16_tflops_sustained"):
+        out["all_conv_frac_of_sustained"] = out["all_conv_tflops"] / pk["bf16_tflops_sustained"]
+    return out
+
+
+def measure_config(b3d, torch, dev, name, crop, steps=5, **kw):
+    """A further BASELINE configuration as an extra entry: graphed training step (+ inference forward) of a model built
+    with **kw at `crop` (cfg 5: skull-strip 256x256x192; the CLI-default bf=32 / r=8 model of the README's V100 run)."""
+    import synthdata as R
+    in_ch, out_ch = kw.get("in_ch", 2), kw.get("out_ch", 3)
+    bf, red = kw.get("base_filters", 16), kw.get("reduction", 2)
+    p = R.init_params(R.param_shapes(in_ch=in_ch, out_ch=out_ch, base_filters=bf, reduction=red, crop=crop),
+                      dtype=torch.float32)
+    x, y, _, _ = R.synth_batch((1,) + crop, in_ch=in_ch, out_ch=out_ch, latent=bf * 4, dtype=torch.float32)
+    xd, yd = x.to(dev), y.to(dev)
+    torch.cuda.reset_peak_memory_stats()
+    model = b3d.Model(**kw)
+    with torch.no_grad():
+        model(xd, training=False, inference=False)
+    model.load_named_weights(p)
+    opt = b3d.ScheduledOptim(learning_rate=1e-4)
+    opt(epoch=0)
+    step = b3d.GraphedTrainStep(model, opt, b3d.DiceVAELoss(), b3d.DiceCoefficient(), xd, yd, warmup=2)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record(); e1.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    gi = b3d.GraphedInference(model, xd)
+    gi()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(3):
+        gi()
+    f1.record(); f1.synchronize()
+    msi = f0.elapsed_time(f1) / 3
+    vox = crop[0] * crop[1] * crop[2]
+    res = {"config": name, "crop": list(crop), "model": kw, "params": int(model.flat.total),
+           "train_ms_per_step": ms, "train_crops_per_s": 1e3 / ms, "loss": float(out[0]),
+           "inference_ms_per_forward": msi, "inference_mvoxel_per_s": vox / msi / 1e3,
+           "peak_gpu_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+    del step, gi, model
+    torch.cuda.empty_cache()
+    return res
 
 
 def measure_inference(b3d, torch, dev, model, reps=3):
@@ -274,7 +368,7 @@ def run_b3d(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     b3d = importlib.import_module(PKG)
-    from oracle import ref_model as R   # synthetic weight / input generators only (seeded numpy)
+    import synthdata as R               # seeded synthetic weights / inputs (neutral module: nothing under oracle/)
 
     # ---- model, synthetic data (rank r uses seed + 100 r), optimizer
     p = R.init_params(R.param_shapes(crop=CROP), dtype=torch.float32)
@@ -348,15 +442,26 @@ def run_b3d(args):
         finish()
         return
     pk, pk_src = peaks()
-    conv_ms, conv_flops = measure_conv_roofline(b3d, torch, dev)
+    conv_ms, conv_flops, conv_alg_bytes = measure_conv_roofline(b3d, torch, dev)
     ach = conv_flops / (conv_ms * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "conv_tc_kernel, kd-folded variant (tcgen05 kind::f16, fp16 operands, fp32 accumulate) dec.L0 conv1 "
-                                                 "128^3 32->16",
+    cap = roofline_capture()
+    roof = {"bound": "tensor",
+            "kernel": "conv_tc_kernel<TcCfg<16,8,1,3,1,OP_F16,FOLD>> (tcgen05 kind::f16, kd-folded, fp16 P16 operand fetched "
+                      "by TMA, fp32 accumulate in TMEM, fused bias + GroupNorm statistics) on dec.L0 conv1 128^3 32->16",
             "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
             "peak_source": f"{pk_src} dense bf16 burst (cuBLAS 8192^3); 16-bit operands, same tensor-pipe rate",
-            "ms_per_launch": conv_ms, "traffic": 363.6e6, "traffic_unit": "bytes/launch (dram read+write, ncu --set full, "
-            "profiles/r01_ncu_conv_tc_fp16_128cube_32to16.csv = the capture of the unfolded variant, the "
-            "kd-folded one reads the same tensors through a 8x16x8 tile; algorithmic 402.7e6)"}
+            "ms_per_launch": conv_ms, "algorithmic_flops": conv_flops, "algorithmic_bytes": conv_alg_bytes,
+            "traffic": (cap or {}).get("dram_bytes"),
+            "traffic_source": (cap or {}).get("source", "no ncu capture committed for this build"),
+            "tensor_pipe": {k: (cap or {}).get(k) for k in ("pipe_tensor_cycles_active_pct_of_peak_sustained_elapsed",
+                                                             "hmma_cycles_active_realtime_sum_over_subpipes",
+                                                             "sm_cycles_elapsed", "duration_us_under_ncu")}}
+    classes = measure_step_classes(b3d, torch, model, opt, xd, yd, pk)
+    step_tflop = 3 * FWD_GFLOP / 1e3
+    mfu = {"step_tflop": step_tflop, "achieved_tflops": step_tflop / (ms / args.steps / 1e3),
+           "peak_tflops_sustained": pk.get("bf16_tflops_sustained"),
+           "frac_of_sustained": step_tflop / (ms / args.steps / 1e3) / pk["bf16_tflops_sustained"]
+           if pk.get("bf16_tflops_sustained") else None}
     # CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -377,9 +482,17 @@ def run_b3d(args):
             "e2e": {"value": e2e_val, "unit": "crops/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": int(step.launches_per_step * args.steps),
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "step_mfu": mfu, "step_classes": classes, "cpu_baseline": cpu,
             "inference": measure_inference(b3d, torch, dev, model) if world == 1 else inf_sharded,
             "inference_tta": tta}
+    if world == 1 and not args.no_extra_configs:
+        del step
+        torch.cuda.empty_cache()
+        line["extra_configs"] = [
+            measure_config(b3d, torch, dev, "cfg5 skull-strip (in 1 / out 1) 256x256x192", (256, 256, 192), steps=3,
+                           in_ch=1, out_ch=1),
+            measure_config(b3d, torch, dev, "CLI defaults base_filters=32 reduction=8 (README V100 configuration), 128^3",
+                           CROP, steps=5, base_filters=32, reduction=8)]
     print(json.dumps(line), flush=True)
     finish()
 
@@ -391,6 +504,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b3d", choices=["b3d", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -181,6 +181,15 @@ int b3d_loss_fwd(const DLTensor* x, const DLTensor* y, const DLTensor* y_pred, c
 int b3d_loss_bwd(const DLTensor* x, const DLTensor* y, const DLTensor* y_pred, const DLTensor* y_vae,
                  const DLTensor* z_mean, const DLTensor* z_logvar, const DLTensor* sums, const DLTensor* gout,
                  DLTensor* dy_pred, DLTensor* dy_vae, DLTensor* dz_mean, DLTensor* dz_logvar, void* stream);
+/* Batch-global objective under data parallelism (util.py:11,18-20 sums I, P, T over the BATCH axis too): each
+ * rank runs b3d_loss_fwd on its crops, all-reduces (sum) the 3C+2 fp64 `sums` over the `replicas` ranks, calls
+ * b3d_loss_finalize with the global element counts (out = the loss of the whole batch, identical on every rank) and
+ * b3d_loss_bwd_dp for this rank's part of the gradient; the parameter gradients are then SUMMED over ranks, not averaged. */
+int b3d_loss_finalize(const DLTensor* sums, DLTensor* out, long long n_rec_total, long long n_lat_total, void* stream);
+int b3d_loss_bwd_dp(const DLTensor* x, const DLTensor* y, const DLTensor* y_pred, const DLTensor* y_vae,
+                    const DLTensor* z_mean, const DLTensor* z_logvar, const DLTensor* sums, const DLTensor* gout,
+                    DLTensor* dy_pred, DLTensor* dy_vae, DLTensor* dz_mean, DLTensor* dz_logvar, int replicas,
+                    void* stream);
 int b3d_dice_coeff(const DLTensor* y, const DLTensor* y_pred, DLTensor* acc /*fp32 [W*C*3]*/,
                    DLTensor* out /*fp32 [2] macro, micro*/, int reduce_w /*1: channels_first macro (util.py:36)*/,
                    void* stream);
@@ -258,8 +267,10 @@ int b3d_p16_unpack(const DLTensor* src /*P16*/, DLTensor* y /*fp32 NDHWC, may be
 int b3d_p16_copy_planes(const DLTensor* src /*P16*/, DLTensor* dst /*P16, wider*/, int c8off, void* stream);
 int b3d_colsum(const DLTensor* x /*fp32 NDHWC*/, DLTensor* out /*fp32 [C]*/, void* stream);
 /* the three conv passes with P16 input operands (same semantics as b3d_conv3d_fwd / _dgrad / _wgrad; tcgen05 path only:
- * wpacked is required).  x0..x3: the sources whose channels are concatenated (x1..x3 nullable), all fp16 (forward
- * operand type fp16) or all bf16.  The weight gradient does NOT produce the bias gradient on this path: it is emitted
+ * wpacked is required).  x0..x3: the sources whose channels are concatenated (x1..x3 nullable), all of the pass's MMA
+ * operand type (forward: fp16 by default; data gradient: bf16).  The weight gradient takes bf16 twins of BOTH operands
+ * (tcgen05 kind::f16 has one operand type for A and B; mixing f16 with bf16 is an illegal instruction), which is why
+ * forward activations carry a second, bf16 twin (y16b / out16b below) when the forward type is fp16.  The weight gradient does NOT produce the bias gradient on this path: it is emitted
  * by the kernel that writes dy (`dbias` of b3d_gn_bwd_apply_p16 / b3d_block_epilogue_bwd_apply_p16, `colsum` of
  * b3d_p16_pack).  scratch (nullable, 16-bit, 1-D): see b3d_conv3d_wgrad_p16_plan. */
 int b3d_conv3d_fwd_p16(const DLTensor* x0, const DLTensor* x1, const DLTensor* x2, const DLTensor* x3, const DLTensor* w,
@@ -278,13 +289,15 @@ int b3d_conv3d_wgrad_p16_plan(int k, int stride, int transposed, int cin, int co
  * (y, dx, out, dres, dh2) are nullable: NULL = only the twin is written (every consumer is a conv).  dbias* (nullable,
  * fp32 [C]): column sums of the gradient written = the bias gradient of the conv that produced the kernel's input. */
 int b3d_gn_apply_p16(const DLTensor* x, const DLTensor* stats, const DLTensor* gamma, const DLTensor* beta, DLTensor* y,
-                     DLTensor* y16, int groups, float eps, int relu, void* stream);
+                     DLTensor* y16, DLTensor* y16b /*nullable: second, bf16 twin*/, int groups, float eps, int relu,
+                     void* stream);
 int b3d_gn_bwd_apply_p16(const DLTensor* dy, const DLTensor* x, const DLTensor* stats, const DLTensor* gamma,
                          const DLTensor* beta, const DLTensor* csum, DLTensor* dx, DLTensor* dx16, DLTensor* dbias,
                          int groups, float eps, int relu, void* stream);
 int b3d_block_epilogue_fwd_p16(const DLTensor* res, const DLTensor* h2, const DLTensor* stats, const DLTensor* gamma,
                                const DLTensor* beta, const DLTensor* wsp, const DLTensor* chse, DLTensor* out,
-                               DLTensor* out16, int groups, float eps, int has_gn, void* stream);
+                               DLTensor* out16, DLTensor* out16b /*nullable: second, bf16 twin*/, int groups, float eps,
+                               int has_gn, void* stream);
 int b3d_block_epilogue_bwd_apply_p16(const DLTensor* dout, const DLTensor* res, const DLTensor* h2,
                                      const DLTensor* stats, const DLTensor* gamma, const DLTensor* beta,
                                      const DLTensor* wsp, const DLTensor* chse, const DLTensor* dgap,

@@ -62,14 +62,17 @@ def _worker(rank, world, port, q):
         grad_scale = 1.0
 
     opt = O()
+    with torch.no_grad():
+        flat.theta.copy_(torch.arange(flat.total, dtype=torch.float32) * (1.0 + rank))   # replicas start apart ...
     dp = b3d.DataParallel(M(), opt, world, n_buckets=3)
+    synced = bool(torch.equal(flat.theta, torch.arange(flat.total, dtype=torch.float32)))  # ... rank 0's weights win
     dp.begin_backward()
     for i, v in enumerate(vs):                       # "backward": rank-dependent gradients
         v.tensor.grad.fill_(float((rank + 1) * (i + 1)))
     dp.finish_backward()
     expect = [float(sum((r + 1) * (i + 1) for r in range(world))) for i in range(len(vs))]
     ok = all(torch.all(v.tensor.grad == e) for v, e in zip(vs, expect)) and opt.grad_scale == 1.0 / world
-    q.put((rank, bool(ok)))
+    q.put((rank, bool(ok) and synced))
     dist.destroy_process_group()
 
 

@@ -55,6 +55,28 @@ for n, cin, cout in SHAPES:
         io = 4.0 * n ** 3 * (cin + cout)
         line += (f"| fwd {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s (io {io / ms / 1e6:6.0f} GB/s) "
                  f"| no-stats {ms2 * 1e3:8.1f} us {flops / ms2 / 1e9:7.1f} TF/s ")
+    if which in ("fwd16", "all") and cin % 16 == 0 and cout % 16 == 0:
+        # the way the model feeds it: fp16 / bf16 P16 twins, TMA-fetched
+        dt = torch.float16 if prec == "fp16" else torch.bfloat16
+        wp = ops.pack_weights(w, False)
+        tw = ops.to_p16(x, dt)
+        st = stats if cout % 8 == 0 else None
+        ms = timeit(lambda: ops._call("b3d_conv3d_fwd_p16", tw, None, None, None, w, bias, y, 1, 0, 0, st, 8, None, 0, wp))
+        line += f"| fwd(P16/TMA) {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s "
+        dyb = ops.to_p16(dy, torch.bfloat16)
+        xb16 = ops.to_p16(x, torch.bfloat16)
+        prev = ops.get_conv_precision()
+        ops.set_conv_precision(prev[0], "bf16")
+        wpd = ops.pack_weights(w, True)
+        dx = torch.empty_like(x)
+        ms = timeit(lambda: ops._call("b3d_conv3d_dgrad_p16", dyb, w, dx, 1, 0, 0, wpd))
+        line += f"| dgrad(P16/TMA) {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s "
+        plan = b3d._lib.lib.b3d_conv3d_wgrad_p16_plan(3, 1, 0, cin, cout, n)
+        scratch = torch.empty(dyb.numel(), device=dev, dtype=torch.bfloat16) if plan == 3 else None
+        dw = torch.empty_like(w)
+        ms = timeit(lambda: ops._call("b3d_conv3d_wgrad_p16", xb16, None, None, None, dyb, dw, 1, 0, scratch))
+        line += f"| wgrad(P16, plan {plan}) {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s "
+        ops.set_conv_precision(*prev)
     if which in ("wgrad", "all"):
         dw = torch.empty_like(w)
         import ctypes

@@ -9,7 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 b3d = importlib.import_module("3d-brain-tumor-segmentation_b200")
-from oracle import ref_model as R  # noqa: E402
+import synthdata as R  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 crop = tuple(int(v) for v in sys.argv[2].split("x")) if len(sys.argv) > 2 else (128, 128, 128)
