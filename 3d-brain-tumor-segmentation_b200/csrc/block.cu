@@ -20,45 +20,6 @@ struct BlockGeom {
   int vox_per_cta;    // voxels handled by one CTA
 };
 
-// P16 twin output (common.cuh): half cell (4 channels) of voxel `vox` (index inside sample b) at channel c
-struct P16Out {
-  uint2* p;         // nullptr: no twin
-  unsigned W, C8;   // voxels per row, channel octets
-  unsigned rows;    // D*H rows per sample
-  int bf16;
-  uint2* p2;        // optional second twin, always bf16 (see norm.cu)
-};
-// (row, w) of a voxel: one division per thread at the start, then advanced by the kernel's voxel stride
-struct P16Pos { unsigned row, w; };
-__device__ __forceinline__ P16Pos p16_pos(const P16Out& o, unsigned vox) {
-  P16Pos k;
-  k.row = vox / o.W;
-  k.w = vox - k.row * o.W;
-  return k;
-}
-__device__ __forceinline__ void p16_advance(const P16Out& o, P16Pos& k, unsigned dv) {
-  k.w += dv;
-  while (k.w >= o.W) { k.w -= o.W; ++k.row; }
-}
-__device__ __forceinline__ void p16_store4(const P16Out& o, long long b, const P16Pos& k, int c, const float4& v) {
-  const unsigned row = k.row, w = k.w;
-  uint2 q;
-  if (o.bf16) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v.y), "f"(v.x));
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v.w), "f"(v.z));
-  } else {
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v.y), "f"(v.x));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v.w), "f"(v.z));
-  }
-  const unsigned long long idx = ((((unsigned long long)b * o.rows + row) * o.C8 + (c >> 3)) * o.W + w) * 2 + ((c >> 2) & 1);
-  o.p[idx] = q;
-  if (o.p2 != nullptr) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v.y), "f"(v.x));
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v.w), "f"(v.z));
-    o.p2[idx] = q;
-  }
-}
-
 __device__ __forceinline__ float group_sum(float v, int T) {
   for (int o = T >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -80,8 +41,7 @@ __global__ void __launch_bounds__(kBT)
     block_epilogue_fwd_kernel(const float* __restrict__ res, const float* __restrict__ h2,
                               const double* __restrict__ stats, const float* __restrict__ gamma,
                               const float* __restrict__ beta, const float* __restrict__ wsp,
-                              const float* __restrict__ chse, float* __restrict__ out, BlockGeom gm, float eps,
-                              P16Out out16) {
+                              const float* __restrict__ chse, float* __restrict__ out, BlockGeom gm, float eps) {
   const int chunk = blockIdx.y, b = chunk / gm.G, g = chunk % gm.G;
   const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
   float mean = 0.f, rstd = 1.f;
@@ -109,8 +69,6 @@ __global__ void __launch_bounds__(kBT)
   const long long vend = min(v0 + gm.vox_per_cta, gm.vpc);
   const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
   const int iters = (int)((vend - v0 + vstep - 1) / vstep);   // CTA-uniform: whole warps stay in the shuffles
-  P16Pos pos = {0, 0};
-  if (out16.p != nullptr) pos = p16_pos(out16, (unsigned)((long long)g * gm.vpc + v0 + vl));
   for (int it = 0; it < iters; ++it) {
     const long long v = v0 + (long long)it * vstep + vl;
     const bool act = v < vend;
@@ -144,11 +102,9 @@ __global__ void __launch_bounds__(kBT)
           o.y = r[q].y * (s + c4[q].y) + a.y;
           o.z = r[q].z * (s + c4[q].z) + a.z;
           o.w = r[q].w * (s + c4[q].w) + a.w;
-          if (out != nullptr) st_stream(reinterpret_cast<float4*>(out + eo + c), o);
-          if (out16.p != nullptr) p16_store4(out16, b, pos, c, o);
+          st_stream(reinterpret_cast<float4*>(out + eo + c), o);
         }
     }
-    if (out16.p != nullptr) p16_advance(out16, pos, (unsigned)vstep);
   }
 }
 
@@ -298,17 +254,7 @@ __global__ void __launch_bounds__(kBT)
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ wsp, const float* __restrict__ chse,
                                     const float* __restrict__ dgap, const double* __restrict__ csum,
-                                    float* __restrict__ dres, float* __restrict__ dh2, BlockGeom gm, float eps,
-                                    P16Out dres16, P16Out dh216, float* __restrict__ dbias_res,
-                                    float* __restrict__ dbias_h2) {
-  extern __shared__ float sdb[];      // [2][F]: column sums of dres / dh2 (bias gradients of the pointwise / second conv)
-  if (dbias_res != nullptr) {
-    for (int i = threadIdx.x; i < 2 * gm.F; i += kBT) sdb[i] = 0.f;
-    __syncthreads();
-  }
-  float4 acc_r[NPL], acc_h[NPL];
-#pragma unroll
-  for (int q = 0; q < NPL; ++q) acc_r[q] = acc_h[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    float* __restrict__ dres, float* __restrict__ dh2, BlockGeom gm, float eps) {
   const int chunk = blockIdx.y, b = chunk / gm.G, g = chunk % gm.G;
   const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
   float mean = 0.f, rstd = 1.f, m1 = 0.f, m2 = 0.f;
@@ -342,9 +288,6 @@ __global__ void __launch_bounds__(kBT)
   const long long vend = min(v0 + gm.vox_per_cta, gm.vpc);
   const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
   const int iters = (int)((vend - v0 + vstep - 1) / vstep);   // CTA-uniform: whole warps stay in the shuffles
-  P16Pos pos = {0, 0};
-  const P16Out& any16 = dres16.p != nullptr ? dres16 : dh216;
-  if (any16.p != nullptr) pos = p16_pos(any16, (unsigned)((long long)g * gm.vpc + v0 + vl));
   for (int it = 0; it < iters; ++it) {
     const long long v = v0 + (long long)it * vstep + vl;
     const bool act = v < vend;
@@ -374,9 +317,7 @@ __global__ void __launch_bounds__(kBT)
           o.y = d[q].y * (s + c4[q].y) + dl * w4[q].y + g4[q].y;
           o.z = d[q].z * (s + c4[q].z) + dl * w4[q].z + g4[q].z;
           o.w = d[q].w * (s + c4[q].w) + dl * w4[q].w + g4[q].w;
-          if (dres != nullptr) st_stream(reinterpret_cast<float4*>(dres + eo + c), o);
-          if (dres16.p != nullptr) p16_store4(dres16, b, pos, c, o);
-          acc_r[q].x += o.x; acc_r[q].y += o.y; acc_r[q].z += o.z; acc_r[q].w += o.w;
+          st_stream(reinterpret_cast<float4*>(dres + eo + c), o);
           if (HAS_GN) {
             const float4 hv = ld_stream(reinterpret_cast<const float4*>(h2 + eo + c));
             const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
@@ -390,32 +331,199 @@ __global__ void __launch_bounds__(kBT)
               const float gq = (xh * ga[i] + be[i]) > 0.f ? dd[i] : 0.f;
               oo[i] = rstd * (gq * ga[i] - m1 - xh * m2);
             }
-            const float4 o2 = make_float4(oo[0], oo[1], oo[2], oo[3]);
-            if (dh2 != nullptr) st_stream(reinterpret_cast<float4*>(dh2 + eo + c), o2);
-            if (dh216.p != nullptr) p16_store4(dh216, b, pos, c, o2);
-            acc_h[q].x += o2.x; acc_h[q].y += o2.y; acc_h[q].z += o2.z; acc_h[q].w += o2.w;
+            st_stream(reinterpret_cast<float4*>(dh2 + eo + c), make_float4(oo[0], oo[1], oo[2], oo[3]));
           }
         }
     }
-    if (any16.p != nullptr) p16_advance(any16, pos, (unsigned)vstep);
   }
-  if (dbias_res != nullptr) {
+}
+
+// ================================================================================================ P16 twin forms
+// The same forward / backward-apply passes writing the 16-bit operand twins of their results ([B, D, H, C/8, W, 8],
+// common.cuh) for the tcgen05 convs that consume them.  Lane mapping: T = F/8 lanes cooperate on one voxel and every
+// lane owns ONE 16-byte cell (8 consecutive channels): two 128-bit loads per input tensor, one 128-bit store per twin.
+struct Twin16 {
+  uint4* p;         // nullptr: no twin
+  uint4* p2;        // optional second twin, always bf16
+  unsigned W, C8;   // voxels per row, channel octets
+  unsigned rows;    // D*H rows per sample
+  int bf16;
+};
+struct VoxPos { unsigned row, w; };
+__device__ __forceinline__ VoxPos vox_pos(unsigned W, unsigned vox) {
+  VoxPos k;
+  k.row = vox / W;
+  k.w = vox - k.row * W;
+  return k;
+}
+__device__ __forceinline__ void vox_advance(unsigned W, VoxPos& k, unsigned dv) {
+  k.w += dv;
+  while (k.w >= W) { k.w -= W; ++k.row; }
+}
+__device__ __forceinline__ uint32_t pk16(float lo, float hi, int bf16) {
+  uint32_t r;
+  if (bf16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void cell_store(const Twin16& o, unsigned b, const VoxPos& k, unsigned c8, const float (&v)[8]) {
+  if (o.p == nullptr) return;
+  const unsigned long long idx = (((unsigned long long)b * o.rows + k.row) * o.C8 + c8) * o.W + k.w;
+  o.p[idx] = make_uint4(pk16(v[0], v[1], o.bf16), pk16(v[2], v[3], o.bf16), pk16(v[4], v[5], o.bf16),
+                        pk16(v[6], v[7], o.bf16));
+  if (o.p2 != nullptr)
+    o.p2[idx] = make_uint4(pk16(v[0], v[1], 1), pk16(v[2], v[3], 1), pk16(v[4], v[5], 1), pk16(v[6], v[7], 1));
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = ld_stream(reinterpret_cast<const float4*>(p));
+  const float4 c = ld_stream(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  st_stream(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  st_stream(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
+}
+
+// grid: (segments per chunk, B*G); gm.T = F/8 lanes per voxel
+template <bool HAS_GN>
+__global__ void __launch_bounds__(kBT)
+    block_fwd16_kernel(const float* __restrict__ res, const float* __restrict__ h2, const double* __restrict__ stats,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ wsp,
+                       const float* __restrict__ chse, float* __restrict__ out, BlockGeom gm, float eps, Twin16 tw) {
+  const int chunk = blockIdx.y, b = chunk / gm.G, g = chunk % gm.G;
+  const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
+  const int c = lane * 8;
+  float mean = 0.f, rstd = 1.f;
+  if (HAS_GN) moments(stats, chunk, 1.0 / ((double)gm.vpc * gm.F), eps, mean, rstd);
+  float w8[8], c8v[8], ga8[8], be8[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    w8[i] = wsp[c + i];
+    c8v[i] = chse[(long long)b * gm.F + c + i];
+    const int j = g * gm.cg + (c + i) % gm.cg;
+    ga8[i] = HAS_GN ? rstd * gamma[j] : 1.f;
+    be8[i] = HAS_GN ? beta[j] : 0.f;
+  }
+  const long long v0 = (long long)blockIdx.x * gm.vox_per_cta;
+  const long long vend = min(v0 + gm.vox_per_cta, gm.vpc);
+  const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
+  const int iters = (int)((vend - v0 + vstep - 1) / vstep);   // CTA-uniform: whole warps stay in the shuffles
+  VoxPos pos = vox_pos(tw.W, (unsigned)((long long)g * gm.vpc + v0 + vl));
+  for (int it = 0; it < iters; ++it) {
+    const long long v = v0 + (long long)it * vstep + vl;
+    const bool act = v < vend;
+    const long long eo = (vbase + (act ? v : v0)) * gm.F + c;
+    float r[8], h[8];
+    ld8(res + eo, r);
+    ld8(h2 + eo, h);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dot += r[i] * w8[i];
+    dot = group_sum(dot, T);
+    const float s = sigmoidf_(dot);
+    if (act) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a = HAS_GN ? fmaxf(fmaf(h[i] - mean, ga8[i], be8[i]), 0.f) : h[i];
+        o[i] = r[i] * (s + c8v[i]) + a;
+      }
+      if (out != nullptr) st8(out + eo, o);
+      cell_store(tw, (unsigned)b, pos, (unsigned)lane, o);
+    }
+    vox_advance(tw.W, pos, (unsigned)vstep);
+  }
+}
+
+// dres, dh2 as bf16 twins (+ optional fp32) and their column sums (bias gradients of the pointwise / second conv)
+template <bool HAS_DB>
+__global__ void __launch_bounds__(kBT)
+    block_bwd_apply16_kernel(const float* __restrict__ dout, const float* __restrict__ res,
+                             const float* __restrict__ h2, const double* __restrict__ stats,
+                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                             const float* __restrict__ wsp, const float* __restrict__ chse,
+                             const float* __restrict__ dgap, const double* __restrict__ csum,
+                             float* __restrict__ dres, float* __restrict__ dh2, BlockGeom gm, float eps, Twin16 tr,
+                             Twin16 th, float* __restrict__ dbias_res, float* __restrict__ dbias_h2) {
+  extern __shared__ float sdb[];      // [2][F]
+  if (HAS_DB) {
+    for (int i = threadIdx.x; i < 2 * gm.F; i += kBT) sdb[i] = 0.f;
+    __syncthreads();
+  }
+  const int chunk = blockIdx.y, b = chunk / gm.G, g = chunk % gm.G;
+  const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
+  const int c = lane * 8;
+  float mean, rstd;
+  const double L = (double)gm.vpc * gm.F;
+  moments(stats, chunk, 1.0 / L, eps, mean, rstd);
+  const float m1 = (float)(csum[2 * chunk] / L), m2 = (float)(csum[2 * chunk + 1] / L);
+  float w8[8], c8v[8], g8[8], ga8[8], be8[8], ar[HAS_DB ? 8 : 1], ah[HAS_DB ? 8 : 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    w8[i] = wsp[c + i];
+    c8v[i] = chse[(long long)b * gm.F + c + i];
+    g8[i] = dgap[(long long)b * gm.F + c + i];
+    const int j = g * gm.cg + (c + i) % gm.cg;
+    ga8[i] = gamma[j];
+    be8[i] = beta[j];
+    if (HAS_DB) ar[i] = ah[i] = 0.f;
+  }
+  const long long v0 = (long long)blockIdx.x * gm.vox_per_cta;
+  const long long vend = min(v0 + gm.vox_per_cta, gm.vpc);
+  const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
+  const int iters = (int)((vend - v0 + vstep - 1) / vstep);
+  VoxPos pos = vox_pos(tr.W, (unsigned)((long long)g * gm.vpc + v0 + vl));
+  for (int it = 0; it < iters; ++it) {
+    const long long v = v0 + (long long)it * vstep + vl;
+    const bool act = v < vend;
+    const long long eo = (vbase + (act ? v : v0)) * gm.F + c;
+    float r[8], d[8], h[8];
+    ld8(res + eo, r);
+    ld8(dout + eo, d);
+    ld8(h2 + eo, h);
+    float dot = 0.f, ds = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dot += r[i] * w8[i]; ds += r[i] * d[i]; }
+    dot = group_sum(dot, T);
+    ds = group_sum(ds, T);
+    const float s = sigmoidf_(dot);
+    const float dl = ds * s * (1.f - s);
+    if (act) {
+      float o1[8], o2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o1[i] = d[i] * (s + c8v[i]) + dl * w8[i] + g8[i];
+        const float xh = (h[i] - mean) * rstd;
+        const float gq = (xh * ga8[i] + be8[i]) > 0.f ? d[i] : 0.f;
+        o2[i] = rstd * (gq * ga8[i] - m1 - xh * m2);
+        if (HAS_DB) { ar[i] += o1[i]; ah[i] += o2[i]; }
+      }
+      if (dres != nullptr) st8(dres + eo, o1);
+      if (dh2 != nullptr) st8(dh2 + eo, o2);
+      cell_store(tr, (unsigned)b, pos, (unsigned)lane, o1);
+      cell_store(th, (unsigned)b, pos, (unsigned)lane, o2);
+    }
+    vox_advance(tr.W, pos, (unsigned)vstep);
+  }
+  if (HAS_DB) {
     // lanes of a warp with equal (lane % T) hold the same channels: butterfly over the voxel sub-index first
     const int wl = threadIdx.x & 31;
 #pragma unroll
-    for (int q = 0; q < NPL; ++q) {
-      const int c = (q * T + lane) * 4;
-      float a[8] = {acc_r[q].x, acc_r[q].y, acc_r[q].z, acc_r[q].w, acc_h[q].x, acc_h[q].y, acc_h[q].z, acc_h[q].w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        for (int o = 16; o >= T; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
-        if (wl < T) atomicAdd(&sdb[(i >> 2) * gm.F + c + (i & 3)], a[i]);
+    for (int i = 0; i < 8; ++i) {
+      float a0 = ar[i], a1 = ah[i];
+      for (int o = 16; o >= T; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      }
+      if (wl < T) {
+        atomicAdd(&sdb[c + i], a0);
+        atomicAdd(&sdb[gm.F + c + i], a1);
       }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < gm.F; c += kBT) {
-      atomicAdd(&dbias_res[c], sdb[c]);
-      if (HAS_GN && dbias_h2 != nullptr) atomicAdd(&dbias_h2[c], sdb[gm.F + c]);
+    for (int i = threadIdx.x; i < gm.F; i += kBT) {
+      atomicAdd(&dbias_res[i], sdb[i]);
+      atomicAdd(&dbias_h2[i], sdb[gm.F + i]);
     }
   }
 }
@@ -544,26 +652,6 @@ static int vecF(const DLTensor* t, long long n, const char* name, TView* v) {
   return B3D_OK;
 }
 
-static int p16_out(const DLTensor* twin_, const TView& x, P16Out* o, const DLTensor* twin2_ = nullptr) {
-  o->p = nullptr; o->p2 = nullptr;
-  if (twin_ == nullptr) return B3D_OK;
-  if (twin2_ != nullptr) {
-    P16View v2;
-    B3D_TRY(view_p16(twin2_, "twin (bf16)", &v2));
-    B3D_REQUIRE(v2.bf16 && twin_->ndim == 6 && twin2_->ndim == 6, B3D_ERR_DTYPE, "second twin must be bf16");
-    for (int i = 0; i < 6; ++i)
-      B3D_REQUIRE(twin_->shape[i] == twin2_->shape[i], B3D_ERR_SHAPE, "twins differ in shape");
-    o->p2 = (uint2*)v2.p;
-  }
-  P16View v;
-  B3D_TRY(view_p16(twin_, "twin", &v));
-  B3D_REQUIRE(x.ndim == 5 && v.B == x.shape[0] && v.D == x.shape[1] && v.H == x.shape[2] && v.W == x.shape[3] &&
-                  8 * v.C8 == x.shape[4], B3D_ERR_SHAPE, "twin: must be the [B, D, H, C/8, W, 8] form of the fp32 tensor");
-  B3D_REQUIRE((long long)v.D * v.H * v.W < (1LL << 32), B3D_ERR_UNSUPPORTED, "twin: sample too large");
-  o->p = (uint2*)v.p; o->W = (unsigned)v.W; o->C8 = (unsigned)v.C8; o->rows = (unsigned)(v.D * v.H); o->bf16 = v.bf16;
-  return B3D_OK;
-}
-
 }  // namespace b3d
 
 using namespace b3d;
@@ -606,24 +694,17 @@ extern "C" int b3d_se_fc_bwd(const DLTensor* gap_sum_, const DLTensor* w1_, cons
   return B3D_OK;
 }
 
-static int block_fwd_impl(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
-                          const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
-                          const DLTensor* chse_, DLTensor* out_, DLTensor* out16_, DLTensor* out16b_, int groups, float eps,
-                          int has_gn, void* stream) {
+extern "C" int b3d_block_epilogue_fwd(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
+                                      const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
+                                      const DLTensor* chse_, DLTensor* out_, int groups, float eps, int has_gn,
+                                      void* stream) {
   TView res, h2, out, st, ga, be, wsp, ch;
   BlockGeom gm;
   int nchunks;
   B3D_TRY(view(res_, DT_F32, -1, false, "res", &res));
   B3D_TRY(view(h2_, DT_F32, -1, false, "h2", &h2));
-  B3D_REQUIRE(out_ != nullptr || out16_ != nullptr, B3D_ERR_ARG, "block epilogue: no output");
-  out.p = nullptr;
-  if (out_ != nullptr) {
-    B3D_TRY(view(out_, DT_F32, -1, false, "out", &out));
-    B3D_REQUIRE(res.numel == out.numel, B3D_ERR_SHAPE, "block epilogue: size mismatch");
-  }
-  B3D_REQUIRE(res.numel == h2.numel, B3D_ERR_SHAPE, "block epilogue: size mismatch");
-  P16Out o16;
-  B3D_TRY(p16_out(out16_, res, &o16, out16b_));
+  B3D_TRY(view(out_, DT_F32, -1, false, "out", &out));
+  B3D_REQUIRE(res.numel == h2.numel && res.numel == out.numel, B3D_ERR_SHAPE, "block epilogue: size mismatch");
   B3D_TRY(block_geom(res, groups, has_gn != 0, &gm, &nchunks));
   B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
   B3D_TRY(vecF(chse_, res.shape[0] * gm.F, "chse", &ch));
@@ -635,30 +716,14 @@ static int block_fwd_impl(const DLTensor* res_, const DLTensor* h2_, const DLTen
     B3D_TRY(vecF(beta_, gm.F, "beta", &be));
     B3D_NPL(gm.npl, (block_epilogue_fwd_kernel<true, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
         (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
-        (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps, o16)));
+        (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps)));
   } else {
     B3D_NPL(gm.npl, (block_epilogue_fwd_kernel<false, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
         (const float*)res.p, (const float*)h2.p, nullptr, nullptr, nullptr, (const float*)wsp.p,
-        (const float*)ch.p, (float*)out.p, gm, eps, o16)));
+        (const float*)ch.p, (float*)out.p, gm, eps)));
   }
   B3D_LAUNCH_CHECK("block_epilogue_fwd");
   return B3D_OK;
-}
-
-extern "C" int b3d_block_epilogue_fwd(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
-                                      const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
-                                      const DLTensor* chse_, DLTensor* out_, int groups, float eps, int has_gn,
-                                      void* stream) {
-  return block_fwd_impl(res_, h2_, stats_, gamma_, beta_, wsp_, chse_, out_, nullptr, nullptr, groups, eps, has_gn, stream);
-}
-
-// out16: P16 twin of the block output for the convs that consume it (`out` may then be NULL); out16b (nullable): second,
-// bf16 twin for their weight gradients when out16 is fp16
-extern "C" int b3d_block_epilogue_fwd_p16(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
-                                          const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
-                                          const DLTensor* chse_, DLTensor* out_, DLTensor* out16_, DLTensor* out16b_,
-                                          int groups, float eps, int has_gn, void* stream) {
-  return block_fwd_impl(res_, h2_, stats_, gamma_, beta_, wsp_, chse_, out_, out16_, out16b_, groups, eps, has_gn, stream);
 }
 
 extern "C" int b3d_block_epilogue_bwd_reduce(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,
@@ -706,83 +771,130 @@ extern "C" int b3d_block_epilogue_bwd_reduce(const DLTensor* dout_, const DLTens
   return B3D_OK;
 }
 
-static int block_bwd_apply_impl(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,
-                                const DLTensor* stats_, const DLTensor* gamma_,
-                                const DLTensor* beta_, const DLTensor* wsp_, const DLTensor* chse_,
-                                const DLTensor* dgap_, const DLTensor* csum_, DLTensor* dres_,
-                                DLTensor* dh2_, DLTensor* dres16_, DLTensor* dh216_, DLTensor* dbias_res_,
-                                DLTensor* dbias_h2_, int groups, float eps, int has_gn, void* stream) {
-  TView dout, res, h2, st, ga, be, wsp, ch, dg, cs, dres, dh2;
-  BlockGeom gm;
-  int nchunks;
-  B3D_TRY(view(dout_, DT_F32, -1, false, "dout", &dout));
-  B3D_TRY(view(res_, DT_F32, -1, false, "res", &res));
-  B3D_REQUIRE(dres_ != nullptr || dres16_ != nullptr, B3D_ERR_ARG, "block epilogue bwd: no dres output");
-  dres.p = nullptr; dh2.p = nullptr;
-  if (dres_ != nullptr) {
-    B3D_TRY(view(dres_, DT_F32, -1, false, "dres", &dres));
-    B3D_REQUIRE(res.numel == dres.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
-  }
-  B3D_REQUIRE(res.numel == dout.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
-  P16Out r16, h16;
-  B3D_TRY(p16_out(dres16_, res, &r16));
-  B3D_TRY(p16_out(dh216_, res, &h16));
-  float *dbr = nullptr, *dbh = nullptr;
-  B3D_TRY(block_geom(res, groups, has_gn != 0, &gm, &nchunks));
-  B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
-  B3D_TRY(vecF(chse_, res.shape[0] * gm.F, "chse", &ch));
-  B3D_TRY(vecF(dgap_, res.shape[0] * gm.F, "dgap", &dg));
-  cudaStream_t s = (cudaStream_t)stream;
-  if (dbias_res_ != nullptr) {
-    TView t;
-    B3D_TRY(vecF(dbias_res_, gm.F, "dbias_res", &t));
-    dbr = (float*)t.p;
-    B3D_TRY(cuda_ok(cudaMemsetAsync(dbr, 0, sizeof(float) * gm.F, s), "memset"));
-    if (dbias_h2_ != nullptr) {
-      B3D_TRY(vecF(dbias_h2_, gm.F, "dbias_h2", &t));
-      dbh = (float*)t.p;
-      B3D_TRY(cuda_ok(cudaMemsetAsync(dbh, 0, sizeof(float) * gm.F, s), "memset"));
-    }
-  }
-  const size_t smem = dbr != nullptr ? sizeof(float) * 2 * gm.F : 0;
-  if (has_gn) {
-    B3D_TRY(view(h2_, DT_F32, -1, false, "h2", &h2));
-    B3D_REQUIRE(dh2_ != nullptr || dh216_ != nullptr, B3D_ERR_ARG, "block epilogue bwd: no dh2 output");
-    if (dh2_ != nullptr) {
-      B3D_TRY(view(dh2_, DT_F32, -1, false, "dh2", &dh2));
-      B3D_REQUIRE(res.numel == dh2.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
-    }
-    B3D_REQUIRE(res.numel == h2.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
-    B3D_TRY(view(stats_, DT_F64, -1, false, "stats", &st));
-    B3D_TRY(view(csum_, DT_F64, -1, false, "csum", &cs));
-    B3D_REQUIRE(st.numel == 2LL * nchunks && cs.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats/csum: wrong size");
-    B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
-    B3D_TRY(vecF(beta_, gm.F, "beta", &be));
-    B3D_NPL(gm.npl, (block_epilogue_bwd_apply_kernel<true, kN><<<block_grid(gm, nchunks), kBT, smem, s>>>(
-        (const float*)dout.p, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p,
-        (const float*)be.p, (const float*)wsp.p, (const float*)ch.p, (const float*)dg.p, (const double*)cs.p,
-        (float*)dres.p, (float*)dh2.p, gm, eps, r16, h16, dbr, dbh)));
-  } else {
-    B3D_NPL(gm.npl, (block_epilogue_bwd_apply_kernel<false, kN><<<block_grid(gm, nchunks), kBT, smem, s>>>(
-        (const float*)dout.p, (const float*)res.p, nullptr, nullptr, nullptr, nullptr, (const float*)wsp.p,
-        (const float*)ch.p, (const float*)dg.p, nullptr, (float*)dres.p, nullptr, gm, eps, r16, h16, dbr, nullptr)));
-  }
-  B3D_LAUNCH_CHECK("block_epilogue_bwd_apply");
-  return B3D_OK;
-}
-
 extern "C" int b3d_block_epilogue_bwd_apply(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,
                                             const DLTensor* stats_, const DLTensor* gamma_,
                                             const DLTensor* beta_, const DLTensor* wsp_, const DLTensor* chse_,
                                             const DLTensor* dgap_, const DLTensor* csum_, DLTensor* dres_,
                                             DLTensor* dh2_, int groups, float eps, int has_gn, void* stream) {
-  return block_bwd_apply_impl(dout_, res_, h2_, stats_, gamma_, beta_, wsp_, chse_, dgap_, csum_, dres_, dh2_, nullptr,
-                              nullptr, nullptr, nullptr, groups, eps, has_gn, stream);
+  TView dout, res, h2, st, ga, be, wsp, ch, dg, cs, dres, dh2;
+  BlockGeom gm;
+  int nchunks;
+  B3D_TRY(view(dout_, DT_F32, -1, false, "dout", &dout));
+  B3D_TRY(view(res_, DT_F32, -1, false, "res", &res));
+  B3D_TRY(view(dres_, DT_F32, -1, false, "dres", &dres));
+  B3D_REQUIRE(res.numel == dout.numel && res.numel == dres.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+  B3D_TRY(block_geom(res, groups, has_gn != 0, &gm, &nchunks));
+  B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
+  B3D_TRY(vecF(chse_, res.shape[0] * gm.F, "chse", &ch));
+  B3D_TRY(vecF(dgap_, res.shape[0] * gm.F, "dgap", &dg));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (has_gn) {
+    B3D_TRY(view(h2_, DT_F32, -1, false, "h2", &h2));
+    B3D_TRY(view(dh2_, DT_F32, -1, false, "dh2", &dh2));
+    B3D_REQUIRE(res.numel == h2.numel && res.numel == dh2.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+    B3D_TRY(view(stats_, DT_F64, -1, false, "stats", &st));
+    B3D_TRY(view(csum_, DT_F64, -1, false, "csum", &cs));
+    B3D_REQUIRE(st.numel == 2LL * nchunks && cs.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats/csum: wrong size");
+    B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
+    B3D_TRY(vecF(beta_, gm.F, "beta", &be));
+    B3D_NPL(gm.npl, (block_epilogue_bwd_apply_kernel<true, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+        (const float*)dout.p, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p,
+        (const float*)be.p, (const float*)wsp.p, (const float*)ch.p, (const float*)dg.p, (const double*)cs.p,
+        (float*)dres.p, (float*)dh2.p, gm, eps)));
+  } else {
+    B3D_NPL(gm.npl, (block_epilogue_bwd_apply_kernel<false, kN><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+        (const float*)dout.p, (const float*)res.p, nullptr, nullptr, nullptr, nullptr, (const float*)wsp.p,
+        (const float*)ch.p, (const float*)dg.p, nullptr, (float*)dres.p, nullptr, gm, eps)));
+  }
+  B3D_LAUNCH_CHECK("block_epilogue_bwd_apply");
+  return B3D_OK;
 }
 
-// dres16 / dh216 (nullable): bf16 P16 twins of the two gradients for the data / weight gradients of the pointwise and the
-// second 3x3x3 conv; dbias_res / dbias_h2 (nullable): their column sums = those convs' bias gradients.  dres / dh2 may be
-// NULL when only the twins are wanted.
+
+// ---- P16 twin forms ---------------------------------------------------------------------------------------------
+namespace {
+int twin16(const DLTensor* t1_, const DLTensor* t2_, const TView& x, b3d::Twin16* tw) {
+  using namespace b3d;
+  tw->p = nullptr; tw->p2 = nullptr; tw->W = (unsigned)x.shape[3]; tw->C8 = (unsigned)(x.shape[4] / 8);
+  tw->rows = (unsigned)(x.shape[1] * x.shape[2]); tw->bf16 = 1;
+  if (t1_ == nullptr) return B3D_OK;
+  P16View v;
+  B3D_TRY(view_p16(t1_, "twin", &v));
+  B3D_REQUIRE(x.ndim == 5 && v.B == x.shape[0] && v.D == x.shape[1] && v.H == x.shape[2] && v.W == x.shape[3] &&
+                  8 * v.C8 == x.shape[4], B3D_ERR_SHAPE, "twin: must be the [B, D, H, C/8, W, 8] form of the fp32 tensor");
+  tw->p = (uint4*)v.p; tw->bf16 = v.bf16;
+  if (t2_ != nullptr) {
+    P16View v2;
+    B3D_TRY(view_p16(t2_, "twin (bf16)", &v2));
+    B3D_REQUIRE(v2.bf16 && v2.B == v.B && v2.D == v.D && v2.H == v.H && v2.W == v.W && v2.C8 == v.C8, B3D_ERR_SHAPE,
+                "second twin: bf16, same shape");
+    tw->p2 = (uint4*)v2.p;
+  }
+  return B3D_OK;
+}
+// geometry of the cell kernels: T = F/8 lanes per voxel (a power of two <= 32)
+int block_geom16(const TView& res, int groups, bool has_gn, b3d::BlockGeom* gm, int* nchunks) {
+  using namespace b3d;
+  B3D_REQUIRE(res.ndim == 5, B3D_ERR_SHAPE, "block epilogue (P16): res must be [B, D, H, W, F]");
+  B3D_TRY(block_geom(res, groups, has_gn, gm, nchunks));
+  const int T = gm->F / 8;
+  B3D_REQUIRE(gm->F % 8 == 0 && T >= 1 && T <= 32 && (T & (T - 1)) == 0, B3D_ERR_UNSUPPORTED,
+              "block epilogue (P16): filters must be 8 * 2^k <= 256 (got %d)", gm->F);
+  B3D_REQUIRE(res.numel / res.shape[0] / gm->F < (1LL << 32), B3D_ERR_UNSUPPORTED, "block epilogue (P16): sample too large");
+  gm->T = T; gm->npl = 2;
+  const int vstep = kBT / T;
+  long long vp = (long long)vstep * 16;
+  const long long B = res.shape[0];
+  const long long cap = (3LL * sm_count() + B * gm->G - 1) / (B * gm->G);
+  const long long need = ((gm->vpc + cap - 1) / cap + vstep - 1) / vstep * vstep;
+  if (need > vp) vp = need;
+  gm->vox_per_cta = (int)vp;
+  return B3D_OK;
+}
+}  // namespace
+
+// out (nullable fp32) and the P16 twin(s) of the block output: out16 in the forward operand type, out16b (nullable) a
+// second, bf16 twin for the weight gradients of the consuming convs
+extern "C" int b3d_block_epilogue_fwd_p16(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
+                                          const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
+                                          const DLTensor* chse_, DLTensor* out_, DLTensor* out16_, DLTensor* out16b_,
+                                          int groups, float eps, int has_gn, void* stream) {
+  TView res, h2, out, st, ga, be, wsp, ch;
+  BlockGeom gm;
+  int nchunks;
+  B3D_TRY(view(res_, DT_F32, -1, false, "res", &res));
+  B3D_TRY(view(h2_, DT_F32, -1, false, "h2", &h2));
+  out.p = nullptr;
+  if (out_ != nullptr) {
+    B3D_TRY(view(out_, DT_F32, -1, false, "out", &out));
+    B3D_REQUIRE(res.numel == out.numel, B3D_ERR_SHAPE, "block epilogue: size mismatch");
+  }
+  B3D_REQUIRE(res.numel == h2.numel && out16_ != nullptr, B3D_ERR_SHAPE, "block epilogue (P16): sizes / twin required");
+  B3D_TRY(block_geom16(res, groups, has_gn != 0, &gm, &nchunks));
+  B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
+  B3D_TRY(vecF(chse_, res.shape[0] * gm.F, "chse", &ch));
+  Twin16 tw;
+  B3D_TRY(twin16(out16_, out16b_, res, &tw));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (has_gn) {
+    B3D_TRY(view(stats_, DT_F64, -1, false, "stats", &st));
+    B3D_REQUIRE(st.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats: wrong size");
+    B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
+    B3D_TRY(vecF(beta_, gm.F, "beta", &be));
+    block_fwd16_kernel<true><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+        (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+        (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps, tw);
+  } else {
+    block_fwd16_kernel<false><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+        (const float*)res.p, (const float*)h2.p, nullptr, nullptr, nullptr, (const float*)wsp.p, (const float*)ch.p,
+        (float*)out.p, gm, eps, tw);
+  }
+  B3D_LAUNCH_CHECK("block_fwd16");
+  return B3D_OK;
+}
+
+// dres / dh2 (nullable fp32), their bf16 P16 twins for the data / weight gradients of the pointwise and the second 3x3x3
+// conv, and dbias_res / dbias_h2 (nullable, both or none): their column sums = those convs' bias gradients.  GN form only.
 extern "C" int b3d_block_epilogue_bwd_apply_p16(const DLTensor* dout_, const DLTensor* res_, const DLTensor* h2_,
                                                 const DLTensor* stats_, const DLTensor* gamma_,
                                                 const DLTensor* beta_, const DLTensor* wsp_, const DLTensor* chse_,
@@ -790,6 +902,56 @@ extern "C" int b3d_block_epilogue_bwd_apply_p16(const DLTensor* dout_, const DLT
                                                 DLTensor* dh2_, DLTensor* dres16_, DLTensor* dh216_,
                                                 DLTensor* dbias_res_, DLTensor* dbias_h2_, int groups, float eps,
                                                 int has_gn, void* stream) {
-  return block_bwd_apply_impl(dout_, res_, h2_, stats_, gamma_, beta_, wsp_, chse_, dgap_, csum_, dres_, dh2_, dres16_,
-                              dh216_, dbias_res_, dbias_h2_, groups, eps, has_gn, stream);
+  TView dout, res, h2, st, ga, be, wsp, ch, dg, cs, dres, dh2;
+  BlockGeom gm;
+  int nchunks;
+  B3D_REQUIRE(has_gn, B3D_ERR_UNSUPPORTED, "block epilogue bwd (P16): the fused-GroupNorm form only");
+  B3D_TRY(view(dout_, DT_F32, -1, false, "dout", &dout));
+  B3D_TRY(view(res_, DT_F32, -1, false, "res", &res));
+  B3D_TRY(view(h2_, DT_F32, -1, false, "h2", &h2));
+  B3D_REQUIRE(res.numel == dout.numel && res.numel == h2.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+  dres.p = nullptr; dh2.p = nullptr;
+  if (dres_ != nullptr) {
+    B3D_TRY(view(dres_, DT_F32, -1, false, "dres", &dres));
+    B3D_REQUIRE(res.numel == dres.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+  }
+  if (dh2_ != nullptr) {
+    B3D_TRY(view(dh2_, DT_F32, -1, false, "dh2", &dh2));
+    B3D_REQUIRE(res.numel == dh2.numel, B3D_ERR_SHAPE, "block epilogue bwd: size mismatch");
+  }
+  B3D_REQUIRE((dres_ != nullptr || dres16_ != nullptr) && (dh2_ != nullptr || dh216_ != nullptr), B3D_ERR_ARG,
+              "block epilogue bwd: every gradient needs an output");
+  B3D_TRY(block_geom16(res, groups, true, &gm, &nchunks));
+  B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
+  B3D_TRY(vecF(chse_, res.shape[0] * gm.F, "chse", &ch));
+  B3D_TRY(vecF(dgap_, res.shape[0] * gm.F, "dgap", &dg));
+  B3D_TRY(view(stats_, DT_F64, -1, false, "stats", &st));
+  B3D_TRY(view(csum_, DT_F64, -1, false, "csum", &cs));
+  B3D_REQUIRE(st.numel == 2LL * nchunks && cs.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats/csum: wrong size");
+  B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
+  B3D_TRY(vecF(beta_, gm.F, "beta", &be));
+  Twin16 tr, th;
+  B3D_TRY(twin16(dres16_, nullptr, res, &tr));
+  B3D_TRY(twin16(dh216_, nullptr, res, &th));
+  cudaStream_t s = (cudaStream_t)stream;
+  float *dbr = nullptr, *dbh = nullptr;
+  B3D_REQUIRE((dbias_res_ == nullptr) == (dbias_h2_ == nullptr), B3D_ERR_ARG, "block epilogue bwd: both bias gradients or none");
+  if (dbias_res_ != nullptr) {
+    TView t;
+    B3D_TRY(vecF(dbias_res_, gm.F, "dbias_res", &t));
+    dbr = (float*)t.p;
+    B3D_TRY(vecF(dbias_h2_, gm.F, "dbias_h2", &t));
+    dbh = (float*)t.p;
+    B3D_TRY(cuda_ok(cudaMemsetAsync(dbr, 0, sizeof(float) * gm.F, s), "memset"));
+    B3D_TRY(cuda_ok(cudaMemsetAsync(dbh, 0, sizeof(float) * gm.F, s), "memset"));
+  }
+#define B3D_BWD16(DB)                                                                                              \
+  block_bwd_apply16_kernel<DB><<<block_grid(gm, nchunks), kBT, DB ? sizeof(float) * 2 * gm.F : 0, s>>>(           \
+      (const float*)dout.p, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p,      \
+      (const float*)be.p, (const float*)wsp.p, (const float*)ch.p, (const float*)dg.p, (const double*)cs.p,        \
+      (float*)dres.p, (float*)dh2.p, gm, eps, tr, th, dbr, dbh)
+  if (dbr != nullptr) B3D_BWD16(true); else B3D_BWD16(false);
+#undef B3D_BWD16
+  B3D_LAUNCH_CHECK("block_bwd_apply16");
+  return B3D_OK;
 }

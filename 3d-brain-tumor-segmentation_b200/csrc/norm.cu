@@ -30,56 +30,6 @@ __device__ __forceinline__ void chunk_moments(const double* __restrict__ stats, 
   rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-// P16 twin output (common.cuh): where the 4 consecutive channels starting at flat element `ea` of sample `b` live in a
-// [B, D*H, C/8, W, 8] 16-bit tensor, as an 8-byte half cell.  C % 8 == 0, ea % 4 == 0.
-struct P16Out {
-  uint2* p;         // nullptr: no twin
-  unsigned W, C;    // voxels per row, channels
-  unsigned rows;    // D*H rows per sample
-  int bf16;
-  uint2* p2;        // optional second twin, always bf16 (forward activations: fp16 for the conv, bf16 for the weight
-                    // gradient, whose MMA takes one operand type for A and B)
-};
-// Position of a thread's float4 inside the twin: computed once per thread (two divisions) and then ADVANCED by the
-// kernel's fixed element stride (kThreads * VEC per iteration, a multiple of C for every layer of this model), so the
-// streaming loop carries no division.
-struct P16Cursor {
-  unsigned long long rowbase;   // (b * rows + row) * C8 + c8
-  unsigned w, half;             // voxel inside the row, which half of the 16-byte cell
-  unsigned dv;                  // voxels per step (0: stride not a multiple of C -> recompute from the element index)
-};
-__device__ __forceinline__ P16Cursor p16_cursor(const P16Out& o, long long b, unsigned ea, unsigned step_elems) {
-  const unsigned vox = ea / o.C, c = ea - vox * o.C;
-  const unsigned row = vox / o.W;
-  P16Cursor k;
-  k.rowbase = ((unsigned long long)b * o.rows + row) * (o.C >> 3) + (c >> 3);
-  k.w = vox - row * o.W;
-  k.half = (c >> 2) & 1;
-  k.dv = (step_elems % o.C == 0) ? step_elems / o.C : 0;
-  return k;
-}
-__device__ __forceinline__ void p16_advance(const P16Out& o, P16Cursor& k) {
-  k.w += k.dv;
-  while (k.w >= o.W) { k.w -= o.W; k.rowbase += (o.C >> 3); }
-}
-__device__ __forceinline__ void p16_store4(const P16Out& o, const P16Cursor& k, const float (&v)[4]) {
-  uint2 q;
-  if (o.bf16) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v[1]), "f"(v[0]));
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v[3]), "f"(v[2]));
-  } else {
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v[1]), "f"(v[0]));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v[3]), "f"(v[2]));
-  }
-  const unsigned long long idx = (k.rowbase * o.W + k.w) * 2 + k.half;
-  o.p[idx] = q;
-  if (o.p2 != nullptr) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(v[1]), "f"(v[0]));
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(v[3]), "f"(v[2]));
-    o.p2[idx] = q;
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats,
@@ -130,7 +80,7 @@ template <int VEC, bool RELU>
 __global__ void __launch_bounds__(kThreads)
     gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float* __restrict__ y, ChunkGeom gm, float eps,
-                    long long shift, long long n_local, P16Out y16) {
+                    long long shift, long long n_local) {
   const int chunk = blockIdx.y;
   const int g = chunk % gm.G;
   const long long e_lo = max(0LL, shift - (long long)chunk * gm.L),
@@ -155,9 +105,6 @@ __global__ void __launch_bounds__(kThreads)
       sh[i] = __ldg(beta + jbase + j);
     }
   }
-  P16Cursor cur = {0, 0, 0, 0};
-  if (VEC == 4 && y16.p != nullptr)
-    cur = p16_cursor(y16, chunk / gm.G, (unsigned)(goff + base + threadIdx.x * VEC), kThreads * VEC);
   float in[kIter][4];
 #pragma unroll
   for (int k = 0; k < kIter; ++k) {
@@ -192,16 +139,9 @@ __global__ void __launch_bounds__(kThreads)
           o[i] = RELU ? fmaxf(t, 0.f) : t;
         }
       }
-      if (y != nullptr) {
-        if (VEC == 4) st_stream(reinterpret_cast<float4*>(y + off + e), make_float4(o[0], o[1], o[2], o[3]));
-        else y[off + e] = o[0];
-      }
-      if (VEC == 4 && y16.p != nullptr) {
-        if (cur.dv == 0) cur = p16_cursor(y16, chunk / gm.G, (unsigned)(goff + e), 0);
-        p16_store4(y16, cur, o);
-      }
+      if (VEC == 4) st_stream(reinterpret_cast<float4*>(y + off + e), make_float4(o[0], o[1], o[2], o[3]));
+      else y[off + e] = o[0];
     }
-    if (VEC == 4 && y16.p != nullptr) p16_advance(y16, cur);
   }
 }
 
@@ -320,14 +260,7 @@ template <int VEC, bool RELU>
 __global__ void __launch_bounds__(kThreads)
     gn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const double* __restrict__ stats,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                        const double* __restrict__ csum, float* __restrict__ dx, ChunkGeom gm, float eps,
-                        P16Out dx16, float* __restrict__ dbias) {
-  extern __shared__ float sdb[];      // [C] column sums of dx (the bias gradient of the conv that produced x)
-  if (dbias != nullptr) {
-    for (int i = threadIdx.x; i < gm.C; i += kThreads) sdb[i] = 0.f;
-    __syncthreads();
-  }
-  float db[4] = {0.f, 0.f, 0.f, 0.f};
+                        const double* __restrict__ csum, float* __restrict__ dx, ChunkGeom gm, float eps) {
   const int chunk = blockIdx.y;
   const int g = chunk % gm.G;
   float mean, rstd;
@@ -348,9 +281,6 @@ __global__ void __launch_bounds__(kThreads)
       bei[i] = __ldg(beta + jbase + (c_first + i) % gm.cg);
     }
   }
-  P16Cursor cur = {0, 0, 0, 0};
-  if (VEC == 4 && dx16.p != nullptr)
-    cur = p16_cursor(dx16, chunk / gm.G, (unsigned)(goff + base + threadIdx.x * VEC), kThreads * VEC);
 #pragma unroll
   for (int k = 0; k < kIter; ++k) {
     const long long e = base + ((long long)k * kThreads + threadIdx.x) * VEC;
@@ -382,30 +312,343 @@ __global__ void __launch_bounds__(kThreads)
         if (RELU) gq = (xh * ga + be) > 0.f ? gq : 0.f;
         o[i] = rstd * (gq * ga - m1 - xh * m2);
       }
-      if (dx != nullptr) {
-        if (VEC == 4)
-          st_stream(reinterpret_cast<float4*>(dx + off + e), make_float4(o[0], o[1], o[2], o[3]));
-        else
-          dx[off + e] = o[0];
-      }
-      if (VEC == 4 && dx16.p != nullptr) {
-        if (cur.dv == 0) cur = p16_cursor(dx16, chunk / gm.G, (unsigned)(goff + e), 0);
-        p16_store4(dx16, cur, o);
-      }
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) db[i] += o[i];
+      if (VEC == 4)
+        st_stream(reinterpret_cast<float4*>(dx + off + e), make_float4(o[0], o[1], o[2], o[3]));
+      else
+        dx[off + e] = o[0];
     }
-    if (VEC == 4 && dx16.p != nullptr) p16_advance(dx16, cur);
+  }
+}
+
+// ================================================================================================ P16 twin forms
+// GroupNorm apply / backward-apply that write the 16-bit operand twins the tcgen05 convs consume ([B, D, H, C/8, W, 8],
+// common.cuh) — one thread = one 16-byte CELL (8 consecutive channels of a voxel): two 128-bit loads per input tensor,
+// one 128-bit store per twin, consecutive lanes = consecutive cells of the fp32 tensor, so the reads are contiguous and
+// the stores of a warp fall into C/8 plane rows as 16*32/(C/8)-byte runs.  The position inside the twin is computed
+// once per thread and advanced by the loop stride (no division in the streaming loop); grids are capped (grid-stride
+// loop) so that the per-CTA bias-gradient atomics stay few.
+constexpr int kCell = 8;               // elements per thread and step
+constexpr int kIter16 = 4;             // cells per thread per CTA pass
+
+struct Twin16 {
+  uint4* p;         // first twin (type `bf16`), nullptr: none
+  uint4* p2;        // optional second twin, always bf16
+  unsigned W, C8;   // voxels per row, channel octets
+  unsigned rows;    // D*H rows per sample
+  int bf16;
+};
+struct CellPos {
+  unsigned long long rowbase;   // (b * rows + row) * C8 + c8
+  unsigned w;                   // voxel inside the row
+  unsigned dr1, dw1;            // small step (to the thread's next cell of a pass: kThreads cells on) as rows / voxels
+  unsigned dr2, dw2;            // big step (from the last cell of a pass to the first of the next)
+};
+// elem: index of the thread's first element inside sample b; cells1 / cells2: the two strides in cells (multiples of C8)
+__device__ __forceinline__ CellPos cell_pos(const Twin16& o, unsigned b, unsigned long long elem, unsigned cells1,
+                                            unsigned long long cells2) {
+  const unsigned cell = (unsigned)(elem >> 3);
+  const unsigned vox = cell / o.C8, c8 = cell - vox * o.C8;
+  const unsigned row = vox / o.W;
+  CellPos k;
+  k.rowbase = ((unsigned long long)b * o.rows + row) * o.C8 + c8;
+  k.w = vox - row * o.W;
+  const unsigned v1 = cells1 / o.C8;
+  const unsigned long long v2 = cells2 / o.C8;
+  k.dr1 = v1 / o.W; k.dw1 = v1 - k.dr1 * o.W;
+  k.dr2 = (unsigned)(v2 / o.W); k.dw2 = (unsigned)(v2 - (unsigned long long)k.dr2 * o.W);
+  return k;
+}
+__device__ __forceinline__ void cell_step(const Twin16& o, CellPos& k, unsigned dr, unsigned dw) {
+  k.w += dw;
+  unsigned r = dr;
+  if (k.w >= o.W) { k.w -= o.W; ++r; }
+  k.rowbase += (unsigned long long)r * o.C8;
+}
+__device__ __forceinline__ uint32_t pk16(float lo, float hi, int bf16) {
+  uint32_t r;
+  if (bf16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void cell_store(const Twin16& o, const CellPos& k, const float (&v)[8]) {
+  const unsigned long long idx = k.rowbase * o.W + k.w;
+  o.p[idx] = make_uint4(pk16(v[0], v[1], o.bf16), pk16(v[2], v[3], o.bf16), pk16(v[4], v[5], o.bf16),
+                        pk16(v[6], v[7], o.bf16));
+  if (o.p2 != nullptr)
+    o.p2[idx] = make_uint4(pk16(v[0], v[1], 1), pk16(v[2], v[3], 1), pk16(v[4], v[5], 1), pk16(v[6], v[7], 1));
+}
+
+// y = act((x - mean) * rstd * gamma_j + beta_j) -> twins (+ optional fp32 y).  grid (gx, chunks), grid-stride inside
+// the chunk.  Requires L % 8 == 0 and cg | 8 or 8 | cg (affine indices of a cell are loop-invariant per thread).
+template <bool RELU>
+__global__ void __launch_bounds__(kThreads)
+    gn_apply16_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float* __restrict__ y, ChunkGeom gm, float eps, Twin16 tw) {
+  const int chunk = blockIdx.y, g = chunk % gm.G, b = chunk / gm.G;
+  float mean, rstd;
+  chunk_moments(stats, chunk, 1.0 / (double)gm.L, eps, mean, rstd);
+  const long long off = (long long)chunk * gm.L;
+  const long long goff = (long long)g * gm.L;
+  // a pass of the grid covers gridDim.x * kIter16 * kThreads cells; a thread's k-th cell of a pass is kThreads cells on
+  const long long pass = (long long)gridDim.x * (kIter16 * kThreads * kCell);
+  long long e0 = ((long long)blockIdx.x * (kIter16 * kThreads) + threadIdx.x) * kCell;
+  // affine constants of this thread's 8 channels (invariant: all strides are multiples of cg)
+  float sc[8], sh[8];
+  {
+    const int c_first = (int)((goff + e0) % gm.cg);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = g * gm.cg + (c_first + i) % gm.cg;
+      sc[i] = rstd * __ldg(gamma + j);
+      sh[i] = __ldg(beta + j);
+    }
+  }
+  CellPos pos = cell_pos(tw, (unsigned)b, (unsigned long long)(goff + e0), kThreads,
+                         (unsigned long long)(pass / kCell) - (kIter16 - 1) * kThreads);
+  for (; e0 < gm.L; e0 += pass) {
+    float in[kIter16][8];
+#pragma unroll
+    for (int k = 0; k < kIter16; ++k) {
+      const long long e = e0 + (long long)k * (kThreads * kCell);
+      if (e < gm.L) {
+        const float4 a = ld_stream(reinterpret_cast<const float4*>(x + off + e));
+        const float4 c = ld_stream(reinterpret_cast<const float4*>(x + off + e) + 1);
+        in[k][0] = a.x; in[k][1] = a.y; in[k][2] = a.z; in[k][3] = a.w;
+        in[k][4] = c.x; in[k][5] = c.y; in[k][6] = c.z; in[k][7] = c.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kIter16; ++k) {
+      const long long e = e0 + (long long)k * (kThreads * kCell);
+      if (e < gm.L) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t = fmaf(in[k][i] - mean, sc[i], sh[i]);
+          o[i] = RELU ? fmaxf(t, 0.f) : t;
+        }
+        if (y != nullptr) {
+          st_stream(reinterpret_cast<float4*>(y + off + e), make_float4(o[0], o[1], o[2], o[3]));
+          st_stream(reinterpret_cast<float4*>(y + off + e) + 1, make_float4(o[4], o[5], o[6], o[7]));
+        }
+        cell_store(tw, pos, o);
+      }
+      if (k < kIter16 - 1) cell_step(tw, pos, pos.dr1, pos.dw1);
+      else cell_step(tw, pos, pos.dr2, pos.dw2);
+    }
+  }
+}
+
+// dx = rstd * (h - S1/L - xhat * S2/L) -> bf16 twin (+ optional fp32 dx) and dbias[c] += sum_vox dx (the bias gradient
+// of the conv that produced x)
+template <bool RELU>
+__global__ void __launch_bounds__(kThreads)
+    gn_bwd_apply16_kernel(const float* __restrict__ dy, const float* __restrict__ x, const double* __restrict__ stats,
+                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                          const double* __restrict__ csum, float* __restrict__ dx, ChunkGeom gm, float eps, Twin16 tw,
+                          float* __restrict__ dbias) {
+  extern __shared__ float sdb[];      // [C]
+  if (dbias != nullptr) {
+    for (int i = threadIdx.x; i < gm.C; i += kThreads) sdb[i] = 0.f;
+    __syncthreads();
+  }
+  constexpr int KI = 2;               // cells per thread and pass (4 x 128-bit loads each)
+  const int chunk = blockIdx.y, g = chunk % gm.G, b = chunk / gm.G;
+  float mean, rstd;
+  chunk_moments(stats, chunk, 1.0 / (double)gm.L, eps, mean, rstd);
+  const float m1 = (float)(csum[2 * chunk] / (double)gm.L);
+  const float m2 = (float)(csum[2 * chunk + 1] / (double)gm.L);
+  const long long off = (long long)chunk * gm.L;
+  const long long goff = (long long)g * gm.L;
+  const long long pass = (long long)gridDim.x * (KI * kThreads * kCell);
+  long long e0 = ((long long)blockIdx.x * (KI * kThreads) + threadIdx.x) * kCell;
+  const long long e_first = e0;
+  float ga[8], be[8], db[8];
+  const int c_first = (int)((goff + e0) % gm.cg);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = g * gm.cg + (c_first + i) % gm.cg;
+    ga[i] = __ldg(gamma + j);
+    be[i] = __ldg(beta + j);
+    db[i] = 0.f;
+  }
+  CellPos pos = cell_pos(tw, (unsigned)b, (unsigned long long)(goff + e0), kThreads,
+                         (unsigned long long)(pass / kCell) - (KI - 1) * kThreads);
+  for (; e0 < gm.L; e0 += pass) {
+    float dv[KI][8], xv[KI][8];
+#pragma unroll
+    for (int k = 0; k < KI; ++k) {
+      const long long e = e0 + (long long)k * (kThreads * kCell);
+      if (e < gm.L) {
+        const float4 d0 = ld_stream(reinterpret_cast<const float4*>(dy + off + e));
+        const float4 d1 = ld_stream(reinterpret_cast<const float4*>(dy + off + e) + 1);
+        const float4 x0 = ld_stream(reinterpret_cast<const float4*>(x + off + e));
+        const float4 x1 = ld_stream(reinterpret_cast<const float4*>(x + off + e) + 1);
+        dv[k][0] = d0.x; dv[k][1] = d0.y; dv[k][2] = d0.z; dv[k][3] = d0.w;
+        dv[k][4] = d1.x; dv[k][5] = d1.y; dv[k][6] = d1.z; dv[k][7] = d1.w;
+        xv[k][0] = x0.x; xv[k][1] = x0.y; xv[k][2] = x0.z; xv[k][3] = x0.w;
+        xv[k][4] = x1.x; xv[k][5] = x1.y; xv[k][6] = x1.z; xv[k][7] = x1.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KI; ++k) {
+      const long long e = e0 + (long long)k * (kThreads * kCell);
+      if (e < gm.L) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (xv[k][i] - mean) * rstd;
+          float gq = dv[k][i];
+          if (RELU) gq = (xh * ga[i] + be[i]) > 0.f ? gq : 0.f;
+          o[i] = rstd * (gq * ga[i] - m1 - xh * m2);
+          db[i] += o[i];
+        }
+        if (dx != nullptr) {
+          st_stream(reinterpret_cast<float4*>(dx + off + e), make_float4(o[0], o[1], o[2], o[3]));
+          st_stream(reinterpret_cast<float4*>(dx + off + e) + 1, make_float4(o[4], o[5], o[6], o[7]));
+        }
+        cell_store(tw, pos, o);
+      }
+      if (k < KI - 1) cell_step(tw, pos, pos.dr1, pos.dw1);
+      else cell_step(tw, pos, pos.dr2, pos.dw2);
+    }
   }
   if (dbias != nullptr) {
-    // channels of a thread's elements are loop-invariant (the host requires C | kThreads * VEC)
-    const int c0 = (int)((goff + base + threadIdx.x * VEC) % gm.C);
+    // a thread's channel octet is the same for all its cells (C8 divides every stride): lanes C8 apart in the warp hold
+    // the same octet -> butterfly over those lane offsets, then min(C8, 32) lanes touch shared memory
+    const int C8 = gm.C >> 3;
+    const int c0 = (int)((goff + e_first) % gm.C);
+    const int P = C8 < 32 ? C8 : 32;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) atomicAdd(&sdb[(c0 + i) % gm.C], db[i]);
+    for (int i = 0; i < 8; ++i) {
+      float a = db[i];
+      for (int o2 = 16; o2 >= P; o2 >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o2);
+      if ((threadIdx.x & 31) < P) atomicAdd(&sdb[c0 + i], a);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < gm.C; i += kThreads)
       if (sdb[i] != 0.f) atomicAdd(&dbias[i], sdb[i]);
   }
+}
+
+// backward pass 1 in the same cell-per-thread form (8 consecutive channels per thread and step, affine constants and
+// per-index accumulators in registers — the element-wise form above re-loads gamma / beta per element and is bound by
+// its load/store unit, 37-50 % of the HBM peak):  csum[chunk] = (sum h, sum h*xhat), dgamma_j, dbeta_j.
+template <bool RELU>
+__global__ void __launch_bounds__(kThreads)
+    gn_bwd_reduce8_kernel(const float* __restrict__ dy, const float* __restrict__ x, const double* __restrict__ stats,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, double* __restrict__ csum, ChunkGeom gm, float eps) {
+  extern __shared__ float sm[];  // [2*cg]
+  for (int i = threadIdx.x; i < 2 * gm.cg; i += kThreads) sm[i] = 0.f;
+  __syncthreads();
+  const int chunk = blockIdx.y, g = chunk % gm.G;
+  float mean, rstd;
+  chunk_moments(stats, chunk, 1.0 / (double)gm.L, eps, mean, rstd);
+  const long long off = (long long)chunk * gm.L;
+  const long long goff = (long long)g * gm.L;
+  constexpr int KI = 2;               // cells per thread and pass (4 x 128-bit loads each)
+  const long long pass = (long long)gridDim.x * (KI * kThreads * kCell);
+  long long e0 = ((long long)blockIdx.x * (KI * kThreads) + threadIdx.x) * kCell;
+  const int c_first = (int)((goff + e0) % gm.cg);
+  float ga[8], be[8], ag[8], ab[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = g * gm.cg + (c_first + i) % gm.cg;
+    ga[i] = __ldg(gamma + j);
+    be[i] = __ldg(beta + j);
+    ag[i] = ab[i] = 0.f;
+  }
+  float s1 = 0.f, s2 = 0.f;
+  for (; e0 < gm.L; e0 += pass) {
+    float dv[KI][8], xv[KI][8];
+#pragma unroll
+    for (int k = 0; k < KI; ++k) {
+      const long long e = e0 + (long long)k * (kThreads * kCell);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dv[k][i] = 0.f, xv[k][i] = mean;
+      if (e < gm.L) {
+        const float4 d0 = ld_stream(reinterpret_cast<const float4*>(dy + off + e));
+        const float4 d1 = ld_stream(reinterpret_cast<const float4*>(dy + off + e) + 1);
+        const float4 x0 = ld_stream(reinterpret_cast<const float4*>(x + off + e));
+        const float4 x1 = ld_stream(reinterpret_cast<const float4*>(x + off + e) + 1);
+        dv[k][0] = d0.x; dv[k][1] = d0.y; dv[k][2] = d0.z; dv[k][3] = d0.w;
+        dv[k][4] = d1.x; dv[k][5] = d1.y; dv[k][6] = d1.z; dv[k][7] = d1.w;
+        xv[k][0] = x0.x; xv[k][1] = x0.y; xv[k][2] = x0.z; xv[k][3] = x0.w;
+        xv[k][4] = x1.x; xv[k][5] = x1.y; xv[k][6] = x1.z; xv[k][7] = x1.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KI; ++k) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (xv[k][i] - mean) * rstd;
+        float gq = dv[k][i];
+        if (RELU) gq = (xh * ga[i] + be[i]) > 0.f ? gq : 0.f;
+        const float h = gq * ga[i];
+        s1 += h;
+        s2 += h * xh;
+        ag[i] += gq * xh;
+        ab[i] += gq;
+      }
+    }
+  }
+  // affine index of accumulator i: (c_first + i) % cg.  cg <= 8 (cg | 8): every thread holds the same index pattern ->
+  // fold the 8 accumulators onto cg, warp-sum, one lane adds.  cg = 8*m: lanes m apart share their 8 indices -> butterfly
+  // over the lane offsets >= m, lanes [0, m) add.
+  const int lane = threadIdx.x & 31;
+  if (gm.cg <= 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < gm.cg) {
+        float a = 0.f, b2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if ((c_first + i) % gm.cg == j) { a += ag[i]; b2 += ab[i]; }
+        a = warp_sum(a);
+        b2 = warp_sum(b2);
+        if (lane == 0) { atomicAdd(&sm[j], a); atomicAdd(&sm[gm.cg + j], b2); }
+      }
+    }
+  } else {
+    const int m = gm.cg >> 3;
+    const int P = m < 32 ? m : 32;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = ag[i], b2 = ab[i];
+      for (int o = 16; o >= P; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+      }
+      if (lane < P) {
+        atomicAdd(&sm[(c_first + i) % gm.cg], a);
+        atomicAdd(&sm[gm.cg + (c_first + i) % gm.cg], b2);
+      }
+    }
+  }
+  __shared__ double red[64];
+  double d[2] = {(double)s1, (double)s2};
+  block_sum<2, double>(d, red);  // contains __syncthreads -> smem atomics above are complete
+  if (threadIdx.x == 0) {
+    atomicAdd(&csum[2 * chunk], d[0]);
+    atomicAdd(&csum[2 * chunk + 1], d[1]);
+  }
+  for (int j = threadIdx.x; j < gm.cg; j += kThreads) {
+    atomicAdd(&dgamma[g * gm.cg + j], sm[j]);
+    atomicAdd(&dbeta[g * gm.cg + j], sm[gm.cg + j]);
+  }
+}
+
+// CTAs per chunk for the cell kernels: every thread runs >= kIter16 steps, at most ~3 waves of CTAs in total, and the
+// grid-stride (gx * kThreads cells) is a multiple of C8 so that a thread keeps its channel octet
+static inline dim3 gn_grid16(const ChunkGeom& gm, int nchunks) {
+  const long long cells = gm.L / kCell;
+  long long gx = (cells + (long long)kThreads * kIter16 - 1) / ((long long)kThreads * kIter16);
+  long long cap = (8LL * sm_count() + nchunks - 1) / nchunks;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)nchunks, 1);
 }
 
 static int gn_geom(const TView& x, int groups, ChunkGeom* gm, int* nchunks) {
@@ -475,53 +718,24 @@ extern "C" int b3d_gn_stats(const DLTensor* x_, DLTensor* stats_, int groups, vo
   return B3D_OK;
 }
 
-// twin_: nullable P16 [B, D, H, C/8, W, 8] (fp16 | bf16) copy of y for the tcgen05 convs that consume it; y_ may then be
-// NULL (the fp32 result is not materialised)
-static int p16_out(const DLTensor* twin_, const TView& x, P16Out* o, const DLTensor* twin2_ = nullptr) {
-  o->p = nullptr; o->p2 = nullptr;
-  if (twin_ == nullptr) return B3D_OK;
-  if (twin2_ != nullptr) {
-    P16View v2;
-    B3D_TRY(view_p16(twin2_, "twin (bf16)", &v2));
-    B3D_REQUIRE(v2.bf16 && twin_->ndim == 6 && twin2_->ndim == 6, B3D_ERR_DTYPE, "second twin must be bf16");
-    for (int i = 0; i < 6; ++i)
-      B3D_REQUIRE(twin_->shape[i] == twin2_->shape[i], B3D_ERR_SHAPE, "twins differ in shape");
-    o->p2 = (uint2*)v2.p;
-  }
-  P16View v;
-  B3D_TRY(view_p16(twin_, "twin", &v));
-  B3D_REQUIRE(x.ndim == 5 && v.B == x.shape[0] && v.D == x.shape[1] && v.H == x.shape[2] && v.W == x.shape[3] &&
-                  8 * v.C8 == x.shape[4], B3D_ERR_SHAPE, "twin: must be the [B, D, H, C/8, W, 8] form of the fp32 tensor");
-  B3D_REQUIRE(x.numel / x.shape[0] < (1LL << 32), B3D_ERR_UNSUPPORTED, "twin: sample too large");
-  o->p = (uint2*)v.p; o->W = (unsigned)v.W; o->C = 8u * v.C8; o->rows = (unsigned)(v.D * v.H); o->bf16 = v.bf16;
-  return B3D_OK;
-}
-
-static int gn_apply_impl(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_, const DLTensor* beta_,
-                         DLTensor* y_, DLTensor* y16_, DLTensor* y16b_, int groups, float eps, int relu, void* stream) {
+extern "C" int b3d_gn_apply(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
+                            const DLTensor* beta_, DLTensor* y_, int groups, float eps, int relu, void* stream) {
   TView x, y, st, ga, be;
   ChunkGeom gm;
   int nchunks;
   B3D_TRY(view(x_, DT_F32, -1, false, "x", &x));
-  B3D_REQUIRE(y_ != nullptr || y16_ != nullptr, B3D_ERR_ARG, "gn_apply: no output");
-  y.p = nullptr;
-  if (y_ != nullptr) {
-    B3D_TRY(view(y_, DT_F32, -1, false, "y", &y));
-    B3D_REQUIRE(x.numel == y.numel, B3D_ERR_SHAPE, "gn_apply: x/y size mismatch");
-  }
+  B3D_TRY(view(y_, DT_F32, -1, false, "y", &y));
+  B3D_REQUIRE(x.numel == y.numel, B3D_ERR_SHAPE, "gn_apply: x/y size mismatch");
   B3D_TRY(gn_geom(x, groups, &gm, &nchunks));
   B3D_TRY(check_stats(stats_, nchunks, "stats", &st));
   B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
   B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
-  P16Out o16;
-  B3D_TRY(p16_out(y16_, x, &o16, y16b_));
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 = (gm.L % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)y.p) & 15) == 0);
-  B3D_REQUIRE(v4 || o16.p == nullptr, B3D_ERR_LAYOUT, "gn_apply: the P16 twin needs 16-byte aligned chunks");
 #define LAUNCH(V, R)                                                                                     \
   gn_apply_kernel<V, R><<<gn_grid(gm, nchunks, V), kThreads, 0, s>>>(                                    \
       (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, 0,   \
-      x.numel, o16)
+      x.numel)
   if (v4) {
     if (relu) LAUNCH(4, true); else LAUNCH(4, false);
   } else {
@@ -530,17 +744,6 @@ static int gn_apply_impl(const DLTensor* x_, const DLTensor* stats_, const DLTen
 #undef LAUNCH
   B3D_LAUNCH_CHECK("gn_apply");
   return B3D_OK;
-}
-
-extern "C" int b3d_gn_apply(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
-                            const DLTensor* beta_, DLTensor* y_, int groups, float eps, int relu, void* stream) {
-  return gn_apply_impl(x_, stats_, gamma_, beta_, y_, nullptr, nullptr, groups, eps, relu, stream);
-}
-
-extern "C" int b3d_gn_apply_p16(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
-                                const DLTensor* beta_, DLTensor* y_, DLTensor* y16_, DLTensor* y16b_, int groups,
-                                float eps, int relu, void* stream) {
-  return gn_apply_impl(x_, stats_, gamma_, beta_, y_, y16_, y16b_, groups, eps, relu, stream);
 }
 
 // ---- depth-slab forms (whole-volume inference sharded along D; batch 1): x is this rank's contiguous part
@@ -595,7 +798,7 @@ extern "C" int b3d_gn_apply_slab(const DLTensor* x_, const DLTensor* stats_, con
 #define LAUNCH(V, R)                                                                                     \
   gn_apply_kernel<V, R><<<gn_grid(gm, groups, V), kThreads, 0, s>>>(                                     \
       (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps,     \
-      elem_offset, x.numel, P16Out{nullptr, 0, 0, 0, 0, nullptr})
+      elem_offset, x.numel)
   if (v4) {
     if (relu) LAUNCH(4, true); else LAUNCH(4, false);
   } else {
@@ -628,6 +831,22 @@ extern "C" int b3d_gn_bwd_reduce(const DLTensor* dy_, const DLTensor* x_, const 
   B3D_TRY(cuda_ok(cudaMemsetAsync(dbe.p, 0, sizeof(float) * gm.C, s), "memset dbeta"));
   const bool v4 = (gm.L % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)dy.p) & 15) == 0);
   const size_t smem = sizeof(float) * 2 * gm.cg;
+  // cell-per-thread form: whole cells per chunk, affine indices that repeat with the loop stride (a thread keeps them
+  // in registers), and cg a power of two (the lane butterfly)
+  const bool cells = v4 && gm.L % 8 == 0 && (kThreads * kCell) % gm.cg == 0 && (gm.cg & (gm.cg - 1)) == 0 &&
+                     (gm.cg <= 8 || gm.cg % 8 == 0);
+  if (cells) {
+    if (relu)
+      gn_bwd_reduce8_kernel<true><<<gn_grid16(gm, nchunks), kThreads, smem, s>>>(
+          (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+          (float*)dga.p, (float*)dbe.p, (double*)cs.p, gm, eps);
+    else
+      gn_bwd_reduce8_kernel<false><<<gn_grid16(gm, nchunks), kThreads, smem, s>>>(
+          (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+          (float*)dga.p, (float*)dbe.p, (double*)cs.p, gm, eps);
+    B3D_LAUNCH_CHECK("gn_bwd_reduce8");
+    return B3D_OK;
+  }
 #define LAUNCH(V, R)                                                                                       \
   gn_bwd_reduce_kernel<V, R><<<gn_grid(gm, nchunks, V, true), kThreads, smem, s>>>(                              \
       (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, \
@@ -642,46 +861,28 @@ extern "C" int b3d_gn_bwd_reduce(const DLTensor* dy_, const DLTensor* x_, const 
   return B3D_OK;
 }
 
-static int gn_bwd_apply_impl(const DLTensor* dy_, const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
-                             const DLTensor* beta_, const DLTensor* csum_, DLTensor* dx_, DLTensor* dx16_,
-                             DLTensor* dbias_, int groups, float eps, int relu, void* stream) {
+extern "C" int b3d_gn_bwd_apply(const DLTensor* dy_, const DLTensor* x_, const DLTensor* stats_,
+                                const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* csum_,
+                                DLTensor* dx_, int groups, float eps, int relu, void* stream) {
   TView x, dy, dx, st, ga, be, cs;
   ChunkGeom gm;
   int nchunks;
   B3D_TRY(view(x_, DT_F32, -1, false, "x", &x));
   B3D_TRY(view(dy_, DT_F32, -1, false, "dy", &dy));
-  B3D_REQUIRE(dx_ != nullptr || dx16_ != nullptr, B3D_ERR_ARG, "gn_bwd_apply: no output");
-  dx.p = nullptr;
-  if (dx_ != nullptr) {
-    B3D_TRY(view(dx_, DT_F32, -1, false, "dx", &dx));
-    B3D_REQUIRE(x.numel == dx.numel, B3D_ERR_SHAPE, "gn_bwd_apply: size mismatch");
-  }
-  B3D_REQUIRE(x.numel == dy.numel, B3D_ERR_SHAPE, "gn_bwd_apply: size mismatch");
+  B3D_TRY(view(dx_, DT_F32, -1, false, "dx", &dx));
+  B3D_REQUIRE(x.numel == dy.numel && x.numel == dx.numel, B3D_ERR_SHAPE, "gn_bwd_apply: size mismatch");
   B3D_TRY(gn_geom(x, groups, &gm, &nchunks));
   B3D_TRY(check_stats(stats_, nchunks, "stats", &st));
   B3D_TRY(check_stats(csum_, nchunks, "csum", &cs));
   B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
   B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
-  P16Out o16;
-  B3D_TRY(p16_out(dx16_, x, &o16));
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 =
       (gm.L % 4 == 0) && ((((uintptr_t)x.p | (uintptr_t)dy.p | (uintptr_t)dx.p) & 15) == 0);
-  B3D_REQUIRE(v4 || o16.p == nullptr, B3D_ERR_LAYOUT, "gn_bwd_apply: the P16 twin needs 16-byte aligned chunks");
-  float* db = nullptr;
-  if (dbias_ != nullptr) {
-    TView dbv;
-    B3D_TRY(check_affine(dbias_, gm.C, "dbias", &dbv));
-    B3D_REQUIRE(v4 && (kThreads * 4) % gm.C == 0 && gm.L % gm.C == 0, B3D_ERR_UNSUPPORTED,
-                "gn_bwd_apply: fused bias gradient needs C | %d and voxel-aligned chunks", kThreads * 4);
-    db = (float*)dbv.p;
-    B3D_TRY(cuda_ok(cudaMemsetAsync(db, 0, sizeof(float) * gm.C, s), "memset dbias"));
-  }
-  const size_t smem = db != nullptr ? sizeof(float) * gm.C : 0;
 #define LAUNCH(V, R)                                                                                       \
-  gn_bwd_apply_kernel<V, R><<<gn_grid(gm, nchunks, V), kThreads, smem, s>>>(                               \
+  gn_bwd_apply_kernel<V, R><<<gn_grid(gm, nchunks, V), kThreads, 0, s>>>(                                  \
       (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, \
-      (const double*)cs.p, (float*)dx.p, gm, eps, o16, db)
+      (const double*)cs.p, (float*)dx.p, gm, eps)
   if (v4) {
     if (relu) LAUNCH(4, true); else LAUNCH(4, false);
   } else {
@@ -692,17 +893,114 @@ static int gn_bwd_apply_impl(const DLTensor* dy_, const DLTensor* x_, const DLTe
   return B3D_OK;
 }
 
-extern "C" int b3d_gn_bwd_apply(const DLTensor* dy_, const DLTensor* x_, const DLTensor* stats_,
-                                const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* csum_,
-                                DLTensor* dx_, int groups, float eps, int relu, void* stream) {
-  return gn_bwd_apply_impl(dy_, x_, stats_, gamma_, beta_, csum_, dx_, nullptr, nullptr, groups, eps, relu, stream);
+
+// ---- P16 twin forms (see the kernels above) ----------------------------------------------------------------------
+namespace {
+int twin_view(const DLTensor* t1_, const DLTensor* t2_, const TView& x, b3d::Twin16* tw) {
+  using namespace b3d;
+  tw->p = nullptr; tw->p2 = nullptr;
+  P16View v;
+  B3D_TRY(view_p16(t1_, "twin", &v));
+  B3D_REQUIRE(x.ndim == 5 && v.B == x.shape[0] && v.D == x.shape[1] && v.H == x.shape[2] && v.W == x.shape[3] &&
+                  8 * v.C8 == x.shape[4], B3D_ERR_SHAPE, "twin: must be the [B, D, H, C/8, W, 8] form of the fp32 tensor");
+  tw->p = (uint4*)v.p; tw->W = (unsigned)v.W; tw->C8 = (unsigned)v.C8; tw->rows = (unsigned)(v.D * v.H); tw->bf16 = v.bf16;
+  if (t2_ != nullptr) {
+    P16View v2;
+    B3D_TRY(view_p16(t2_, "twin (bf16)", &v2));
+    B3D_REQUIRE(v2.bf16 && v2.B == v.B && v2.D == v.D && v2.H == v.H && v2.W == v.W && v2.C8 == v.C8, B3D_ERR_SHAPE,
+                "second twin: bf16, same shape");
+    tw->p2 = (uint4*)v2.p;
+  }
+  return B3D_OK;
+}
+// the cell kernels need whole cells per chunk, power-of-two octet counts dividing the thread block (so that a thread
+// keeps its channel octet over the grid-stride loop) and affine indices that repeat within a cell stride
+int cell_ok(const b3d::ChunkGeom& gm, const TView& x) {
+  using namespace b3d;
+  const int C8 = gm.C / 8;
+  B3D_REQUIRE(gm.C % 8 == 0 && gm.L % 8 == 0 && (C8 & (C8 - 1)) == 0 && C8 <= kThreads &&
+                  ((kThreads * kCell) % gm.cg == 0) && (gm.cg % 8 == 0 || 8 % gm.cg == 0) &&
+                  (x.numel / x.shape[0]) / 8 < (1LL << 32) && ((uintptr_t)x.p & 15) == 0,
+              B3D_ERR_UNSUPPORTED, "GroupNorm twin kernels: C = 8 * 2^k channels, 8 | chunk length (C=%d, L=%lld)", gm.C,
+              (long long)gm.L);
+  return B3D_OK;
+}
+}  // namespace
+
+// y (nullable fp32) and the P16 twin(s) of GroupNorm(+ReLU): y16 in the forward operand type, y16b (nullable) a second,
+// bf16 twin for the weight gradient of the consuming conv
+extern "C" int b3d_gn_apply_p16(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
+                                const DLTensor* beta_, DLTensor* y_, DLTensor* y16_, DLTensor* y16b_, int groups,
+                                float eps, int relu, void* stream) {
+  TView x, y, st, ga, be;
+  ChunkGeom gm;
+  int nchunks;
+  B3D_TRY(view(x_, DT_F32, 5, false, "x", &x));
+  y.p = nullptr;
+  if (y_ != nullptr) {
+    B3D_TRY(view(y_, DT_F32, -1, false, "y", &y));
+    B3D_REQUIRE(x.numel == y.numel && ((uintptr_t)y.p & 15) == 0, B3D_ERR_SHAPE, "gn_apply: x/y size mismatch");
+  }
+  B3D_TRY(gn_geom(x, groups, &gm, &nchunks));
+  B3D_TRY(check_stats(stats_, nchunks, "stats", &st));
+  B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
+  B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
+  B3D_TRY(cell_ok(gm, x));
+  Twin16 tw;
+  B3D_TRY(twin_view(y16_, y16b_, x, &tw));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (relu)
+    gn_apply16_kernel<true><<<gn_grid16(gm, nchunks), kThreads, 0, s>>>(
+        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw);
+  else
+    gn_apply16_kernel<false><<<gn_grid16(gm, nchunks), kThreads, 0, s>>>(
+        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw);
+  B3D_LAUNCH_CHECK("gn_apply16");
+  return B3D_OK;
 }
 
-// dx16 (nullable): bf16 P16 twin of dx for the data / weight gradient of the conv that produced x; dbias (nullable): fp32
-// [C] column sums of dx = that conv's bias gradient.  dx may be NULL when only the twin is wanted.
+// dx (nullable fp32), its bf16 P16 twin for the data / weight gradient of the conv that produced x, and dbias (nullable,
+// fp32 [C]) = column sums of dx = that conv's bias gradient
 extern "C" int b3d_gn_bwd_apply_p16(const DLTensor* dy_, const DLTensor* x_, const DLTensor* stats_,
                                     const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* csum_,
                                     DLTensor* dx_, DLTensor* dx16_, DLTensor* dbias_, int groups, float eps, int relu,
                                     void* stream) {
-  return gn_bwd_apply_impl(dy_, x_, stats_, gamma_, beta_, csum_, dx_, dx16_, dbias_, groups, eps, relu, stream);
+  TView x, dy, dx, st, ga, be, cs;
+  ChunkGeom gm;
+  int nchunks;
+  B3D_TRY(view(x_, DT_F32, 5, false, "x", &x));
+  B3D_TRY(view(dy_, DT_F32, -1, false, "dy", &dy));
+  dx.p = nullptr;
+  if (dx_ != nullptr) {
+    B3D_TRY(view(dx_, DT_F32, -1, false, "dx", &dx));
+    B3D_REQUIRE(x.numel == dx.numel && ((uintptr_t)dx.p & 15) == 0, B3D_ERR_SHAPE, "gn_bwd_apply: size mismatch");
+  }
+  B3D_REQUIRE(x.numel == dy.numel && ((uintptr_t)dy.p & 15) == 0, B3D_ERR_SHAPE, "gn_bwd_apply: size mismatch");
+  B3D_TRY(gn_geom(x, groups, &gm, &nchunks));
+  B3D_TRY(check_stats(stats_, nchunks, "stats", &st));
+  B3D_TRY(check_stats(csum_, nchunks, "csum", &cs));
+  B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
+  B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
+  B3D_TRY(cell_ok(gm, x));
+  Twin16 tw;
+  B3D_TRY(twin_view(dx16_, nullptr, x, &tw));
+  cudaStream_t s = (cudaStream_t)stream;
+  float* db = nullptr;
+  if (dbias_ != nullptr) {
+    TView dbv;
+    B3D_TRY(check_affine(dbias_, gm.C, "dbias", &dbv));
+    db = (float*)dbv.p;
+    B3D_TRY(cuda_ok(cudaMemsetAsync(db, 0, sizeof(float) * gm.C, s), "memset dbias"));
+  }
+  const size_t smem = db != nullptr ? sizeof(float) * gm.C : 0;
+  if (relu)
+    gn_bwd_apply16_kernel<true><<<gn_grid16(gm, nchunks), kThreads, smem, s>>>(
+        (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+        (const double*)cs.p, (float*)dx.p, gm, eps, tw, db);
+  else
+    gn_bwd_apply16_kernel<false><<<gn_grid16(gm, nchunks), kThreads, smem, s>>>(
+        (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+        (const double*)cs.p, (float*)dx.p, gm, eps, tw, db);
+  B3D_LAUNCH_CHECK("gn_bwd_apply16");
+  return B3D_OK;
 }

@@ -380,8 +380,11 @@ def run_b3d(args):
     model.load_named_weights(p)
     opt = b3d.ScheduledOptim(learning_rate=1e-4)
     opt(epoch=0)
-    dp = b3d.DataParallel(model, opt, world) if world > 1 else None
-    step = b3d.GraphedTrainStep(model, opt, b3d.DiceVAELoss(), b3d.DiceCoefficient(), xd, yd, warmup=2, dp=dp)
+    # data parallel: the reference's `--batch_size N` objective (Dice sums over the batch axis, util.py:11,18-20): the
+    # 3C+2 loss sums are all-reduced in the forward, parameter gradients are summed (train.DataParallel docstring)
+    loss_fn = b3d.DiceVAELoss()
+    dp = b3d.DataParallel(model, opt, world, objective="global_batch", loss_fn=loss_fn) if world > 1 else None
+    step = b3d.GraphedTrainStep(model, opt, loss_fn, b3d.DiceCoefficient(), xd, yd, warmup=2, dp=dp)
 
     def barrier():
         if world > 1:
@@ -430,13 +433,23 @@ def run_b3d(args):
     tta = measure_tta(b3d, torch, dist, dev, model, world)
 
     def finish():
-        # NCCL communicators captured into CUDA graphs make destroy_process_group() hang at teardown:
-        # synchronise, flush and leave without running destructors.
+        # Orderly teardown: the CUDA graphs that captured NCCL collectives are destroyed BEFORE the process group (the
+        # other order deadlocks inside ncclCommDestroy), then the group.  A watchdog ends the process should a
+        # communicator still refuse to go down, so that a finished measurement is never turned into a hung job.
         if world > 1:
+            import gc
+            nonlocal step, dp
+            sys.stdout.flush()
             dist.barrier()
             torch.cuda.synchronize()
-            sys.stdout.flush()
-            os._exit(0)
+            step = dp = None
+            gc.collect()
+            torch.cuda.synchronize()
+            guard = threading.Timer(30.0, lambda: os._exit(0))
+            guard.daemon = True
+            guard.start()
+            dist.destroy_process_group()
+            guard.cancel()
 
     if rank != 0:
         finish()
@@ -475,7 +488,10 @@ def run_b3d(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "fp16 forward / bf16 backward operands, fp32 accumulate and storage", "data": "synthetic",
             "config": {"workload": "train_128cube_b1_default_model", "crop": list(CROP), "per_gpu_batch": 1,
                        "global_batch": world, "in_ch": 2, "out_ch": 3, "base_filters": 16,
-                       "parallelism": f"dp{world}", "l2_flush": "working set (4.6 GiB of activations per step) "
+                       "parallelism": f"dp{world}",
+                       "dp_objective": "global_batch: batch-global Dice as in the reference's --batch_size N (3C+2 loss "
+                                       "sums all-reduced in the forward, gradients summed)" if world > 1 else None,
+                       "l2_flush": "working set (4.6 GiB of activations per step) "
                                                               "exceeds the 126 MB L2",
                        "train_tflop_per_step": 3 * FWD_GFLOP / 1e3, "cuda_graph": True},
             "clocks": clocks,

@@ -77,8 +77,29 @@ for n, C in ((128, 16), (64, 32), (32, 64)):
     report(f"block_epilogue_bwd_apply {tag}", 20 * E,
            lambda: ops._call("b3d_block_epilogue_bwd_apply", dy, res, h2, st, ga, be, wsp, chse, dgap, cs, dres, dh2,
                              8, 1e-5, 1))
-    xb = torch.empty(shp, device=dev, dtype=torch.bfloat16)
-    del res, h2, out, dres, dh2
+    # ---- the P16 twin forms the training step actually runs (fp32 outputs not materialised)
+    t16, t16b = ops.p16_empty(shp, x, torch.float16), ops.p16_empty(shp, x, torch.bfloat16)
+    u16b = ops.p16_empty(shp, x, torch.bfloat16)
+    dbias, dbias2 = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    report(f"gn_apply_p16 fp16 twin only (inference) {tag}", 6 * E,
+           lambda: ops._call("b3d_gn_apply_p16", x, st, ga, be, None, t16, None, 8, 1e-5, 1))
+    report(f"gn_apply_p16 fp16+bf16 twins (training) {tag}", 8 * E,
+           lambda: ops._call("b3d_gn_apply_p16", x, st, ga, be, None, t16, t16b, 8, 1e-5, 1))
+    report(f"gn_apply_p16 fp32 + both twins {tag}", 12 * E,
+           lambda: ops._call("b3d_gn_apply_p16", x, st, ga, be, y, t16, t16b, 8, 1e-5, 1))
+    report(f"gn_bwd_apply_p16 bf16 twin + dbias {tag}", 10 * E,
+           lambda: ops._call("b3d_gn_bwd_apply_p16", dy, x, st, ga, be, cs, None, t16b, dbias, 8, 1e-5, 1))
+    report(f"gn_bwd_apply_p16 bf16 twin, no dbias {tag}", 10 * E,
+           lambda: ops._call("b3d_gn_bwd_apply_p16", dy, x, st, ga, be, cs, None, t16b, None, 8, 1e-5, 1))
+    report(f"block_epilogue_fwd_p16 twins only {tag}", 12 * E,
+           lambda: ops._call("b3d_block_epilogue_fwd_p16", res, h2, st, ga, be, wsp, chse, None, t16, t16b, 8, 1e-5, 1))
+    report(f"block_epilogue_bwd_apply_p16 twins + dbias {tag}", 16 * E,
+           lambda: ops._call("b3d_block_epilogue_bwd_apply_p16", dy, res, h2, st, ga, be, wsp, chse, dgap, cs, None, None,
+                             t16b, u16b, dbias, dbias2, 8, 1e-5, 1))
+    report(f"block_epilogue_bwd_apply_p16 twins, no dbias {tag}", 16 * E,
+           lambda: ops._call("b3d_block_epilogue_bwd_apply_p16", dy, res, h2, st, ga, be, wsp, chse, dgap, cs, None, None,
+                             t16b, u16b, None, None, 8, 1e-5, 1))
+    del res, h2, out, dres, dh2, t16, t16b, u16b
 
 # loss / dice at 128^3 (out_ch 3, in_ch 2)
 n = 128
