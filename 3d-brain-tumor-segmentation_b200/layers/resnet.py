@@ -85,9 +85,10 @@ class ResnetBlock(Layer):
 
     def call(self, inputs, training=None):
         g = self.groups if self._fused_stats else 0
-        res, _, gap = self.conv3d_ptwise.call(inputs, want_gap=True, aux=True, share_x=True)
+        box = {} if ops.SHARE_DGRAD["on"] else None      # the two data gradients w.r.t. `inputs` are summed in-kernel
+        res, _, gap = self.conv3d_ptwise.call(inputs, want_gap=True, aux=True, share_x=True, grad_box=box)
         (conv1, norm1, _), (conv2, norm2, _) = self.convs
-        h1, st1, _ = conv1.call(inputs, gn_groups=g, aux=True, share_x=True)
+        h1, st1, _ = conv1.call(inputs, gn_groups=g, aux=True, share_x=True, grad_box=box)
         a1 = norm1.call(h1, stats=st1, relu=True, operand_only=True)      # only conv2 reads it: 16-bit twin only
         h2, st2, _ = conv2.call(a1, gn_groups=g, aux=True)
         if st2 is None:                                   # chunk boundaries not voxel-aligned: unfused GN2

@@ -202,6 +202,12 @@ def _grad_done(p, direct):
 USE_TC = {"on": True}
 
 
+def _os_env_flag(name, default):
+    import os
+    v = os.environ.get(name)
+    return default if v is None else v not in ("0", "", "off", "false")
+
+
 # ---- P16 operand twins -------------------------------------------------------------------------------------------
 # Every tensor that feeds a tcgen05 conv exists as a 16-bit "P16" twin [B, D, H, C/8, W, 8] (csrc/p16.cu) written by the
 # kernel that PRODUCES it (GroupNorm apply, block epilogue, their backward kernels): fp16 for forward activations, bf16
@@ -210,6 +216,9 @@ USE_TC = {"on": True}
 # is not materialised at all: the autograd-visible tensor is then a zero-stride placeholder of the logical shape
 # (`_b3d_virtual`) that carries the twin(s); `materialize()` rebuilds fp32 for the rare consumer that needs it.
 P16 = {"on": True}
+# the pointwise and the first 3x3x3 conv of a ResnetBlock read the same tensor: sum their data gradients in the second
+# kernel's epilogue instead of an autograd add pass (Conv3dFn.backward, `grad_box`); B3D_SHARE_DGRAD=0 for A/B runs
+SHARE_DGRAD = {"on": _os_env_flag("B3D_SHARE_DGRAD", True)}
 # inside a Model forward (`fused_scope`) layer outputs are consumed by convs only, so blocks / resampling layers emit
 # twin-only outputs and channel concatenation is virtual; outside (layers used on their own) outputs stay real fp32
 import threading as _threading
@@ -422,9 +431,10 @@ class Conv3dFn(Function):
     the data and the weight gradient).  Everything else takes the fp32 entry points."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, stride, transposed, act, gn_groups, want_gap, share_x=False):
+    def forward(ctx, x, w, bias, stride, transposed, act, gn_groups, want_gap, share_x=False, grad_box=None):
         ctx.set_materialize_grads(False)       # no zero tensors for the statistics / pooling outputs in backward
         ctx.share_x = bool(share_x)
+        ctx.grad_box = grad_box
         B, D, H, W_, Cin = x.shape
         k = w.shape[0]
         if transposed:
@@ -479,7 +489,7 @@ class Conv3dFn(Function):
     @staticmethod
     def backward(ctx, dy, _ds, _dg):
         if dy is None:                         # output unused by the loss (grads are not zero-materialised)
-            return (None,) * 9
+            return (None,) * 10
         x, w, y = ctx.saved_tensors
         srcs = ctx.srcs
         stride, transposed, act, has_bias = ctx.cfg
@@ -520,14 +530,24 @@ class Conv3dFn(Function):
             bias_done = bias_done or (need_dw and has_bias)
         dx = dw = None
         if need_dx:
-            dx = torch.empty(ctx.xshape, device=w.device, dtype=_f32)
+            # Two convs reading the same tensor (pointwise + first 3x3x3 of a ResnetBlock) share a `grad_box`: the first
+            # data gradient to run writes a fresh buffer and hands it to autograd, the second ADDS into that buffer in
+            # its epilogue (accumulate = 1) and returns no gradient — same sum, no separate add pass over the tensor.
+            box, acc = ctx.grad_box, 0
+            if box is not None and "dx" in box:
+                dx_buf, acc = box.pop("dx"), 1
+            else:
+                dx_buf = torch.empty(ctx.xshape, device=w.device, dtype=_f32)
+                if box is not None:
+                    box["dx"] = dx_buf
+                dx = dx_buf
             wp = pack_weights(w, True, stride, transposed) if tcd else None
             _tag_conv(w, ctx.nv, stride, transposed)
             if tcd and dy16 is not None:
-                _call("b3d_conv3d_dgrad_p16", dy16, w, dx, stride, int(transposed), 0, wp)
+                _call("b3d_conv3d_dgrad_p16", dy16, w, dx_buf, stride, int(transposed), acc, wp)
             else:
                 dy = materialize(dy)
-                _call("b3d_conv3d_dgrad", dy, w, dx, stride, int(transposed), 0, wp)
+                _call("b3d_conv3d_dgrad", dy, w, dx_buf, stride, int(transposed), acc, wp)
         if need_dw:
             dw, dw_direct = _grad_target(pw)
             if plan and dy16 is not None:
@@ -569,7 +589,7 @@ class Conv3dFn(Function):
             if has_bias:
                 _grad_done(pb, db_direct)
             dw, db = (None if dw_direct else dw), (None if (db_direct or not has_bias) else db)
-        return dx, dw, db, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
 # bf16 copies of conv inputs shared between two weight gradients of one backward pass (fp32 entry points only;
@@ -577,11 +597,12 @@ class Conv3dFn(Function):
 _XB_CACHE = {}
 
 
-def conv3d(x, w, bias=None, stride=1, transposed=False, act=0, gn_groups=0, want_gap=False, share_x=False):
+def conv3d(x, w, bias=None, stride=1, transposed=False, act=0, gn_groups=0, want_gap=False, share_x=False,
+           grad_box=None):
     ctx = _slab.current()
     if ctx is not None:        # depth-slab sharded inference: halo exchange + all-reduced GAP, no fused GN stats
         return ctx.conv3d(x, w, bias, stride, transposed, act, want_gap)
-    return Conv3dFn.apply(x, w, bias, stride, transposed, act, gn_groups, want_gap, share_x)
+    return Conv3dFn.apply(x, w, bias, stride, transposed, act, gn_groups, want_gap, share_x, grad_box)
 
 
 class GroupNormFn(Function):

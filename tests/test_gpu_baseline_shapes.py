@@ -24,7 +24,10 @@ from oracle import ref_model as R
 
 pytestmark = pytest.mark.gpu
 
-GRAD_SLACK = 2.0          # CUDA-vs-exact may be at most this many times the modelled rounding error (measured: 1.0x)
+GRAD_SLACK = 3.0          # per tensor: CUDA-vs-exact may be at most this many times the modelled rounding error (the model
+                          # is ONE realisation of the rounding noise; small tensors such as a 16-element spatial-SE
+                          # kernel scatter by 2x around it, seen with the round-1 kernels and these alike)
+MEDIAN_SLACK = 1.5        # over the 260 tensors the noise averages out: measured 1.0x
 GRAD_FLOOR = 5e-3         # fp32 oracle's own noise on an ill-conditioned gradient (test_gpu_model.py docstring)
 
 
@@ -108,7 +111,7 @@ def test_train_step_128cube_mixed_precision_vs_oracle(b3d, dev, crop):
         print(f"    worst: {r[4]}: cuda-exact {r[0]:.2e} model {r[1]:.2e} cuda-rounded {r[2]:.2e} cos {r[3]:.4f}")
     bad = [r for r in rows if r[0] > GRAD_SLACK * r[1] + GRAD_FLOOR]
     assert not bad, bad[:8]
-    assert med(0) <= GRAD_SLACK * med(1) + GRAD_FLOOR
+    assert med(0) <= MEDIAN_SLACK * med(1) + GRAD_FLOOR
     assert min(r[3] for r in rows) > 0.98, rows[:3]
 
 
