@@ -125,6 +125,8 @@ SIGNATURES = {
     "b3d_p16_unpack": "TTv",
     "b3d_p16_copy_planes": "TTiv",
     "b3d_colsum": "TTv",
+    "b3d_fold_dup": "TTiv",
+    "b3d_unfold_dup": "TTiv",
     "b3d_conv3d_fwd_p16": "TTTTTTTiiiTiTiTv",
     "b3d_conv3d_dgrad_p16": "TTTiiiTv",
     "b3d_conv3d_wgrad_p16": "TTTTTTiiTv",

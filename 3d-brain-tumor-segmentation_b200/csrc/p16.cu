@@ -250,3 +250,70 @@ extern "C" int b3d_colsum(const DLTensor* x_, DLTensor* out_, void* stream) {
   return launch_colsum((const float*)x.p, (float*)o.p, x.numel / x.shape[4], (int)x.shape[4], x.pitch, true,
                        (cudaStream_t)stream);
 }
+
+// ---- F3: the encoder's dense connections duplicate a tensor (encoder.py:83-87: `dense([inputs] + cache)` with `inputs
+// is cache[-1]`), so a conv over [a_last, a_0, ..., a_last] equals a conv over [a_0, ..., a_last] with the two weight
+// slices of a_last ADDED — exact, one K segment less, no duplicated operand.  Keras keeps the (k,k,k,(j+1)F,Cout) kernel;
+// these two kernels maintain the folded (k,k,k,jF,Cout) form and scatter its gradient back:
+//   fold:    w'[t][c][o] = w[t][F + c][o]                          c <  (j-1)F
+//            w'[t][c][o] = w[t][F + c][o] + w[t][c - (j-1)F][o]    c >= (j-1)F   (the duplicated tensor is the LAST source)
+//   unfold:  dw[t][F + c][o] = dw'[t][c][o];   dw[t][c][o] = dw'[t][(j-1)F + c][o]  for c < F
+namespace b3d {
+__global__ void __launch_bounds__(256)
+    fold_dup_kernel(const float* __restrict__ w, float* __restrict__ wf, long long taps, int Cf, int F, int Cout) {
+  const long long total = taps * Cf * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % Cout);
+    const long long r = i / Cout;
+    const int c = (int)(r % Cf);
+    const long long t = r / Cf;
+    const float* wt = w + t * (long long)(Cf + F) * Cout;
+    float v = wt[(long long)(F + c) * Cout + o];
+    if (c >= Cf - F) v += wt[(long long)(c - (Cf - F)) * Cout + o];
+    wf[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256)
+    unfold_dup_kernel(const float* __restrict__ dwf, float* __restrict__ dw, long long taps, int Cf, int F, int Cout) {
+  const long long total = taps * (Cf + F) * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % Cout);
+    const long long r = i / Cout;
+    const int c = (int)(r % (Cf + F));
+    const long long t = r / (Cf + F);
+    const int cf = c >= F ? c - F : (Cf - F) + c;
+    dw[i] = dwf[(t * Cf + cf) * Cout + o];
+  }
+}
+}  // namespace b3d
+
+// w: Keras kernel (k,k,k,Cf+F,Cout) of a conv whose input is [a_last (F ch), a_0 .., a_last]; wf: (k,k,k,Cf,Cout)
+extern "C" int b3d_fold_dup(const DLTensor* w_, DLTensor* wf_, int F, void* stream) {
+  TView w, wf;
+  B3D_TRY(view(w_, DT_F32, 5, false, "w", &w));
+  B3D_TRY(view(wf_, DT_F32, 5, false, "wf", &wf));
+  const int Cf = (int)wf.shape[3], Cout = (int)w.shape[4];
+  B3D_REQUIRE(F > 0 && Cf >= F && w.shape[3] == Cf + F && wf.shape[4] == Cout && w.shape[0] == wf.shape[0] &&
+                  w.shape[1] == wf.shape[1] && w.shape[2] == wf.shape[2], B3D_ERR_SHAPE, "fold_dup: kernel shapes");
+  const long long taps = w.shape[0] * w.shape[1] * w.shape[2];
+  fold_dup_kernel<<<grid_for(taps * Cf * Cout, 256, 8), 256, 0, (cudaStream_t)stream>>>((const float*)w.p, (float*)wf.p,
+                                                                                         taps, Cf, F, Cout);
+  B3D_LAUNCH_CHECK("fold_dup");
+  return B3D_OK;
+}
+
+extern "C" int b3d_unfold_dup(const DLTensor* dwf_, DLTensor* dw_, int F, void* stream) {
+  TView dw, dwf;
+  B3D_TRY(view(dw_, DT_F32, 5, false, "dw", &dw));
+  B3D_TRY(view(dwf_, DT_F32, 5, false, "dwf", &dwf));
+  const int Cf = (int)dwf.shape[3], Cout = (int)dw.shape[4];
+  B3D_REQUIRE(F > 0 && Cf >= F && dw.shape[3] == Cf + F && dwf.shape[4] == Cout && dw.shape[0] == dwf.shape[0] &&
+                  dw.shape[1] == dwf.shape[1] && dw.shape[2] == dwf.shape[2], B3D_ERR_SHAPE, "unfold_dup: kernel shapes");
+  const long long taps = dw.shape[0] * dw.shape[1] * dw.shape[2];
+  unfold_dup_kernel<<<grid_for(taps * (Cf + F) * Cout, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      (const float*)dwf.p, (float*)dw.p, taps, Cf, F, Cout);
+  B3D_LAUNCH_CHECK("unfold_dup");
+  return B3D_OK;
+}

@@ -219,8 +219,11 @@ class Conv3D(Layer):
             self.bias = self.add_weight("bias", (self.filters,), "zeros", device)
         self.built = True
 
-    def call(self, x, training=None, gn_groups=0, want_gap=False, aux=False, share_x=False, grad_box=None):
-        y, stats, gap = ops.conv3d(x, self.kernel, self.bias, self.strides, False,
+    def call(self, x, training=None, gn_groups=0, want_gap=False, aux=False, share_x=False, grad_box=None,
+             kernel=None):
+        """kernel: a tensor derived from self.kernel to convolve with instead (the folded kernel of a dense-connection
+        input, ops.fold_dup)."""
+        y, stats, gap = ops.conv3d(x, self.kernel if kernel is None else kernel, self.bias, self.strides, False,
                                    1 if self.activation == "sigmoid" else 0, gn_groups, want_gap, share_x, grad_box)
         return (y, stats, gap) if aux else y
 

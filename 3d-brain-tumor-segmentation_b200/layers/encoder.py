@@ -81,9 +81,15 @@ class Encoder(Layer):
             convs, concat, downsample = level
             cache = []
             for conv, dense in convs:
+                dup = 0
                 if dense is not None:
-                    inputs = dense([inputs] + cache)
-                inputs = conv(inputs, training=training)
+                    if conv.built and self._can_dedup(cache):
+                        # `inputs is cache[-1]`: [inputs] + cache lists it twice (encoder.py:85).  Feed [cache] only
+                        # and let the block fold the duplicate's weight slice (exact; one K segment less)
+                        inputs, dup = dense(cache), inputs.shape[-1]
+                    else:
+                        inputs = dense([inputs] + cache)
+                inputs = conv(inputs, training=training, dup_first=dup) if dup else conv(inputs, training=training)
                 cache.append(inputs)
             if concat is not None:
                 inputs = concat(cache)
@@ -91,6 +97,11 @@ class Encoder(Layer):
             if downsample is not None:
                 inputs = downsample(inputs, training=training)
         return residuals
+
+    @staticmethod
+    def _can_dedup(cache):
+        return (ops.DEDUP["on"] and ops.FUSED["on"] and ops.twin_dtype(False) is not None
+                and all(ops.sources(t) is not None for t in cache))
 
     def get_config(self):
         return self.config

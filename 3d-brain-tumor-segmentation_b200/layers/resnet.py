@@ -83,12 +83,17 @@ class ResnetBlock(Layer):
             norm.build(shp, device)
         self.built = True
 
-    def call(self, inputs, training=None):
+    def call(self, inputs, training=None, dup_first=0):
+        """dup_first = F > 0 (Encoder, inside a Model): the reference input is [a_last (F channels), a_0, .., a_last] and
+        `inputs` holds only [a_0, .., a_last]; the two convs reading it use their kernels with the duplicate's weight
+        slice folded into the last source's (exact)."""
         g = self.groups if self._fused_stats else 0
         box = {} if ops.SHARE_DGRAD["on"] else None      # the two data gradients w.r.t. `inputs` are summed in-kernel
-        res, _, gap = self.conv3d_ptwise.call(inputs, want_gap=True, aux=True, share_x=True, grad_box=box)
         (conv1, norm1, _), (conv2, norm2, _) = self.convs
-        h1, st1, _ = conv1.call(inputs, gn_groups=g, aux=True, share_x=True, grad_box=box)
+        kpt = ops.fold_dup(self.conv3d_ptwise.kernel, dup_first) if dup_first else None
+        kc1 = ops.fold_dup(conv1.kernel, dup_first) if dup_first else None
+        res, _, gap = self.conv3d_ptwise.call(inputs, want_gap=True, aux=True, share_x=True, grad_box=box, kernel=kpt)
+        h1, st1, _ = conv1.call(inputs, gn_groups=g, aux=True, share_x=True, grad_box=box, kernel=kc1)
         a1 = norm1.call(h1, stats=st1, relu=True, operand_only=True)      # only conv2 reads it: 16-bit twin only
         h2, st2, _ = conv2.call(a1, gn_groups=g, aux=True)
         if st2 is None:                                   # chunk boundaries not voxel-aligned: unfused GN2

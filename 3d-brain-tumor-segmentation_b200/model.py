@@ -90,6 +90,7 @@ class FlatParams:
         self.packs = {}
         self.pack_table = None
         self.epoch = 0
+        self.folds = []                # (kernel, folded kernel, F) of the dense-connection convs (ops.FoldDupFn)
 
     def zero_grad(self):
         self.grad.zero_()

@@ -88,6 +88,7 @@ def pack_weights(w: torch.Tensor, dgrad: bool, stride: int = 1, transposed: bool
     buffer) keep ONE persistent packed buffer per pass: it is refreshed for all layers together by
     `repack_all(flat)` right after the optimiser step (one launch instead of ~120 per training step, none per
     inference forward), or singly here when the stamp shows the weights were changed some other way."""
+    w = getattr(w, "_b3d_base", w)          # a per-call alias of a persistent derived kernel (FoldDupFn)
     flat = getattr(w, "_b3d_flat", None)
     if flat is None:
         out = _new((lib.b3d_conv3d_packed_elems(w.shape[0], stride, w.shape[3], w.shape[4]),), w)
@@ -153,6 +154,9 @@ def repack_all(flat):
     """The weights of `flat` have just been changed by a kernel (Adam): refresh every registered packed operand with
     ONE launch (csrc/conv_tc.cu pack_many_kernel).  Captured at the end of the graphed training step."""
     flat.epoch += 1
+    for w, wf, F in getattr(flat, "folds", ()):          # folded (F3) kernels follow the weights, then get packed
+        _call("b3d_fold_dup", w, wf, F)
+        w._b3d_fold[1] = (w._version, flat.theta._version, flat.epoch)
     if not flat.packs:
         return
     tab, n, blocks, _, entries = ensure_pack_table(flat)
@@ -216,9 +220,14 @@ def _os_env_flag(name, default):
 # is not materialised at all: the autograd-visible tensor is then a zero-stride placeholder of the logical shape
 # (`_b3d_virtual`) that carries the twin(s); `materialize()` rebuilds fp32 for the rare consumer that needs it.
 P16 = {"on": True}
-# the pointwise and the first 3x3x3 conv of a ResnetBlock read the same tensor: sum their data gradients in the second
-# kernel's epilogue instead of an autograd add pass (Conv3dFn.backward, `grad_box`); B3D_SHARE_DGRAD=0 for A/B runs
-SHARE_DGRAD = {"on": _os_env_flag("B3D_SHARE_DGRAD", True)}
+# the pointwise and the first 3x3x3 conv of a ResnetBlock read the same tensor: their data gradients can be summed in the
+# second kernel's epilogue (Conv3dFn.backward, `grad_box`) instead of an autograd add pass.  OFF by default: measured on
+# B200 (A/B, same box, 128^3 step) 17.03 ms with it vs 16.53 ms without — the read-modify-write in the conv epilogue costs
+# more than the 16 add launches it removes (0.32 ms), as in round 1.  B3D_SHARE_DGRAD=1 switches it on.
+SHARE_DGRAD = {"on": _os_env_flag("B3D_SHARE_DGRAD", False)}
+# the encoder's dense connections list the previous block output twice; inside a Model the duplicate is
+# dropped and its weight slice folded into the other one (ops.FoldDupFn) — exact.  B3D_DEDUP=0 for A/B runs
+DEDUP = {"on": _os_env_flag("B3D_DEDUP", True)}
 # inside a Model forward (`fused_scope`) layer outputs are consumed by convs only, so blocks / resampling layers emit
 # twin-only outputs and channel concatenation is virtual; outside (layers used on their own) outputs stay real fp32
 import threading as _threading
@@ -459,8 +468,10 @@ class Conv3dFn(Function):
         wp = None
         if tc:
             wp = pack_weights(w, False, stride, transposed)
-        elif USE_TC["on"] and getattr(w, "_b3d_flat", None) is not None and tc_supported(w, stride, transposed, True):
-            _register_pack(w._b3d_flat, w, True, stride, transposed)     # forward on CUDA cores, data gradient on TC
+        elif USE_TC["on"] and getattr(getattr(w, "_b3d_base", w), "_b3d_flat", None) is not None and \
+                tc_supported(w, stride, transposed, True):
+            wb = getattr(w, "_b3d_base", w)
+            _register_pack(wb._b3d_flat, wb, True, stride, transposed)   # forward on CUDA cores, data gradient on TC
         nv = B * (D * H * W_ if transposed else S)      # voxels the FLOP formula counts (transposed: input voxels)
         _tag_conv(w, nv, stride, transposed)
         if use16:
@@ -590,6 +601,49 @@ class Conv3dFn(Function):
                 _grad_done(pb, db_direct)
             dw, db = (None if dw_direct else dw), (None if (db_direct or not has_bias) else db)
         return dx, dw, db, None, None, None, None, None, None, None
+
+
+class FoldDupFn(Function):
+    """Folded form of a Keras conv kernel whose input lists one tensor twice (encoder.py:83-87):
+    (k,k,k,Cf+F,Cout) -> (k,k,k,Cf,Cout), the slice of the leading duplicate added to the slice of the last source.
+    The folded tensor is persistent per layer and refreshed when the weights change; backward scatters its gradient
+    straight into the kernel's slot of the flat gradient buffer (both slices receive the same values)."""
+
+    @staticmethod
+    def forward(ctx, w, F):
+        F = int(F)
+        st = getattr(w, "_b3d_fold", None)
+        flat = getattr(w, "_b3d_flat", None)
+        stamp = (w._version, flat.theta._version if flat is not None else 0, flat.epoch if flat is not None else 0)
+        if st is None or st[0].shape[3] != w.shape[3] - F:
+            wf = torch.empty(tuple(w.shape[:3]) + (w.shape[3] - F, w.shape[4]), device=w.device, dtype=_f32)
+            st = [wf, None]
+            w._b3d_fold = st
+        if flat is not None and getattr(st[0], "_b3d_flat", None) is not flat:
+            st[0]._b3d_flat = flat           # its packed operands join the batched re-pack (ops.repack_all)
+            flat.folds.append((w, st[0], F))
+        if st[1] != stamp:
+            _call("b3d_fold_dup", w, st[0], F)
+            st[1] = stamp
+        ctx.F, ctx.param = F, w
+        ctx.wshape = tuple(w.shape)
+        # a fresh alias per call: the persistent tensor must not carry autograd history from one step (and stream) into
+        # the next — under CUDA-graph capture that is a dependency on uncaptured work
+        out = st[0].detach()
+        out._b3d_base = st[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dwf):
+        pw = ctx.param
+        dw, direct = _grad_target(pw)
+        _call("b3d_unfold_dup", dwf.contiguous(), dw, ctx.F)
+        _grad_done(pw, direct)
+        return (None if direct else dw), None
+
+
+def fold_dup(w, F):
+    return FoldDupFn.apply(w, F)
 
 
 # bf16 copies of conv inputs shared between two weight gradients of one backward pass (fp32 entry points only;

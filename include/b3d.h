@@ -266,6 +266,12 @@ int b3d_p16_pack(const DLTensor* x /*fp32 NDHWC, C % 8 == 0, may be a channel sl
 int b3d_p16_unpack(const DLTensor* src /*P16*/, DLTensor* y /*fp32 NDHWC, may be a channel slice*/, void* stream);
 int b3d_p16_copy_planes(const DLTensor* src /*P16*/, DLTensor* dst /*P16, wider*/, int c8off, void* stream);
 int b3d_colsum(const DLTensor* x /*fp32 NDHWC*/, DLTensor* out /*fp32 [C]*/, void* stream);
+/* The encoder's dense connections feed a block [a_last, a_0, .., a_last] (encoder.py:83-87: `inputs is cache[-1]`): the conv
+ * over it equals a conv over [a_0, .., a_last] with the two weight slices of a_last added.  w: Keras kernel
+ * (k,k,k,Cf+F,Cout); wf: its folded form (k,k,k,Cf,Cout); unfold scatters d(wf) back to d(w) (both slices of a_last get
+ * the same gradient). */
+int b3d_fold_dup(const DLTensor* w, DLTensor* wf, int F, void* stream);
+int b3d_unfold_dup(const DLTensor* dwf, DLTensor* dw, int F, void* stream);
 /* the three conv passes with P16 input operands (same semantics as b3d_conv3d_fwd / _dgrad / _wgrad; tcgen05 path only:
  * wpacked is required).  x0..x3: the sources whose channels are concatenated (x1..x3 nullable), all of the pass's MMA
  * operand type (forward: fp16 by default; data gradient: bf16).  The weight gradient takes bf16 twins of BOTH operands
