@@ -86,6 +86,14 @@ for n, cin, cout in SHAPES:
         yb = torch.empty(n ** 3 * yc.value, device=dev, dtype=torch.bfloat16)
         ms = timeit(lambda: ops._call("b3d_conv3d_wgrad", x, dy, dw, None, 1, 0, xb, yb, 0))
         line += f"| wgrad(+casts) {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TF/s "
+    if which in ("k1p16", "all") and cin % 16 == 0 and cout % 16 == 0:
+        w1 = torch.randn(1, 1, 1, cin, cout, device=dev) * 0.05
+        wp1 = ops.pack_weights(w1, False)
+        gap = torch.empty(1, cout, device=dev)
+        tw = ops.to_p16(x, torch.float16 if prec == "fp16" else torch.bfloat16)
+        ms = timeit(lambda: ops._call("b3d_conv3d_fwd_p16", tw, None, None, None, w1, bias, y, 1, 0, 0, None, 1, gap, 0, wp1))
+        io = n ** 3 * (2.0 * cin + 4.0 * cout)
+        line += f"| 1x1x1+gap(P16) {ms * 1e3:8.1f} us (io {io / ms / 1e6:6.0f} GB/s) "
     if which in ("k1", "all") and cin >= 8 and cout >= 16:
         w1 = torch.randn(1, 1, 1, cin, cout, device=dev) * 0.05
         wp1 = ops.pack_weights(w1, False)
