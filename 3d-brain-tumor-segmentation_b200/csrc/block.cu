@@ -627,65 +627,96 @@ __global__ void __launch_bounds__(kBT)
 }
 
 // ---- channel squeeze-excitation FCs (resnet.py:121-124); one CTA, loops over the batch ----------
-__global__ void __launch_bounds__(256)
+// The matrices are tiny (F x R, F <= 512) but the kernels sit on the critical path 32 times per training step, so what
+// counts is the LENGTH of the dependent load chains: both products are split over all 256 threads.
+//   colvec: out[n] = sum_m v[m] * W[m*N + n]  (n contiguous): thread (part, n) sums rows m = part (mod P), P = 256 / N
+//           partial sums, combined through shared memory
+//   rowvec: out[r] = sum_j W[r*L + j] * v[j]  (j contiguous): one warp per row, lanes over j, shuffle reduction
+constexpr int kSeThreads = 256;
+template <class Fin>
+__device__ __forceinline__ void se_colvec(const float* __restrict__ v, const float* __restrict__ W, int M, int N,
+                                          float* __restrict__ red, Fin finish) {
+  int P = 1;
+  while (P * 2 * N <= kSeThreads) P *= 2;
+  for (int n0 = 0; n0 < N; n0 += kSeThreads) {          // N > 256: one pass per 256 outputs (P = 1)
+    const int t = threadIdx.x, n = n0 + t % (N < kSeThreads ? N : kSeThreads), part = N < kSeThreads ? t / N : 0;
+    float a = 0.f;
+    if (part < P && n < N) {
+#pragma unroll 8
+      for (int m = part; m < M; m += P) a += v[m] * __ldg(W + (long long)m * N + n);
+    }
+    if (P > 1) {
+      if (part < P) red[part * N + n] = a;
+      __syncthreads();
+      if (t < N) {
+        a = red[t];
+        for (int q = 1; q < P; ++q) a += red[q * N + t];
+        finish(t, a);
+      }
+      __syncthreads();
+    } else if (n < N) {
+      finish(n, a);
+    }
+  }
+}
+template <class Fin>
+__device__ __forceinline__ void se_rowvec(const float* __restrict__ W, const float* __restrict__ v, int Rows, int L,
+                                          Fin finish) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < Rows; r += kSeThreads / 32) {
+    float a = 0.f;
+    for (int j = lane; j < L; j += 32) a += __ldg(W + (long long)r * L + j) * v[j];
+    a = warp_sum(a);
+    if (lane == 0) finish(r, a);
+  }
+}
+
+__global__ void __launch_bounds__(kSeThreads)
     se_fc_fwd_kernel(const float* __restrict__ gap_sum, const float* __restrict__ w1, const float* __restrict__ w2,
                      float* __restrict__ hidden, float* __restrict__ chse, int B, int F, int R, float inv_vox) {
-  extern __shared__ float sm[];  // mean[F], hid[R]
+  extern __shared__ float sm[];  // mean[F], hid[R], red[256]
   float* mean = sm;
   float* hid = sm + F;
+  float* red = hid + R;
   for (int b = 0; b < B; ++b) {
-    for (int c = threadIdx.x; c < F; c += blockDim.x) mean[c] = gap_sum[b * F + c] * inv_vox;
+    for (int c = threadIdx.x; c < F; c += kSeThreads) mean[c] = gap_sum[b * F + c] * inv_vox;
     __syncthreads();
-    for (int k = threadIdx.x; k < R; k += blockDim.x) {
-      float a = 0.f;
-      for (int c = 0; c < F; ++c) a += mean[c] * w1[c * R + k];
+    se_colvec(mean, w1, F, R, red, [&](int k, float a) {
       a = fmaxf(a, 0.f);
       hid[k] = a;
       hidden[b * R + k] = a;
-    }
+    });
     __syncthreads();
-    for (int c = threadIdx.x; c < F; c += blockDim.x) {
-      float a = 0.f;
-      for (int k = 0; k < R; ++k) a += hid[k] * w2[k * F + c];
-      chse[b * F + c] = 1.f / (1.f + expf(-a));
-    }
+    se_colvec(hid, w2, R, F, red, [&](int c, float a) { chse[b * F + c] = 1.f / (1.f + expf(-a)); });
     __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSeThreads)
     se_fc_bwd_kernel(const float* __restrict__ gap_sum, const float* __restrict__ w1, const float* __restrict__ w2,
                      const float* __restrict__ hidden, const float* __restrict__ chse,
                      const float* __restrict__ dchse, float* __restrict__ dw1, float* __restrict__ dw2,
                      float* __restrict__ dgap, int B, int F, int R, float inv_vox) {
-  extern __shared__ float sm[];  // dz2[F], dz1[R]
+  extern __shared__ float sm[];  // dz2[F], dz1[R], red[256]
   float* dz2 = sm;
   float* dz1 = sm + F;
-  for (int i = threadIdx.x; i < F * R; i += blockDim.x) dw1[i] = 0.f, dw2[i] = 0.f;
-  __syncthreads();
   for (int b = 0; b < B; ++b) {
-    for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    for (int c = threadIdx.x; c < F; c += kSeThreads) {
       const float y = chse[b * F + c];
       dz2[c] = dchse[b * F + c] * y * (1.f - y);
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < R; k += blockDim.x) {
-      float a = 0.f;
-      for (int c = 0; c < F; ++c) a += w2[k * F + c] * dz2[c];
-      dz1[k] = hidden[b * R + k] > 0.f ? a : 0.f;
-    }
+    se_rowvec(w2, dz2, R, F, [&](int k, float a) { dz1[k] = hidden[b * R + k] > 0.f ? a : 0.f; });
     __syncthreads();
-    for (int i = threadIdx.x; i < F * R; i += blockDim.x) {
+    for (int i = threadIdx.x; i < F * R; i += kSeThreads) {
       const int k2 = i / F, c2 = i % F;              // dw2[k][c]
-      dw2[i] += hidden[b * R + k2] * dz2[c2];
+      const float g2 = hidden[b * R + k2] * dz2[c2];
       const int c1 = i / R, k1 = i % R;              // dw1[c][k]
-      dw1[i] += gap_sum[b * F + c1] * inv_vox * dz1[k1];
+      const float g1 = gap_sum[b * F + c1] * inv_vox * dz1[k1];
+      dw2[i] = b == 0 ? g2 : dw2[i] + g2;
+      dw1[i] = b == 0 ? g1 : dw1[i] + g1;
     }
-    for (int c = threadIdx.x; c < F; c += blockDim.x) {
-      float a = 0.f;
-      for (int k = 0; k < R; ++k) a += w1[c * R + k] * dz1[k];
-      dgap[b * F + c] = a * inv_vox;
-    }
+    se_rowvec(w1, dz1, F, R, [&](int c, float a) { dgap[b * F + c] = a * inv_vox; });
     __syncthreads();
   }
 }
@@ -764,7 +795,7 @@ extern "C" int b3d_se_fc_fwd(const DLTensor* gap_sum_, const DLTensor* w1_, cons
   B3D_REQUIRE(w1.shape[0] == F && w2.shape[0] == R && w2.shape[1] == F, B3D_ERR_SHAPE, "se_fc: weight shapes");
   B3D_TRY(vecF(hidden_, (long long)B * R, "hidden", &hid));
   B3D_TRY(vecF(chse_, (long long)B * F, "chse", &ch));
-  se_fc_fwd_kernel<<<1, 256, sizeof(float) * (F + R), (cudaStream_t)stream>>>(
+  se_fc_fwd_kernel<<<1, kSeThreads, sizeof(float) * (F + R + kSeThreads), (cudaStream_t)stream>>>(
       (const float*)gs.p, (const float*)w1.p, (const float*)w2.p, (float*)hid.p, (float*)ch.p, B, F, R, inv_vox);
   B3D_LAUNCH_CHECK("se_fc_fwd");
   return B3D_OK;
@@ -785,7 +816,7 @@ extern "C" int b3d_se_fc_bwd(const DLTensor* gap_sum_, const DLTensor* w1_, cons
   B3D_TRY(vecF(dw1_, (long long)F * R, "dw1", &dw1));
   B3D_TRY(vecF(dw2_, (long long)F * R, "dw2", &dw2));
   B3D_TRY(vecF(dgap_, (long long)B * F, "dgap", &dg));
-  se_fc_bwd_kernel<<<1, 256, sizeof(float) * (F + R), (cudaStream_t)stream>>>(
+  se_fc_bwd_kernel<<<1, kSeThreads, sizeof(float) * (F + R + kSeThreads), (cudaStream_t)stream>>>(
       (const float*)gs.p, (const float*)w1.p, (const float*)w2.p, (const float*)hid.p, (const float*)ch.p,
       (const float*)dch.p, (float*)dw1.p, (float*)dw2.p, (float*)dg.p, B, F, R, inv_vox);
   B3D_LAUNCH_CHECK("se_fc_bwd");

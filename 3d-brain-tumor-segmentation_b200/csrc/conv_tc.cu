@@ -67,7 +67,7 @@ struct TcCfg {
   static constexpr int WST_BYTES = TPS * TAP_BYTES;
   static constexpr int WS = (KS == 1) ? 8 : 3;
   static constexpr int ACC_COLS = 256;                // per accumulator stage (P*N <= 256)
-  static constexpr int BAR_BYTES = 512;
+  static constexpr int BAR_BYTES = 768;               // mbarriers + TMEM slot (256 B) | CTA-level statistics / pooling sums
   static constexpr int HS = (3 * HALO_BYTES + WS * WST_BYTES + BAR_BYTES <= 220 * 1024) ? 3 : 2;
   static constexpr int SMEM = HS * HALO_BYTES + WS * WST_BYTES + BAR_BYTES;
   static constexpr int ACC_BLOCKS = FOLD ? NW * (TD + 4) : P;     // N-column accumulator blocks per stage
@@ -138,6 +138,15 @@ __device__ __forceinline__ void ld256(const float* p, float* r) {
                : "l"(p));
 }
 
+// 256-bit store: one full 32-byte sector per lane (sm_100 STG.E.256).  The epilogue's lanes each own the 16 channels
+// (64 bytes) of one voxel; with 128-bit stores every warp instruction touches 32 sectors HALF — twice the L2 write
+// requests, all of them partial
+__device__ __forceinline__ void st256(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e),
+               "f"(f), "f"(g), "f"(h)
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -172,12 +181,44 @@ __device__ __noinline__ void flush_stats(double* stats, int cur_chunk, float s0,
   }
 }
 
+// the same for a warp's LAST flush: warps of a CTA end in the same chunk (or two), so their sums are combined in shared
+// memory (4 slots tagged with the chunk; a slot taken by another chunk falls back to the global atomics) and written
+// by the CTA once, after its final barrier
+__device__ __noinline__ void flush_stats_cta(double* stats, int cur_chunk, float s0, float s1, int lane, double* acc,
+                                             int* tag) {
+  const int cc = __reduce_max_sync(0xffffffffu, cur_chunk);
+  if (cc < 0) return;
+  const bool uni = __all_sync(0xffffffffu, cur_chunk == cc || cur_chunk < 0);
+  if (uni) {
+    const float a0 = warp_sum(cur_chunk >= 0 ? s0 : 0.f), a1 = warp_sum(cur_chunk >= 0 ? s1 : 0.f);
+    if (lane == 0) {
+      const int slot = cc & 3;
+      const int old = atomicCAS(&tag[slot], -1, cc);
+      if (old == -1 || old == cc) {
+        atomicAdd(&acc[2 * slot], (double)a0);
+        atomicAdd(&acc[2 * slot + 1], (double)a1);
+      } else {
+        atomicAdd(&stats[2 * cc], (double)a0);
+        atomicAdd(&stats[2 * cc + 1], (double)a1);
+      }
+    }
+  } else if (cur_chunk >= 0) {
+    atomicAdd(&stats[2 * cur_chunk], (double)s0);
+    atomicAdd(&stats[2 * cur_chunk + 1], (double)s1);
+  }
+}
+
 constexpr int kLoaderWarps = 8;
 // Number of MMA-issuing warps (each owns the patches p = its index mod kMmaWarps).  One warp can issue a tcgen05.mma
 // only every ~50 cycles (profiles/r01_umma_rate.txt), but measured with 2 issuers this kernel does not get faster (the
 // shifted-tile A fetch from shared memory, ~56 cycles per N = 16 MMA here, is the limit, not the issue rate): 1.
 constexpr int kMmaWarps = 1;
-constexpr int kTcThreads = (4 + kLoaderWarps + 2 + (kMmaWarps - 1)) * 32;   // 4 epilogue + loaders + MMA + weights + MMA
+static_assert(kMmaWarps == 1, "warp roles below assume one MMA-issuing warp");
+// warps: 0-3 epilogue | 4-11 operand loaders (thread-loader form) or 8 MORE epilogue warps (TMA form: the loaders have
+// nothing to do, and the 1x1x1 / narrow layers are bound by the epilogue's store rate: profiles/r02e) | 12 MMA issuer |
+// 13 weight producer (+ TMEM alloc) | 14 TMA producer of the operand halos
+constexpr int kTmaWarp = kLoaderWarps + 6;
+constexpr int kTcThreads = (kTmaWarp + 1) * 32;
 
 template <class C>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams prm, const __grid_constant__ TcMaps maps) {
@@ -192,19 +233,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
   uint64_t* acc_full = bars + 8 + 2 * C::WS;   // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]  4 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  // final flush of the epilogue warps' running sums goes through shared memory: one set of global atomics per CTA
+  double* cta_stat = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [4 slots][2]
+  int* cta_stat_tag = reinterpret_cast<int*>(cta_stat + 8);                                // [4] chunk of the slot, -1 = free
+  float* cta_gap = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);       // [64] (N <= 64)
+  int* cta_gap_b = reinterpret_cast<int*>(cta_gap + 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks_all = prm.Cin / C::CK;
   const int c_begin = blockIdx.z * prm.kchunks;
   const int nchunks = min(prm.kchunks, nchunks_all - c_begin);   // this CTA's K chunks: [c_begin, c_begin + nchunks)
   const int nsp = blockIdx.y;  // N split
+  // a persistent CTA owns a CONTIGUOUS range of tiles: its GroupNorm chunk (and sample) then changes once or twice in
+  // its life instead of every other tile, which is what the number of same-address statistics atomics scales with
+  // (~15 ns each once they queue up on one L2 address)
+  const int tpc = prm.ntiles / (int)gridDim.x, trem = prm.ntiles % (int)gridDim.x;
+  const int tile0 = (int)blockIdx.x * tpc + min((int)blockIdx.x, trem), tile1 = tile0 + tpc + ((int)blockIdx.x < trem ? 1 : 0);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::HS; ++i) { mbar_init(smem_u32(&halo_full[i]), prm.tma ? 1 : kLoaderWarps * 32); mbar_init(smem_u32(&halo_empty[i]), kMmaWarps); }
     for (int i = 0; i < C::WS; ++i) { mbar_init(smem_u32(&w_full[i]), 1); mbar_init(smem_u32(&w_empty[i]), kMmaWarps); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), kMmaWarps); mbar_init(smem_u32(&acc_empty[i]), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), kMmaWarps); mbar_init(smem_u32(&acc_empty[i]), prm.tma ? 4 + kLoaderWarps : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x < 64) cta_gap[threadIdx.x] = 0.f;
+  if (threadIdx.x < 8) cta_stat[threadIdx.x] = 0.0;
+  if (threadIdx.x < 4) cta_stat_tag[threadIdx.x] = -1;
+  if (threadIdx.x == 0) *cta_gap_b = -1;
   if (warp == kLoaderWarps + 5) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(512));
@@ -215,12 +270,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 4 + kLoaderWarps && prm.tma) {
+  if (warp == kTmaWarp) {
     // ============ operand loader, TMA form: one elected thread fetches the halo of every K chunk as ONE 5-D box
     // {HW voxels, 2 planes, HH, HD, 1} of the source's P16 tensor map (zero fill outside the volume = TF 'SAME' padding)
-    if (warp == 4 && lane == 0) {
+    if (prm.tma && lane == 0) {
       int hs = 0, hph = 0;
-      for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < tile1; ++tile) {
         int t = tile;
         const int wt = t % prm.ntw; t /= prm.ntw;
         const int ht = t % prm.nth; t /= prm.nth;
@@ -240,11 +295,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
         }
       }
     }
-  } else if (warp >= 4 && warp < 4 + kLoaderWarps) {
+  } else if (warp >= 4 && warp < 4 + kLoaderWarps && !prm.tma) {
     // ============ operand loaders: global fp32 -> (bf16|tf32) cells in shared memory ============
     const int lw = warp - 4;
     int hs = 0, hph = 0;
-    for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < tile1; ++tile) {
       int t = tile;
       const int wt = t % prm.ntw; t /= prm.ntw;
       const int ht = t % prm.nth; t /= prm.nth;
@@ -371,7 +426,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
       const uint8_t* wsrc =
           reinterpret_cast<const uint8_t*>(prm.wp) + ((size_t)nsp * nchunks_all + c_begin) * C::TAPS * C::TAP_BYTES;
       constexpr int kStagesPerChunk = C::TAPS / C::TPS;
-      for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < tile1; ++tile) {
         for (int cs = 0; cs < nchunks * kStagesPerChunk; ++cs) {
           mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
           const uint32_t full = smem_u32(&w_full[ws]);
@@ -381,10 +436,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
         }
       }
     }
-  } else if (warp == kLoaderWarps + 4 || warp >= kLoaderWarps + 6) {
+  } else if (warp == kLoaderWarps + 4) {
     // ============ MMA issuer: the whole warp runs the (warp-uniform) control flow so that descriptors stay
     // in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit ============
-    const int mw = warp == kLoaderWarps + 4 ? 0 : warp - (kLoaderWarps + 5);   // which issuing warp: patches p = mw (mod kMmaWarps)
+    const int mw = 0;                                   // which issuing warp: patches p = mw (mod kMmaWarps)
     const bool leader = elect_one();
     // instruction descriptor: D=f32, A=B=(bf16|tf32), K-major both, N, M=128
     const uint32_t fmt = C::OP == OP_F16 ? 0u : (C::OP == OP_BF16 ? 1u : 2u);   // kind::f16: 0 = f16, 1 = bf16
@@ -392,7 +447,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
         (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C::N >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t halo_addr = smem_u32(halo), wst_addr = smem_u32(wst);
     int hs = 0, hph = 0, ws = 0, wph = 0, it = 0;
-    for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < tile1; ++tile, ++it) {
       const int as = it & 1, aph = (it >> 1) & 1;
       mbar_wait(smem_u32(&acc_empty[as]), aph ^ 1);
       tc_fence_after();
@@ -469,9 +524,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
       if (leader) tc_commit(smem_u32(&acc_full[as]));
       __syncwarp();
     }
-  } else if (warp < 4) {
+  } else if (warp < 4 + kLoaderWarps) {
     // ============ epilogue (TMEM -> registers -> NDHWC global) ============
-    const int q = warp;                     // TMEM lane quarter == warp % 4
+    // thread-loader form: warps 0-3, one per TMEM lane quarter; TMA form: warps 0-11, three per quarter, each taking
+    // every third patch of a tile
+    const int q = warp & 3;                 // TMEM lane quarter == warp % 4
+    const int eg = warp >> 2, neg = prm.tma ? 1 + kLoaderWarps / 4 : 1;
+    const bool wide_st = prm.act == 0 && !prm.accumulate && prm.ksplit <= 1 && (prm.yp & 7) == 0 &&
+                         (reinterpret_cast<uintptr_t>(prm.y) & 31) == 0;
     const int row = q * 32 + lane;          // patch row: h = row/8, w = row%8
     const int ph = row >> 3, pwv = row & 7;
     const long long S = (long long)prm.D * prm.H * prm.W * (prm.d2s ? 8 : 1);   // voxels of y per sample
@@ -497,7 +557,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
         }
     };
     int it = 0;
-    for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x, ++it) {
+    // running GroupNorm sums of this warp: kept ACROSS tiles and flushed when the chunk changes (a persistent CTA's
+    // consecutive tiles usually lie in the same chunk) — the fp64 atomics all land on 2 * groups addresses
+    int cur_chunk = -1;
+    float s0 = 0.f, s1 = 0.f;
+    for (int tile = tile0; tile < tile1; ++tile, ++it) {
       const int as = it & 1, aph = (it >> 1) & 1;
       int t = tile;
       const int wt = t % prm.ntw; t /= prm.ntw;
@@ -507,8 +571,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
       if (kGapPersist && b != gap_b) { flush_gap(gap_b); gap_b = b; }
       mbar_wait(smem_u32(&acc_full[as]), aph);
       tc_fence_after();
-      int cur_chunk = -1;
-      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         // output column block -> (parity, channel offset) when the result is stored depth-to-space
@@ -525,7 +587,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
         for (int i = 0; i < 16; ++i) bv[i] = (prm.bias != nullptr && i < ncol) ? __ldg(prm.bias + ycol + i) : 0.f;
         float (&gs)[16] = gsum[kGapPersist ? j : 0];
 #pragma unroll 1
-        for (int p = 0; p < C::P; ++p) {
+        for (int p = eg; p < C::P; p += neg) {
           const int pd = p / C::NW, pw = p % C::NW;
           const int d = dt * C::TD + pd, h = ht * C::TH + ph, w = wt * C::TW + pw * 8 + pwv;
           const bool valid = d < prm.D && h < prm.H && w < prm.W;
@@ -547,9 +609,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
           tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + (C::FOLD ? C::acc_block(pd, pw) : p) * C::N + j * 16, v);
           if (valid && prm.ksplit > 1) {
             // partial sums of this K range -> workspace slice blockIdx.z
-            float4* dst = reinterpret_cast<float4*>(yp + (long long)blockIdx.z * prm.ws_slice);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            float* dst = yp + (long long)blockIdx.z * prm.ws_slice;       // workspace slices are 128-byte aligned
+            st256(dst, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+            st256(dst + 8, v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
           } else if (valid && ncol < 16) {
             // narrow output (Cout < 16: the 2-3 channel output convs): scalar stores, optional sigmoid
 #pragma unroll
@@ -563,6 +625,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
                 s1 += o * o;
                 gs[i] += o;
               }
+          } else if (valid && wide_st) {
+            // plain epilogue (every conv of the training step but the sigmoid / accumulate forms): 2 x 256-bit stores
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              o[i] = v[i] + bv[i];
+              s0 += o[i];
+              s1 += o[i] * o[i];
+              gs[i] += o[i];
+            }
+            st256(yp, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+            st256(yp + 8, o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]);
           } else if (valid) {
             float4* dst = reinterpret_cast<float4*>(yp);
 #pragma unroll
@@ -599,14 +673,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
-      if (prm.stats != nullptr) flush_stats(prm.stats, cur_chunk, s0, s1, lane);
     }
-    if (kGapPersist) flush_gap(gap_b);
+    if (prm.stats != nullptr) flush_stats_cta(prm.stats, cur_chunk, s0, s1, lane, cta_stat, cta_stat_tag);
+    if (kGapPersist && prm.gap != nullptr && gap_b >= 0) {
+      // all epilogue warps end on the same tile, hence the same sample
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = warp_sum(gsum[j][i]);
+          if (lane == 0) atomicAdd(&cta_gap[j * 16 + i], a);
+        }
+      if (lane == 0) *cta_gap_b = gap_b;
+    }
   }
 
   // ---- teardown
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x < 4 && prm.stats != nullptr && cta_stat_tag[threadIdx.x] >= 0) {
+    atomicAdd(&prm.stats[2 * cta_stat_tag[threadIdx.x]], cta_stat[2 * threadIdx.x]);
+    atomicAdd(&prm.stats[2 * cta_stat_tag[threadIdx.x] + 1], cta_stat[2 * threadIdx.x + 1]);
+  }
+  if (C::N <= 64 && threadIdx.x >= 32 && threadIdx.x < 32 + C::N && prm.gap != nullptr && *cta_gap_b >= 0) {
+    const int i = threadIdx.x - 32;
+    if (nsp * C::N + i < prm.cout_real)
+      atomicAdd(&prm.gap[(long long)*cta_gap_b * prm.cout_real + nsp * C::N + i], cta_gap[i]);
+  }
   if (warp == kLoaderWarps + 5) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));

@@ -252,22 +252,26 @@ __global__ void dice_finalize_kernel(const float* __restrict__ acc, float* __res
 }
 
 // ================================================================ dense (Flatten->Dense, Dense relu)
-// y[b][n] = act(sum_k x[b][k] w[k][n] + bias[n]);  block = 32 (n) x 16 (k-slices)
+// y[b][n] = act(sum_k x[b][k] w[k][n] + bias[n]);  block = 8 (n) x 64 (k-slices): the layers are matrix-vector
+// products on the critical path (K up to 4096, N <= 256), so the grid is N/8 CTAs and each thread's dependent chain K/64
+// long; a quarter-warp reads one 32-byte sector of a weight row
 __global__ void __launch_bounds__(512)
     dense_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                      float* __restrict__ y, int K, int N, int act) {
-  __shared__ float red[16][33];
-  const int lane = threadIdx.x & 31, ks = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + lane, b = blockIdx.y;
+  __shared__ float red[64][9];
+  const int lane = threadIdx.x & 31, nl = lane & 7, ks = (threadIdx.x >> 5) * 4 + (lane >> 3);
+  const int n = blockIdx.x * 8 + nl, b = blockIdx.y;
   float a = 0.f;
-  if (n < N)
-    for (int k = ks; k < K; k += 16) a = fmaf(__ldg(x + (long long)b * K + k), __ldg(w + (long long)k * N + n), a);
-  red[ks][lane] = a;
+  if (n < N) {
+#pragma unroll 4
+    for (int k = ks; k < K; k += 64) a = fmaf(__ldg(x + (long long)b * K + k), __ldg(w + (long long)k * N + n), a);
+  }
+  red[ks][nl] = a;
   __syncthreads();
-  if (ks == 0 && n < N) {
+  if (threadIdx.x < 8 && n < N) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s += red[i][lane];
+    for (int i = 0; i < 64; ++i) s += red[i][nl];
     s += bias ? bias[n] : 0.f;
     y[(long long)b * N + n] = act == 1 ? fmaxf(s, 0.f) : s;
   }
@@ -686,7 +690,7 @@ extern "C" int b3d_dense_fwd(const DLTensor* x_, const DLTensor* w_, const DLTen
     B3D_REQUIRE(b.numel == N, B3D_ERR_SHAPE, "dense: bias size");
     bp = (const float*)b.p;
   }
-  dense_fwd_kernel<<<dim3((N + 31) / 32, B), 512, 0, (cudaStream_t)stream>>>((const float*)x.p, (const float*)w.p,
+  dense_fwd_kernel<<<dim3((N + 7) / 8, B), 512, 0, (cudaStream_t)stream>>>((const float*)x.p, (const float*)w.p,
                                                                             bp, (float*)y.p, K, N, act);
   B3D_LAUNCH_CHECK("dense_fwd");
   return B3D_OK;
