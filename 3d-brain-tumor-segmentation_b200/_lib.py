@@ -93,6 +93,7 @@ SIGNATURES = {
     "b3d_block_epilogue_bwd_reduce": "TTTTTTTTTTTTifiv",
     "b3d_block_epilogue_bwd_apply": "TTTTTTTTTTTTifiv",
     "b3d_loss_fwd": "TTTTTTTTv",
+    "b3d_loss_dice_fwd": "TTTTTTTTTTiv",
     "b3d_loss_bwd": "TTTTTTTTTTTTv",
     "b3d_loss_finalize": "TTLLv",
     "b3d_loss_bwd_dp": "TTTTTTTTTTTTiv",
@@ -105,6 +106,8 @@ SIGNATURES = {
     "b3d_l2_losses": "TTTfv",
     "b3d_l2_grad": "TTTTfv",
     "b3d_axpy": "TTLfTv",
+    "b3d_sum_add": "TTTv",
+    "b3d_zero": "Tv",
     "b3d_dropout": "TTTfUTv",
     "b3d_mul_scale": "TTTfv",
     "b3d_sigmoid_bwd": "TTTv",

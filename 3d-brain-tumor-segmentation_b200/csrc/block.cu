@@ -374,16 +374,6 @@ __device__ __forceinline__ void cell_store(const Twin16& o, unsigned b, const Vo
   if (o.p2 != nullptr)
     o.p2[idx] = make_uint4(pk16(v[0], v[1], 1), pk16(v[2], v[3], 1), pk16(v[4], v[5], 1), pk16(v[6], v[7], 1));
 }
-__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
-  const float4 a = ld_stream(reinterpret_cast<const float4*>(p));
-  const float4 c = ld_stream(reinterpret_cast<const float4*>(p) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-}
-__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
-  st_stream(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
-  st_stream(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
-}
-
 // grid: (segments per chunk, B*G); gm.T = F/8 lanes per voxel
 template <bool HAS_GN>
 __global__ void __launch_bounds__(kBT)
@@ -560,36 +550,44 @@ __global__ void __launch_bounds__(kBT)
   const long long vend = min(v0 + gm.vox_per_cta, gm.vpc);
   const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
   const int iters = (int)((vend - v0 + vstep - 1) / vstep);   // CTA-uniform: whole warps stay in the shuffles
-  for (int it = 0; it < iters; ++it) {
-    const long long v = v0 + (long long)it * vstep + vl;
-    const bool act = v < vend;
-    const long long eo = (vbase + (act ? v : v0)) * gm.F + c;
-    float r[8], d[8], h[8];
-    ld8(res + eo, r);
-    ld8(dout + eo, d);
-    ld8(h2 + eo, h);
-    float dot = 0.f, ds = 0.f;
+  // two voxels per thread and step: all six 32-byte loads are issued before the first shuffle reduction
+  for (int it = 0; it < iters; it += 2) {
+    float r[2][8], d[2][8], h[2][8];
+    bool act[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (!act) d[i] = 0.f;
-      dot += r[i] * w8[i];
-      ds += r[i] * d[i];
+    for (int u = 0; u < 2; ++u) {
+      const long long v = v0 + (long long)(it + u) * vstep + vl;
+      act[u] = it + u < iters && v < vend;
+      const long long eo = (vbase + (act[u] ? v : v0)) * gm.F + c;
+      ld8(res + eo, r[u]);
+      ld8(dout + eo, d[u]);
+      ld8(h2 + eo, h[u]);
     }
-    dot = group_sum(dot, T);
-    ds = group_sum(ds, T);
-    const float s = sigmoidf_(dot);
-    const float dl = ds * s * (1.f - s);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      ac[i] += d[i] * r[i];
-      aw[i] += dl * r[i];
-      const float xh = (h[i] - mean) * rstd;
-      const float gq = (xh * ga8[i] + be8[i]) > 0.f ? d[i] : 0.f;
-      ag[i] += gq * xh;
-      ab[i] += gq;
-      const float hq = gq * ga8[i];
-      s1 += hq;
-      s2 += hq * xh;
+    for (int u = 0; u < 2; ++u) {
+      float dot = 0.f, ds = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!act[u]) d[u][i] = 0.f;
+        dot += r[u][i] * w8[i];
+        ds += r[u][i] * d[u][i];
+      }
+      dot = group_sum(dot, T);
+      ds = group_sum(ds, T);
+      const float s = sigmoidf_(dot);
+      const float dl = ds * s * (1.f - s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ac[i] += d[u][i] * r[u][i];
+        aw[i] += dl * r[u][i];
+        const float xh = (h[u][i] - mean) * rstd;
+        const float gq = (xh * ga8[i] + be8[i]) > 0.f ? d[u][i] : 0.f;
+        ag[i] += gq * xh;
+        ab[i] += gq;
+        const float hq = gq * ga8[i];
+        s1 += hq;
+        s2 += hq * xh;
+      }
     }
   }
   // lanes of a warp with equal (lane % T) hold the same channels: butterfly over the voxel sub-index first
@@ -662,12 +660,21 @@ __device__ __forceinline__ void se_colvec(const float* __restrict__ v, const flo
 template <class Fin>
 __device__ __forceinline__ void se_rowvec(const float* __restrict__ W, const float* __restrict__ v, int Rows, int L,
                                           Fin finish) {
+  // four rows per warp and step: their loads and shuffle reductions are independent and overlap
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < Rows; r += kSeThreads / 32) {
-    float a = 0.f;
-    for (int j = lane; j < L; j += 32) a += __ldg(W + (long long)r * L + j) * v[j];
-    a = warp_sum(a);
-    if (lane == 0) finish(r, a);
+  for (int r0 = warp * 4; r0 < Rows; r0 += (kSeThreads / 32) * 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = lane; j < L; j += 32) {
+      const float vj = v[j];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u < Rows) a[u] += __ldg(W + (long long)(r0 + u) * L + j) * vj;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = warp_sum(a[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (lane == 0 && r0 + u < Rows) finish(r0 + u, a[u]);
   }
 }
 

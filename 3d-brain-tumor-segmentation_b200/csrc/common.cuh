@@ -122,4 +122,24 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                "f"(v.z), "f"(v.w));
 }
 
+// 8 consecutive floats of a read-once / write-once tensor.  Stores: ONE 256-bit access when 32-byte aligned (sm_100
+// STG.256: a lane owns a whole 32-byte sector, where a pair of 128-bit stores makes every warp instruction write 32
+// sectors half), else the pair.
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  // loads stay a pair of 128-bit accesses: measured on B200 (tools/hbm_bench.py) the 256-bit form is no faster for the
+  // apply kernels and SLOWER for the reducing ones (gn_bwd_reduce 67 -> 58 % of the HBM peak)
+  const float4 a = ld_stream(reinterpret_cast<const float4*>(p));
+  const float4 c = ld_stream(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  if ((reinterpret_cast<unsigned long long>(p) & 31ull) == 0) {
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+                 "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]));
+  } else {
+    st_stream(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    st_stream(reinterpret_cast<float4*>(p) + 1, make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+
 }  // namespace b3d

@@ -79,6 +79,112 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ================================================================ loss forward + hard-Dice metric in ONE pass
+// The training loop evaluates DiceVAELoss and DiceCoefficient on the same (y, y_pred) (train.py:143,147): this kernel
+// reads them once.  A thread owns 4 consecutive voxels of a fixed W position (C float4 loads per tensor, channel of
+// every element known at compile time) and walks the (b, d, h) rows: the soft-Dice sums are scalar per class, the
+// metric's are per (w, class) — the reference leaves W un-reduced (util.py:36) — and stay in registers until the end.
+template <int C>
+__global__ void __launch_bounds__(256)
+    loss_dice_fwd_kernel(const float* __restrict__ yp, const float* __restrict__ y, long long nrows, int W,
+                         const float* __restrict__ x, const float* __restrict__ yv, long long n_rec,
+                         const float* __restrict__ mu, const float* __restrict__ lv, int n_lat,
+                         double* __restrict__ sums, float* __restrict__ acc) {
+  extern __shared__ float sm[];  // [W][C][3]
+  for (int i = threadIdx.x; i < W * C * 3; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int QW = W / 4;
+  const int rpb = blockDim.x >= QW ? blockDim.x / QW : 1;
+  const int wl = threadIdx.x % QW, rl = threadIdx.x / QW;
+  const bool active = rl < rpb;
+  float I[C], P[C], T[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) I[c] = P[c] = T[c] = 0.f;
+  for (int wq = wl; wq < QW && active; wq += blockDim.x >= QW ? QW : blockDim.x) {
+    float a0[4][C], a1[4][C], a2[4][C];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int c = 0; c < C; ++c) a0[u][c] = a1[u][c] = a2[u][c] = 0.f;
+#pragma unroll 2
+    for (long long r = (long long)blockIdx.x * rpb + rl; r < nrows; r += (long long)gridDim.x * rpb) {
+      const long long e = (r * W + 4 * wq) * C;
+      float p[4 * C], t[4 * C];
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(yp + e) + q);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(y + e) + q);
+        p[4 * q] = a.x; p[4 * q + 1] = a.y; p[4 * q + 2] = a.z; p[4 * q + 3] = a.w;
+        t[4 * q] = b.x; t[4 * q + 1] = b.y; t[4 * q + 2] = b.z; t[4 * q + 3] = b.w;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int am = 0;
+        float mx = -1e30f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float pv = p[u * C + c], tv = t[u * C + c];
+          I[c] += pv * tv;
+          P[c] += pv * pv;
+          T[c] += tv * tv;
+          if (pv > mx) { mx = pv; am = c; }     // first maximum, like tf.argmax
+        }
+        const float on = mx > 0.5f ? 1.f : 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float h = (c == am) ? on : 0.f;
+          a0[u][c] += h * t[u * C + c];
+          a1[u][c] += h;
+          a2[u][c] += t[u * C + c];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float* a = sm + ((4 * wq + u) * C + c) * 3;
+        atomicAdd(a, a0[u][c]);
+        atomicAdd(a + 1, a1[u][c]);
+        atomicAdd(a + 2, a2[u][c]);
+      }
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float sse = 0.f;
+  if (x != nullptr) {
+    const long long m4 = n_rec / 4;
+#pragma unroll 4
+    for (long long i = tid; i < m4; i += stride) {
+      const float4 a = ld_stream(reinterpret_cast<const float4*>(x) + i);
+      const float4 b = ld_stream(reinterpret_cast<const float4*>(yv) + i);
+      const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+      sse += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    if (tid == 0)
+      for (long long e = m4 * 4; e < n_rec; ++e) { const float d = x[e] - yv[e]; sse += d * d; }
+  }
+  float kl = 0.f;
+  if (mu != nullptr && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_lat; i += blockDim.x) kl += mu[i] * mu[i] + expf(lv[i]) - lv[i] - 1.0f;
+
+  __shared__ float red[32 * (3 * C + 2)];
+  float v[3 * C + 2];
+#pragma unroll
+  for (int c = 0; c < C; ++c) { v[c] = I[c]; v[C + c] = P[c]; v[2 * C + c] = T[c]; }
+  v[3 * C] = sse;
+  v[3 * C + 1] = kl;
+  block_sum<3 * C + 2, float>(v, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 3 * C + 2; ++i)
+      if (v[i] != 0.f) atomicAdd(&sums[i], (double)v[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < W * C * 3; i += blockDim.x)
+    if (sm[i] != 0.f) atomicAdd(&acc[i], sm[i]);
+}
+
 // out[0] = total, out[1] = dice, out[2] = l2 (mean), out[3] = kld (mean)
 __global__ void loss_finalize_kernel(const double* __restrict__ sums, float* __restrict__ out, int C,
                                      double inv_rec, double inv_lat, int with_vae) {
@@ -577,6 +683,55 @@ extern "C" int b3d_loss_fwd(const DLTensor* x_, const DLTensor* y_, const DLTens
   return B3D_OK;
 }
 
+// b3d_loss_fwd and b3d_dice_coeff(reduce_w = 0 | 1) of the same (y, y_pred) in one pass over them (5-D NDHWC tensors,
+// W % 4 == 0).  acc: fp32 [W*C*3] workspace, dice: fp32 [2] = macro, micro.
+extern "C" int b3d_loss_dice_fwd(const DLTensor* x_, const DLTensor* y_, const DLTensor* ypred_, const DLTensor* yvae_,
+                                 const DLTensor* zmean_, const DLTensor* zlogvar_, DLTensor* sums_, DLTensor* out_,
+                                 DLTensor* acc_, DLTensor* dice_, int reduce_w, void* stream) {
+  TView y, yp, x, yv, mu, lv, sums, out, acc, dice;
+  B3D_TRY(view(y_, DT_F32, 5, false, "y", &y));
+  B3D_TRY(view(ypred_, DT_F32, 5, false, "y_pred", &yp));
+  B3D_REQUIRE(y.numel == yp.numel, B3D_ERR_SHAPE, "loss: y / y_pred size mismatch");
+  const int W = (int)yp.shape[3], C = (int)yp.shape[4];
+  B3D_REQUIRE(W % 4 == 0, B3D_ERR_UNSUPPORTED, "loss_dice_fwd: W (%d) must be a multiple of 4", W);
+  const bool vae = yvae_ != nullptr;
+  if (vae) {
+    B3D_REQUIRE(x_ && zmean_ && zlogvar_, B3D_ERR_ARG, "loss: x, z_mean, z_logvar required with y_vae");
+    B3D_TRY(flat_f32(x_, "x", &x));
+    B3D_TRY(flat_f32(yvae_, "y_vae", &yv));
+    B3D_TRY(flat_f32(zmean_, "z_mean", &mu));
+    B3D_TRY(flat_f32(zlogvar_, "z_logvar", &lv));
+    B3D_REQUIRE(x.numel == yv.numel && mu.numel == lv.numel, B3D_ERR_SHAPE, "loss: VAE tensor size mismatch");
+  }
+  B3D_TRY(view(sums_, DT_F64, 1, false, "sums", &sums));
+  B3D_REQUIRE(sums.numel == 3 * C + 2, B3D_ERR_SHAPE, "sums: expected %d fp64 values", 3 * C + 2);
+  B3D_TRY(flat_f32(out_, "out", &out));
+  B3D_REQUIRE(out.numel == 4, B3D_ERR_SHAPE, "out: expected 4 floats");
+  B3D_TRY(flat_f32(acc_, "acc", &acc));
+  B3D_TRY(flat_f32(dice_, "dice", &dice));
+  B3D_REQUIRE(acc.numel == (long long)W * C * 3 && dice.numel == 2, B3D_ERR_SHAPE, "dice: workspace sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  B3D_TRY(cuda_ok(cudaMemsetAsync(sums.p, 0, sizeof(double) * sums.numel, s), "memset sums"));
+  B3D_TRY(cuda_ok(cudaMemsetAsync(acc.p, 0, sizeof(float) * acc.numel, s), "memset acc"));
+  const long long nrows = yp.numel / ((long long)W * C);
+  const int QW = W / 4, rpb = 256 >= QW ? 256 / QW : 1;
+  long long want = (nrows + rpb - 1) / rpb;                    // one row group per CTA at most
+  if (want > 2LL * sm_count()) want = 2LL * sm_count();        // every CTA ends in W*C*3 + 3C+2 global atomics
+  const unsigned grid = (unsigned)(want < 1 ? 1 : want);
+  const size_t smem = sizeof(float) * W * C * 3;
+  DISPATCH_C(C, (loss_dice_fwd_kernel<kC><<<grid, 256, smem, s>>>(
+                    (const float*)yp.p, (const float*)y.p, nrows, W, vae ? (const float*)x.p : nullptr,
+                    vae ? (const float*)yv.p : nullptr, vae ? x.numel : 0, vae ? (const float*)mu.p : nullptr,
+                    vae ? (const float*)lv.p : nullptr, vae ? (int)mu.numel : 0, (double*)sums.p, (float*)acc.p)));
+  B3D_LAUNCH_CHECK("loss_dice_fwd");
+  loss_finalize_kernel<<<1, 32, 0, s>>>((const double*)sums.p, (float*)out.p, C, vae ? 1.0 / (double)x.numel : 0.0,
+                                        vae ? 1.0 / (double)mu.numel : 0.0, vae ? 1 : 0);
+  B3D_LAUNCH_CHECK("loss_finalize");
+  dice_finalize_kernel<<<1, 32, 0, s>>>((const float*)acc.p, (float*)dice.p, W, C, reduce_w);
+  B3D_LAUNCH_CHECK("dice_finalize");
+  return B3D_OK;
+}
+
 static int loss_bwd_impl(const DLTensor* x_, const DLTensor* y_, const DLTensor* ypred_, const DLTensor* yvae_,
                          const DLTensor* zmean_, const DLTensor* zlogvar_, const DLTensor* sums_,
                          const DLTensor* gout_, DLTensor* dypred_, DLTensor* dyvae_, DLTensor* dzmean_,
@@ -802,6 +957,37 @@ extern "C" int b3d_axpy(const DLTensor* flat_, DLTensor* grad_, long long n, flo
   if (gout_) { B3D_TRY(flat_f32(gout_, "gout", &go)); gp = (const float*)go.p; }
   axpy_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const float*)f.p, (float*)g.p, n, coef, gp);
   B3D_LAUNCH_CHECK("axpy");
+  return B3D_OK;
+}
+
+// out[0] = sum(v[0..n)) (+ addend[0]): tf.reduce_sum(model.losses) added to the data loss (train.py:146) — one warp-shuffle
+// block instead of torch's stack + sum + add
+__global__ void __launch_bounds__(256) sum_add_kernel(const float* __restrict__ v, long long n,
+                                                       const float* __restrict__ addend, float* __restrict__ out) {
+  __shared__ double red[32];
+  double a[1] = {0.0};
+  for (long long i = threadIdx.x; i < n; i += 256) a[0] += (double)v[i];
+  block_sum<1, double>(a, red);
+  if (threadIdx.x == 0) out[0] = (float)(a[0] + (addend != nullptr ? (double)addend[0] : 0.0));
+}
+
+extern "C" int b3d_sum_add(const DLTensor* v_, const DLTensor* addend_, DLTensor* out_, void* stream) {
+  TView v, a, o;
+  B3D_TRY(flat_f32(v_, "v", &v));
+  B3D_TRY(flat_f32(out_, "out", &o));
+  B3D_REQUIRE(o.numel == 1, B3D_ERR_SHAPE, "sum_add: out must hold one float");
+  const float* ap = nullptr;
+  if (addend_) { B3D_TRY(flat_f32(addend_, "addend", &a)); B3D_REQUIRE(a.numel == 1, B3D_ERR_SHAPE, "sum_add: addend must hold one float"); ap = (const float*)a.p; }
+  sum_add_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const float*)v.p, v.numel, ap, (float*)o.p);
+  B3D_LAUNCH_CHECK("sum_add");
+  return B3D_OK;
+}
+
+// zero a contiguous fp32 tensor with a memset node (the flat gradient buffer at the start of backward)
+extern "C" int b3d_zero(DLTensor* t_, void* stream) {
+  TView t;
+  B3D_TRY(flat_f32(t_, "t", &t));
+  B3D_TRY(cuda_ok(cudaMemsetAsync(t.p, 0, sizeof(float) * t.numel, (cudaStream_t)stream), "memset"));
   return B3D_OK;
 }
 

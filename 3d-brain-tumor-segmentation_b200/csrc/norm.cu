@@ -411,10 +411,7 @@ __global__ void __launch_bounds__(kThreads)
     for (int k = 0; k < kIter16; ++k) {
       const long long e = e0 + (long long)k * (kThreads * kCell);
       if (e < gm.L) {
-        const float4 a = ld_stream(reinterpret_cast<const float4*>(x + off + e));
-        const float4 c = ld_stream(reinterpret_cast<const float4*>(x + off + e) + 1);
-        in[k][0] = a.x; in[k][1] = a.y; in[k][2] = a.z; in[k][3] = a.w;
-        in[k][4] = c.x; in[k][5] = c.y; in[k][6] = c.z; in[k][7] = c.w;
+        ld8(x + off + e, in[k]);
       }
     }
 #pragma unroll
@@ -427,10 +424,7 @@ __global__ void __launch_bounds__(kThreads)
           const float t = fmaf(in[k][i] - mean, sc[i], sh[i]);
           o[i] = RELU ? fmaxf(t, 0.f) : t;
         }
-        if (y != nullptr) {
-          st_stream(reinterpret_cast<float4*>(y + off + e), make_float4(o[0], o[1], o[2], o[3]));
-          st_stream(reinterpret_cast<float4*>(y + off + e) + 1, make_float4(o[4], o[5], o[6], o[7]));
-        }
+        if (y != nullptr) st8(y + off + e, o);
         cell_store(tw, pos, o);
       }
       if (k < kIter16 - 1) cell_step(tw, pos, pos.dr1, pos.dw1);
@@ -480,14 +474,8 @@ __global__ void __launch_bounds__(kThreads)
     for (int k = 0; k < KI; ++k) {
       const long long e = e0 + (long long)k * (kThreads * kCell);
       if (e < gm.L) {
-        const float4 d0 = ld_stream(reinterpret_cast<const float4*>(dy + off + e));
-        const float4 d1 = ld_stream(reinterpret_cast<const float4*>(dy + off + e) + 1);
-        const float4 x0 = ld_stream(reinterpret_cast<const float4*>(x + off + e));
-        const float4 x1 = ld_stream(reinterpret_cast<const float4*>(x + off + e) + 1);
-        dv[k][0] = d0.x; dv[k][1] = d0.y; dv[k][2] = d0.z; dv[k][3] = d0.w;
-        dv[k][4] = d1.x; dv[k][5] = d1.y; dv[k][6] = d1.z; dv[k][7] = d1.w;
-        xv[k][0] = x0.x; xv[k][1] = x0.y; xv[k][2] = x0.z; xv[k][3] = x0.w;
-        xv[k][4] = x1.x; xv[k][5] = x1.y; xv[k][6] = x1.z; xv[k][7] = x1.w;
+        ld8(dy + off + e, dv[k]);
+        ld8(x + off + e, xv[k]);
       }
     }
 #pragma unroll
@@ -503,10 +491,7 @@ __global__ void __launch_bounds__(kThreads)
           o[i] = rstd * (gq * ga[i] - m1 - xh * m2);
           db[i] += o[i];
         }
-        if (dx != nullptr) {
-          st_stream(reinterpret_cast<float4*>(dx + off + e), make_float4(o[0], o[1], o[2], o[3]));
-          st_stream(reinterpret_cast<float4*>(dx + off + e) + 1, make_float4(o[4], o[5], o[6], o[7]));
-        }
+        if (dx != nullptr) st8(dx + off + e, o);
         cell_store(tw, pos, o);
       }
       if (k < KI - 1) cell_step(tw, pos, pos.dr1, pos.dw1);
@@ -547,7 +532,7 @@ __global__ void __launch_bounds__(kThreads)
   chunk_moments(stats, chunk, 1.0 / (double)gm.L, eps, mean, rstd);
   const long long off = (long long)chunk * gm.L;
   const long long goff = (long long)g * gm.L;
-  constexpr int KI = 2;               // cells per thread and pass (4 x 128-bit loads each)
+  constexpr int KI = 4;               // cells per thread and pass (4 x 128-bit loads each): 256 B in flight per thread
   const long long pass = (long long)gridDim.x * (KI * kThreads * kCell);
   long long e0 = ((long long)blockIdx.x * (KI * kThreads) + threadIdx.x) * kCell;
   const int c_first = (int)((goff + e0) % gm.cg);
@@ -568,14 +553,8 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
       for (int i = 0; i < 8; ++i) dv[k][i] = 0.f, xv[k][i] = mean;
       if (e < gm.L) {
-        const float4 d0 = ld_stream(reinterpret_cast<const float4*>(dy + off + e));
-        const float4 d1 = ld_stream(reinterpret_cast<const float4*>(dy + off + e) + 1);
-        const float4 x0 = ld_stream(reinterpret_cast<const float4*>(x + off + e));
-        const float4 x1 = ld_stream(reinterpret_cast<const float4*>(x + off + e) + 1);
-        dv[k][0] = d0.x; dv[k][1] = d0.y; dv[k][2] = d0.z; dv[k][3] = d0.w;
-        dv[k][4] = d1.x; dv[k][5] = d1.y; dv[k][6] = d1.z; dv[k][7] = d1.w;
-        xv[k][0] = x0.x; xv[k][1] = x0.y; xv[k][2] = x0.z; xv[k][3] = x0.w;
-        xv[k][4] = x1.x; xv[k][5] = x1.y; xv[k][6] = x1.z; xv[k][7] = x1.w;
+        ld8(dy + off + e, dv[k]);
+        ld8(x + off + e, xv[k]);
       }
     }
 #pragma unroll

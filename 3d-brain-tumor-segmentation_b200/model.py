@@ -93,7 +93,7 @@ class FlatParams:
         self.folds = []                # (kernel, folded kernel, F) of the dense-connection convs (ops.FoldDupFn)
 
     def zero_grad(self):
-        self.grad.zero_()
+        ops._call("b3d_zero", self.grad)           # a memset node under graph capture, not a fill kernel
 
     def notify(self, tensor):
         """A backward kernel has written `tensor`'s gradient straight into the flat buffer (ops.direct_param_grads):
@@ -114,6 +114,15 @@ class FlatParams:
         for v in self.order:
             off, n = self.spans[id(v.tensor)]
             v.tensor.grad = self.grad[off:off + n].view(v.tensor.shape)
+
+
+class _LossList(list):
+    """model.losses: the per-tensor penalties as a list (Keras), remembering the vector they are views of so that
+    train.reduce_sum can add them up with one kernel."""
+
+    def __init__(self, vec):
+        super().__init__(vec.unbind(0))
+        self.vector = vec
 
 
 class _L2LossesFn(torch.autograd.Function):
@@ -212,7 +221,7 @@ class Model(Layer):
         """L2 penalties of all regularised tensors (168 for the default model; train.py:146 sums them)."""
         flat = self.flatten_parameters()
         out = _L2LossesFn.apply(flat, *flat.reg_tensors)
-        return list(out.unbind(0))
+        return _LossList(out)
 
     # ---- weight exchange by this repo's structural names (oracle.ref_model.param_shapes)
     def named_variables(self):

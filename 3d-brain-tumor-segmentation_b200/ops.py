@@ -1002,8 +1002,16 @@ class DiceVAELossFn(Function):
         x, y, y_pred, y_vae, z_mean, z_logvar = map(c, (x, y, y_pred, y_vae, z_mean, z_logvar))
         sums = _new((3 * C + 2,), y_pred, torch.float64)
         out = _new((4,), y_pred)
-        _call("b3d_loss_fwd", x if vae else None, y, y_pred, y_vae, z_mean if vae else None,
-              z_logvar if vae else None, sums, out)
+        _LAST_DICE["v"] = None
+        if y_pred.dim() == 5 and y_pred.shape[3] % 4 == 0:
+            # the hard-Dice metric of the same (y, y_pred) comes out of the same pass (picked up by dice_coefficient)
+            acc, dice = _new((y_pred.shape[3] * C * 3,), y_pred), _new((2,), y_pred)
+            _call("b3d_loss_dice_fwd", x if vae else None, y, y_pred, y_vae, z_mean if vae else None,
+                  z_logvar if vae else None, sums, out, acc, dice, 0)
+            _LAST_DICE["v"] = dice
+        else:
+            _call("b3d_loss_fwd", x if vae else None, y, y_pred, y_vae, z_mean if vae else None,
+                  z_logvar if vae else None, sums, out)
         ctx.replicas = 1
         if dp is not None and dp[1] > 1:
             import torch.distributed as dist
@@ -1032,13 +1040,25 @@ class DiceVAELossFn(Function):
         return None, None, dyp, dyv, dmu, dlv, None
 
 
+_LAST_DICE = {"v": None}       # (macro, micro) left by DiceVAELossFn.forward for its wrapper
+
+
 def dice_vae_loss(x, y, y_pred, y_vae=None, z_mean=None, z_logvar=None, dp=None):
-    return DiceVAELossFn.apply(x, y, y_pred, y_vae, z_mean, z_logvar, dp)
+    loss = DiceVAELossFn.apply(x, y, y_pred, y_vae, z_mean, z_logvar, dp)
+    dice, _LAST_DICE["v"] = _LAST_DICE["v"], None
+    if dice is not None and y.is_contiguous() and y_pred.is_contiguous():
+        import weakref
+        # the metric of exactly these tensors, for a following dice_coefficient(y, y_pred) (train.py:143,147)
+        y_pred._b3d_dice = (weakref.ref(y), y._version, y_pred._version, dice)
+    return loss
 
 
 def dice_coefficient(y_true, y_pred, reduce_w=False):
     """util.py:35-57 -> (macro, micro) as 0-d tensors (no gradient).  reduce_w: the channels_first macro average."""
     _check(y_pred, "y_pred")
+    c = getattr(y_pred, "_b3d_dice", None)
+    if c is not None and not reduce_w and c[0]() is y_true and c[1] == y_true._version and c[2] == y_pred._version:
+        return c[3][0], c[3][1]                # computed by the loss kernel's pass over the same tensors
     y_true, y_pred = y_true.contiguous(), y_pred.detach().contiguous()
     W, C = y_pred.shape[3], y_pred.shape[4]
     acc = _new((W * C * 3,), y_pred)

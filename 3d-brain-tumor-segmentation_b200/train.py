@@ -52,9 +52,29 @@ class GradientTape:
         return [v.grad for v in variables]
 
 
-def reduce_sum(xs):
-    """tf.reduce_sum over a list of scalars (train.py:146)."""
-    return torch.stack(list(xs)).sum() if len(xs) else 0.0
+class _SumAddFn(torch.autograd.Function):
+    """sum(vec) (+ addend) by one kernel; differentiable (d/dvec = gout broadcast, d/daddend = gout)."""
+
+    @staticmethod
+    def forward(ctx, vec, addend):
+        out = torch.empty((), device=vec.device, dtype=torch.float32)
+        ops._call("b3d_sum_add", vec.contiguous(), None if addend is None else addend.reshape(1), out.reshape(1))
+        ctx.n = vec.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.expand(ctx.n), (g if ctx.needs_input_grad[1] else None)
+
+
+def reduce_sum(xs, addend=None):
+    """tf.reduce_sum over a list of scalars (train.py:146), optionally + `addend` (the data loss).  `model.losses`
+    remembers the vector its entries are views of, which makes this one kernel."""
+    vec = getattr(xs, "vector", None)
+    if vec is None:
+        s = torch.stack(list(xs)).sum() if len(xs) else 0.0
+        return s if addend is None else addend + s
+    return _SumAddFn.apply(vec, addend)
 
 
 def train_step(model: Model, optimizer: ScheduledOptim, loss_fn: DiceVAELoss, dice_fn: DiceCoefficient, x, y,
@@ -68,8 +88,8 @@ def train_step(model: Model, optimizer: ScheduledOptim, loss_fn: DiceVAELoss, di
         y_pred, y_vae, z_mean, z_logvar = model(x, training=True, inference=False,
                                                 dropout_mask=dropout_mask, eps=eps)
         data_loss = loss_fn(x, y, y_pred, y_vae, z_mean, z_logvar)
-        reg = reduce_sum(model.losses)
-        loss = data_loss + reg.detach()
+        with torch.no_grad():      # reported loss only: the regulariser's gradient is applied as one axpy below
+            loss = reduce_sum(model.losses, addend=data_loss)
     macro_dice, micro_dice = dice_fn(y, y_pred)
     variables = model.trainable_variables
     if dp is not None:

@@ -190,6 +190,11 @@ int b3d_loss_bwd_dp(const DLTensor* x, const DLTensor* y, const DLTensor* y_pred
                     const DLTensor* z_mean, const DLTensor* z_logvar, const DLTensor* sums, const DLTensor* gout,
                     DLTensor* dy_pred, DLTensor* dy_vae, DLTensor* dz_mean, DLTensor* dz_logvar, int replicas,
                     void* stream);
+/* b3d_loss_fwd + b3d_dice_coeff of the same (y, y_pred) in ONE pass over them: the training loop evaluates both on the
+ * same tensors (/root/reference/train.py:143,147; util.py:13-24, 35-57).  5-D NDHWC y / y_pred with W % 4 == 0. */
+int b3d_loss_dice_fwd(const DLTensor* x, const DLTensor* y, const DLTensor* y_pred, const DLTensor* y_vae,
+                      const DLTensor* z_mean, const DLTensor* z_logvar, DLTensor* sums, DLTensor* out,
+                      DLTensor* acc /*fp32 [W*C*3]*/, DLTensor* dice /*fp32 [2]*/, int reduce_w, void* stream);
 int b3d_dice_coeff(const DLTensor* y, const DLTensor* y_pred, DLTensor* acc /*fp32 [W*C*3]*/,
                    DLTensor* out /*fp32 [2] macro, micro*/, int reduce_w /*1: channels_first macro (util.py:36)*/,
                    void* stream);
@@ -204,6 +209,10 @@ int b3d_l2_losses(const DLTensor* flat, const DLTensor* offsets /*int64 [n+1]*/,
 int b3d_l2_grad(const DLTensor* flat, DLTensor* grad, const DLTensor* offsets, const DLTensor* gout, float coef,
                 void* stream);
 int b3d_axpy(const DLTensor* flat, DLTensor* grad, long long n, float coef, const DLTensor* gout, void* stream);
+/* out[0] = sum(v) + addend[0] (addend nullable): tf.reduce_sum(model.losses) added to the data loss,
+ * /root/reference/train.py:146.  b3d_zero: cudaMemsetAsync of a contiguous fp32 tensor. */
+int b3d_sum_add(const DLTensor* v, const DLTensor* addend /*nullable*/, DLTensor* out, void* stream);
+int b3d_zero(DLTensor* t, void* stream);
 
 /* ---- input Dropout (encoder.py:39,71), concat materialisation, small elementwise helpers --------*/
 int b3d_dropout(const DLTensor* x, DLTensor* y, DLTensor* mask /*nullable*/, float rate, unsigned long long seed,

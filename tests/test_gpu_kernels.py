@@ -229,6 +229,38 @@ def test_loss_and_dice(b3d, dev):
         assert abs(float(macro) - float(mr)) < 1e-5 and abs(float(micro) - float(ur)) < 1e-5
 
 
+def test_fused_loss_and_dice_pass(b3d, dev):
+    """DiceVAELoss followed by DiceCoefficient on the SAME tensors (train.py:143,147): the metric comes out of the loss
+    kernel's pass (b3d_loss_dice_fwd); it must equal the oracle and the stand-alone metric kernel, and a changed
+    y_pred must not pick up the stale result."""
+    ops = b3d.ops
+    for C, shape in ((3, (2, 6, 5, 8)), (1, (1, 4, 4, 12)), (3, (1, 16, 16, 16)), (2, (1, 3, 5, 260))):
+        x, yv = t64(*shape, 2, seed=1), t64(*shape, 2, seed=2)
+        yp = torch.sigmoid(t64(*shape, C, seed=3) * 2)
+        y = (t64(*shape, C, seed=4) > 0.8).double()
+        mu, lv = t64(shape[0], 64, seed=5), t64(shape[0], 64, seed=6) * 0.5
+        d = lambda t, g=False: dev32(t, dev, g)
+        yd, ypd = d(y), d(yp, True)
+        n0 = ops.LAUNCHES["n"]
+        l = b3d.DiceVAELoss()(d(x), yd, ypd, d(yv), d(mu), d(lv))
+        n1 = ops.LAUNCHES["n"]
+        macro, micro = b3d.DiceCoefficient()(yd, ypd)
+        assert ops.LAUNCHES["n"] == n1, "the metric of the same tensors must not launch anything"
+        assert n1 - n0 == 1
+        lr_ = R.dice_vae_loss(x, y, yp, yv, mu, lv)
+        mr, ur = R.dice_coefficient(y, yp)
+        assert abs(float(l) - float(lr_)) / abs(float(lr_)) < 1e-5
+        assert abs(float(macro) - float(mr)) < 1e-5 and abs(float(micro) - float(ur)) < 1e-5
+        m2, u2 = b3d.DiceCoefficient()(yd.clone(), ypd.detach().clone())        # other objects: stand-alone kernel
+        assert ops.LAUNCHES["n"] == n1 + 1
+        assert abs(float(m2) - float(macro)) < 1e-6 and abs(float(u2) - float(micro)) < 1e-6
+        with torch.no_grad():
+            ypd.mul_(0.5)                                                        # version bump: cached metric is stale
+        m3, u3 = b3d.DiceCoefficient()(yd, ypd)
+        mr3, ur3 = R.dice_coefficient(y, yp * 0.5)
+        assert abs(float(m3) - float(mr3)) < 1e-5 and abs(float(u3) - float(ur3)) < 1e-5
+
+
 def test_dense_and_sample(b3d, dev):
     for B, K, N, act in ((1, 4096, 128, 0), (2, 64, 512, 1), (3, 37, 5, 1)):
         x, w, b = t64(B, K, seed=1), t64(K, N, seed=2, scale=0.1), t64(N, seed=3)

@@ -116,6 +116,8 @@ report("loss_bwd 128^3", 4 * (3 * S * 3 + 3 * S * 2),
        lambda: ops._call("b3d_loss_bwd", xin, yt, yp, yv, mu, lv, sums, g1, dyp, dyv, dmu, dlv))
 acc, out2 = torch.empty(n * 3 * 3, device=dev), torch.empty(2, device=dev)
 report("dice_coeff 128^3", 4 * (2 * S * 3), lambda: ops._call("b3d_dice_coeff", yt, yp, acc, out2, 0))
+report("loss_fwd + dice_coeff in one pass 128^3", 4 * (2 * S * 3 + 2 * S * 2),
+       lambda: ops._call("b3d_loss_dice_fwd", xin, yt, yp, yv, mu, lv, sums, out4, acc, out2, 0))
 # Adam over the flat parameter buffer (10.6 M params; 28 B/param)
 P = 10_636_064
 th, m, v, g = (torch.randn(P, device=dev) * 0.01 for _ in range(4))
