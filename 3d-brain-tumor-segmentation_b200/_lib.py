@@ -120,6 +120,10 @@ SIGNATURES = {
     "b3d_upsample2_bwd": "TTv",
     "b3d_halo_exchange": "TTTTLLTTiLv",
     "b3d_peer_allreduce": "TTiTTiv",
+    "b3d_peer_allreduce2": "TTTiTTiv",
+    "b3d_conv3d_fwd_p16_slab": "TTTTTTTiiiiiTiLLTTiv",
+    "b3d_gn_apply_p16_slab": "TTTTTTifiLLv",
+    "b3d_block_epilogue_fwd_p16_slab": "TTTTTTTTTifiLLv",
     "b3d_epoch_tick": "Tv",
     "b3d_flip_normalize": "TTTTiv",
     "b3d_flip_accumulate": "TTTifiv",

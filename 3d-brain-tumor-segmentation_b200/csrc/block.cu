@@ -18,6 +18,9 @@ struct BlockGeom {
   int F, T, npl;      // channels, lanes per voxel, float4 per lane
   int G, cg;
   int vox_per_cta;    // voxels handled by one CTA
+  // depth-slab form (forward twin kernel only; batch 1): the tensors hold voxels [vshift, vshift + S_local) of the
+  // volume S / vpc describe.  S_local < 0: the tensors are the volume
+  long long vshift, S_local;
 };
 
 __device__ __forceinline__ float group_sum(float v, int T) {
@@ -394,11 +397,18 @@ __global__ void __launch_bounds__(kBT)
     ga8[i] = HAS_GN ? rstd * gamma[j] : 1.f;
     be8[i] = HAS_GN ? beta[j] : 0.f;
   }
-  const long long v0 = (long long)blockIdx.x * gm.vox_per_cta;
-  const long long vend = min(v0 + gm.vox_per_cta, gm.vpc);
-  const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
+  long long v_lo = 0, v_hi = gm.vpc, vshift = 0;
+  if (gm.S_local >= 0) {                                       // the part of this chunk inside the slab
+    vshift = gm.vshift;
+    v_lo = max(0LL, vshift - (long long)g * gm.vpc);
+    v_hi = min(gm.vpc, vshift + gm.S_local - (long long)g * gm.vpc);
+  }
+  const long long v0 = v_lo + (long long)blockIdx.x * gm.vox_per_cta;
+  const long long vend = min(v0 + gm.vox_per_cta, v_hi);
+  if (v0 >= vend) return;                                      // CTA-uniform
+  const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc) - vshift;
   const int iters = (int)((vend - v0 + vstep - 1) / vstep);   // CTA-uniform: whole warps stay in the shuffles
-  VoxPos pos = vox_pos(tw.W, (unsigned)((long long)g * gm.vpc + v0 + vl));
+  VoxPos pos = vox_pos(tw.W, (unsigned)((long long)g * gm.vpc + v0 + vl - vshift));
   for (int it = 0; it < iters; ++it) {
     const long long v = v0 + (long long)it * vstep + vl;
     const bool act = v < vend;
@@ -747,6 +757,7 @@ static int block_geom(const TView& res, int groups, bool has_gn, BlockGeom* gm, 
   while (T < 32 && q % (T * 2) == 0) T *= 2;
   B3D_REQUIRE(q / T <= kMaxNPL, B3D_ERR_UNSUPPORTED, "block epilogue: unsupported filter count %d", F);
   gm->S = S;
+  gm->vshift = 0; gm->S_local = -1;
   gm->vpc = S / G;
   gm->F = F;
   gm->T = T;
@@ -1046,6 +1057,54 @@ extern "C" int b3d_block_epilogue_fwd_p16(const DLTensor* res_, const DLTensor* 
         (float*)out.p, gm, eps, tw);
   }
   B3D_LAUNCH_CHECK("block_fwd16");
+  return B3D_OK;
+}
+
+// The same for one depth slab (slab.py): res / h2 / out16 hold voxels [vox_offset, vox_offset + D*H*W) of a volume of
+// total_vox voxels; `stats` = the all-reduced GroupNorm statistics of the whole volume's chunks, `chse` from the
+// all-reduced pooling sums.
+extern "C" int b3d_block_epilogue_fwd_p16_slab(const DLTensor* res_, const DLTensor* h2_, const DLTensor* stats_,
+                                               const DLTensor* gamma_, const DLTensor* beta_, const DLTensor* wsp_,
+                                               const DLTensor* chse_, DLTensor* out_, DLTensor* out16_, int groups,
+                                               float eps, int has_gn, long long vox_offset, long long total_vox,
+                                               void* stream) {
+  TView res, h2, out, st, ga, be, wsp, ch;
+  BlockGeom gm;
+  int nchunks;
+  B3D_TRY(view(res_, DT_F32, -1, false, "res", &res));
+  B3D_TRY(view(h2_, DT_F32, -1, false, "h2", &h2));
+  out.p = nullptr;
+  if (out_ != nullptr) {
+    B3D_TRY(view(out_, DT_F32, -1, false, "out", &out));
+    B3D_REQUIRE(res.numel == out.numel, B3D_ERR_SHAPE, "block epilogue: size mismatch");
+  }
+  B3D_REQUIRE(res.numel == h2.numel && out16_ != nullptr, B3D_ERR_SHAPE, "block epilogue (P16): sizes / twin required");
+  B3D_REQUIRE(res.ndim == 5 && res.shape[0] == 1, B3D_ERR_SHAPE, "block epilogue (slab): batch 1");
+  B3D_TRY(block_geom16(res, groups, has_gn != 0, &gm, &nchunks));
+  const long long S_local = gm.S;
+  B3D_REQUIRE(total_vox > 0 && vox_offset >= 0 && vox_offset + S_local <= total_vox && total_vox % gm.G == 0 &&
+                  total_vox < (1LL << 32), B3D_ERR_ARG, "block epilogue (slab): bad window (%lld + %lld of %lld)",
+              vox_offset, S_local, total_vox);
+  gm.S = total_vox; gm.vpc = total_vox / gm.G; gm.vshift = vox_offset; gm.S_local = S_local;
+  B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
+  B3D_TRY(vecF(chse_, gm.F, "chse", &ch));
+  Twin16 tw;
+  B3D_TRY(twin16(out16_, nullptr, res, &tw));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (has_gn) {
+    B3D_TRY(view(stats_, DT_F64, -1, false, "stats", &st));
+    B3D_REQUIRE(st.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats: wrong size");
+    B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
+    B3D_TRY(vecF(beta_, gm.F, "beta", &be));
+    block_fwd16_kernel<true><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+        (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+        (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps, tw);
+  } else {
+    block_fwd16_kernel<false><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+        (const float*)res.p, (const float*)h2.p, nullptr, nullptr, nullptr, (const float*)wsp.p, (const float*)ch.p,
+        (float*)out.p, gm, eps, tw);
+  }
+  B3D_LAUNCH_CHECK("block_fwd16 (slab)");
   return B3D_OK;
 }
 

@@ -47,26 +47,28 @@ void fill_out(ConvGeom& g, const TView& y) {
 
 int run(const ConvGeom& g, const TView& x, const TView& w, const float* bias, const TView& y,
         const DLTensor* stats_, int groups, const DLTensor* gap_, const DLTensor* wpacked_, cudaStream_t s,
-        const TcSources* srcs = nullptr) {
+        const TcSources* srcs = nullptr, bool prezeroed = false) {
+  // prezeroed: the caller hands in statistics / pooling buffers that are already zero (slices of an arena it clears
+  // once per forward) — no memset nodes here
   double* stats = nullptr;
   float* gap = nullptr;
   if (stats_ != nullptr) {
     TView st;
     B3D_TRY(view(stats_, DT_F64, -1, false, "gn_stats", &st));
-    const long long S = (long long)g.Do * g.Ho * g.Wo;
+    const long long S = g.stat_total > 0 ? g.stat_total : (long long)g.Do * g.Ho * g.Wo;
     B3D_REQUIRE(groups >= 1 && g.Cout % groups == 0 && S % groups == 0, B3D_ERR_UNSUPPORTED,
                 "conv: fused GN stats need Cout %% groups == 0 and D*H*W %% groups == 0");
     B3D_REQUIRE(st.numel == 2LL * g.B * groups, B3D_ERR_SHAPE, "gn_stats: expected %d fp64 values", 2 * g.B * groups);
     B3D_REQUIRE(y.pitch == g.Cout, B3D_ERR_LAYOUT, "conv: fused GN stats need a contiguous output");
     stats = (double*)st.p;
-    B3D_TRY(cuda_ok(cudaMemsetAsync(stats, 0, sizeof(double) * st.numel, s), "memset stats"));
+    if (!prezeroed) B3D_TRY(cuda_ok(cudaMemsetAsync(stats, 0, sizeof(double) * st.numel, s), "memset stats"));
   }
   if (gap_ != nullptr) {
     TView gp;
     B3D_TRY(view(gap_, DT_F32, 2, false, "gap", &gp));
     B3D_REQUIRE(gp.shape[0] == g.B && gp.shape[1] == g.Cout, B3D_ERR_SHAPE, "gap: expected [B, Cout]");
     gap = (float*)gp.p;
-    B3D_TRY(cuda_ok(cudaMemsetAsync(gap, 0, sizeof(float) * gp.numel, s), "memset gap"));
+    if (!prezeroed) B3D_TRY(cuda_ok(cudaMemsetAsync(gap, 0, sizeof(float) * gp.numel, s), "memset gap"));
   }
   if (wpacked_ != nullptr) {
     TView wp;
@@ -461,6 +463,44 @@ extern "C" int b3d_conv3d_fwd_p16(const DLTensor* x0_, const DLTensor* x1_, cons
   const float* bias;
   B3D_TRY(bias_ptr(bias_, g.Cout, &bias));
   return run(g, x, w, bias, y, gn_stats_, groups, gap_, wpacked_, (cudaStream_t)stream, &src);
+}
+
+// The same for one depth slab of a volume (slab.py): the sources carry `halo_before` / `halo_after` extra depth slices
+// (the neighbours' boundary slices, received in place), the output holds this slab's slices only, and the fused
+// GroupNorm statistics are this slab's PARTIAL sums over the chunks of the whole volume (stat_total output voxels, of
+// which this slab's first is stat_off) — the caller all-reduces them.
+extern "C" int b3d_conv3d_fwd_p16_slab(const DLTensor* x0_, const DLTensor* x1_, const DLTensor* x2_,
+                                       const DLTensor* x3_, const DLTensor* w_, const DLTensor* bias_, DLTensor* y_,
+                                       int stride, int transposed, int act, int halo_before, int halo_after,
+                                       DLTensor* gn_stats_, int groups, long long stat_off, long long stat_total,
+                                       DLTensor* gap_, const DLTensor* wpacked_, int prezeroed, void* stream) {
+  const DLTensor* xs[4] = {x0_, x1_, x2_, x3_};
+  TcSources src;
+  P16View first;
+  int ctot;
+  B3D_TRY(p16_sources(xs, &src, &first, &ctot));
+  TView w, y;
+  int k;
+  B3D_TRY(view(y_, DT_F32, 5, true, "y", &y));
+  B3D_TRY(weight_view(w_, &w, &k));
+  B3D_REQUIRE(stride == 1 || (stride == 2 && k == 3), B3D_ERR_UNSUPPORTED, "conv: stride must be 1, or 2 with k=3");
+  B3D_REQUIRE(!transposed || stride == 2, B3D_ERR_UNSUPPORTED, "conv-transpose: only k=3 stride=2");
+  B3D_REQUIRE(wpacked_ != nullptr, B3D_ERR_ARG, "conv (P16): packed weights required (tcgen05 path only)");
+  B3D_REQUIRE(halo_before >= 0 && halo_after >= 0 && halo_before <= 1 && halo_after <= 1 && first.B == 1, B3D_ERR_ARG,
+              "conv: slab halos are 0 or 1 slice per side, batch 1");
+  const TView x = virtual_view(first, ctot);
+  ConvGeom g;
+  B3D_TRY(geom_fwd(g, x, w, y, k, stride, transposed, halo_before, halo_after));
+  g.act = act; g.groups = groups;
+  if (gn_stats_ != nullptr) {
+    const long long S = (long long)g.Do * g.Ho * g.Wo;
+    B3D_REQUIRE(stat_total > 0 && stat_off >= 0 && stat_off + S <= stat_total, B3D_ERR_ARG,
+                "conv (slab): bad statistics window (%lld + %lld of %lld)", stat_off, S, stat_total);
+    g.stat_off = stat_off; g.stat_total = stat_total;
+  }
+  const float* bias;
+  B3D_TRY(bias_ptr(bias_, g.Cout, &bias));
+  return run(g, x, w, bias, y, gn_stats_, groups, gap_, wpacked_, (cudaStream_t)stream, &src, prezeroed != 0);
 }
 
 extern "C" int b3d_conv3d_dgrad_p16(const DLTensor* dy_, const DLTensor* w_, DLTensor* dx_, int stride, int transposed,

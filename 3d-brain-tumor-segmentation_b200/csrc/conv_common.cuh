@@ -19,6 +19,9 @@ struct ConvGeom {
   int groups;               // GN groups when stats are requested
   int bwd;                  // 1 = backward pass (operand-precision choice of the tcgen05 path)
   int doff;                 // slab halos: logical input depth slice i lives at buffer slice i + doff (of Di)
+  // depth-slab inference with fused GroupNorm statistics: the output tensor is voxels [stat_off, stat_off + Do*Ho*Wo) of
+  // a volume of stat_total voxels whose 1/groups chunks the statistics are taken over (0 / 0: the tensor is the volume)
+  long long stat_off, stat_total;
 };
 
 // outer-product form:  dw[t][a][b] = sum_{n,o} big[n, s*o+t-pad, a] * small[n, o, b]

@@ -90,6 +90,7 @@ struct TcParams {
   int ntd, nth, ntw, ntiles;
   int accumulate, groups;
   long long vpc;       // voxels per GN chunk (of the tensor y is stored as)
+  long long voff;      // first voxel of y inside the whole volume (depth slabs; 0 otherwise)
   // stride-2 family (conv_s2.cu): the kernel works on the COARSE grid [D,H,W];
   //   s2d: x is the fine tensor [B,2D,2H,2W,Csub]; virtual input channel k' = parity*Csub + c  (space-to-depth)
   //   d2s: y is the fine tensor [B,2D,2H,2W,Csub]; virtual output column n' = parity*Csub + c (depth-to-space)
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
           if (prm.stats != nullptr) {
             // the GroupNorm chunk of this patch's voxels; when any lane moves on to another chunk the whole warp
             // flushes its running sums (warp-reduced: two fp64 atomics per warp, not per lane)
-            const int chunk = valid ? b * prm.groups + (int)(vox / prm.vpc) : cur_chunk;
+            const int chunk = valid ? b * prm.groups + (int)((vox + prm.voff) / prm.vpc) : cur_chunk;
             if (__any_sync(0xffffffffu, chunk != cur_chunk && cur_chunk >= 0)) {
               flush_stats(prm.stats, cur_chunk, s0, s1, lane);
               cur_chunk = -1; s0 = 0.f; s1 = 0.f;
@@ -713,17 +714,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
 __global__ void __launch_bounds__(256)
     conv_finish_kernel(float* __restrict__ y, const float* __restrict__ ws, int ksplit, long long ws_slice,
                        const float* __restrict__ bias, double* __restrict__ stats, float* __restrict__ gap,
-                       long long L, int C, int G) {
+                       long long L, int C, int G, long long shift, long long n_local) {
   extern __shared__ float sgap[];                  // [C]
   __shared__ double red[64];
   const int b = blockIdx.x / G, g = blockIdx.x % G;
+  // depth-slab form (n_local >= 0, batch 1): y holds the elements [shift, shift + n_local) of the volume whose chunks
+  // (G, L) describe; a CTA covers the part of its chunk's segment that lies inside
+  long long e_lo = 0, e_hi = L, sh = 0;
+  if (n_local >= 0) {
+    sh = shift;
+    e_lo = max(0LL, shift - (long long)g * L);
+    e_hi = min(L, shift + n_local - (long long)g * L);
+  }
+  const long long seg0 = e_lo + (long long)blockIdx.y * 8192, seg1 = min(e_hi, seg0 + 8192);
+  if (seg0 >= seg1) return;                        // CTA-uniform
   for (int i = threadIdx.x; i < C; i += 256) sgap[i] = 0.f;
   __syncthreads();
-  const long long off = ((long long)b * G + g) * L;
+  const long long off = ((long long)b * G + g) * L - sh;
   float* yc = y + off;
   const long long e0 = (long long)g * L;           // element offset inside the sample (channel = (e0 + e) % C)
   double d[2] = {0.0, 0.0};
-  const long long seg0 = (long long)blockIdx.y * 8192, seg1 = min(L, seg0 + 8192);
   for (long long e = seg0 + threadIdx.x * 4LL; e < seg1; e += 256 * 4) {
     float4 v = ld_stream(reinterpret_cast<const float4*>(ws + off + e));
     for (int z = 1; z < ksplit; ++z) {
@@ -1035,7 +1045,8 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   p.ntd = (q.D + C::TD - 1) / C::TD; p.nth = (q.H + C::TH - 1) / C::TH; p.ntw = (q.W + C::TW - 1) / C::TW;
   p.ntiles = g.B * p.ntd * p.nth * p.ntw;
   p.accumulate = g.accumulate; p.groups = g.groups > 0 ? g.groups : 1;
-  p.vpc = ((long long)g.Do * g.Ho * g.Wo) / p.groups;
+  p.vpc = (g.stat_total > 0 ? g.stat_total : (long long)g.Do * g.Ho * g.Wo) / p.groups;
+  p.voff = g.stat_total > 0 ? g.stat_off : 0;
   p.s2d = q.s2d; p.d2s = q.d2s; p.Csub = q.Csub;
   p.Din = g.Di; p.doff = g.doff;
   p.cin_real = g.mode == CONV_S1 ? g.Cin : q.Cin; p.cout_real = g.mode == CONV_UP ? q.Cout : g.Cout; p.act = g.act;
@@ -1058,7 +1069,8 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   const int ctas = (int)(grid.x * grid.y);
   float* ws = nullptr;
   if (ctas * 2 <= sm_count() && nchunks >= 8 && g.act == 0 && !g.accumulate && g.Cout % 16 == 0 && g.yp == g.Cout &&
-      (S * g.Cout) % 32 == 0 && (stats == nullptr || p.groups == 8 || S % p.groups == 0)) {
+      (S * g.Cout) % 32 == 0 && (stats == nullptr || p.groups == 8 || S % p.groups == 0) &&
+      (stats == nullptr || g.stat_total == 0 || (g.B == 1 && (g.stat_total * g.Cout) % (4LL * p.groups) == 0))) {
     int ks = sm_count() / ctas;
     if (ks > nchunks / 4) ks = nchunks / 4;
     if (ks > 8) ks = 8;
@@ -1077,9 +1089,12 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   B3D_LAUNCH_CHECK("conv_tc");
   if (p.ksplit > 1) {
     const int G = stats != nullptr ? (g.groups > 0 ? g.groups : 1) : 8;
-    const long long L = S * g.Cout / G;
-    conv_finish_kernel<<<dim3(g.B * G, (unsigned)((L + 8191) / 8192)), 256, sizeof(float) * g.Cout, s>>>(
-        y, ws, p.ksplit, out_elems, bias, stats, gap, L, g.Cout, G);
+    const bool slab = stats != nullptr && g.stat_total > 0;       // chunks of the whole volume, window of this slab
+    const long long L = (slab ? g.stat_total : S) * g.Cout / G;
+    const long long span = slab && out_elems < L ? out_elems : L;  // longest part of a chunk a CTA row can hold
+    conv_finish_kernel<<<dim3(g.B * G, (unsigned)((span + 8191) / 8192)), 256, sizeof(float) * g.Cout, s>>>(
+        y, ws, p.ksplit, out_elems, bias, stats, gap, L, g.Cout, G, slab ? g.stat_off * g.Cout : 0,
+        slab ? out_elems : -1);
     B3D_LAUNCH_CHECK("conv_finish");
   }
   return B3D_OK;

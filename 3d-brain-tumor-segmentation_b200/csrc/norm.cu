@@ -383,15 +383,26 @@ __device__ __forceinline__ void cell_store(const Twin16& o, const CellPos& k, co
 template <bool RELU>
 __global__ void __launch_bounds__(kThreads)
     gn_apply16_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
-                      const float* __restrict__ beta, float* __restrict__ y, ChunkGeom gm, float eps, Twin16 tw) {
+                      const float* __restrict__ beta, float* __restrict__ y, ChunkGeom gm, float eps, Twin16 tw,
+                      long long shift, long long n_local) {
+  // depth-slab form (n_local >= 0; batch 1): x / y / the twin hold the flat elements [shift, shift + n_local) of the
+  // volume whose chunks gm describes; a CTA covers the part of its chunk that lies inside
   const int chunk = blockIdx.y, g = chunk % gm.G, b = chunk / gm.G;
+  long long e_lo = 0, e_hi = gm.L;
+  if (n_local >= 0) {
+    e_lo = max(0LL, shift - (long long)chunk * gm.L);
+    e_hi = min(gm.L, shift + n_local - (long long)chunk * gm.L);
+    if (e_lo >= e_hi) return;
+  } else {
+    shift = 0;
+  }
   float mean, rstd;
   chunk_moments(stats, chunk, 1.0 / (double)gm.L, eps, mean, rstd);
-  const long long off = (long long)chunk * gm.L;
+  const long long off = (long long)chunk * gm.L - shift;
   const long long goff = (long long)g * gm.L;
   // a pass of the grid covers gridDim.x * kIter16 * kThreads cells; a thread's k-th cell of a pass is kThreads cells on
   const long long pass = (long long)gridDim.x * (kIter16 * kThreads * kCell);
-  long long e0 = ((long long)blockIdx.x * (kIter16 * kThreads) + threadIdx.x) * kCell;
+  long long e0 = e_lo + ((long long)blockIdx.x * (kIter16 * kThreads) + threadIdx.x) * kCell;
   // affine constants of this thread's 8 channels (invariant: all strides are multiples of cg)
   float sc[8], sh[8];
   {
@@ -403,21 +414,21 @@ __global__ void __launch_bounds__(kThreads)
       sh[i] = __ldg(beta + j);
     }
   }
-  CellPos pos = cell_pos(tw, (unsigned)b, (unsigned long long)(goff + e0), kThreads,
+  CellPos pos = cell_pos(tw, (unsigned)b, (unsigned long long)(goff + e0 - shift), kThreads,
                          (unsigned long long)(pass / kCell) - (kIter16 - 1) * kThreads);
-  for (; e0 < gm.L; e0 += pass) {
+  for (; e0 < e_hi; e0 += pass) {
     float in[kIter16][8];
 #pragma unroll
     for (int k = 0; k < kIter16; ++k) {
       const long long e = e0 + (long long)k * (kThreads * kCell);
-      if (e < gm.L) {
+      if (e < e_hi) {
         ld8(x + off + e, in[k]);
       }
     }
 #pragma unroll
     for (int k = 0; k < kIter16; ++k) {
       const long long e = e0 + (long long)k * (kThreads * kCell);
-      if (e < gm.L) {
+      if (e < e_hi) {
         float o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -930,11 +941,46 @@ extern "C" int b3d_gn_apply_p16(const DLTensor* x_, const DLTensor* stats_, cons
   cudaStream_t s = (cudaStream_t)stream;
   if (relu)
     gn_apply16_kernel<true><<<gn_grid16(gm, nchunks), kThreads, 0, s>>>(
-        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw);
+        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw, 0, -1);
   else
     gn_apply16_kernel<false><<<gn_grid16(gm, nchunks), kThreads, 0, s>>>(
-        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw);
+        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw, 0, -1);
   B3D_LAUNCH_CHECK("gn_apply16");
+  return B3D_OK;
+}
+
+// The same for one depth slab (slab.py): x / y / y16 hold the flat elements [elem_offset, elem_offset + numel) of a
+// volume of total_elems elements per sample, `stats` the (all-reduced) chunk statistics of the WHOLE volume.
+extern "C" int b3d_gn_apply_p16_slab(const DLTensor* x_, const DLTensor* stats_, const DLTensor* gamma_,
+                                     const DLTensor* beta_, DLTensor* y_, DLTensor* y16_, int groups, float eps,
+                                     int relu, long long elem_offset, long long total_elems, void* stream) {
+  TView x, y, st, ga, be;
+  ChunkGeom gm;
+  B3D_TRY(view(x_, DT_F32, 5, false, "x", &x));
+  B3D_REQUIRE(x.shape[0] == 1, B3D_ERR_SHAPE, "gn_apply (slab): batch 1");
+  y.p = nullptr;
+  if (y_ != nullptr) {
+    B3D_TRY(view(y_, DT_F32, -1, false, "y", &y));
+    B3D_REQUIRE(x.numel == y.numel && ((uintptr_t)y.p & 15) == 0, B3D_ERR_SHAPE, "gn_apply: x/y size mismatch");
+  }
+  B3D_TRY(slab_geom(x, groups, elem_offset, total_elems, &gm));
+  B3D_TRY(check_stats(stats_, groups, "stats", &st));
+  B3D_TRY(check_affine(gamma_, gm.C, "gamma", &ga));
+  B3D_TRY(check_affine(beta_, gm.C, "beta", &be));
+  B3D_TRY(cell_ok(gm, x));
+  B3D_REQUIRE(elem_offset % kCell == 0 && x.numel % kCell == 0, B3D_ERR_LAYOUT, "gn_apply (slab): window not cell-aligned");
+  Twin16 tw;
+  B3D_TRY(twin_view(y16_, nullptr, x, &tw));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (relu)
+    gn_apply16_kernel<true><<<gn_grid16(gm, groups), kThreads, 0, s>>>(
+        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw,
+        elem_offset, x.numel);
+  else
+    gn_apply16_kernel<false><<<gn_grid16(gm, groups), kThreads, 0, s>>>(
+        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw,
+        elem_offset, x.numel);
+  B3D_LAUNCH_CHECK("gn_apply16 (slab)");
   return B3D_OK;
 }
 

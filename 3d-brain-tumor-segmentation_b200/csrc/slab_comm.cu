@@ -8,8 +8,8 @@
 //   [    0,  2048)  u64 flags:  [dir*2 + slot] halo (dir 0 = written by rank-1, dir 1 = written by rank+1);
 //                                [8 + slot*16 + r] all-reduce contribution of rank r
 //   [ 2048,  4096)  u32 local "blocks done" counters (one per direction), never touched by peers
-//   [ 4096, 20480)  all-reduce slots  [slot 2][rank 16][64 x 8 bytes]
-//   [32768, ...  )  mailboxes         [dir 2][slot 2][mailbox_bytes]
+//   [ 4096, 69632)  all-reduce slots  [slot 2][rank 16][256 x 8 bytes]
+//   [131072, ... )  mailboxes         [dir 2][slot 2][mailbox_bytes]
 // Sequence numbers: value = epoch * 65536 + seq + 1 where `epoch` is a device counter ticked once per forward (so a
 // replayed CUDA graph publishes fresh values) and `seq` counts the exchanges inside one forward.  Slots alternate
 // with seq; every exchange is bidirectional at the protocol level (a flag is sent even when no data moves), hence a
@@ -19,8 +19,8 @@
 
 namespace b3d {
 
-constexpr int kOffDone = 2048, kOffAr = 4096, kOffMailbox = 32768;
-constexpr int kArMaxRanks = 16, kArMaxWords = 64;
+constexpr int kOffDone = 2048, kOffAr = 4096, kOffMailbox = 131072;
+constexpr int kArMaxRanks = 16, kArMaxWords = 256;
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -89,6 +89,39 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// send + receive in ONE launch: every CTA first stores its share of the outgoing slice into the neighbour's mailbox
+// (the last one to finish publishes the flag), then waits for the neighbour's flag and copies its share of the incoming
+// slice.  Sends never wait for anything, and the <= 128 CTAs of the grid are co-resident, so the spin cannot deadlock.
+__global__ void __launch_bounds__(256)
+    halo_xchg_kernel(HaloSide s0, HaloSide s1, char* self, const unsigned long long* epoch, int seq,
+                     long long mailbox_bytes) {
+  const HaloSide s = blockIdx.y == 0 ? s0 : s1;
+  if (s.peer == nullptr) return;
+  const int slot = seq & 1, dir = blockIdx.y;
+  const unsigned long long want = *epoch * 65536ULL + (unsigned long long)seq + 1ULL;
+  float4* mbo = reinterpret_cast<float4*>(s.peer + kOffMailbox + (long long)(s.peer_dir * 2 + slot) * mailbox_bytes);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < s.n16_send; i += (long long)gridDim.x * 256)
+    mbo[i] = s.src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* done = reinterpret_cast<unsigned int*>(self + kOffDone) + blockIdx.y;
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {       // last block of this side: publish
+      *done = 0u;
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<unsigned long long*>(s.peer) + s.peer_dir * 2 + slot, want);
+    }
+    wait_flag(reinterpret_cast<const unsigned long long*>(self) + dir * 2 + slot, want);
+  }
+  __syncthreads();
+  const float4* mbi = reinterpret_cast<const float4*>(self + kOffMailbox + (long long)(dir * 2 + slot) * mailbox_bytes);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < s.n16_recv; i += (long long)gridDim.x * 256) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mbi + i));
+    s.dst[i] = v;
+  }
+}
+
 // one CTA: x (n <= 64 words of T) is summed over all ranks, in rank order (bit-identical on every rank)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -118,6 +151,43 @@ __global__ void __launch_bounds__(256)
       acc += src[e];
     }
     x[e] = acc;
+  }
+}
+
+// the same for a PAIR of vectors in one exchange: `a` (fp64, na values: GroupNorm chunk statistics) and `b` (fp32, nb
+// values: SE pooling sums) — a ResnetBlock's conv2 statistics and its pooling sums are needed at the same point
+__global__ void __launch_bounds__(256)
+    peer_allreduce2_kernel(double* a, int na, float* b, int nb, const long long* peers, int rank, int world, char* self,
+                           const unsigned long long* epoch, int seq) {
+  const int slot = seq & 1;
+  const unsigned long long want = *epoch * 65536ULL + (unsigned long long)seq + 1ULL;
+  const long long my_off = kOffAr + (long long)((slot * kArMaxRanks + rank) * kArMaxWords) * 8;
+  for (int i = threadIdx.x; i < (na + nb) * world; i += blockDim.x) {
+    const int p = i / (na + nb), e = i - p * (na + nb);
+    char* dst = reinterpret_cast<char*>(peers[p]) + my_off;
+    if (e < na) reinterpret_cast<double*>(dst)[e] = a[e];
+    else reinterpret_cast<float*>(dst + (long long)na * 8)[e - na] = b[e - na];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world)
+    st_release_sys(reinterpret_cast<unsigned long long*>(peers[threadIdx.x]) + 8 + slot * kArMaxRanks + rank, want);
+  if (threadIdx.x < world)
+    wait_flag(reinterpret_cast<const unsigned long long*>(self) + 8 + slot * kArMaxRanks + threadIdx.x, want);
+  __syncthreads();
+  for (int e = threadIdx.x; e < na + nb; e += blockDim.x) {
+    if (e < na) {
+      double acc = 0.0;
+      for (int r = 0; r < world; ++r)
+        acc += reinterpret_cast<const volatile double*>(self + kOffAr + (long long)((slot * kArMaxRanks + r) * kArMaxWords) * 8)[e];
+      a[e] = acc;
+    } else {
+      float acc = 0.f;
+      for (int r = 0; r < world; ++r)
+        acc += reinterpret_cast<const volatile float*>(self + kOffAr + (long long)((slot * kArMaxRanks + r) * kArMaxWords) * 8 +
+                                                       (long long)na * 8)[e - na];
+      b[e - na] = acc;
+    }
   }
 }
 
@@ -181,10 +251,8 @@ extern "C" int b3d_halo_exchange(const DLTensor* send_prev_, const DLTensor* sen
   if (blocks < 1) blocks = 1;
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid((unsigned)blocks, 2, 1);
-  halo_send_kernel<<<grid, 256, 0, st>>>(s[0], s[1], (char*)sym.p, (const unsigned long long*)ep.p, seq, mailbox_bytes);
-  B3D_LAUNCH_CHECK("halo_send");
-  halo_recv_kernel<<<grid, 256, 0, st>>>(s[0], s[1], (char*)sym.p, (const unsigned long long*)ep.p, seq, mailbox_bytes);
-  B3D_LAUNCH_CHECK("halo_recv");
+  halo_xchg_kernel<<<grid, 256, 0, st>>>(s[0], s[1], (char*)sym.p, (const unsigned long long*)ep.p, seq, mailbox_bytes);
+  B3D_LAUNCH_CHECK("halo_xchg");
   return B3D_OK;
 }
 
@@ -201,7 +269,7 @@ extern "C" int b3d_peer_allreduce(DLTensor* x_, const DLTensor* peers_, int rank
   cudaStream_t st = (cudaStream_t)stream;
   const bool f64 = x_->dtype.code == kDLFloat && x_->dtype.bits == 64;
   B3D_TRY(view(x_, f64 ? DT_F64 : DT_F32, -1, false, "x", &x));
-  B3D_REQUIRE(x.numel * (f64 ? 8 : 4) <= kArMaxWords * 8, B3D_ERR_SHAPE, "peer_allreduce: at most 512 bytes");
+  B3D_REQUIRE(x.numel * (f64 ? 8 : 4) <= kArMaxWords * 8, B3D_ERR_SHAPE, "peer_allreduce: at most %d bytes", kArMaxWords * 8);
   if (f64)
     peer_allreduce_kernel<double><<<1, 256, 0, st>>>((double*)x.p, (int)x.numel, (const long long*)pe.p, rank, world,
                                                      (char*)sym.p, (const unsigned long long*)ep.p, seq);
@@ -209,6 +277,25 @@ extern "C" int b3d_peer_allreduce(DLTensor* x_, const DLTensor* peers_, int rank
     peer_allreduce_kernel<float><<<1, 256, 0, st>>>((float*)x.p, (int)x.numel, (const long long*)pe.p, rank, world,
                                                     (char*)sym.p, (const unsigned long long*)ep.p, seq);
   B3D_LAUNCH_CHECK("peer_allreduce");
+  return B3D_OK;
+}
+
+// In-place sums over all ranks of a fp64 vector and a fp32 vector in ONE exchange (together <= 2 KB).
+extern "C" int b3d_peer_allreduce2(DLTensor* a_, DLTensor* b_, const DLTensor* peers_, int rank, DLTensor* sym_,
+                                   const DLTensor* epoch_, int seq, void* stream) {
+  TView pe, sym, ep, a, b;
+  B3D_TRY(view(peers_, DT_I64, 1, false, "peers", &pe));
+  B3D_TRY(view(sym_, DT_F32, 1, false, "sym", &sym));
+  B3D_TRY(view(epoch_, DT_I64, 1, false, "epoch", &ep));
+  B3D_TRY(view(a_, DT_F64, -1, false, "a", &a));
+  B3D_TRY(view(b_, DT_F32, -1, false, "b", &b));
+  const int world = (int)pe.numel;
+  B3D_REQUIRE(world >= 1 && world <= kArMaxRanks && rank >= 0 && rank < world, B3D_ERR_ARG, "peer_allreduce: bad world/rank");
+  B3D_REQUIRE(a.numel * 8 + b.numel * 4 <= kArMaxWords * 8, B3D_ERR_SHAPE, "peer_allreduce2: at most %d bytes", kArMaxWords * 8);
+  peer_allreduce2_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((double*)a.p, (int)a.numel, (float*)b.p, (int)b.numel,
+                                                             (const long long*)pe.p, rank, world, (char*)sym.p,
+                                                             (const unsigned long long*)ep.p, seq);
+  B3D_LAUNCH_CHECK("peer_allreduce2");
   return B3D_OK;
 }
 

@@ -265,8 +265,11 @@ _TWIN_DT = {"fp16": torch.float16, "bf16": torch.bfloat16}
 
 def twin_dtype(bwd: bool):
     """16-bit type of the operand twins of a pass (None: the pass does not run with 16-bit operands)."""
-    if not (P16["on"] and USE_TC["on"]) or _slab.current() is not None:
+    if not (P16["on"] and USE_TC["on"]):
         return None
+    ctx = _slab.current()
+    if ctx is not None:          # depth-slab inference (forward only): the slab context's choice
+        return None if bwd else ctx.p16
     return _TWIN_DT.get(get_conv_precision()[1 if bwd else 0])
 
 
@@ -654,8 +657,8 @@ _XB_CACHE = {}
 def conv3d(x, w, bias=None, stride=1, transposed=False, act=0, gn_groups=0, want_gap=False, share_x=False,
            grad_box=None):
     ctx = _slab.current()
-    if ctx is not None:        # depth-slab sharded inference: halo exchange + all-reduced GAP, no fused GN stats
-        return ctx.conv3d(x, w, bias, stride, transposed, act, want_gap)
+    if ctx is not None:        # depth-slab sharded inference: halo exchange, partial statistics / pooling sums
+        return ctx.conv3d(x, w, bias, stride, transposed, act, want_gap, gn_groups)
     return Conv3dFn.apply(x, w, bias, stride, transposed, act, gn_groups, want_gap, share_x, grad_box)
 
 
@@ -783,7 +786,7 @@ def group_norm(x, gamma, beta, stats=None, groups=8, eps=1e-5, relu=False, chann
             raise NotImplementedError("b3d: depth-slab inference is built for the channels_last GroupNorm semantics")
         return GroupNormChannelFn.apply(x, gamma, beta, groups, eps, relu)
     if ctx is not None:        # chunk statistics of the WHOLE volume: partial sums + all-reduce
-        return ctx.group_norm(x, gamma, beta, groups, eps, relu)
+        return ctx.group_norm(x, gamma, beta, groups, eps, relu, stats, operand_only)
     y, y16, y16b = GroupNormFn.apply(x, gamma, beta, stats, groups, eps, relu, bool(operand_only),
                                      torch.is_grad_enabled())
     if y16 is not None and not is_virtual(y):
@@ -920,7 +923,11 @@ class BlockEpilogueFn(Function):
 
 
 def block_epilogue(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups=8, eps=1e-5, keep_f32=False):
-    operand_only = FUSED["on"] and _slab.current() is None and not keep_f32
+    sctx = _slab.current()
+    if sctx is not None and sctx.p16 is not None and p16_ok(res.shape):
+        return sctx.block_epilogue(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps,
+                                   keep_f32 or not FUSED["on"])
+    operand_only = FUSED["on"] and sctx is None and not keep_f32
     out, out16, out16b = BlockEpilogueFn.apply(res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps,
                                                operand_only, torch.is_grad_enabled())
     if out16 is not None and not is_virtual(out):

@@ -61,6 +61,11 @@ class Comm:
     def all_reduce_sum(self, t: torch.Tensor) -> None:
         raise NotImplementedError
 
+    def all_reduce_sum2(self, a: torch.Tensor, b: torch.Tensor) -> None:
+        """A fp64 and a fp32 vector summed over the ranks; backends that can do so use ONE exchange."""
+        self.all_reduce_sum(a)
+        self.all_reduce_sum(b)
+
     def all_gather_cat(self, t: torch.Tensor, sizes: Sequence[int]) -> torch.Tensor:
         """Concatenate the ranks' tensors (dim 1 extents `sizes`) on every rank."""
         raise NotImplementedError
@@ -152,6 +157,15 @@ class PeerComm(Comm):
         ops._call("b3d_peer_allreduce", t, self.peers, self.rank, self.sym, self.epoch, self.aseq)
         self.aseq += 1
 
+    def all_reduce_sum2(self, a, b):
+        from . import ops
+        if self.world == 1:
+            return
+        if a.numel() * 8 + b.numel() * 4 > 2048:
+            return Comm.all_reduce_sum2(self, a, b)
+        ops._call("b3d_peer_allreduce2", a, b, self.peers, self.rank, self.sym, self.epoch, self.aseq)
+        self.aseq += 1
+
     def all_gather_cat(self, t, sizes):
         if self.world == 1:
             return t
@@ -210,6 +224,9 @@ class ThreadComm(Comm):
 
 # ------------------------------------------------------------------------------------------ context
 _TLS = threading.local()
+# A/B switch: B3D_SLAB_P16=0 keeps fp32 activations between the layers of a slab (the round-1 form)
+import os as _os
+SLAB_P16 = {"on": _os.environ.get("B3D_SLAB_P16", "1") not in ("0", "", "off", "false")}
 
 
 def current() -> Optional["SlabContext"]:
@@ -227,17 +244,34 @@ class SlabContext:
         self.local_depth = self.d1 - self.d0
         self.stats = {"halo_exchanges": 0, "halo_bytes": 0, "all_reduces": 0, "halo_copies": 0}
         self._padded = {}        # data_ptr of an activation -> the [1, Dl+2, H, W, C] buffer it is the interior of
+        # P16 form (the default): activations between layers are 16-bit twins [1, Dl, H, C/8, W, 8] allocated between
+        # two spare depth slices, the convs read them through TMA, GroupNorm statistics come out of the conv epilogues
+        # as partial sums and are all-reduced together with the SE pooling sums.  `p16` = the twin dtype or None.
+        self.p16 = None
+        self._halo_done = {}     # data_ptr of a P16 activation -> set of halo sides already received
+        self._arena, self._arena_used, self._arena_dev = None, 0, None
+        self._pending = []       # partial sums (fp64 statistics, fp32 pooling sums) awaiting their all-reduce
 
     def __enter__(self):
+        from . import ops
         self._prev = current()
         _TLS.ctx = self
         if hasattr(self.comm, "begin_forward"):
             self.comm.begin_forward()
+        self.p16 = None
+        self._arena_used = 0
+        if ops.P16["on"] and ops.USE_TC["on"] and SLAB_P16["on"]:
+            self.p16 = ops._TWIN_DT.get(ops.get_conv_precision()[0])
         return self
 
     def __exit__(self, *a):
         _TLS.ctx = self._prev
         self._padded.clear()
+        self._halo_done.clear()
+        if a[0] is None and self._pending:
+            self._pending = []
+            raise RuntimeError("slab: partial sums were left without their all-reduce")
+        self._pending = []
 
     def new_activation(self, shape, like: torch.Tensor) -> torch.Tensor:
         """Allocate an activation [1, Dl, H, W, C] as the interior of a buffer with one spare depth slice on each
@@ -296,13 +330,137 @@ class SlabContext:
         self.stats["halo_bytes"] += sum(t.numel() * 4 for t in (send_prev, send_next) if t is not None)
         return pad
 
-    # ---- the three rerouted operations (forward only)
-    def conv3d(self, x, w, bias, stride, transposed, act, want_gap):
+    # ---- P16 activations
+    def new_p16(self, shape5, like: torch.Tensor) -> torch.Tensor:
+        """P16 twin [1, Dl, H, C/8, W, 8] of a local activation, allocated between two spare depth slices (the halo
+        slices are received in place; at the ends of the volume the operand handed to the conv simply ends there and
+        the loaders' zero fill is TF's 'SAME' padding, as in the un-sharded forward)."""
+        _, dl, H, W_, C = (int(v) for v in shape5)
+        parent = torch.empty((1, dl + 2, H, C // 8, W_, 8), dtype=self.p16, device=like.device)
+        view = parent[:, 1:dl + 1]
+        self._padded[view.data_ptr()] = parent
+        self._halo_done[view.data_ptr()] = set()
+        return view
+
+    def with_halo_p16(self, t: torch.Tensor, before: int, after: int) -> torch.Tensor:
+        """[1, Dl, H, C/8, W, 8] -> (the window of its buffer that includes the halo slices a neighbour provides, halo
+        slices before, after), after receiving those that have not been received yet (a tensor read by two 3x3x3-type
+        convs is exchanged once)."""
+        c = self.comm
+        dl = t.shape[1]
+        parent = self._padded.get(t.data_ptr())
+        if parent is None or tuple(parent.shape) != (1, dl + 2) + tuple(t.shape[2:]):
+            raise RuntimeError("slab: a P16 operand that was not allocated by the slab context")
+        done = self._halo_done[t.data_ptr()]
+        need_b, need_a = bool(before) and "b" not in done, bool(after) and "a" not in done
+        has_prev, has_next = c.rank > 0, c.rank < c.world - 1
+        if (need_b or need_a) and c.world > 1:
+            f = lambda v: v.view(_f32)
+            send_prev = f(t[:, :1]) if (need_a and has_prev) else None          # my first slice = prev's "after" halo
+            send_next = f(t[:, dl - 1:]) if (need_b and has_next) else None     # my last slice = next's "before" halo
+            recv_prev = f(parent[:, :1]) if (need_b and has_prev) else None
+            recv_next = f(parent[:, dl + 1:]) if (need_a and has_next) else None
+            c.exchange(send_prev, send_next, recv_prev, recv_next)
+            self.stats["halo_exchanges"] += 1
+            self.stats["halo_bytes"] += sum(v.numel() * 4 for v in (send_prev, send_next) if v is not None)
+        if need_b:
+            done.add("b")
+        if need_a:
+            done.add("a")
+        b_eff, a_eff = (before if has_prev else 0), (after if has_next else 0)
+        return parent[:, 1 - b_eff:1 + dl + a_eff], b_eff, a_eff
+
+    def arena(self, n: int, dtype) -> torch.Tensor:
+        """n zero-initialised values (fp64 statistics / fp32 pooling sums) for a conv epilogue to accumulate into:
+        slices of one buffer that is cleared ONCE per forward instead of a memset node per conv."""
+        if self._arena is None:
+            self._arena = torch.empty(8192, dtype=torch.float64, device=self._arena_dev)
+            self._arena_used = 0
+        if self._arena_used == 0:
+            from . import ops
+            ops._call("b3d_zero", self._arena.view(_f32))
+        words = n if dtype == torch.float64 else (n + 1) // 2
+        if self._arena_used + words > self._arena.numel():
+            return None
+        t = self._arena[self._arena_used:self._arena_used + words]
+        self._arena_used += words
+        return t if dtype == torch.float64 else t.view(_f32)[:n]
+
+    def flush(self):
+        """All-reduce the pending partial sums: a fp64 vector and a fp32 vector share one exchange."""
+        p, self._pending = self._pending, []
+        f64 = [t for t in p if t.dtype == torch.float64]
+        f32 = [t for t in p if t.dtype != torch.float64]
+        while f64 and f32:
+            self.comm.all_reduce_sum2(f64.pop(0), f32.pop(0))
+            self.stats["all_reduces"] += 1
+        for t in f64 + f32:
+            self.comm.all_reduce_sum(t)
+            self.stats["all_reduces"] += 1
+
+    def _conv3d_p16(self, srcs, w, bias, stride, transposed, act, want_gap, gn_groups, before, after):
         from . import ops
-        ops._check(x)
-        x = x.contiguous()
+        dl, H, W_ = srcs[0].shape[1], srcs[0].shape[2], srcs[0].shape[4]
+        xin, b_eff, a_eff = list(srcs), 0, 0
+        if before + after:
+            wins = [self.with_halo_p16(t, before, after) for t in srcs]
+            xin, b_eff, a_eff = [w_[0] for w_ in wins], wins[0][1], wins[0][2]
+        if transposed:
+            cout, od = w.shape[3], (2 * dl, 2 * H, 2 * W_)
+        else:
+            cout = w.shape[4]
+            od = (dl, H, W_) if stride == 1 else (dl // 2, H // 2, W_ // 2)
+        y = torch.empty((1,) + od + (cout,), dtype=_f32, device=w.device)
+        g0, dg = self.geometry(y)
+        hw = od[1] * od[2]
+        self._arena_dev = w.device
+        stats = gap = None
+        pre = 1
+        if gn_groups and cout % gn_groups == 0 and (dg * hw) % gn_groups == 0:
+            stats = self.arena(2 * gn_groups, torch.float64)
+            if stats is None:
+                stats, pre = torch.empty(2 * gn_groups, dtype=torch.float64, device=w.device), 0
+            stats = stats.view(1, gn_groups, 2)
+        if want_gap:
+            gap = self.arena(cout, _f32) if pre else None
+            if gap is None:
+                if stats is not None and pre:          # mixed: let the ABI clear both
+                    stats.zero_()
+                gap, pre = torch.empty(cout, dtype=_f32, device=w.device), 0
+            gap = gap.view(1, cout)
+        wp = ops.pack_weights(w, False, stride, transposed)
+        ops._call("b3d_conv3d_fwd_p16_slab", *ops._pad4(xin), w, bias, y, stride, int(transposed), int(act), b_eff, a_eff,
+                  stats, gn_groups or 1, g0 * hw, dg * hw, gap, wp, pre)
+        for t in (stats, gap):
+            if t is not None:
+                self._pending.append(t)
+        return y, stats, gap
+
+    def block_epilogue(self, res, h2, stats2, gamma2, beta2, wsp, gap_sum, w1, w2, groups, eps, keep_f32):
+        """BlockEpilogueFn.forward for one slab in the P16 form (ops.block_epilogue routes here)."""
+        from . import ops
+        self.flush()
+        F = res.shape[-1]
+        R = w1.shape[1]
+        hidden, chse = torch.empty((1, R), dtype=_f32, device=res.device), torch.empty((1, F), dtype=_f32, device=res.device)
+        ops._call("b3d_se_fc_fwd", gap_sum, w1, w2, hidden, chse, 1.0 / self.global_voxels(res))
+        has_gn = stats2 is not None
+        out16 = self.new_p16(res.shape, res)
+        out = torch.empty_like(res) if keep_f32 else None
+        g0, dg = self.geometry(res)
+        hw = res.shape[2] * res.shape[3]
+        ops._call("b3d_block_epilogue_fwd_p16_slab", res.contiguous(), ops.materialize(h2), stats2,
+                  gamma2 if has_gn else None, beta2 if has_gn else None, wsp.reshape(F), chse, out, out16, groups,
+                  float(eps), int(has_gn), g0 * hw, dg * hw)
+        if out is None:
+            return ops.virtual(res.shape, res, [out16], None)
+        ops._attach(out, out16, None)
+        return out
+
+    # ---- the three rerouted operations (forward only)
+    def conv3d(self, x, w, bias, stride, transposed, act, want_gap, gn_groups=0):
+        from . import ops
         k = w.shape[0]
-        _, dl, H, W_, _ = x.shape
         if k == 1:
             before = after = 0
         elif transposed:
@@ -311,6 +469,13 @@ class SlabContext:
             before, after = 0, 1
         else:
             before, after = 1, 1
+        srcs = ops.sources(x)
+        if (self.p16 is not None and srcs is not None and len(srcs) <= 4 and all(t.dtype == self.p16 for t in srcs)
+                and (not act or stride == 1) and ops.tc_supported(w, stride, transposed, False)):
+            return self._conv3d_p16(srcs, w, bias, stride, transposed, act, want_gap, gn_groups, before, after)
+        x = ops.materialize(x)
+        ops._check(x)
+        _, dl, H, W_, _ = x.shape
         xin = self.with_halo(x, before, after) if before + after else x
         if transposed:
             cout, od = w.shape[3], (2 * dl, 2 * H, 2 * W_)
@@ -328,10 +493,10 @@ class SlabContext:
             self.stats["all_reduces"] += 1
         return y, None, gap
 
-    def group_norm(self, x, gamma, beta, groups, eps, relu):
+    def group_norm(self, x, gamma, beta, groups, eps, relu, stats=None, operand_only=False):
         from . import ops
+        x = ops.materialize(x)
         ops._check(x)
-        x = x.contiguous()
         C = x.shape[-1]
         if C < groups:      # reference group_norm.py:51-59
             raise ValueError(f"Number of groups ({groups}) cannot be more than the number of channels ({C}).")
@@ -340,10 +505,20 @@ class SlabContext:
         g0, dg = self.geometry(x)
         per_slice = x.shape[2] * x.shape[3] * C
         off, total = g0 * per_slice, dg * per_slice
-        stats = torch.empty((1, groups, 2), dtype=torch.float64, device=x.device)
-        ops._call("b3d_gn_stats_slab", x, stats, groups, off, total)
-        self.comm.all_reduce_sum(stats)
-        self.stats["all_reduces"] += 1
+        if stats is None:
+            stats = torch.empty((1, groups, 2), dtype=torch.float64, device=x.device)
+            ops._call("b3d_gn_stats_slab", x, stats, groups, off, total)
+            self._pending.append(stats)
+        self.flush()             # the conv epilogue's (or the kernel's above) partial sums -> whole-volume statistics
+        L = total // groups
+        if self.p16 is not None and ops.p16_ok(x.shape) and L % 8 == 0 and per_slice % 8 == 0:
+            y16 = self.new_p16(x.shape, x)
+            y = None if operand_only else torch.empty_like(x)
+            ops._call("b3d_gn_apply_p16_slab", x, stats, gamma, beta, y, y16, groups, float(eps), int(relu), off, total)
+            if y is None:
+                return ops.virtual(x.shape, x, [y16], None)
+            ops._attach(y, y16, None)
+            return y
         y = self.new_activation(x.shape, x)
         ops._call("b3d_gn_apply_slab", x, stats, gamma, beta, y, groups, float(eps), int(relu), off, total)
         return y

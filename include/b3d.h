@@ -246,14 +246,35 @@ int b3d_upsample2_bwd(const DLTensor* dy, DLTensor* dx, void* stream);
  *   copied to recv_prev / recv_next (nullable).  prev_base / next_base: device addresses of the neighbours' symmetric
  *   buffers (0 = no neighbour).  epoch: int64 [1] device counter ticked once per forward (b3d_epoch_tick), seq: index
  *   of this exchange inside the forward.  peer_allreduce: in-place sum over all ranks (rank order, bit-identical
- *   everywhere) of <= 512 bytes of fp32 / fp64 (GroupNorm chunk statistics, SE pooling sums). */
+ *   everywhere) of <= 2 KB of fp32 / fp64 (GroupNorm chunk statistics, SE pooling sums); peer_allreduce2: a fp64 and a
+ *   fp32 vector in one exchange. */
 long long b3d_slab_sym_bytes(long long mailbox_bytes);
 int b3d_halo_exchange(const DLTensor* send_prev, const DLTensor* send_next, DLTensor* recv_prev, DLTensor* recv_next,
                       long long prev_base, long long next_base, DLTensor* sym, const DLTensor* epoch, int seq,
                       long long mailbox_bytes, void* stream);
 int b3d_peer_allreduce(DLTensor* x, const DLTensor* peers /*int64 [world]*/, int rank, DLTensor* sym,
                        const DLTensor* epoch, int seq, void* stream);
+int b3d_peer_allreduce2(DLTensor* a /*fp64*/, DLTensor* b /*fp32*/, const DLTensor* peers, int rank, DLTensor* sym,
+                        const DLTensor* epoch, int seq, void* stream);
 int b3d_epoch_tick(DLTensor* epoch, void* stream);
+
+/* Depth-slab forms of the P16 forward kernels (whole-volume inference sharded along D; /root/reference/test.py:133 on one
+ * slab per GPU): the conv reads P16 sources that carry halo_before / halo_after extra depth slices and emits this slab's
+ * PARTIAL GroupNorm statistics over the chunks of the whole volume (stat_total output voxels per sample, this slab's
+ * first = stat_off; /root/reference/layers/group_norm.py:83-124 reshapes the whole volume); GroupNorm apply and the
+ * block epilogue take the all-reduced statistics and the window [offset, offset + local size) of the volume. */
+int b3d_conv3d_fwd_p16_slab(const DLTensor* x0, const DLTensor* x1, const DLTensor* x2, const DLTensor* x3,
+                            const DLTensor* w, const DLTensor* bias /*nullable*/, DLTensor* y, int stride,
+                            int transposed, int act, int halo_before, int halo_after, DLTensor* gn_stats /*nullable*/,
+                            int groups, long long stat_off, long long stat_total, DLTensor* gap /*nullable*/,
+                            const DLTensor* wpacked, int prezeroed /*gn_stats / gap are already zero*/, void* stream);
+int b3d_gn_apply_p16_slab(const DLTensor* x, const DLTensor* stats, const DLTensor* gamma, const DLTensor* beta,
+                          DLTensor* y /*nullable*/, DLTensor* y16, int groups, float eps, int relu,
+                          long long elem_offset, long long total_elems, void* stream);
+int b3d_block_epilogue_fwd_p16_slab(const DLTensor* res, const DLTensor* h2, const DLTensor* stats,
+                                    const DLTensor* gamma, const DLTensor* beta, const DLTensor* wsp,
+                                    const DLTensor* chse, DLTensor* out /*nullable*/, DLTensor* out16, int groups,
+                                    float eps, int has_gn, long long vox_offset, long long total_vox, void* stream);
 
 /* ---- test-time augmentation (test.py:105-161): flip bits 1=D 2=H 4=W on one [D,H,W,C] volume ------------
  * flip_normalize: out = (flip(x) - mean)/std (test.py:107,128; mean/std nullable).

@@ -112,7 +112,14 @@ def test_train_step_128cube_mixed_precision_vs_oracle(b3d, dev, crop):
     bad = [r for r in rows if r[0] > GRAD_SLACK * r[1] + GRAD_FLOOR]
     assert not bad, bad[:8]
     assert med(0) <= MEDIAN_SLACK * med(1) + GRAD_FLOOR
-    assert min(r[3] for r in rows) > 0.98, rows[:3]
+    # direction: a relative error e costs about e^2/2 of cosine, so the per-tensor cosine bound follows from the SAME
+    # per-tensor error bound as above (no free constant).  The worst tensor is the first block's 16x8 SE kernel, an
+    # ill-conditioned sum over the whole volume: three runs of one build gave rel-L2 0.155 / 0.233 / 0.168 and cosine
+    # 0.9892 / 0.9769 / 0.9874 for it (profiles/r02e_parity_spread.txt) — the forward is not bit-reproducible (fp32
+    # atomics of the pooling sums decide 16-bit rounding ties downstream), the model's bound for it is 0.295 / 0.956.
+    bad_dir = [r for r in rows if r[3] < 1.0 - 0.5 * (GRAD_SLACK * r[1] + GRAD_FLOOR) ** 2]
+    assert not bad_dir, bad_dir[:8]
+    assert min(r[3] for r in rows) > 0.95, rows[:3]
 
 
 def _padded_volume(shape, orig, in_ch, seed):
@@ -147,7 +154,7 @@ def test_inference_160x192x160_and_depth_slabs_vs_oracle(b3d, dev):
     for world in (2, 4, 8):
         got, stats = b3d.slab.run_virtual_ranks(model, xd, world)
         assert got.shape == yr.shape
-        assert stats[0]["halo_exchanges"] == 32
+        assert stats[0]["halo_exchanges"] == 35       # 32 convs + the second source of the 3 decoder concats
         check(got, f"{world} slabs {[b - a for a, b in b3d.slab_bounds(shape[0], world)]}")
 
 
