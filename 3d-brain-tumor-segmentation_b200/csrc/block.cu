@@ -21,6 +21,7 @@ struct BlockGeom {
   // depth-slab form (forward twin kernel only; batch 1): the tensors hold voxels [vshift, vshift + S_local) of the
   // volume S / vpc describe.  S_local < 0: the tensors are the volume
   long long vshift, S_local;
+  int chunk0;         // first chunk the grid covers (slab form: only the chunks that intersect the slab are launched)
 };
 
 __device__ __forceinline__ float group_sum(float v, int T) {
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(kBT)
     block_fwd16_kernel(const float* __restrict__ res, const float* __restrict__ h2, const double* __restrict__ stats,
                        const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ wsp,
                        const float* __restrict__ chse, float* __restrict__ out, BlockGeom gm, float eps, Twin16 tw) {
-  const int chunk = blockIdx.y, b = chunk / gm.G, g = chunk % gm.G;
+  const int chunk = blockIdx.y + gm.chunk0, b = chunk / gm.G, g = chunk % gm.G;
   const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
   const int c = lane * 8;
   float mean = 0.f, rstd = 1.f;
@@ -757,7 +758,7 @@ static int block_geom(const TView& res, int groups, bool has_gn, BlockGeom* gm, 
   while (T < 32 && q % (T * 2) == 0) T *= 2;
   B3D_REQUIRE(q / T <= kMaxNPL, B3D_ERR_UNSUPPORTED, "block epilogue: unsupported filter count %d", F);
   gm->S = S;
-  gm->vshift = 0; gm->S_local = -1;
+  gm->vshift = 0; gm->S_local = -1; gm->chunk0 = 0;
   gm->vpc = S / G;
   gm->F = F;
   gm->T = T;
@@ -768,7 +769,7 @@ static int block_geom(const TView& res, int groups, bool has_gn, BlockGeom* gm, 
   // ~8 voxel-iterations per thread-group, but enough CTAs to fill the machine
   // ~16 voxel-iterations per thread-group at least, and no more than ~4 waves of CTAs in total (the reducing
   // kernels end in a handful of atomics per CTA)
-  long long vp = (long long)vstep * 16;
+  long long vp = (long long)vstep * 4;
   const long long cap = (4LL * sm_count() + B * G - 1) / (B * G);
   const long long need = ((gm->vpc + cap - 1) / cap + vstep - 1) / vstep * vstep;
   if (need > vp) vp = need;
@@ -911,7 +912,7 @@ extern "C" int b3d_block_epilogue_bwd_reduce(const DLTensor* dout_, const DLTens
         BlockGeom g8 = gm;
         g8.T = T8; g8.npl = 2;
         const int vstep = kBT / T8;
-        long long vp = (long long)vstep * 16;
+        long long vp = (long long)vstep * 4;
         const long long Bn = res.shape[0];
         const long long cap = (3LL * sm_count() + Bn * gm.G - 1) / (Bn * gm.G);
         const long long need = ((gm.vpc + cap - 1) / cap + vstep - 1) / vstep * vstep;
@@ -1010,7 +1011,7 @@ int block_geom16(const TView& res, int groups, bool has_gn, b3d::BlockGeom* gm, 
   B3D_REQUIRE(res.numel / res.shape[0] / gm->F < (1LL << 32), B3D_ERR_UNSUPPORTED, "block epilogue (P16): sample too large");
   gm->T = T; gm->npl = 2;
   const int vstep = kBT / T;
-  long long vp = (long long)vstep * 16;
+  long long vp = (long long)vstep * 2;     // >= 2 voxel steps per thread; small tensors get many short CTAs, not a 16-step latency chain
   const long long B = res.shape[0];
   const long long cap = (3LL * sm_count() + B * gm->G - 1) / (B * gm->G);
   const long long need = ((gm->vpc + cap - 1) / cap + vstep - 1) / vstep * vstep;
@@ -1086,6 +1087,8 @@ extern "C" int b3d_block_epilogue_fwd_p16_slab(const DLTensor* res_, const DLTen
                   total_vox < (1LL << 32), B3D_ERR_ARG, "block epilogue (slab): bad window (%lld + %lld of %lld)",
               vox_offset, S_local, total_vox);
   gm.S = total_vox; gm.vpc = total_vox / gm.G; gm.vshift = vox_offset; gm.S_local = S_local;
+  gm.chunk0 = (int)(vox_offset / gm.vpc);
+  const int nlaunch = (int)((vox_offset + S_local - 1) / gm.vpc) - gm.chunk0 + 1;     // chunks that intersect the slab
   B3D_TRY(vecF(wsp_, gm.F, "wsp", &wsp));
   B3D_TRY(vecF(chse_, gm.F, "chse", &ch));
   Twin16 tw;
@@ -1096,11 +1099,11 @@ extern "C" int b3d_block_epilogue_fwd_p16_slab(const DLTensor* res_, const DLTen
     B3D_REQUIRE(st.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats: wrong size");
     B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
     B3D_TRY(vecF(beta_, gm.F, "beta", &be));
-    block_fwd16_kernel<true><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+    block_fwd16_kernel<true><<<block_grid(gm, nlaunch), kBT, 0, s>>>(
         (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
         (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps, tw);
   } else {
-    block_fwd16_kernel<false><<<block_grid(gm, nchunks), kBT, 0, s>>>(
+    block_fwd16_kernel<false><<<block_grid(gm, nlaunch), kBT, 0, s>>>(
         (const float*)res.p, (const float*)h2.p, nullptr, nullptr, nullptr, (const float*)wsp.p, (const float*)ch.p,
         (float*)out.p, gm, eps, tw);
   }

@@ -714,10 +714,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
 __global__ void __launch_bounds__(256)
     conv_finish_kernel(float* __restrict__ y, const float* __restrict__ ws, int ksplit, long long ws_slice,
                        const float* __restrict__ bias, double* __restrict__ stats, float* __restrict__ gap,
-                       long long L, int C, int G, long long shift, long long n_local) {
+                       long long L, int C, int G, long long shift, long long n_local, int chunk0) {
   extern __shared__ float sgap[];                  // [C]
   __shared__ double red[64];
-  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  const int chunk = blockIdx.x + chunk0;           // slab form: the grid starts at the first intersecting chunk
+  const int b = chunk / G, g = chunk % G;
   // depth-slab form (n_local >= 0, batch 1): y holds the elements [shift, shift + n_local) of the volume whose chunks
   // (G, L) describe; a CTA covers the part of its chunk's segment that lies inside
   long long e_lo = 0, e_hi = L, sh = 0;
@@ -751,8 +752,8 @@ __global__ void __launch_bounds__(256)
   }
   block_sum<2, double>(d, red);
   if (stats != nullptr && threadIdx.x == 0) {      // G == groups when statistics are requested
-    atomicAdd(&stats[2 * blockIdx.x], d[0]);
-    atomicAdd(&stats[2 * blockIdx.x + 1], d[1]);
+    atomicAdd(&stats[2 * chunk], d[0]);
+    atomicAdd(&stats[2 * chunk + 1], d[1]);
   }
   __syncthreads();
   if (gap != nullptr)
@@ -1092,9 +1093,10 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
     const bool slab = stats != nullptr && g.stat_total > 0;       // chunks of the whole volume, window of this slab
     const long long L = (slab ? g.stat_total : S) * g.Cout / G;
     const long long span = slab && out_elems < L ? out_elems : L;  // longest part of a chunk a CTA row can hold
-    conv_finish_kernel<<<dim3(g.B * G, (unsigned)((span + 8191) / 8192)), 256, sizeof(float) * g.Cout, s>>>(
-        y, ws, p.ksplit, out_elems, bias, stats, gap, L, g.Cout, G, slab ? g.stat_off * g.Cout : 0,
-        slab ? out_elems : -1);
+    const long long sh = slab ? g.stat_off * g.Cout : 0;
+    const int c0 = slab ? (int)(sh / L) : 0, nc = slab ? (int)((sh + out_elems - 1) / L) - c0 + 1 : g.B * G;
+    conv_finish_kernel<<<dim3(nc, (unsigned)((span + 8191) / 8192)), 256, sizeof(float) * g.Cout, s>>>(
+        y, ws, p.ksplit, out_elems, bias, stats, gap, L, g.Cout, G, sh, slab ? out_elems : -1, c0);
     B3D_LAUNCH_CHECK("conv_finish");
   }
   return B3D_OK;

@@ -384,10 +384,11 @@ template <bool RELU>
 __global__ void __launch_bounds__(kThreads)
     gn_apply16_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float* __restrict__ y, ChunkGeom gm, float eps, Twin16 tw,
-                      long long shift, long long n_local) {
+                      long long shift, long long n_local, int chunk0) {
   // depth-slab form (n_local >= 0; batch 1): x / y / the twin hold the flat elements [shift, shift + n_local) of the
-  // volume whose chunks gm describes; a CTA covers the part of its chunk that lies inside
-  const int chunk = blockIdx.y, g = chunk % gm.G, b = chunk / gm.G;
+  // volume whose chunks gm describes; a CTA covers the part of its chunk that lies inside (the grid starts at the
+  // first chunk that intersects: chunk0)
+  const int chunk = blockIdx.y + chunk0, g = chunk % gm.G, b = chunk / gm.G;
   long long e_lo = 0, e_hi = gm.L;
   if (n_local >= 0) {
     e_lo = max(0LL, shift - (long long)chunk * gm.L);
@@ -941,10 +942,10 @@ extern "C" int b3d_gn_apply_p16(const DLTensor* x_, const DLTensor* stats_, cons
   cudaStream_t s = (cudaStream_t)stream;
   if (relu)
     gn_apply16_kernel<true><<<gn_grid16(gm, nchunks), kThreads, 0, s>>>(
-        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw, 0, -1);
+        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw, 0, -1, 0);
   else
     gn_apply16_kernel<false><<<gn_grid16(gm, nchunks), kThreads, 0, s>>>(
-        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw, 0, -1);
+        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw, 0, -1, 0);
   B3D_LAUNCH_CHECK("gn_apply16");
   return B3D_OK;
 }
@@ -972,14 +973,18 @@ extern "C" int b3d_gn_apply_p16_slab(const DLTensor* x_, const DLTensor* stats_,
   Twin16 tw;
   B3D_TRY(twin_view(y16_, nullptr, x, &tw));
   cudaStream_t s = (cudaStream_t)stream;
+  const int c0 = (int)(elem_offset / gm.L), nc = (int)((elem_offset + x.numel - 1) / gm.L) - c0 + 1;
+  ChunkGeom gl = gm;                               // grid sized for the part of a chunk a slab can hold
+  if (x.numel < gl.L) gl.L = (x.numel + kCell - 1) / kCell * kCell;
+  const dim3 grid = gn_grid16(gl, nc);
   if (relu)
-    gn_apply16_kernel<true><<<gn_grid16(gm, groups), kThreads, 0, s>>>(
+    gn_apply16_kernel<true><<<grid, kThreads, 0, s>>>(
         (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw,
-        elem_offset, x.numel);
+        elem_offset, x.numel, c0);
   else
-    gn_apply16_kernel<false><<<gn_grid16(gm, groups), kThreads, 0, s>>>(
+    gn_apply16_kernel<false><<<grid, kThreads, 0, s>>>(
         (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw,
-        elem_offset, x.numel);
+        elem_offset, x.numel, c0);
   B3D_LAUNCH_CHECK("gn_apply16 (slab)");
   return B3D_OK;
 }
