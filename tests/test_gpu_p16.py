@@ -273,7 +273,9 @@ def test_train_step_with_and_without_twins(b3d, dev):
     a, b = g1.double().flatten(), g0.double().flatten()
     cosine = float((a @ b) / (a.norm() * b.norm()))
     print(f"outputs rel {[f'{rel(u, v):.1e}' for u, v in zip(o1, o0)]}; flat-gradient cosine {cosine:.5f}")
-    assert abs(l1 - l0) / abs(l0) < 1e-4
+    # (north_star's loss tolerance against the reference is 1e-3; between the two operand paths 0.3-1.1e-4 is measured,
+    # the same size as the run-to-run spread of ONE path: profiles/r02e_parity_spread.txt)
+    assert abs(l1 - l0) / abs(l0) < 3e-4
     assert rel(o1[0], o0[0]) < 1e-3 and rel(o1[1], o0[1]) < 4e-3
     assert cosine > 0.995
     assert n1 < n0                       # no cast passes, no concat copies
