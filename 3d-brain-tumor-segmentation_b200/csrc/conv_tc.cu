@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
     // every third patch of a tile
     const int q = warp & 3;                 // TMEM lane quarter == warp % 4
     const int eg = warp >> 2, neg = prm.tma ? 1 + kLoaderWarps / 4 : 1;
-    const bool wide_st = prm.act == 0 && !prm.accumulate && prm.ksplit <= 1 && (prm.yp & 7) == 0 &&
+    const bool wide_st = prm.act == 0 && prm.ksplit <= 1 && (prm.yp & 7) == 0 &&
                          (reinterpret_cast<uintptr_t>(prm.y) & 31) == 0;
     const int row = q * 32 + lane;          // patch row: h = row/8, w = row%8
     const int ph = row >> 3, pwv = row & 7;
@@ -629,6 +629,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
           } else if (valid && wide_st) {
             // plain epilogue (every conv of the training step but the sigmoid / accumulate forms): 2 x 256-bit stores
             float o[16];
+            if (prm.accumulate) {
+              // y += result (the second of two data gradients w.r.t. one tensor): the 64 bytes are fetched with four
+              // 128-bit loads issued together
+              float4 e[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) e[i] = __ldcg(reinterpret_cast<const float4*>(yp) + i);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                v[4 * i] += e[i].x; v[4 * i + 1] += e[i].y; v[4 * i + 2] += e[i].z; v[4 * i + 3] += e[i].w;
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               o[i] = v[i] + bv[i];

@@ -100,9 +100,38 @@ def check_data_format(data_format):
     return data_format
 
 
+# Keras names layers `snake_case(class)` + `_<n>` with one process-wide counter per class, starting without a suffix
+# (tf.keras.backend.unique_object_name, zero-based): 'conv3d', 'conv3d_1', ... — what the weight names of a Keras
+# checkpoint are made of.  `reset_uids()` is tf.keras.backend.clear_session()'s effect on them.
+import collections as _collections
+import re as _re
+
+_UIDS = _collections.defaultdict(int)
+# the Keras class each host class stands for (names are derived from the reference's class names)
+_KERAS_CLASS = {"LinearUpsample": "LinearUpsample", "MaxDownsample": "MaxDownsample"}
+
+
+def to_snake_case(name: str) -> str:
+    """tf.python.keras.utils.generic_utils.to_snake_case."""
+    intermediate = _re.sub("(.)([A-Z][a-z0-9]+)", r"\1_\2", name)
+    insecure = _re.sub("([a-z])([A-Z])", r"\1_\2", intermediate).lower()
+    return insecure if insecure[0] != "_" else "private" + insecure
+
+
+def unique_layer_name(cls_name: str) -> str:
+    base = to_snake_case(cls_name)
+    n = _UIDS[base]
+    _UIDS[base] += 1
+    return base if n == 0 else f"{base}_{n}"
+
+
+def reset_uids():
+    _UIDS.clear()
+
+
 class Layer:
     def __init__(self, name: Optional[str] = None, **kwargs):
-        self.name = name or type(self).__name__.lower()
+        self.name = name or unique_layer_name(_KERAS_CLASS.get(type(self).__name__, type(self).__name__))
         self.built = False
         self._vars: List[Variable] = []
 

@@ -272,22 +272,107 @@ class Model(Layer):
             out["vae.out.kernel"], out["vae.out.bias"] = v.out.kernel, v.out.bias
         return out
 
-    # ---- checkpoints (train.py:99-100 load_weights, :199-201 save_weights).  h5py is not in this image, so the file is
-    # a NumPy .npz with this repo's structural names (Keras layouts, fp32) plus the `epoch` variable (model.py:29);
-    # oracle/run_reference.py::load_params holds the mapping to the reference's attribute tree.
+    # ---- checkpoints (train.py:99-100 load_weights, :199-201 save_weights)
+    # The reference calls Keras' `save_weights('chkpt.hdf5')` on a subclassed model: an HDF5 file with one group per
+    # top-level layer (`model.layers` = encoder, decoder, variational_autoencoder; attribute `layer_names`), each with
+    # its `weight_names` attribute and one dataset per weight, written / read back TOPOLOGICALLY (layers in order,
+    # weights in `layer.weights` order; hdf5_format.save_weights_to_hdf5_group / load_weights_from_hdf5_group).  The
+    # model's own `epoch` variable (model.py:29) is not part of `model.layers` and so not in Keras' file.
+    # `keras_weight_groups()` reproduces that structure — layer names by Keras' per-class counters, weight names
+    # `<scope path>/<var>:0`, Keras layouts, fp32.  With h5py it is written as that HDF5 file; h5py is NOT in this image, so
+    # here the same structure goes into a NumPy .npz (keys '<layer>/<weight name>', '__layer_names__',
+    # '__weight_names__/<layer>', plus '__epoch__'), which tools/npz_to_keras_h5.py turns into the .hdf5 on a machine
+    # that has h5py.  TF itself cannot run here, so the names are restated from Keras' rules, not verified against it;
+    # loading is topological, like Keras', so it does not depend on them.
+    def keras_weight_groups(self):
+        """[(top-level layer name, [(Keras weight name, tensor), ...]), ...] in `model.layers` / `layer.weights` order."""
+        groups = []
+        for top in self._sublayers():
+            items = []
+
+            def walk(layer, scope):
+                for v in layer._vars:
+                    items.append((f"{scope}/{v.name}:0", v.tensor))
+                for sub in layer._sublayers():
+                    walk(sub, f"{scope}/{sub.name}")
+
+            walk(top, f"{self.name}/{top.name}")
+            if items:
+                groups.append((top.name, items))
+        return groups
+
     def save_weights(self, filepath):
         import numpy as np
-        arrs = {k: t.detach().cpu().numpy() for k, t in self.named_variables().items()}
-        arrs["__epoch__"] = np.asarray(int(self.epoch), dtype=np.int64)
+        groups = self.keras_weight_groups()
+        if str(filepath).endswith((".h5", ".hdf5", ".keras")):
+            try:
+                import h5py
+            except ImportError:
+                h5py = None
+            if h5py is not None:
+                with h5py.File(filepath, "w") as f:
+                    f.attrs["layer_names"] = [n.encode("utf8") for n, _ in groups]
+                    f.attrs["backend"] = b"tensorflow"
+                    f.attrs["keras_version"] = b"2.2.4-tf"
+                    for lname, items in groups:
+                        g = f.create_group(lname)
+                        g.attrs["weight_names"] = [wn.encode("utf8") for wn, _ in items]
+                        for wn, t in items:
+                            g.create_dataset(wn, data=t.detach().cpu().numpy())
+                return
+            raise ImportError("b3d: writing Keras' HDF5 container needs h5py (not in this image); save to a '.npz' path "
+                              "and convert with tools/npz_to_keras_h5.py")
+        arrs = {"__layer_names__": np.array([n for n, _ in groups]),
+                "__epoch__": np.asarray(int(self.epoch), dtype=np.int64)}
+        for lname, items in groups:
+            arrs[f"__weight_names__/{lname}"] = np.array([wn for wn, _ in items])
+            for wn, t in items:
+                arrs[f"{lname}/{wn}"] = t.detach().cpu().numpy()
         with open(filepath, "wb") as f:
             np.savez(f, **arrs)
 
     def load_weights(self, filepath):
+        """Topological load (Keras: by_name=False): the file's layers in order onto this model's weighted top-level
+        layers, each layer's weights in order; shapes are checked.  Also reads the round-1 structural-name .npz."""
         import numpy as np
-        with np.load(filepath) as z:
-            self.load_named_weights({k: torch.from_numpy(z[k]) for k in z.files if k != "__epoch__"})
-            if "__epoch__" in z.files:
-                self.epoch.assign(int(z["__epoch__"]))
+        groups = self.keras_weight_groups()
+        saved = None
+        try:
+            z = np.load(filepath, allow_pickle=False)
+        except Exception:        # not an .npz: Keras' HDF5
+            import h5py          # raises ImportError with a clear message when absent
+            with h5py.File(filepath, "r") as f:
+                lnames = [n.decode("utf8") if isinstance(n, bytes) else n for n in f.attrs["layer_names"]]
+                saved = []
+                for ln in lnames:
+                    wns = [n.decode("utf8") if isinstance(n, bytes) else n for n in f[ln].attrs["weight_names"]]
+                    if wns:
+                        saved.append((ln, [torch.from_numpy(np.asarray(f[ln][wn])) for wn in wns]))
+        else:
+            with z:
+                if "__layer_names__" not in z.files:          # round-1 file: this repo's structural names
+                    self.load_named_weights({k: torch.from_numpy(z[k]) for k in z.files if k != "__epoch__"})
+                    if "__epoch__" in z.files:
+                        self.epoch.assign(int(z["__epoch__"]))
+                    return
+                saved = [(str(ln), [torch.from_numpy(z[f"{ln}/{wn}"]) for wn in z[f"__weight_names__/{ln}"]])
+                         for ln in z["__layer_names__"]]
+                if "__epoch__" in z.files:
+                    self.epoch.assign(int(z["__epoch__"]))
+        if len(saved) != len(groups):
+            raise ValueError(f"You are trying to load a weight file containing {len(saved)} layers into a model with "
+                             f"{len(groups)} layers.")
+        with torch.no_grad():
+            for (ln, vals), (mn, items) in zip(saved, groups):
+                if len(vals) != len(items):
+                    raise ValueError(f"Layer {mn} expects {len(items)} weights, but the saved weights have {len(vals)} "
+                                     f"elements.")
+                for src, (wn, t) in zip(vals, items):
+                    if tuple(src.shape) != tuple(t.shape):
+                        raise ValueError(f"{wn}: shape {tuple(src.shape)} != {tuple(t.shape)}")
+                    t.copy_(src.to(device=t.device, dtype=t.dtype))
+        if self._flat is not None:
+            ops.repack_all(self._flat)
 
     def load_named_weights(self, params):
         nv = self.named_variables()

@@ -312,6 +312,16 @@ class TrainLog:
             with open(os.path.join(save_folder, 'train.log'), 'w') as f:
                 f.write(','.join(self.HEADER) + '\n')
 
+    @staticmethod
+    def checkpoint_name() -> str:
+        """'chkpt.hdf5' (train.py:201) when h5py can write Keras' container, else the same structure as 'chkpt.npz'
+        (Model.save_weights)."""
+        try:
+            import h5py  # noqa: F401
+            return 'chkpt.hdf5'
+        except ImportError:
+            return 'chkpt.npz'
+
     def end_epoch(self, epoch, lr, train, val, model=None):
         """train / val: (loss, macro_dice, micro_dice).  Returns False when training should stop (patience)."""
         import os
@@ -323,7 +333,7 @@ class TrainLog:
             self.best_val_dice, self.patience = float(val[1]), 0
             if self.save_folder and model is not None:
                 model.epoch.assign(epoch)
-                model.save_weights(os.path.join(self.save_folder, 'chkpt.npz'))
+                model.save_weights(os.path.join(self.save_folder, self.checkpoint_name()))
             return True
         if self.patience == self.patience_limit:
             return False

@@ -191,6 +191,10 @@ def measure_step_classes(b3d, torch, model, opt, xd, yd, pk):
     b3d.train_step(*args, xd, yd)
     torch.cuda.synchronize()
     with ops.profile_calls() as rows:
+        # the host needs ~30 ms to issue the ~400 calls of an eager step, the GPU ~15 ms to run them: without a head
+        # start the GPU idles between calls and every event pair also measures launch latency (round-2 numbers were
+        # 1.7x the ncu durations).  A spin kernel of ~80 ms lets the host run ahead, so the calls execute back to back.
+        torch.cuda._sleep(int(1.6e8))
         b3d.train_step(*args, xd, yd)
         torch.cuda.synchronize()
     agg = {}
@@ -207,7 +211,8 @@ def measure_step_classes(b3d, torch, model, opt, xd, yd, pk):
     cls = lambda pre: [v for k, v in conv.items() if k.startswith(pre)]
     tf = lambda vs: (sum(v[2] for v in vs) / 1e12) / (sum(v[1] for v in vs) / 1e3) if vs and sum(v[1] for v in vs) > 0 else None
     k3 = [v for k, v in conv.items() if k.startswith("conv_k3_") and not k.endswith("wgrad")]
-    out = {"how": "one eager step, CUDA events around every C-ABI call (includes the call's memsets / helper kernels)",
+    out = {"how": "one eager step queued behind an 80 ms spin kernel (the host runs ahead, calls execute back to back), "
+                  "CUDA events around every C-ABI call (includes the call's memsets / helper kernels)",
            "abi_calls": len(rows), "sum_ms": tot,
            "k3_fwd_dgrad_tflops": tf(k3), "k3_wgrad_tflops": tf(cls("conv_k3_wgrad")),
            "all_conv_tflops": tf(list(conv.values())),

@@ -343,8 +343,20 @@ def test_checkpoint_roundtrip_and_train_log(b3d, dev, tmp_path):
     b3d.keras_compat.set_seed(77)
     other = b3d.Model()
     other(torch.zeros((1,) + crop + (2,), device=dev), training=False, inference=False)
-    other.load_weights(str(tmp_path / "chkpt.npz"))
+    ck = tmp_path / b3d.TrainLog.checkpoint_name()
+    other.load_weights(str(ck))
     assert int(other.epoch) == 3
+    # the container mirrors Keras' HDF5 layout (model.layers in order, layer.weights in order, Keras-style names)
+    groups = model.keras_weight_groups()
+    assert [g[0].rstrip("_0123456789") for g in groups] == ["encoder", "decoder", "variational_autoencoder"]
+    assert sum(len(g[1]) for g in groups) == 260
+    first = groups[0][1][0][0]
+    assert first.startswith("model") and "/encoder" in first and first.endswith("/kernel:0") and "resnet_block" in first
+    if ck.suffix == ".npz":
+        import numpy as np
+        with np.load(ck) as z:
+            assert [str(n) for n in z["__layer_names__"]] == [g[0] for g in groups]
+            assert all(f"{ln}/{wn}" in z.files for ln, items in groups for wn, _ in items)
     nv0, nv1 = model.named_variables(), other.named_variables()
     assert all(torch.equal(nv0[k], nv1[k]) for k in nv0)
     with torch.no_grad():
