@@ -60,6 +60,13 @@ CONV_CASES = [
     ((8, 8, 16), [32, 32], 32, 3, 2, False),
     ((4, 8, 8), [32], 16, 3, 2, True),               # transposed
     ((4, 4, 8), [64, 64], 32, 3, 2, True),
+    # shapes of the kh-folded TS weight gradient (conv_tc_wgrad_ts.cu; off by default, B3D_WGRAD_TSF=1 in the environment
+    # of the test run selects it): all 9 (kd, kw) pairs per CTA | one kd | one pair; several sources
+    ((8, 16, 8), [16], 32, 3, 1, False),
+    ((6, 10, 24), [48], 16, 3, 1, False),            # 432 accumulator columns, partial tiles in d and h
+    ((8, 8, 16), [64], 32, 3, 1, False),             # N' = 192, one pair per CTA
+    ((4, 8, 16), [32, 32, 32], 32, 3, 1, False),     # three sources, 288 columns
+    ((4, 6, 8), [16, 32], 16, 3, 1, False),          # unequal sources
 ]
 
 
