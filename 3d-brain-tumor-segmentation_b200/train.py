@@ -154,6 +154,7 @@ class DataParallel:
         self.side = torch.cuda.Stream() if self.flat.grad.is_cuda else None
         self.buckets = self.plan_buckets(self.flat, n_buckets)
         self._pending = [0] * len(self.buckets)
+        self._seen = set()
         self._owner = {}
         for bi, (lo, hi, members) in enumerate(self.buckets):
             for t in members:
@@ -180,6 +181,7 @@ class DataParallel:
 
     def begin_backward(self):
         self._pending = [len(m) for _, _, m in self.buckets]
+        self._seen = set()
         self._active = True
 
     def _reduce(self, bi):
@@ -195,6 +197,13 @@ class DataParallel:
     def _on_grad(self, param):
         if not self._active:
             return
+        # a parameter can be announced twice in one backward — by the kernel that wrote its gradient straight into the
+        # flat buffer (FlatParams.notify) AND by autograd's post-accumulate hook (measured on torch 2.11: every
+        # parameter, although those backward functions return None for it); counting both made every bucket's
+        # all-reduce start when only HALF its gradients existed and run a second time in finish_backward
+        if id(param) in self._seen:
+            return
+        self._seen.add(id(param))
         bi = self._owner[id(param)]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:

@@ -72,7 +72,21 @@ def _worker(rank, world, port, q):
     dp.finish_backward()
     expect = [float(sum((r + 1) * (i + 1) for r in range(world))) for i in range(len(vs))]
     ok = all(torch.all(v.tensor.grad == e) for v, e in zip(vs, expect)) and opt.grad_scale == 1.0 / world
-    q.put((rank, bool(ok) and synced))
+    # overlap scheduling: every parameter announced TWICE (direct-write callback + autograd's post-accumulate hook, as
+    # seen on torch 2.11) must still count once — each bucket is reduced exactly once, and only when complete
+    dp.overlap = True
+    calls = []
+    real = dp._reduce
+    dp._reduce = lambda bi: (calls.append((bi, [v.tensor.grad.flatten()[0].item() for v in vs])), real(bi))[1]
+    dp.begin_backward()
+    for i, v in enumerate(vs):
+        v.tensor.grad.fill_(float((rank + 1) * (i + 1)))
+        dp._on_grad(v.tensor)
+        dp._on_grad(v.tensor)
+    dp.finish_backward()
+    ok2 = sorted(bi for bi, _ in calls) == list(range(len(dp.buckets)))
+    ok2 = ok2 and all(torch.all(v.tensor.grad == e) for v, e in zip(vs, expect))
+    q.put((rank, bool(ok) and synced and bool(ok2)))
     dist.destroy_process_group()
 
 
