@@ -124,6 +124,8 @@ def test_two_gpu_dp_step_equals_single_gpu_step():
             # same kernels, same rounding points; the difference is the summation order of the all-reduce and of the
             # per-sample partial sums (fp32), amplified by the network's conditioning at 32^3
             assert v["loss_rel"] < 5e-5, (objective, v)
-            assert v["grad_rel"] < 1e-2, (objective, v)
+            # two runs of the SAME single-GPU step differ by 4-6e-3 here (tools/dp_debug2.py: atomics order decides
+            # 16-bit rounding ties); a missed or doubled bucket all-reduce shows as 0.5-1.0
+            assert v["grad_rel"] < 2e-2, (objective, v)
             assert v["replicas_equal"] and v["graph_unchanged_by_warmup"], (objective, v)
             assert 0.0 < v["moved"] < 1e-3 and 0.0 < v["graph_moved"] < 1e-3, (objective, v)
