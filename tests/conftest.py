@@ -27,5 +27,6 @@ def b3d():
 @pytest.fixture(scope="session")
 def dev():
     import torch
-    assert torch.cuda.is_available()
+    if not torch.cuda.is_available():      # `-m gpu` on a CPU-only runner: skip, do not error
+        pytest.skip("needs a CUDA device")
     return torch.device("cuda:0")
