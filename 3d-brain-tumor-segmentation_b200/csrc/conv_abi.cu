@@ -539,6 +539,45 @@ static bool wgrad_tsf_on() {
   }
   return on == 1;
 }
+// Data gradient of a stride-1 conv whose INPUT was a virtual channel concat: dx comes out as one compact tensor per
+// concatenated piece (dx0 .. dx3, channel counts multiples of 16 adding up to the layer's Cin) instead of one tensor the
+// framework would have to slice — and copy — afterwards.
+extern "C" int b3d_conv3d_dgrad_p16_split(const DLTensor* dy_, const DLTensor* w_, DLTensor* dx0_, DLTensor* dx1_,
+                                          DLTensor* dx2_, DLTensor* dx3_, int accumulate, const DLTensor* wpacked_,
+                                          void* stream) {
+  const DLTensor* xs[4] = {dy_, nullptr, nullptr, nullptr};
+  DLTensor* ds[4] = {dx0_, dx1_, dx2_, dx3_};
+  TcSources src;
+  P16View first;
+  int ctot;
+  B3D_TRY(p16_sources(xs, &src, &first, &ctot));
+  TView w, d[4];
+  int k;
+  B3D_TRY(weight_view(w_, &w, &k));
+  B3D_REQUIRE(wpacked_ != nullptr, B3D_ERR_ARG, "conv (P16): packed weights required (tcgen05 path only)");
+  int n = 0, cin = 0;
+  ConvGeom g0;
+  memset(&g0, 0, sizeof(g0));
+  for (int i = 0; i < 4 && ds[i] != nullptr; ++i, ++n) {
+    B3D_TRY(view(ds[i], DT_F32, 5, false, "dx piece", &d[i]));
+    B3D_REQUIRE(d[i].shape[4] % 16 == 0 && ((uintptr_t)d[i].p & 31) == 0, B3D_ERR_LAYOUT,
+                "dgrad (split): pieces need channels %% 16 == 0 and 32-byte alignment");
+    for (int q = 0; q < 4; ++q)
+      B3D_REQUIRE(d[i].shape[q] == d[0].shape[q], B3D_ERR_SHAPE, "dgrad (split): pieces differ in batch / space");
+    cin += (int)d[i].shape[4];
+    g0.yd[i] = (float*)d[i].p; g0.yde[i] = cin;
+  }
+  B3D_REQUIRE(n >= 1, B3D_ERR_ARG, "dgrad (split): at least one piece");
+  TView dx = d[0];                       // the virtual whole: same batch / space, all channels
+  dx.shape[4] = cin; dx.pitch = cin; dx.numel = d[0].numel / d[0].shape[4] * cin;
+  const TView dy = virtual_view(first, ctot);
+  ConvGeom g;
+  B3D_TRY(geom_dgrad(g, dy, w, dx, k, 1, 0));
+  g.accumulate = accumulate;
+  if (n > 1) { g.nyd = n; for (int i = 0; i < n; ++i) { g.yd[i] = g0.yd[i]; g.yde[i] = g0.yde[i]; } }
+  return run(g, dy, w, nullptr, dx, nullptr, 1, nullptr, wpacked_, (cudaStream_t)stream, &src);
+}
+
 extern "C" int b3d_conv3d_wgrad_p16_plan(int k, int stride, int transposed, int cin, int cout, int w_sp) {
   const WgradPlan p = wgrad_plan(k, stride, transposed, cin, cout);
   if (p.kind != 1 || cin % 8 != 0 || cout % 8 != 0) return 0;

@@ -22,6 +22,11 @@ struct ConvGeom {
   // depth-slab inference with fused GroupNorm statistics: the output tensor is voxels [stat_off, stat_off + Do*Ho*Wo) of
   // a volume of stat_total voxels whose 1/groups chunks the statistics are taken over (0 / 0: the tensor is the volume)
   long long stat_off, stat_total;
+  // output split by channel ranges into separate compact tensors (the data gradient of a conv whose input is a virtual
+  // concat: one tensor per concatenated piece, no slicing copies afterwards).  nyd = 0: one output (y, yp).
+  int nyd;
+  float* yd[4];
+  int yde[4];               // cumulative channel end of piece i (multiples of 16)
 };
 
 // outer-product form:  dw[t][a][b] = sum_{n,o} big[n, s*o+t-pad, a] * small[n, o, b]

@@ -91,6 +91,9 @@ struct TcParams {
   int accumulate, groups;
   long long vpc;       // voxels per GN chunk (of the tensor y is stored as)
   long long voff;      // first voxel of y inside the whole volume (depth slabs; 0 otherwise)
+  // output split into up to 4 compact tensors by channel ranges (stride-1 convs; nyd = 0: y / yp)
+  int nyd, yde[4];
+  float* yd[4];
   // stride-2 family (conv_s2.cu): the kernel works on the COARSE grid [D,H,W];
   //   s2d: x is the fine tensor [B,2D,2H,2W,Csub]; virtual input channel k' = parity*Csub + c  (space-to-depth)
   //   d2s: y is the fine tensor [B,2D,2H,2W,Csub]; virtual output column n' = parity*Csub + c (depth-to-space)
@@ -537,7 +540,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
     const int ph = row >> 3, pwv = row & 7;
     const long long S = (long long)prm.D * prm.H * prm.W * (prm.d2s ? 8 : 1);   // voxels of y per sample
     // global-average-pool partial sums: kept in registers across the tiles of one sample when N <= 64
-    constexpr bool kGapPersist = C::N <= 64;
+    constexpr bool kGapPersist = C::N <= 32;      // (N = 64 would hold 64 accumulator registers and spill)
     constexpr int NJ = C::N / 16;
     float gsum[kGapPersist ? NJ : 1][16];
 #pragma unroll
@@ -583,6 +586,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
         }
         const int ncol = min(16, prm.cout_real - (nsp * C::N + j * 16));    // real output channels in this block
         if (ncol <= 0) continue;
+        float* ybase = prm.y;
+        long long ypitch = prm.yp;
+        if (prm.nyd > 1) {                  // which output piece this 16-column block belongs to
+          int si = 0;
+          while (si + 1 < prm.nyd && ycol >= prm.yde[si]) ++si;
+          const int c0 = si > 0 ? prm.yde[si - 1] : 0;
+          ybase = prm.yd[si]; ypitch = prm.yde[si] - c0; ycol -= c0;
+        }
         float bv[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) bv[i] = (prm.bias != nullptr && i < ncol) ? __ldg(prm.bias + ycol + i) : 0.f;
@@ -595,7 +606,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
           const long long vox =
               prm.d2s ? ((long long)(2 * d + ep_d) * (2 * prm.H) + (2 * h + ep_h)) * (2 * prm.W) + (2 * w + ep_w)
                       : ((long long)d * prm.H + h) * prm.W + w;
-          float* yp = prm.y + ((long long)b * S + vox) * prm.yp + ycol;
+          float* yp = ybase + ((long long)b * S + vox) * ypitch + ycol;
           if (prm.stats != nullptr) {
             // the GroupNorm chunk of this patch's voxels; when any lane moves on to another chunk the whole warp
             // flushes its running sums (warp-reduced: two fp64 atomics per warp, not per lane)
@@ -671,14 +682,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
           }
         }
         if (!kGapPersist && prm.gap != nullptr) {
-          // wide layers: column sums flushed per tile (a tile lies in one sample)
+          // wide layers: column sums flushed per tile (a tile lies in one sample) — into the CTA's shared-memory sums
+          // when there is one sample (N = 64; written out once at the end), else straight to global memory
+          const bool to_smem = C::N <= 64 && prm.B == 1;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float a = warp_sum(gs[i]);
-            if (lane == 0 && nsp * C::N + j * 16 + i < prm.cout_real)
-              atomicAdd(&prm.gap[(long long)b * prm.cout_real + nsp * C::N + j * 16 + i], a);
+            if (lane == 0 && nsp * C::N + j * 16 + i < prm.cout_real) {
+              if (to_smem) atomicAdd(&cta_gap[j * 16 + i], a);
+              else atomicAdd(&prm.gap[(long long)b * prm.cout_real + nsp * C::N + j * 16 + i], a);
+            }
             gs[i] = 0.f;
           }
+          if (to_smem && lane == 0) *cta_gap_b = b;
         }
       }
       // release the accumulator stage as soon as TMEM has been read
@@ -747,11 +763,15 @@ __global__ void __launch_bounds__(256)
   const long long e0 = (long long)g * L;           // element offset inside the sample (channel = (e0 + e) % C)
   double d[2] = {0.0, 0.0};
   for (long long e = seg0 + threadIdx.x * 4LL; e < seg1; e += 256 * 4) {
-    float4 v = ld_stream(reinterpret_cast<const float4*>(ws + off + e));
-    for (int z = 1; z < ksplit; ++z) {
-      const float4 t = ld_stream(reinterpret_cast<const float4*>(ws + (long long)z * ws_slice + off + e));
-      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-    }
+    // all slices' loads are issued before the first add (ksplit <= 8): one L2 round trip per element, not ksplit
+    float4 t[8];
+#pragma unroll
+    for (int z = 0; z < 8; ++z)
+      if (z < ksplit) t[z] = ld_stream(reinterpret_cast<const float4*>(ws + (long long)z * ws_slice + off + e));
+    float4 v = t[0];
+#pragma unroll
+    for (int z = 1; z < 8; ++z)
+      if (z < ksplit) { v.x += t[z].x; v.y += t[z].y; v.z += t[z].z; v.w += t[z].w; }
     const int c = (int)((e0 + e) % C);
     if (bias != nullptr) { v.x += bias[c]; v.y += bias[c + 1]; v.z += bias[c + 2]; v.w += bias[c + 3]; }
     *reinterpret_cast<float4*>(yc + e) = v;
@@ -1061,6 +1081,8 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   p.voff = g.stat_total > 0 ? g.stat_off : 0;
   p.s2d = q.s2d; p.d2s = q.d2s; p.Csub = q.Csub;
   p.Din = g.Di; p.doff = g.doff;
+  p.nyd = g.nyd;
+  for (int i = 0; i < g.nyd && i < 4; ++i) { p.yd[i] = g.yd[i]; p.yde[i] = g.yde[i]; }
   p.cin_real = g.mode == CONV_S1 ? g.Cin : q.Cin; p.cout_real = g.mode == CONV_UP ? q.Cout : g.Cout; p.act = g.act;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1081,6 +1103,7 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   const int ctas = (int)(grid.x * grid.y);
   float* ws = nullptr;
   if (ctas * 2 <= sm_count() && nchunks >= 8 && g.act == 0 && !g.accumulate && g.Cout % 16 == 0 && g.yp == g.Cout &&
+      g.nyd <= 1 &&
       (S * g.Cout) % 32 == 0 && (stats == nullptr || p.groups == 8 || S % p.groups == 0) &&
       (stats == nullptr || g.stat_total == 0 || (g.B == 1 && (g.stat_total * g.Cout) % (4LL * p.groups) == 0))) {
     int ks = sm_count() / ctas;

@@ -220,11 +220,12 @@ def _os_env_flag(name, default):
 # is not materialised at all: the autograd-visible tensor is then a zero-stride placeholder of the logical shape
 # (`_b3d_virtual`) that carries the twin(s); `materialize()` rebuilds fp32 for the rare consumer that needs it.
 P16 = {"on": True}
-# the pointwise and the first 3x3x3 conv of a ResnetBlock read the same tensor: their data gradients can be summed in the
-# second kernel's epilogue (Conv3dFn.backward, `grad_box`) instead of an autograd add pass.  OFF by default: measured on
-# B200 (A/B, same box, 128^3 step) 17.03 ms with it vs 16.53 ms without — the read-modify-write in the conv epilogue costs
-# more than the 16 add launches it removes (0.32 ms), as in round 1.  B3D_SHARE_DGRAD=1 switches it on.
-SHARE_DGRAD = {"on": _os_env_flag("B3D_SHARE_DGRAD", False)}
+# the pointwise and the first 3x3x3 conv of a ResnetBlock read the same tensor: their data gradients are summed in the
+# second kernel's epilogue (Conv3dFn.backward, `grad_box`: accumulate = 1, 256-bit read-modify-write by 12 epilogue
+# warps) instead of an autograd add pass.  Speed-neutral on B200 (A/B on one box, 128^3 step: 14.58 ms with it, 14.62 ms
+# without; with the round-1 4-warp epilogue it cost 0.5 ms) and it takes 16 torch `add` launches off the path.
+# B3D_SHARE_DGRAD=0 switches it off.
+SHARE_DGRAD = {"on": _os_env_flag("B3D_SHARE_DGRAD", True)}
 # the encoder's dense connections list the previous block output twice; inside a Model the duplicate is
 # dropped and its weight slice folded into the other one (ops.FoldDupFn) — exact.  B3D_DEDUP=0 for A/B runs
 DEDUP = {"on": _os_env_flag("B3D_DEDUP", True)}
@@ -317,6 +318,18 @@ def want_wgrad_twin(td, grad_enabled):
     """A second (bf16) twin is written when the forward operand type is fp16 and a backward pass will follow.
     (`grad_enabled` is sampled by the caller OUTSIDE the autograd Function: inside `forward` grad mode is always off.)"""
     return td == torch.float16 and bool(grad_enabled)
+
+
+_ZERO1 = {}
+
+
+def _zero_placeholder(shape, device):
+    """A zero gradient of `shape` without memory or a kernel per use (one cached scalar per device, zero strides): what
+    autograd is handed when the real gradient travels through a gradient box; safe to be ADDED to a real gradient."""
+    z = _ZERO1.get(device)
+    if z is None:
+        z = _ZERO1[device] = torch.zeros(1, device=device, dtype=_f32)
+    return z.expand(tuple(shape))
 
 
 def _grad_placeholder(like):
@@ -484,6 +497,9 @@ class Conv3dFn(Function):
             _call("b3d_conv3d_fwd", x, w, bias, y, stride, int(transposed), int(act), stats, gn_groups or 1, gap, 0, wp)
         ctx.save_for_backward(None if use16 and is_virtual(x) else x, w, y if act else None)
         ctx.srcs = srcs if srcs is not None and td is not None and srcs[0].dtype == td else None
+        # input = a virtual concat (VirtualConcatFn): its data gradient is written piece by piece (stride-1 convs)
+        ctx.pieces = getattr(x, "_b3d_pieces", None) if (stride == 1 and not transposed) else None
+        ctx.gradbox = getattr(x, "_b3d_gradbox", None) if ctx.pieces is not None else None
         ctx.srcs_w = sources_w(x) if ctx.srcs is not None else None
         ctx.xshape = tuple(x.shape)
         ctx.nv = nv
@@ -548,8 +564,20 @@ class Conv3dFn(Function):
             # data gradient to run writes a fresh buffer and hands it to autograd, the second ADDS into that buffer in
             # its epilogue (accumulate = 1) and returns no gradient — same sum, no separate add pass over the tensor.
             box, acc = ctx.grad_box, 0
+            split = ctx.pieces is not None and ctx.gradbox is not None and tcd and dy16 is not None
             if box is not None and "dx" in box:
                 dx_buf, acc = box.pop("dx"), 1
+            elif split:
+                # one compact tensor per piece of the concatenated input, handed to VirtualConcatFn.backward through
+                # the input's gradient box; autograd itself only sees a zero placeholder
+                dx_buf = [torch.empty(ctx.xshape[:-1] + (c,), device=w.device, dtype=_f32) for c in ctx.pieces]
+                parts = ctx.gradbox.setdefault("parts", [])
+                parts.append(dx_buf)
+                if box is not None:
+                    box["dx"] = dx_buf
+                # the first depositor hands autograd a zero placeholder (so that VirtualConcatFn.backward runs); later
+                # ones return nothing — two placeholders would be "summed" by a full-size torch kernel
+                dx = _zero_placeholder(ctx.xshape, w.device) if len(parts) == 1 else None
             else:
                 dx_buf = torch.empty(ctx.xshape, device=w.device, dtype=_f32)
                 if box is not None:
@@ -557,7 +585,11 @@ class Conv3dFn(Function):
                 dx = dx_buf
             wp = pack_weights(w, True, stride, transposed) if tcd else None
             _tag_conv(w, ctx.nv, stride, transposed)
-            if tcd and dy16 is not None:
+            if isinstance(dx_buf, list):
+                if not (tcd and dy16 is not None):
+                    raise RuntimeError("b3d: a split data gradient needs the P16 tensor-core path for both convs of a block")
+                _call("b3d_conv3d_dgrad_p16_split", dy16, w, *_pad4(dx_buf), acc, wp)
+            elif tcd and dy16 is not None:
                 _call("b3d_conv3d_dgrad_p16", dy16, w, dx_buf, stride, int(transposed), acc, wp)
             else:
                 dy = materialize(dy)
@@ -1166,14 +1198,32 @@ class VirtualConcatFn(Function):
         wl = [sources_w(t) for t in xs]
         wtwins = [tw for l in wl for tw in l] if all(l is not None for l in wl) else None
         ctx.C = C
-        return virtual(tuple(xs[0].shape[:-1]) + (sum(C),), twins[0], twins, wtwins)
+        out = virtual(tuple(xs[0].shape[:-1]) + (sum(C),), twins[0], twins, wtwins)
+        # stride-1 convs reading `out` write their data gradient as one compact tensor per piece into this box
+        # (Conv3dFn.backward) instead of one tensor that would have to be sliced — and copied — here
+        out._b3d_pieces = tuple(C) if (len(C) <= 4 and all(c % 16 == 0 for c in C)) else None
+        out._b3d_gradbox = ctx.box = {}
+        return out
 
     @staticmethod
     def backward(ctx, d):
-        d = materialize(d)
+        parts = ctx.box.pop("parts", None)
+        real = d is not None and not (d.dim() > 0 and all(st == 0 for st in d.stride()))   # not just the zero placeholder
+        if real:
+            d = materialize(d)
         outs, o = [], 0
         for i, c in enumerate(ctx.C):
-            outs.append(d[..., o:o + c] if ctx.needs_input_grad[i] else None)
+            g = None
+            if ctx.needs_input_grad[i]:
+                if parts:
+                    g = parts[0][i]
+                    for other in parts[1:]:
+                        g = g + other[i]
+                    if real:
+                        g = g + d[..., o:o + c]
+                elif real:
+                    g = d[..., o:o + c]
+            outs.append(g)
             o += c
         return tuple(outs)
 

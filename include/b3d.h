@@ -315,6 +315,10 @@ int b3d_conv3d_fwd_p16(const DLTensor* x0, const DLTensor* x1, const DLTensor* x
                        void* stream);
 int b3d_conv3d_dgrad_p16(const DLTensor* dy /*P16*/, const DLTensor* w, DLTensor* dx, int stride, int transposed,
                          int accumulate, const DLTensor* wpacked, void* stream);
+/* the same for a stride-1 conv whose input was a virtual channel concat: one compact dx tensor per concatenated piece */
+int b3d_conv3d_dgrad_p16_split(const DLTensor* dy /*P16*/, const DLTensor* w, DLTensor* dx0, DLTensor* dx1 /*nullable*/,
+                               DLTensor* dx2 /*nullable*/, DLTensor* dx3 /*nullable*/, int accumulate,
+                               const DLTensor* wpacked, void* stream);
 int b3d_conv3d_wgrad_p16(const DLTensor* x0, const DLTensor* x1, const DLTensor* x2, const DLTensor* x3,
                          const DLTensor* dy /*P16*/, DLTensor* dw, int stride, int transposed, DLTensor* scratch,
                          void* stream);
