@@ -136,6 +136,7 @@ SIGNATURES = {
     "b3d_unfold_dup": "TTiv",
     "b3d_conv3d_fwd_p16": "TTTTTTTiiiTiTiTv",
     "b3d_conv3d_dgrad_p16_split": "TTTTTTiTv",
+    "b3d_conv3d_dgrad_p16_block": "TTTTTTTTTTv",
     "b3d_conv3d_dgrad_p16": "TTTiiiTv",
     "b3d_conv3d_wgrad_p16": "TTTTTTiiTv",
     "b3d_gn_apply_p16": "TTTTTTTifiv",

@@ -578,6 +578,63 @@ extern "C" int b3d_conv3d_dgrad_p16_split(const DLTensor* dy_, const DLTensor* w
   return run(g, dy, w, nullptr, dx, nullptr, 1, nullptr, wpacked_, (cudaStream_t)stream, &src);
 }
 
+// Data gradient w.r.t. the input of a ResnetBlock from BOTH convs that read it (layers/resnet.py:118,133): the 3x3x3
+// conv (gradient dy, kernel w) and the pointwise conv (gradient dres, kernel w_pw) — one kernel: dres joins dy as a
+// further K segment that is multiplied with w_pw at the centre tap only.  dx as one compact tensor per piece of a
+// virtually concatenated input (one piece: the plain case).
+extern "C" int b3d_conv3d_dgrad_p16_block(const DLTensor* dy_, const DLTensor* dres_, const DLTensor* w_,
+                                          const DLTensor* wpw_, DLTensor* dx0_, DLTensor* dx1_, DLTensor* dx2_,
+                                          DLTensor* dx3_, const DLTensor* wpacked_, const DLTensor* wpacked_pw_,
+                                          void* stream) {
+  const DLTensor* xs[4] = {dy_, dres_, nullptr, nullptr};
+  DLTensor* ds[4] = {dx0_, dx1_, dx2_, dx3_};
+  TcSources src;
+  P16View first;
+  int ctot;
+  B3D_TRY(p16_sources(xs, &src, &first, &ctot));
+  B3D_REQUIRE(src.n == 2 && src.C[0] == src.C[1], B3D_ERR_SHAPE, "dgrad (block): dy and dres must have the same channels");
+  TView w, wpw, d[4], wp, wpc;
+  int k, k1;
+  B3D_TRY(weight_view(w_, &w, &k));
+  B3D_TRY(weight_view(wpw_, &wpw, &k1));
+  B3D_REQUIRE(k == 3 && k1 == 1, B3D_ERR_SHAPE, "dgrad (block): a 3x3x3 and a 1x1x1 kernel");
+  B3D_REQUIRE(wpacked_ != nullptr && wpacked_pw_ != nullptr, B3D_ERR_ARG, "dgrad (block): packed operands required");
+  int n = 0, cin = 0;
+  ConvGeom g;
+  float* yd[4];
+  int yde[4];
+  for (int i = 0; i < 4 && ds[i] != nullptr; ++i, ++n) {
+    B3D_TRY(view(ds[i], DT_F32, 5, false, "dx piece", &d[i]));
+    B3D_REQUIRE(d[i].shape[4] % 16 == 0 && ((uintptr_t)d[i].p & 31) == 0, B3D_ERR_LAYOUT,
+                "dgrad (block): pieces need channels %% 16 == 0 and 32-byte alignment");
+    for (int q = 0; q < 4; ++q)
+      B3D_REQUIRE(d[i].shape[q] == d[0].shape[q], B3D_ERR_SHAPE, "dgrad (block): pieces differ in batch / space");
+    cin += (int)d[i].shape[4];
+    yd[i] = (float*)d[i].p; yde[i] = cin;
+  }
+  B3D_REQUIRE(n >= 1, B3D_ERR_ARG, "dgrad (block): at least one piece");
+  TView dx = d[0];
+  dx.shape[4] = cin; dx.pitch = cin; dx.numel = d[0].numel / d[0].shape[4] * cin;
+  const int cb = src.C[0];                               // the block's filters
+  const TView dy = virtual_view(first, cb);
+  B3D_TRY(geom_dgrad(g, dy, w, dx, 3, 1, 0));            // the 3x3x3 part: checks kernel / channel / spatial agreement
+  B3D_REQUIRE(wpw.shape[3] == cin && wpw.shape[4] == cb, B3D_ERR_SHAPE, "dgrad (block): pointwise kernel shape");
+  B3D_REQUIRE(tc_conv_supported(g), B3D_ERR_UNSUPPORTED, "dgrad (block): shape not on the tcgen05 path");
+  B3D_TRY(view(wpacked_, DT_F32, 1, false, "wpacked", &wp));
+  B3D_TRY(view(wpacked_pw_, DT_F32, 1, false, "wpacked (pointwise)", &wpc));
+  B3D_REQUIRE((size_t)wp.numel == tc_packed_weight_elems(g), B3D_ERR_SHAPE, "wpacked: wrong size");
+  ConvGeom g1 = g;                                       // the pointwise layer's data-gradient geometry (size check)
+  g1.k = 1; g1.pad = 0; g1.flip = 0;
+  B3D_REQUIRE((size_t)wpc.numel == tc_packed_weight_elems(g1), B3D_ERR_SHAPE, "wpacked (pointwise): wrong size");
+  B3D_REQUIRE(tc_operand_type(g) != OP_TF32 && tc_operand_type(g1) == tc_operand_type(g), B3D_ERR_UNSUPPORTED,
+              "dgrad (block): 16-bit operands");
+  g.Cin = 2 * cb; g.xp = 2 * cb;                          // K = [dy | dres]
+  g.c_center = cb; g.wp_center = wpc.p;
+  if (n > 1) { g.nyd = n; for (int i = 0; i < n; ++i) { g.yd[i] = yd[i]; g.yde[i] = yde[i]; } }
+  return launch_conv_tc(g, (const float*)dy.p, (const float*)wp.p, nullptr, (float*)dx.p, nullptr, nullptr,
+                        (cudaStream_t)stream, &src);
+}
+
 extern "C" int b3d_conv3d_wgrad_p16_plan(int k, int stride, int transposed, int cin, int cout, int w_sp) {
   const WgradPlan p = wgrad_plan(k, stride, transposed, cin, cout);
   if (p.kind != 1 || cin % 8 != 0 || cout % 8 != 0) return 0;

@@ -24,6 +24,10 @@ struct ConvGeom {
   long long stat_off, stat_total;
   // output split by channel ranges into separate compact tensors (the data gradient of a conv whose input is a virtual
   // concat: one tensor per concatenated piece, no slicing copies afterwards).  nyd = 0: one output (y, yp).
+  // 3x3x3 stride-1 only: the last c_center input channels are multiplied with the packed 1x1x1 operand wp_center at the
+  // centre tap only (conv_tc.cu, TcParams::cfull); Cin counts them, the 3x3x3 packed operand does not
+  int c_center;
+  const void* wp_center;
   int nyd;
   float* yd[4];
   int yde[4];               // cumulative channel end of piece i (multiples of 16)

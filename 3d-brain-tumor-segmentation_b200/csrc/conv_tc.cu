@@ -91,6 +91,12 @@ struct TcParams {
   int accumulate, groups;
   long long vpc;       // voxels per GN chunk (of the tensor y is stored as)
   long long voff;      // first voxel of y inside the whole volume (depth slabs; 0 otherwise)
+  // centre-tap K segment (3x3x3 only): K chunks >= `cfull` are multiplied with the 1x1x1 operand `wpc` (packed like a
+  // k = 1 layer: [nsplit][chunk][1 tap][2 planes][N][T]) at the centre tap only — the data gradient of a ResnetBlock's
+  // pointwise conv computed inside the data gradient of its first 3x3x3 conv (both are gradients w.r.t. the block
+  // input: one kernel, one output, no add).  cfull = all chunks: no such segment.
+  int cfull;
+  const void* wpc;
   // output split into up to 4 compact tensors by channel ranges (stride-1 convs; nyd = 0: y / yp)
   int nyd, yde[4];
   float* yd[4];
@@ -428,15 +434,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
     if (lane == 0) {
       int ws = 0, wph = 0;
       const uint8_t* wsrc =
-          reinterpret_cast<const uint8_t*>(prm.wp) + ((size_t)nsp * nchunks_all + c_begin) * C::TAPS * C::TAP_BYTES;
+          reinterpret_cast<const uint8_t*>(prm.wp) + ((size_t)nsp * prm.cfull + c_begin) * C::TAPS * C::TAP_BYTES;
       constexpr int kStagesPerChunk = C::TAPS / C::TPS;
+      const uint8_t* wsrc_c = reinterpret_cast<const uint8_t*>(prm.wpc) +
+                              (size_t)nsp * (nchunks_all - prm.cfull) * C::TAP_BYTES;      // centre-tap segment
       for (int tile = tile0; tile < tile1; ++tile) {
-        for (int cs = 0; cs < nchunks * kStagesPerChunk; ++cs) {
-          mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
-          const uint32_t full = smem_u32(&w_full[ws]);
-          mbar_expect_tx(full, C::WST_BYTES);
-          bulk_g2s(smem_u32(wst + ws * C::WST_BYTES), wsrc + (size_t)cs * C::WST_BYTES, C::WST_BYTES, full);
-          if (++ws == C::WS) { ws = 0; wph ^= 1; }
+        for (int c = 0; c < nchunks; ++c) {
+          const int cg = c_begin + c;
+          if (cg >= prm.cfull) {          // one stage holding the single tap tile of this chunk
+            mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
+            const uint32_t full = smem_u32(&w_full[ws]);
+            mbar_expect_tx(full, C::TAP_BYTES);
+            bulk_g2s(smem_u32(wst + ws * C::WST_BYTES), wsrc_c + (size_t)(cg - prm.cfull) * C::TAP_BYTES, C::TAP_BYTES, full);
+            if (++ws == C::WS) { ws = 0; wph ^= 1; }
+            continue;
+          }
+          for (int st = 0; st < kStagesPerChunk; ++st) {
+            mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
+            const uint32_t full = smem_u32(&w_full[ws]);
+            mbar_expect_tx(full, C::WST_BYTES);
+            bulk_g2s(smem_u32(wst + ws * C::WST_BYTES), wsrc + (size_t)(c * kStagesPerChunk + st) * C::WST_BYTES,
+                     C::WST_BYTES, full);
+            if (++ws == C::WS) { ws = 0; wph ^= 1; }
+          }
         }
       }
     }
@@ -460,6 +480,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
         mbar_wait(smem_u32(&halo_full[hs]), hph);
         tc_fence_after();
         const uint64_t adesc0 = make_desc(halo_addr + hs * C::HALO_BYTES, C::HW * 16, C::RP * 16);
+        if (C::KS == 3 && c_begin + c >= prm.cfull) {
+          // centre-tap chunk: one N-wide MMA per output patch, A at the tap (1, 1, 1) of the halo
+          mbar_wait(smem_u32(&w_full[ws]), wph);
+          tc_fence_after();
+          const uint64_t bdesc = make_desc(wst_addr + ws * C::WST_BYTES, C::N * 16, 128);
+          if (leader) {
+#pragma unroll
+            for (int p = 0; p < C::P; ++p) {
+              const int pd = p / C::NW, pw = p % C::NW;
+              const uint32_t aoff = (uint32_t)(((pd + 1) * C::HH + 1) * C::RP + pw * 8 + 1);
+              const uint32_t dcol = dbase + (uint32_t)((C::FOLD ? C::acc_block(pd, pw) : p) * C::N);
+              const uint32_t acc_c = c > 0 ? 1u : 0u;      // (a split-K range may start inside the centre segment)
+              if (C::BF16) tc_mma_f16(dcol, adesc0 + aoff, bdesc, idesc, acc_c);
+              else tc_mma_tf32(dcol, adesc0 + aoff, bdesc, idesc, acc_c);
+            }
+            tc_commit(smem_u32(&w_empty[ws]));
+          }
+          __syncwarp();
+          if (++ws == C::WS) { ws = 0; wph ^= 1; }
+        } else
 #pragma unroll
         for (int st = 0; st < C::TAPS / C::TPS; ++st) {
           mbar_wait(smem_u32(&w_full[ws]), wph);
@@ -1081,6 +1121,8 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
   p.voff = g.stat_total > 0 ? g.stat_off : 0;
   p.s2d = q.s2d; p.d2s = q.d2s; p.Csub = q.Csub;
   p.Din = g.Di; p.doff = g.doff;
+  p.cfull = (q.Cin - (q.ks == 3 ? g.c_center : 0)) / C::CK;
+  p.wpc = g.wp_center;
   p.nyd = g.nyd;
   for (int i = 0; i < g.nyd && i < 4; ++i) { p.yd[i] = g.yd[i]; p.yde[i] = g.yde[i]; }
   p.cin_real = g.mode == CONV_S1 ? g.Cin : q.Cin; p.cout_real = g.mode == CONV_UP ? q.Cout : g.Cout; p.act = g.act;

@@ -36,10 +36,19 @@ class profile_calls:
         return False
 
 
+# One C-ABI call at a time per process: a call may launch several kernels that share library-owned state on ONE stream
+# (split-K conv + its finish kernel and the 64 MB workspace between them).  Real ranks are separate processes; the
+# virtual ranks of slab.run_virtual_ranks are THREADS on one stream, and ctypes drops the GIL during a call — without
+# the lock two threads' conv + finish pairs interleaved now and then (8 slabs: rel-L2 2.2e-3 instead of 6.1e-4, 1 run in 3).
+import threading as _thr
+_CALL_LOCK = _thr.Lock()
+
+
 def _call(name, *a):
     LAUNCHES["n"] += 1
     if not _PROF["on"]:
-        return call(name, *a)
+        with _CALL_LOCK:
+            return call(name, *a)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     rc = call(name, *a)
@@ -226,6 +235,10 @@ P16 = {"on": True}
 # without; with the round-1 4-warp epilogue it cost 0.5 ms) and it takes 16 torch `add` launches off the path.
 # B3D_SHARE_DGRAD=0 switches it off.
 SHARE_DGRAD = {"on": _os_env_flag("B3D_SHARE_DGRAD", True)}
+# ... and, better, computed by ONE kernel: the pointwise conv's incoming gradient joins the 3x3x3 conv's as a further K
+# segment that is used at the centre tap only (b3d_conv3d_dgrad_p16_block) — no pointwise data-gradient launch at all.
+# Needs SHARE_DGRAD (the two convs find each other through the block's grad_box).  B3D_FUSE_BLOCK_DGRAD=0 for A/B runs.
+FUSE_BLOCK_DGRAD = {"on": _os_env_flag("B3D_FUSE_BLOCK_DGRAD", True)}
 # the encoder's dense connections list the previous block output twice; inside a Model the duplicate is
 # dropped and its weight slice folded into the other one (ops.FoldDupFn) — exact.  B3D_DEDUP=0 for A/B runs
 DEDUP = {"on": _os_env_flag("B3D_DEDUP", True)}
@@ -512,6 +525,8 @@ class Conv3dFn(Function):
         f32_grad = not (ctx.srcs_w is not None and twin_dtype(True) == torch.bfloat16 and lib.b3d_conv3d_wgrad_p16_plan(
             k, stride, int(transposed), Cin, Cout, od[2]) != 0)
         ctx.mb = y._b3d_mb = {"bias": bias, "f32_grad": f32_grad}
+        if grad_box is not None and k == 1 and stride == 1 and not transposed:
+            grad_box["pw"] = {"mb": ctx.mb, "w": w}      # the block's pointwise conv: see FUSE_BLOCK_DGRAD
         outs = (y, stats, gap)
         ctx.mark_non_differentiable(*[t for t in (stats, gap) if t is not None])
         return outs
@@ -565,7 +580,17 @@ class Conv3dFn(Function):
             # its epilogue (accumulate = 1) and returns no gradient — same sum, no separate add pass over the tensor.
             box, acc = ctx.grad_box, 0
             split = ctx.pieces is not None and ctx.gradbox is not None and tcd and dy16 is not None
-            if box is not None and "dx" in box:
+            fused_pw = None
+            if (FUSE_BLOCK_DGRAD["on"] and box is not None and "pw" in box and "dx" not in box and k == 3 and stride == 1
+                    and not transposed and tcd and dy16 is not None and box["pw"]["mb"] is not mb
+                    and ctx.xshape[-1] % 16 == 0):
+                dres16 = box["pw"]["mb"].get("dy16")
+                if dres16 is not None and dres16.dtype == dy16.dtype and tuple(dres16.shape) == tuple(dy16.shape) and \
+                        tc_supported(box["pw"]["w"], 1, False, True):
+                    fused_pw = (dres16, box["pw"]["w"])
+            if box is not None and box.get("dx_fused"):
+                dx_buf = None                      # the 3x3x3 conv's kernel has already added this conv's part
+            elif box is not None and "dx" in box:
                 dx_buf, acc = box.pop("dx"), 1
             elif split:
                 # one compact tensor per piece of the concatenated input, handed to VirtualConcatFn.backward through
@@ -583,9 +608,17 @@ class Conv3dFn(Function):
                 if box is not None:
                     box["dx"] = dx_buf
                 dx = dx_buf
-            wp = pack_weights(w, True, stride, transposed) if tcd else None
+            wp = pack_weights(w, True, stride, transposed) if (tcd and dx_buf is not None) else None
             _tag_conv(w, ctx.nv, stride, transposed)
-            if isinstance(dx_buf, list):
+            if dx_buf is None:
+                _PROF["tag"] = None
+            elif fused_pw is not None:
+                bufs = dx_buf if isinstance(dx_buf, list) else [dx_buf]
+                _call("b3d_conv3d_dgrad_p16_block", dy16, fused_pw[0], w, fused_pw[1], *_pad4(bufs), wp,
+                      pack_weights(fused_pw[1], True, 1, False))
+                box.pop("dx", None)
+                box["dx_fused"] = True
+            elif isinstance(dx_buf, list):
                 if not (tcd and dy16 is not None):
                     raise RuntimeError("b3d: a split data gradient needs the P16 tensor-core path for both convs of a block")
                 _call("b3d_conv3d_dgrad_p16_split", dy16, w, *_pad4(dx_buf), acc, wp)

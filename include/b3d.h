@@ -319,6 +319,12 @@ int b3d_conv3d_dgrad_p16(const DLTensor* dy /*P16*/, const DLTensor* w, DLTensor
 int b3d_conv3d_dgrad_p16_split(const DLTensor* dy /*P16*/, const DLTensor* w, DLTensor* dx0, DLTensor* dx1 /*nullable*/,
                                DLTensor* dx2 /*nullable*/, DLTensor* dx3 /*nullable*/, int accumulate,
                                const DLTensor* wpacked, void* stream);
+/* data gradient w.r.t. the input of a ResnetBlock from both convs reading it (/root/reference/layers/resnet.py:118,133):
+ * dres (gradient of the pointwise conv's output) joins dy as a K segment used at the centre tap only */
+int b3d_conv3d_dgrad_p16_block(const DLTensor* dy /*P16*/, const DLTensor* dres /*P16*/, const DLTensor* w,
+                               const DLTensor* w_pw, DLTensor* dx0, DLTensor* dx1 /*nullable*/, DLTensor* dx2 /*nullable*/,
+                               DLTensor* dx3 /*nullable*/, const DLTensor* wpacked, const DLTensor* wpacked_pw,
+                               void* stream);
 int b3d_conv3d_wgrad_p16(const DLTensor* x0, const DLTensor* x1, const DLTensor* x2, const DLTensor* x3,
                          const DLTensor* dy /*P16*/, DLTensor* dw, int stride, int transposed, DLTensor* scratch,
                          void* stream);

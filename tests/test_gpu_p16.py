@@ -161,6 +161,35 @@ def test_conv_backward_p16_equals_fp32_operand_path(b3d, dev, case):
     assert e < 2e-5 and rel(dw1, dw0) < 2e-5, (e, rel(dw1, dw0))
 
 
+@pytest.mark.parametrize("case", [((8, 16, 8), [16], 16), ((9, 17, 11), [32], 16), ((8, 16, 16), [16, 16], 32),
+                                  ((4, 16, 16), [32, 64], 64), ((4, 8, 8), [64, 64, 128], 128), ((6, 10, 12), [48], 32)])
+def test_block_input_data_gradient_in_one_kernel(b3d, dev, case):
+    """b3d_conv3d_dgrad_p16_block: d/dx of conv3x3x3(x, w) and of conv1x1x1(x, w_pw) in ONE launch — the pointwise conv's
+    incoming gradient is a further K segment used at the centre tap only — written as one compact tensor per piece of a
+    virtually concatenated input; against the two separate data gradients (same operand roundings) and their split form."""
+    sp, pieces, cb = case
+    ops = b3d.ops
+    cin = sum(pieces)
+    w = rnd(3, 3, 3, cin, cb, seed=5, scale=0.1, dev=dev)
+    wpw = rnd(1, 1, 1, cin, cb, seed=6, scale=0.3, dev=dev)
+    dy, dres = rnd(2, *sp, cb, seed=7, dev=dev), rnd(2, *sp, cb, seed=8, dev=dev)
+    dy16, dres16 = ops.to_p16(dy, torch.bfloat16), ops.to_p16(dres, torch.bfloat16)
+    wp, wpp = ops.pack_weights(w, True, 1, False), ops.pack_weights(wpw, True, 1, False)
+    ref = torch.empty(2, *sp, cin, device=dev)
+    ops._call("b3d_conv3d_dgrad_p16", dy16, w, ref, 1, 0, 0, wp)
+    ops._call("b3d_conv3d_dgrad_p16", dres16, wpw, ref, 1, 0, 1, wpp)            # accumulate = 1
+    outs = [torch.full((2,) + tuple(sp) + (c,), float("nan"), device=dev) for c in pieces]
+    ops._call("b3d_conv3d_dgrad_p16_block", dy16, dres16, w, wpw, *(outs + [None] * (4 - len(outs))), wp, wpp)
+    got = torch.cat(outs, dim=-1)
+    assert rel(got, ref) < 2e-6, rel(got, ref)
+    # the split form of the plain data gradient (no pointwise part)
+    ref3 = torch.empty(2, *sp, cin, device=dev)
+    ops._call("b3d_conv3d_dgrad_p16", dy16, w, ref3, 1, 0, 0, wp)
+    outs3 = [torch.full((2,) + tuple(sp) + (c,), float("nan"), device=dev) for c in pieces]
+    ops._call("b3d_conv3d_dgrad_p16_split", dy16, w, *(outs3 + [None] * (4 - len(outs3))), 0, wp)
+    assert rel(torch.cat(outs3, dim=-1), ref3) < 2e-6
+
+
 def _dw_ref(x, dy, k, stride, tr):
     """fp64 weight gradient by autograd of the oracle's conv restatement."""
     from oracle import ref_model as R
