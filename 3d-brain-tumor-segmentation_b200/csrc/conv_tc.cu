@@ -499,7 +499,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
           }
           __syncwarp();
           if (++ws == C::WS) { ws = 0; wph ^= 1; }
-        } else
+          if (leader) tc_commit(smem_u32(&halo_empty[hs]));
+          __syncwarp();
+          if (++hs == C::HS) { hs = 0; hph ^= 1; }
+          continue;
+        }
 #pragma unroll
         for (int st = 0; st < C::TAPS / C::TPS; ++st) {
           mbar_wait(smem_u32(&w_full[ws]), wph);
