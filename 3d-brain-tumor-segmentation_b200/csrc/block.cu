@@ -474,37 +474,47 @@ __global__ void __launch_bounds__(kBT)
   const long long vbase = ((long long)b * gm.S + (long long)g * gm.vpc);
   const int iters = (int)((vend - v0 + vstep - 1) / vstep);
   VoxPos pos = vox_pos(tr.W, (unsigned)((long long)g * gm.vpc + v0 + vl));
-  for (int it = 0; it < iters; ++it) {
-    const long long v = v0 + (long long)it * vstep + vl;
-    const bool act = v < vend;
-    const long long eo = (vbase + (act ? v : v0)) * gm.F + c;
-    float r[8], d[8], h[8];
-    ld8(res + eo, r);
-    ld8(dout + eo, d);
-    ld8(h2 + eo, h);
-    float dot = 0.f, ds = 0.f;
+  // two voxels per thread and step: all six 32-byte loads are issued before the first shuffle reduction
+  for (int it = 0; it < iters; it += 2) {
+    float r[2][8], d[2][8], h[2][8];
+    bool act[2];
+    long long eo[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { dot += r[i] * w8[i]; ds += r[i] * d[i]; }
-    dot = group_sum(dot, T);
-    ds = group_sum(ds, T);
-    const float s = sigmoidf_(dot);
-    const float dl = ds * s * (1.f - s);
-    if (act) {
-      float o1[8], o2[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        o1[i] = d[i] * (s + c8v[i]) + dl * w8[i] + g8[i];
-        const float xh = (h[i] - mean) * rstd;
-        const float gq = (xh * ga8[i] + be8[i]) > 0.f ? d[i] : 0.f;
-        o2[i] = rstd * (gq * ga8[i] - m1 - xh * m2);
-        if (HAS_DB) { ar[i] += o1[i]; ah[i] += o2[i]; }
-      }
-      if (dres != nullptr) st8(dres + eo, o1);
-      if (dh2 != nullptr) st8(dh2 + eo, o2);
-      cell_store(tr, (unsigned)b, pos, (unsigned)lane, o1);
-      cell_store(th, (unsigned)b, pos, (unsigned)lane, o2);
+    for (int u = 0; u < 2; ++u) {
+      const long long v = v0 + (long long)(it + u) * vstep + vl;
+      act[u] = it + u < iters && v < vend;
+      eo[u] = (vbase + (act[u] ? v : v0)) * gm.F + c;
+      ld8(res + eo[u], r[u]);
+      ld8(dout + eo[u], d[u]);
+      ld8(h2 + eo[u], h[u]);
     }
-    vox_advance(tr.W, pos, (unsigned)vstep);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && it + 1 >= iters) break;          // CTA-uniform: whole warps stay in the shuffles
+      float dot = 0.f, ds = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dot += r[u][i] * w8[i]; ds += r[u][i] * d[u][i]; }
+      dot = group_sum(dot, T);
+      ds = group_sum(ds, T);
+      const float s = sigmoidf_(dot);
+      const float dl = ds * s * (1.f - s);
+      if (act[u]) {
+        float o1[8], o2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o1[i] = d[u][i] * (s + c8v[i]) + dl * w8[i] + g8[i];
+          const float xh = (h[u][i] - mean) * rstd;
+          const float gq = (xh * ga8[i] + be8[i]) > 0.f ? d[u][i] : 0.f;
+          o2[i] = rstd * (gq * ga8[i] - m1 - xh * m2);
+          if (HAS_DB) { ar[i] += o1[i]; ah[i] += o2[i]; }
+        }
+        if (dres != nullptr) st8(dres + eo[u], o1);
+        if (dh2 != nullptr) st8(dh2 + eo[u], o2);
+        cell_store(tr, (unsigned)b, pos, (unsigned)lane, o1);
+        cell_store(th, (unsigned)b, pos, (unsigned)lane, o2);
+      }
+      vox_advance(tr.W, pos, (unsigned)vstep);
+    }
   }
   if (HAS_DB) {
     // lanes of a warp with equal (lane % T) hold the same channels: butterfly over the voxel sub-index first
