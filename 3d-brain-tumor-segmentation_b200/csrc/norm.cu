@@ -632,10 +632,12 @@ __global__ void __launch_bounds__(kThreads)
 
 // CTAs per chunk for the cell kernels: every thread runs >= kIter16 steps, at most ~3 waves of CTAs in total, and the
 // grid-stride (gx * kThreads cells) is a multiple of C8 so that a thread keeps its channel octet
-static inline dim3 gn_grid16(const ChunkGeom& gm, int nchunks) {
+static inline dim3 gn_grid16(const ChunkGeom& gm, int nchunks, int waves = 8) {
+  // waves: cap of the grid in CTAs per SM.  Kernels that end in per-CTA atomics on a handful of addresses (the fused bias
+  // gradient: C addresses shared by ALL CTAs, ~15 ns per queued same-address atomic) take a smaller grid
   const long long cells = gm.L / kCell;
   long long gx = (cells + (long long)kThreads * kIter16 - 1) / ((long long)kThreads * kIter16);
-  long long cap = (8LL * sm_count() + nchunks - 1) / nchunks;
+  long long cap = ((long long)waves * sm_count() + nchunks - 1) / nchunks;
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
@@ -1024,11 +1026,11 @@ extern "C" int b3d_gn_bwd_apply_p16(const DLTensor* dy_, const DLTensor* x_, con
   }
   const size_t smem = db != nullptr ? sizeof(float) * gm.C : 0;
   if (relu)
-    gn_bwd_apply16_kernel<true><<<gn_grid16(gm, nchunks), kThreads, smem, s>>>(
+    gn_bwd_apply16_kernel<true><<<gn_grid16(gm, nchunks, db != nullptr ? 3 : 8), kThreads, smem, s>>>(
         (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
         (const double*)cs.p, (float*)dx.p, gm, eps, tw, db);
   else
-    gn_bwd_apply16_kernel<false><<<gn_grid16(gm, nchunks), kThreads, smem, s>>>(
+    gn_bwd_apply16_kernel<false><<<gn_grid16(gm, nchunks, db != nullptr ? 3 : 8), kThreads, smem, s>>>(
         (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
         (const double*)cs.p, (float*)dx.p, gm, eps, tw, db);
   B3D_LAUNCH_CHECK("gn_bwd_apply16");
