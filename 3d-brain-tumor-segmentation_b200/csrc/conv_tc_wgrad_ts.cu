@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(kTsThreads, 1)
 
 // The kernel handles Cin up to 256, but it only beats conv3_wgrad_tc_kernel where that one wastes most of its M rows:
 // measured (tools/conv_bench.py wgrad) 128^3 16->16 544 -> 275 us, 64^3 16->32 112 -> 71 us, but 128^3 32->16
-// 589 -> 642 us and 64^3 96->32 185 -> 237 us (three tap groups, each paying the per-K-step TMEM copies).
+// 589 -> 642 us and 64^3 96->32 185 -> 237 us (three tap groups, each paying the per-K-step TMEM copies).  Re-measured
+// in round 2 with P16 operands and 2 / 3 / 4 / 6 issuing warps per CTA instead of 8: 64^3 32->32 128-138 us vs 87 us.
 bool tc_wgrad_ts_supported(const WgradGeom& wg) {
   return wg.k == 3 && wg.s == 1 && (wg.nB == 16 || wg.nB == 32) && wg.nA == 16 && wg.Ws % 8 == 0 && wg.bigp % 8 == 0;
 }
