@@ -218,6 +218,34 @@ __device__ __noinline__ void flush_stats_cta(double* stats, int cur_chunk, float
   }
 }
 
+// Column sums over the 32 lanes of 16 per-lane values by a butterfly reduce-scatter: 15 + 1 shuffles instead of 16 warp
+// sums (80).  Afterwards every lane holds the total of ONE column: column = (lane >> 1) with its 4 bits reversed... see
+// `col` below; lanes 2k and 2k + 1 hold the same column.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane, int& col) {
+  float a[8], b[4], c[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = h16 ? v[i + 8] : v[i], send = h16 ? v[i] : v[i + 8];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);              // column i + 8 * bit4
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h8 ? a[i + 4] : a[i], send = h8 ? a[i] : a[i + 4];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);               // column i + 4 * bit3 + 8 * bit4
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = h4 ? b[i + 2] : b[i], send = h4 ? b[i] : b[i + 2];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);               // column i + 2 * bit2 + 4 * bit3 + 8 * bit4
+  }
+  const float keep = h2 ? c[1] : c[0], send = h2 ? c[0] : c[1];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);              // column bit1 + 2 * bit2 + 4 * bit3 + 8 * bit4
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  col = (h2 ? 1 : 0) | (h4 ? 2 : 0) | (h8 ? 4 : 0) | (h16 ? 8 : 0);
+  return d;
+}
+
 constexpr int kLoaderWarps = 8;
 // Number of MMA-issuing warps (each owns the patches p = its index mod kMmaWarps).  One warp can issue a tcgen05.mma
 // only every ~50 cycles (profiles/r01_umma_rate.txt), but measured with 2 issuers this kernel does not get faster (the
@@ -729,15 +757,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcParams p
           // wide layers: column sums flushed per tile (a tile lies in one sample) — into the CTA's shared-memory sums
           // when there is one sample (N = 64; written out once at the end), else straight to global memory
           const bool to_smem = C::N <= 64 && prm.B == 1;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float a = warp_sum(gs[i]);
-            if (lane == 0 && nsp * C::N + j * 16 + i < prm.cout_real) {
-              if (to_smem) atomicAdd(&cta_gap[j * 16 + i], a);
-              else atomicAdd(&prm.gap[(long long)b * prm.cout_real + nsp * C::N + j * 16 + i], a);
-            }
-            gs[i] = 0.f;
+          int i = 0;
+          const float a = warp_colsum16(gs, lane, i);        // this lane's column of the 16 (lanes 2k, 2k+1: the same)
+          if ((lane & 1) == 0 && nsp * C::N + j * 16 + i < prm.cout_real) {
+            if (to_smem) atomicAdd(&cta_gap[j * 16 + i], a);
+            else atomicAdd(&prm.gap[(long long)b * prm.cout_real + nsp * C::N + j * 16 + i], a);
           }
+#pragma unroll
+          for (int q2 = 0; q2 < 16; ++q2) gs[q2] = 0.f;
           if (to_smem && lane == 0) *cta_gap_b = b;
         }
       }
