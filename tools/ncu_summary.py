@@ -17,7 +17,10 @@ hdr, units, vals = rows[0], rows[1], rows[2]
 def get(name, scale_units=True):
     for i, h in enumerate(hdr):
         if h == name:
-            v = float(vals[i].replace(",", ""))
+            try:
+                v = float(vals[i].replace(",", ""))
+            except ValueError:          # "no data": the counter was not collected in this capture
+                return None
             u = units[i]
             if scale_units:
                 v *= {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
