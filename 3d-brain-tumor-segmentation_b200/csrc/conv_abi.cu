@@ -731,5 +731,6 @@ extern "C" int b3d_conv3d_wgrad_p16(const DLTensor* x0_, const DLTensor* x1_, co
     wp.n = src.n;
     for (int i = 0; i < src.n; ++i) { wp.big[i] = src.p[i]; wp.C[i] = src.C[i]; }
   }
+  if (!transposed && tc_wgrad_kdf_supported(wg, &wp)) return launch_conv_wgrad_kdf(wg, (float*)dw.p, s, wp);
   return launch_conv_wgrad_tc(wg, big.p, sml.p, (float*)dw.p, s, 0, 0, 0, &wp);
 }

@@ -130,6 +130,9 @@ int launch_p16_t8(const void* src, void* dst, long long rows, int W, int C8, cud
 bool tc_wgrad_ts_supported(const WgradGeom& wg);
 int launch_conv_wgrad_ts(const WgradGeom& wg, const void* x_bf16, const void* dyT_bf16, float* dw, cudaStream_t s,
                          int x_p16 = 0, int x_f16 = 0);
+// 3x3x3 weight gradient with the depth taps folded into M (conv_tc_wgrad.cu): Cin 32 | 64, Cout 16 | 32, P16 sources
+bool tc_wgrad_kdf_supported(const WgradGeom& wg, const WgP16* p16);
+int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const WgP16& p16);
 // kh-folded TS-mode weight gradient (conv_tc_wgrad_ts.cu): P16 sources (virtual concat), Cout 16 | 32
 bool tc_wgrad_tsf_supported(const WgradGeom& wg, const WgP16* p16);
 int launch_conv_wgrad_tsf(const WgradGeom& wg, const WgP16& src, const void* dyT_bf16, float* dw, cudaStream_t s);

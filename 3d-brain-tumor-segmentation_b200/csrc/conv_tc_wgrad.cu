@@ -367,6 +367,230 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
 }
 
 
+// ================================================================================================ kd folded into M
+// For Cin = 32 / 64 the kernel above computes M = 64 / 128 rows per MMA of which Cin are real, 27 MMAs per K step.  Here
+// the three depth taps share ONE MMA: the x halo of a 32-channel tile is laid out [d][plane (4)][h][w] (one TMA box per
+// (plane, depth slice)), so the M groups (kd, plane) of the A operand lie at ONE stride — a plane slice — and
+//     D_(kh,kw)[(kd, ci)][co] += sum_v x[v + (kd-1, kh-1, kw-1)][ci] * dy[v][co]
+// uses 96 of 128 rows: 9 MMAs per K step instead of 27, all 9 accumulators (9 * Cout <= 288 columns) in one CTA, so no
+// tap groups re-reading the halo either.  Channel tiles of 32 (Cin = 64: two) and voxel ranges are spread over the CTAs.
+struct KdfParams {
+  float* dw;
+  int Cin, Cout;
+  int TD, TH, TW, HD, HH, HW;
+  int pslice;                      // pitch of one (plane, depth slice) of the halo: HH * HW * 16 bytes padded to 128
+  int py;                          // bytes of one dy plane of the tile
+  int xbytes, stage_bytes, nstages;
+  int ntd, nth, ntw, ntiles, nsplit;
+  int nsrc, cend8[4];
+  int ntg;                         // 1: a CTA holds all 9 (kh, kw) accumulators; 3: blockIdx.z = kh (small volumes: the
+                                   // final fp32 atomics per CTA are 27 * 32 * Cout otherwise — 3x the per-tap kernel's)
+};
+
+__global__ void __launch_bounds__(256, 1)
+    conv3_wgrad_kdf_kernel(const __grid_constant__ WgMaps maps, const KdfParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgSmem - 128);
+  uint64_t* full = bars;        // [4]
+  uint64_t* empty = bars + 4;   // [4]
+  uint64_t* done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cbase = blockIdx.y * 32;          // channel tile
+  const int yplanes = prm.Cout / 8;
+  const int kh0 = prm.ntg == 3 ? (int)blockIdx.z : 0, nt = prm.ntg == 3 ? 3 : 9;   // this CTA's taps: (kh0 + t / 3, t % 3)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < prm.nstages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+    mbar_init(smem_u32(done), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      const uint32_t bytes = (uint32_t)(prm.HD * 4 * prm.HH * prm.HW * 16 + yplanes * prm.py);
+      for (int tile = blockIdx.x; tile < prm.ntiles; tile += prm.nsplit) {
+        int t = tile;
+        const int wt = t % prm.ntw; t /= prm.ntw;
+        const int ht = t % prm.nth; t /= prm.nth;
+        const int dt = t % prm.ntd; t /= prm.ntd;
+        const int b = t;
+        const int w0 = wt * prm.TW, h0 = ht * prm.TH, d0 = dt * prm.TD;
+        mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+        const uint32_t fb = smem_u32(&full[s]);
+        mbar_expect_tx(fb, bytes);
+        const uint32_t xdst = smem_u32(smem + (size_t)s * prm.stage_bytes);
+        const uint32_t ydst = xdst + (uint32_t)prm.xbytes;
+        for (int p = 0; p < 4; ++p) {
+          const int gp = (cbase >> 3) + p;
+          int si = 0;
+          while (si + 1 < prm.nsrc && gp >= prm.cend8[si]) ++si;
+          const int lp = gp - (si > 0 ? prm.cend8[si - 1] : 0);
+          for (int d = 0; d < prm.HD; ++d)
+            tma_load_5d(xdst + (uint32_t)((d * 4 + p) * prm.pslice), &maps.x[si], 4 * (w0 - 1), lp, h0 - 1 + kh0, d0 - 1 + d, b,
+                        fb);
+        }
+        for (int q = 0; q < yplanes; ++q) tma_load_5d(ydst + q * prm.py, &maps.y, 4 * w0, q, h0, d0, b, fb);
+        if (++s == prm.nstages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    // D = f32, A = B = bf16, both MN-major, N = Cout, M = 128 (rows (kd, ci): 96 real)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(prm.Cout >> 3) << 17) | ((128u >> 4) << 24);
+    int s = 0, ph = 0;
+    uint32_t acc = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    const int slicec = prm.pslice / 16;          // cells between consecutive (plane, depth slice) blocks
+    for (int tile = blockIdx.x; tile < prm.ntiles; tile += prm.nsplit) {
+      mbar_wait(smem_u32(&full[s]), ph);
+      tc_fence_after();
+      const uint32_t xaddr = smem_base + (uint32_t)s * (uint32_t)prm.stage_bytes;
+      // A: K = 8 voxels along w x 2 h rows (LBO = halo row), M groups (kd, plane) one plane slice apart (SBO)
+      const uint64_t adesc0 = make_desc(xaddr, (uint32_t)prm.HW * 16, (uint32_t)prm.pslice);
+      const uint64_t bdesc0 = make_desc(xaddr + (uint32_t)prm.xbytes, (uint32_t)prm.TW * 16, (uint32_t)prm.py);
+      for (int d = 0; d < prm.TD; ++d)
+        for (int h = 0; h < prm.TH; h += 2)
+          for (int w8 = 0; w8 < prm.TW; w8 += 8) {
+            const uint32_t ycell = (uint32_t)((d * prm.TH + h) * prm.TW + w8);
+            const uint32_t xcell = (uint32_t)(d * 4 * slicec + h * prm.HW + w8);
+            if (leader) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                if (t >= nt) break;
+                const uint32_t off = xcell + (uint32_t)((t / 3) * prm.HW + t % 3);
+                tc_mma_bf16(tmem_base + t * prm.Cout, adesc0 + off, bdesc0 + ycell, idesc, acc);
+              }
+            }
+            acc = 1;
+          }
+      if (leader) tc_commit(smem_u32(&empty[s]));
+      __syncwarp();
+      if (++s == prm.nstages) { s = 0; ph ^= 1; }
+    }
+    if (leader) tc_commit(smem_u32(done));
+    __syncwarp();
+  } else if (warp >= 4) {
+    // final reduction: accumulator row r = kd * 32 + (ci - cbase) lives in TMEM lane r
+    const int q = warp - 4, r = q * 32 + lane;
+    const int kd = r >> 5, ci = cbase + (r & 31);
+    mbar_wait(smem_u32(done), 0);
+    tc_fence_after();
+    const bool live = blockIdx.x < prm.ntiles && r < 96;
+#pragma unroll 1
+    for (int t = 0; t < nt; ++t) {
+      float* dst = prm.dw + ((size_t)(kd * 9 + kh0 * 3 + t) * prm.Cin + ci) * prm.Cout;
+      for (int j = 0; j < prm.Cout; j += 16) {
+        float v[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + t * prm.Cout + j, v);
+        if (live) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dst + j + i, v[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+bool tc_wgrad_kdf_supported(const WgradGeom& wg, const WgP16* p16) {
+  static const int on = [] { const char* e = getenv("B3D_WGRAD_KDF"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+  if (!on || p16 == nullptr) return false;
+  // Cin = 32 only: with 64 input channels the per-tap kernel's M = 64 rows are all real (27 x ~33 cycles per K step vs
+  // 2 channel tiles x 9 x ~45 here: measured 99 vs 112 us at 64^3 64->32)
+  if (!(wg.k == 3 && wg.s == 1 && wg.nA == 32 && (wg.nB == 16 || wg.nB == 32))) return false;
+  if (wg.Ws % 8 != 0 || wg.Hs % 2 != 0) return false;
+  for (int i = 0; i < p16->n; ++i)
+    if (p16->C[i] % 8 != 0) return false;
+  return p16->big_bf16 && p16->small_bf16;
+}
+
+int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const WgP16& p16) {
+  B3D_REQUIRE(tc_wgrad_kdf_supported(wg, &p16), B3D_ERR_UNSUPPORTED, "wgrad (kd in M): shape not supported");
+  B3D_REQUIRE(((uintptr_t)dw & 15) == 0, B3D_ERR_LAYOUT, "wgrad: alignment");
+  const int Cin = wg.nA, Cout = wg.nB, nmt = Cin / 32;
+  static const int cand[][3] = {{1, 4, 8}, {2, 4, 8}, {2, 4, 16}, {2, 8, 16}, {4, 8, 16}, {4, 8, 32}};
+  KdfParams p;
+  memset(&p, 0, sizeof(p));
+  // small volumes: split the kh taps over 3 CTA groups (fewer final atomics per CTA, all SMs still busy)
+  const long long vox = (long long)wg.B * wg.Ds * wg.Hs * wg.Ws;
+  const int ntg = vox / 512 < 16LL * (sm_count() / nmt) ? 3 : 1;
+  p.ntg = ntg;
+  const int budget = kWgSmem - 128;
+  bool found = false;
+  for (int i = 0; i < (int)(sizeof(cand) / sizeof(cand[0])); ++i) {
+    const int TD = cand[i][0], TH = cand[i][1], TW = cand[i][2];
+    if (found && (TD > wg.Ds * 2 || TH > wg.Hs * 2 || TW > wg.Ws * 2)) continue;
+    const int HD = TD + 2, HH = TH + (ntg == 3 ? 0 : 2), HW = TW + 2;
+    if (4 * HW > 256) continue;
+    const int pslice = ((HH * HW * 16 + 127) / 128) * 128;
+    // the A operand spans 16 M groups (M = 128) from the LAST depth slice a K step starts in: 12 are real, the rest
+    // must still lie inside this stage's x region or the dy tile (never past the allocation): keep 4 slices of slack
+    const long long xbytes = (((long long)HD * 4 * pslice + 127) / 128) * 128;
+    const int py = TD * TH * TW * 16;
+    const long long stage = ((xbytes + (long long)(Cout / 8) * py + 127) / 128) * 128;
+    for (int ns = 4; ns >= 2; --ns) {
+      const long long last = (long long)(ns - 1) * stage;
+      // last K step of the last stage: group 15 starts at (TD-1)*4 slices + 15 slices + h/w offset
+      if (ns * stage <= budget && last + ((long long)(TD - 1) * 4 + 16 + 1) * pslice <= budget) {
+        // prefer >= 3 stages (one thread issues ~28 small TMA boxes per tile: the pipeline needs the depth) over a
+        // larger tile with 2
+        if (found && ns < 3 && p.nstages >= 3) break;
+        p.TD = TD; p.TH = TH; p.TW = TW; p.HD = HD; p.HH = HH; p.HW = HW;
+        p.pslice = pslice; p.py = py; p.xbytes = (int)xbytes; p.stage_bytes = (int)stage; p.nstages = ns;
+        found = true;
+        break;
+      }
+    }
+  }
+  B3D_REQUIRE(found, B3D_ERR_UNSUPPORTED, "wgrad (kd in M): no tile fits shared memory (Cin=%d Cout=%d)", Cin, Cout);
+  p.dw = dw; p.Cin = Cin; p.Cout = Cout;
+  p.ntd = (wg.Ds + p.TD - 1) / p.TD; p.nth = (wg.Hs + p.TH - 1) / p.TH; p.ntw = (wg.Ws + p.TW - 1) / p.TW;
+  p.ntiles = wg.B * p.ntd * p.nth * p.ntw;
+  int nsplit = sm_count() / (nmt * ntg);
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > p.ntiles) nsplit = p.ntiles;
+  p.nsplit = nsplit;
+  WgMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.nsrc = p16.n;
+  int cum = 0;
+  for (int i = 0; i < p16.n; ++i) {
+    cum += p16.C[i] / 8;
+    p.cend8[i] = cum;
+    // one box = one (plane, depth slice) of the halo: {HW voxels, 1 plane, HH rows, 1 slice}
+    B3D_TRY(make_p16_map(&maps.x[i], p16.big[i], 1, wg.B, wg.Db, wg.Hb, wg.Wb, p16.C[i] / 8, p.HW, 1, p.HH, 1));
+  }
+  B3D_REQUIRE(cum * 8 == Cin, B3D_ERR_SHAPE, "wgrad (kd in M): sources hold %d channels, expected %d", cum * 8, Cin);
+  B3D_TRY(make_p16_map(&maps.y, p16.small, 1, wg.B, wg.Ds, wg.Hs, wg.Ws, Cout / 8, p.TW, 1, p.TH, p.TD));
+  B3D_TRY(cuda_ok(cudaMemsetAsync(dw, 0, sizeof(float) * 27 * (size_t)Cin * Cout, s), "memset dw"));
+  static bool attr = false;
+  if (!attr) {
+    B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv3_wgrad_kdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem),
+                    "cudaFuncSetAttribute(wgrad_kdf)"));
+    attr = true;
+  }
+  conv3_wgrad_kdf_kernel<<<dim3((unsigned)nsplit, (unsigned)nmt, (unsigned)ntg), 256, kWgSmem, s>>>(maps, p);
+  B3D_LAUNCH_CHECK("conv3_wgrad_kdf");
+  return B3D_OK;
+}
+
 // ---- fp32 -> bf16 copies for the tensor-core weight gradient (+ optional column sums = bias gradient)
 // thread -> (voxel, channel octet); the octet of a thread is loop-invariant (blockDim % (C/8) == 0)
 __global__ void cast_bf16_kernel(const float* __restrict__ src, uint4* __restrict__ dst, long long nvox, int C,
