@@ -709,6 +709,12 @@ extern "C" int b3d_conv3d_wgrad_p16(const DLTensor* x0_, const DLTensor* x1_, co
     wp.n = 1; wp.big[0] = scratch; wp.C[0] = 8 * cbig;
     return launch_conv_wgrad_tc(wg, scratch, sml.p, (float*)dw.p, s, 0, 0, 0, &wp);
   }
+  if (!transposed) {
+    wp.n = src.n;
+    for (int i = 0; i < src.n; ++i) { wp.big[i] = src.p[i]; wp.C[i] = src.C[i]; }
+    // depth taps folded into M (Cin = 32, and Cin = 16 ahead of the TS-mode kernel of plan 3)
+    if (tc_wgrad_kdf_supported(wg, &wp)) return launch_conv_wgrad_kdf(wg, (float*)dw.p, s, wp);
+  }
   if (plan == 3) {
     const long long need = (long long)dy.B * dy.D * dy.H * dy.W * cout;
     B3D_REQUIRE(scratch != nullptr && scratch_n >= need, B3D_ERR_ARG, "wgrad (P16, TS): scratch of %lld elements", need);
@@ -727,10 +733,5 @@ extern "C" int b3d_conv3d_wgrad_p16(const DLTensor* x0_, const DLTensor* x1_, co
     // neither TS form takes these sources: the plan-1 kernel below (the scratch stays unused)
   }
   if (transposed) { wp.n = 1; wp.big[0] = big.p; wp.C[0] = cbig; }
-  else {
-    wp.n = src.n;
-    for (int i = 0; i < src.n; ++i) { wp.big[i] = src.p[i]; wp.C[i] = src.C[i]; }
-  }
-  if (!transposed && tc_wgrad_kdf_supported(wg, &wp)) return launch_conv_wgrad_kdf(wg, (float*)dw.p, s, wp);
   return launch_conv_wgrad_tc(wg, big.p, sml.p, (float*)dw.p, s, 0, 0, 0, &wp);
 }

@@ -194,37 +194,55 @@ __global__ void __launch_bounds__(256, 1)
     // final reduction of this CTA's partial dw into global memory
     // accumulator row r lives in TMEM lane r (M = 128) or lane 32*(r/16) + r%16 (M = 64; tools/umma_probe_m64.cu)
     const int q = warp - 4;
-    const int ci = prm.M == 128 ? cbase + q * 32 + lane : (lane < 16 ? cbase + q * 16 + lane : prm.Cin);
     mbar_wait(smem_u32(done), 0);
     tc_fence_after();
     const bool has_tiles = blockIdx.x < prm.ntiles;
-    // stride-2 family: row ci = (parity, channel); coarse tap d and parity p give the fine tap 2d + p (<= 2)
-    int row = ci, rows = prm.Cin, par = 0;
-    if (prm.s2_nA > 0) { par = ci / prm.s2_nA; row = ci - par * prm.s2_nA; rows = prm.s2_nA; }
+    // A warp's 32 rows x NT columns go through shared memory (the stage buffers are free once `done` fired) so that
+    // consecutive lanes add consecutive 16-byte pieces of a dw row (REDG.128): with a row per lane every scalar atomic
+    // instruction touched 32 sectors, and the split-K CTAs queued on them for tens of microseconds per launch.
+    const int pitch = prm.NT + 4, c4n = prm.NT / 4;
+    float* stg = reinterpret_cast<float*>(smem) + q * 32 * pitch;
+    const bool vec = prm.tr_cn == 0 && (prm.Cout & 3) == 0;
 #pragma unroll 1
-    for (int t = 0; t < TG; ++t) {
-      int tap = allD ? t : (TG == KS * KS ? tg * TG + t : (TG == KS ? tg * KS + t : tg));
-      bool live = has_tiles && ci < prm.rows_real;
-      if (prm.s2_nA > 0) {
-        const int td = 2 * (tap >> 2) + (par >> 2), th = 2 * ((tap >> 1) & 1) + ((par >> 1) & 1),
-                  tw = 2 * (tap & 1) + (par & 1);
-        live = live && td <= 2 && th <= 2 && tw <= 2;
-        tap = (td * 3 + th) * 3 + tw;
-      }
-      float* dst = prm.dw + ((size_t)tap * rows + row) * prm.Cout + nb0;
+    for (int tt = 0; tt < TG; ++tt) {
+      const int t = (tt + (int)blockIdx.x) % TG;          // CTAs start at different taps: fewer same-address queues
+      const int tap0 = allD ? t : (TG == KS * KS ? tg * TG + t : (TG == KS ? tg * KS + t : tg));
       for (int j = 0; j < prm.NT; j += 16) {
         float v[16];
         tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + t * prm.NT + j, v);
-        if (live && prm.tr_cn > 0) {
-          const int tt = row / prm.tr_cn, cc = row - tt * prm.tr_cn;     // row = (tap, narrow channel)
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            atomicAdd(prm.dw + ((size_t)tt * prm.Cout + nb0 + j + i) * prm.tr_cn + cc, v[i]);
-        } else if (live) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(dst + j + i, v[i]);
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(stg + lane * pitch + j + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      __syncwarp();
+      // rows of the block: lane-row rl -> input channel (or (parity, channel) / (tap, narrow channel)) row ci
+      const int nel = vec ? 32 * c4n : 32 * prm.NT;
+      for (int e = lane; has_tiles && e < nel; e += 32) {
+        const int rl = vec ? e / c4n : e / prm.NT, c = vec ? (e - rl * c4n) * 4 : e - rl * prm.NT;
+        const int ci = prm.M == 128 ? cbase + q * 32 + rl : (rl < 16 ? cbase + q * 16 + rl : prm.Cin);
+        if (ci >= prm.rows_real) continue;
+        // stride-2 family: row ci = (parity, channel); coarse tap d and parity p give the fine tap 2d + p (<= 2)
+        int row = ci, rows = prm.Cin, tap = tap0;
+        if (prm.s2_nA > 0) {
+          const int par = ci / prm.s2_nA;
+          row = ci - par * prm.s2_nA; rows = prm.s2_nA;
+          const int td = 2 * (tap0 >> 2) + (par >> 2), th = 2 * ((tap0 >> 1) & 1) + ((par >> 1) & 1),
+                    tw = 2 * (tap0 & 1) + (par & 1);
+          if (td > 2 || th > 2 || tw > 2) continue;
+          tap = (td * 3 + th) * 3 + tw;
+        }
+        const float* src = stg + rl * pitch + c;
+        if (vec) {
+          atomicAdd(reinterpret_cast<float4*>(prm.dw + ((size_t)tap * rows + row) * prm.Cout + nb0 + c),
+                    *reinterpret_cast<const float4*>(src));
+        } else if (prm.tr_cn > 0) {
+          const int tr = row / prm.tr_cn, cc = row - tr * prm.tr_cn;     // row = (tap, narrow channel)
+          atomicAdd(prm.dw + ((size_t)tr * prm.Cout + nb0 + c) * prm.tr_cn + cc, *src);
+        } else {
+          atomicAdd(prm.dw + ((size_t)tap * rows + row) * prm.Cout + nb0 + c, *src);
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -367,13 +385,20 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
 }
 
 
-// ================================================================================================ kd folded into M
+// ================================================================================ kd folded into M, kw folded into N
 // For Cin = 32 / 64 the kernel above computes M = 64 / 128 rows per MMA of which Cin are real, 27 MMAs per K step.  Here
-// the three depth taps share ONE MMA: the x halo of a 32-channel tile is laid out [d][plane (4)][h][w] (one TMA box per
-// (plane, depth slice)), so the M groups (kd, plane) of the A operand lie at ONE stride — a plane slice — and
-//     D_(kh,kw)[(kd, ci)][co] += sum_v x[v + (kd-1, kh-1, kw-1)][ci] * dy[v][co]
-// uses 96 of 128 rows: 9 MMAs per K step instead of 27, all 9 accumulators (9 * Cout <= 288 columns) in one CTA, so no
-// tap groups re-reading the halo either.  Channel tiles of 32 (Cin = 64: two) and voxel ranges are spread over the CTAs.
+// the three depth taps share the M dimension and the three width taps the N dimension of ONE MMA:
+//   * the x tile (32 or 16 channels, halo in d and h only) is laid out [d][plane][h][w], one TMA box per (plane, depth
+//     slice), so the M groups (kd, plane) of the A operand lie at ONE stride (a plane slice): 96 of 128 rows (Cin = 32)
+//     or 48 of 64 (Cin = 16) are real;
+//   * the dy tile is loaded three times, shifted by 1 - kw voxels along w (TMA zero fill at the volume edge), so the N
+//     groups (kw, plane) of the B operand lie at one stride as well and
+//         D_kh[(kd, ci)][(kw, co)] += sum_u x[u + (kd-1, kh-1, 0)][ci] * dy[u - (0, 0, kw-1)][co]
+//     is the weight gradient with the voxel sum re-indexed (u = v + (0, 0, kw-1));
+//   * no operand is read at a w offset: every 128-byte core matrix the tensor core fetches from shared memory is
+//     aligned (the form with kw as an MMA loop measured ~63 cycles per M = 128, N = 16 MMA, twice its operand bytes).
+// 3 MMAs (N = 3 Cout) per K step instead of 27, all accumulators (9 Cout <= 288 columns) in one CTA; voxel ranges are
+// spread over the CTAs (and the kh taps over blockIdx.z for small volumes).
 struct KdfParams {
   float* dw;
   int Cin, Cout;
@@ -383,6 +408,9 @@ struct KdfParams {
   int xbytes, stage_bytes, nstages;
   int ntd, nth, ntw, ntiles, nsplit;
   int nsrc, cend8[4];
+  int dbg;                         // timing experiments only (B3D_KDF_DBG): 1 no MMAs, 2 one dy copy, 4 one x slice,
+                                   // 8 no final reduction
+  int P;                           // channel planes (octets) of the tile: 4 (Cin = 32, M = 128) or 2 (Cin = 16, M = 64)
   int ntg;                         // 1: a CTA holds all 9 (kh, kw) accumulators; 3: blockIdx.z = kh (small volumes: the
                                    // final fp32 atomics per CTA are 27 * 32 * Cout otherwise — 3x the per-tap kernel's)
 };
@@ -396,9 +424,11 @@ __global__ void __launch_bounds__(256, 1)
   uint64_t* done = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cbase = blockIdx.y * 32;          // channel tile
+  const int P = prm.P;
+  const int cbase = blockIdx.y * 8 * P;       // channel tile
   const int yplanes = prm.Cout / 8;
   const int kh0 = prm.ntg == 3 ? (int)blockIdx.z : 0, nt = prm.ntg == 3 ? 3 : 9;   // this CTA's taps: (kh0 + t / 3, t % 3)
+  const int nkh = nt / 3;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < prm.nstages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
@@ -416,39 +446,49 @@ __global__ void __launch_bounds__(256, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0, ph = 0;
-      const uint32_t bytes = (uint32_t)(prm.HD * 4 * prm.HH * prm.HW * 16 + yplanes * prm.py);
-      for (int tile = blockIdx.x; tile < prm.ntiles; tile += prm.nsplit) {
-        int t = tile;
-        const int wt = t % prm.ntw; t /= prm.ntw;
-        const int ht = t % prm.nth; t /= prm.nth;
-        const int dt = t % prm.ntd; t /= prm.ntd;
-        const int b = t;
-        const int w0 = wt * prm.TW, h0 = ht * prm.TH, d0 = dt * prm.TD;
+    // producer warp: lane 0 waits for the slot and arms the barrier, then the lanes issue the tile's boxes in parallel
+    // (HD * P halo slices of x + 3 * yplanes planes of dy: 20-40 small boxes, too many for one thread per tile)
+    int s = 0, ph = 0;
+    const int nxb = (prm.dbg & 4) ? 1 : prm.HD * P, nbox = nxb + ((prm.dbg & 2) ? 1 : 3) * yplanes;
+    const uint32_t bytes = (uint32_t)(nxb * prm.HH * prm.HW * 16 + (nbox - nxb) * prm.py);
+    for (int tile = blockIdx.x; tile < prm.ntiles; tile += prm.nsplit) {
+      int t = tile;
+      const int wt = t % prm.ntw; t /= prm.ntw;
+      const int ht = t % prm.nth; t /= prm.nth;
+      const int dt = t % prm.ntd; t /= prm.ntd;
+      const int b = t;
+      const int w0 = wt * prm.TW, h0 = ht * prm.TH, d0 = dt * prm.TD;
+      const uint32_t fb = smem_u32(&full[s]);
+      if (lane == 0) {
         mbar_wait(smem_u32(&empty[s]), ph ^ 1);
-        const uint32_t fb = smem_u32(&full[s]);
         mbar_expect_tx(fb, bytes);
-        const uint32_t xdst = smem_u32(smem + (size_t)s * prm.stage_bytes);
-        const uint32_t ydst = xdst + (uint32_t)prm.xbytes;
-        for (int p = 0; p < 4; ++p) {
+      }
+      __syncwarp();
+      const uint32_t xdst = smem_u32(smem + (size_t)s * prm.stage_bytes);
+      const uint32_t ydst = xdst + (uint32_t)prm.xbytes;
+      for (int j = lane; j < nbox; j += 32) {
+        if (j < nxb) {
+          const int d = j / P, p = j - d * P;
           const int gp = (cbase >> 3) + p;
           int si = 0;
           while (si + 1 < prm.nsrc && gp >= prm.cend8[si]) ++si;
           const int lp = gp - (si > 0 ? prm.cend8[si - 1] : 0);
-          for (int d = 0; d < prm.HD; ++d)
-            tma_load_5d(xdst + (uint32_t)((d * 4 + p) * prm.pslice), &maps.x[si], 4 * (w0 - 1), lp, h0 - 1 + kh0, d0 - 1 + d, b,
-                        fb);
+          tma_load_5d(xdst + (uint32_t)(j * prm.pslice), &maps.x[si], 4 * w0, lp, h0 - 1 + kh0, d0 - 1 + d, b, fb);
+        } else {
+          // dy three times, shifted by 1 - kw voxels along w (zero fill outside the volume): copy kw at in-tile voxel u
+          // holds dy[u - (kw - 1)], the partner of x[u + (kd - 1, kh - 1, 0)]
+          const int jj = j - nxb, kw = jj / yplanes, q = jj - kw * yplanes;
+          tma_load_5d(ydst + jj * prm.py, &maps.y, 4 * (w0 + 1 - kw), q, h0, d0, b, fb);
         }
-        for (int q = 0; q < yplanes; ++q) tma_load_5d(ydst + q * prm.py, &maps.y, 4 * w0, q, h0, d0, b, fb);
-        if (++s == prm.nstages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == prm.nstages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
-    // D = f32, A = B = bf16, both MN-major, N = Cout, M = 128 (rows (kd, ci): 96 real)
+    // D = f32, A = B = bf16, both MN-major, N = 3 Cout (columns (kw, co)), M = 128 / 64 (rows (kd, ci): 96 / 48 real)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(prm.Cout >> 3) << 17) | ((128u >> 4) << 24);
+                           ((uint32_t)((3 * prm.Cout) >> 3) << 17) | (((uint32_t)(32 * P) >> 4) << 24);
     int s = 0, ph = 0;
     uint32_t acc = 0;
     const uint32_t smem_base = smem_u32(smem);
@@ -457,20 +497,21 @@ __global__ void __launch_bounds__(256, 1)
       mbar_wait(smem_u32(&full[s]), ph);
       tc_fence_after();
       const uint32_t xaddr = smem_base + (uint32_t)s * (uint32_t)prm.stage_bytes;
-      // A: K = 8 voxels along w x 2 h rows (LBO = halo row), M groups (kd, plane) one plane slice apart (SBO)
+      // A: K = 8 voxels along w x 2 h rows (LBO = halo row), M groups (kd, plane) one plane slice apart (SBO);
+      // B: the same K cells of the three dy copies, N groups (kw, plane) one dy plane apart
       const uint64_t adesc0 = make_desc(xaddr, (uint32_t)prm.HW * 16, (uint32_t)prm.pslice);
       const uint64_t bdesc0 = make_desc(xaddr + (uint32_t)prm.xbytes, (uint32_t)prm.TW * 16, (uint32_t)prm.py);
       for (int d = 0; d < prm.TD; ++d)
         for (int h = 0; h < prm.TH; h += 2)
           for (int w8 = 0; w8 < prm.TW; w8 += 8) {
             const uint32_t ycell = (uint32_t)((d * prm.TH + h) * prm.TW + w8);
-            const uint32_t xcell = (uint32_t)(d * 4 * slicec + h * prm.HW + w8);
-            if (leader) {
+            const uint32_t xcell = (uint32_t)(d * P * slicec + h * prm.HW + w8);
+            if (leader && !(prm.dbg & 1)) {
 #pragma unroll
-              for (int t = 0; t < 9; ++t) {
-                if (t >= nt) break;
-                const uint32_t off = xcell + (uint32_t)((t / 3) * prm.HW + t % 3);
-                tc_mma_bf16(tmem_base + t * prm.Cout, adesc0 + off, bdesc0 + ycell, idesc, acc);
+              for (int t = 0; t < 3; ++t) {
+                if (t >= nkh) break;
+                tc_mma_bf16(tmem_base + t * 3 * prm.Cout, adesc0 + xcell + (uint32_t)(t * prm.HW), bdesc0 + ycell, idesc,
+                            acc);
               }
             }
             acc = 1;
@@ -482,23 +523,39 @@ __global__ void __launch_bounds__(256, 1)
     if (leader) tc_commit(smem_u32(done));
     __syncwarp();
   } else if (warp >= 4) {
-    // final reduction: accumulator row r = kd * 32 + (ci - cbase) lives in TMEM lane r
-    const int q = warp - 4, r = q * 32 + lane;
-    const int kd = r >> 5, ci = cbase + (r & 31);
+    // final reduction: accumulator row r = kd * 8P + (ci - cbase) lives in TMEM lane r (M = 128) or lane
+    // 32 * (r / 16) + r % 16 (M = 64): either way warp q reads depth tap q, lane = channel
+    const int q = warp - 4;
+    const int kd = q;
     mbar_wait(smem_u32(done), 0);
     tc_fence_after();
-    const bool live = blockIdx.x < prm.ntiles && r < 96;
+    const bool live = blockIdx.x < prm.ntiles && q < 3 && !(prm.dbg & 8);
+    // the (kd, tap) block of dw — rows ci of this tile x Cout — is contiguous: stage the warp's 32 rows through shared
+    // memory (the stage buffers are free once `done` fired) and add it with 16-byte vector reductions, consecutive lanes
+    // on consecutive addresses (row-per-lane scalar atomics are 32 sectors per instruction, 8 P Cout of them per tap);
+    // the CTAs start at different taps so that they do not queue on the same addresses
+    const int pitch = prm.Cout + 4;
+    float* stg = reinterpret_cast<float*>(smem) + q * 32 * pitch;
+    const int n4 = 8 * P * prm.Cout / 4;
 #pragma unroll 1
-    for (int t = 0; t < nt; ++t) {
-      float* dst = prm.dw + ((size_t)(kd * 9 + kh0 * 3 + t) * prm.Cin + ci) * prm.Cout;
+    for (int tt = 0; tt < nt; ++tt) {
+      const int t = (tt + (int)blockIdx.x) % nt;
       for (int j = 0; j < prm.Cout; j += 16) {
         float v[16];
         tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + t * prm.Cout + j, v);
-        if (live) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(dst + j + i, v[i]);
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(stg + lane * pitch + j + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      __syncwarp();
+      if (live) {
+        float4* blk = reinterpret_cast<float4*>(prm.dw + ((size_t)(kd * 9 + kh0 * 3 + t) * prm.Cin + cbase) * prm.Cout);
+        for (int e = lane; e < n4; e += 32) {
+          const int r = (e * 4) / prm.Cout, c = (e * 4) % prm.Cout;
+          atomicAdd(blk + e, *reinterpret_cast<const float4*>(stg + r * pitch + c));
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -514,7 +571,9 @@ bool tc_wgrad_kdf_supported(const WgradGeom& wg, const WgP16* p16) {
   if (!on || p16 == nullptr) return false;
   // Cin = 32 only: with 64 input channels the per-tap kernel's M = 64 rows are all real (27 x ~33 cycles per K step vs
   // 2 channel tiles x 9 x ~45 here: measured 99 vs 112 us at 64^3 64->32)
-  if (!(wg.k == 3 && wg.s == 1 && wg.nA == 32 && (wg.nB == 16 || wg.nB == 32))) return false;
+  // Cin = 16: M = 64 with 48 real rows (in place of the TS-mode kernel, B3D_WGRAD_KDF16=0 keeps that one)
+  static const int on16 = [] { const char* e = getenv("B3D_WGRAD_KDF16"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+  if (!(wg.k == 3 && wg.s == 1 && (wg.nA == 32 || (wg.nA == 16 && on16)) && (wg.nB == 16 || wg.nB == 32))) return false;
   if (wg.Ws % 8 != 0 || wg.Hs % 2 != 0) return false;
   for (int i = 0; i < p16->n; ++i)
     if (p16->C[i] % 8 != 0) return false;
@@ -524,7 +583,7 @@ bool tc_wgrad_kdf_supported(const WgradGeom& wg, const WgP16* p16) {
 int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const WgP16& p16) {
   B3D_REQUIRE(tc_wgrad_kdf_supported(wg, &p16), B3D_ERR_UNSUPPORTED, "wgrad (kd in M): shape not supported");
   B3D_REQUIRE(((uintptr_t)dw & 15) == 0, B3D_ERR_LAYOUT, "wgrad: alignment");
-  const int Cin = wg.nA, Cout = wg.nB, nmt = Cin / 32;
+  const int Cin = wg.nA, Cout = wg.nB, nmt = 1, P = Cin / 8;
   static const int cand[][3] = {{1, 4, 8}, {2, 4, 8}, {2, 4, 16}, {2, 8, 16}, {4, 8, 16}, {4, 8, 32}};
   KdfParams p;
   memset(&p, 0, sizeof(p));
@@ -537,18 +596,18 @@ int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const 
   for (int i = 0; i < (int)(sizeof(cand) / sizeof(cand[0])); ++i) {
     const int TD = cand[i][0], TH = cand[i][1], TW = cand[i][2];
     if (found && (TD > wg.Ds * 2 || TH > wg.Hs * 2 || TW > wg.Ws * 2)) continue;
-    const int HD = TD + 2, HH = TH + (ntg == 3 ? 0 : 2), HW = TW + 2;
+    const int HD = TD + 2, HH = TH + (ntg == 3 ? 0 : 2), HW = TW;      // no w halo: the kw shifts are in the dy copies
     if (4 * HW > 256) continue;
     const int pslice = ((HH * HW * 16 + 127) / 128) * 128;
     // the A operand spans 16 M groups (M = 128) from the LAST depth slice a K step starts in: 12 are real, the rest
     // must still lie inside this stage's x region or the dy tile (never past the allocation): keep 4 slices of slack
-    const long long xbytes = (((long long)HD * 4 * pslice + 127) / 128) * 128;
+    const long long xbytes = (((long long)HD * P * pslice + 127) / 128) * 128;
     const int py = TD * TH * TW * 16;
-    const long long stage = ((xbytes + (long long)(Cout / 8) * py + 127) / 128) * 128;
+    const long long stage = ((xbytes + 3LL * (Cout / 8) * py + 127) / 128) * 128;
     for (int ns = 4; ns >= 2; --ns) {
       const long long last = (long long)(ns - 1) * stage;
       // last K step of the last stage: group 15 starts at (TD-1)*4 slices + 15 slices + h/w offset
-      if (ns * stage <= budget && last + ((long long)(TD - 1) * 4 + 16 + 1) * pslice <= budget) {
+      if (ns * stage <= budget && last + ((long long)(TD - 1) * P + 4 * P + 1) * pslice <= budget) {
         // prefer >= 3 stages (one thread issues ~28 small TMA boxes per tile: the pipeline needs the depth) over a
         // larger tile with 2
         if (found && ns < 3 && p.nstages >= 3) break;
@@ -560,7 +619,8 @@ int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const 
     }
   }
   B3D_REQUIRE(found, B3D_ERR_UNSUPPORTED, "wgrad (kd in M): no tile fits shared memory (Cin=%d Cout=%d)", Cin, Cout);
-  p.dw = dw; p.Cin = Cin; p.Cout = Cout;
+  p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.P = P;
+  { const char* e = getenv("B3D_KDF_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.ntd = (wg.Ds + p.TD - 1) / p.TD; p.nth = (wg.Hs + p.TH - 1) / p.TH; p.ntw = (wg.Ws + p.TW - 1) / p.TW;
   p.ntiles = wg.B * p.ntd * p.nth * p.ntw;
   int nsplit = sm_count() / (nmt * ntg);

@@ -67,7 +67,10 @@ CONV_CASES = [
     ((8, 8, 16), [64], 32, 3, 1, False),             # N' = 192, one pair per CTA
     ((4, 8, 16), [32, 32, 32], 32, 3, 1, False),     # three sources, 288 columns
     ((4, 6, 8), [16, 32], 16, 3, 1, False),          # unequal sources
-    # weight gradient with the depth taps folded into M (conv3_wgrad_kdf_kernel): Cin 32 | 64, Cout 16 | 32
+    # weight gradient with the depth taps folded into M (conv3_wgrad_kdf_kernel): Cin 16 (M = 64) | 32 (M = 128),
+    # Cout 16 | 32; the 64-channel cases stay on the per-tap kernel
+    ((5, 6, 24), [16], 32, 3, 1, False),             # M = 64, partial tiles
+    ((9, 10, 8), [16], 16, 3, 1, False),             # M = 64, partial tiles in d and h
     ((8, 16, 16), [32], 32, 3, 1, False),
     ((5, 6, 24), [16, 16], 16, 3, 1, False),         # two sources inside one channel tile, partial tiles
     ((4, 8, 8), [32, 32], 32, 3, 1, False),          # two channel tiles
