@@ -310,7 +310,11 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
   memset(&p, 0, sizeof(p));
   const int budget = kWgSmem - 128;
   bool found = false;
+  // timing experiments only: B3D_KDF_TILE = candidate index, B3D_KDF_NS = stage count
+  static const int force_tile = [] { const char* e = getenv("B3D_KDF_TILE"); return e ? atoi(e) : -1; }();
+  static const int force_ns = [] { const char* e = getenv("B3D_KDF_NS"); return e ? atoi(e) : 0; }();
   for (int i = 0; i < (int)(sizeof(cand) / sizeof(cand[0])); ++i) {
+    if (force_tile >= 0 && i != force_tile) continue;
     const int TD = cand[i][0], TH = cand[i][1], TW = cand[i][2];
     if (found && (TD > wg.Ds * 2 || TH > wg.Hs * 2 || TW > wg.Ws * 2)) continue;   // do not over-tile tiny volumes
     const int HD = TD + (allD ? KS - 1 : 0), HH = TH + (allH ? KS - 1 : 0), HW = TW + (allW ? KS - 1 : 0);
@@ -569,11 +573,12 @@ __global__ void __launch_bounds__(256, 1)
 bool tc_wgrad_kdf_supported(const WgradGeom& wg, const WgP16* p16) {
   static const int on = [] { const char* e = getenv("B3D_WGRAD_KDF"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
   if (!on || p16 == nullptr) return false;
-  // Cin = 32 only: with 64 input channels the per-tap kernel's M = 64 rows are all real (27 x ~33 cycles per K step vs
-  // 2 channel tiles x 9 x ~45 here: measured 99 vs 112 us at 64^3 64->32)
-  // Cin = 16: M = 64 with 48 real rows (in place of the TS-mode kernel, B3D_WGRAD_KDF16=0 keeps that one)
+  // Cin = 16: M = 64 with 48 real rows (in place of the TS-mode kernel, B3D_WGRAD_KDF16=0 keeps that one); Cin = 64 /
+  // 96 / 128: one CTA row per 32-channel tile (B3D_WGRAD_KDF64=0 keeps the per-tap kernel)
   static const int on16 = [] { const char* e = getenv("B3D_WGRAD_KDF16"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
-  if (!(wg.k == 3 && wg.s == 1 && (wg.nA == 32 || (wg.nA == 16 && on16)) && (wg.nB == 16 || wg.nB == 32))) return false;
+  static const int on64 = [] { const char* e = getenv("B3D_WGRAD_KDF64"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+  const bool cin_ok = wg.nA == 32 || (wg.nA == 16 && on16) || (on64 && wg.nA % 32 == 0 && wg.nA <= 128);
+  if (!(wg.k == 3 && wg.s == 1 && cin_ok && (wg.nB == 16 || wg.nB == 32))) return false;
   if (wg.Ws % 8 != 0 || wg.Hs % 2 != 0) return false;
   for (int i = 0; i < p16->n; ++i)
     if (p16->C[i] % 8 != 0) return false;
@@ -583,17 +588,25 @@ bool tc_wgrad_kdf_supported(const WgradGeom& wg, const WgP16* p16) {
 int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const WgP16& p16) {
   B3D_REQUIRE(tc_wgrad_kdf_supported(wg, &p16), B3D_ERR_UNSUPPORTED, "wgrad (kd in M): shape not supported");
   B3D_REQUIRE(((uintptr_t)dw & 15) == 0, B3D_ERR_LAYOUT, "wgrad: alignment");
-  const int Cin = wg.nA, Cout = wg.nB, nmt = 1, P = Cin / 8;
+  const int Cin = wg.nA, Cout = wg.nB, P = Cin == 16 ? 2 : 4, nmt = Cin / (8 * P);
   static const int cand[][3] = {{1, 4, 8}, {2, 4, 8}, {2, 4, 16}, {2, 8, 16}, {4, 8, 16}, {4, 8, 32}};
   KdfParams p;
   memset(&p, 0, sizeof(p));
   // small volumes: split the kh taps over 3 CTA groups (fewer final atomics per CTA, all SMs still busy)
   const long long vox = (long long)wg.B * wg.Ds * wg.Hs * wg.Ws;
-  const int ntg = vox / 512 < 16LL * (sm_count() / nmt) ? 3 : 1;
+  static const int force_ntg = [] { const char* e = getenv("B3D_KDF_NTG"); return e ? atoi(e) : 0; }();
+  // kh groups over blockIdx.z (ntg = 3) measured slower everywhere once the final reduction was vectorised (64^3
+  // 32->32: 64 vs 36 us): kept for experiments only
+  const int ntg = force_ntg ? force_ntg : 1;
+  (void)vox;
   p.ntg = ntg;
   const int budget = kWgSmem - 128;
   bool found = false;
+  // timing experiments only: B3D_KDF_TILE = candidate index, B3D_KDF_NS = stage count
+  static const int force_tile = [] { const char* e = getenv("B3D_KDF_TILE"); return e ? atoi(e) : -1; }();
+  static const int force_ns = [] { const char* e = getenv("B3D_KDF_NS"); return e ? atoi(e) : 0; }();
   for (int i = 0; i < (int)(sizeof(cand) / sizeof(cand[0])); ++i) {
+    if (force_tile >= 0 && i != force_tile) continue;
     const int TD = cand[i][0], TH = cand[i][1], TW = cand[i][2];
     if (found && (TD > wg.Ds * 2 || TH > wg.Hs * 2 || TW > wg.Ws * 2)) continue;
     const int HD = TD + 2, HH = TH + (ntg == 3 ? 0 : 2), HW = TW;      // no w halo: the kw shifts are in the dy copies
@@ -604,13 +617,10 @@ int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const 
     const long long xbytes = (((long long)HD * P * pslice + 127) / 128) * 128;
     const int py = TD * TH * TW * 16;
     const long long stage = ((xbytes + 3LL * (Cout / 8) * py + 127) / 128) * 128;
-    for (int ns = 4; ns >= 2; --ns) {
+    for (int ns = force_ns > 0 ? force_ns : 4; ns >= 2; --ns) {
       const long long last = (long long)(ns - 1) * stage;
       // last K step of the last stage: group 15 starts at (TD-1)*4 slices + 15 slices + h/w offset
       if (ns * stage <= budget && last + ((long long)(TD - 1) * P + 4 * P + 1) * pslice <= budget) {
-        // prefer >= 3 stages (one thread issues ~28 small TMA boxes per tile: the pipeline needs the depth) over a
-        // larger tile with 2
-        if (found && ns < 3 && p.nstages >= 3) break;
         p.TD = TD; p.TH = TH; p.TW = TW; p.HD = HD; p.HH = HH; p.HW = HW;
         p.pslice = pslice; p.py = py; p.xbytes = (int)xbytes; p.stage_bytes = (int)stage; p.nstages = ns;
         found = true;
