@@ -139,6 +139,7 @@ SIGNATURES = {
     "b3d_conv3d_dgrad_p16_block": "TTTTTTTTTTv",
     "b3d_conv3d_dgrad_p16": "TTTiiiTv",
     "b3d_conv3d_wgrad_p16": "TTTTTTiiTv",
+    "b3d_conv3d_wgrad_p16_block": "TTTTTTTTv",
     "b3d_gn_apply_p16": "TTTTTTTifiv",
     "b3d_gn_bwd_apply_p16": "TTTTTTTTTifiv",
     "b3d_block_epilogue_fwd_p16": "TTTTTTTTTTifiv",
@@ -167,6 +168,8 @@ lib.b3d_slab_sym_bytes.restype = _ll
 lib.b3d_get_conv_precision.restype = _i
 lib.b3d_conv3d_wgrad_p16_plan.argtypes = [_i] * 6
 lib.b3d_conv3d_wgrad_p16_plan.restype = _i
+lib.b3d_conv3d_wgrad_p16_block_ok.argtypes = [_i] * 4
+lib.b3d_conv3d_wgrad_p16_block_ok.restype = _i
 
 
 class B3DError(RuntimeError):

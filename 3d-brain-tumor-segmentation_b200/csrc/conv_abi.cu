@@ -647,6 +647,57 @@ extern "C" int b3d_conv3d_wgrad_p16_plan(int k, int stride, int transposed, int 
   return (g_wgrad_ts && tc_wgrad_ts_supported(wg)) ? 3 : 1;
 }
 
+// Both weight gradients of a ResnetBlock's input convs in one pass over x (resnet.py:118 pointwise, :133 first 3x3x3):
+// dw = the 3x3x3 layer's (x, dy), dw_pw = the pointwise layer's (x, dres).  kd-in-M kernel only (stride 1, Cin = 16 or a
+// multiple of 32 up to 128, Cout 16 | 32, W % 8 == 0, H % 2 == 0): b3d_conv3d_wgrad_p16_block_ok tells.
+extern "C" int b3d_conv3d_wgrad_p16_block_ok(int cin, int cout, int h_sp, int w_sp) {
+  WgradGeom wg;
+  memset(&wg, 0, sizeof(wg));
+  wg.k = 3; wg.s = 1; wg.nA = cin; wg.nB = cout; wg.Ws = w_sp; wg.Hs = h_sp;
+  WgP16 wp;
+  memset(&wp, 0, sizeof(wp));
+  wp.n = 1; wp.C[0] = cin; wp.big_bf16 = wp.small_bf16 = 1;
+  return tc_wgrad_kdf_supported(wg, &wp) ? 1 : 0;
+}
+
+extern "C" int b3d_conv3d_wgrad_p16_block(const DLTensor* x0_, const DLTensor* x1_, const DLTensor* x2_,
+                                          const DLTensor* x3_, const DLTensor* dy_, const DLTensor* dres_, DLTensor* dw_,
+                                          DLTensor* dw_pw_, void* stream) {
+  const DLTensor* xs[4] = {x0_, x1_, x2_, x3_};
+  TcSources src;
+  P16View xf, dy, dres;
+  int cin;
+  B3D_TRY(p16_sources(xs, &src, &xf, &cin));
+  B3D_TRY(view_p16(dy_, "dy (P16)", &dy));
+  B3D_TRY(view_p16(dres_, "dres (P16)", &dres));
+  TView dw, dwp;
+  int k, kp;
+  B3D_TRY(weight_view(dw_, &dw, &k));
+  B3D_TRY(weight_view(dw_pw_, &dwp, &kp));
+  const int cout = 8 * dy.C8;
+  B3D_REQUIRE(k == 3 && kp == 1, B3D_ERR_SHAPE, "wgrad (block): a 3x3x3 and a 1x1x1 kernel");
+  B3D_REQUIRE(xf.bf16 && dy.bf16 && dres.bf16, B3D_ERR_DTYPE, "wgrad (block): bf16 twins of all operands");
+  B3D_REQUIRE(dres.B == dy.B && dres.D == dy.D && dres.H == dy.H && dres.W == dy.W && dres.C8 == dy.C8, B3D_ERR_SHAPE,
+              "wgrad (block): dres must match dy");
+  B3D_REQUIRE(xf.B == dy.B && xf.D == dy.D && xf.H == dy.H && xf.W == dy.W, B3D_ERR_SHAPE, "wgrad (block): spatial dims");
+  B3D_REQUIRE(dw.shape[3] == cin && dw.shape[4] == cout && dwp.shape[3] == cin && dwp.shape[4] == cout, B3D_ERR_SHAPE,
+              "wgrad (block): dw channel dims");
+  WgradGeom wg;
+  memset(&wg, 0, sizeof(wg));
+  wg.B = xf.B; wg.Db = xf.D; wg.Hb = xf.H; wg.Wb = xf.W; wg.nA = cin;
+  wg.Ds = dy.D; wg.Hs = dy.H; wg.Ws = dy.W; wg.nB = cout;
+  wg.k = 3; wg.s = 1; wg.pad = 1;
+  wg.bigp = cin; wg.smallp = cout;
+  WgP16 wp;
+  memset(&wp, 0, sizeof(wp));
+  wp.small = dy.p; wp.small_bf16 = 1; wp.big_bf16 = 1;
+  wp.n = src.n;
+  for (int i = 0; i < src.n; ++i) { wp.big[i] = src.p[i]; wp.C[i] = src.C[i]; }
+  B3D_REQUIRE(tc_wgrad_kdf_supported(wg, &wp), B3D_ERR_UNSUPPORTED, "wgrad (block): layer not on the kd-in-M path (%d->%d)",
+              cin, cout);
+  return launch_conv_wgrad_kdf(wg, (float*)dw.p, (cudaStream_t)stream, wp, dres.p, (float*)dwp.p);
+}
+
 // dw of a Conv3D (x = layer input, up to 4 concatenated P16 sources; dy = P16 gradient of the output) or of a
 // Conv3DTranspose (transposed = 1: single source).  The bias gradient is NOT produced here: on this path it is emitted
 // by the kernel that writes dy (b3d_gn_bwd_apply / b3d_block_epilogue_bwd_apply, `dbias`).

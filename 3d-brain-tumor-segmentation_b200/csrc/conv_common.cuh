@@ -132,7 +132,8 @@ int launch_conv_wgrad_ts(const WgradGeom& wg, const void* x_bf16, const void* dy
                          int x_p16 = 0, int x_f16 = 0);
 // 3x3x3 weight gradient with the depth taps folded into M (conv_tc_wgrad.cu): Cin 32 | 64, Cout 16 | 32, P16 sources
 bool tc_wgrad_kdf_supported(const WgradGeom& wg, const WgP16* p16);
-int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const WgP16& p16);
+int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const WgP16& p16,
+                          const void* dres = nullptr, float* dw2 = nullptr);
 // kh-folded TS-mode weight gradient (conv_tc_wgrad_ts.cu): P16 sources (virtual concat), Cout 16 | 32
 bool tc_wgrad_tsf_supported(const WgradGeom& wg, const WgP16* p16);
 int launch_conv_wgrad_tsf(const WgradGeom& wg, const WgP16& src, const void* dyT_bf16, float* dw, cudaStream_t s);

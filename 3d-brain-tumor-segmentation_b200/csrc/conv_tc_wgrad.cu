@@ -67,6 +67,7 @@ struct WgParams {
 struct alignas(64) WgMaps {
   CUtensorMap x[4];
   CUtensorMap y;
+  CUtensorMap y2;      // kd-in-M kernel only: gradient of the block's pointwise conv output (same x, second dw)
 };
 
 constexpr int kWgSmem = 227 * 1024;
@@ -405,6 +406,8 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
 // spread over the CTAs (and the kh taps over blockIdx.z for small volumes).
 struct KdfParams {
   float* dw;
+  float* dw2;                      // != nullptr: also dw of the pointwise conv reading the same x, [Cin][Cout]: one more
+                                   // MMA per K step (A = the centre rows of the x tile, B = a tile of its dy)
   int Cin, Cout;
   int TD, TH, TW, HD, HH, HW;
   int pslice;                      // pitch of one (plane, depth slice) of the halo: HH * HW * 16 bytes padded to 128
@@ -412,6 +415,7 @@ struct KdfParams {
   int xbytes, stage_bytes, nstages;
   int ntd, nth, ntw, ntiles, nsplit;
   int nsrc, cend8[4];
+  int pf;                          // L2 prefetch distance in tile rounds (0: off)
   int dbg;                         // timing experiments only (B3D_KDF_DBG): 1 no MMAs, 2 one dy copy, 4 one x slice,
                                    // 8 no final reduction
   int P;                           // channel planes (octets) of the tile: 4 (Cin = 32, M = 128) or 2 (Cin = 16, M = 64)
@@ -453,7 +457,8 @@ __global__ void __launch_bounds__(256, 1)
     // producer warp: lane 0 waits for the slot and arms the barrier, then the lanes issue the tile's boxes in parallel
     // (HD * P halo slices of x + 3 * yplanes planes of dy: 20-40 small boxes, too many for one thread per tile)
     int s = 0, ph = 0;
-    const int nxb = (prm.dbg & 4) ? 1 : prm.HD * P, nbox = nxb + ((prm.dbg & 2) ? 1 : 3) * yplanes;
+    const int nxb = (prm.dbg & 4) ? 1 : prm.HD * P, nyb = ((prm.dbg & 2) ? 1 : 3) * yplanes;
+    const int nbox = nxb + nyb + (prm.dw2 != nullptr ? yplanes : 0);
     const uint32_t bytes = (uint32_t)(nxb * prm.HH * prm.HW * 16 + (nbox - nxb) * prm.py);
     for (int tile = blockIdx.x; tile < prm.ntiles; tile += prm.nsplit) {
       int t = tile;
@@ -482,7 +487,30 @@ __global__ void __launch_bounds__(256, 1)
           // dy three times, shifted by 1 - kw voxels along w (zero fill outside the volume): copy kw at in-tile voxel u
           // holds dy[u - (kw - 1)], the partner of x[u + (kd - 1, kh - 1, 0)]
           const int jj = j - nxb, kw = jj / yplanes, q = jj - kw * yplanes;
-          tma_load_5d(ydst + jj * prm.py, &maps.y, 4 * (w0 + 1 - kw), q, h0, d0, b, fb);
+          if (jj < nyb) tma_load_5d(ydst + jj * prm.py, &maps.y, 4 * (w0 + 1 - kw), q, h0, d0, b, fb);
+          else tma_load_5d(ydst + (3 * yplanes + q) * prm.py, &maps.y2, 4 * w0, q, h0, d0, b, fb);
+        }
+      }
+      // L2 prefetch of the tile `pf` rounds ahead: a TMA load that misses L2 holds its request slots for the DRAM
+      // latency, and the per-SM fill rate follows (outstanding requests / latency)
+      const int ptile = tile + prm.pf * prm.nsplit;
+      if (prm.pf > 0 && ptile < prm.ntiles) {
+        int u = ptile;
+        const int pwt = u % prm.ntw; u /= prm.ntw;
+        const int pht = u % prm.nth; u /= prm.nth;
+        const int pdt = u % prm.ntd; u /= prm.ntd;
+        const int pw0 = pwt * prm.TW, ph0 = pht * prm.TH, pd0 = pdt * prm.TD;
+        for (int j = lane; j < nxb + yplanes; j += 32) {
+          if (j < nxb) {
+            const int d = j / P, p = j - d * P;
+            const int gp = (cbase >> 3) + p;
+            int si = 0;
+            while (si + 1 < prm.nsrc && gp >= prm.cend8[si]) ++si;
+            const int lp = gp - (si > 0 ? prm.cend8[si - 1] : 0);
+            tma_prefetch_5d(&maps.x[si], 4 * pw0, lp, ph0 - 1 + kh0, pd0 - 1 + d, u);
+          } else {
+            tma_prefetch_5d(&maps.y, 4 * pw0, j - nxb, ph0, pd0, u);
+          }
         }
       }
       __syncwarp();
@@ -493,6 +521,8 @@ __global__ void __launch_bounds__(256, 1)
     // D = f32, A = B = bf16, both MN-major, N = 3 Cout (columns (kw, co)), M = 128 / 64 (rows (kd, ci): 96 / 48 real)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                            ((uint32_t)((3 * prm.Cout) >> 3) << 17) | (((uint32_t)(32 * P) >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                            ((uint32_t)(prm.Cout >> 3) << 17) | (((uint32_t)(32 * P) >> 4) << 24);
     int s = 0, ph = 0;
     uint32_t acc = 0;
     const uint32_t smem_base = smem_u32(smem);
@@ -505,6 +535,8 @@ __global__ void __launch_bounds__(256, 1)
       // B: the same K cells of the three dy copies, N groups (kw, plane) one dy plane apart
       const uint64_t adesc0 = make_desc(xaddr, (uint32_t)prm.HW * 16, (uint32_t)prm.pslice);
       const uint64_t bdesc0 = make_desc(xaddr + (uint32_t)prm.xbytes, (uint32_t)prm.TW * 16, (uint32_t)prm.py);
+      const uint64_t bdesc2 = make_desc(xaddr + (uint32_t)(prm.xbytes + 3 * yplanes * prm.py), (uint32_t)prm.TW * 16,
+                                        (uint32_t)prm.py);
       for (int d = 0; d < prm.TD; ++d)
         for (int h = 0; h < prm.TH; h += 2)
           for (int w8 = 0; w8 < prm.TW; w8 += 8) {
@@ -517,6 +549,9 @@ __global__ void __launch_bounds__(256, 1)
                 tc_mma_bf16(tmem_base + t * 3 * prm.Cout, adesc0 + xcell + (uint32_t)(t * prm.HW), bdesc0 + ycell, idesc,
                             acc);
               }
+              // pointwise conv: rows kd = 1 of the centre (kh = 1) A operand are x[u] itself
+              if (prm.dw2 != nullptr)
+                tc_mma_bf16(tmem_base + 9 * prm.Cout, adesc0 + xcell + (uint32_t)prm.HW, bdesc2 + ycell, idesc2, acc);
             }
             acc = 1;
           }
@@ -542,8 +577,8 @@ __global__ void __launch_bounds__(256, 1)
     float* stg = reinterpret_cast<float*>(smem) + q * 32 * pitch;
     const int n4 = 8 * P * prm.Cout / 4;
 #pragma unroll 1
-    for (int tt = 0; tt < nt; ++tt) {
-      const int t = (tt + (int)blockIdx.x) % nt;
+    for (int tt = 0; tt < nt + (prm.dw2 != nullptr ? 1 : 0); ++tt) {
+      const int t = tt < nt ? (tt + (int)blockIdx.x) % nt : 9;      // 9: the pointwise accumulator (rows kd = 1 only)
       for (int j = 0; j < prm.Cout; j += 16) {
         float v[16];
         tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + t * prm.Cout + j, v);
@@ -552,8 +587,9 @@ __global__ void __launch_bounds__(256, 1)
           *reinterpret_cast<float4*>(stg + lane * pitch + j + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
       __syncwarp();
-      if (live) {
-        float4* blk = reinterpret_cast<float4*>(prm.dw + ((size_t)(kd * 9 + kh0 * 3 + t) * prm.Cin + cbase) * prm.Cout);
+      if (live && (t < 9 || kd == 1)) {
+        float4* blk = reinterpret_cast<float4*>(
+            t < 9 ? prm.dw + ((size_t)(kd * 9 + kh0 * 3 + t) * prm.Cin + cbase) * prm.Cout : prm.dw2 + (size_t)cbase * prm.Cout);
         for (int e = lane; e < n4; e += 32) {
           const int r = (e * 4) / prm.Cout, c = (e * 4) % prm.Cout;
           atomicAdd(blk + e, *reinterpret_cast<const float4*>(stg + r * pitch + c));
@@ -585,11 +621,12 @@ bool tc_wgrad_kdf_supported(const WgradGeom& wg, const WgP16* p16) {
   return p16->big_bf16 && p16->small_bf16;
 }
 
-int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const WgP16& p16) {
+int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const WgP16& p16, const void* dres,
+                          float* dw2) {
   B3D_REQUIRE(tc_wgrad_kdf_supported(wg, &p16), B3D_ERR_UNSUPPORTED, "wgrad (kd in M): shape not supported");
   B3D_REQUIRE(((uintptr_t)dw & 15) == 0, B3D_ERR_LAYOUT, "wgrad: alignment");
   const int Cin = wg.nA, Cout = wg.nB, P = Cin == 16 ? 2 : 4, nmt = Cin / (8 * P);
-  static const int cand[][3] = {{1, 4, 8}, {2, 4, 8}, {2, 4, 16}, {2, 8, 16}, {4, 8, 16}, {4, 8, 32}};
+  static const int cand[][3] = {{1, 4, 8}, {2, 4, 8}, {2, 4, 16}, {2, 8, 16}, {3, 8, 16}, {4, 8, 16}, {4, 8, 32}};
   KdfParams p;
   memset(&p, 0, sizeof(p));
   // small volumes: split the kh taps over 3 CTA groups (fewer final atomics per CTA, all SMs still busy)
@@ -616,7 +653,7 @@ int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const 
     // must still lie inside this stage's x region or the dy tile (never past the allocation): keep 4 slices of slack
     const long long xbytes = (((long long)HD * P * pslice + 127) / 128) * 128;
     const int py = TD * TH * TW * 16;
-    const long long stage = ((xbytes + 3LL * (Cout / 8) * py + 127) / 128) * 128;
+    const long long stage = ((xbytes + (dw2 != nullptr ? 4LL : 3LL) * (Cout / 8) * py + 127) / 128) * 128;
     for (int ns = force_ns > 0 ? force_ns : 4; ns >= 2; --ns) {
       const long long last = (long long)(ns - 1) * stage;
       // last K step of the last stage: group 15 starts at (TD-1)*4 slices + 15 slices + h/w offset
@@ -629,8 +666,11 @@ int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const 
     }
   }
   B3D_REQUIRE(found, B3D_ERR_UNSUPPORTED, "wgrad (kd in M): no tile fits shared memory (Cin=%d Cout=%d)", Cin, Cout);
-  p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.P = P;
+  p.dw = dw; p.dw2 = dw2; p.Cin = Cin; p.Cout = Cout; p.P = P;
+  B3D_REQUIRE((dw2 == nullptr) == (dres == nullptr) && (dw2 == nullptr || (ntg == 1 && ((uintptr_t)dw2 & 15) == 0)),
+              B3D_ERR_ARG, "wgrad (kd in M): pointwise operands");
   { const char* e = getenv("B3D_KDF_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { static const int pf = [] { const char* e = getenv("B3D_KDF_PF"); return e ? atoi(e) : 0; }(); p.pf = pf; }
   p.ntd = (wg.Ds + p.TD - 1) / p.TD; p.nth = (wg.Hs + p.TH - 1) / p.TH; p.ntw = (wg.Ws + p.TW - 1) / p.TW;
   p.ntiles = wg.B * p.ntd * p.nth * p.ntw;
   int nsplit = sm_count() / (nmt * ntg);
@@ -650,6 +690,10 @@ int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const 
   B3D_REQUIRE(cum * 8 == Cin, B3D_ERR_SHAPE, "wgrad (kd in M): sources hold %d channels, expected %d", cum * 8, Cin);
   B3D_TRY(make_p16_map(&maps.y, p16.small, 1, wg.B, wg.Ds, wg.Hs, wg.Ws, Cout / 8, p.TW, 1, p.TH, p.TD));
   B3D_TRY(cuda_ok(cudaMemsetAsync(dw, 0, sizeof(float) * 27 * (size_t)Cin * Cout, s), "memset dw"));
+  if (dw2 != nullptr) {
+    B3D_TRY(make_p16_map(&maps.y2, dres, 1, wg.B, wg.Ds, wg.Hs, wg.Ws, Cout / 8, p.TW, 1, p.TH, p.TD));
+    B3D_TRY(cuda_ok(cudaMemsetAsync(dw2, 0, sizeof(float) * (size_t)Cin * Cout, s), "memset dw (pointwise)"));
+  }
   static bool attr = false;
   if (!attr) {
     B3D_TRY(cuda_ok(cudaFuncSetAttribute(conv3_wgrad_kdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem),

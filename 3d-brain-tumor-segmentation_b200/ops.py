@@ -239,6 +239,10 @@ SHARE_DGRAD = {"on": _os_env_flag("B3D_SHARE_DGRAD", True)}
 # segment that is used at the centre tap only (b3d_conv3d_dgrad_p16_block) — no pointwise data-gradient launch at all.
 # Needs SHARE_DGRAD (the two convs find each other through the block's grad_box).  B3D_FUSE_BLOCK_DGRAD=0 for A/B runs.
 FUSE_BLOCK_DGRAD = {"on": _os_env_flag("B3D_FUSE_BLOCK_DGRAD", True)}
+# The same pair of convs shares its input in the weight-gradient pass too: where the 3x3x3 layer runs on the kd-in-M
+# kernel (csrc/conv_tc_wgrad.cu) the pointwise layer's dw is one more MMA per K step over the x tile already in shared
+# memory (b3d_conv3d_wgrad_p16_block) instead of a second pass over x.  B3D_FUSE_BLOCK_WGRAD=0 for A/B runs.
+FUSE_BLOCK_WGRAD = {"on": _os_env_flag("B3D_FUSE_BLOCK_WGRAD", True)}
 # the encoder's dense connections list the previous block output twice; inside a Model the duplicate is
 # dropped and its weight slice folded into the other one (ops.FoldDupFn) — exact.  B3D_DEDUP=0 for A/B runs
 DEDUP = {"on": _os_env_flag("B3D_DEDUP", True)}
@@ -526,7 +530,8 @@ class Conv3dFn(Function):
             k, stride, int(transposed), Cin, Cout, od[2]) != 0)
         ctx.mb = y._b3d_mb = {"bias": bias, "f32_grad": f32_grad}
         if grad_box is not None and k == 1 and stride == 1 and not transposed:
-            grad_box["pw"] = {"mb": ctx.mb, "w": w}      # the block's pointwise conv: see FUSE_BLOCK_DGRAD
+            # the block's pointwise conv: see FUSE_BLOCK_DGRAD / FUSE_BLOCK_WGRAD
+            grad_box["pw"] = {"mb": ctx.mb, "w": w, "srcs_w": ctx.srcs_w}
         outs = (y, stats, gap)
         ctx.mark_non_differentiable(*[t for t in (stats, gap) if t is not None])
         return outs
@@ -628,8 +633,36 @@ class Conv3dFn(Function):
                 dy = materialize(dy)
                 _call("b3d_conv3d_dgrad", dy, w, dx_buf, stride, int(transposed), acc, wp)
         if need_dw:
+            pwbox = ctx.grad_box.get("pw") if ctx.grad_box is not None else None
+            pre = pwbox.pop("dw", None) if (pwbox is not None and pwbox["mb"] is mb) else None
+            if pre is not None:                    # this pointwise conv's dw came out of the 3x3x3 layer's kernel
+                dw, dw_direct = pre
+                if has_bias and not bias_done:
+                    _call("b3d_colsum", materialize(dy), db)
+                _grad_done(pw, dw_direct)
+                if has_bias:
+                    _grad_done(pb, db_direct)
+                return (dx, None if dw_direct else dw, None if (db_direct or not has_bias) else db,
+                        None, None, None, None, None, None, None)
+            if pwbox is not None and pwbox["mb"] is mb:
+                pwbox["done"] = True
             dw, dw_direct = _grad_target(pw)
-            if plan and dy16 is not None:
+            fuse_w = None
+            if (FUSE_BLOCK_WGRAD["on"] and plan and dy16 is not None and pwbox is not None and pwbox["mb"] is not mb
+                    and not pwbox.get("done") and k == 3 and stride == 1 and not transposed
+                    and pwbox["w"].requires_grad and _same_sources(pwbox.get("srcs_w"), srcs_w)):
+                dres16 = pwbox["mb"].get("dy16")
+                if dres16 is not None and dres16.dtype == dy16.dtype and tuple(dres16.shape) == tuple(dy16.shape) and \
+                        lib.b3d_conv3d_wgrad_p16_block_ok(cin, cout, dy.shape[2], dy.shape[3]):
+                    fuse_w = dres16
+            if fuse_w is not None:
+                dwp, dwp_direct = _grad_target(pwbox["w"])
+                _tag_conv(w, ctx.nv, stride, transposed)
+                _call("b3d_conv3d_wgrad_p16_block", *_pad4(srcs_w), dy16, fuse_w, dw, dwp)
+                pwbox["dw"] = (dwp, dwp_direct)
+                if has_bias and not bias_done:
+                    _call("b3d_colsum", materialize(dy), db)
+            elif plan and dy16 is not None:
                 scratch = None
                 if plan == 2:
                     n = dy16.numel() if transposed else sum(t.numel() for t in srcs_w)
@@ -669,6 +702,11 @@ class Conv3dFn(Function):
                 _grad_done(pb, db_direct)
             dw, db = (None if dw_direct else dw), (None if (db_direct or not has_bias) else db)
         return dx, dw, db, None, None, None, None, None, None, None
+
+
+def _same_sources(a, b):
+    return a is not None and b is not None and len(a) == len(b) and all(
+        u.data_ptr() == v.data_ptr() and u.shape == v.shape and u.dtype == v.dtype for u, v in zip(a, b))
 
 
 class FoldDupFn(Function):

@@ -328,6 +328,13 @@ int b3d_conv3d_dgrad_p16_block(const DLTensor* dy /*P16*/, const DLTensor* dres 
 int b3d_conv3d_wgrad_p16(const DLTensor* x0, const DLTensor* x1, const DLTensor* x2, const DLTensor* x3,
                          const DLTensor* dy /*P16*/, DLTensor* dw, int stride, int transposed, DLTensor* scratch,
                          void* stream);
+/* both weight gradients of the convs reading a ResnetBlock's input (/root/reference/layers/resnet.py:118 pointwise, :133
+ * first 3x3x3) in one pass over x: dw <- (x, dy), dw_pw <- (x, dres).  Only where b3d_conv3d_wgrad_p16_block_ok(cin,
+ * cout, H, W) returns 1 (else B3D_ERR_UNSUPPORTED: call b3d_conv3d_wgrad_p16 twice). */
+int b3d_conv3d_wgrad_p16_block(const DLTensor* x0, const DLTensor* x1, const DLTensor* x2, const DLTensor* x3,
+                               const DLTensor* dy /*P16*/, const DLTensor* dres /*P16*/, DLTensor* dw, DLTensor* dw_pw,
+                               void* stream);
+int b3d_conv3d_wgrad_p16_block_ok(int cin, int cout, int h_sp, int w_sp);
 /* 0: the layer's weight gradient is not on the P16 path; 1: straight from the operands; 2: needs a 16-bit scratch of
  * numel(big tensor) elements (stride-2 family); 3: of numel(dy) elements (TS-mode kernel).  w_sp = W of dy. */
 int b3d_conv3d_wgrad_p16_plan(int k, int stride, int transposed, int cin, int cout, int w_sp);

@@ -29,7 +29,8 @@ def test_python_signatures_cover_header(b3d):
     declared = set(_declared()) - {"b3d_last_error", "b3d_abi_version", "b3d_conv3d_tc_supported",
                                    "b3d_conv3d_packed_elems", "b3d_conv3d_wgrad_tc_supported", "b3d_conv3d_wgrad_plan", "b3d_slab_sym_bytes", "b3d_set_wgrad_ts", "b3d_conv3d_pack_job", "b3d_conv3d_pack_job_bytes", "b3d_set_conv_kdfold",
                                    "b3d_set_conv_precision",
-                                   "b3d_get_conv_precision", "b3d_conv3d_wgrad_p16_plan"}
+                                   "b3d_get_conv_precision", "b3d_conv3d_wgrad_p16_plan",
+                                   "b3d_conv3d_wgrad_p16_block_ok"}
     assert declared == set(b3d._lib.SIGNATURES), declared ^ set(b3d._lib.SIGNATURES)
 
 

@@ -198,6 +198,40 @@ def test_block_input_data_gradient_in_one_kernel(b3d, dev, case):
     assert rel(torch.cat(outs3, dim=-1), ref3) < 2e-6
 
 
+@pytest.mark.parametrize("case", [((8, 16, 8), [16], 16), ((9, 10, 24), [32], 16), ((8, 16, 16), [16, 16], 32),
+                                  ((4, 16, 16), [32, 64], 32), ((5, 6, 16), [16], 32), ((4, 8, 8), [64, 32, 32], 16)])
+def test_block_weight_gradients_in_one_kernel(b3d, dev, case):
+    """b3d_conv3d_wgrad_p16_block: dw of conv3x3x3(x, .) and of conv1x1x1(x, .) in ONE launch of the kd-in-M kernel (the
+    pointwise layer is one more MMA per K step over the x tile in shared memory) against the two separate weight
+    gradients from the same bf16 operands (same products, different summation order) and against fp64."""
+    sp, pieces, cb = case
+    ops = b3d.ops
+    cin = sum(pieces)
+    assert b3d._lib.lib.b3d_conv3d_wgrad_p16_block_ok(cin, cb, sp[1], sp[2]) == 1
+    xs = [rnd(2, *sp, c, seed=11 + i, dev=dev) for i, c in enumerate(pieces)]
+    xs16 = [ops.to_p16(t, torch.bfloat16) for t in xs]
+    dy, dres = rnd(2, *sp, cb, seed=7, dev=dev), rnd(2, *sp, cb, seed=8, dev=dev)
+    dy16, dres16 = ops.to_p16(dy, torch.bfloat16), ops.to_p16(dres, torch.bfloat16)
+    pad = xs16 + [None] * (4 - len(xs16))
+    ref3, ref1 = torch.empty(3, 3, 3, cin, cb, device=dev), torch.empty(1, 1, 1, cin, cb, device=dev)
+    plan = b3d._lib.lib.b3d_conv3d_wgrad_p16_plan(3, 1, 0, cin, cb, sp[2])
+    scratch = torch.empty(dy16.numel(), device=dev, dtype=torch.bfloat16) if plan == 3 else None
+    ops._call("b3d_conv3d_wgrad_p16", *pad, dy16, ref3, 1, 0, scratch)
+    ops._call("b3d_conv3d_wgrad_p16", *pad, dres16, ref1, 1, 0, None)
+    dw3 = torch.full_like(ref3, float("nan"))
+    dw1 = torch.full_like(ref1, float("nan"))
+    ops._call("b3d_conv3d_wgrad_p16_block", *pad, dy16, dres16, dw3, dw1)
+    assert rel(dw3, ref3) < 2e-6, rel(dw3, ref3)
+    assert rel(dw1, ref1) < 2e-6, rel(dw1, ref1)
+    # fp64 reference from the bf16-rounded operands
+    xr = torch.cat([t.bfloat16().float() for t in xs], dim=-1)
+    e1 = torch.einsum("bdhwi,bdhwo->io", xr.double(), dres.bfloat16().double())
+    assert rel(dw1[0, 0, 0].double(), e1) < 1e-5
+    assert rel(dw3.double().cpu(), _dw_ref(xr.double(), dy.bfloat16().double(), 3, 1, False)) < 1e-5
+    # a layer off the kd-in-M path is refused, not mis-computed
+    assert b3d._lib.lib.b3d_conv3d_wgrad_p16_block_ok(256, 64, 32, 32) == 0
+
+
 def _dw_ref(x, dy, k, stride, tr):
     """fp64 weight gradient by autograd of the oracle's conv restatement."""
     from oracle import ref_model as R
