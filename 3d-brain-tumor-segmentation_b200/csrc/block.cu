@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(kBT)
     block_fwd16_kernel(const float* __restrict__ res, const float* __restrict__ h2, const double* __restrict__ stats,
                        const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ wsp,
                        const float* __restrict__ chse, float* __restrict__ out, BlockGeom gm, float eps, Twin16 tw) {
+  pdl_trigger();
   const int chunk = blockIdx.y + gm.chunk0, b = chunk / gm.G, g = chunk % gm.G;
   const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
   const int c = lane * 8;
@@ -446,6 +447,7 @@ __global__ void __launch_bounds__(kBT)
                              const float* __restrict__ dgap, const double* __restrict__ csum,
                              float* __restrict__ dres, float* __restrict__ dh2, BlockGeom gm, float eps, Twin16 tr,
                              Twin16 th, float* __restrict__ dbias_res, float* __restrict__ dbias_h2) {
+  pdl_trigger();
   extern __shared__ float sdb[];      // [2][F]
   if (HAS_DB) {
     for (int i = threadIdx.x; i < 2 * gm.F; i += kBT) sdb[i] = 0.f;

@@ -75,6 +75,12 @@ inline int cuda_ok(cudaError_t e, const char* what) {
 int sm_count();
 
 // ---- device helpers -------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// its CTAs (prologue: barrier init, TMEM allocation) while the previous kernel in the stream drains; pdl_wait() blocks
+// until that kernel has completed and its writes are visible.  pdl_trigger() in the previous kernel allows the start.
+// Both are no-ops in launches without the attribute / without a dependent.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -75,6 +75,7 @@ constexpr int kWgSmem = 227 * 1024;
 template <int KS, int TG>
 __global__ void __launch_bounds__(256, 1)
     conv3_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams prm) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   // barriers live at the very end of the allocation (the garbage MN groups never reach them: host planner)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgSmem - 128);
@@ -311,11 +312,7 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
   memset(&p, 0, sizeof(p));
   const int budget = kWgSmem - 128;
   bool found = false;
-  // timing experiments only: B3D_KDF_TILE = candidate index, B3D_KDF_NS = stage count
-  static const int force_tile = [] { const char* e = getenv("B3D_KDF_TILE"); return e ? atoi(e) : -1; }();
-  static const int force_ns = [] { const char* e = getenv("B3D_KDF_NS"); return e ? atoi(e) : 0; }();
   for (int i = 0; i < (int)(sizeof(cand) / sizeof(cand[0])); ++i) {
-    if (force_tile >= 0 && i != force_tile) continue;
     const int TD = cand[i][0], TH = cand[i][1], TW = cand[i][2];
     if (found && (TD > wg.Ds * 2 || TH > wg.Hs * 2 || TW > wg.Ws * 2)) continue;   // do not over-tile tiny volumes
     const int HD = TD + (allD ? KS - 1 : 0), HH = TH + (allH ? KS - 1 : 0), HW = TW + (allW ? KS - 1 : 0);
@@ -425,6 +422,7 @@ struct KdfParams {
 
 __global__ void __launch_bounds__(256, 1)
     conv3_wgrad_kdf_kernel(const __grid_constant__ WgMaps maps, const KdfParams prm) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgSmem - 128);
   uint64_t* full = bars;        // [4]

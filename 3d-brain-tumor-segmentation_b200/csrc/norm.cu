@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(kThreads)
     gn_apply16_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float* __restrict__ y, ChunkGeom gm, float eps, Twin16 tw,
                       long long shift, long long n_local, int chunk0) {
+  pdl_trigger();
   // depth-slab form (n_local >= 0; batch 1): x / y / the twin hold the flat elements [shift, shift + n_local) of the
   // volume whose chunks gm describes; a CTA covers the part of its chunk that lies inside (the grid starts at the
   // first chunk that intersects: chunk0)
@@ -453,6 +454,7 @@ __global__ void __launch_bounds__(kThreads)
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           const double* __restrict__ csum, float* __restrict__ dx, ChunkGeom gm, float eps, Twin16 tw,
                           float* __restrict__ dbias) {
+  pdl_trigger();
   extern __shared__ float sdb[];      // [C]
   if (dbias != nullptr) {
     for (int i = threadIdx.x; i < gm.C; i += kThreads) sdb[i] = 0.f;
