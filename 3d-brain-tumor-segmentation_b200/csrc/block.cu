@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(kBT)
                        const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ wsp,
                        const float* __restrict__ chse, float* __restrict__ out, BlockGeom gm, float eps, Twin16 tw) {
   pdl_trigger();
+  pdl_wait();
   const int chunk = blockIdx.y + gm.chunk0, b = chunk / gm.G, g = chunk % gm.G;
   const int T = gm.T, lane = threadIdx.x % T, vl = threadIdx.x / T, vstep = kBT / T;
   const int c = lane * 8;
@@ -448,6 +449,7 @@ __global__ void __launch_bounds__(kBT)
                              float* __restrict__ dres, float* __restrict__ dh2, BlockGeom gm, float eps, Twin16 tr,
                              Twin16 th, float* __restrict__ dbias_res, float* __restrict__ dbias_h2) {
   pdl_trigger();
+  pdl_wait();
   extern __shared__ float sdb[];      // [2][F]
   if (HAS_DB) {
     for (int i = threadIdx.x; i < 2 * gm.F; i += kBT) sdb[i] = 0.f;
@@ -551,6 +553,8 @@ __global__ void __launch_bounds__(kBT)
                              const float* __restrict__ wsp, float* __restrict__ dchse, float* __restrict__ dwsp,
                              float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ csum,
                              BlockGeom gm, float eps) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];  // [4][F]: dchse, dwsp, dgam(c), dbet(c)
   for (int i = threadIdx.x; i < 4 * gm.F; i += kBT) sm[i] = 0.f;
   __syncthreads();
@@ -930,8 +934,7 @@ extern "C" int b3d_block_epilogue_bwd_reduce(const DLTensor* dout_, const DLTens
         const long long need = ((gm.vpc + cap - 1) / cap + vstep - 1) / vstep * vstep;
         if (need > vp) vp = need;
         g8.vox_per_cta = (int)vp;
-        block_bwd_reduce8_kernel<<<block_grid(g8, nchunks), kBT, smem, s>>>(
-            (const float*)dout.p, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p,
+        launch_pdl(block_bwd_reduce8_kernel, block_grid(g8, nchunks), kBT, smem, s, (const float*)dout.p, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p,
             (const float*)be.p, (const float*)wsp.p, (float*)dch.p, (float*)dws.p, (float*)dga.p, (float*)dbe.p,
             (double*)cs.p, g8, eps);
         B3D_LAUNCH_CHECK("block_bwd_reduce8");
@@ -1061,12 +1064,10 @@ extern "C" int b3d_block_epilogue_fwd_p16(const DLTensor* res_, const DLTensor* 
     B3D_REQUIRE(st.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats: wrong size");
     B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
     B3D_TRY(vecF(beta_, gm.F, "beta", &be));
-    block_fwd16_kernel<true><<<block_grid(gm, nchunks), kBT, 0, s>>>(
-        (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+    launch_pdl(block_fwd16_kernel<true>, block_grid(gm, nchunks), kBT, 0, s, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
         (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps, tw);
   } else {
-    block_fwd16_kernel<false><<<block_grid(gm, nchunks), kBT, 0, s>>>(
-        (const float*)res.p, (const float*)h2.p, nullptr, nullptr, nullptr, (const float*)wsp.p, (const float*)ch.p,
+    launch_pdl(block_fwd16_kernel<false>, block_grid(gm, nchunks), kBT, 0, s, (const float*)res.p, (const float*)h2.p, nullptr, nullptr, nullptr, (const float*)wsp.p, (const float*)ch.p,
         (float*)out.p, gm, eps, tw);
   }
   B3D_LAUNCH_CHECK("block_fwd16");
@@ -1111,12 +1112,10 @@ extern "C" int b3d_block_epilogue_fwd_p16_slab(const DLTensor* res_, const DLTen
     B3D_REQUIRE(st.numel == 2LL * nchunks, B3D_ERR_SHAPE, "stats: wrong size");
     B3D_TRY(vecF(gamma_, gm.F, "gamma", &ga));
     B3D_TRY(vecF(beta_, gm.F, "beta", &be));
-    block_fwd16_kernel<true><<<block_grid(gm, nlaunch), kBT, 0, s>>>(
-        (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+    launch_pdl(block_fwd16_kernel<true>, block_grid(gm, nlaunch), kBT, 0, s, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
         (const float*)wsp.p, (const float*)ch.p, (float*)out.p, gm, eps, tw);
   } else {
-    block_fwd16_kernel<false><<<block_grid(gm, nlaunch), kBT, 0, s>>>(
-        (const float*)res.p, (const float*)h2.p, nullptr, nullptr, nullptr, (const float*)wsp.p, (const float*)ch.p,
+    launch_pdl(block_fwd16_kernel<false>, block_grid(gm, nlaunch), kBT, 0, s, (const float*)res.p, (const float*)h2.p, nullptr, nullptr, nullptr, (const float*)wsp.p, (const float*)ch.p,
         (float*)out.p, gm, eps, tw);
   }
   B3D_LAUNCH_CHECK("block_fwd16 (slab)");
@@ -1176,7 +1175,7 @@ extern "C" int b3d_block_epilogue_bwd_apply_p16(const DLTensor* dout_, const DLT
     B3D_TRY(cuda_ok(cudaMemsetAsync(dbh, 0, sizeof(float) * gm.F, s), "memset"));
   }
 #define B3D_BWD16(DB)                                                                                              \
-  block_bwd_apply16_kernel<DB><<<block_grid(gm, nchunks), kBT, DB ? sizeof(float) * 2 * gm.F : 0, s>>>(           \
+  launch_pdl(block_bwd_apply16_kernel<DB>, block_grid(gm, nchunks), kBT, DB ? sizeof(float) * 2 * gm.F : 0, s, \
       (const float*)dout.p, (const float*)res.p, (const float*)h2.p, (const double*)st.p, (const float*)ga.p,      \
       (const float*)be.p, (const float*)wsp.p, (const float*)ch.p, (const float*)dg.p, (const double*)cs.p,        \
       (float*)dres.p, (float*)dh2.p, gm, eps, tr, th, dbr, dbh)

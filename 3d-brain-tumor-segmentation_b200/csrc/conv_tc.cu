@@ -816,6 +816,7 @@ __global__ void __launch_bounds__(256)
                        const float* __restrict__ bias, double* __restrict__ stats, float* __restrict__ gap,
                        long long L, int C, int G, long long shift, long long n_local, int chunk0) {
   pdl_trigger();
+  pdl_wait();
   extern __shared__ float sgap[];                  // [C]
   __shared__ double red[64];
   const int chunk = blockIdx.x + chunk0;           // slab form: the grid starts at the first intersecting chunk
@@ -1217,8 +1218,7 @@ static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, con
     const long long span = slab && out_elems < L ? out_elems : L;  // longest part of a chunk a CTA row can hold
     const long long sh = slab ? g.stat_off * g.Cout : 0;
     const int c0 = slab ? (int)(sh / L) : 0, nc = slab ? (int)((sh + out_elems - 1) / L) - c0 + 1 : g.B * G;
-    conv_finish_kernel<<<dim3(nc, (unsigned)((span + 8191) / 8192)), 256, sizeof(float) * g.Cout, s>>>(
-        y, ws, p.ksplit, out_elems, bias, stats, gap, L, g.Cout, G, sh, slab ? out_elems : -1, c0);
+    launch_pdl(conv_finish_kernel, dim3(nc, (unsigned)((span + 8191) / 8192)), 256, sizeof(float) * g.Cout, s, y, ws, p.ksplit, out_elems, bias, stats, gap, L, g.Cout, G, sh, slab ? out_elems : -1, c0);
     B3D_LAUNCH_CHECK("conv_finish");
   }
   return B3D_OK;

@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(kThreads)
                       const float* __restrict__ beta, float* __restrict__ y, ChunkGeom gm, float eps, Twin16 tw,
                       long long shift, long long n_local, int chunk0) {
   pdl_trigger();
+  pdl_wait();
   // depth-slab form (n_local >= 0; batch 1): x / y / the twin hold the flat elements [shift, shift + n_local) of the
   // volume whose chunks gm describes; a CTA covers the part of its chunk that lies inside (the grid starts at the
   // first chunk that intersects: chunk0)
@@ -455,6 +456,7 @@ __global__ void __launch_bounds__(kThreads)
                           const double* __restrict__ csum, float* __restrict__ dx, ChunkGeom gm, float eps, Twin16 tw,
                           float* __restrict__ dbias) {
   pdl_trigger();
+  pdl_wait();
   extern __shared__ float sdb[];      // [C]
   if (dbias != nullptr) {
     for (int i = threadIdx.x; i < gm.C; i += kThreads) sdb[i] = 0.f;
@@ -538,6 +540,8 @@ __global__ void __launch_bounds__(kThreads)
     gn_bwd_reduce8_kernel(const float* __restrict__ dy, const float* __restrict__ x, const double* __restrict__ stats,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dgamma,
                           float* __restrict__ dbeta, double* __restrict__ csum, ChunkGeom gm, float eps) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];  // [2*cg]
   for (int i = threadIdx.x; i < 2 * gm.cg; i += kThreads) sm[i] = 0.f;
   __syncthreads();
@@ -832,12 +836,10 @@ extern "C" int b3d_gn_bwd_reduce(const DLTensor* dy_, const DLTensor* x_, const 
                      (gm.cg <= 8 || gm.cg % 8 == 0);
   if (cells) {
     if (relu)
-      gn_bwd_reduce8_kernel<true><<<gn_grid16(gm, nchunks), kThreads, smem, s>>>(
-          (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+      launch_pdl(gn_bwd_reduce8_kernel<true>, gn_grid16(gm, nchunks), kThreads, smem, s, (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
           (float*)dga.p, (float*)dbe.p, (double*)cs.p, gm, eps);
     else
-      gn_bwd_reduce8_kernel<false><<<gn_grid16(gm, nchunks), kThreads, smem, s>>>(
-          (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+      launch_pdl(gn_bwd_reduce8_kernel<false>, gn_grid16(gm, nchunks), kThreads, smem, s, (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
           (float*)dga.p, (float*)dbe.p, (double*)cs.p, gm, eps);
     B3D_LAUNCH_CHECK("gn_bwd_reduce8");
     return B3D_OK;
@@ -945,11 +947,9 @@ extern "C" int b3d_gn_apply_p16(const DLTensor* x_, const DLTensor* stats_, cons
   B3D_TRY(twin_view(y16_, y16b_, x, &tw));
   cudaStream_t s = (cudaStream_t)stream;
   if (relu)
-    gn_apply16_kernel<true><<<gn_grid16(gm, nchunks), kThreads, 0, s>>>(
-        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw, 0, -1, 0);
+    launch_pdl(gn_apply16_kernel<true>, gn_grid16(gm, nchunks), kThreads, 0, s, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw, 0, -1, 0);
   else
-    gn_apply16_kernel<false><<<gn_grid16(gm, nchunks), kThreads, 0, s>>>(
-        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw, 0, -1, 0);
+    launch_pdl(gn_apply16_kernel<false>, gn_grid16(gm, nchunks), kThreads, 0, s, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw, 0, -1, 0);
   B3D_LAUNCH_CHECK("gn_apply16");
   return B3D_OK;
 }
@@ -982,12 +982,10 @@ extern "C" int b3d_gn_apply_p16_slab(const DLTensor* x_, const DLTensor* stats_,
   if (x.numel < gl.L) gl.L = (x.numel + kCell - 1) / kCell * kCell;
   const dim3 grid = gn_grid16(gl, nc);
   if (relu)
-    gn_apply16_kernel<true><<<grid, kThreads, 0, s>>>(
-        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw,
+    launch_pdl(gn_apply16_kernel<true>, grid, kThreads, 0, s, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw,
         elem_offset, x.numel, c0);
   else
-    gn_apply16_kernel<false><<<grid, kThreads, 0, s>>>(
-        (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw,
+    launch_pdl(gn_apply16_kernel<false>, grid, kThreads, 0, s, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p, (float*)y.p, gm, eps, tw,
         elem_offset, x.numel, c0);
   B3D_LAUNCH_CHECK("gn_apply16 (slab)");
   return B3D_OK;
@@ -1028,12 +1026,10 @@ extern "C" int b3d_gn_bwd_apply_p16(const DLTensor* dy_, const DLTensor* x_, con
   }
   const size_t smem = db != nullptr ? sizeof(float) * gm.C : 0;
   if (relu)
-    gn_bwd_apply16_kernel<true><<<gn_grid16(gm, nchunks, db != nullptr ? 3 : 8), kThreads, smem, s>>>(
-        (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+    launch_pdl(gn_bwd_apply16_kernel<true>, gn_grid16(gm, nchunks, db != nullptr ? 3 : 8), kThreads, smem, s, (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
         (const double*)cs.p, (float*)dx.p, gm, eps, tw, db);
   else
-    gn_bwd_apply16_kernel<false><<<gn_grid16(gm, nchunks, db != nullptr ? 3 : 8), kThreads, smem, s>>>(
-        (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
+    launch_pdl(gn_bwd_apply16_kernel<false>, gn_grid16(gm, nchunks, db != nullptr ? 3 : 8), kThreads, smem, s, (const float*)dy.p, (const float*)x.p, (const double*)st.p, (const float*)ga.p, (const float*)be.p,
         (const double*)cs.p, (float*)dx.p, gm, eps, tw, db);
   B3D_LAUNCH_CHECK("gn_bwd_apply16");
   return B3D_OK;
