@@ -47,6 +47,10 @@ for sp, cs, cout, k, stride, tr in CASES:
         scratch = torch.empty(dy16.numel(), device=dev, dtype=torch.bfloat16)
     dw = torch.empty_like(w)
     ops._call("b3d_conv3d_wgrad_p16", *(twb + [None] * (4 - len(twb))), dy16, dw, stride, int(tr), scratch)
+    if k == 3 and stride == 1 and not tr and b3d._lib.lib.b3d_conv3d_wgrad_p16_block_ok(cin, cout, od[1], od[2]):
+        dres16 = ops.to_p16(rnd(1, *od, cout), torch.bfloat16)        # kd-in-M kernel with the pointwise layer's dw
+        dwp = torch.empty(1, 1, 1, cin, cout, device=dev)
+        ops._call("b3d_conv3d_wgrad_p16_block", *(twb + [None] * (4 - len(twb))), dy16, dres16, dw, dwp)
     torch.cuda.synchronize()
     print("ok", sp, cs, cout, k, stride, tr, "wgrad plan", plan, flush=True)
 
