@@ -1120,6 +1120,34 @@ int make_p16_map(CUtensorMap* tm, const void* base, int bf16, int B, int D, int 
   return B3D_OK;
 }
 
+// the same tensor with the dimensions in another ORDER, so that one box lands in shared memory as [o3][o2][o1][w]:
+// order = 0: (4W, H, C/8, D, B) -> a box {4bw, bh, planes, bd} is [d][plane][h][w] (x tile of the kd-in-M weight gradient);
+// order = 1: (4W, H, D, C/8, B) -> a box {4bw, bh, bd, planes} is [plane][d][h][w] (its dy tile, all planes at once)
+int make_p16_map_perm(CUtensorMap* tm, const void* base, int order, int B, int D, int H, int W, int C8, int bw, int planes,
+                      int bh, int bd) {
+  EncodeTiledFn enc = tma_encode_fn();
+  B3D_REQUIRE(enc != nullptr, B3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  B3D_REQUIRE(4 * bw <= 256 && planes <= 256 && bh <= 256 && bd <= 256, B3D_ERR_UNSUPPORTED, "P16 map: box too large");
+  const cuuint64_t row = (cuuint64_t)W * 16;
+  const cuuint64_t sp = row, sh = row * C8, sd = row * C8 * H, sb = row * C8 * H * D;
+  cuuint64_t dims[5] = {(cuuint64_t)W * 4, (cuuint64_t)H, 0, 0, (cuuint64_t)B};
+  cuuint64_t strides[4] = {sh, 0, 0, sb};
+  cuuint32_t box[5] = {(cuuint32_t)(4 * bw), (cuuint32_t)bh, 0, 0, 1};
+  if (order == 0) {
+    dims[2] = (cuuint64_t)C8; dims[3] = (cuuint64_t)D; strides[1] = sp; strides[2] = sd;
+    box[2] = (cuuint32_t)planes; box[3] = (cuuint32_t)bd;
+  } else {
+    dims[2] = (cuuint64_t)D; dims[3] = (cuuint64_t)C8; strides[1] = sd; strides[2] = sp;
+    box[2] = (cuuint32_t)bd; box[3] = (cuuint32_t)planes;
+  }
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, (void*)base,
+                         dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B3D_REQUIRE(r == CUDA_SUCCESS, B3D_ERR_CUDA, "cuTensorMapEncodeTiled(P16, permuted) failed (%d)", (int)r);
+  return B3D_OK;
+}
+
 template <class C>
 static int launch_cfg(const ConvGeom& g, const TcProblem& q, const float* x, const float* wp, const float* bias,
                       float* y, double* stats, float* gap, cudaStream_t s, const TcSources* srcs) {

@@ -390,9 +390,10 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
 // ================================================================================ kd folded into M, kw folded into N
 // For Cin = 32 / 64 the kernel above computes M = 64 / 128 rows per MMA of which Cin are real, 27 MMAs per K step.  Here
 // the three depth taps share the M dimension and the three width taps the N dimension of ONE MMA:
-//   * the x tile (32 or 16 channels, halo in d and h only) is laid out [d][plane][h][w], one TMA box per (plane, depth
-//     slice), so the M groups (kd, plane) of the A operand lie at ONE stride (a plane slice): 96 of 128 rows (Cin = 32)
-//     or 48 of 64 (Cin = 16) are real;
+//   * the x tile (32 or 16 channels, halo in d and h only) is laid out [d][plane][h][w] — ONE TMA box of a tensor map
+//     whose dimensions are ordered (w, h, plane, d) when a single source covers the tile's planes, else one box per
+//     depth slice and source piece — so the M groups (kd, plane) of the A operand lie at ONE stride (a plane slice):
+//     96 of 128 rows (Cin = 32) or 48 of 64 (Cin = 16) are real;
 //   * the dy tile is loaded three times, shifted by 1 - kw voxels along w (TMA zero fill at the volume edge), so the N
 //     groups (kw, plane) of the B operand lie at one stride as well and
 //         D_kh[(kd, ci)][(kw, co)] += sum_u x[u + (kd-1, kh-1, 0)][ci] * dy[u - (0, 0, kw-1)][co]
@@ -412,9 +413,9 @@ struct KdfParams {
   int xbytes, stage_bytes, nstages;
   int ntd, nth, ntw, ntiles, nsplit;
   int nsrc, cend8[4];
-  int pf;                          // L2 prefetch distance in tile rounds (0: off)
-  int dbg;                         // timing experiments only (B3D_KDF_DBG): 1 no MMAs, 2 one dy copy, 4 one x slice,
-                                   // 8 no final reduction
+  int g, xbd;                      // an x box holds g planes x xbd depth slices (xbd = HD when one source covers the
+                                   // tile's planes: the whole halo is ONE box; else one box per (depth slice, g planes))
+  int dbg;                         // timing experiments only (B3D_KDF_DBG): 1 no MMAs, 8 no final reduction
   int P;                           // channel planes (octets) of the tile: 4 (Cin = 32, M = 128) or 2 (Cin = 16, M = 64)
   int ntg;                         // 1: a CTA holds all 9 (kh, kw) accumulators; 3: blockIdx.z = kh (small volumes: the
                                    // final fp32 atomics per CTA are 27 * 32 * Cout otherwise — 3x the per-tap kernel's)
@@ -453,11 +454,12 @@ __global__ void __launch_bounds__(256, 1)
 
   if (warp == 0) {
     // producer warp: lane 0 waits for the slot and arms the barrier, then the lanes issue the tile's boxes in parallel
-    // (HD * P halo slices of x + 3 * yplanes planes of dy: 20-40 small boxes, too many for one thread per tile)
     int s = 0, ph = 0;
-    const int nxb = (prm.dbg & 4) ? 1 : prm.HD * P, nyb = ((prm.dbg & 2) ? 1 : 3) * yplanes;
-    const int nbox = nxb + nyb + (prm.dw2 != nullptr ? yplanes : 0);
-    const uint32_t bytes = (uint32_t)(nxb * prm.HH * prm.HW * 16 + (nbox - nxb) * prm.py);
+    // boxes of a tile (tensor maps with permuted dimensions: a box is a whole [d][plane][h][w] / [plane][d][h][w] block):
+    // x: (HD / xbd) x (P / g); dy: one per copy, all planes; dres: one
+    const int pg = P / prm.g, nxb = (prm.HD / prm.xbd) * pg, nyb = 3;
+    const int nbox = nxb + nyb + (prm.dw2 != nullptr ? 1 : 0);
+    const uint32_t bytes = (uint32_t)(prm.HD * P * prm.HH * prm.HW * 16 + (nbox - nxb) * yplanes * prm.py);
     for (int tile = blockIdx.x; tile < prm.ntiles; tile += prm.nsplit) {
       int t = tile;
       const int wt = t % prm.ntw; t /= prm.ntw;
@@ -475,40 +477,18 @@ __global__ void __launch_bounds__(256, 1)
       const uint32_t ydst = xdst + (uint32_t)prm.xbytes;
       for (int j = lane; j < nbox; j += 32) {
         if (j < nxb) {
-          const int d = j / P, p = j - d * P;
+          const int d = j / pg, p = (j - d * pg) * prm.g;
           const int gp = (cbase >> 3) + p;
           int si = 0;
           while (si + 1 < prm.nsrc && gp >= prm.cend8[si]) ++si;
           const int lp = gp - (si > 0 ? prm.cend8[si - 1] : 0);
-          tma_load_5d(xdst + (uint32_t)(j * prm.pslice), &maps.x[si], 4 * w0, lp, h0 - 1 + kh0, d0 - 1 + d, b, fb);
+          tma_load_5d(xdst + (uint32_t)((d * P + p) * prm.pslice), &maps.x[si], 4 * w0, h0 - 1 + kh0, lp, d0 - 1 + d, b, fb);
         } else {
           // dy three times, shifted by 1 - kw voxels along w (zero fill outside the volume): copy kw at in-tile voxel u
           // holds dy[u - (kw - 1)], the partner of x[u + (kd - 1, kh - 1, 0)]
-          const int jj = j - nxb, kw = jj / yplanes, q = jj - kw * yplanes;
-          if (jj < nyb) tma_load_5d(ydst + jj * prm.py, &maps.y, 4 * (w0 + 1 - kw), q, h0, d0, b, fb);
-          else tma_load_5d(ydst + (3 * yplanes + q) * prm.py, &maps.y2, 4 * w0, q, h0, d0, b, fb);
-        }
-      }
-      // L2 prefetch of the tile `pf` rounds ahead: a TMA load that misses L2 holds its request slots for the DRAM
-      // latency, and the per-SM fill rate follows (outstanding requests / latency)
-      const int ptile = tile + prm.pf * prm.nsplit;
-      if (prm.pf > 0 && ptile < prm.ntiles) {
-        int u = ptile;
-        const int pwt = u % prm.ntw; u /= prm.ntw;
-        const int pht = u % prm.nth; u /= prm.nth;
-        const int pdt = u % prm.ntd; u /= prm.ntd;
-        const int pw0 = pwt * prm.TW, ph0 = pht * prm.TH, pd0 = pdt * prm.TD;
-        for (int j = lane; j < nxb + yplanes; j += 32) {
-          if (j < nxb) {
-            const int d = j / P, p = j - d * P;
-            const int gp = (cbase >> 3) + p;
-            int si = 0;
-            while (si + 1 < prm.nsrc && gp >= prm.cend8[si]) ++si;
-            const int lp = gp - (si > 0 ? prm.cend8[si - 1] : 0);
-            tma_prefetch_5d(&maps.x[si], 4 * pw0, lp, ph0 - 1 + kh0, pd0 - 1 + d, u);
-          } else {
-            tma_prefetch_5d(&maps.y, 4 * pw0, j - nxb, ph0, pd0, u);
-          }
+          const int jj = j - nxb;
+          if (jj >= nyb) tma_load_5d(ydst + 3 * yplanes * prm.py, &maps.y2, 4 * w0, h0, d0, 0, b, fb);
+          else tma_load_5d(ydst + jj * yplanes * prm.py, &maps.y, 4 * (w0 + 1 - jj), h0, d0, 0, b, fb);
         }
       }
       __syncwarp();
@@ -668,7 +648,6 @@ int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const 
   B3D_REQUIRE((dw2 == nullptr) == (dres == nullptr) && (dw2 == nullptr || (ntg == 1 && ((uintptr_t)dw2 & 15) == 0)),
               B3D_ERR_ARG, "wgrad (kd in M): pointwise operands");
   { const char* e = getenv("B3D_KDF_DBG"); p.dbg = e ? atoi(e) : 0; }
-  { static const int pf = [] { const char* e = getenv("B3D_KDF_PF"); return e ? atoi(e) : 0; }(); p.pf = pf; }
   p.ntd = (wg.Ds + p.TD - 1) / p.TD; p.nth = (wg.Hs + p.TH - 1) / p.TH; p.ntw = (wg.Ws + p.TW - 1) / p.TW;
   p.ntiles = wg.B * p.ntd * p.nth * p.ntw;
   int nsplit = sm_count() / (nmt * ntg);
@@ -678,18 +657,28 @@ int launch_conv_wgrad_kdf(const WgradGeom& wg, float* dw, cudaStream_t s, const 
   WgMaps maps;
   memset(&maps, 0, sizeof(maps));
   p.nsrc = p16.n;
+  {
+    int g = P;                               // planes per x box: the gcd of the tile and every source's plane count
+    for (int i = 0; i < p16.n; ++i) {
+      int a = g, b = p16.C[i] / 8;
+      while (b) { const int t = a % b; a = b; b = t; }
+      g = a;
+    }
+    static const int big = [] { const char* e = getenv("B3D_KDF_BIGBOX"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+    if (!big) g = 1;
+    p.g = g; p.xbd = (g == P && big) ? p.HD : 1;
+  }
   int cum = 0;
   for (int i = 0; i < p16.n; ++i) {
     cum += p16.C[i] / 8;
     p.cend8[i] = cum;
-    // one box = one (plane, depth slice) of the halo: {HW voxels, 1 plane, HH rows, 1 slice}
-    B3D_TRY(make_p16_map(&maps.x[i], p16.big[i], 1, wg.B, wg.Db, wg.Hb, wg.Wb, p16.C[i] / 8, p.HW, 1, p.HH, 1));
+    B3D_TRY(make_p16_map_perm(&maps.x[i], p16.big[i], 0, wg.B, wg.Db, wg.Hb, wg.Wb, p16.C[i] / 8, p.HW, p.g, p.HH, p.xbd));
   }
   B3D_REQUIRE(cum * 8 == Cin, B3D_ERR_SHAPE, "wgrad (kd in M): sources hold %d channels, expected %d", cum * 8, Cin);
-  B3D_TRY(make_p16_map(&maps.y, p16.small, 1, wg.B, wg.Ds, wg.Hs, wg.Ws, Cout / 8, p.TW, 1, p.TH, p.TD));
+  B3D_TRY(make_p16_map_perm(&maps.y, p16.small, 1, wg.B, wg.Ds, wg.Hs, wg.Ws, Cout / 8, p.TW, Cout / 8, p.TH, p.TD));
   B3D_TRY(cuda_ok(cudaMemsetAsync(dw, 0, sizeof(float) * 27 * (size_t)Cin * Cout, s), "memset dw"));
   if (dw2 != nullptr) {
-    B3D_TRY(make_p16_map(&maps.y2, dres, 1, wg.B, wg.Ds, wg.Hs, wg.Ws, Cout / 8, p.TW, 1, p.TH, p.TD));
+    B3D_TRY(make_p16_map_perm(&maps.y2, dres, 1, wg.B, wg.Ds, wg.Hs, wg.Ws, Cout / 8, p.TW, Cout / 8, p.TH, p.TD));
     B3D_TRY(cuda_ok(cudaMemsetAsync(dw2, 0, sizeof(float) * (size_t)Cin * Cout, s), "memset dw (pointwise)"));
   }
   static bool attr = false;

@@ -112,5 +112,8 @@ EncodeTiledFn tma_encode_fn();
 // tensor map of a P16 operand [B, D, H, C/8, W, 8] (common.cuh) for boxes {8*bw, planes, bh, bd, 1} (conv_tc.cu)
 int make_p16_map(CUtensorMap* tm, const void* base, int bf16, int B, int D, int H, int W, int C8, int bw, int planes,
                  int bh, int bd);
+// dimensions re-ordered so that ONE box is a whole operand tile: order 0 -> [d][plane][h][w], 1 -> [plane][d][h][w]
+int make_p16_map_perm(CUtensorMap* tm, const void* base, int order, int B, int D, int H, int W, int C8, int bw, int planes,
+                      int bh, int bd);
 
 }  // namespace b3d
