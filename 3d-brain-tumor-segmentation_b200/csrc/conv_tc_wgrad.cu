@@ -438,8 +438,9 @@ __global__ void __launch_bounds__(256, 1)
   const int nkh = nt / 3;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < prm.nstages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
-    mbar_init(smem_u32(done), 1);
+    // one MMA-issuing warp per kh tap (a warp can issue a tcgen05.mma only every ~50 cycles: profiles/r01_umma_rate.txt)
+    for (int i = 0; i < prm.nstages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), nkh); }
+    mbar_init(smem_u32(done), nkh);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -494,7 +495,9 @@ __global__ void __launch_bounds__(256, 1)
       __syncwarp();
       if (++s == prm.nstages) { s = 0; ph ^= 1; }
     }
-  } else if (warp == 1) {
+  } else if (warp >= 1 && warp <= nkh) {
+    // warps 1..3: the MMAs of kh tap (warp - 1), each into its own accumulator block
+    const int t = warp - 1;
     const bool leader = elect_one();
     // D = f32, A = B = bf16, both MN-major, N = 3 Cout (columns (kw, co)), M = 128 / 64 (rows (kd, ci): 96 / 48 real)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
@@ -521,14 +524,9 @@ __global__ void __launch_bounds__(256, 1)
             const uint32_t ycell = (uint32_t)((d * prm.TH + h) * prm.TW + w8);
             const uint32_t xcell = (uint32_t)(d * P * slicec + h * prm.HW + w8);
             if (leader && !(prm.dbg & 1)) {
-#pragma unroll
-              for (int t = 0; t < 3; ++t) {
-                if (t >= nkh) break;
-                tc_mma_bf16(tmem_base + t * 3 * prm.Cout, adesc0 + xcell + (uint32_t)(t * prm.HW), bdesc0 + ycell, idesc,
-                            acc);
-              }
+              tc_mma_bf16(tmem_base + t * 3 * prm.Cout, adesc0 + xcell + (uint32_t)(t * prm.HW), bdesc0 + ycell, idesc, acc);
               // pointwise conv: rows kd = 1 of the centre (kh = 1) A operand are x[u] itself
-              if (prm.dw2 != nullptr)
+              if (prm.dw2 != nullptr && t == 1)
                 tc_mma_bf16(tmem_base + 9 * prm.Cout, adesc0 + xcell + (uint32_t)prm.HW, bdesc2 + ycell, idesc2, acc);
             }
             acc = 1;
