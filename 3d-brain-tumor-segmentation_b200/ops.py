@@ -685,15 +685,17 @@ class Conv3dFn(Function):
                     kind = lib.b3d_conv3d_wgrad_plan(k, stride, int(transposed), cin, cout, _byref(xc), _byref(yc))
                     if kind:
                         # the two convs of a ResnetBlock (pointwise + first 3x3x3) read the same input: its plain bf16
-                        # copy is made by whichever weight gradient runs first and handed to the other
-                        key = (x.data_ptr(), tuple(x.shape)) if (kind == 1 and stride == 1 and ctx.share_x) else None
-                        xb = _XB_CACHE.pop(key, None) if key is not None else None
-                        if xb is not None:
+                        # copy is made by whichever weight gradient runs first and handed to the other through the
+                        # block's grad_box (one dict per ResnetBlock.call: nothing outlives the forward it belongs to)
+                        holder = ctx.grad_box if (kind == 1 and stride == 1 and ctx.share_x) else None
+                        need = x.numel() // x.shape[-1] * xc.value
+                        xb = holder.pop("xb", None) if holder is not None else None
+                        if xb is not None and xb.numel() == need and holder.pop("xb_ptr", None) == x.data_ptr():
                             ready = 1
                         else:
-                            xb = torch.empty(x.numel() // x.shape[-1] * xc.value, device=x.device, dtype=torch.bfloat16)
-                            if key is not None:
-                                _XB_CACHE[key] = xb
+                            xb = torch.empty(need, device=x.device, dtype=torch.bfloat16)
+                            if holder is not None:
+                                holder["xb"], holder["xb_ptr"] = xb, x.data_ptr()
                         yb = torch.empty(dy.numel() // dy.shape[-1] * yc.value, device=x.device, dtype=torch.bfloat16)
                 _tag_conv(w, ctx.nv, stride, transposed)
                 _call("b3d_conv3d_wgrad", x, dy, dw, None if bias_done else db, stride, int(transposed), xb, yb, ready)
@@ -750,11 +752,6 @@ class FoldDupFn(Function):
 
 def fold_dup(w, F):
     return FoldDupFn.apply(w, F)
-
-
-# bf16 copies of conv inputs shared between two weight gradients of one backward pass (fp32 entry points only;
-# cleared every step)
-_XB_CACHE = {}
 
 
 def conv3d(x, w, bias=None, stride=1, transposed=False, act=0, gn_groups=0, want_gap=False, share_x=False,

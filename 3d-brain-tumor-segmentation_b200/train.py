@@ -42,13 +42,11 @@ class GradientTape:
         else:
             for v in variables:
                 v.grad = None
-        ops._XB_CACHE.clear()
         if direct and flat is not None:
             with ops.direct_param_grads(flat):
                 loss.backward()
         else:
             loss.backward()
-        ops._XB_CACHE.clear()
         return [v.grad for v in variables]
 
 
