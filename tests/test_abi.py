@@ -34,6 +34,22 @@ def test_python_signatures_cover_header(b3d):
     assert declared == set(b3d._lib.SIGNATURES), declared ^ set(b3d._lib.SIGNATURES)
 
 
+def test_host_side_planning_queries(b3d):
+    """Pure host logic behind the C-ABI (no device needed): which layers the fused block weight gradient and the P16
+    weight-gradient plans accept."""
+    lib = b3d._lib.lib
+    ok = lib.b3d_conv3d_wgrad_p16_block_ok
+    # kd-in-M kernel: stride-1 3x3x3, Cin = 16 or a multiple of 32 up to 128, Cout 16 | 32, W % 8 == 0, H even
+    assert ok(16, 16, 128, 128) == 1 and ok(32, 16, 128, 128) == 1 and ok(96, 32, 64, 64) == 1
+    assert ok(256, 64, 32, 32) == 0          # Cout = 64: 9 accumulators do not fit the tensor memory
+    assert ok(48, 16, 64, 64) == 0           # channel tiles of 32
+    assert ok(32, 16, 64, 12) == 0 and ok(32, 16, 7, 16) == 0
+    plan = lib.b3d_conv3d_wgrad_p16_plan
+    assert plan(3, 2, 0, 32, 64, 32) == 2    # stride-2 family: space-to-depth scratch
+    assert plan(3, 1, 0, 2, 16, 128) == 0    # narrow input: not on the P16 path
+    assert plan(3, 1, 0, 64, 64, 32) == 1
+
+
 def test_cpu_tensors_are_rejected(b3d):
     x = torch.zeros(1, 4, 4, 4, 8)
     st = torch.zeros(1, 8, 2, dtype=torch.float64)
