@@ -400,8 +400,10 @@ int launch_conv_wgrad_tc(const WgradGeom& wg, const void* x, const void* dy, flo
 //     is the weight gradient with the voxel sum re-indexed (u = v + (0, 0, kw-1));
 //   * no operand is read at a w offset: every 128-byte core matrix the tensor core fetches from shared memory is
 //     aligned (the form with kw as an MMA loop measured ~63 cycles per M = 128, N = 16 MMA, twice its operand bytes).
-// 3 MMAs (N = 3 Cout) per K step instead of 27, all accumulators (9 Cout <= 288 columns) in one CTA; voxel ranges are
-// spread over the CTAs (and the kh taps over blockIdx.z for small volumes).
+// 3 MMAs (N = 3 Cout) per K step instead of 27, one per kh tap, each issued by its own warp into its own accumulator
+// block (a warp issues a tcgen05.mma only every ~50 cycles); all accumulators (9 Cout <= 288 columns, + Cout for the
+// pointwise layer) in one CTA; 32-channel tiles (blockIdx.y) and voxel ranges (blockIdx.x) are spread over the CTAs.
+// Warps: 0 TMA producer, 1..3 MMA issuers (2 also owns the TMEM allocation), 4..7 final reduction.
 struct KdfParams {
   float* dw;
   float* dw2;                      // != nullptr: also dw of the pointwise conv reading the same x, [Cin][Cout]: one more
@@ -417,8 +419,8 @@ struct KdfParams {
                                    // tile's planes: the whole halo is ONE box; else one box per (depth slice, g planes))
   int dbg;                         // timing experiments only (B3D_KDF_DBG): 1 no MMAs, 8 no final reduction
   int P;                           // channel planes (octets) of the tile: 4 (Cin = 32, M = 128) or 2 (Cin = 16, M = 64)
-  int ntg;                         // 1: a CTA holds all 9 (kh, kw) accumulators; 3: blockIdx.z = kh (small volumes: the
-                                   // final fp32 atomics per CTA are 27 * 32 * Cout otherwise — 3x the per-tap kernel's)
+  int ntg;                         // 1: a CTA holds all 9 (kh, kw) accumulators (always, since the final reduction is
+                                   // vectorised); 3: blockIdx.z = kh — measured slower, experiments only (B3D_KDF_NTG)
 };
 
 __global__ void __launch_bounds__(256, 1)
